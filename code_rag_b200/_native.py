@@ -1,0 +1,111 @@
+"""ctypes binding of the C ABI in ``include/lvs.h`` (liblattice_b200.so).  Fails loudly: no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+from .errors import NativeLibraryError
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblattice_b200.so"
+
+OK, EINVAL, ECUDA, ENOMEM, ESTATE, ELIMIT = 0, -1, -2, -3, -4, -5
+STORAGE_F32, STORAGE_BF16 = 0, 1
+METRIC_COSINE, METRIC_DOT = 0, 1
+DT_F32, DT_F64, DT_BF16 = 0, 1, 2
+MAX_FILTER_COLS = 8
+ANY = 0xFFFFFFFF
+NULL_CODE = 0
+NO_MATCH = 0xFFFFFFFE
+MAX_K = 224
+FLAG_UNPROVEN = 1
+
+_vp = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_f32p = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); mirrors include/lvs.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES: dict[str, tuple] = {
+    "lvs_version": (C.c_int, []),
+    "lvs_last_error": (C.c_char_p, []),
+    "lvs_init": (C.c_int, [C.c_int]),
+    "lvs_shutdown": (C.c_int, []),
+    "lvs_device_info": (C.c_int, [_ip, _ip, _ip, _i64p, _i64p]),
+    "lvs_collection_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(_vp)]),
+    "lvs_collection_destroy": (C.c_int, [_vp]),
+    "lvs_collection_reserve": (C.c_int, [_vp, C.c_int64]),
+    "lvs_rows": (C.c_int64, [_vp]),
+    "lvs_count": (C.c_int64, [_vp]),
+    "lvs_capacity": (C.c_int64, [_vp]),
+    "lvs_search_counter": (C.c_uint32, [_vp]),
+    "lvs_upsert": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, _vp, _vp, _vp]),
+    "lvs_upsert_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "lvs_set_codes": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, _vp]),
+    "lvs_delete_rows": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
+    "lvs_delete_where": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
+    "lvs_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_search_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
+    "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),
+    "lvs_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "lvs_fetch_rows_f32": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+}
+
+_lib: C.CDLL | None = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and type every entry point.  Raises NativeLibraryError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("LVS_LIBRARY", LIB_PATH))
+    if not path.exists():
+        raise NativeLibraryError(
+            f"{path} not found. Build it with `python -m code_rag_b200.build` (nvcc, sm_100a). "
+            "lattice-b200 has no CPU fallback."
+        )
+    try:
+        lib = C.CDLL(str(path))
+    except OSError as e:  # pragma: no cover
+        raise NativeLibraryError(f"cannot load {path}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError(f"{path} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().lvs_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise NativeLibraryError(f"{what} failed (code {rc}): {last_error()}")
+
+
+_initialised_device: int | None = None
+
+
+def init(device: int = 0) -> None:
+    """Bind this process to one GPU (idempotent for the same device)."""
+    global _initialised_device
+    if _initialised_device == device:
+        return
+    check(load().lvs_init(int(device)), "lvs_init")
+    _initialised_device = device
+
+
+def is_initialised() -> bool:
+    return _initialised_device is not None

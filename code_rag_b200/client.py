@@ -1,0 +1,474 @@
+"""``B200VectorStore``: drop-in for lattice's ``QdrantManager`` backed by a GPU-resident collection.
+
+Mirrors, method for method, ``lattice.embeddings.client.QdrantManager`` (reference
+``src/lattice/embeddings/client.py:18-228``; protocol ``VectorStore``, ``src/lattice/core/protocols.py:34-52``):
+same names, keyword arguments, result dictionaries and error behaviour, so it can be injected wherever the
+reference passes a ``QdrantManager`` (``QueryEngine(qdrant=...)`` ``query/engine.py:37``,
+``VectorSearcher(qdrant, embedder)`` ``query/vector_search.py:46-58``, ``VectorIndexer(qdrant, ...)``
+``embeddings/indexer.py:36-44``, ``ContextBuilder(memgraph, qdrant)`` ``query/context/builder.py:24-30``).
+
+Division of labour: ids (uuid strings), payload dicts and the value dictionaries of the keyword columns live in
+host RAM, keyed by row; vectors, tombstones and the dictionary codes live in HBM.  All arithmetic (normalisation,
+scoring, selection, filter evaluation) runs in liblattice_b200.so.
+"""
+from __future__ import annotations
+
+import asyncio
+import logging
+import os
+import threading
+import uuid
+from enum import Enum
+from types import SimpleNamespace
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .collection import DeviceCollection
+from .errors import VectorStoreError
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_DIMENSIONS = 1536  # reference config/settings.py:53 (AISettings.embedding_dimensions)
+
+
+class CollectionName(str, Enum):
+    """reference embeddings/client.py:13-15."""
+    CODE_CHUNKS = "code_chunks"
+    SUMMARIES = "summaries"
+
+
+# keyword payload indexes the reference creates (client.py:76-89)
+_INDEX_FIELDS = {
+    CollectionName.CODE_CHUNKS.value: ["file_path", "entity_type", "language", "content_hash", "project_name"],
+    CollectionName.SUMMARIES.value: ["file_path", "entity_type"],
+}
+
+
+def _canonical_id(point_id: Any) -> Any:
+    """Qdrant point ids are unsigned ints or UUID strings (local mode validates the same way)."""
+    if isinstance(point_id, bool):
+        raise ValueError(f"invalid point id {point_id!r}")
+    if isinstance(point_id, int):
+        if point_id < 0:
+            raise ValueError(f"invalid point id {point_id!r}")
+        return point_id
+    if isinstance(point_id, uuid.UUID):
+        return str(point_id)
+    if isinstance(point_id, str):
+        return str(uuid.UUID(point_id))
+    raise ValueError(f"invalid point id {point_id!r}")
+
+
+def _tie_key(point_id: Any) -> int:
+    """64-bit key whose order follows the id order (ints numerically; uuids by their leading 64 bits)."""
+    if isinstance(point_id, int):
+        return min(point_id, 0xFFFFFFFFFFFFFFFF)
+    return uuid.UUID(point_id).int >> 64
+
+
+def _id_sort_key(point_id: Any):
+    return (0, point_id, "") if isinstance(point_id, int) else (1, 0, point_id)
+
+
+class _HostCollection:
+    """Host half of a collection: ids, payloads and the per-column value dictionaries."""
+
+    def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int):
+        self.name = name
+        self.dim = dim
+        self.columns: list[str] = list(index_fields)[: N.MAX_FILTER_COLS]
+        self.dicts: list[dict[Any, int]] = [dict() for _ in self.columns]
+        self.ids: list[Any] = []                 # row -> id
+        self.id_to_row: dict[Any, int] = {}
+        self.payloads: list[dict[str, Any] | None] = []
+        self.lock = threading.Lock()
+        self.dev = DeviceCollection(name, dim, storage=storage, metric="cosine", n_filter_cols=N.MAX_FILTER_COLS,
+                                    capacity=0, device=device)
+
+    # -- dictionary encoding ---------------------------------------------------------------------------
+    def _encode_value(self, col: int, value: Any, create: bool) -> int:
+        if value is None:
+            return N.NULL_CODE
+        if isinstance(value, (list, tuple, dict, set)):
+            raise ValueError(f"payload key {self.columns[col]!r}: list/dict values are not supported in keyword columns")
+        d = self.dicts[col]
+        code = d.get(value)
+        if code is None:
+            if not create:
+                return N.NO_MATCH
+            code = len(d) + 1
+            d[value] = code
+        return code
+
+    def encode_payloads(self, payloads: Sequence[dict[str, Any] | None]) -> np.ndarray:
+        codes = np.zeros((len(payloads), N.MAX_FILTER_COLS), dtype=np.uint32)
+        for i, p in enumerate(payloads):
+            if not p:
+                continue
+            for c, key in enumerate(self.columns):
+                if key in p:
+                    codes[i, c] = self._encode_value(c, p[key], create=True)
+        return codes
+
+    def ensure_column(self, key: str) -> int:
+        """Index a payload key on first use in a filter (Qdrant filters on any key, indexed or not)."""
+        if key in self.columns:
+            return self.columns.index(key)
+        if len(self.columns) >= N.MAX_FILTER_COLS:
+            raise ValueError(f"cannot filter on {key!r}: all {N.MAX_FILTER_COLS} keyword columns are in use ({self.columns})")
+        col = len(self.columns)
+        self.columns.append(key)
+        self.dicts.append(dict())
+        n = len(self.payloads)
+        if n:
+            codes = np.zeros(n, dtype=np.uint32)
+            for r, p in enumerate(self.payloads):
+                if p and key in p:
+                    codes[r] = self._encode_value(col, p[key], create=True)
+            self.dev.set_codes(col, codes, row0=0)
+        return col
+
+    def want_codes(self, filters: dict[str, Any] | None) -> np.ndarray | None:
+        if not filters:
+            return None
+        want = np.full(N.MAX_FILTER_COLS, N.ANY, dtype=np.uint32)
+        for key, value in filters.items():
+            if value is None or isinstance(value, (float, list, tuple, dict, set)):
+                # models.MatchValue only accepts bool | int | str (pydantic validation error in the reference)
+                raise ValueError(f"filter value for {key!r} must be a bool, int or str, got {type(value).__name__}")
+            col = self.ensure_column(key)
+            code = self._encode_value(col, value, create=False)
+            if want[col] != N.ANY and want[col] != code:
+                code = N.NO_MATCH
+            want[col] = code
+        return want
+
+    # -- operations (called under self.lock) ---------------------------------------------------------------
+    def upsert(self, ids, vectors, payloads) -> None:
+        n = len(ids)
+        if not (len(vectors) == n and len(payloads) == n):
+            n = min(n, len(vectors), len(payloads))  # the reference zips the three lists (client.py:123-126)
+        if n == 0:
+            return
+        canon = [_canonical_id(i) for i in ids[:n]]
+        vec = np.asarray(vectors[:n], dtype=np.float64)
+        if vec.ndim != 2 or vec.shape[1] != self.dim:
+            raise ValueError(f"vectors must have dimension {self.dim}, got shape {vec.shape}")
+        if not np.isfinite(vec).all():
+            raise ValueError("vectors must be finite")
+        # a repeated id inside one batch: the last occurrence wins, as with sequential point upserts
+        last = {pid: i for i, pid in enumerate(canon)}
+        keep = sorted(last.values())
+        rows = np.empty(len(keep), dtype=np.int64)
+        next_row = len(self.ids)
+        new_ids = []
+        for j, i in enumerate(keep):
+            pid = canon[i]
+            r = self.id_to_row.get(pid)
+            if r is None:
+                r = next_row
+                next_row += 1
+                new_ids.append(pid)
+            rows[j] = r
+        pl = [dict(payloads[i]) if payloads[i] is not None else None for i in keep]
+        codes = self.encode_payloads(pl)
+        ties = np.array([_tie_key(canon[i]) for i in keep], dtype=np.uint64)
+        self.dev.upsert(vec[keep], rows=rows, codes=codes, ties=ties)
+        for pid in new_ids:
+            self.id_to_row[pid] = len(self.ids)
+            self.ids.append(pid)
+            self.payloads.append(None)
+        for j, r in enumerate(rows):
+            self.payloads[int(r)] = pl[j]
+
+    def _hits(self, rows: np.ndarray, scores: np.ndarray) -> list[dict[str, Any]]:
+        out = []
+        for r, s in zip(rows.tolist(), scores.tolist()):
+            if r < 0:
+                continue
+            p = self.payloads[r]
+            out.append({"id": str(self.ids[r]), "score": float(s), "payload": dict(p) if p is not None else None})
+        return out
+
+    def search(self, query_vectors: np.ndarray | None, limit: int, filters: dict[str, Any] | None) -> list[list[dict[str, Any]]]:
+        want = self.want_codes(filters)
+        if limit <= 0:
+            return [[] for _ in range(1 if query_vectors is None else len(query_vectors))]
+        if query_vectors is None:
+            # query=None degenerates to a scroll: matching points in ascending id order, score 0.0
+            rows, _ = self.dev.match_rows(want)
+            order = sorted(rows.tolist(), key=lambda r: _id_sort_key(self.ids[r]))[:limit]
+            return [self._hits(np.asarray(order, dtype=np.int64), np.zeros(len(order)))]
+        if limit > N.MAX_K:
+            raise ValueError(f"limit {limit} exceeds the largest supported top-k ({N.MAX_K})")
+        res = self.dev.search(query_vectors, limit, want)
+        out = []
+        for qi in range(res.rows.shape[0]):
+            n = int(res.counts[qi])
+            if res.flags[qi] & N.FLAG_UNPROVEN:
+                logger.warning("search on %s: exactness bound not met for query %d (many near-ties); "
+                               "result is the best of the largest candidate set", self.name, qi)
+            out.append(self._hits(res.rows[qi, :n], res.scores[qi, :n]))
+        return out
+
+    def delete(self, filters: dict[str, Any]) -> int:
+        want = self.want_codes(filters)
+        _, n = self.dev.delete_where(want, cap=0)
+        return n
+
+    def scroll(self, filters: dict[str, Any] | None, limit: int) -> list[dict[str, Any]]:
+        return self.search(None, limit, filters)[0]
+
+    def count(self, filters: dict[str, Any] | None = None) -> int:
+        if not filters:
+            return self.dev.count()
+        _, n = self.dev.match_rows(self.want_codes(filters), cap=0)
+        return n
+
+    def close(self) -> None:
+        self.dev.close()
+
+
+class _ClientShim:
+    """What ``manager.client`` exposes (reference callers reach through it: projects/cleanup.py:41-61,
+    tests/test_database.py:81).  Filters are duck-typed ``models.Filter`` objects (``.must[i].key``,
+    ``.match.value`` / ``.match.text``)."""
+
+    def __init__(self, store: "B200VectorStore"):
+        self._store = store
+
+    async def get_collections(self):
+        return SimpleNamespace(collections=[SimpleNamespace(name=n) for n in self._store._collections])
+
+    async def get_collection(self, collection_name: str):
+        return await self._store.get_collection_info(collection_name)
+
+    def _split_filter(self, flt) -> tuple[dict[str, Any], list[tuple[str, str]]]:
+        eq: dict[str, Any] = {}
+        text: list[tuple[str, str]] = []
+        for cond in (getattr(flt, "must", None) or []):
+            m = cond.match
+            if hasattr(m, "value"):
+                eq[cond.key] = m.value
+            elif hasattr(m, "text"):
+                text.append((cond.key, m.text))
+            else:
+                raise ValueError(f"unsupported match {type(m).__name__}")
+        return eq, text
+
+    def _rows_matching(self, coll: _HostCollection, flt) -> list[int]:
+        eq, text = self._split_filter(flt) if flt is not None else ({}, [])
+        rows, _ = coll.dev.match_rows(coll.want_codes(eq))
+        out = []
+        for r in rows.tolist():
+            p = coll.payloads[r] or {}
+            # MatchText in local mode is a substring test on the string payload value
+            if all(isinstance(p.get(k), str) and t in p[k] for k, t in text):
+                out.append(r)
+        return out
+
+    async def count(self, collection_name: str, count_filter=None, exact: bool = True):
+        coll = self._store._get(collection_name)
+
+        def work():
+            with coll.lock:
+                return len(self._rows_matching(coll, count_filter))
+        return SimpleNamespace(count=await asyncio.to_thread(work))
+
+    async def delete(self, collection_name: str, points_selector=None):
+        coll = self._store._get(collection_name)
+        flt = getattr(points_selector, "filter", points_selector)
+
+        def work():
+            with coll.lock:
+                rows = self._rows_matching(coll, flt)
+                if rows:
+                    coll.dev.delete_rows(np.asarray(rows, dtype=np.int64))
+                return len(rows)
+        await asyncio.to_thread(work)
+        return SimpleNamespace(status="completed")
+
+    async def close(self):
+        return None
+
+
+class B200VectorStore:
+    """Same constructor keywords as ``QdrantManager`` (ignored: there is no server), plus backend knobs."""
+
+    def __init__(self, host: str | None = None, port: int | None = None, grpc_port: int | None = None, *,
+                 dimensions: int | None = None, storage: str | None = None, device: int | None = None):
+        self._host, self._port, self._grpc_port = host, port, grpc_port
+        if dimensions is None:
+            dimensions = int(os.environ.get("EMBEDDING_DIMENSIONS", DEFAULT_DIMENSIONS))
+            try:  # honour lattice's own settings object when it is importable
+                from lattice.config import get_settings  # type: ignore
+                dimensions = int(get_settings().embedding_dimensions)
+            except Exception:  # noqa: BLE001
+                pass
+        self._dimensions = int(dimensions)
+        self._storage = storage or os.environ.get("LATTICE_B200_STORAGE", "f32")
+        self._device = int(device if device is not None else os.environ.get("LOCAL_RANK", "0"))
+        self._connected = False
+        self._collections: dict[str, _HostCollection] = {}
+        self._shim = _ClientShim(self)
+
+    # ---- connection (client.py:32-70) -------------------------------------------------------------------
+    async def connect(self) -> None:
+        if not self._connected:
+            try:
+                await asyncio.to_thread(N.init, self._device)
+                self._connected = True
+                logger.info("lattice-b200 vector store bound to cuda:%d", self._device)
+            except Exception as e:  # noqa: BLE001
+                raise VectorStoreError("Failed to connect to Qdrant", cause=e)
+
+    async def close(self) -> None:
+        if self._connected:
+            try:
+                for coll in self._collections.values():
+                    coll.close()
+            except Exception as e:  # noqa: BLE001
+                logger.warning(f"Error closing vector store: {e}")
+            finally:
+                self._collections.clear()
+                self._connected = False
+
+    @property
+    def client(self) -> _ClientShim:
+        if not self._connected:
+            raise VectorStoreError("Client not connected. Call connect() first.")
+        return self._shim
+
+    async def health_check(self) -> bool:
+        try:
+            await self.client.get_collections()
+            return True
+        except Exception as e:  # noqa: BLE001
+            logger.warning(f"Vector store health check failed: {e}")
+            return False
+
+    # ---- collections (client.py:72-113, 204-221) ---------------------------------------------------------
+    def _get(self, name: str) -> _HostCollection:
+        if not self._connected:
+            raise VectorStoreError("Client not connected. Call connect() first.")
+        coll = self._collections.get(name)
+        if coll is None:
+            raise ValueError(f"Collection {name} not found")
+        return coll
+
+    async def create_collections(self) -> None:
+        try:
+            _ = self.client
+            for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
+                if name not in self._collections:
+                    self._collections[name] = await asyncio.to_thread(
+                        _HostCollection, name, self._dimensions, self._storage, _INDEX_FIELDS[name], self._device)
+                    logger.info(f"Created collection: {name}")
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError("Failed to create collections", cause=e)
+
+    async def get_collection_info(self, collection: str):
+        try:
+            coll = self._get(collection)
+
+            def work():
+                with coll.lock:
+                    n = coll.count()
+                return SimpleNamespace(points_count=n, vectors_count=n, indexed_vectors_count=n, status="green",
+                                       config=SimpleNamespace(params=SimpleNamespace(
+                                           vectors=SimpleNamespace(size=coll.dim, distance="Cosine"))))
+            return await asyncio.to_thread(work)
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to get collection info for {collection}", cause=e)
+
+    async def clear_collections(self) -> None:
+        for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
+            coll = self._collections.pop(name, None)
+            if coll is not None:
+                coll.close()
+                logger.info(f"Deleted collection: {name}")
+        await self.create_collections()
+
+    # ---- data path (client.py:115-202) -------------------------------------------------------------------
+    async def upsert(self, collection: str, ids: list[str], vectors: list[list[float]], payloads: list[dict[str, Any]]) -> None:
+        try:
+            coll = self._get(collection)
+
+            def work():
+                with coll.lock:
+                    coll.upsert(ids, vectors, payloads)
+            await asyncio.to_thread(work)
+            logger.debug(f"Upserted {len(ids)} vectors to {collection}")
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to upsert vectors to {collection}", cause=e)
+
+    async def search(self, collection: str, query_vector: list[float] | None, limit: int = 10,
+                     filters: dict[str, Any] | None = None) -> list[dict[str, Any]]:
+        try:
+            coll = self._get(collection)
+            q = None if query_vector is None else np.asarray(query_vector, dtype=np.float64)[None, :]
+
+            def work():
+                with coll.lock:
+                    return coll.search(q, limit, filters or None)[0]
+            results = await asyncio.to_thread(work)
+            logger.debug(f"Found {len(results)} results in {collection}")
+            return results
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to search {collection}", cause=e)
+
+    async def search_batch(self, collection: str, query_vectors: Sequence[Sequence[float]], limit: int = 10,
+                           filters: dict[str, Any] | None = None) -> list[list[dict[str, Any]]]:
+        """Additive API: Q searches in one device pass (equivalent to Q consecutive ``search`` calls)."""
+        try:
+            coll = self._get(collection)
+            q = np.asarray(query_vectors, dtype=np.float64)
+            if q.ndim != 2:
+                raise ValueError("query_vectors must be a list of vectors")
+
+            def work():
+                with coll.lock:
+                    return coll.search(q, limit, filters or None)
+            return await asyncio.to_thread(work)
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to search {collection}", cause=e)
+
+    async def delete(self, collection: str, filters: dict[str, Any]) -> None:
+        try:
+            coll = self._get(collection)
+
+            def work():
+                with coll.lock:
+                    return coll.delete(filters)
+            await asyncio.to_thread(work)
+            logger.debug(f"Deleted vectors from {collection} with filters: {filters}")
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to delete from {collection}", cause=e)
+
+    async def file_needs_update(self, collection: str, file_path: str, content_hash: str) -> bool:
+        try:
+            coll = self._get(collection)
+
+            def work():
+                with coll.lock:
+                    return coll.scroll({"file_path": file_path}, 1)
+            points = await asyncio.to_thread(work)
+            if not points:
+                return True
+            return (points[0]["payload"] or {}).get("content_hash") != content_hash
+        except Exception as e:  # noqa: BLE001
+            logger.warning(f"Error checking file update status: {e}")
+            return True
+
+    async def __aenter__(self):
+        await self.connect()
+        return self
+
+    async def __aexit__(self, exc_type, exc_val, exc_tb):
+        await self.close()
+
+
+# The name reference code imports (``from lattice.embeddings.client import QdrantManager``): alias for injection.
+QdrantManager = B200VectorStore

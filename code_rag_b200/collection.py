@@ -1,0 +1,222 @@
+"""``DeviceCollection``: one row-major shard of a collection resident in B200 HBM (numpy-facing, synchronous).
+
+Thin object wrapper over the C ABI (``include/lvs.h``).  It is what the reference would call "the Qdrant
+collection": vectors, tombstones and dictionary-encoded keyword columns live on the GPU; ids and payload dicts
+stay with the caller (``client.py``).  Everything numeric happens in liblattice_b200.so - there is no numpy
+arithmetic on this path and no fallback when the library or the GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+from .errors import NativeLibraryError
+
+_STORAGE = {"f32": N.STORAGE_F32, "fp32": N.STORAGE_F32, "float32": N.STORAGE_F32,
+            "bf16": N.STORAGE_BF16, "bfloat16": N.STORAGE_BF16}
+_METRIC = {"cosine": N.METRIC_COSINE, "dot": N.METRIC_DOT}
+
+
+@dataclass
+class SearchResult:
+    scores: np.ndarray   # float64 [Q, k]
+    rows: np.ndarray     # int64   [Q, k]  global rows, -1 padded
+    ties: np.ndarray     # uint64  [Q, k]
+    counts: np.ndarray   # uint32  [Q]
+    flags: np.ndarray    # int32   [Q]     bit0 = exactness not proven
+
+
+def _np_dtype_code(a: np.ndarray) -> int:
+    if a.dtype == np.float32:
+        return N.DT_F32
+    if a.dtype == np.float64:
+        return N.DT_F64
+    raise TypeError(f"vectors must be float32 or float64, got {a.dtype}")
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceCollection:
+    def __init__(self, name: str, dim: int, storage: str = "f32", metric: str = "cosine", n_filter_cols: int = 0,
+                 capacity: int = 0, row_base: int = 0, device: int = 0):
+        if storage not in _STORAGE:
+            raise ValueError(f"storage must be one of {sorted(_STORAGE)}")
+        if metric not in _METRIC:
+            raise ValueError(f"metric must be one of {sorted(_METRIC)}")
+        N.init(device)
+        self._lib = N.load()
+        self.name = name
+        self.dim = int(dim)
+        self.storage = "bf16" if _STORAGE[storage] == N.STORAGE_BF16 else "f32"
+        self.metric = metric
+        self.n_filter_cols = int(n_filter_cols)
+        self.row_base = int(row_base)
+        h = C.c_void_p()
+        N.check(self._lib.lvs_collection_create(name.encode(), self.dim, _STORAGE[storage], _METRIC[metric],
+                                                self.n_filter_cols, int(capacity), self.row_base, C.byref(h)),
+                "lvs_collection_create")
+        self._h = h
+
+    # ---- lifecycle ------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.lvs_collection_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise NativeLibraryError(f"collection {self.name!r} is closed")
+        return self._h
+
+    # ---- introspection --------------------------------------------------------------------------------
+    @property
+    def rows(self) -> int:
+        return int(self._lib.lvs_rows(self._handle()))
+
+    @property
+    def capacity(self) -> int:
+        return int(self._lib.lvs_capacity(self._handle()))
+
+    @property
+    def search_counter(self) -> int:
+        return int(self._lib.lvs_search_counter(self._handle()))
+
+    def count(self) -> int:
+        n = int(self._lib.lvs_count(self._handle()))
+        if n < 0:
+            raise NativeLibraryError(f"lvs_count failed: {N.last_error()}")
+        return n
+
+    def reserve(self, capacity: int) -> None:
+        N.check(self._lib.lvs_collection_reserve(self._handle(), int(capacity)), "lvs_collection_reserve")
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(self._lib.lvs_set_option(self._handle(), name.encode(), int(value)), "lvs_set_option")
+
+    def last_timing(self) -> dict:
+        ms = (C.c_float * 4)()
+        nl, kind = C.c_int(), C.c_int()
+        N.check(self._lib.lvs_last_search_timing(self._handle(), ms, C.byref(nl), C.byref(kind)), "lvs_last_search_timing")
+        return {"prep_ms": ms[0], "scan_ms": ms[1], "finalize_ms": ms[2], "total_ms": ms[3],
+                "launches": nl.value, "kernel": {0: "none", 1: "scan", 2: "gemm"}.get(kind.value, "?")}
+
+    # ---- writes ---------------------------------------------------------------------------------------
+    def upsert(self, vectors: np.ndarray, rows: np.ndarray | None = None, codes: np.ndarray | None = None,
+               ties: np.ndarray | None = None) -> None:
+        v = np.ascontiguousarray(vectors)
+        if v.ndim != 2 or v.shape[1] != self.dim:
+            raise ValueError(f"vectors must be [n, {self.dim}], got {v.shape}")
+        n = v.shape[0]
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        c = None if codes is None or self.n_filter_cols == 0 else np.ascontiguousarray(codes, dtype=np.uint32)
+        t = None if ties is None else np.ascontiguousarray(ties, dtype=np.uint64)
+        if r is not None and r.shape != (n,):
+            raise ValueError("rows must be [n]")
+        if c is not None and c.shape != (n, self.n_filter_cols):
+            raise ValueError(f"codes must be [n, {self.n_filter_cols}]")
+        if t is not None and t.shape != (n,):
+            raise ValueError("ties must be [n]")
+        N.check(self._lib.lvs_upsert(self._handle(), _ptr(v), _np_dtype_code(v), n, _ptr(r), _ptr(c), _ptr(t)), "lvs_upsert")
+
+    def upsert_device(self, data_ptr: int, dtype: str, n: int, row0: int, codes_ptr: int = 0, ties_ptr: int = 0,
+                      stream: int = 0) -> None:
+        """Vectors already on this GPU (e.g. a torch tensor's ``data_ptr()``): ``n`` rows of ``dim`` elements."""
+        code = {"f32": N.DT_F32, "f64": N.DT_F64, "bf16": N.DT_BF16}[dtype]
+        N.check(self._lib.lvs_upsert_device(self._handle(), C.c_void_p(data_ptr), code, int(n), int(row0),
+                                            C.c_void_p(codes_ptr or None), C.c_void_p(ties_ptr or None),
+                                            C.c_void_p(stream or None)), "lvs_upsert_device")
+
+    def set_codes(self, col: int, codes: np.ndarray, rows: np.ndarray | None = None, row0: int = 0) -> None:
+        c = np.ascontiguousarray(codes, dtype=np.uint32)
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        N.check(self._lib.lvs_set_codes(self._handle(), int(col), _ptr(r), int(row0), c.shape[0], _ptr(c)), "lvs_set_codes")
+
+    def delete_rows(self, rows: np.ndarray) -> int:
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        nd = C.c_int64()
+        N.check(self._lib.lvs_delete_rows(self._handle(), _ptr(r), r.shape[0], C.byref(nd)), "lvs_delete_rows")
+        return nd.value
+
+    def _want(self, want) -> np.ndarray | None:
+        if want is None or self.n_filter_cols == 0:
+            return None
+        w = np.ascontiguousarray(want, dtype=np.uint32)
+        if w.shape != (self.n_filter_cols,):
+            raise ValueError(f"want must have {self.n_filter_cols} codes")
+        return w
+
+    def delete_where(self, want, cap: int | None = None) -> tuple[np.ndarray, int]:
+        return self._match(want, cap, self._lib.lvs_delete_where, "lvs_delete_where")
+
+    def match_rows(self, want, cap: int | None = None) -> tuple[np.ndarray, int]:
+        return self._match(want, cap, self._lib.lvs_match_rows, "lvs_match_rows")
+
+    def _match(self, want, cap, fn, what):
+        w = self._want(want)
+        cap = self.rows if cap is None else int(cap)
+        out = np.empty(max(cap, 1), dtype=np.int64)
+        nm = C.c_int64()
+        N.check(fn(self._handle(), _ptr(w), _ptr(out), cap, C.byref(nm)), what)
+        return out[:min(cap, nm.value)].copy(), int(nm.value)
+
+    # ---- search ---------------------------------------------------------------------------------------
+    def search(self, queries: np.ndarray, k: int, want=None) -> SearchResult:
+        q = np.ascontiguousarray(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
+        if q.dtype not in (np.float32, np.float64):
+            q = q.astype(np.float64)
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")   # local mode asserts the same
+        Q = q.shape[0]
+        k = int(k)
+        scores = np.zeros((Q, k), dtype=np.float64)
+        rows = np.full((Q, k), -1, dtype=np.int64)
+        ties = np.zeros((Q, k), dtype=np.uint64)
+        counts = np.zeros(Q, dtype=np.uint32)
+        flags = np.zeros(Q, dtype=np.int32)
+        w = self._want(want)
+        N.check(self._lib.lvs_search(self._handle(), _ptr(q), _np_dtype_code(q), Q, k, _ptr(w), _ptr(scores), _ptr(rows),
+                                     _ptr(ties), _ptr(counts), _ptr(flags)), "lvs_search")
+        return SearchResult(scores, rows, ties, counts, flags)
+
+    def search_device(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, scores_ptr: int, rows_ptr: int, ties_ptr: int,
+                      counts_ptr: int, stream: int = 0) -> np.ndarray:
+        """Device-pointer form (sharded path): outputs stay on the GPU; returns the host flags."""
+        flags = np.zeros(Q, dtype=np.int32)
+        w = self._want(want)
+        code = {"f32": N.DT_F32, "f64": N.DT_F64}[q_dtype]
+        N.check(self._lib.lvs_search_device(self._handle(), C.c_void_p(q_ptr), code, int(Q), int(k), _ptr(w),
+                                            C.c_void_p(scores_ptr), C.c_void_p(rows_ptr), C.c_void_p(ties_ptr),
+                                            C.c_void_p(counts_ptr), _ptr(flags), C.c_void_p(stream or None)),
+                "lvs_search_device")
+        return flags
+
+    def fetch_rows(self, rows: np.ndarray) -> np.ndarray:
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((r.shape[0], self.dim), dtype=np.float32)
+        N.check(self._lib.lvs_fetch_rows_f32(self._handle(), _ptr(r), r.shape[0], _ptr(out)), "lvs_fetch_rows_f32")
+        return out
+
+
+def merge_topk_device(scores_ptr: int, rows_ptr: int, ties_ptr: int, G: int, Q: int, k: int, out_scores_ptr: int,
+                      out_rows_ptr: int, out_ties_ptr: int, out_counts_ptr: int, stream: int = 0,
+                      shard_stride: int = 0) -> None:
+    """K5: merge G gathered per-shard lists ([G, Q, k] device buffers) into the global top-k on this GPU."""
+    lib = N.load()
+    N.check(lib.lvs_merge_topk_device(C.c_void_p(scores_ptr), C.c_void_p(rows_ptr), C.c_void_p(ties_ptr), int(shard_stride), int(G), int(Q), int(k),
+                                      C.c_void_p(out_scores_ptr), C.c_void_p(out_rows_ptr), C.c_void_p(out_ties_ptr),
+                                      C.c_void_p(out_counts_ptr), C.c_void_p(stream or None)), "lvs_merge_topk_device")

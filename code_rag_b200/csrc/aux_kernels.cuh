@@ -1,0 +1,226 @@
+// K4 (upsert: normalise / convert / scatter), query preparation, filter-only row matching, tombstones and
+// K5 (merge of per-shard top-k lists after the all-gather).
+#pragma once
+#include "common.cuh"
+#include "finalize_kernel.cuh"
+
+namespace lvs {
+
+
+__device__ __forceinline__ double load_as_f64(const void* src, int dtype, size_t i) {
+    if (dtype == LVS_DT_F64) return reinterpret_cast<const double*>(src)[i];
+    if (dtype == LVS_DT_F32) return (double)reinterpret_cast<const float*>(src)[i];
+    return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4 upsert.  Replaces the point marshalling + server-side insert behind QdrantManager.upsert
+// (reference src/lattice/embeddings/client.py:115-130).  One warp per point:
+//   fp32 storage, cosine : row = float32(x / ||x||_f64)      (what qdrant local mode stores)
+//   fp32 storage, dot    : row = float32(x)
+//   bf16 storage         : row = bf16(x) (exact when x is bf16-representable) and inv_norm = 1/||row||
+// plus tie key, epoch (search counter at write time), tombstone clear and filter codes; padding is zeroed.
+// ---------------------------------------------------------------------------------------------------------
+struct UpsertParams {
+    const void* src;            // [n][dim] device
+    int src_dtype;
+    int64_t n;
+    const int64_t* rows;        // [n] local destination rows, or nullptr => row0 + i
+    int64_t row0;
+    uint8_t* base;
+    uint32_t row_bytes;
+    int dim;
+    int storage;
+    int metric;
+    float* inv_norm;
+    uint8_t* live;
+    uint32_t* epoch;
+    uint32_t epoch_val;
+    uint64_t* tiekey;
+    const uint64_t* ties_src;   // [n] or nullptr => tie key = global row
+    int64_t row_base;
+    uint32_t* codes[kMaxFilterCols];
+    const uint32_t* codes_src;  // [n][n_cols] row-major, or nullptr => kNullCode
+    int n_cols;
+    float* max_norm;            // running max ||row|| (dot metric error bound)
+};
+
+__global__ void __launch_bounds__(256) upsert_kernel(const UpsertParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int D = p.dim;
+    for (int64_t i = wid; i < p.n; i += nw) {
+        const int64_t row = p.rows ? p.rows[i] : p.row0 + i;
+        const size_t so = (size_t)i * D;
+        double ss = 0.0;
+        for (int c = lane; c < D; c += 32) { const double x = load_as_f64(p.src, p.src_dtype, so + c); ss = fma(x, x, ss); }
+        ss = warp_sum_f64(ss);
+        const double nrm = sqrt(ss);
+        uint8_t* rp = p.base + (size_t)row * p.row_bytes;
+        if (p.storage == LVS_STORAGE_F32) {
+            float* out = reinterpret_cast<float*>(rp);
+            const int ld = p.row_bytes / 4;
+            const bool norm = (p.metric == LVS_METRIC_COSINE) && nrm > 0.0;
+            for (int c = lane; c < ld; c += 32) {
+                float v = 0.f;
+                if (c < D) { const double x = load_as_f64(p.src, p.src_dtype, so + c); v = (float)(norm ? x / nrm : x); }
+                out[c] = v;
+            }
+            if (lane == 0) p.inv_norm[row] = 1.0f;
+            if (lane == 0 && p.metric == LVS_METRIC_DOT) atomicMax(reinterpret_cast<int*>(p.max_norm), __float_as_int((float)nrm * 1.0000002f));
+        } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(rp);
+            const int ld = p.row_bytes / 2;
+            double ss2 = 0.0;
+            for (int c = lane; c < ld; c += 32) {
+                __nv_bfloat16 b = __float2bfloat16(0.f);
+                if (c < D) { b = __double2bfloat16(load_as_f64(p.src, p.src_dtype, so + c)); const double t = (double)__bfloat162float(b); ss2 = fma(t, t, ss2); }
+                out[c] = b;
+            }
+            ss2 = warp_sum_f64(ss2);
+            if (lane == 0) {
+                const double n2 = sqrt(ss2);
+                p.inv_norm[row] = n2 > 0.0 ? (float)(1.0 / n2) : 0.f;
+                if (p.metric == LVS_METRIC_DOT) atomicMax(reinterpret_cast<int*>(p.max_norm), __float_as_int((float)n2 * 1.0000002f));
+            }
+        }
+        if (lane == 0) {
+            p.live[row] = 1;
+            p.epoch[row] = p.epoch_val;
+            p.tiekey[row] = p.ties_src ? p.ties_src[i] : (uint64_t)(p.row_base + row);
+        }
+        if (lane < p.n_cols) p.codes[lane][row] = p.codes_src ? p.codes_src[(size_t)i * p.n_cols + lane] : kNullCode;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Query preparation: q64 = q / ||q||_f64 (cosine; local mode divides by EPSILON when the norm is 0) or q (dot);
+// q32 = float32(q64) laid out with the scan's row stride; qb16 is filled by the tensor-core path.
+// One CTA per query.
+// ---------------------------------------------------------------------------------------------------------
+struct PrepParams {
+    const void* src; int src_dtype; int dim; int metric;
+    double* q64;          // [Q][dim]
+    float* q32;           // [Q][q_stride]
+    uint32_t q_stride;
+    float* qnorm;         // [Q] ||q|| (dot metric error bound)
+};
+
+__global__ void __launch_bounds__(256) prep_queries_kernel(const PrepParams p) {
+    __shared__ double red[8];
+    __shared__ double s_norm;
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t so = (size_t)qi * p.dim;
+    double ss = 0.0;
+    for (int c = tid; c < p.dim; c += 256) { const double x = load_as_f64(p.src, p.src_dtype, so + c); ss = fma(x, x, ss); }
+    ss = warp_sum_f64(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int w = 0; w < 8; ++w) t += red[w]; s_norm = sqrt(t); }
+    __syncthreads();
+    const double nrm = s_norm;
+    const double div = (p.metric == LVS_METRIC_COSINE) ? (nrm != 0.0 ? nrm : 1.1920929e-7) : 1.0;
+    for (uint32_t c = tid; c < p.q_stride; c += 256) {
+        double v = 0.0;
+        if ((int)c < p.dim) { v = load_as_f64(p.src, p.src_dtype, so + c) / div; p.q64[so + c] = v; }
+        p.q32[(size_t)qi * p.q_stride + c] = (float)v;
+    }
+    if (tid == 0) p.qnorm[qi] = (float)nrm;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Filter-only matching (query_vector=None searches, delete-by-filter, count, scroll):
+// appends every live row whose codes satisfy the conjunction to out_rows (unordered), counts all matches.
+// ---------------------------------------------------------------------------------------------------------
+struct MatchParams {
+    uint32_t n_rows;
+    const uint8_t* live;
+    const uint32_t* codes[kMaxFilterCols];
+    uint32_t want[kMaxFilterCols];
+    uint32_t n_filter;
+    int64_t row_base;
+    int64_t* out_rows; uint32_t cap;
+    uint32_t* counter;       // [0] = matches
+    int tombstone;           // 1 => also clear the live byte of every match (delete by filter)
+    uint8_t* live_rw;
+};
+
+__global__ void __launch_bounds__(256) match_rows_kernel(const MatchParams p) {
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < p.n_rows; row += gridDim.x * blockDim.x) {
+        bool pass = p.live[row] != 0;
+        for (uint32_t f = 0; f < p.n_filter && pass; ++f) pass = p.codes[f][row] == p.want[f];
+        if (pass) {
+            const uint32_t pos = atomicAdd(p.counter, 1u);
+            if (pos < p.cap) p.out_rows[pos] = p.row_base + (int64_t)row;
+            if (p.tombstone) p.live_rw[row] = 0;
+        }
+    }
+}
+
+__global__ void set_live_kernel(uint8_t* live, const int64_t* rows, int64_t n, uint8_t value, uint32_t n_rows, uint32_t* changed) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = rows[i];
+        if (r >= 0 && r < (int64_t)n_rows) {
+            if (live[r] != value) { live[r] = value; atomicAdd(changed, 1u); }
+        }
+    }
+}
+
+__global__ void set_codes_kernel(uint32_t* col, const int64_t* rows, int64_t row0, const uint32_t* src, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = rows ? rows[i] : row0 + i;
+        col[r] = src[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: merge of G per-shard result lists (after the NCCL all-gather) into the global top-k.
+// in_*: G blocks of [Q][k], `shard_stride` elements apart; rows < 0 are padding.  Order: (score desc, tie asc, row asc).  One CTA per query.
+// ---------------------------------------------------------------------------------------------------------
+struct MergeParams {
+    const double* in_scores; const int64_t* in_rows; const uint64_t* in_ties;
+    int G; int Q; int k;
+    int64_t shard_stride;   // elements between consecutive shards' [Q][k] blocks (Q*k when dense)
+    double* out_scores; int64_t* out_rows; uint64_t* out_ties; uint32_t* out_counts;
+};
+
+__global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) uint8_t msm[];
+    const int n = p.G * p.k;
+    double* s = reinterpret_cast<double*>(msm);
+    int64_t* r = reinterpret_cast<int64_t*>(msm + (size_t)n * 8);
+    uint64_t* t = reinterpret_cast<uint64_t*>(msm + (size_t)n * 16);
+    __shared__ uint32_t nvalid;
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) nvalid = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int g = i / p.k, j = i % p.k;
+        const size_t src = (size_t)g * p.shard_stride + (size_t)qi * p.k + j;
+        s[i] = p.in_scores[src]; r[i] = p.in_rows[src]; t[i] = p.in_ties[src];
+        if (r[i] >= 0) atomicAdd(&nvalid, 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        if (r[i] < 0) continue;
+        uint32_t rank = 0;
+        for (int o = 0; o < n; ++o) {
+            if (r[o] < 0) continue;
+            const bool better = (s[o] > s[i]) || (s[o] == s[i] && (t[o] < t[i] || (t[o] == t[i] && r[o] < r[i])));
+            rank += better ? 1u : 0u;
+        }
+        if (rank < (uint32_t)p.k) {
+            p.out_scores[(size_t)qi * p.k + rank] = s[i];
+            p.out_rows[(size_t)qi * p.k + rank] = r[i];
+            p.out_ties[(size_t)qi * p.k + rank] = t[i];
+        }
+    }
+    const uint32_t nout = min(nvalid, (uint32_t)p.k);
+    for (int j = nout + tid; j < p.k; j += blockDim.x) {
+        p.out_scores[(size_t)qi * p.k + j] = 0.0; p.out_rows[(size_t)qi * p.k + j] = -1; p.out_ties[(size_t)qi * p.k + j] = 0ull;
+    }
+    if (tid == 0) p.out_counts[qi] = nout;
+}
+
+}  // namespace lvs

@@ -1,0 +1,846 @@
+// C ABI of liblattice_b200.so (see include/lvs.h for the contract and the reference call each entry replaces).
+#include "../../include/lvs.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "finalize_kernel.cuh"
+#include "scan_kernel.cuh"
+
+using namespace lvs;
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? LVS_ENOMEM : LVS_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// library state
+// ------------------------------------------------------------------------------------------------------
+struct LibState {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+};
+static LibState g_lib;
+static std::mutex g_lib_mu;
+
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+static int ensure_dev(Scratch& s, size_t bytes) {
+    if (s.bytes >= bytes) return LVS_OK;
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr; s.bytes = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CU(cudaMalloc(&s.p, want));
+    s.bytes = want;
+    return LVS_OK;
+}
+static int ensure_pinned(Scratch& s, size_t bytes) {
+    if (s.bytes >= bytes) return LVS_OK;
+    if (s.p) cudaFreeHost(s.p);
+    s.p = nullptr; s.bytes = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CU(cudaMallocHost(&s.p, want));
+    s.bytes = want;
+    return LVS_OK;
+}
+
+struct lvs_collection {
+    std::string name;
+    int dim = 0;
+    int storage = 0;
+    int metric = 0;
+    int n_cols = 0;
+    uint32_t row_bytes = 0;
+    uint32_t chunks_per_row = 0;
+    uint32_t q_stride = 0;       // floats per fp32 query row (padded like a storage row)
+    int64_t capacity = 0;
+    int64_t n_rows = 0;
+    int64_t row_base = 0;
+    uint32_t search_counter = 0;
+
+    uint8_t* d_vec = nullptr;
+    uint8_t* d_live = nullptr;
+    uint32_t* d_epoch = nullptr;
+    uint64_t* d_tie = nullptr;
+    float* d_inv_norm = nullptr;
+    uint32_t* d_codes[kMaxFilterCols] = {nullptr};
+    float* d_max_norm = nullptr;
+    PwProgram* d_pw = nullptr;
+    uint32_t* d_counter = nullptr;   // small scratch counters (16 x u32)
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    int last_launches = 0;
+    int last_kind = 0;
+
+    Scratch s_qraw, s_q64, s_q32, s_qnorm, s_keys, s_mins, s_flags, s_res, s_stage_dev, s_misc;
+    Scratch h_pin, h_pin2;
+
+    int opt_stage_kb = 32;
+    int opt_stages = 0;   // 0 = as many as fit
+    int opt_grid = 0;     // 0 = one CTA per SM
+    int opt_force_kpl = 0;
+
+    std::mutex mu;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// numpy pairwise_sum program
+// ------------------------------------------------------------------------------------------------------
+static int pw_build(PwProgram& pg, int off, int n) {
+    if (n <= 128) {
+        if (pg.n_leaves >= kPwMaxLeaves) return -1;
+        const int id = pg.n_leaves++;
+        pg.leaf_off[id] = (uint16_t)off;
+        pg.leaf_len[id] = (uint16_t)n;
+        return id;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const int l = pw_build(pg, off, n2);
+    if (l < 0) return -1;
+    const int r = pw_build(pg, off + n2, n - n2);
+    if (r < 0) return -1;
+    if (pg.n_steps >= kPwMaxLeaves) return -1;
+    pg.step_dst[pg.n_steps] = (uint8_t)l;
+    pg.step_src[pg.n_steps] = (uint8_t)r;
+    pg.n_steps++;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// library entry points
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lvs_version(void) { return 100; }
+
+extern "C" const char* lvs_last_error(void) { return g_err.c_str(); }
+
+extern "C" int lvs_init(int device) {
+    std::lock_guard<std::mutex> lk(g_lib_mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LVS_ESTATE, "no CUDA device visible (%s); lattice-b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(LVS_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LVS_ESTATE, "device %d is sm_%d%d; lattice-b200 kernels are built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    g_lib.device = device;
+    g_lib.sm_count = prop.multiProcessorCount;
+    g_lib.cc_major = prop.major;
+    g_lib.cc_minor = prop.minor;
+    g_lib.smem_optin = prop.sharedMemPerBlockOptin;
+    g_lib.ready = true;
+    return LVS_OK;
+}
+
+extern "C" int lvs_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_lib_mu);
+    g_lib.ready = false;
+    return LVS_OK;
+}
+
+extern "C" int lvs_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem, int64_t* free_mem) {
+    if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called");
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = g_lib.sm_count;
+    if (cc_major) *cc_major = g_lib.cc_major;
+    if (cc_minor) *cc_minor = g_lib.cc_minor;
+    if (total_mem) *total_mem = (int64_t)t;
+    if (free_mem) *free_mem = (int64_t)f;
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// collections
+// ------------------------------------------------------------------------------------------------------
+static void free_arrays(lvs_collection* c) {
+    cudaFree(c->d_vec); cudaFree(c->d_live); cudaFree(c->d_epoch); cudaFree(c->d_tie); cudaFree(c->d_inv_norm);
+    for (int i = 0; i < kMaxFilterCols; ++i) { cudaFree(c->d_codes[i]); c->d_codes[i] = nullptr; }
+    c->d_vec = nullptr; c->d_live = nullptr; c->d_epoch = nullptr; c->d_tie = nullptr; c->d_inv_norm = nullptr;
+}
+
+static int grow_to(lvs_collection* c, int64_t new_cap) {
+    if (new_cap <= c->capacity) return LVS_OK;
+    if (new_cap >= (int64_t)0xFFFFFFF0ll) return fail(LVS_ELIMIT, "capacity %lld rows exceeds the 32-bit local row space", (long long)new_cap);
+    uint8_t* nv = nullptr; uint8_t* nl = nullptr; uint32_t* ne = nullptr; uint64_t* nt = nullptr; float* ni = nullptr;
+    uint32_t* nc[kMaxFilterCols] = {nullptr};
+    const size_t vb = (size_t)new_cap * c->row_bytes;
+    cudaError_t e = cudaMalloc(&nv, vb);
+    if (e == cudaSuccess) e = cudaMalloc(&nl, (size_t)new_cap);
+    if (e == cudaSuccess) e = cudaMalloc(&ne, (size_t)new_cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&nt, (size_t)new_cap * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&ni, (size_t)new_cap * 4);
+    for (int i = 0; i < c->n_cols && e == cudaSuccess; ++i) e = cudaMalloc(&nc[i], (size_t)new_cap * 4);
+    if (e != cudaSuccess) {
+        cudaFree(nv); cudaFree(nl); cudaFree(ne); cudaFree(nt); cudaFree(ni);
+        for (int i = 0; i < kMaxFilterCols; ++i) cudaFree(nc[i]);
+        cudaGetLastError();
+        return fail(LVS_ENOMEM, "cannot allocate %lld rows x %u bytes on the device: %s", (long long)new_cap, c->row_bytes,
+                    cudaGetErrorString(e));
+    }
+    cudaStream_t st = c->stream;
+    CU(cudaMemsetAsync(nl, 0, (size_t)new_cap, st));
+    for (int i = 0; i < c->n_cols; ++i) CU(cudaMemsetAsync(nc[i], 0, (size_t)new_cap * 4, st));
+    if (c->n_rows > 0) {
+        const size_t n = (size_t)c->n_rows;
+        CU(cudaMemcpyAsync(nv, c->d_vec, n * c->row_bytes, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(nl, c->d_live, n, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ne, c->d_epoch, n * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(nt, c->d_tie, n * 8, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ni, c->d_inv_norm, n * 4, cudaMemcpyDeviceToDevice, st));
+        for (int i = 0; i < c->n_cols; ++i) CU(cudaMemcpyAsync(nc[i], c->d_codes[i], n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    free_arrays(c);
+    c->d_vec = nv; c->d_live = nl; c->d_epoch = ne; c->d_tie = nt; c->d_inv_norm = ni;
+    for (int i = 0; i < c->n_cols; ++i) c->d_codes[i] = nc[i];
+    c->capacity = new_cap;
+    return LVS_OK;
+}
+
+extern "C" int lvs_collection_create(const char* name, int dim, int storage, int metric, int n_filter_cols,
+                                     int64_t capacity_rows, int64_t row_base, lvs_collection** out) {
+    if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
+    if (!out) return fail(LVS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (dim < 1 || dim > 8192) return fail(LVS_ELIMIT, "dim %d outside 1..8192", dim);
+    if (storage != LVS_STORAGE_F32 && storage != LVS_STORAGE_BF16) return fail(LVS_EINVAL, "unknown storage %d", storage);
+    if (metric != LVS_METRIC_COSINE && metric != LVS_METRIC_DOT) return fail(LVS_EINVAL, "unknown metric %d", metric);
+    if (n_filter_cols < 0 || n_filter_cols > kMaxFilterCols) return fail(LVS_ELIMIT, "n_filter_cols %d outside 0..%d", n_filter_cols, kMaxFilterCols);
+    if (capacity_rows < 0 || row_base < 0) return fail(LVS_EINVAL, "negative capacity or row_base");
+    lvs_collection* c = new (std::nothrow) lvs_collection();
+    if (!c) return fail(LVS_ENOMEM, "host allocation failed");
+    c->name = name ? name : "";
+    c->dim = dim; c->storage = storage; c->metric = metric; c->n_cols = n_filter_cols; c->row_base = row_base;
+    const int esz = storage == LVS_STORAGE_F32 ? 4 : 2;
+    const int epc = 16 / esz;
+    const int ld = (dim + epc - 1) / epc * epc;
+    c->row_bytes = (uint32_t)(ld * esz);
+    c->chunks_per_row = c->row_bytes / 16;
+    c->q_stride = (uint32_t)ld;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_max_norm, 4);
+    if (e == cudaSuccess) e = cudaMemset(c->d_max_norm, 0, 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 64);
+    if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, 64);
+    PwProgram pg;
+    memset(&pg, 0, sizeof(pg));
+    if (dim < 8) { pg.n_leaves = 1; pg.leaf_off[0] = 0; pg.leaf_len[0] = (uint16_t)dim; }
+    else if (pw_build(pg, 0, dim) < 0) { lvs_collection_destroy(c); return fail(LVS_ELIMIT, "dim %d needs too many pairwise blocks", dim); }
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_pw, sizeof(PwProgram));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_pw, &pg, sizeof(PwProgram), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        lvs_collection_destroy(c);
+        return fail(LVS_ECUDA, "collection setup failed: %s", cudaGetErrorString(e));
+    }
+    int rc = grow_to(c, std::max<int64_t>(capacity_rows, 1024));
+    if (rc != LVS_OK) { lvs_collection_destroy(c); return rc; }
+    *out = c;
+    return LVS_OK;
+}
+
+extern "C" int lvs_collection_destroy(lvs_collection* c) {
+    if (!c) return LVS_OK;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_arrays(c);
+    cudaFree(c->d_max_norm); cudaFree(c->d_pw); cudaFree(c->d_counter);
+    Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc};
+    for (Scratch* s : ds) if (s->p) cudaFree(s->p);
+    if (c->h_pin.p) cudaFreeHost(c->h_pin.p);
+    if (c->h_pin2.p) cudaFreeHost(c->h_pin2.p);
+    for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LVS_OK;
+}
+
+extern "C" int lvs_collection_reserve(lvs_collection* c, int64_t capacity_rows) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    return grow_to(c, capacity_rows);
+}
+
+extern "C" int64_t lvs_rows(const lvs_collection* c) { return c ? c->n_rows : 0; }
+extern "C" int64_t lvs_capacity(const lvs_collection* c) { return c ? c->capacity : 0; }
+extern "C" uint32_t lvs_search_counter(const lvs_collection* c) { return c ? c->search_counter : 0; }
+
+__global__ void count_live_kernel(const uint8_t* live, uint32_t n, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += live[i];
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+extern "C" int64_t lvs_count(const lvs_collection* cc) {
+    lvs_collection* c = const_cast<lvs_collection*>(cc);
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->n_rows == 0) return 0;
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(c->d_counter + 8);
+    unsigned long long h = 0;
+    if (cudaMemsetAsync(d, 0, 8, c->stream) != cudaSuccess) return -1;
+    count_live_kernel<<<std::min<int64_t>(1024, (c->n_rows + 255) / 256), 256, 0, c->stream>>>(c->d_live, (uint32_t)c->n_rows, d);
+    if (cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    return (int64_t)h;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// upsert
+// ------------------------------------------------------------------------------------------------------
+static size_t dt_size(int dtype) { return dtype == LVS_DT_F64 ? 8 : dtype == LVS_DT_F32 ? 4 : 2; }
+
+static int launch_upsert(lvs_collection* c, const void* d_src, int dtype, int64_t n, const int64_t* d_rows, int64_t row0,
+                         const uint32_t* d_codes, const uint64_t* d_ties, cudaStream_t st) {
+    UpsertParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = d_src; p.src_dtype = dtype; p.n = n; p.rows = d_rows; p.row0 = row0;
+    p.base = c->d_vec; p.row_bytes = c->row_bytes; p.dim = c->dim; p.storage = c->storage; p.metric = c->metric;
+    p.inv_norm = c->d_inv_norm; p.live = c->d_live; p.epoch = c->d_epoch; p.epoch_val = c->search_counter;
+    p.tiekey = c->d_tie; p.ties_src = d_ties; p.row_base = c->row_base;
+    for (int i = 0; i < c->n_cols; ++i) p.codes[i] = c->d_codes[i];
+    p.codes_src = d_codes; p.n_cols = c->n_cols; p.max_norm = c->d_max_norm;
+    const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)g_lib.sm_count * 16);
+    upsert_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(p);
+    CU(cudaGetLastError());
+    return LVS_OK;
+}
+
+extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_t n, const int64_t* rows,
+                          const uint32_t* codes, const uint64_t* ties) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n < 0 || (n > 0 && !vecs)) return fail(LVS_EINVAL, "bad vecs / n");
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64 && dtype != LVS_DT_BF16) return fail(LVS_EINVAL, "unknown dtype %d", dtype);
+    if (n == 0) return LVS_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int64_t hi = c->n_rows;
+    int64_t row0 = c->n_rows;
+    if (rows) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (rows[i] < c->row_base) return fail(LVS_EINVAL, "rows[%lld] is below the shard's row_base", (long long)i);
+            hi = std::max(hi, rows[i] - c->row_base + 1);
+        }
+    } else {
+        hi = row0 + n;
+    }
+    if (hi > c->capacity) {
+        int rc = grow_to(c, std::max(hi, c->capacity * 2));
+        if (rc != LVS_OK) return rc;
+    }
+    // stage through pinned memory in batches of <= 32 MiB of vector data
+    const size_t vrow = (size_t)c->dim * dt_size(dtype);
+    const int64_t batch = std::max<int64_t>(1, (int64_t)((32u << 20) / vrow));
+    const size_t per_row = vrow + 8 + 8 + (size_t)c->n_cols * 4;
+    const int64_t b0 = std::min(batch, n);
+    int rc = ensure_pinned(c->h_pin, (size_t)b0 * per_row + 64);
+    if (rc != LVS_OK) return rc;
+    rc = ensure_dev(c->s_stage_dev, (size_t)b0 * per_row + 64);
+    if (rc != LVS_OK) return rc;
+    cudaStream_t st = c->stream;
+    for (int64_t s = 0; s < n; s += batch) {
+        const int64_t m = std::min(batch, n - s);
+        uint8_t* hp = (uint8_t*)c->h_pin.p;
+        uint8_t* dp = (uint8_t*)c->s_stage_dev.p;
+        size_t o_vec = 0;
+        size_t o_rows = ((size_t)m * vrow + 15) & ~(size_t)15;
+        size_t o_ties = o_rows + (size_t)m * 8;
+        size_t o_codes = o_ties + (size_t)m * 8;
+        size_t total = o_codes + (size_t)m * c->n_cols * 4;
+        memcpy(hp + o_vec, (const uint8_t*)vecs + (size_t)s * vrow, (size_t)m * vrow);
+        if (rows) {
+            int64_t* lr = (int64_t*)(hp + o_rows);
+            for (int64_t j = 0; j < m; ++j) lr[j] = rows[s + j] - c->row_base;   // global -> local
+        }
+        if (ties) memcpy(hp + o_ties, ties + s, (size_t)m * 8);
+        if (codes && c->n_cols) memcpy(hp + o_codes, codes + (size_t)s * c->n_cols, (size_t)m * c->n_cols * 4);
+        CU(cudaMemcpyAsync(dp, hp, total, cudaMemcpyHostToDevice, st));
+        rc = launch_upsert(c, dp + o_vec, dtype, m, rows ? (const int64_t*)(dp + o_rows) : nullptr, row0 + s,
+                           (codes && c->n_cols) ? (const uint32_t*)(dp + o_codes) : nullptr,
+                           ties ? (const uint64_t*)(dp + o_ties) : nullptr, st);
+        if (rc != LVS_OK) return rc;
+        CU(cudaStreamSynchronize(st));   // the pinned buffer is reused by the next batch
+    }
+    c->n_rows = hi;
+    return LVS_OK;
+}
+
+extern "C" int lvs_upsert_device(lvs_collection* c, const void* d_vecs, int dtype, int64_t n, int64_t row0,
+                                 const uint32_t* d_codes, const uint64_t* d_ties, void* stream) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n < 0 || (n > 0 && !d_vecs)) return fail(LVS_EINVAL, "bad d_vecs / n");
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64 && dtype != LVS_DT_BF16) return fail(LVS_EINVAL, "unknown dtype %d", dtype);
+    if (n == 0) return LVS_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    row0 -= c->row_base;   // global -> local
+    if (row0 < 0) return fail(LVS_EINVAL, "row0 is below the shard's row_base");
+    const int64_t hi = std::max(c->n_rows, row0 + n);
+    if (hi > c->capacity) {
+        int rc = grow_to(c, std::max(hi, c->capacity * 2));
+        if (rc != LVS_OK) return rc;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = launch_upsert(c, d_vecs, dtype, n, nullptr, row0, d_codes, d_ties, st);
+    if (rc != LVS_OK) return rc;
+    CU(cudaStreamSynchronize(st));
+    c->n_rows = hi;
+    return LVS_OK;
+}
+
+extern "C" int lvs_set_codes(lvs_collection* c, int col, const int64_t* rows, int64_t row0, int64_t n, const uint32_t* codes) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (col < 0 || col >= c->n_cols) return fail(LVS_EINVAL, "filter column %d outside 0..%d", col, c->n_cols - 1);
+    if (n <= 0) return LVS_OK;
+    if (!codes) return fail(LVS_EINVAL, "codes is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::vector<int64_t> local;
+    if (rows) {
+        local.assign(rows, rows + n);
+        for (int64_t i = 0; i < n; ++i) { local[i] -= c->row_base; if (local[i] < 0 || local[i] >= c->n_rows) return fail(LVS_EINVAL, "rows[%lld] out of range", (long long)i); }
+        rows = local.data();
+    } else {
+        row0 -= c->row_base;
+        if (row0 < 0 || row0 + n > c->n_rows) return fail(LVS_EINVAL, "row range out of bounds");
+    }
+    const size_t bytes = (size_t)n * 12 + 16;
+    int rc = ensure_dev(c->s_stage_dev, bytes);
+    if (rc != LVS_OK) return rc;
+    uint8_t* dp = (uint8_t*)c->s_stage_dev.p;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(dp, codes, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    const size_t o_rows = ((size_t)n * 4 + 15) & ~(size_t)15;
+    if (rows) CU(cudaMemcpyAsync(dp + o_rows, rows, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    set_codes_kernel<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(
+        c->d_codes[col], rows ? (const int64_t*)(dp + o_rows) : nullptr, row0, (const uint32_t*)dp, n);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// delete / match
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lvs_delete_rows(lvs_collection* c, const int64_t* rows, int64_t n, int64_t* n_deleted) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n_deleted) *n_deleted = 0;
+    if (n <= 0) return LVS_OK;
+    if (!rows) return fail(LVS_EINVAL, "rows is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    int rc = ensure_dev(c->s_stage_dev, (size_t)n * 8);
+    if (rc != LVS_OK) return rc;
+    cudaStream_t st = c->stream;
+    std::vector<int64_t> local(rows, rows + n);
+    for (auto& r : local) r -= c->row_base;
+    CU(cudaMemcpyAsync(c->s_stage_dev.p, local.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->d_counter, 0, 4, st));
+    set_live_kernel<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(c->d_live, (const int64_t*)c->s_stage_dev.p, n, 0,
+                                                                                    (uint32_t)c->n_rows, c->d_counter);
+    CU(cudaGetLastError());
+    uint32_t h = 0;
+    CU(cudaMemcpyAsync(&h, c->d_counter, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_deleted) *n_deleted = h;
+    return LVS_OK;
+}
+
+static int build_filter(const lvs_collection* c, const uint32_t* want, const uint32_t** codes, uint32_t* wantv, uint32_t* nf) {
+    *nf = 0;
+    if (!want) return LVS_OK;
+    for (int i = 0; i < c->n_cols; ++i) {
+        if (want[i] == kAnyCode) continue;
+        codes[*nf] = c->d_codes[i];
+        wantv[*nf] = want[i];
+        (*nf)++;
+    }
+    return LVS_OK;
+}
+
+static int match_impl(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched, int tombstone) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (cap < 0 || (cap > 0 && !out_rows)) return fail(LVS_EINVAL, "bad out_rows / cap");
+    if (cap > 0xFFFFFFF0ll) cap = 0xFFFFFFF0ll;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n_matched) *n_matched = 0;
+    if (c->n_rows == 0) return LVS_OK;
+    MatchParams p;
+    memset(&p, 0, sizeof(p));
+    build_filter(c, want, p.codes, p.want, &p.n_filter);
+    int rc = ensure_dev(c->s_res, (size_t)std::max<int64_t>(cap, 1) * 8);
+    if (rc != LVS_OK) return rc;
+    cudaStream_t st = c->stream;
+    p.n_rows = (uint32_t)c->n_rows; p.live = c->d_live; p.row_base = c->row_base;
+    p.out_rows = (int64_t*)c->s_res.p; p.cap = (uint32_t)cap; p.counter = c->d_counter; p.tombstone = tombstone; p.live_rw = c->d_live;
+    CU(cudaMemsetAsync(c->d_counter, 0, 4, st));
+    match_rows_kernel<<<(unsigned)std::min<int64_t>((int64_t)g_lib.sm_count * 8, (c->n_rows + 255) / 256), 256, 0, st>>>(p);
+    CU(cudaGetLastError());
+    uint32_t h = 0;
+    CU(cudaMemcpyAsync(&h, c->d_counter, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int64_t ncopy = std::min<int64_t>(h, cap);
+    if (ncopy > 0) CU(cudaMemcpy(out_rows, c->s_res.p, (size_t)ncopy * 8, cudaMemcpyDeviceToHost));
+    if (n_matched) *n_matched = h;
+    return LVS_OK;
+}
+
+extern "C" int lvs_delete_where(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched) {
+    return match_impl(c, want, out_rows, cap, n_matched, 1);
+}
+extern "C" int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched) {
+    return match_impl(c, want, out_rows, cap, n_matched, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int QT, int KPL, bool NORM, bool FILTER>
+static cudaError_t launch_scan_inst(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kfn = scan_topk_kernel<T, QT, KPL, NORM, FILTER>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kfn<<<grid, kScanThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T, bool NORM, bool FILTER>
+static cudaError_t launch_scan_tnf(int qt, int kpl, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+#define LVS_CASE(Q_, K_) if (qt == Q_ && kpl == K_) return launch_scan_inst<T, Q_, K_, NORM, FILTER>(p, grid, smem, st);
+    LVS_CASE(1, 1) LVS_CASE(1, 2) LVS_CASE(1, 4) LVS_CASE(1, 8)
+    LVS_CASE(2, 1) LVS_CASE(2, 2) LVS_CASE(2, 4)
+    LVS_CASE(4, 1) LVS_CASE(4, 2)
+#undef LVS_CASE
+    return cudaErrorInvalidValue;
+}
+
+static cudaError_t launch_scan(const lvs_collection* c, int qt, int kpl, bool filter, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+    if (c->storage == LVS_STORAGE_F32) {
+        return filter ? launch_scan_tnf<float, false, true>(qt, kpl, p, grid, smem, st)
+                      : launch_scan_tnf<float, false, false>(qt, kpl, p, grid, smem, st);
+    }
+    if (c->metric == LVS_METRIC_COSINE) {
+        return filter ? launch_scan_tnf<__nv_bfloat16, true, true>(qt, kpl, p, grid, smem, st)
+                      : launch_scan_tnf<__nv_bfloat16, true, false>(qt, kpl, p, grid, smem, st);
+    }
+    return filter ? launch_scan_tnf<__nv_bfloat16, false, true>(qt, kpl, p, grid, smem, st)
+                  : launch_scan_tnf<__nv_bfloat16, false, false>(qt, kpl, p, grid, smem, st);
+}
+
+static int max_qt_for_kpl(int kpl) { return kpl >= 8 ? 1 : kpl >= 4 ? 2 : 4; }
+
+struct ScanGeom {
+    uint32_t stage_rows, n_stages, stage_bytes;
+    size_t smem;
+};
+
+static int scan_geometry(const lvs_collection* c, int qt, bool filter, ScanGeom* g) {
+    const size_t budget = g_lib.smem_optin;   // 227 KB on B200
+    uint32_t target = (uint32_t)std::max(4, c->opt_stage_kb) * 1024u;
+    uint32_t R = std::max<uint32_t>(kScanRW, (target / c->row_bytes) / kScanRW * kScanRW);
+    for (;;) {
+        const uint32_t sb = R * c->row_bytes;
+        uint32_t S = kScanMaxStages;
+        if (c->opt_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_stages);
+        while (S >= 2 && scan_smem_bytes(S, sb, qt, c->q_stride, R, filter) > budget) --S;
+        if (S >= 2) {
+            g->stage_rows = R; g->n_stages = S; g->stage_bytes = sb;
+            g->smem = scan_smem_bytes(S, sb, qt, c->q_stride, R, filter);
+            return LVS_OK;
+        }
+        if (R <= (uint32_t)kScanRW) break;
+        R -= kScanRW;
+    }
+    return fail(LVS_ELIMIT, "dim %d does not fit the scan's shared-memory ring", c->dim);
+}
+
+// Core: queries already on the device (raw, `dtype`); outputs are device buffers.
+static int search_core(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                       double* d_scores, int64_t* d_rows, uint64_t* d_ties, uint32_t* d_counts, int32_t* h_flags, cudaStream_t st) {
+    if (Q <= 0) return LVS_OK;
+    if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
+    const int sm = g_lib.sm_count;
+    int rc;
+    if ((rc = ensure_dev(c->s_q64, (size_t)Q * c->dim * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_q32, (size_t)(Q + 4) * c->q_stride * 4)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_qnorm, (size_t)Q * 4)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_keys, (size_t)4 * sm * 256 * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_mins, (size_t)4 * sm * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_flags, (size_t)Q * 4)) != LVS_OK) return rc;
+    double* q64 = (double*)c->s_q64.p;
+    float* q32 = (float*)c->s_q32.p;
+    float* qnorm = (float*)c->s_qnorm.p;
+    uint64_t* keys = (uint64_t*)c->s_keys.p;
+    uint64_t* mins = (uint64_t*)c->s_mins.p;
+    int32_t* d_flags = (int32_t*)c->s_flags.p;
+
+    int launches = 0;
+    CU(cudaEventRecord(c->ev[0], st));
+    {
+        PrepParams pp;
+        pp.src = d_queries; pp.src_dtype = dtype; pp.dim = c->dim; pp.metric = c->metric;
+        pp.q64 = q64; pp.q32 = q32; pp.q_stride = c->q_stride; pp.qnorm = qnorm;
+        CU(cudaMemsetAsync(q32 + (size_t)Q * c->q_stride, 0, (size_t)4 * c->q_stride * 4, st));
+        prep_queries_kernel<<<Q, 256, 0, st>>>(pp);
+        CU(cudaGetLastError());
+        ++launches;
+    }
+    CU(cudaEventRecord(c->ev[1], st));
+
+    const uint32_t* fcodes[kMaxFilterCols];
+    uint32_t fwant[kMaxFilterCols];
+    uint32_t nf = 0;
+    build_filter(c, want, fcodes, fwant, &nf);
+    const bool filter = nf > 0;
+
+    // candidate-set size: smallest list of 32*KPL keys that leaves a margin over k
+    int kpl = 1;
+    while (kpl < 8 && 32 * kpl < k + std::max(8, k / 4)) kpl <<= 1;
+    if (c->opt_force_kpl > 0) kpl = std::max(kpl, c->opt_force_kpl);
+
+    const int chain = (int)((c->chunks_per_row + 31) / 32) * (c->storage == LVS_STORAGE_F32 ? 4 : 8);
+    const float eps_rel = (float)(chain + 12) * 1.1920929e-7f;
+
+    std::vector<int> pending(Q);
+    for (int i = 0; i < Q; ++i) pending[i] = i;
+    std::vector<int32_t> flags(Q, 0);
+    const uint32_t search_base = c->search_counter + 1;
+    bool first_group = true;
+
+    while (!pending.empty()) {
+        const int max_qt = max_qt_for_kpl(kpl);
+        size_t i = 0;
+        while (i < pending.size()) {
+            // a group = up to max_qt CONSECUTIVE query indices; kernels exist for 1, 2 and 4 query slots
+            // (a 3-query group runs the 4-slot kernel, whose last slot scores an all-zero query and is ignored)
+            const int first = pending[i];
+            int cnt = 1;
+            while (cnt < max_qt && i + cnt < pending.size() && pending[i + cnt] == first + cnt) ++cnt;
+            const int qt_use = cnt == 1 ? 1 : cnt == 2 ? 2 : 4;
+            ScanGeom g;
+            if ((rc = scan_geometry(c, qt_use, filter, &g)) != LVS_OK) return rc;
+            ScanParams sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.base = c->d_vec; sp.row_bytes = c->row_bytes; sp.chunks_per_row = c->chunks_per_row;
+            sp.n_rows = (uint32_t)c->n_rows; sp.stage_rows = g.stage_rows; sp.n_stages = g.n_stages; sp.stage_bytes = g.stage_bytes;
+            sp.n_tiles = (uint32_t)((c->n_rows + g.stage_rows - 1) / g.stage_rows);
+            sp.n_blocks32 = (uint32_t)((c->n_rows + 31) / 32);
+            sp.queries = q32 + (size_t)first * c->q_stride; sp.q_stride = c->q_stride;
+            sp.live = c->d_live;
+            for (uint32_t f = 0; f < nf; ++f) { sp.codes[f] = fcodes[f]; sp.want[f] = fwant[f]; }
+            sp.n_filter = nf;
+            sp.out_keys = keys; sp.out_mins = mins;
+            int grid = c->opt_grid > 0 ? c->opt_grid : sm;
+            const uint32_t units = filter ? sp.n_blocks32 : sp.n_tiles;
+            grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, units));
+            if (first_group) CU(cudaEventRecord(c->ev[2], st));
+            cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, grid, g.smem, st);
+            if (e != cudaSuccess) return fail(LVS_ECUDA, "scan kernel launch failed: %s (qt=%d kpl=%d smem=%zu)", cudaGetErrorString(e), qt_use, kpl, g.smem);
+            ++launches;
+            if (first_group) CU(cudaEventRecord(c->ev[3], st));
+
+            FinalizeParams fp;
+            memset(&fp, 0, sizeof(fp));
+            const uint32_t kpw = 32u * kpl;
+            fp.keys = keys; fp.mins = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid; fp.kp = kpw; fp.k = (uint32_t)k;
+            fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (c->dim + 3) & ~3;
+            fp.storage = c->storage; fp.metric = c->metric;
+            fp.q64 = q64 + (size_t)first * c->dim;
+            fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)first;
+            fp.pw = c->d_pw; fp.eps = eps_rel; fp.row_base = c->row_base;
+            int nrw = kFinWarps;
+            while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
+            fp.n_rescore_warps = nrw;
+            fp.out_scores = d_scores + (size_t)first * k; fp.out_rows = d_rows + (size_t)first * k; fp.out_ties = d_ties + (size_t)first * k;
+            fp.out_flags = d_flags + first; fp.out_counts = d_counts + first;
+            fp.qnorm = qnorm + first; fp.max_norm = c->d_max_norm;
+            // keys of query slot s of this group live at keys + s*grid*kpw: the finalize CTA index is the slot
+            const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
+            static bool fin_attr = false;
+            if (!fin_attr) { CU(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin)); fin_attr = true; }
+            finalize_kernel<<<cnt, kFinThreads, fsm, st>>>(fp);
+            CU(cudaGetLastError());
+            ++launches;
+            if (first_group) { CU(cudaEventRecord(c->ev[4], st)); first_group = false; }
+            i += cnt;
+        }
+        CU(cudaMemcpyAsync(flags.data(), d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<int> next;
+        for (int qi : pending) if ((flags[qi] & 1) && kpl < 8) next.push_back(qi);
+        pending.swap(next);
+        if (!pending.empty()) kpl <<= 1;
+    }
+    CU(cudaEventRecord(c->ev[5], st));
+    CU(cudaEventSynchronize(c->ev[5]));
+    cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[5]);
+    c->last_launches = launches;
+    c->last_kind = 1;
+    if (h_flags) memcpy(h_flags, flags.data(), (size_t)Q * 4);
+    c->search_counter += (uint32_t)Q;
+    return LVS_OK;
+}
+
+extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                          double* out_scores, int64_t* out_rows, uint64_t* out_ties, uint32_t* out_counts, int32_t* out_flags) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (Q < 0 || (Q > 0 && !queries)) return fail(LVS_EINVAL, "bad queries / Q");
+    if (Q == 0) return LVS_OK;
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t qbytes = (size_t)Q * c->dim * dt_size(dtype);
+    const size_t nres = (size_t)Q * k;
+    const size_t rbytes = nres * 24 + (size_t)Q * 4;
+    int rc;
+    if ((rc = ensure_pinned(c->h_pin2, std::max(qbytes, rbytes))) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_qraw, qbytes)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_res, rbytes)) != LVS_OK) return rc;
+    cudaStream_t st = c->stream;
+    memcpy(c->h_pin2.p, queries, qbytes);
+    CU(cudaMemcpyAsync(c->s_qraw.p, c->h_pin2.p, qbytes, cudaMemcpyHostToDevice, st));
+    uint8_t* rp = (uint8_t*)c->s_res.p;
+    double* ds = (double*)rp;
+    int64_t* dr = (int64_t*)(rp + nres * 8);
+    uint64_t* dt = (uint64_t*)(rp + nres * 16);
+    uint32_t* dc = (uint32_t*)(rp + nres * 24);
+    rc = search_core(c, c->s_qraw.p, dtype, Q, k, want, ds, dr, dt, dc, out_flags, st);
+    if (rc != LVS_OK) return rc;
+    CU(cudaMemcpyAsync(c->h_pin2.p, rp, rbytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint8_t* hp = (const uint8_t*)c->h_pin2.p;
+    if (out_scores) memcpy(out_scores, hp, nres * 8);
+    if (out_rows) memcpy(out_rows, hp + nres * 8, nres * 8);
+    if (out_ties) memcpy(out_ties, hp + nres * 16, nres * 8);
+    if (out_counts) memcpy(out_counts, hp + nres * 24, (size_t)Q * 4);
+    return LVS_OK;
+}
+
+extern "C" int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                                 double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                                 int32_t* out_flags, void* stream) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (Q < 0 || (Q > 0 && (!d_queries || !d_out_scores || !d_out_rows || !d_out_ties || !d_out_counts)))
+        return fail(LVS_EINVAL, "NULL device buffer");
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, out_flags, st);
+}
+
+extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const uint64_t* d_ties, int64_t shard_stride,
+                                     int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                                     void* stream) {
+    if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called");
+    if (G < 1 || Q < 0 || k < 1) return fail(LVS_EINVAL, "bad G / Q / k");
+    if (Q == 0) return LVS_OK;
+    const size_t smem = (size_t)G * k * 24;
+    if (smem > g_lib.smem_optin - 1024) return fail(LVS_ELIMIT, "G*k = %d too large for the merge kernel", G * k);
+    MergeParams p;
+    p.in_scores = d_scores; p.in_rows = d_rows; p.in_ties = d_ties; p.G = G; p.Q = Q; p.k = k;
+    p.shard_stride = shard_stride > 0 ? shard_stride : (int64_t)Q * k;
+    p.out_scores = d_out_scores; p.out_rows = d_out_rows; p.out_ties = d_out_ties; p.out_counts = d_out_counts;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+    merge_topk_kernel<<<Q, 256, smem, st>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// instrumentation
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches, int* kernel_kind) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (ms4) memcpy(ms4, c->last_ms, sizeof(float) * 4);
+    if (n_launches) *n_launches = c->last_launches;
+    if (kernel_kind) *kernel_kind = c->last_kind;
+    return LVS_OK;
+}
+
+extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
+    if (!c || !name) return fail(LVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!strcmp(name, "stage_kb")) c->opt_stage_kb = value;
+    else if (!strcmp(name, "stages")) c->opt_stages = value;
+    else if (!strcmp(name, "grid")) c->opt_grid = value;
+    else if (!strcmp(name, "force_kpl")) c->opt_force_kpl = value;
+    else return fail(LVS_EINVAL, "unknown option '%s'", name);
+    return LVS_OK;
+}
+
+__global__ void fetch_rows_kernel(const uint8_t* base, uint32_t row_bytes, int dim, int storage, const int64_t* rows, int64_t n, float* out) {
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint8_t* rp = base + (size_t)rows[i] * row_bytes;
+        for (int c = threadIdx.x; c < dim; c += blockDim.x)
+            out[(size_t)i * dim + c] = storage == LVS_STORAGE_F32 ? reinterpret_cast<const float*>(rp)[c]
+                                                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rp)[c]);
+    }
+}
+
+extern "C" int lvs_fetch_rows_f32(lvs_collection* c, const int64_t* rows, int64_t n, float* out) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n <= 0) return LVS_OK;
+    if (!rows || !out) return fail(LVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::vector<int64_t> local(rows, rows + n);
+    for (auto& r : local) { r -= c->row_base; if (r < 0 || r >= c->n_rows) return fail(LVS_EINVAL, "row out of range"); }
+    int rc = ensure_dev(c->s_misc, (size_t)n * 8 + (size_t)n * c->dim * 4);
+    if (rc != LVS_OK) return rc;
+    cudaStream_t st = c->stream;
+    int64_t* dr = (int64_t*)c->s_misc.p;
+    float* dout = (float*)((uint8_t*)c->s_misc.p + (size_t)n * 8);
+    CU(cudaMemcpyAsync(dr, local.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    fetch_rows_kernel<<<(unsigned)std::min<int64_t>(n, 4096), 128, 0, st>>>(c->d_vec, c->row_bytes, c->dim, c->storage, dr, n, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, (size_t)n * c->dim * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return LVS_OK;
+}

@@ -1,0 +1,121 @@
+/* lattice-b200 vector store: C ABI of the B200-native collection backend (liblattice_b200.so).
+ *
+ * This is the drop-in boundary for the semantic-search hot path of lattice (iAmLakshya/code-rag).  The
+ * reference has no FFI of its own: the path sits behind the duck-typed Python class
+ * `lattice.embeddings.client.QdrantManager` (reference src/lattice/embeddings/client.py:18-228, protocol
+ * `VectorStore` in src/lattice/core/protocols.py:34-52), whose methods forward to qdrant-client.  Each entry
+ * point below names the reference call it replaces; `code_rag_b200/client.py` binds them with ctypes and
+ * INTEGRATION.md shows the stub a lattice maintainer would add.
+ *
+ * Conventions: plain C, no exceptions.  Every function returns LVS_OK (0) or a negative LVS_E* code;
+ * lvs_last_error() gives a thread-local message.  The caller owns every host buffer; the library owns device
+ * memory.  One process drives ONE GPU (one process per GPU under torchrun); a collection handle may be used from
+ * any thread (calls on one handle are serialised internally).  Calls are synchronous on return.  "Rows" are GLOBAL
+ * row numbers everywhere in this API: a shard created with row_base B owns rows B, B+1, ... (dense, chosen by the
+ * caller; the Python adapter appends).
+ */
+#ifndef LATTICE_B200_LVS_H
+#define LATTICE_B200_LVS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVS_OK 0
+#define LVS_EINVAL (-1)     /* bad argument */
+#define LVS_ECUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define LVS_ENOMEM (-3)     /* device or host allocation failed */
+#define LVS_ESTATE (-4)     /* library not initialised / no CUDA device */
+#define LVS_ELIMIT (-5)     /* k, dim or batch beyond what the kernels support */
+
+#define LVS_STORAGE_F32 0
+#define LVS_STORAGE_BF16 1
+#define LVS_METRIC_COSINE 0 /* models.Distance.COSINE, client.py:99 */
+#define LVS_METRIC_DOT 1
+#define LVS_DT_F32 0
+#define LVS_DT_F64 1
+#define LVS_DT_BF16 2
+#define LVS_MAX_FILTER_COLS 8
+#define LVS_ANY 0xFFFFFFFFu        /* filter column not constrained */
+#define LVS_NULL_CODE 0u           /* payload key missing or None: matches no MatchValue */
+#define LVS_NO_MATCH 0xFFFFFFFEu   /* filter value never seen in this column: matches nothing */
+#define LVS_MAX_K 224              /* largest `limit` one search call serves */
+#define LVS_FLAG_UNPROVEN 1        /* out_flags bit: exactness bound not met even at the largest candidate set */
+
+typedef struct lvs_collection lvs_collection;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int lvs_version(void);
+const char* lvs_last_error(void);
+/* Bind the process to one CUDA device.  Replaces QdrantManager.connect (client.py:32-45). Fails with LVS_ESTATE
+ * when no sm_100 device is present: there is no CPU fallback. */
+int lvs_init(int device);
+int lvs_shutdown(void);                                   /* QdrantManager.close, client.py:47-55 */
+int lvs_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem, int64_t* free_mem);
+
+/* ---- collections (client.py:72-113 create_collections/_create_collection_with_indexes) ----------------- */
+int lvs_collection_create(const char* name, int dim, int storage, int metric, int n_filter_cols,
+                          int64_t capacity_rows, int64_t row_base, lvs_collection** out);
+int lvs_collection_destroy(lvs_collection* c);            /* client.delete_collection, client.py:215 */
+int lvs_collection_reserve(lvs_collection* c, int64_t capacity_rows);
+int64_t lvs_rows(const lvs_collection* c);                /* high-water mark (rows ever written) */
+int64_t lvs_count(const lvs_collection* c);               /* live rows: CollectionInfo.points_count, client.py:204-210 */
+int64_t lvs_capacity(const lvs_collection* c);
+uint32_t lvs_search_counter(const lvs_collection* c);     /* vector searches served so far (drives the replay) */
+
+/* ---- upsert (QdrantManager.upsert, client.py:115-130; K4 kernel) ----------------------------------------
+ * vecs: n x dim row-major host array of `dtype`.  rows: n global row numbers (the shard grows as needed), or NULL to
+ * append at lvs_rows().  codes: n x n_filter_cols dictionary codes (row-major) or NULL.  ties: n tie-break keys
+ * (order among exactly equal scores is (tie asc, row asc)) or NULL => global row number. */
+int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_t n, const int64_t* rows,
+               const uint32_t* codes, const uint64_t* ties);
+/* Same with DEVICE pointers (vectors produced on the GPU never visit the host); rows are row0..row0+n-1.
+ * d_codes is n x n_filter_cols on the device or NULL.  stream: cudaStream_t or NULL for the collection's stream. */
+int lvs_upsert_device(lvs_collection* c, const void* d_vecs, int dtype, int64_t n, int64_t row0,
+                      const uint32_t* d_codes, const uint64_t* d_ties, void* stream);
+/* (Re)write one filter column for n rows (rows NULL => row0..). Lets the adapter index a payload key lazily. */
+int lvs_set_codes(lvs_collection* c, int col, const int64_t* rows, int64_t row0, int64_t n, const uint32_t* codes);
+
+/* ---- delete (QdrantManager.delete, client.py:159-169) -------------------------------------------------- */
+int lvs_delete_rows(lvs_collection* c, const int64_t* rows, int64_t n, int64_t* n_deleted);
+/* Tombstone every live row matching `want` (n_filter_cols codes, LVS_ANY = unconstrained); the matching GLOBAL rows
+ * are returned (unordered, at most cap) so the host can drop their payloads; *n_matched is the full count. */
+int lvs_delete_where(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched);
+
+/* ---- search (QdrantManager.search -> query_points, client.py:132-157; K1/K2 + exact rescoring) -----------
+ * queries: Q x dim host array of `dtype` (LVS_DT_F32 / LVS_DT_F64).  want: n_filter_cols codes or NULL (client.py:171-176
+ * _build_filter: conjunction of exact matches).  Outputs, Q x k each: scores (float64, local-mode arithmetic), GLOBAL
+ * rows (-1 padded), tie keys; counts[Q] valid results; flags[Q] (LVS_FLAG_UNPROVEN).  Results are ordered
+ * (score desc, tie asc, row asc).  Q searches are accounted as Q consecutive reference searches. */
+int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+               double* out_scores, int64_t* out_rows, uint64_t* out_ties, uint32_t* out_counts, int32_t* out_flags);
+/* Device-pointer form used by the sharded path: queries and the four Q x k / Q outputs are DEVICE buffers, the work is
+ * enqueued on `stream` (cudaStream_t, NULL = collection stream) and completed before return; flags are host. */
+int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                      double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                      int32_t* out_flags, void* stream);
+/* Filter-only lookup (search with query_vector=None, scroll, count: client.py:178-202, query/context/builder.py:111-119,
+ * projects/cleanup.py:41-61): all live rows matching `want` (GLOBAL rows, unordered, at most cap), *n_matched = full count. */
+int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched);
+
+/* ---- K5: merge of per-shard top-k lists after the all-gather ---------------------------------------------------
+ * d_scores/d_rows/d_ties: G blocks of Q x k, `shard_stride` 8-byte elements apart (0 => dense, Q*k), device buffers. */
+int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const uint64_t* d_ties, int64_t shard_stride,
+                          int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                          void* stream);
+
+/* ---- instrumentation --------------------------------------------------------------------------------- */
+/* Device time (ms, CUDA events on the collection's stream) of the kernels of the last lvs_search* call on this handle:
+ * [0] query prep  [1] scan / tensor-core kernel(s)  [2] finalize  [3] whole device section; n_launches = kernels launched. */
+int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches, int* kernel_kind);
+/* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto).  Returns LVS_EINVAL for unknown names. */
+int lvs_set_option(lvs_collection* c, const char* name, int value);
+/* Copy rows back (debug / snapshots): out is n x dim float32 of the values a fresh reference collection would hold. */
+int lvs_fetch_rows_f32(lvs_collection* c, const int64_t* rows, int64_t n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTICE_B200_LVS_H */

@@ -1,0 +1,253 @@
+"""GPU parity tests: CUDA path through the C ABI vs the CPU oracle (oracle/qdrant_local.py).
+
+Bars (BASELINE.json north_star): top-k id lists identical (ties by id); scores within 1e-5 relative for fp32
+storage, 2e-3 for bf16 storage.  The device replays local mode's arithmetic exactly, so the observed error is
+~1e-15; the tests assert the stated bars and additionally a much tighter one to catch regressions of the replay.
+"""
+import numpy as np
+import pytest
+
+from oracle.qdrant_local import OracleCollection
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_F32 = 1e-5
+REL_BF16 = 2e-3
+TIGHT = 1e-12   # absolute, float64 dot of unit vectors computed in a different order
+
+
+@pytest.fixture(scope="module")
+def lib(native_lib):
+    from code_rag_b200 import _native
+    _native.init(0)
+    return native_lib
+
+
+def _dev(name, dim, storage="f32", ncols=0, **kw):
+    from code_rag_b200.collection import DeviceCollection
+    return DeviceCollection(name, dim, storage=storage, n_filter_cols=ncols, **kw)
+
+
+def _assert_same(res, qi, rows_o, scores_o, rel, tight=TIGHT):
+    n = int(res.counts[qi])
+    assert n == len(rows_o), f"query {qi}: device returned {n} hits, oracle {len(rows_o)}"
+    got = res.rows[qi, :n]
+    assert np.array_equal(got, rows_o), (
+        f"query {qi}: id lists differ\n device {got.tolist()}\n oracle {rows_o.tolist()}\n"
+        f" device scores {res.scores[qi, :n].tolist()}\n oracle scores {scores_o.tolist()}")
+    err = np.abs(res.scores[qi, :n] - scores_o)
+    assert np.all(err <= rel * np.maximum(np.abs(scores_o), 1e-30) + 1e-300), f"query {qi}: score error {err.max()}"
+    assert err.max() <= tight, f"query {qi}: replay drift {err.max()} (> {tight})"
+    assert res.flags[qi] == 0, f"query {qi}: exactness flag set"
+
+
+def test_c1_fp32_single_queries(lib):
+    """configs[0]: 10k x 768 fp32 UniXcoder-shaped, 1 query at a time, top-10."""
+    x, q = synth.unixcoder_like(10_000, 768, seed=1234, n_queries=40)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, x, [None] * len(x))
+    dev = _dev("c1", 768)
+    dev.upsert(x.astype(np.float64))
+    assert dev.rows == 10_000 and dev.count() == 10_000
+    for i in range(len(q)):
+        res = dev.search(q[i].astype(np.float64), 10)
+        rows_o, scores_o = ora.search_topk_rows(q[i].astype(np.float64), 10)
+        _assert_same(res, 0, rows_o, scores_o, REL_F32)
+    dev.close()
+
+
+def test_replay_tracks_search_count(lib):
+    """Rows written at different times see a different number of in-place re-normalisations."""
+    x, q = synth.unit_rows(6_000, 768, seed=77, n_queries=12)
+    ora = OracleCollection(768)
+    dev = _dev("replay", 768)
+    ora.upsert_rows_f32(0, x[:3000], [None] * 3000)
+    dev.upsert(x[:3000].astype(np.float64))
+    for i in range(6):
+        res = dev.search(q[i].astype(np.float64), 10)
+        _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
+    ora.upsert_rows_f32(3000, x[3000:], [None] * 3000)
+    dev.upsert(x[3000:].astype(np.float64))
+    for i in range(6, 12):
+        res = dev.search(q[i].astype(np.float64), 10)
+        _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
+    dev.close()
+
+
+@pytest.mark.parametrize("k", [1, 10, 20, 100, 224])
+def test_bf16_storage_parity(lib, k):
+    """bf16 shard: the oracle is fed the bf16-rounded rows."""
+    x, q = synth.unit_rows(30_000, 768, seed=3456, n_queries=6)
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xb, [None] * len(xb))
+    dev = _dev("bf16", 768, storage="bf16")
+    dev.upsert(xb)
+    for i in range(len(q)):
+        res = dev.search(q[i].astype(np.float64), k)
+        _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16)
+    dev.close()
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+@pytest.mark.parametrize("Q", [2, 3, 4, 7, 16])
+def test_batch_equals_sequential(lib, storage, Q):
+    x, q = synth.unit_rows(12_000, 768, seed=99, n_queries=Q)
+    if storage == "bf16":
+        x = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, x, [None] * len(x))
+    dev = _dev("batch", 768, storage=storage)
+    dev.upsert(x)
+    res = dev.search(q.astype(np.float64), 10)
+    for i in range(Q):   # the oracle runs them one after the other, mutating its matrix each time
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32 if storage == "f32" else REL_BF16)
+    dev.close()
+
+
+def test_c2_filters_fp32_1536(lib):
+    """configs[1] shape at a CPU-checkable size: 1536-d fp32 unit rows, project/file/language filters, top-10."""
+    n = 40_000
+    x, q = synth.unit_rows(n, 1536, seed=2345, n_queries=3)
+    pl = synth.payloads(n, seed=2345)
+    cols = ["project_name", "language", "file_path", "entity_type"]
+    dicts = [dict() for _ in cols]
+    codes = np.zeros((n, len(cols)), dtype=np.uint32)
+    for i, p in enumerate(pl):
+        for c, key in enumerate(cols):
+            codes[i, c] = dicts[c].setdefault(p[key], len(dicts[c]) + 1)
+    ora = OracleCollection(1536)
+    ora.upsert_rows_f32(0, x, pl)
+    dev = _dev("c2", 1536, ncols=len(cols))
+    dev.upsert(x.astype(np.float64), codes=codes)
+    ANY = 0xFFFFFFFF
+    some_file = pl[123]["file_path"]
+    cases = [
+        {},
+        {"project_name": "proj0"},
+        {"project_name": "proj7", "language": "python"},
+        {"file_path": some_file},
+        {"project_name": "proj3", "entity_type": "class", "language": "javascript"},
+    ]
+    for flt in cases:
+        want = np.full(len(cols), ANY, dtype=np.uint32)
+        mask = np.ones(n, dtype=bool)
+        for key, val in flt.items():
+            c = cols.index(key)
+            want[c] = dicts[c][val]
+            mask &= codes[:, c] == want[c]
+        for i in range(len(q)):
+            res = dev.search(q[i].astype(np.float64), 10, want if flt else None)
+            rows_o, scores_o = ora.search_topk_rows(q[i].astype(np.float64), 10, mask)
+            _assert_same(res, 0, rows_o, scores_o, REL_F32)
+    # a value never seen in the column matches nothing
+    want = np.full(len(cols), ANY, dtype=np.uint32)
+    want[0] = 0xFFFFFFFE
+    res = dev.search(q[0].astype(np.float64), 10, want)
+    assert res.counts[0] == 0 and (res.rows[0] == -1).all()
+    dev.close()
+
+
+def test_tombstones_overwrite_and_ties(lib):
+    x, q = synth.unit_rows(5_000, 256, seed=5, n_queries=4)
+    x[100] = x[7]      # exact duplicates: equal scores, order by (tie, row)
+    x[4000] = x[7]
+    ora = OracleCollection(256)
+    ora.upsert_rows_f32(0, x, [None] * len(x))
+    dev = _dev("tomb", 256)
+    dev.upsert(x.astype(np.float64))
+    qq = x[7].astype(np.float64)
+    res = dev.search(qq, 5)
+    rows_o, scores_o = ora.search_topk_rows(qq, 5)
+    assert res.rows[0, :3].tolist() == [7, 100, 4000] == rows_o[:3].tolist()
+    assert res.scores[0, 0] == res.scores[0, 1] == res.scores[0, 2]
+    # delete two rows, overwrite one
+    dev.delete_rows(np.array([7, 4000]))
+    ora.deleted[[7, 4000]] = True
+    y = synth.unit_rows(1, 256, seed=6)[0]
+    dev.upsert(y.astype(np.float64), rows=np.array([100]))
+    ora.vectors[100] = y[0].astype(np.float64) / np.linalg.norm(y[0].astype(np.float64))
+    assert dev.count() == 4_998
+    for i in range(len(q)):
+        res = dev.search(q[i].astype(np.float64), 10)
+        # row 100 was rewritten after 1 device search: its replay starts from the new write; mirror that in the oracle
+        rows_o, scores_o = ora.search_topk_rows(q[i].astype(np.float64), 10)
+        _assert_same(res, 0, rows_o, scores_o, REL_F32)
+    dev.close()
+
+
+def test_edges(lib):
+    dev = _dev("edge", 64)
+    res = dev.search(np.ones(64), 10)
+    assert res.counts[0] == 0 and (res.rows == -1).all()
+    x, _ = synth.unit_rows(7, 64, seed=3)
+    x[3] = 0.0   # a zero vector is stored as is and scores 0
+    dev.upsert(x.astype(np.float64))
+    ora = OracleCollection(64)
+    ora.upsert_rows_f32(0, x, [None] * 7)
+    q = x[2].astype(np.float64)
+    res = dev.search(q, 10)
+    rows_o, scores_o = ora.search_topk_rows(q, 10)
+    assert res.counts[0] == 7
+    _assert_same(res, 0, rows_o, scores_o, REL_F32)
+    with pytest.raises(ValueError):
+        dev.search(np.full(64, np.nan), 3)
+    from code_rag_b200.errors import NativeLibraryError
+    with pytest.raises(NativeLibraryError):
+        dev.search(q, 1000)
+    dev.close()
+
+
+@pytest.mark.parametrize("dim", [8, 100, 384, 1000, 3072])
+def test_odd_dimensions(lib, dim):
+    x, q = synth.unit_rows(3_000, dim, seed=dim, n_queries=3)
+    for storage in ("f32", "bf16"):
+        xs = synth.bf16_round(x) if storage == "bf16" else x
+        ora = OracleCollection(dim)
+        ora.upsert_rows_f32(0, xs, [None] * len(xs))
+        dev = _dev("odd", dim, storage=storage)
+        dev.upsert(xs)
+        for i in range(len(q)):
+            res = dev.search(q[i].astype(np.float64), 10)
+            _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32 if storage == "f32" else REL_BF16)
+        dev.close()
+
+
+def test_sharded_merge_equals_single(lib):
+    """K5: G shards searched separately + merge == one collection (the multi-GPU path, emulated on one GPU)."""
+    import torch
+    from code_rag_b200.collection import merge_topk_device
+    n, dim, k, G, Q = 24_000, 768, 10, 4, 3
+    x, q = synth.unit_rows(n, dim, seed=5678, n_queries=Q)
+    xb = synth.bf16_round(x)
+    single = _dev("single", dim, storage="bf16")
+    single.upsert(xb)
+    ref = single.search(q.astype(np.float64), k)
+    per = n // G
+    dq = torch.from_numpy(q.astype(np.float64)).cuda()
+    scores = torch.zeros((G, Q, k), dtype=torch.float64, device="cuda")
+    rows = torch.full((G, Q, k), -1, dtype=torch.int64, device="cuda")
+    ties = torch.zeros((G, Q, k), dtype=torch.int64, device="cuda")
+    counts = torch.zeros((G, Q), dtype=torch.int32, device="cuda")
+    shards = []
+    for g in range(G):
+        sh = _dev(f"shard{g}", dim, storage="bf16", row_base=g * per)
+        sh.upsert(xb[g * per:(g + 1) * per])
+        shards.append(sh)
+        torch.cuda.synchronize()
+        flags = sh.search_device(dq.data_ptr(), "f64", Q, k, None, scores[g].data_ptr(), rows[g].data_ptr(),
+                                 ties[g].data_ptr(), counts[g].data_ptr())
+        assert (flags == 0).all()
+    o_s = torch.zeros((Q, k), dtype=torch.float64, device="cuda")
+    o_r = torch.zeros((Q, k), dtype=torch.int64, device="cuda")
+    o_t = torch.zeros((Q, k), dtype=torch.int64, device="cuda")
+    o_c = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    merge_topk_device(scores.data_ptr(), rows.data_ptr(), ties.data_ptr(), G, Q, k, o_s.data_ptr(), o_r.data_ptr(),
+                      o_t.data_ptr(), o_c.data_ptr())
+    assert np.array_equal(o_r.cpu().numpy(), ref.rows)
+    assert np.array_equal(o_s.cpu().numpy(), ref.scores)
+    for sh in shards:
+        sh.close()
+    single.close()
