@@ -125,51 +125,62 @@ def run_reference(args) -> None:
 # clocks
 # --------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML every ~10 ms while the timed region runs."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[float, int]] = []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    idx = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self._err = repr(e)
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:  # noqa: BLE001
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append((float(mhz), int(rs)))
+                except Exception as e:  # noqa: BLE001
+                    self._err = repr(e)
+                    return
+                time.sleep(0.01)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [f"no samples: {self._err}"], "samples": 0}
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        seen = 0
+        for _, r in self.samples:
+            seen |= r
+        return {"sm_mhz": statistics.median(m for m, _ in self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b_, n in bits.items() if seen & b_), "samples": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.qdrant_local import OracleCollection
-from tests import synth
+import lvs_synth as synth
 
 pytestmark = pytest.mark.gpu
 
