@@ -781,13 +781,13 @@ extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_ro
     if (G < 1 || Q < 0 || k < 1) return fail(LVS_EINVAL, "bad G / Q / k");
     if (Q == 0) return LVS_OK;
     const size_t smem = (size_t)G * k * 24;
-    if (smem > g_lib.smem_optin - 1024) return fail(LVS_ELIMIT, "G*k = %d too large for the merge kernel", G * k);
+    if (smem > g_lib.smem_optin - 2048) return fail(LVS_ELIMIT, "G*k = %d too large for the merge kernel", G * k);
     MergeParams p;
     p.in_scores = d_scores; p.in_rows = d_rows; p.in_ties = d_ties; p.G = G; p.Q = Q; p.k = k;
     p.shard_stride = shard_stride > 0 ? shard_stride : (int64_t)Q * k;
     p.out_scores = d_out_scores; p.out_rows = d_out_rows; p.out_ties = d_out_ties; p.out_counts = d_out_counts;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_topk_kernel<<<Q, 256, smem, st>>>(p);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
