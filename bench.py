@@ -249,42 +249,85 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: device-resident queries ----------------
-    for i in range(W):
-        searcher.search_device(dq_all[i], k)
+    # ---------------- value: device-resident queries, searches enqueued back to back ----------------
+    # (each search is still one full pass over the corpus; results stay in HBM, flags are checked after the loop)
+    NSLOT = searcher.n_slots
+    stream = searcher.stream
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    scan_ms, fin_ms, launches = [], [], 0
+    launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
-    for i in range(W, W + K):
-        searcher.search_device(dq_all[i], k)
-        t = shard.last_timing()
-        scan_ms.append(t["scan_ms"]); fin_ms.append(t["finalize_ms"]); launches += t["launches"]
-    e1.record()
+    flag_bufs = {}
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(W, W + K):
+            out = searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+            flag_bufs[id(out[4])] = out[4]
+            launches += 3          # prep + scan + finalize per search
+        e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
+    n_flagged = int(sum(int(f.sum().item()) for f in flag_bufs.values()))
     launches += searcher.merge_launches if world > 1 else 0
     clocks = sampler.stop() if rank == 0 else None
+    ms_ring, bytes_ring = shard.scan_times(min(K, 256))
+    scan_ms = [float(v) for v in ms_ring]
 
-    # ---------------- e2e: host buffers through the public API ----------------
-    for i in range(W):
-        searcher.search(qs[i], k) if world > 1 else shard.search(qs[i], k)
+    # ---------------- sync: one search at a time, the host waits for each result (latency-bound) ----------------
+    fin_ms = []
     barrier()
     t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for i in range(W, W + K):
+            searcher.search_device(dq_all[i], k)
+            fin_ms.append(shard.last_timing()["finalize_ms"])
+    barrier()
+    sync_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---------------- e2e: host buffers through the public API, every step H2D(query) + D2H(result) ----------------
+    # N=1: the C ABI's pipelined pair lvs_search_submit / lvs_search_wait (host pointers in, host pointers out);
+    # N>1: ShardedSearcher.submit / wait (adds the all-gather + merge).  Two searches are kept in flight, so the copies
+    # and the host work of step i+1 overlap the scan of step i.
+    DEPTH = 2
+
+    def e2e_submit(qh):
+        return searcher.submit(qh, k) if world > 1 else shard.search_submit(qh, k)
+
+    def e2e_wait(h):
+        return searcher.wait(h) if world > 1 else shard.search_wait(h)
+
+    for i in range(W):
+        e2e_wait(e2e_submit(qs[i]))
+    barrier()
+    t0 = time.perf_counter()
+    inflight = []
     last = None
     for i in range(W, W + K):
-        last = searcher.search(qs[i], k) if world > 1 else shard.search(qs[i], k)
+        inflight.append(e2e_submit(qs[i]))
+        if len(inflight) >= DEPTH:
+            last = e2e_wait(inflight.pop(0))
+    while inflight:
+        last = e2e_wait(inflight.pop(0))
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    # depth 1 (strict request/response latency)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        last = e2e_wait(e2e_submit(qs[i]))
+    barrier()
+    e2e1_ms = (time.perf_counter() - t0) * 1e3
 
-    t_dev = torch.tensor([dev_ms, e2e_ms, statistics.mean(scan_ms)], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([dev_ms, e2e_ms, statistics.mean(scan_ms), sync_ms, float(n_flagged)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, scan_mean = (float(v) for v in t_dev.cpu())
+    dev_ms, e2e_ms, scan_mean, sync_ms, n_flagged = (float(v) for v in t_dev.cpu())
 
     if rank == 0:
         peaks = {}
@@ -308,9 +351,14 @@ def run_ours(args) -> None:
                                    f"row-sharded over {world} GPU(s)",
                        "rows": args.rows, "dim": args.dim, "k": k, "queries_per_step": Q, "storage": args.storage,
                        "rows_per_gpu": n_local, "l2": "inputs_exceed_l2", "corpus_gen_s": round(t_gen, 1),
-                       "parallelism": f"row-shard x{world} + all-gather(top-k) + merge"},
+                       "parallelism": f"row-shard x{world} + all-gather(top-k) + merge",
+                       "value_mode": "K searches enqueued back to back on one stream (device-resident queries/results)",
+                       "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K,
+                       "unproven_queries": int(n_flagged)},
             "e2e": {"value": K * Q / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Q * args.dim * 8,
-                    "d2h_bytes_per_step": Q * k * 24 + Q * 4, "ms_per_step": e2e_ms / K},
+                    "d2h_bytes_per_step": Q * k * 24 + Q * 8, "ms_per_step": e2e_ms / K, "in_flight": DEPTH,
+                    "api": "lvs_search_submit/lvs_search_wait (C ABI, host buffers)" if world == 1 else "ShardedSearcher.submit/wait",
+                    "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,

@@ -49,7 +49,11 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_delete_rows": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
     "lvs_delete_where": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_search_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]),
+    "lvs_search_wait": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_search_device_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_scan_times": (C.c_int, [_vp, C.c_int, _f32p, _f64p, _ip]),
     "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),

@@ -193,6 +193,33 @@ class DeviceCollection:
                                      _ptr(ties), _ptr(counts), _ptr(flags)), "lvs_search")
         return SearchResult(scores, rows, ties, counts, flags)
 
+    def search_submit(self, queries: np.ndarray, k: int, want=None) -> tuple[int, int, int]:
+        """Pipelined search: returns a ticket for :meth:`search_wait`; up to 4 searches may be in flight."""
+        q = np.ascontiguousarray(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
+        if q.dtype not in (np.float32, np.float64):
+            q = q.astype(np.float64)
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")
+        t = C.c_int()
+        N.check(self._lib.lvs_search_submit(self._handle(), _ptr(q), _np_dtype_code(q), q.shape[0], int(k), _ptr(self._want(want)),
+                                            C.byref(t)), "lvs_search_submit")
+        return (t.value, q.shape[0], int(k))
+
+    def search_wait(self, ticket: tuple[int, int, int]) -> SearchResult:
+        t, Q, k = ticket
+        scores = np.zeros((Q, k), dtype=np.float64)
+        rows = np.full((Q, k), -1, dtype=np.int64)
+        ties = np.zeros((Q, k), dtype=np.uint64)
+        counts = np.zeros(Q, dtype=np.uint32)
+        flags = np.zeros(Q, dtype=np.int32)
+        N.check(self._lib.lvs_search_wait(self._handle(), t, _ptr(scores), _ptr(rows), _ptr(ties), _ptr(counts), _ptr(flags)),
+                "lvs_search_wait")
+        return SearchResult(scores, rows, ties, counts, flags)
+
     def search_device(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, scores_ptr: int, rows_ptr: int, ties_ptr: int,
                       counts_ptr: int, stream: int = 0) -> np.ndarray:
         """Device-pointer form (sharded path): outputs stay on the GPU; returns the host flags."""
@@ -204,6 +231,25 @@ class DeviceCollection:
                                             C.c_void_p(counts_ptr), _ptr(flags), C.c_void_p(stream or None)),
                 "lvs_search_device")
         return flags
+
+    def search_device_async(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, scores_ptr: int, rows_ptr: int,
+                            ties_ptr: int, counts_ptr: int, flags_ptr: int, stream: int = 0) -> None:
+        """Enqueue-only search (pipelined callers): nothing is synchronised; flags land in a device buffer."""
+        w = self._want(want)
+        code = {"f32": N.DT_F32, "f64": N.DT_F64}[q_dtype]
+        N.check(self._lib.lvs_search_device_async(self._handle(), C.c_void_p(q_ptr), code, int(Q), int(k), _ptr(w),
+                                                  C.c_void_p(scores_ptr), C.c_void_p(rows_ptr), C.c_void_p(ties_ptr),
+                                                  C.c_void_p(counts_ptr), C.c_void_p(flags_ptr), C.c_void_p(stream or None)),
+                "lvs_search_device_async")
+
+    def scan_times(self, max_n: int = 256) -> tuple[np.ndarray, np.ndarray]:
+        """(ms, algorithmic bytes) of the last scan-kernel launches (CUDA events on the launching stream)."""
+        ms = np.zeros(max_n, dtype=np.float32)
+        by = np.zeros(max_n, dtype=np.float64)
+        n = C.c_int()
+        N.check(self._lib.lvs_scan_times(self._handle(), int(max_n), ms.ctypes.data_as(C.POINTER(C.c_float)),
+                                         by.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)), "lvs_scan_times")
+        return ms[:n.value], by[:n.value]
 
     def fetch_rows(self, rows: np.ndarray) -> np.ndarray:
         r = np.ascontiguousarray(rows, dtype=np.int64)

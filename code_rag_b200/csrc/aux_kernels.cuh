@@ -105,12 +105,17 @@ struct PrepParams {
     float* q32;           // [Q][q_stride]
     uint32_t q_stride;
     float* qnorm;         // [Q] ||q|| (dot metric error bound)
+    int n_zero_rows;      // the CTA after the last query zeroes this many fp32 query rows (unused scan slots)
 };
 
 __global__ void __launch_bounds__(256) prep_queries_kernel(const PrepParams p) {
     __shared__ double red[8];
     __shared__ double s_norm;
     const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (qi == (int)gridDim.x - 1) {
+        for (uint32_t c = tid; c < (uint32_t)p.n_zero_rows * p.q_stride; c += 256) p.q32[(size_t)qi * p.q_stride + c] = 0.f;
+        return;
+    }
     const size_t so = (size_t)qi * p.dim;
     double ss = 0.0;
     for (int c = tid; c < p.dim; c += 256) { const double x = load_as_f64(p.src, p.src_dtype, so + c); ss = fma(x, x, ss); }

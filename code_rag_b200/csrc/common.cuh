@@ -105,6 +105,43 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return v;
 }
 
+// Running top-(32*KPL) of 64-bit keys held in registers by one warp (KPL keys per lane).
+template <int KPL>
+struct WarpTopK {
+    uint64_t key[KPL];
+    uint64_t thr;   // current minimum over the 32*KPL slots (warp-uniform)
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) key[j] = 0ull;
+        thr = 0ull;
+    }
+    // warp-uniform call: replace the current minimum by k (k > thr) and recompute the minimum
+    __device__ __forceinline__ void insert(uint64_t k, int lane) {
+        bool has = false;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) has |= (key[j] == thr);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+        const int owner = __ffs(m) - 1;
+        if (lane == owner) {
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                if (!done && key[j] == thr) { key[j] = k; done = true; }
+            }
+        }
+        uint64_t lm = key[0];
+#pragma unroll
+        for (int j = 1; j < KPL; ++j) lm = key[j] < lm ? key[j] : lm;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            uint64_t other = shfl_xor_u64(lm, o);
+            lm = other < lm ? other : lm;
+        }
+        thr = lm;
+    }
+};
+
 // bf16 pair (packed in a 32-bit word, little endian: element 0 in the low half) -> two floats
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

@@ -4,8 +4,8 @@
 // engine behind the reference's QdrantManager.search (reference src/lattice/embeddings/client.py:132-157) -
 // scores in float64 on a float32 matrix that it re-normalises IN PLACE on every cosine search
 // (oracle/qdrant_local.py, point 2).  To return bit-identical id lists this kernel
-//   1. selects the k' best fast keys out of the per-CTA lists (threshold filter + bitonic sort, with an exact
-//      8-pass radix select as the fallback when too many keys survive the threshold),
+//   1. selects the k' best fast keys out of the per-CTA lists (8 warps fold the lists into register top-k' lists
+//      with the scan's threshold-and-insert step, the 8 lists are ranked in shared memory),
 //   2. recomputes each candidate's score the way local mode does: float32 row (for bf16 storage:
 //      float32(row / ||row||_f64), i.e. what local mode would have stored), the per-search float32 in-place
 //      re-normalisation replayed `searches since the row was written` times (numpy's pair-wise float32 row
@@ -39,7 +39,7 @@ struct PwProgram {
 
 struct FinalizeParams {
     const uint64_t* keys;      // [Q][M]   fast keys (0 = empty)
-    const uint64_t* mins;      // [Q][L]   minimum of each list (L lists of M/L keys), or nullptr
+    const uint64_t* mins;      // [Q][L]   minimum of each list (unused by the merge-based selection)
     uint32_t M;
     uint32_t L;
     uint32_t kp;               // k' candidates to rescore (<= kMaxCand)
@@ -59,7 +59,9 @@ struct FinalizeParams {
     const float* qnorm;        // [Q] ||q||      } dot metric: the bound scales with ||q|| * max ||row||
     const float* max_norm;     // [1] max ||row|| }
     int64_t row_base;          // global row of local row 0
-    int n_rescore_warps;       // warps that own chain buffers
+    int n_rescore_warps;       // warps per CTA that own chain buffers
+    double* cand_scores;       // [Q][kMaxCand] scratch: exact scores exchanged between the CTAs of a query
+    uint32_t* tickets;         // [Q] zero-initialised arrival counters (reset by the last CTA)
     double* out_scores;        // [Q][k]
     int64_t* out_rows;         // [Q][k]   -1 padded
     uint64_t* out_ties;        // [Q][k]
@@ -69,10 +71,11 @@ struct FinalizeParams {
 
 __host__ __device__ inline size_t finalize_smem_bytes(int dim_pad, int n_rescore_warps) {
     size_t b = 0;
-    b += (size_t)kSortCap * 8;                    // sort buffer
-    b += 256 * 4 + 64;                            // histogram + scalars
+    b += (size_t)kSortCap * 8;                    // merged warp lists / sort buffer
+    b += 64 + ((sizeof(PwProgram) + 15) & ~(size_t)15);   // scalars + pair-wise program
     b += (size_t)kMaxCand * (8 + 8 + 8 + 4 + 4);  // cand key, score, tie, row, rank
     b = (b + 15) & ~(size_t)15;
+    b += (size_t)dim_pad * 8;                     // float64 query
     b += (size_t)n_rescore_warps * ((size_t)3 * dim_pad * 4 + kPwMaxLeaves * 4);
     return b;
 }
@@ -118,47 +121,59 @@ __device__ __forceinline__ float np_norm_f32(const float* v, const PwProgram* pw
     return __fsqrt_rn(tot);
 }
 
-// Exact score of one candidate row (warp-cooperative).  buf = 3 * dim_pad floats of shared memory.
-__device__ __forceinline__ double exact_score(const FinalizeParams& p, uint32_t row, const double* q, uint32_t search_no,
-                                              float* buf, float* leaf_out, int lane) {
+// Exact score of one candidate row (warp-cooperative).  buf = 3 * dim_pad floats of shared memory; q = the float64
+// query staged in shared memory.
+__device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwProgram* pw, uint32_t row, const double* q,
+                                              uint32_t search_no, float* buf, float* leaf_out, int lane) {
     const int D = p.dim;
     const uint8_t* rp = p.base + (size_t)row * p.row_bytes;
-    if (p.metric == LVS_METRIC_DOT) {
-        double acc = 0.0;
-        if (p.storage == LVS_STORAGE_F32) {
-            const float* x = reinterpret_cast<const float*>(rp);
-            for (int i = lane; i < D; i += 32) acc = fma((double)x[i], q[i], acc);
-        } else {
-            const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(rp);
-            for (int i = lane; i < D; i += 32) acc = fma((double)__bfloat162float(x[i]), q[i], acc);
-        }
-        return warp_sum_f64(acc);
-    }
+    const uint32_t cpr = p.row_bytes / 16;
     float* cur = buf;
     float* prev = buf + p.dim_pad;
     float* nxt = buf + 2 * p.dim_pad;
+    // stage the stored row as float32 (128-bit loads, all chunks of a lane in flight together); the padding
+    // columns of a row are zero, so they may be staged and summed as well
+    double ss = 0.0;
     if (p.storage == LVS_STORAGE_F32) {
-        const float* x = reinterpret_cast<const float*>(rp);
-        for (int i = lane; i < D; i += 32) cur[i] = x[i];
+        const uint4* src = reinterpret_cast<const uint4*>(rp);
+        for (uint32_t c = lane; c < cpr; c += 32) {
+            const uint4 v = __ldg(src + c);
+            const float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y), x2 = __uint_as_float(v.z), x3 = __uint_as_float(v.w);
+            *reinterpret_cast<float4*>(cur + 4 * c) = make_float4(x0, x1, x2, x3);
+        }
     } else {
-        // what local mode would have stored for this (bf16-representable) input: float32(x / ||x||_f64)
-        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(rp);
-        double ss = 0.0;
-        for (int i = lane; i < D; i += 32) { const double t = (double)__bfloat162float(x[i]); ss = fma(t, t, ss); }
-        ss = warp_sum_f64(ss);
-        const double nrm = sqrt(ss);
-        for (int i = lane; i < D; i += 32) {
-            const double t = (double)__bfloat162float(x[i]);
-            cur[i] = (float)(nrm > 0.0 ? t / nrm : t);
+        const uint4* src = reinterpret_cast<const uint4*>(rp);
+        for (uint32_t c = lane; c < cpr; c += 32) {
+            const uint4 v = __ldg(src + c);
+            const float x[8] = {bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y), bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w)};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const double t = (double)x[e]; ss = fma(t, t, ss); }
+            *reinterpret_cast<float4*>(cur + 8 * c) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4*>(cur + 8 * c + 4) = make_float4(x[4], x[5], x[6], x[7]);
         }
     }
     __syncwarp();
+    if (p.metric == LVS_METRIC_DOT) {
+        double acc = 0.0;
+        for (int i = lane; i < D; i += 32) acc = fma((double)cur[i], q[i], acc);
+        __syncwarp();
+        return warp_sum_f64(acc);
+    }
+    if (p.storage == LVS_STORAGE_BF16) {
+        // what local mode would have stored for this (bf16-representable) input: float32(x / ||x||_f64)
+        ss = warp_sum_f64(ss);
+        const double nrm = sqrt(ss);
+        if (nrm > 0.0) {
+            for (int i = lane; i < D; i += 32) cur[i] = (float)((double)cur[i] / nrm);
+        }
+        __syncwarp();
+    }
     // replay of the per-search in-place re-normalisation
     uint32_t count = search_no - p.epoch[row];          // searches run since the row was written, this one included
     if (count > 64u) count = 64u + ((count - 64u) & 1u);
     bool have_prev = false;
     for (uint32_t j = 1; j <= count; ++j) {
-        const float n = np_norm_f32(cur, p.pw, leaf_out, lane);
+        const float n = np_norm_f32(cur, pw, leaf_out, lane);
         if (n == 1.0f) break;                            // fixed point
         const float d = (n != 0.0f) ? n : 1.1920929e-7f;
         bool same_cur = true, same_prev = true;
@@ -201,12 +216,18 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* buf, int n, int tid)
     }
 }
 
+// grid = (queries of the group, C).  Every CTA of a query repeats the (cheap, deterministic) selection, rescoring is
+// split over the C CTAs (one candidate per warp), and the last CTA to finish (atomic ticket) orders and emits.
+// Selection: each of the 8 warps folds its share of the L per-CTA lists into a register top-(32*KPL) with the same
+// threshold-and-insert step the scan uses; the 8 warp lists (<= 2048 keys) are then ranked in shared memory.
+template <int KPL>
 __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinalizeParams p) {
+    constexpr uint32_t KPW = 32u * KPL;
     extern __shared__ __align__(16) uint8_t fsm[];
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(fsm);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(fsm + (size_t)kSortCap * 8);
-    uint32_t* scal = hist + 256;                       // [0]=survivor count [1]=digit [2]=remaining [4..5]=T
-    uint8_t* cp = reinterpret_cast<uint8_t*>(scal + 16);
+    uint32_t* scal = reinterpret_cast<uint32_t*>(fsm + (size_t)kSortCap * 8);   // [3]=is_last
+    PwProgram* pws = reinterpret_cast<PwProgram*>(scal + 16);
+    uint8_t* cp = reinterpret_cast<uint8_t*>(pws) + ((sizeof(PwProgram) + 15) & ~(size_t)15);
     uint64_t* ckey = reinterpret_cast<uint64_t*>(cp);  cp += (size_t)kMaxCand * 8;
     double* cscore = reinterpret_cast<double*>(cp);    cp += (size_t)kMaxCand * 8;
     uint64_t* ctie = reinterpret_cast<uint64_t*>(cp);  cp += (size_t)kMaxCand * 8;
@@ -214,109 +235,116 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     uint32_t* crank = reinterpret_cast<uint32_t*>(cp); cp += (size_t)kMaxCand * 4;
     size_t off = (size_t)(cp - fsm);
     off = (off + 15) & ~(size_t)15;
+    double* qs = reinterpret_cast<double*>(fsm + off);
+    off += (size_t)p.dim_pad * 8;
     float* chain = reinterpret_cast<float*>(fsm + off);
     const size_t per_warp = (size_t)3 * p.dim_pad + kPwMaxLeaves;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t qi = blockIdx.x;
+    const uint32_t C = gridDim.y;
     const uint64_t* keys = p.keys + (size_t)qi * p.M;
-    const uint32_t kp = p.kp;
+    const uint32_t kp = p.kp;                            // == KPW
 
-    // ---- 1. threshold T = max over lists of the list minimum (>= kp keys are >= T when lists are full) ----
-    unsigned long long* Tp = reinterpret_cast<unsigned long long*>(scal + 4);
-    if (tid == 0) { scal[0] = 0; *Tp = 0ull; }
-    __syncthreads();
-    if (p.mins != nullptr && (p.M / p.L) >= kp) {
-        uint64_t t = 0;
-        for (uint32_t i = tid; i < p.L; i += kFinThreads) { const uint64_t v = p.mins[(size_t)qi * p.L + i]; t = v > t ? v : t; }
+    // stage the float64 query and the pair-wise program while the lists stream in
+    const double* qg = p.q64 + (size_t)qi * p.dim;
+    for (int i = tid; i < p.dim; i += kFinThreads) qs[i] = qg[i];
+    for (int i = tid; i < (int)(sizeof(PwProgram) / 4); i += kFinThreads)
+        reinterpret_cast<uint32_t*>(pws)[i] = reinterpret_cast<const uint32_t*>(p.pw)[i];
+
+    // ---- 1. per-warp fold of the lists ----
+    WarpTopK<KPL> acc;
+    acc.init();
+    uint64_t nxt[KPL];
+    uint32_t l = warp;
+    if (l < p.L) {
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) { const uint64_t v = shfl_xor_u64(t, o); t = v > t ? v : t; }
-        if (lane == 0) atomicMax(Tp, (unsigned long long)t);
+        for (int j = 0; j < KPL; ++j) nxt[j] = keys[(size_t)l * KPW + j * 32 + lane];
     }
-    __syncthreads();
-    uint64_t T = *Tp;
-    if (T == 0) T = 1;                                  // keep every non-empty key
-    // ---- 2. gather survivors ----
-    for (uint32_t i = tid; i < p.M; i += kFinThreads) {
-        const uint64_t v = keys[i];
-        if (v >= T) {
-            const uint32_t pos = atomicAdd(&scal[0], 1u);
-            if (pos < (uint32_t)kSortCap) sortbuf[pos] = v;
+    while (l < p.L) {
+        uint64_t cur[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) cur[j] = nxt[j];
+        const uint32_t ln = l + kFinWarps;
+        if (ln < p.L) {
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) nxt[j] = keys[(size_t)ln * KPW + j * 32 + lane];
         }
-    }
-    __syncthreads();
-    uint32_t nsurv = scal[0];
-    __syncthreads();
-    if (nsurv > (uint32_t)kSortCap) {
-        // ---- fallback: exact radix select of the kp-th largest key, then gather keys >= it ----
-        uint64_t prefix = 0, mask = 0;
-        uint32_t remaining = kp;
-        for (int pass = 0; pass < 8; ++pass) {
-            const int shift = 56 - 8 * pass;
-            hist[tid] = 0;
-            __syncthreads();
-            for (uint32_t i = tid; i < p.M; i += kFinThreads) {
-                const uint64_t v = keys[i];
-                if (v != 0 && (v & mask) == prefix) atomicAdd(&hist[(uint32_t)(v >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t cum = 0; int digit = 0; uint32_t rem = remaining;
-                for (int b = 255; b >= 0; --b) {
-                    if (cum + hist[b] >= rem) { digit = b; rem -= cum; break; }
-                    cum += hist[b];
-                    if (b == 0) { digit = 0; rem = 0; }   // fewer than kp keys in total
-                }
-                scal[1] = (uint32_t)digit; scal[2] = rem;
-            }
-            __syncthreads();
-            prefix |= (uint64_t)scal[1] << shift;
-            mask |= 0xFFull << shift;
-            remaining = scal[2];
-            __syncthreads();
-            if (remaining == 0) { prefix = 1; break; }
-        }
-        if (tid == 0) scal[0] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < p.M; i += kFinThreads) {
-            const uint64_t v = keys[i];
-            if (v != 0 && v >= prefix) {
-                const uint32_t pos = atomicAdd(&scal[0], 1u);
-                if (pos < (uint32_t)kSortCap) sortbuf[pos] = v;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            uint32_t ball = __ballot_sync(0xFFFFFFFFu, cur[j] > acc.thr);
+            while (ball) {
+                const int src = __ffs(ball) - 1;
+                ball &= ball - 1;
+                const uint64_t kk = shfl_u64(cur[j], src);
+                if (kk > acc.thr) acc.insert(kk, lane);
             }
         }
-        __syncthreads();
-        nsurv = min(scal[0], (uint32_t)kSortCap);
-        __syncthreads();
+        l = ln;
     }
-    // ---- 3. sort survivors, keep kp ----
-    int n2 = 32;
-    while (n2 < (int)nsurv) n2 <<= 1;
-    for (int i = nsurv + tid; i < n2; i += kFinThreads) sortbuf[i] = 0ull;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) sortbuf[(size_t)warp * KPW + j * 32 + lane] = acc.key[j];
     __syncthreads();
-    bitonic_sort_desc(sortbuf, n2, tid);
+    // ---- 2. rank the 8*KPW merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
+    const uint32_t nmerged = kFinWarps * KPW;
+    if (tid == 0) scal[0] = 0;
+    __syncthreads();
+    {
+        uint32_t nz = 0;
+        for (uint32_t i = tid; i < nmerged; i += kFinThreads) nz += sortbuf[i] != 0ull ? 1u : 0u;
+        for (int o = 16; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
+        if (lane == 0 && nz) atomicAdd(&scal[0], nz);
+    }
+    __syncthreads();
+    const uint32_t nsurv = scal[0];
     const uint32_t ncand = min(nsurv, kp);
-    // the fast-score bound for every row that is NOT a candidate
-    const bool lists_dropped_nothing = nsurv < kp;      // fewer keys than k' in total => no list ever overflowed
-    const float t_fast = ncand > 0 ? key_score(sortbuf[ncand - 1]) : 0.f;
-    for (uint32_t c = tid; c < ncand; c += kFinThreads) {
-        const uint64_t kk = sortbuf[c];
-        ckey[c] = kk;
-        const uint32_t r = key_row(kk);
-        crow[c] = r;
-        ctie[c] = p.tiekey[r];
+    if (nmerged <= 512u) {
+        for (uint32_t i = tid; i < nmerged; i += kFinThreads) {
+            const uint64_t v = sortbuf[i];
+            if (v == 0ull) continue;
+            uint32_t rank = 0;
+            for (uint32_t o = 0; o < nmerged; ++o) rank += sortbuf[o] > v ? 1u : 0u;
+            if (rank < kp) ckey[rank] = v;
+        }
+        __syncthreads();
+    } else {
+        bitonic_sort_desc(sortbuf, (int)nmerged, tid);
+        for (uint32_t c = tid; c < ncand; c += kFinThreads) ckey[c] = sortbuf[c];
+        __syncthreads();
     }
-    __syncthreads();
-    // ---- 4. exact rescoring ----
-    const double* q = p.q64 + (size_t)qi * p.dim;
-    if (warp < p.n_rescore_warps) {
+    // the fast-score bound for every row that is NOT a candidate
+    const bool lists_dropped_nothing = nsurv < kp;      // fewer keys than k' survive => no list ever overflowed
+    const float t_fast = ncand > 0 ? key_score(ckey[ncand - 1]) : 0.f;
+    // ---- 4. exact rescoring: candidate c belongs to CTA c / nrw, warp c % nrw ----
+    const uint32_t nrw = (uint32_t)p.n_rescore_warps;
+    double* gscore = p.cand_scores + (size_t)qi * kMaxCand;
+    if ((uint32_t)warp < nrw) {
         float* buf = chain + (size_t)warp * per_warp;
         float* leaf_out = buf + (size_t)3 * p.dim_pad;
-        for (uint32_t c = warp; c < ncand; c += p.n_rescore_warps) {
-            const double s = exact_score(p, crow[c], q, p.search_no + qi, buf, leaf_out, lane);
-            if (lane == 0) cscore[c] = s;
+        for (uint32_t c = blockIdx.y * nrw + warp; c < ncand; c += C * nrw) {
+            const double s = exact_score(p, pws, key_row(ckey[c]), qs, p.search_no + qi, buf, leaf_out, lane);
+            if (lane == 0) gscore[c] = s;
         }
     }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t last = 1;
+        if (C > 1) {
+            __threadfence();
+            last = (atomicAdd(p.tickets + qi, 1u) == C - 1) ? 1u : 0u;
+        }
+        scal[3] = last;
+    }
+    __syncthreads();
+    if (scal[3] == 0) return;
+    __threadfence();
+    for (uint32_t c = tid; c < ncand; c += kFinThreads) {
+        const uint32_t r = key_row(ckey[c]);
+        crow[c] = r;
+        ctie[c] = p.tiekey[r];
+        cscore[c] = __ldcg(gscore + c);
+    }
+    if (tid == 0 && C > 1) p.tickets[qi] = 0;            // ready for the next launch
     __syncthreads();
     // ---- 5. final order: (score desc, tie asc, row asc) by rank counting ----
     for (uint32_t c = tid; c < ncand; c += kFinThreads) {

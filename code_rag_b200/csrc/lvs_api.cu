@@ -77,6 +77,9 @@ static int ensure_pinned(Scratch& s, size_t bytes) {
     return LVS_OK;
 }
 
+constexpr int kEventRing = 256;
+constexpr int kSubmitSlots = 4;
+
 struct lvs_collection {
     std::string name;
     int dim = 0;
@@ -107,10 +110,29 @@ struct lvs_collection {
     int last_launches = 0;
     int last_kind = 0;
 
-    Scratch s_qraw, s_q64, s_q32, s_qnorm, s_keys, s_mins, s_flags, s_res, s_stage_dev, s_misc;
-    Scratch h_pin, h_pin2;
+    Scratch s_qraw, s_q64, s_q32, s_qnorm, s_keys, s_mins, s_flags, s_res, s_stage_dev, s_misc, s_cand;
+    Scratch h_pin, h_pin2, h_flags;
 
-    int opt_stage_kb = 32;
+    // ring of event pairs around the scan launches (read back by lvs_scan_times after a synchronisation)
+    cudaEvent_t ring_ev[2 * kEventRing] = {nullptr};
+    double ring_bytes[kEventRing] = {0};
+    uint64_t ring_pos = 0;
+    cudaEvent_t first_scan_start = nullptr, first_scan_end = nullptr;
+    int opt_timing = 1;
+    int last_kpl = 0;
+
+    // pipelined host API (lvs_search_submit / lvs_search_wait)
+    struct Slot {
+        bool in_use = false;
+        int Q = 0, k = 0, dtype = 0, kpl = 0;
+        uint32_t base = 0;
+        bool has_want = false;
+        uint32_t want[kMaxFilterCols];
+        Scratch h, d_q, d_res;
+        cudaEvent_t done = nullptr;
+    } slots[kSubmitSlots];
+
+    int opt_stage_kb = 64;
     int opt_stages = 0;   // 0 = as many as fit
     int opt_grid = 0;     // 0 = one CTA per SM
     int opt_force_kpl = 0;
@@ -260,6 +282,7 @@ extern "C" int lvs_collection_create(const char* name, int dim, int storage, int
     c->q_stride = (uint32_t)ld;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 2 * kEventRing && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ring_ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_max_norm, 4);
     if (e == cudaSuccess) e = cudaMemset(c->d_max_norm, 0, 4);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 64);
@@ -290,6 +313,15 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     if (c->h_pin.p) cudaFreeHost(c->h_pin.p);
     if (c->h_pin2.p) cudaFreeHost(c->h_pin2.p);
     for (int i = 0; i < 6; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2 * kEventRing; ++i) if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
+    if (c->s_cand.p) cudaFree(c->s_cand.p);
+    for (auto& sl : c->slots) {
+        if (sl.h.p) cudaFreeHost(sl.h.p);
+        if (sl.d_q.p) cudaFree(sl.d_q.p);
+        if (sl.d_res.p) cudaFree(sl.d_res.p);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (c->h_flags.p) cudaFreeHost(c->h_flags.p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return LVS_OK;
@@ -568,6 +600,18 @@ static cudaError_t launch_scan(const lvs_collection* c, int qt, int kpl, bool fi
                   : launch_scan_tnf<__nv_bfloat16, false, false>(qt, kpl, p, grid, smem, st);
 }
 
+template <int KPL>
+static cudaError_t launch_finalize(const FinalizeParams& fp, int nq, unsigned ncta, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(finalize_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    finalize_kernel<KPL><<<dim3((unsigned)nq, ncta), kFinThreads, smem, st>>>(fp);
+    return cudaGetLastError();
+}
+
 static int max_qt_for_kpl(int kpl) { return kpl >= 8 ? 1 : kpl >= 4 ? 2 : 4; }
 
 struct ScanGeom {
@@ -595,9 +639,99 @@ static int scan_geometry(const lvs_collection* c, int qt, bool filter, ScanGeom*
     return fail(LVS_ELIMIT, "dim %d does not fit the scan's shared-memory ring", c->dim);
 }
 
-// Core: queries already on the device (raw, `dtype`); outputs are device buffers.
+// Enqueue one level of the search for the query indices in `pending` (ascending): scan + finalize per group of up to
+// max_qt consecutive queries.  No synchronisation.
+static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int k, int kpl, bool filter, const uint32_t* const* fcodes,
+                         const uint32_t* fwant, uint32_t nf, uint32_t search_base, double* d_scores, int64_t* d_rows,
+                         uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches, bool time_first) {
+    const int sm = g_lib.sm_count;
+    double* q64 = (double*)c->s_q64.p;
+    float* q32 = (float*)c->s_q32.p;
+    float* qnorm = (float*)c->s_qnorm.p;
+    uint64_t* keys = (uint64_t*)c->s_keys.p;
+    uint64_t* mins = (uint64_t*)c->s_mins.p;
+    const int chain = (int)((c->chunks_per_row + 31) / 32) * (c->storage == LVS_STORAGE_F32 ? 4 : 8);
+    const float eps_rel = (float)(chain + 12) * 1.1920929e-7f;
+    const int max_qt = max_qt_for_kpl(kpl);
+    int rc;
+    size_t i = 0;
+    bool first_group = time_first;
+    while (i < pending.size()) {
+        // a group = up to max_qt CONSECUTIVE query indices; kernels exist for 1, 2 and 4 query slots
+        // (a 3-query group runs the 4-slot kernel, whose last slot scores an all-zero query and is ignored)
+        const int first = pending[i];
+        int cnt = 1;
+        while (cnt < max_qt && i + cnt < pending.size() && pending[i + cnt] == first + cnt) ++cnt;
+        const int qt_use = cnt == 1 ? 1 : cnt == 2 ? 2 : 4;
+        ScanGeom g;
+        if ((rc = scan_geometry(c, qt_use, filter, &g)) != LVS_OK) return rc;
+        ScanParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.base = c->d_vec; sp.row_bytes = c->row_bytes; sp.chunks_per_row = c->chunks_per_row;
+        sp.n_rows = (uint32_t)c->n_rows; sp.stage_rows = g.stage_rows; sp.n_stages = g.n_stages; sp.stage_bytes = g.stage_bytes;
+        sp.n_tiles = (uint32_t)((c->n_rows + g.stage_rows - 1) / g.stage_rows);
+        sp.n_blocks32 = (uint32_t)((c->n_rows + 31) / 32);
+        sp.queries = q32 + (size_t)first * c->q_stride; sp.q_stride = c->q_stride;
+        sp.live = c->d_live;
+        for (uint32_t f = 0; f < nf; ++f) { sp.codes[f] = fcodes[f]; sp.want[f] = fwant[f]; }
+        sp.n_filter = nf;
+        sp.out_keys = keys; sp.out_mins = mins;
+        int grid = c->opt_grid > 0 ? c->opt_grid : sm;
+        const uint32_t units = filter ? sp.n_blocks32 : sp.n_tiles;
+        grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, units));
+        cudaEvent_t es = nullptr, ee = nullptr;
+        if (c->opt_timing) {
+            const int slot = c->ring_pos % kEventRing;
+            es = c->ring_ev[2 * slot]; ee = c->ring_ev[2 * slot + 1];
+            c->ring_bytes[slot] = (double)c->n_rows * c->row_bytes;
+            c->ring_pos++;
+            CU(cudaEventRecord(es, st));
+        }
+        cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, grid, g.smem, st);
+        if (e != cudaSuccess) return fail(LVS_ECUDA, "scan kernel launch failed: %s (qt=%d kpl=%d smem=%zu)", cudaGetErrorString(e), qt_use, kpl, g.smem);
+        ++*launches;
+        if (c->opt_timing) CU(cudaEventRecord(ee, st));
+        if (first_group) { c->first_scan_start = es; c->first_scan_end = ee; }
+
+        FinalizeParams fp;
+        memset(&fp, 0, sizeof(fp));
+        const uint32_t kpw = 32u * kpl;
+        fp.keys = keys; fp.mins = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid; fp.kp = kpw; fp.k = (uint32_t)k;
+        fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
+        fp.storage = c->storage; fp.metric = c->metric;
+        fp.q64 = q64 + (size_t)first * c->dim;
+        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)first;
+        fp.pw = c->d_pw; fp.eps = eps_rel; fp.row_base = c->row_base;
+        int nrw = kFinWarps;
+        while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
+        if (finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) return fail(LVS_ELIMIT, "dim %d does not fit the rescoring buffers", c->dim);
+        fp.n_rescore_warps = nrw;
+        fp.cand_scores = (double*)c->s_cand.p; fp.tickets = c->d_counter + 12;   // 4 tickets (one per query slot)
+        fp.out_scores = d_scores + (size_t)first * k; fp.out_rows = d_rows + (size_t)first * k; fp.out_ties = d_ties + (size_t)first * k;
+        fp.out_flags = d_flags + first; fp.out_counts = d_counts + first;
+        fp.qnorm = qnorm + first; fp.max_norm = c->d_max_norm;
+        // keys of query slot s of this group live at keys + s*grid*kpw: the finalize CTA x-index is the slot
+        const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
+        const unsigned ncta = (unsigned)std::min<uint32_t>(64u, (kpw + nrw - 1) / nrw);
+        {
+            cudaError_t fe = kpl == 1 ? launch_finalize<1>(fp, cnt, ncta, fsm, st) : kpl == 2 ? launch_finalize<2>(fp, cnt, ncta, fsm, st)
+                           : kpl == 4 ? launch_finalize<4>(fp, cnt, ncta, fsm, st) : launch_finalize<8>(fp, cnt, ncta, fsm, st);
+            if (fe != cudaSuccess) return fail(LVS_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(fe));
+        }
+        ++*launches;
+        if (first_group) { if (c->opt_timing) CU(cudaEventRecord(c->ev[4], st)); first_group = false; }
+        i += cnt;
+    }
+    return LVS_OK;
+}
+
+// Core: queries already on the device (raw, `dtype`); outputs are device buffers.  With `async` the work is only
+// enqueued (no escalation, flags stay on the device in d_flags_out); otherwise flagged queries are repeated with a
+// larger candidate set and the host flags are returned.
 static int search_core(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
-                       double* d_scores, int64_t* d_rows, uint64_t* d_ties, uint32_t* d_counts, int32_t* h_flags, cudaStream_t st) {
+                       double* d_scores, int64_t* d_rows, uint64_t* d_ties, uint32_t* d_counts, int32_t* h_flags,
+                       int32_t* d_flags_out, bool async, cudaStream_t st, int64_t base_override = -1, int kpl_min = 0,
+                       const std::vector<int>* only = nullptr) {
     if (Q <= 0) return LVS_OK;
     if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
     if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
@@ -609,26 +743,21 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     if ((rc = ensure_dev(c->s_keys, (size_t)4 * sm * 256 * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_mins, (size_t)4 * sm * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_flags, (size_t)Q * 4)) != LVS_OK) return rc;
-    double* q64 = (double*)c->s_q64.p;
-    float* q32 = (float*)c->s_q32.p;
-    float* qnorm = (float*)c->s_qnorm.p;
-    uint64_t* keys = (uint64_t*)c->s_keys.p;
-    uint64_t* mins = (uint64_t*)c->s_mins.p;
-    int32_t* d_flags = (int32_t*)c->s_flags.p;
+    if ((rc = ensure_dev(c->s_cand, (size_t)4 * kMaxCand * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_pinned(c->h_flags, (size_t)Q * 4)) != LVS_OK) return rc;
+    int32_t* d_flags = d_flags_out ? d_flags_out : (int32_t*)c->s_flags.p;
 
     int launches = 0;
-    CU(cudaEventRecord(c->ev[0], st));
+    if (c->opt_timing) CU(cudaEventRecord(c->ev[0], st));
     {
         PrepParams pp;
         pp.src = d_queries; pp.src_dtype = dtype; pp.dim = c->dim; pp.metric = c->metric;
-        pp.q64 = q64; pp.q32 = q32; pp.q_stride = c->q_stride; pp.qnorm = qnorm;
-        CU(cudaMemsetAsync(q32 + (size_t)Q * c->q_stride, 0, (size_t)4 * c->q_stride * 4, st));
-        prep_queries_kernel<<<Q, 256, 0, st>>>(pp);
+        pp.q64 = (double*)c->s_q64.p; pp.q32 = (float*)c->s_q32.p; pp.q_stride = c->q_stride; pp.qnorm = (float*)c->s_qnorm.p;
+        pp.n_zero_rows = 4;
+        prep_queries_kernel<<<Q + 1, 256, 0, st>>>(pp);   // CTA Q zeroes the 4 padding query rows
         CU(cudaGetLastError());
         ++launches;
     }
-    CU(cudaEventRecord(c->ev[1], st));
-
     const uint32_t* fcodes[kMaxFilterCols];
     uint32_t fwant[kMaxFilterCols];
     uint32_t nf = 0;
@@ -638,91 +767,44 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     // candidate-set size: smallest list of 32*KPL keys that leaves a margin over k
     int kpl = 1;
     while (kpl < 8 && 32 * kpl < k + std::max(8, k / 4)) kpl <<= 1;
-    if (c->opt_force_kpl > 0) kpl = std::max(kpl, c->opt_force_kpl);
+    if (c->opt_force_kpl > 0) kpl = std::min(8, std::max(kpl, c->opt_force_kpl));
+    if (kpl_min > 0) kpl = std::min(8, std::max(kpl, kpl_min));
 
-    const int chain = (int)((c->chunks_per_row + 31) / 32) * (c->storage == LVS_STORAGE_F32 ? 4 : 8);
-    const float eps_rel = (float)(chain + 12) * 1.1920929e-7f;
-
-    std::vector<int> pending(Q);
-    for (int i = 0; i < Q; ++i) pending[i] = i;
-    std::vector<int32_t> flags(Q, 0);
-    const uint32_t search_base = c->search_counter + 1;
-    bool first_group = true;
-
+    std::vector<int> pending;
+    if (only) pending = *only;
+    else { pending.resize(Q); for (int i = 0; i < Q; ++i) pending[i] = i; }
+    const uint32_t search_base = base_override >= 0 ? (uint32_t)base_override : c->search_counter + 1;
+    int32_t* hf = (int32_t*)c->h_flags.p;
+    bool first = true;
     while (!pending.empty()) {
-        const int max_qt = max_qt_for_kpl(kpl);
-        size_t i = 0;
-        while (i < pending.size()) {
-            // a group = up to max_qt CONSECUTIVE query indices; kernels exist for 1, 2 and 4 query slots
-            // (a 3-query group runs the 4-slot kernel, whose last slot scores an all-zero query and is ignored)
-            const int first = pending[i];
-            int cnt = 1;
-            while (cnt < max_qt && i + cnt < pending.size() && pending[i + cnt] == first + cnt) ++cnt;
-            const int qt_use = cnt == 1 ? 1 : cnt == 2 ? 2 : 4;
-            ScanGeom g;
-            if ((rc = scan_geometry(c, qt_use, filter, &g)) != LVS_OK) return rc;
-            ScanParams sp;
-            memset(&sp, 0, sizeof(sp));
-            sp.base = c->d_vec; sp.row_bytes = c->row_bytes; sp.chunks_per_row = c->chunks_per_row;
-            sp.n_rows = (uint32_t)c->n_rows; sp.stage_rows = g.stage_rows; sp.n_stages = g.n_stages; sp.stage_bytes = g.stage_bytes;
-            sp.n_tiles = (uint32_t)((c->n_rows + g.stage_rows - 1) / g.stage_rows);
-            sp.n_blocks32 = (uint32_t)((c->n_rows + 31) / 32);
-            sp.queries = q32 + (size_t)first * c->q_stride; sp.q_stride = c->q_stride;
-            sp.live = c->d_live;
-            for (uint32_t f = 0; f < nf; ++f) { sp.codes[f] = fcodes[f]; sp.want[f] = fwant[f]; }
-            sp.n_filter = nf;
-            sp.out_keys = keys; sp.out_mins = mins;
-            int grid = c->opt_grid > 0 ? c->opt_grid : sm;
-            const uint32_t units = filter ? sp.n_blocks32 : sp.n_tiles;
-            grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, units));
-            if (first_group) CU(cudaEventRecord(c->ev[2], st));
-            cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, grid, g.smem, st);
-            if (e != cudaSuccess) return fail(LVS_ECUDA, "scan kernel launch failed: %s (qt=%d kpl=%d smem=%zu)", cudaGetErrorString(e), qt_use, kpl, g.smem);
-            ++launches;
-            if (first_group) CU(cudaEventRecord(c->ev[3], st));
-
-            FinalizeParams fp;
-            memset(&fp, 0, sizeof(fp));
-            const uint32_t kpw = 32u * kpl;
-            fp.keys = keys; fp.mins = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid; fp.kp = kpw; fp.k = (uint32_t)k;
-            fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (c->dim + 3) & ~3;
-            fp.storage = c->storage; fp.metric = c->metric;
-            fp.q64 = q64 + (size_t)first * c->dim;
-            fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)first;
-            fp.pw = c->d_pw; fp.eps = eps_rel; fp.row_base = c->row_base;
-            int nrw = kFinWarps;
-            while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
-            fp.n_rescore_warps = nrw;
-            fp.out_scores = d_scores + (size_t)first * k; fp.out_rows = d_rows + (size_t)first * k; fp.out_ties = d_ties + (size_t)first * k;
-            fp.out_flags = d_flags + first; fp.out_counts = d_counts + first;
-            fp.qnorm = qnorm + first; fp.max_norm = c->d_max_norm;
-            // keys of query slot s of this group live at keys + s*grid*kpw: the finalize CTA index is the slot
-            const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
-            static bool fin_attr = false;
-            if (!fin_attr) { CU(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin)); fin_attr = true; }
-            finalize_kernel<<<cnt, kFinThreads, fsm, st>>>(fp);
-            CU(cudaGetLastError());
-            ++launches;
-            if (first_group) { CU(cudaEventRecord(c->ev[4], st)); first_group = false; }
-            i += cnt;
-        }
-        CU(cudaMemcpyAsync(flags.data(), d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+        rc = enqueue_level(c, pending, k, kpl, filter, fcodes, fwant, nf, search_base, d_scores, d_rows, d_ties, d_counts,
+                           d_flags, st, &launches, first);
+        if (rc != LVS_OK) return rc;
+        first = false;
+        if (async) break;
+        CU(cudaMemcpyAsync(hf, d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         std::vector<int> next;
-        for (int qi : pending) if ((flags[qi] & 1) && kpl < 8) next.push_back(qi);
+        for (int qi : pending) if ((hf[qi] & 1) && kpl < 8) next.push_back(qi);
         pending.swap(next);
         if (!pending.empty()) kpl <<= 1;
     }
-    CU(cudaEventRecord(c->ev[5], st));
-    CU(cudaEventSynchronize(c->ev[5]));
-    cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&c->last_ms[2], c->ev[3], c->ev[4]);
-    cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[5]);
     c->last_launches = launches;
     c->last_kind = 1;
-    if (h_flags) memcpy(h_flags, flags.data(), (size_t)Q * 4);
-    c->search_counter += (uint32_t)Q;
+    c->last_kpl = kpl;
+    if (base_override < 0) c->search_counter += (uint32_t)Q;
+    if (!async) {
+        if (c->opt_timing) {
+            CU(cudaEventRecord(c->ev[5], st));
+            CU(cudaEventSynchronize(c->ev[5]));
+            c->last_ms[0] = 0.f;
+            if (c->first_scan_start) cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->first_scan_start);
+            if (c->first_scan_start) cudaEventElapsedTime(&c->last_ms[1], c->first_scan_start, c->first_scan_end);
+            if (c->first_scan_end) cudaEventElapsedTime(&c->last_ms[2], c->first_scan_end, c->ev[4]);
+            cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[5]);
+        }
+        if (h_flags) memcpy(h_flags, hf, (size_t)Q * 4);
+    }
     return LVS_OK;
 }
 
@@ -750,7 +832,7 @@ extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int
     int64_t* dr = (int64_t*)(rp + nres * 8);
     uint64_t* dt = (uint64_t*)(rp + nres * 16);
     uint32_t* dc = (uint32_t*)(rp + nres * 24);
-    rc = search_core(c, c->s_qraw.p, dtype, Q, k, want, ds, dr, dt, dc, out_flags, st);
+    rc = search_core(c, c->s_qraw.p, dtype, Q, k, want, ds, dr, dt, dc, out_flags, nullptr, false, st);
     if (rc != LVS_OK) return rc;
     CU(cudaMemcpyAsync(c->h_pin2.p, rp, rbytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -771,7 +853,117 @@ extern "C" int lvs_search_device(lvs_collection* c, const void* d_queries, int d
     if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, out_flags, st);
+    return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, out_flags, nullptr, false, st);
+}
+
+extern "C" int lvs_search_device_async(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                                       double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                                       int32_t* d_out_flags, void* stream) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (Q < 0 || (Q > 0 && (!d_queries || !d_out_scores || !d_out_rows || !d_out_ties || !d_out_counts || !d_out_flags)))
+        return fail(LVS_EINVAL, "NULL device buffer");
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, nullptr, d_out_flags, true, st);
+}
+
+// Result block layout shared by lvs_search and the submit/wait pair: scores | rows | ties (Q*k*8 each) | counts | flags
+static size_t res_bytes(int Q, int k) { return (size_t)Q * k * 24 + (size_t)Q * 8; }
+
+extern "C" int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket) {
+    if (!c || !ticket) return fail(LVS_EINVAL, "NULL argument");
+    if (Q < 1 || !queries) return fail(LVS_EINVAL, "bad queries / Q");
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
+    std::lock_guard<std::mutex> lk(c->mu);
+    int si = -1;
+    for (int i = 0; i < kSubmitSlots; ++i) if (!c->slots[i].in_use) { si = i; break; }
+    if (si < 0) return fail(LVS_ELIMIT, "%d searches already in flight: call lvs_search_wait first", kSubmitSlots);
+    auto& sl = c->slots[si];
+    const size_t qbytes = (size_t)Q * c->dim * dt_size(dtype);
+    const size_t rbytes = res_bytes(Q, k);
+    int rc;
+    if ((rc = ensure_pinned(sl.h, std::max(qbytes, rbytes))) != LVS_OK) return rc;
+    if ((rc = ensure_dev(sl.d_q, qbytes)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(sl.d_res, rbytes)) != LVS_OK) return rc;
+    if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    cudaStream_t st = c->stream;
+    memcpy(sl.h.p, queries, qbytes);
+    CU(cudaMemcpyAsync(sl.d_q.p, sl.h.p, qbytes, cudaMemcpyHostToDevice, st));
+    const size_t nres = (size_t)Q * k;
+    uint8_t* rp = (uint8_t*)sl.d_res.p;
+    sl.Q = Q; sl.k = k; sl.dtype = dtype; sl.base = c->search_counter + 1;
+    sl.has_want = want != nullptr;
+    if (want) memcpy(sl.want, want, sizeof(uint32_t) * kMaxFilterCols);
+    rc = search_core(c, sl.d_q.p, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
+                     (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st);
+    if (rc != LVS_OK) return rc;
+    sl.kpl = c->last_kpl;
+    // the H2D staging area is free once the copy above has executed, which precedes this D2H in stream order
+    CU(cudaMemcpyAsync(sl.h.p, rp, rbytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(sl.done, st));
+    sl.in_use = true;
+    *ticket = si;
+    return LVS_OK;
+}
+
+extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
+                               uint32_t* out_counts, int32_t* out_flags) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (ticket < 0 || ticket >= kSubmitSlots) return fail(LVS_EINVAL, "bad ticket %d", ticket);
+    cudaEvent_t done;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->slots[ticket].in_use) return fail(LVS_EINVAL, "ticket %d is not in flight", ticket);
+        done = c->slots[ticket].done;
+    }
+    CU(cudaEventSynchronize(done));   // outside the lock: other threads may submit meanwhile
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto& sl = c->slots[ticket];
+    const int Q = sl.Q, k = sl.k;
+    const size_t nres = (size_t)Q * k;
+    uint8_t* hp = (uint8_t*)sl.h.p;
+    int32_t* hflags = (int32_t*)(hp + nres * 24 + (size_t)Q * 4);
+    std::vector<int> redo;
+    for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && sl.kpl < 8) redo.push_back(i);
+    if (!redo.empty()) {
+        // rare: repeat the flagged queries with larger candidate sets, as the same reference searches (same numbers)
+        uint8_t* rp = (uint8_t*)sl.d_res.p;
+        std::vector<int32_t> f2(Q, 0);
+        int rc = search_core(c, sl.d_q.p, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
+                             (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
+                             (int64_t)sl.base, sl.kpl * 2, &redo);
+        if (rc != LVS_OK) { sl.in_use = false; return rc; }
+        CU(cudaMemcpyAsync(hp, rp, nres * 24 + (size_t)Q * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int i : redo) hflags[i] = f2[i];
+    }
+    if (out_scores) memcpy(out_scores, hp, nres * 8);
+    if (out_rows) memcpy(out_rows, hp + nres * 8, nres * 8);
+    if (out_ties) memcpy(out_ties, hp + nres * 16, nres * 8);
+    if (out_counts) memcpy(out_counts, hp + nres * 24, (size_t)Q * 4);
+    if (out_flags) memcpy(out_flags, hflags, (size_t)Q * 4);
+    sl.in_use = false;
+    return LVS_OK;
+}
+
+extern "C" int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n) {
+    if (!c || !out_ms || !n) return fail(LVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const uint64_t have = std::min<uint64_t>(c->ring_pos, (uint64_t)kEventRing);
+    const int cnt = (int)std::min<uint64_t>(have, (uint64_t)std::max(0, max_n));
+    for (int i = 0; i < cnt; ++i) {
+        const int slot = (int)((c->ring_pos - cnt + i) % kEventRing);
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, c->ring_ev[2 * slot], c->ring_ev[2 * slot + 1]);
+        if (e != cudaSuccess) return fail(LVS_ECUDA, "scan events not complete (synchronise the stream first): %s", cudaGetErrorString(e));
+        out_ms[i] = ms;
+        if (out_bytes) out_bytes[i] = c->ring_bytes[slot];
+    }
+    *n = cnt;
+    return LVS_OK;
 }
 
 extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const uint64_t* d_ties, int64_t shard_stride,
@@ -790,7 +982,6 @@ extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_ro
     if (smem > 40 * 1024) CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_topk_kernel<<<Q, 256, smem, st>>>(p);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
     return LVS_OK;
 }
 
@@ -812,6 +1003,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "stages")) c->opt_stages = value;
     else if (!strcmp(name, "grid")) c->opt_grid = value;
     else if (!strcmp(name, "force_kpl")) c->opt_force_kpl = value;
+    else if (!strcmp(name, "timing")) c->opt_timing = value ? 1 : 0;
     else return fail(LVS_EINVAL, "unknown option '%s'", name);
     return LVS_OK;
 }

@@ -70,42 +70,6 @@ __device__ __forceinline__ void warp_reduce_transposed(float (&vals)[V], int lan
     for (; off >= 1; off >>= 1) vals[0] += __shfl_xor_sync(0xFFFFFFFFu, vals[0], off);
 }
 
-template <int KPL>
-struct WarpTopK {
-    uint64_t key[KPL];
-    uint64_t thr;   // current minimum over the 32*KPL slots (warp-uniform)
-
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) key[j] = 0ull;
-        thr = 0ull;
-    }
-    // warp-uniform call: replace the current minimum by k (k > thr) and recompute the minimum
-    __device__ __forceinline__ void insert(uint64_t k, int lane) {
-        bool has = false;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) has |= (key[j] == thr);
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-        const int owner = __ffs(m) - 1;
-        if (lane == owner) {
-            bool done = false;
-#pragma unroll
-            for (int j = 0; j < KPL; ++j) {
-                if (!done && key[j] == thr) { key[j] = k; done = true; }
-            }
-        }
-        uint64_t lm = key[0];
-#pragma unroll
-        for (int j = 1; j < KPL; ++j) lm = key[j] < lm ? key[j] : lm;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            uint64_t other = shfl_xor_u64(lm, o);
-            lm = other < lm ? other : lm;
-        }
-        thr = lm;
-    }
-};
-
 template <typename T> struct ChunkTraits;
 template <> struct ChunkTraits<float> { static constexpr int kElems = 4; };
 template <> struct ChunkTraits<__nv_bfloat16> { static constexpr int kElems = 8; };
@@ -133,8 +97,9 @@ __host__ __device__ inline size_t scan_smem_bytes(uint32_t n_stages, uint32_t st
     if (filtered) b += (size_t)n_stages * (stage_rows + 4) * 4;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)2 * n_stages * 8;
-    b += (size_t)kScanConsumerWarps * 32 * 8 * 8;  // merge scratch: up to 8 warps * (32*KPL<=256) keys, per query pass
-    return b;
+    // the epilogue's merge scratch (8 warps * 32*KPL <= 256 keys * 8 B = 16 KB) aliases the stage ring
+    const size_t merge = (size_t)kScanConsumerWarps * 32 * 8 * 8;
+    return b > merge ? b : merge;
 }
 
 template <typename T, int QT, int KPL, bool NORM, bool FILTER>
@@ -157,7 +122,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     off = (off + 15) & ~(size_t)15;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + off);
     uint64_t* empty_bar = full_bar + S;
-    uint64_t* merge_buf = empty_bar + S;                                // [8 warps][KPW]
+    uint64_t* merge_buf = reinterpret_cast<uint64_t*>(smem);            // [8 warps][KPW], aliases the (drained) stage ring
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;

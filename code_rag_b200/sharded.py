@@ -40,11 +40,17 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self._bufs: dict[tuple[int, int], tuple] = {}
+        self._bufs: dict[tuple, tuple] = {}
+        self._flag_bufs: dict[tuple, object] = {}
+        self._io_bufs: dict[tuple, tuple] = {}
         self.merge_launches = 0
+        # all device work of this searcher is ordered on one side stream (a real handle, never the legacy stream 0)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.n_slots = 4
+        self._next_slot = 0
 
-    def _buffers(self, Q: int, k: int):
-        key = (Q, k)
+    def _buffers(self, Q: int, k: int, slot: int = 0):
+        key = (Q, k, slot)
         if key not in self._bufs:
             t = self.torch
             local = t.zeros((3, Q, k), dtype=t.int64, device=self.device)
@@ -54,6 +60,29 @@ class ShardedSearcher:
             out_counts = t.zeros(Q, dtype=t.int32, device=self.device)
             self._bufs[key] = (local, counts, gathered, out, out_counts)
         return self._bufs[key]
+
+    def search_device_async(self, dq, k: int, want=None, slot: int = 0):
+        """Enqueue-only variant for pipelined callers: no host synchronisation, flags stay on the device.  `slot`
+        selects one of several result buffers so that consecutive searches do not overwrite each other.  Returns
+        (scores, rows, ties, counts, flags, packed) where packed is the [3, Q, k] int64 block holding the first three.
+        Call it under ``torch.cuda.stream(searcher.stream)`` (or any non-default stream)."""
+        t = self.torch
+        Q = int(dq.shape[0])
+        local, counts, gathered, out, out_counts = self._buffers(Q, k, slot)
+        flags = self._flag_bufs.setdefault((Q, slot), t.zeros(Q, dtype=t.int32, device=self.device))
+        stream = t.cuda.current_stream().cuda_stream
+        qd = "f64" if dq.dtype == t.float64 else "f32"
+        self.shard.search_device_async(dq.data_ptr(), qd, Q, k, want, local[0].data_ptr(), local[1].data_ptr(),
+                                       local[2].data_ptr(), counts.data_ptr(), flags.data_ptr(), stream)
+        if self.world == 1:
+            return local[0].view(t.float64), local[1], local[2], counts, flags, local
+        self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
+        n = Q * k
+        base = gathered.data_ptr()
+        merge_topk_device(base, base + 8 * n, base + 16 * n, self.world, Q, k, out[0].data_ptr(), out[1].data_ptr(),
+                          out[2].data_ptr(), out_counts.data_ptr(), stream, shard_stride=3 * n)
+        self.merge_launches += 1
+        return out[0].view(t.float64), out[1], out[2], out_counts, flags, out
 
     def search_device(self, dq, k: int, want=None):
         """dq: CUDA tensor [Q, dim] float32/float64 (same on every rank).  Returns CUDA tensors
@@ -75,13 +104,40 @@ class ShardedSearcher:
         self.merge_launches += 1
         return out[0].view(t.float64), out[1], out[2], out_counts, flags
 
-    def search(self, queries: np.ndarray, k: int, want=None):
-        """Host entry: pinned H2D of the queries, sharded search, D2H of the merged result."""
+    # ---- host entry points ----------------------------------------------------------------------------
+    def submit(self, queries: np.ndarray, k: int, want=None):
+        """Pipelined host entry: pinned H2D of the queries, sharded search, D2H of the merged result, all enqueued
+        on the searcher's stream.  Returns a handle for :meth:`wait`; up to ``n_slots`` may be in flight."""
         t = self.torch
         q = np.ascontiguousarray(queries, dtype=np.float64)
         if q.ndim == 1:
             q = q[None, :]
-        hq = t.from_numpy(q).pin_memory()
-        dq = hq.to(self.device, non_blocking=True)
-        s, r, ti, c, flags = self.search_device(dq, k, want)
-        return s.cpu().numpy(), r.cpu().numpy(), ti.cpu().numpy(), c.cpu().numpy(), flags
+        Q, dim = q.shape
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % self.n_slots
+        key = (Q, k, dim, slot)
+        if key not in self._io_bufs:
+            self._io_bufs[key] = (
+                t.empty((Q, dim), dtype=t.float64).pin_memory(), t.empty((Q, dim), dtype=t.float64, device=self.device),
+                t.empty((3, Q, k), dtype=t.int64).pin_memory(), t.empty(Q, dtype=t.int32).pin_memory(),
+                t.empty(Q, dtype=t.int32).pin_memory(), t.cuda.Event())
+        hq, dq, h_out, h_counts, h_flags, ev = self._io_bufs[key]
+        hq.numpy()[...] = q
+        with t.cuda.stream(self.stream):
+            dq.copy_(hq, non_blocking=True)
+            s, r, ti, c, flags, packed = self.search_device_async(dq, k, want, slot)
+            h_out.copy_(packed, non_blocking=True)
+            h_counts.copy_(c, non_blocking=True)
+            h_flags.copy_(flags, non_blocking=True)
+            ev.record(self.stream)
+        return key
+
+    def wait(self, handle):
+        hq, dq, h_out, h_counts, h_flags, ev = self._io_bufs[handle]
+        ev.synchronize()
+        o = h_out.numpy()
+        return o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy(), h_counts.numpy().copy(), h_flags.numpy().copy()
+
+    def search(self, queries: np.ndarray, k: int, want=None):
+        """Synchronous host entry (one search at a time)."""
+        return self.wait(self.submit(queries, k, want))

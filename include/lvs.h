@@ -91,11 +91,23 @@ int lvs_delete_where(lvs_collection* c, const uint32_t* want, int64_t* out_rows,
  * (score desc, tie asc, row asc).  Q searches are accounted as Q consecutive reference searches. */
 int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
                double* out_scores, int64_t* out_rows, uint64_t* out_ties, uint32_t* out_counts, int32_t* out_flags);
+/* Pipelined form of lvs_search for throughput: submit copies the queries (pinned staging, async H2D), enqueues the search
+ * and the D2H of the result and returns a ticket; wait blocks until that search has finished and fills the outputs (same
+ * meaning as lvs_search, including the repeat of flagged queries).  Up to 4 searches may be in flight per collection; they
+ * execute in submission order and are accounted as consecutive reference searches. */
+int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket);
+int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
+                    uint32_t* out_counts, int32_t* out_flags);
 /* Device-pointer form used by the sharded path: queries and the four Q x k / Q outputs are DEVICE buffers, the work is
  * enqueued on `stream` (cudaStream_t, NULL = collection stream) and completed before return; flags are host. */
 int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                       double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                       int32_t* out_flags, void* stream);
+/* Enqueue-only form for pipelined callers: nothing is synchronised, flags are written to the DEVICE buffer d_out_flags
+ * and a flagged query is NOT repeated with a larger candidate set (the caller may re-issue it synchronously). */
+int lvs_search_device_async(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                            double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                            int32_t* d_out_flags, void* stream);
 /* Filter-only lookup (search with query_vector=None, scroll, count: client.py:178-202, query/context/builder.py:111-119,
  * projects/cleanup.py:41-61): all live rows matching `want` (GLOBAL rows, unordered, at most cap), *n_matched = full count. */
 int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched);
@@ -104,13 +116,16 @@ int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* out_rows, i
  * d_scores/d_rows/d_ties: G blocks of Q x k, `shard_stride` 8-byte elements apart (0 => dense, Q*k), device buffers. */
 int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const uint64_t* d_ties, int64_t shard_stride,
                           int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
-                          void* stream);
+                          void* stream);   /* enqueue only: ordered on `stream` */
 
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the collection's stream) of the kernels of the last lvs_search* call on this handle:
  * [0] query prep  [1] scan / tensor-core kernel(s)  [2] finalize  [3] whole device section; n_launches = kernels launched. */
 int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches, int* kernel_kind);
-/* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto).  Returns LVS_EINVAL for unknown names. */
+/* Device time of the last (up to max_n, <= 256) scan-kernel launches, oldest first, from CUDA events recorded on the
+ * launching stream, with the algorithmic bytes of each launch.  The stream must have been synchronised. */
+int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n);
+/* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record events, default).  Returns LVS_EINVAL for unknown names. */
 int lvs_set_option(lvs_collection* c, const char* name, int value);
 /* Copy rows back (debug / snapshots): out is n x dim float32 of the values a fresh reference collection would hold. */
 int lvs_fetch_rows_f32(lvs_collection* c, const int64_t* rows, int64_t n, float* out);

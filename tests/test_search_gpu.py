@@ -214,6 +214,57 @@ def test_odd_dimensions(lib, dim):
         dev.close()
 
 
+def test_submit_wait_pipeline(lib):
+    """lvs_search_submit / lvs_search_wait: 3 searches in flight are accounted as consecutive reference searches."""
+    x, q = synth.unit_rows(9_000, 768, seed=31, n_queries=9)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, x, [None] * len(x))
+    dev = _dev("pipe", 768)
+    dev.upsert(x.astype(np.float64))
+    inflight, got = [], []
+    for i in range(len(q)):
+        inflight.append(dev.search_submit(q[i].astype(np.float64), 10))
+        if len(inflight) == 3:
+            got.append(dev.search_wait(inflight.pop(0)))
+    while inflight:
+        got.append(dev.search_wait(inflight.pop(0)))
+    for i in range(len(q)):
+        _assert_same(got[i], 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
+    dev.close()
+
+
+def test_sharded_searcher_world1(lib):
+    """ShardedSearcher (world size 1): async device path and the pipelined host path give the oracle's answer."""
+    import torch
+    from code_rag_b200.sharded import ShardedSearcher
+    x, q = synth.unit_rows(8_000, 768, seed=32, n_queries=6)
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xb, [None] * len(xb))
+    dev = _dev("ss1", 768, storage="bf16")
+    dev.upsert(xb)
+    ss = ShardedSearcher(dev)
+    dq = torch.from_numpy(q.astype(np.float64)).cuda()
+    outs = []
+    with torch.cuda.stream(ss.stream):
+        for i in range(3):
+            s, r, t, c, f, _ = ss.search_device_async(dq[i:i + 1], 10, slot=i)
+            outs.append((s, r, c, f))
+    ss.stream.synchronize()
+    for i in range(3):
+        s, r, c, f = outs[i]
+        rows_o, scores_o = ora.search_topk_rows(q[i].astype(np.float64), 10)
+        assert np.array_equal(r.cpu().numpy()[0], rows_o)
+        assert np.abs(s.cpu().numpy()[0] - scores_o).max() <= TIGHT
+        assert int(f.sum().item()) == 0
+    hs = [ss.submit(q[i].astype(np.float64), 10) for i in range(3, 6)]
+    for i, h in zip(range(3, 6), hs):
+        s, r, t, c, f = ss.wait(h)
+        rows_o, scores_o = ora.search_topk_rows(q[i].astype(np.float64), 10)
+        assert np.array_equal(r[0], rows_o) and np.abs(s[0] - scores_o).max() <= TIGHT and f.sum() == 0
+    dev.close()
+
+
 def test_sharded_merge_equals_single(lib):
     """K5: G shards searched separately + merge == one collection (the multi-GPU path, emulated on one GPU)."""
     import torch
