@@ -75,7 +75,7 @@ def _id_sort_key(point_id: Any):
 class _HostCollection:
     """Host half of a collection: ids, payloads and the per-column value dictionaries."""
 
-    def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int):
+    def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int, dev_factory=None):
         self.name = name
         self.dim = dim
         self.columns: list[str] = list(index_fields)[: N.MAX_FILTER_COLS]
@@ -84,8 +84,10 @@ class _HostCollection:
         self.id_to_row: dict[Any, int] = {}
         self.payloads: list[dict[str, Any] | None] = []
         self.lock = threading.Lock()
-        self.dev = DeviceCollection(name, dim, storage=storage, metric="cosine", n_filter_cols=N.MAX_FILTER_COLS,
-                                    capacity=0, device=device)
+        # dev_factory exists so that the host-side bookkeeping can be unit-tested without a GPU (tests only)
+        factory = dev_factory or DeviceCollection
+        self.dev = factory(name, dim, storage=storage, metric="cosine", n_filter_cols=N.MAX_FILTER_COLS,
+                           capacity=0, device=device)
 
     # -- dictionary encoding ---------------------------------------------------------------------------
     def _encode_value(self, col: int, value: Any, create: bool) -> int:
@@ -298,7 +300,8 @@ class B200VectorStore:
     """Same constructor keywords as ``QdrantManager`` (ignored: there is no server), plus backend knobs."""
 
     def __init__(self, host: str | None = None, port: int | None = None, grpc_port: int | None = None, *,
-                 dimensions: int | None = None, storage: str | None = None, device: int | None = None):
+                 dimensions: int | None = None, storage: str | None = None, device: int | None = None,
+                 _device_factory=None):
         self._host, self._port, self._grpc_port = host, port, grpc_port
         if dimensions is None:
             dimensions = int(os.environ.get("EMBEDDING_DIMENSIONS", DEFAULT_DIMENSIONS))
@@ -310,6 +313,7 @@ class B200VectorStore:
         self._dimensions = int(dimensions)
         self._storage = storage or os.environ.get("LATTICE_B200_STORAGE", "f32")
         self._device = int(device if device is not None else os.environ.get("LOCAL_RANK", "0"))
+        self._device_factory = _device_factory
         self._connected = False
         self._collections: dict[str, _HostCollection] = {}
         self._shim = _ClientShim(self)
@@ -318,7 +322,8 @@ class B200VectorStore:
     async def connect(self) -> None:
         if not self._connected:
             try:
-                await asyncio.to_thread(N.init, self._device)
+                if self._device_factory is None:
+                    await asyncio.to_thread(N.init, self._device)
                 self._connected = True
                 logger.info("lattice-b200 vector store bound to cuda:%d", self._device)
             except Exception as e:  # noqa: BLE001
@@ -364,7 +369,8 @@ class B200VectorStore:
             for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
                 if name not in self._collections:
                     self._collections[name] = await asyncio.to_thread(
-                        _HostCollection, name, self._dimensions, self._storage, _INDEX_FIELDS[name], self._device)
+                        _HostCollection, name, self._dimensions, self._storage, _INDEX_FIELDS[name], self._device,
+                        self._device_factory)
                     logger.info(f"Created collection: {name}")
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError("Failed to create collections", cause=e)

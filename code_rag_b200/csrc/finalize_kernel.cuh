@@ -39,7 +39,7 @@ struct PwProgram {
 
 struct FinalizeParams {
     const uint64_t* keys;      // [Q][M]   fast keys (0 = empty)
-    const uint64_t* mins;      // [Q][L]   minimum of each list (unused by the merge-based selection)
+    const uint64_t* tops;      // [Q][L]   best key of each list
     uint32_t M;
     uint32_t L;
     uint32_t kp;               // k' candidates to rescore (<= kMaxCand)
@@ -252,7 +252,48 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     for (int i = tid; i < (int)(sizeof(PwProgram) / 4); i += kFinThreads)
         reinterpret_cast<uint32_t*>(pws)[i] = reinterpret_cast<const uint32_t*>(p.pw)[i];
 
-    // ---- 1. per-warp fold of the lists ----
+    // ---- 1a. fast path (L >= kp lists): the kp-th largest LIST MAXIMUM is a threshold with at least kp keys at or
+    //          above it (the kp maxima themselves) and, for well-mixed shards, few more; gather those keys.
+    bool folded = true;
+    if (p.L >= kp && p.L <= (uint32_t)kSortCap) {
+        const uint64_t* tops = p.tops + (size_t)qi * p.L;
+        if (tid == 0) { scal[0] = 0; scal[1] = 0; }
+        for (uint32_t i = tid; i < p.L; i += kFinThreads) sortbuf[i] = tops[i];
+        __syncthreads();
+        unsigned long long* Tp = reinterpret_cast<unsigned long long*>(scal + 4);
+        for (uint32_t i = tid; i < p.L; i += kFinThreads) {
+            const uint64_t v = sortbuf[i];
+            uint32_t rank = 0;
+            for (uint32_t o = 0; o < p.L; ++o) { const uint64_t w = sortbuf[o]; rank += (w > v || (w == v && o < i)) ? 1u : 0u; }
+            if (rank == kp - 1) *Tp = v;
+        }
+        __syncthreads();
+        uint64_t T = *Tp;
+        if (T == 0ull) T = 1ull;                          // fewer than kp non-empty lists: keep every key
+        __syncthreads();
+        constexpr int U = 4;
+        for (uint32_t i0 = tid; i0 < p.M; i0 += kFinThreads * U) {
+            uint64_t v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const uint32_t i = i0 + u * kFinThreads; v[u] = i < p.M ? keys[i] : 0ull; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (v[u] >= T) {
+                    const uint32_t pos = atomicAdd(&scal[0], 1u);
+                    if (pos < kFinWarps * KPW) sortbuf[pos] = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t got = scal[0];
+        if (got <= kFinWarps * KPW) {
+            for (uint32_t i = got + tid; i < kFinWarps * KPW; i += kFinThreads) sortbuf[i] = 0ull;
+            folded = false;
+        }
+        __syncthreads();
+    }
+    // ---- 1b. general path: per-warp fold of the lists into register top-k' lists ----
+    if (folded) {
     WarpTopK<KPL> acc;
     acc.init();
     uint64_t nxt[KPL];
@@ -285,6 +326,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
 #pragma unroll
     for (int j = 0; j < KPL; ++j) sortbuf[(size_t)warp * KPW + j * 32 + lane] = acc.key[j];
     __syncthreads();
+    }
     // ---- 2. rank the 8*KPW merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
     const uint32_t nmerged = kFinWarps * KPW;
     if (tid == 0) scal[0] = 0;

@@ -72,7 +72,7 @@ static int ensure_pinned(Scratch& s, size_t bytes) {
     if (s.p) cudaFreeHost(s.p);
     s.p = nullptr; s.bytes = 0;
     size_t want = std::max(bytes, (size_t)4096);
-    CU(cudaMallocHost(&s.p, want));
+    CU(cudaHostAlloc(&s.p, want, cudaHostAllocMapped));   // device-visible (zero-copy) as well as DMA-able
     s.bytes = want;
     return LVS_OK;
 }
@@ -128,11 +128,12 @@ struct lvs_collection {
         uint32_t base = 0;
         bool has_want = false;
         uint32_t want[kMaxFilterCols];
-        Scratch h, d_q, d_res;
+        Scratch h;
+        size_t qbytes = 0;
         cudaEvent_t done = nullptr;
     } slots[kSubmitSlots];
 
-    int opt_stage_kb = 64;
+    int opt_stage_kb = 72;
     int opt_stages = 0;   // 0 = as many as fit
     int opt_grid = 0;     // 0 = one CTA per SM
     int opt_force_kpl = 0;
@@ -317,8 +318,6 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     if (c->s_cand.p) cudaFree(c->s_cand.p);
     for (auto& sl : c->slots) {
         if (sl.h.p) cudaFreeHost(sl.h.p);
-        if (sl.d_q.p) cudaFree(sl.d_q.p);
-        if (sl.d_res.p) cudaFree(sl.d_res.p);
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (c->h_flags.p) cudaFreeHost(c->h_flags.p);
@@ -675,7 +674,7 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
         sp.live = c->d_live;
         for (uint32_t f = 0; f < nf; ++f) { sp.codes[f] = fcodes[f]; sp.want[f] = fwant[f]; }
         sp.n_filter = nf;
-        sp.out_keys = keys; sp.out_mins = mins;
+        sp.out_keys = keys; sp.out_tops = mins;
         int grid = c->opt_grid > 0 ? c->opt_grid : sm;
         const uint32_t units = filter ? sp.n_blocks32 : sp.n_tiles;
         grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, units));
@@ -696,7 +695,7 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
         FinalizeParams fp;
         memset(&fp, 0, sizeof(fp));
         const uint32_t kpw = 32u * kpl;
-        fp.keys = keys; fp.mins = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid; fp.kp = kpw; fp.k = (uint32_t)k;
+        fp.keys = keys; fp.tops = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid; fp.kp = kpw; fp.k = (uint32_t)k;
         fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
         fp.storage = c->storage; fp.metric = c->metric;
         fp.q64 = q64 + (size_t)first * c->dim;
@@ -808,42 +807,6 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     return LVS_OK;
 }
 
-extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
-                          double* out_scores, int64_t* out_rows, uint64_t* out_ties, uint32_t* out_counts, int32_t* out_flags) {
-    if (!c) return fail(LVS_EINVAL, "collection is NULL");
-    if (Q < 0 || (Q > 0 && !queries)) return fail(LVS_EINVAL, "bad queries / Q");
-    if (Q == 0) return LVS_OK;
-    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
-    if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
-    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
-    std::lock_guard<std::mutex> lk(c->mu);
-    const size_t qbytes = (size_t)Q * c->dim * dt_size(dtype);
-    const size_t nres = (size_t)Q * k;
-    const size_t rbytes = nres * 24 + (size_t)Q * 4;
-    int rc;
-    if ((rc = ensure_pinned(c->h_pin2, std::max(qbytes, rbytes))) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_qraw, qbytes)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_res, rbytes)) != LVS_OK) return rc;
-    cudaStream_t st = c->stream;
-    memcpy(c->h_pin2.p, queries, qbytes);
-    CU(cudaMemcpyAsync(c->s_qraw.p, c->h_pin2.p, qbytes, cudaMemcpyHostToDevice, st));
-    uint8_t* rp = (uint8_t*)c->s_res.p;
-    double* ds = (double*)rp;
-    int64_t* dr = (int64_t*)(rp + nres * 8);
-    uint64_t* dt = (uint64_t*)(rp + nres * 16);
-    uint32_t* dc = (uint32_t*)(rp + nres * 24);
-    rc = search_core(c, c->s_qraw.p, dtype, Q, k, want, ds, dr, dt, dc, out_flags, nullptr, false, st);
-    if (rc != LVS_OK) return rc;
-    CU(cudaMemcpyAsync(c->h_pin2.p, rp, rbytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const uint8_t* hp = (const uint8_t*)c->h_pin2.p;
-    if (out_scores) memcpy(out_scores, hp, nres * 8);
-    if (out_rows) memcpy(out_rows, hp + nres * 8, nres * 8);
-    if (out_ties) memcpy(out_ties, hp + nres * 16, nres * 8);
-    if (out_counts) memcpy(out_counts, hp + nres * 24, (size_t)Q * 4);
-    return LVS_OK;
-}
-
 extern "C" int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                                  double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                                  int32_t* out_flags, void* stream) {
@@ -868,45 +831,87 @@ extern "C" int lvs_search_device_async(lvs_collection* c, const void* d_queries,
     return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, nullptr, d_out_flags, true, st);
 }
 
-// Result block layout shared by lvs_search and the submit/wait pair: scores | rows | ties (Q*k*8 each) | counts | flags
+// Host-buffer searches are zero-copy: the query block and the result block of a slot live in mapped pinned host memory;
+// the prep kernel reads the queries over PCIe and the finalize kernel stores scores/rows/ties/counts/flags straight into
+// host memory, so a step is kernels only (no copy-engine hops between them).
+// Slot layout: [queries, padded to 256 B][scores | rows | ties (Q*k*8 each) | counts (Q*4) | flags (Q*4)]
 static size_t res_bytes(int Q, int k) { return (size_t)Q * k * 24 + (size_t)Q * 8; }
 
-extern "C" int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket) {
-    if (!c || !ticket) return fail(LVS_EINVAL, "NULL argument");
-    if (Q < 1 || !queries) return fail(LVS_EINVAL, "bad queries / Q");
-    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
-    if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
-    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
-    std::lock_guard<std::mutex> lk(c->mu);
+static int submit_locked(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket) {
     int si = -1;
     for (int i = 0; i < kSubmitSlots; ++i) if (!c->slots[i].in_use) { si = i; break; }
     if (si < 0) return fail(LVS_ELIMIT, "%d searches already in flight: call lvs_search_wait first", kSubmitSlots);
     auto& sl = c->slots[si];
-    const size_t qbytes = (size_t)Q * c->dim * dt_size(dtype);
+    const size_t qbytes = ((size_t)Q * c->dim * dt_size(dtype) + 255) & ~(size_t)255;
     const size_t rbytes = res_bytes(Q, k);
     int rc;
-    if ((rc = ensure_pinned(sl.h, std::max(qbytes, rbytes))) != LVS_OK) return rc;
-    if ((rc = ensure_dev(sl.d_q, qbytes)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(sl.d_res, rbytes)) != LVS_OK) return rc;
+    if ((rc = ensure_pinned(sl.h, qbytes + rbytes)) != LVS_OK) return rc;
     if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    void* dview = nullptr;
+    CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
     cudaStream_t st = c->stream;
-    memcpy(sl.h.p, queries, qbytes);
-    CU(cudaMemcpyAsync(sl.d_q.p, sl.h.p, qbytes, cudaMemcpyHostToDevice, st));
+    memcpy(sl.h.p, queries, (size_t)Q * c->dim * dt_size(dtype));
     const size_t nres = (size_t)Q * k;
-    uint8_t* rp = (uint8_t*)sl.d_res.p;
-    sl.Q = Q; sl.k = k; sl.dtype = dtype; sl.base = c->search_counter + 1;
+    uint8_t* rp = (uint8_t*)dview + qbytes;
+    sl.Q = Q; sl.k = k; sl.dtype = dtype; sl.base = c->search_counter + 1; sl.qbytes = qbytes;
     sl.has_want = want != nullptr;
     if (want) memcpy(sl.want, want, sizeof(uint32_t) * kMaxFilterCols);
-    rc = search_core(c, sl.d_q.p, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
+    rc = search_core(c, dview, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
                      (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st);
     if (rc != LVS_OK) return rc;
     sl.kpl = c->last_kpl;
-    // the H2D staging area is free once the copy above has executed, which precedes this D2H in stream order
-    CU(cudaMemcpyAsync(sl.h.p, rp, rbytes, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(sl.done, st));
     sl.in_use = true;
     *ticket = si;
     return LVS_OK;
+}
+
+static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
+                         uint32_t* out_counts, int32_t* out_flags) {
+    auto& sl = c->slots[ticket];
+    const int Q = sl.Q, k = sl.k;
+    const size_t nres = (size_t)Q * k;
+    uint8_t* hp = (uint8_t*)sl.h.p + sl.qbytes;
+    int32_t* hflags = (int32_t*)(hp + nres * 24 + (size_t)Q * 4);
+    std::vector<int> redo;
+    for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && sl.kpl < 8) redo.push_back(i);
+    if (!redo.empty()) {
+        // rare: repeat the flagged queries with larger candidate sets, as the same reference searches (same numbers)
+        void* dview = nullptr;
+        CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
+        uint8_t* rp = (uint8_t*)dview + sl.qbytes;
+        std::vector<int32_t> f2(Q, 0);
+        int rc = search_core(c, dview, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
+                             (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
+                             (int64_t)sl.base, sl.kpl * 2, &redo);
+        if (rc != LVS_OK) { sl.in_use = false; return rc; }
+        for (int i : redo) hflags[i] = f2[i];
+    }
+    if (out_scores) memcpy(out_scores, hp, nres * 8);
+    if (out_rows) memcpy(out_rows, hp + nres * 8, nres * 8);
+    if (out_ties) memcpy(out_ties, hp + nres * 16, nres * 8);
+    if (out_counts) memcpy(out_counts, hp + nres * 24, (size_t)Q * 4);
+    if (out_flags) memcpy(out_flags, hflags, (size_t)Q * 4);
+    sl.in_use = false;
+    return LVS_OK;
+}
+
+static int check_search_args(const lvs_collection* c, const void* queries, int dtype, int Q, int k) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (Q < 0 || (Q > 0 && !queries)) return fail(LVS_EINVAL, "bad queries / Q");
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
+    return LVS_OK;
+}
+
+extern "C" int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket) {
+    if (!ticket) return fail(LVS_EINVAL, "ticket is NULL");
+    int rc = check_search_args(c, queries, dtype, Q, k);
+    if (rc != LVS_OK) return rc;
+    if (Q < 1) return fail(LVS_EINVAL, "Q must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    return submit_locked(c, queries, dtype, Q, k, want, ticket);
 }
 
 extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
@@ -921,32 +926,27 @@ extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores
     }
     CU(cudaEventSynchronize(done));   // outside the lock: other threads may submit meanwhile
     std::lock_guard<std::mutex> lk(c->mu);
-    auto& sl = c->slots[ticket];
-    const int Q = sl.Q, k = sl.k;
-    const size_t nres = (size_t)Q * k;
-    uint8_t* hp = (uint8_t*)sl.h.p;
-    int32_t* hflags = (int32_t*)(hp + nres * 24 + (size_t)Q * 4);
-    std::vector<int> redo;
-    for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && sl.kpl < 8) redo.push_back(i);
-    if (!redo.empty()) {
-        // rare: repeat the flagged queries with larger candidate sets, as the same reference searches (same numbers)
-        uint8_t* rp = (uint8_t*)sl.d_res.p;
-        std::vector<int32_t> f2(Q, 0);
-        int rc = search_core(c, sl.d_q.p, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
-                             (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
-                             (int64_t)sl.base, sl.kpl * 2, &redo);
-        if (rc != LVS_OK) { sl.in_use = false; return rc; }
-        CU(cudaMemcpyAsync(hp, rp, nres * 24 + (size_t)Q * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        for (int i : redo) hflags[i] = f2[i];
+    return finish_locked(c, ticket, out_scores, out_rows, out_ties, out_counts, out_flags);
+}
+
+extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                          double* out_scores, int64_t* out_rows, uint64_t* out_ties, uint32_t* out_counts, int32_t* out_flags) {
+    int rc = check_search_args(c, queries, dtype, Q, k);
+    if (rc != LVS_OK) return rc;
+    if (Q == 0) return LVS_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int ticket = -1;
+    if ((rc = submit_locked(c, queries, dtype, Q, k, want, &ticket)) != LVS_OK) return rc;
+    CU(cudaEventSynchronize(c->slots[ticket].done));
+    rc = finish_locked(c, ticket, out_scores, out_rows, out_ties, out_counts, out_flags);
+    if (rc == LVS_OK && c->opt_timing && c->first_scan_start) {
+        c->last_ms[0] = 0.f;
+        cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->first_scan_start);
+        cudaEventElapsedTime(&c->last_ms[1], c->first_scan_start, c->first_scan_end);
+        cudaEventElapsedTime(&c->last_ms[2], c->first_scan_end, c->ev[4]);
+        c->last_ms[3] = c->last_ms[0] + c->last_ms[1] + c->last_ms[2];
     }
-    if (out_scores) memcpy(out_scores, hp, nres * 8);
-    if (out_rows) memcpy(out_rows, hp + nres * 8, nres * 8);
-    if (out_ties) memcpy(out_ties, hp + nres * 16, nres * 8);
-    if (out_counts) memcpy(out_counts, hp + nres * 24, (size_t)Q * 4);
-    if (out_flags) memcpy(out_flags, hflags, (size_t)Q * 4);
-    sl.in_use = false;
-    return LVS_OK;
+    return rc;
 }
 
 extern "C" int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n) {

@@ -46,7 +46,7 @@ struct ScanParams {
     uint32_t want[kMaxFilterCols];
     uint32_t n_filter;          // number of constrained columns compacted into codes[]/want[]
     uint64_t* out_keys;         // [QT][gridDim.x][32*KPL]
-    uint64_t* out_mins;         // [QT][gridDim.x]
+    uint64_t* out_tops;         // [QT][gridDim.x] best key of each CTA list (threshold for the finalize step)
 };
 
 // Transposed warp reduction: `vals[0..V)` per lane, V a power of two <= 32.  On return vals[0] of lane l
@@ -340,7 +340,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             uint64_t* dst = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * KPW;
 #pragma unroll
             for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = acc.key[j];
-            if (lane == 0) p.out_mins[(size_t)qi * gridDim.x + blockIdx.x] = acc.thr;
+            uint64_t best = acc.key[0];
+#pragma unroll
+            for (int j = 1; j < KPL; ++j) best = acc.key[j] > best ? acc.key[j] : best;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) { const uint64_t other = shfl_xor_u64(best, o); best = other > best ? other : best; }
+            if (lane == 0) p.out_tops[(size_t)qi * gridDim.x + blockIdx.x] = best;
         }
     }
 }

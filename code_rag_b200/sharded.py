@@ -28,8 +28,21 @@ def shard_bounds(n_total: int, world: int, align: int = 1) -> list[tuple[int, in
     return out
 
 
+def allgather_packed(local, gathered, group=None):
+    """The path's one exchange step: every rank contributes its packed [3, Q, k] int64 block (float64 score bits,
+    global rows, tie keys) and receives all of them as [G, 3, Q, k].  NCCL on GPUs; gloo in the CPU tests."""
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=group)
+    return gathered
+
+
 class ShardedSearcher:
-    """Wraps this rank's shard; `search` returns the same global result on every rank."""
+    """Wraps this rank's shard; every search returns the same global result on every rank.
+
+    All device work is ordered on one side stream (``self.stream``).  Host entry points are zero-copy: queries are read
+    by the prep kernel straight from pinned host memory and the final kernel (finalize, or the merge when world > 1)
+    stores the result straight into pinned host memory, so a step is kernels + one collective, no copy-engine hops.
+    """
 
     def __init__(self, shard: DeviceCollection, group=None):
         import torch
@@ -40,74 +53,68 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self._bufs: dict[tuple, tuple] = {}
-        self._flag_bufs: dict[tuple, object] = {}
-        self._io_bufs: dict[tuple, tuple] = {}
+        self._bufs: dict[tuple, dict] = {}
         self.merge_launches = 0
-        # all device work of this searcher is ordered on one side stream (a real handle, never the legacy stream 0)
         self.stream = torch.cuda.Stream(device=self.device)
         self.n_slots = 4
         self._next_slot = 0
 
-    def _buffers(self, Q: int, k: int, slot: int = 0):
-        key = (Q, k, slot)
-        if key not in self._bufs:
+    def _slot(self, Q: int, k: int, slot: int, host: bool) -> dict:
+        key = (Q, k, slot, host)
+        b = self._bufs.get(key)
+        if b is None:
             t = self.torch
-            local = t.zeros((3, Q, k), dtype=t.int64, device=self.device)
-            counts = t.zeros(Q, dtype=t.int32, device=self.device)
-            gathered = t.zeros((self.world, 3, Q, k), dtype=t.int64, device=self.device) if self.world > 1 else None
-            out = t.zeros((3, Q, k), dtype=t.int64, device=self.device)
-            out_counts = t.zeros(Q, dtype=t.int32, device=self.device)
-            self._bufs[key] = (local, counts, gathered, out, out_counts)
-        return self._bufs[key]
+            mk = (lambda *shape, dtype: t.zeros(shape, dtype=dtype).pin_memory()) if host else \
+                 (lambda *shape, dtype: t.zeros(shape, dtype=dtype, device=self.device))
+            b = {"out": mk(3, Q, k, dtype=t.int64), "counts": mk(Q, dtype=t.int32), "flags": mk(Q, dtype=t.int32),
+                 "event": t.cuda.Event()}
+            if self.world > 1:
+                b["local"] = t.zeros((3, Q, k), dtype=t.int64, device=self.device)
+                b["local_counts"] = t.zeros(Q, dtype=t.int32, device=self.device)
+                b["gathered"] = t.zeros((self.world, 3, Q, k), dtype=t.int64, device=self.device)
+            self._bufs[key] = b
+        return b
 
+    def _enqueue(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, b: dict) -> None:
+        """prep + scan + finalize on the shard, then (world > 1) all-gather + merge, all on self.stream."""
+        stream = self.stream.cuda_stream
+        out = b["out"]
+        if self.world == 1:
+            self.shard.search_device_async(q_ptr, q_dtype, Q, k, want, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                           b["counts"].data_ptr(), b["flags"].data_ptr(), stream)
+            return
+        local = b["local"]
+        self.shard.search_device_async(q_ptr, q_dtype, Q, k, want, local[0].data_ptr(), local[1].data_ptr(), local[2].data_ptr(),
+                                       b["local_counts"].data_ptr(), b["flags"].data_ptr(), stream)
+        with self.torch.cuda.stream(self.stream):
+            allgather_packed(local, b["gathered"], self.group)
+        n = Q * k
+        base = b["gathered"].data_ptr()
+        merge_topk_device(base, base + 8 * n, base + 16 * n, self.world, Q, k, out[0].data_ptr(), out[1].data_ptr(),
+                          out[2].data_ptr(), b["counts"].data_ptr(), stream, shard_stride=3 * n)
+        self.merge_launches += 1
+
+    # ---- device entry points ---------------------------------------------------------------------------
     def search_device_async(self, dq, k: int, want=None, slot: int = 0):
-        """Enqueue-only variant for pipelined callers: no host synchronisation, flags stay on the device.  `slot`
-        selects one of several result buffers so that consecutive searches do not overwrite each other.  Returns
-        (scores, rows, ties, counts, flags, packed) where packed is the [3, Q, k] int64 block holding the first three.
-        Call it under ``torch.cuda.stream(searcher.stream)`` (or any non-default stream)."""
+        """dq: CUDA tensor [Q, dim] float32/float64 (same on every rank), already valid on ``self.stream``.  Enqueue only;
+        returns CUDA tensors (scores f64 [Q,k], rows i64, ties i64, counts i32 [Q], flags i32 [Q]) that are valid once
+        ``self.stream`` has been synchronised.  `slot` rotates result buffers between consecutive searches."""
         t = self.torch
         Q = int(dq.shape[0])
-        local, counts, gathered, out, out_counts = self._buffers(Q, k, slot)
-        flags = self._flag_bufs.setdefault((Q, slot), t.zeros(Q, dtype=t.int32, device=self.device))
-        stream = t.cuda.current_stream().cuda_stream
-        qd = "f64" if dq.dtype == t.float64 else "f32"
-        self.shard.search_device_async(dq.data_ptr(), qd, Q, k, want, local[0].data_ptr(), local[1].data_ptr(),
-                                       local[2].data_ptr(), counts.data_ptr(), flags.data_ptr(), stream)
-        if self.world == 1:
-            return local[0].view(t.float64), local[1], local[2], counts, flags, local
-        self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
-        n = Q * k
-        base = gathered.data_ptr()
-        merge_topk_device(base, base + 8 * n, base + 16 * n, self.world, Q, k, out[0].data_ptr(), out[1].data_ptr(),
-                          out[2].data_ptr(), out_counts.data_ptr(), stream, shard_stride=3 * n)
-        self.merge_launches += 1
-        return out[0].view(t.float64), out[1], out[2], out_counts, flags, out
+        b = self._slot(Q, k, slot, host=False)
+        self._enqueue(dq.data_ptr(), "f64" if dq.dtype == t.float64 else "f32", Q, k, want, b)
+        out = b["out"]
+        return out[0].view(t.float64), out[1], out[2], b["counts"], b["flags"]
 
     def search_device(self, dq, k: int, want=None):
-        """dq: CUDA tensor [Q, dim] float32/float64 (same on every rank).  Returns CUDA tensors
-        (scores f64 [Q,k], rows i64 [Q,k], ties i64 [Q,k], counts i32 [Q]) and the host flags."""
-        t = self.torch
-        Q = int(dq.shape[0])
-        local, counts, gathered, out, out_counts = self._buffers(Q, k)
-        stream = t.cuda.current_stream().cuda_stream
-        qd = "f64" if dq.dtype == t.float64 else "f32"
-        flags = self.shard.search_device(dq.data_ptr(), qd, Q, k, want, local[0].data_ptr(), local[1].data_ptr(),
-                                         local[2].data_ptr(), counts.data_ptr(), stream)
-        if self.world == 1:
-            return local[0].view(t.float64), local[1], local[2], counts, flags
-        self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
-        n = Q * k
-        base = gathered.data_ptr()
-        merge_topk_device(base, base + 8 * n, base + 16 * n, self.world, Q, k, out[0].data_ptr(), out[1].data_ptr(),
-                          out[2].data_ptr(), out_counts.data_ptr(), stream, shard_stride=3 * n)
-        self.merge_launches += 1
-        return out[0].view(t.float64), out[1], out[2], out_counts, flags
+        """Synchronous device entry; returns the tensors plus the host flags."""
+        s, r, ti, c, f = self.search_device_async(dq, k, want, slot=0)
+        self.stream.synchronize()
+        return s, r, ti, c, f.cpu().numpy()
 
-    # ---- host entry points ----------------------------------------------------------------------------
+    # ---- host entry points -----------------------------------------------------------------------------
     def submit(self, queries: np.ndarray, k: int, want=None):
-        """Pipelined host entry: pinned H2D of the queries, sharded search, D2H of the merged result, all enqueued
-        on the searcher's stream.  Returns a handle for :meth:`wait`; up to ``n_slots`` may be in flight."""
+        """Pipelined host entry; returns a handle for :meth:`wait`.  Up to ``n_slots`` searches may be in flight."""
         t = self.torch
         q = np.ascontiguousarray(queries, dtype=np.float64)
         if q.ndim == 1:
@@ -115,28 +122,20 @@ class ShardedSearcher:
         Q, dim = q.shape
         slot = self._next_slot
         self._next_slot = (slot + 1) % self.n_slots
-        key = (Q, k, dim, slot)
-        if key not in self._io_bufs:
-            self._io_bufs[key] = (
-                t.empty((Q, dim), dtype=t.float64).pin_memory(), t.empty((Q, dim), dtype=t.float64, device=self.device),
-                t.empty((3, Q, k), dtype=t.int64).pin_memory(), t.empty(Q, dtype=t.int32).pin_memory(),
-                t.empty(Q, dtype=t.int32).pin_memory(), t.cuda.Event())
-        hq, dq, h_out, h_counts, h_flags, ev = self._io_bufs[key]
-        hq.numpy()[...] = q
-        with t.cuda.stream(self.stream):
-            dq.copy_(hq, non_blocking=True)
-            s, r, ti, c, flags, packed = self.search_device_async(dq, k, want, slot)
-            h_out.copy_(packed, non_blocking=True)
-            h_counts.copy_(c, non_blocking=True)
-            h_flags.copy_(flags, non_blocking=True)
-            ev.record(self.stream)
-        return key
+        b = self._slot(Q, k, slot, host=True)
+        if "hq" not in b or b["hq"].shape != (Q, dim):
+            b["hq"] = t.zeros((Q, dim), dtype=t.float64).pin_memory()
+        b["hq"].numpy()[...] = q
+        # pinned memory is mapped into the device address space (UVA): the kernels read/write it directly
+        self._enqueue(b["hq"].data_ptr(), "f64", Q, k, want, b)
+        b["event"].record(self.stream)
+        return b
 
     def wait(self, handle):
-        hq, dq, h_out, h_counts, h_flags, ev = self._io_bufs[handle]
-        ev.synchronize()
-        o = h_out.numpy()
-        return o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy(), h_counts.numpy().copy(), h_flags.numpy().copy()
+        handle["event"].synchronize()
+        o = handle["out"].numpy()
+        return (o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy(), handle["counts"].numpy().copy(),
+                handle["flags"].numpy().copy())
 
     def search(self, queries: np.ndarray, k: int, want=None):
         """Synchronous host entry (one search at a time)."""

@@ -1,0 +1,181 @@
+"""Adapter scenarios shared by the CPU run (FakeDevice: host logic only) and the GPU run (real DeviceCollection).
+
+They read like the reference's own tests of this seam: call shapes from ``tests/test_embeddings.py:553-565,620-625``
+(keyword arguments ``collection=, query_vector=, limit=, filters=``; result dicts ``{"id","score","payload"}``) and the
+live-database scenario of ``tests/test_database.py:76-124`` (create both collections; upsert ``[0.1]*1536`` then search
+the same vector with ``limit=1``; delete by ``file_path``).  Results are compared with the CPU oracle's QdrantManager
+restatement (``oracle.qdrant_local.OracleManager``) on the same inputs.
+"""
+from __future__ import annotations
+
+import uuid
+
+import numpy as np
+
+import lvs_synth as synth
+from code_rag_b200.client import B200VectorStore, CollectionName
+from code_rag_b200.errors import VectorStoreError
+from oracle.qdrant_local import OracleManager
+
+CODE = CollectionName.CODE_CHUNKS.value
+SUMM = CollectionName.SUMMARIES.value
+
+
+def _same_hits(got, exp, rel=1e-5, what=""):
+    assert [h["id"] for h in got] == [h["id"] for h in exp], f"{what}: ids differ\n got {[h['id'] for h in got]}\n exp {[h['id'] for h in exp]}"
+    for g, e in zip(got, exp):
+        assert abs(g["score"] - e["score"]) <= rel * max(abs(e["score"]), 1e-30) + 1e-300, what
+        assert g["payload"] == e["payload"], what
+
+
+async def scenario_test_database(factory):
+    """reference tests/test_database.py:62-124 against the new backend."""
+    manager = B200VectorStore(dimensions=1536, _device_factory=factory)
+    await manager.connect()
+    assert await manager.health_check() is True
+    await manager.create_collections()
+    await manager.create_collections()          # idempotent (client.py:72-91)
+    names = [c.name for c in (await manager.client.get_collections()).collections]
+    assert "code_chunks" in names and "summaries" in names
+    test_id = str(uuid.uuid4())
+    test_vector = [0.1] * 1536
+    test_payload = {"file_path": "/test/file.py", "entity_type": "function", "entity_name": "test_func",
+                    "language": "python", "content": "def test_func(): pass", "start_line": 1, "end_line": 1}
+    await manager.upsert(collection="code_chunks", ids=[test_id], vectors=[test_vector], payloads=[test_payload])
+    results = await manager.search(collection="code_chunks", query_vector=test_vector, limit=1)
+    assert len(results) >= 1
+    assert results[0]["payload"]["entity_name"] == "test_func"
+    assert results[0]["id"] == test_id
+    assert abs(results[0]["score"] - 1.0) < 1e-6
+    assert (await manager.get_collection_info("code_chunks")).points_count == 1
+    await manager.delete(collection="code_chunks", filters={"file_path": "/test/file.py"})
+    assert await manager.search(collection="code_chunks", query_vector=test_vector, limit=1) == []
+    assert (await manager.get_collection_info("code_chunks")).points_count == 0
+    await manager.close()
+    assert await manager.health_check() is False
+    try:
+        manager.client
+        raise AssertionError("client must raise before connect()")
+    except VectorStoreError as e:
+        assert "Client not connected" in str(e)
+
+
+async def scenario_parity_with_oracle(factory, n=3000, dim=256):
+    """Random uuid4 ids, CodeChunk payloads, every filter shape the reference issues; ids, scores, payloads vs oracle."""
+    x, q = synth.unixcoder_like(n, dim, seed=1234, n_queries=6)
+    pl = synth.payloads(n, seed=7)
+    ids = synth.random_uuids(n, seed=9)
+    store = B200VectorStore(dimensions=dim, _device_factory=factory)
+    ora = OracleManager(dim)
+    await store.connect()
+    await store.create_collections()
+    ora.create_collections()
+    # index file by file like VectorIndexer.index_file (embeddings/indexer.py:46-94): batches of a few chunks
+    step = 257
+    for s in range(0, n, step):
+        sl = slice(s, min(n, s + step))
+        vecs = x[sl].astype(np.float64).tolist()
+        await store.upsert(collection=CODE, ids=ids[sl], vectors=vecs, payloads=pl[sl])
+        ora.upsert(CODE, ids[sl], vecs, pl[sl])
+    assert (await store.get_collection_info(CODE)).points_count == n == ora.points_count(CODE)
+    some_file = pl[11]["file_path"]
+    filter_sets = [None, {"language": "python"}, {"language": "typescript", "entity_type": "class", "project_name": "proj1"},
+                   {"project_name": "proj0"}, {"file_path": some_file}, {"entity_type": "method"}, {"project_name": "nope"},
+                   {"entity_name": pl[5]["entity_name"], "file_path": pl[5]["file_path"]}]
+    for qi in range(len(q)):
+        qv = q[qi].astype(np.float64).tolist()
+        for flt in filter_sets:
+            for limit in (1, 5, 10, 20):
+                if qi > 1 and limit != 10:
+                    continue
+                got = await store.search(collection=CODE, query_vector=qv, limit=limit, filters=flt)
+                exp = ora.search(CODE, qv, limit=limit, filters=flt)
+                _same_hits(got, exp, what=f"q{qi} filters={flt} limit={limit}")
+    # query_vector=None: filter-only lookup used by ContextBuilder (query/context/builder.py:111-119)
+    got = await store.search(collection=CODE, query_vector=None, limit=1,
+                             filters={"entity_name": pl[5]["entity_name"], "file_path": pl[5]["file_path"]})
+    exp = ora.search(CODE, None, limit=1, filters={"entity_name": pl[5]["entity_name"], "file_path": pl[5]["file_path"]})
+    _same_hits(got, exp, what="filter-only")
+    got = await store.search(collection=CODE, query_vector=None, limit=7, filters={"project_name": "proj2"})
+    exp = ora.search(CODE, None, limit=7, filters={"project_name": "proj2"})
+    _same_hits(got, exp, what="filter-only scroll order")
+    # incremental indexing (client.py:178-202)
+    assert await store.file_needs_update(CODE, some_file, pl[11]["content_hash"]) is False
+    assert await store.file_needs_update(CODE, some_file, "other-hash") is True
+    assert await store.file_needs_update(CODE, "missing.py", "h") is True
+    # re-index one file: delete by file_path then upsert new chunks with new ids (indexer.py:61-86)
+    await store.delete(collection=CODE, filters={"file_path": some_file})
+    ora.delete(CODE, {"file_path": some_file})
+    assert (await store.get_collection_info(CODE)).points_count == ora.points_count(CODE)
+    x2, _ = synth.unixcoder_like(5, dim, seed=99)
+    ids2 = synth.random_uuids(5, seed=100)
+    pl2 = [dict(pl[11], entity_name=f"new_{i}", content_hash="h2") for i in range(5)]
+    await store.upsert(collection=CODE, ids=ids2, vectors=x2.astype(np.float64).tolist(), payloads=pl2)
+    ora.upsert(CODE, ids2, x2.astype(np.float64).tolist(), pl2)
+    # overwrite an existing id with a new vector and payload (Qdrant upsert semantics)
+    await store.upsert(collection=CODE, ids=[ids[3]], vectors=[x2[0].astype(np.float64).tolist()], payloads=[dict(pl[3], language="go")])
+    ora.upsert(CODE, [ids[3]], [x2[0].astype(np.float64).tolist()], [dict(pl[3], language="go")])
+    for qi in range(3):
+        qv = q[qi].astype(np.float64).tolist()
+        for flt in (None, {"file_path": some_file}, {"language": "go"}):
+            _same_hits(await store.search(collection=CODE, query_vector=qv, limit=10, filters=flt),
+                       ora.search(CODE, qv, limit=10, filters=flt), what=f"after reindex q{qi} {flt}")
+    # batched additive API == consecutive single searches
+    qb = q[3:6].astype(np.float64)
+    got_b = await store.search_batch(collection=CODE, query_vectors=qb.tolist(), limit=5)
+    for i in range(3):
+        _same_hits(got_b[i], ora.search(CODE, qb[i].tolist(), limit=5), what=f"batch {i}")
+    # summaries collection is independent
+    assert await store.search(collection=SUMM, query_vector=q[0].astype(np.float64).tolist(), limit=3) == []
+    # clear_collections resets both (client.py:212-221)
+    await store.clear_collections()
+    assert (await store.get_collection_info(CODE)).points_count == 0
+    await store.close()
+
+
+async def scenario_errors(factory):
+    store = B200VectorStore(dimensions=8, _device_factory=factory)
+    for coro in (store.search(collection=CODE, query_vector=[0.0] * 8), store.upsert(CODE, [], [], []),
+                 store.delete(CODE, {"a": 1}), store.create_collections(), store.get_collection_info(CODE)):
+        try:
+            await coro
+            raise AssertionError("expected VectorStoreError before connect()")
+        except VectorStoreError:
+            pass
+    assert await store.file_needs_update(CODE, "f", "h") is True      # never raises (client.py:200-202)
+    await store.connect()
+    await store.create_collections()
+    bad = [("not-a-uuid", [0.1] * 8), (str(uuid.uuid4()), [0.1] * 7), (str(uuid.uuid4()), [float("nan")] * 8)]
+    for pid, vec in bad:
+        try:
+            await store.upsert(collection=CODE, ids=[pid], vectors=[vec], payloads=[{}])
+            raise AssertionError(f"expected VectorStoreError for {pid!r}")
+        except VectorStoreError as e:
+            assert e.cause is not None and "Failed to upsert vectors to code_chunks" in str(e)
+    for kw in ({"collection": "nope", "query_vector": [0.1] * 8}, {"collection": CODE, "query_vector": [0.1] * 5},
+               {"collection": CODE, "query_vector": [0.1] * 8, "filters": {"language": None}}):
+        try:
+            await store.search(**kw)
+            raise AssertionError(f"expected VectorStoreError for {kw}")
+        except VectorStoreError as e:
+            assert "Failed to search" in str(e)
+    await store.close()
+
+
+async def scenario_client_shim(factory):
+    """projects/cleanup.py:38-73: count + delete with a MatchText (substring) filter through manager.client."""
+    from types import SimpleNamespace as NS
+    store = B200VectorStore(dimensions=16, _device_factory=factory)
+    await store.connect()
+    await store.create_collections()
+    x, _ = synth.unit_rows(40, 16, seed=1)
+    pl = [{"file_path": f"/repos/{'alpha' if i % 2 else 'beta'}/f{i}.py", "entity_type": "function", "project_name": "p"} for i in range(40)]
+    await store.upsert(CODE, synth.random_uuids(40, 3), x.astype(np.float64).tolist(), pl)
+    flt = NS(must=[NS(key="file_path", match=NS(text="/repos/alpha/"))])
+    assert (await store.client.count(collection_name=CODE, count_filter=flt, exact=True)).count == 20
+    await store.client.delete(collection_name=CODE, points_selector=NS(filter=flt))
+    assert (await store.client.count(collection_name=CODE, count_filter=flt)).count == 0
+    assert (await store.get_collection_info(CODE)).points_count == 20
+    flt2 = NS(must=[NS(key="project_name", match=NS(value="p"))])
+    assert (await store.client.count(collection_name=CODE, count_filter=flt2)).count == 20
+    await store.close()

@@ -1,0 +1,113 @@
+"""Test-only helpers: a CPU stand-in for DeviceCollection (built on the oracle) so that the adapter's HOST logic
+(ids, payloads, dictionary codes, filters) can be exercised without a GPU, and the K5 merge rule in numpy."""
+from __future__ import annotations
+
+import numpy as np
+
+from code_rag_b200.collection import SearchResult
+from oracle.qdrant_local import OracleCollection
+
+ANY = 0xFFFFFFFF
+
+
+class FakeDevice:
+    """Same methods as code_rag_b200.collection.DeviceCollection; arithmetic by the oracle.  TESTS ONLY."""
+
+    def __init__(self, name, dim, storage="f32", metric="cosine", n_filter_cols=0, capacity=0, row_base=0, device=0):
+        self.name, self.dim, self.n_filter_cols = name, dim, n_filter_cols
+        self.ora = OracleCollection(dim)
+        self.codes = np.zeros((0, n_filter_cols), dtype=np.uint32)
+        self.ties = np.zeros(0, dtype=np.uint64)
+        self.closed = False
+
+    @property
+    def rows(self):
+        return len(self.ora.payload)
+
+    def count(self):
+        return self.ora.count(None)
+
+    def _ensure(self, n):
+        if n > len(self.ora.payload):
+            add = n - len(self.ora.payload)
+            base = len(self.ora.payload)
+            self.ora._grow(n)
+            for i in range(add):
+                self.ora.ids[base + i] = base + i
+                self.ora.ids_inv.append(base + i)
+                self.ora.payload.append(None)
+                self.ora.deleted[base + i] = True
+            self.codes = np.vstack([self.codes, np.zeros((add, self.n_filter_cols), dtype=np.uint32)])
+            self.ties = np.concatenate([self.ties, np.zeros(add, dtype=np.uint64)])
+
+    def upsert(self, vectors, rows=None, codes=None, ties=None):
+        v = np.asarray(vectors, dtype=np.float64)
+        n = v.shape[0]
+        rows = np.arange(self.rows, self.rows + n) if rows is None else np.asarray(rows)
+        self._ensure(int(rows.max()) + 1)
+        for i, r in enumerate(rows.tolist()):
+            nrm = np.linalg.norm(v[i])
+            self.ora.vectors[r] = v[i] / nrm if nrm > 0 else v[i]
+            self.ora.deleted[r] = False
+            if codes is not None:
+                self.codes[r] = codes[i]
+            self.ties[r] = ties[i] if ties is not None else r
+
+    def set_codes(self, col, codes, rows=None, row0=0):
+        rows = np.arange(row0, row0 + len(codes)) if rows is None else np.asarray(rows)
+        self.codes[rows, col] = codes
+
+    def _mask(self, want):
+        m = ~self.ora.deleted[:self.rows]
+        if want is not None:
+            for c, w in enumerate(np.asarray(want).tolist()):
+                if w != ANY:
+                    m &= self.codes[:self.rows, c] == w
+        return m
+
+    def match_rows(self, want, cap=None):
+        rows = np.nonzero(self._mask(want))[0].astype(np.int64)
+        n = len(rows)
+        cap = n if cap is None else cap
+        return rows[:cap], n
+
+    def delete_where(self, want, cap=None):
+        rows, n = self.match_rows(want, None)
+        self.ora.deleted[rows] = True
+        return rows[: (n if cap is None else cap)], n
+
+    def delete_rows(self, rows):
+        rows = np.asarray(rows)
+        live = ~self.ora.deleted[rows]
+        self.ora.deleted[rows] = True
+        return int(live.sum())
+
+    def search(self, queries, k, want=None):
+        q = np.atleast_2d(np.asarray(queries, dtype=np.float64))
+        Q = q.shape[0]
+        res = SearchResult(np.zeros((Q, k)), np.full((Q, k), -1, dtype=np.int64), np.zeros((Q, k), dtype=np.uint64),
+                           np.zeros(Q, dtype=np.uint32), np.zeros(Q, dtype=np.int32))
+        mask = self._mask(want)
+        for i in range(Q):
+            scores = self.ora._scores(q[i])
+            cand = np.nonzero(mask)[0]
+            order = cand[np.lexsort((cand, self.ties[cand], -scores[cand]))][:k]
+            res.rows[i, :len(order)] = order
+            res.scores[i, :len(order)] = scores[order]
+            res.counts[i] = len(order)
+        return res
+
+    def close(self):
+        self.closed = True
+
+
+def merge_lists_numpy(scores: np.ndarray, rows: np.ndarray, ties: np.ndarray, k: int):
+    """The K5 merge rule (score desc, tie asc, row asc) over [G, Q, k] lists; rows < 0 are padding."""
+    G, Q, _ = scores.shape
+    o_s = np.zeros((Q, k)); o_r = np.full((Q, k), -1, dtype=np.int64); o_t = np.zeros((Q, k), dtype=np.uint64)
+    for q in range(Q):
+        s = scores[:, q].reshape(-1); r = rows[:, q].reshape(-1); t = ties[:, q].reshape(-1)
+        keep = np.nonzero(r >= 0)[0]
+        order = keep[np.lexsort((r[keep], t[keep], -s[keep]))][:k]
+        o_s[q, :len(order)] = s[order]; o_r[q, :len(order)] = r[order]; o_t[q, :len(order)] = t[order]
+    return o_s, o_r, o_t

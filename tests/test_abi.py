@@ -1,0 +1,62 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/lvs.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "lvs.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lvs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_documented_surface():
+    syms = _declared_symbols()
+    for must in ("lvs_init", "lvs_collection_create", "lvs_upsert", "lvs_search", "lvs_delete_where", "lvs_match_rows",
+                 "lvs_merge_topk_device", "lvs_search_submit", "lvs_search_wait", "lvs_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    for name in _declared_symbols():
+        assert hasattr(native_lib, name), f"liblattice_b200.so does not export {name}"
+
+
+def test_ctypes_table_matches_header(native_lib):
+    from code_rag_b200 import _native
+    assert sorted(_native.SIGNATURES) == _declared_symbols()
+
+
+def test_constants_match_header():
+    from code_rag_b200 import _native
+    text = (ROOT / "include" / "lvs.h").read_text()
+    defs = dict(re.findall(r"#define\s+(LVS_[A-Z0-9_]+)\s+\(?(-?0x[0-9A-Fa-f]+|-?\d+)u?\)?", text))
+    val = lambda k: int(defs[k], 0)
+    assert val("LVS_MAX_K") == _native.MAX_K
+    assert val("LVS_ANY") == _native.ANY and val("LVS_NO_MATCH") == _native.NO_MATCH
+    assert val("LVS_MAX_FILTER_COLS") == _native.MAX_FILTER_COLS
+    assert (val("LVS_STORAGE_BF16"), val("LVS_METRIC_DOT"), val("LVS_DT_F64")) == (_native.STORAGE_BF16, _native.METRIC_DOT, _native.DT_F64)
+    assert (val("LVS_EINVAL"), val("LVS_ESTATE")) == (_native.EINVAL, _native.ESTATE)
+
+
+def test_no_gpu_fails_loudly(native_lib):
+    """Without a CUDA device the product path must raise, never fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    from code_rag_b200 import _native
+    from code_rag_b200.errors import NativeLibraryError
+    with pytest.raises(NativeLibraryError):
+        _native.check(native_lib.lvs_init(0), "lvs_init")
+    h = ctypes.c_void_p()
+    rc = native_lib.lvs_collection_create(b"x", 8, 0, 0, 0, 0, 0, ctypes.byref(h))
+    assert rc == _native.ESTATE and h.value is None
+
+
+def test_product_code_never_imports_the_oracle():
+    for path in (ROOT / "code_rag_b200").rglob("*.py"):
+        src = path.read_text()
+        assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f"{path} mentions the oracle"

@@ -1,0 +1,21 @@
+"""Host logic of the QdrantManager-compatible adapter, on CPU: the device is replaced by an oracle-backed fake."""
+import asyncio
+
+import adapter_scenarios as S
+from helpers import FakeDevice
+
+
+def test_database_scenario():
+    asyncio.run(S.scenario_test_database(FakeDevice))
+
+
+def test_parity_with_oracle_manager():
+    asyncio.run(S.scenario_parity_with_oracle(FakeDevice, n=1200, dim=64))
+
+
+def test_error_convention():
+    asyncio.run(S.scenario_errors(FakeDevice))
+
+
+def test_client_shim_matchtext():
+    asyncio.run(S.scenario_client_shim(FakeDevice))

@@ -246,10 +246,10 @@ def test_sharded_searcher_world1(lib):
     ss = ShardedSearcher(dev)
     dq = torch.from_numpy(q.astype(np.float64)).cuda()
     outs = []
-    with torch.cuda.stream(ss.stream):
-        for i in range(3):
-            s, r, t, c, f, _ = ss.search_device_async(dq[i:i + 1], 10, slot=i)
-            outs.append((s, r, c, f))
+    torch.cuda.synchronize()
+    for i in range(3):
+        s, r, t, c, f = ss.search_device_async(dq[i:i + 1], 10, slot=i)
+        outs.append((s, r, c, f))
     ss.stream.synchronize()
     for i in range(3):
         s, r, c, f = outs[i]
