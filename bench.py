@@ -285,6 +285,7 @@ def run_ours(args) -> None:
         searcher.search_device(dq_all[i], k)
     barrier()
     sync_ms = (time.perf_counter() - t0) * 1e3
+    sync_scan_ms = float(np.mean(shard.scan_times(min(K, 256))[0]))
 
     # ---------------- e2e: host buffers through the public API, every step H2D(query) + D2H(result) ----------------
     # N=1: the C ABI's pipelined pair lvs_search_submit / lvs_search_wait (host pointers in, host pointers out);
@@ -312,6 +313,7 @@ def run_ours(args) -> None:
         last = e2e_wait(inflight.pop(0))
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_scan_ms = float(np.mean(shard.scan_times(min(K, 256))[0]))
     # depth 1 (strict request/response latency)
     barrier()
     t0 = time.perf_counter()
@@ -349,7 +351,8 @@ def run_ours(args) -> None:
                        "rows_per_gpu": n_local, "l2": "inputs_exceed_l2", "corpus_gen_s": round(t_gen, 1),
                        "parallelism": f"row-shard x{world} + all-gather(top-k) + merge",
                        "value_mode": "K searches enqueued back to back on one stream (device-resident queries/results)",
-                       "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K,
+                       "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K, "sync_scan_ms": sync_scan_ms,
+                       "e2e_scan_ms": e2e_scan_ms,
                        "unproven_queries": int(n_flagged)},
             "e2e": {"value": K * Q / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Q * args.dim * 8,
                     "d2h_bytes_per_step": Q * k * 24 + Q * 8, "ms_per_step": e2e_ms / K, "in_flight": DEPTH,
