@@ -56,10 +56,17 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_scan_times": (C.c_int, [_vp, C.c_int, _f32p, _f64p, _ip]),
     "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_rank_fuse": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
     "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),
     "lvs_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lvs_fetch_rows_f32": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
 }
+
+class RankBatch(C.Structure):
+    """``lvs_rank_batch`` of include/lvs.h."""
+    _fields_ = [("n_queries", C.c_int32), ("offsets", _vp), ("kind", _vp), ("key_id", _vp), ("file_id", _vp), ("depth", _vp),
+                ("entity_match", _vp), ("degree", _vp), ("flags", _vp), ("content_len", _vp), ("vscore", _vp), ("weights", _vp)]
+
 
 _lib: C.CDLL | None = None
 

@@ -13,6 +13,7 @@
 
 #include "aux_kernels.cuh"
 #include "finalize_kernel.cuh"
+#include "rank_kernel.cuh"
 #include "scan_kernel.cuh"
 
 using namespace lvs;
@@ -982,6 +983,117 @@ extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_ro
     if (smem > 40 * 1024) CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_topk_kernel<<<Q, 256, smem, st>>>(p);
     CU(cudaGetLastError());
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3 hybrid ranking
+// ------------------------------------------------------------------------------------------------------
+static std::mutex g_rank_mu;
+static Scratch g_rank_dev, g_rank_pin;
+static cudaStream_t g_rank_stream = nullptr;
+static cudaEvent_t g_rank_ev[2] = {nullptr, nullptr};
+
+extern "C" int lvs_rank_fuse(const lvs_rank_batch* in, int mode, int max_per_file, int max_total, double entity_bonus, double rel_bonus,
+                             int32_t* out_count, int32_t* out_index, double* out_score, double* out_norm, double* out_signals,
+                             uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+    if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
+    if (!in || !in->offsets) return fail(LVS_EINVAL, "NULL batch");
+    if (mode != 0 && mode != 1) return fail(LVS_EINVAL, "mode must be 0 (HybridRanker) or 1 (ResultReranker)");
+    const int nq = in->n_queries;
+    if (nq < 0 || max_total < 1) return fail(LVS_EINVAL, "bad n_queries / max_total");
+    if (device_ms) *device_ms = 0.f;
+    if (nq == 0) return LVS_OK;
+    if (!out_count || !out_index || !out_score || !out_leader) return fail(LVS_EINVAL, "NULL output");
+    const int64_t nc = in->offsets[nq];
+    int max_c = 0;
+    for (int q = 0; q < nq; ++q) {
+        const int c = in->offsets[q + 1] - in->offsets[q];
+        if (c < 0) return fail(LVS_EINVAL, "offsets must be non-decreasing");
+        max_c = std::max(max_c, c);
+    }
+    if (max_c > kRankMaxCand) return fail(LVS_ELIMIT, "%d candidates in one query exceed %d", max_c, kRankMaxCand);
+    std::lock_guard<std::mutex> lk(g_rank_mu);
+    if (!g_rank_stream) {
+        CU(cudaStreamCreateWithFlags(&g_rank_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&g_rank_ev[0]));
+        CU(cudaEventCreate(&g_rank_ev[1]));
+    }
+    // one staging block: inputs then outputs, 16-byte aligned sections
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t o = 0;
+    const size_t o_off = o; o = al(o + (size_t)(nq + 1) * 4);
+    const size_t o_kind = o; o = al(o + (size_t)nc);
+    const size_t o_key = o; o = al(o + (size_t)nc * 4);
+    const size_t o_file = o; o = al(o + (size_t)nc * 4);
+    const size_t o_depth = o; o = al(o + (size_t)nc * 4);
+    const size_t o_em = o; o = al(o + (size_t)nc * 8);
+    const size_t o_deg = o; o = al(o + (size_t)nc * 4);
+    const size_t o_flags = o; o = al(o + (size_t)nc);
+    const size_t o_clen = o; o = al(o + (size_t)nc * 4);
+    const size_t o_vs = o; o = al(o + (size_t)nc * 8);
+    const size_t o_w = o; o = al(o + (size_t)nq * 32);
+    const size_t in_bytes = o;
+    const size_t rows = (size_t)nq * max_total;
+    const size_t r_count = o; o = al(o + (size_t)nq * 4);
+    const size_t r_index = o; o = al(o + rows * 4);
+    const size_t r_score = o; o = al(o + rows * 8);
+    const size_t r_norm = o; o = al(o + rows * 8);
+    const size_t r_sig = o; o = al(o + rows * 8 * kRankSignals);
+    const size_t r_mask = o; o = al(o + rows);
+    const size_t r_src = o; o = al(o + rows);
+    const size_t r_lead = o; o = al(o + (size_t)std::max<int64_t>(nc, 1) * 4);
+    const size_t total = o;
+    int rc;
+    if ((rc = ensure_pinned(g_rank_pin, total)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(g_rank_dev, total)) != LVS_OK) return rc;
+    uint8_t* hp = (uint8_t*)g_rank_pin.p;
+    uint8_t* dp = (uint8_t*)g_rank_dev.p;
+    memcpy(hp + o_off, in->offsets, (size_t)(nq + 1) * 4);
+    if (nc > 0) {
+        if (!in->kind || !in->key_id || !in->file_id || !in->depth || !in->entity_match || !in->degree || !in->flags ||
+            !in->content_len || !in->vscore) return fail(LVS_EINVAL, "NULL candidate array");
+        memcpy(hp + o_kind, in->kind, (size_t)nc);
+        memcpy(hp + o_key, in->key_id, (size_t)nc * 4);
+        memcpy(hp + o_file, in->file_id, (size_t)nc * 4);
+        memcpy(hp + o_depth, in->depth, (size_t)nc * 4);
+        memcpy(hp + o_em, in->entity_match, (size_t)nc * 8);
+        memcpy(hp + o_deg, in->degree, (size_t)nc * 4);
+        memcpy(hp + o_flags, in->flags, (size_t)nc);
+        memcpy(hp + o_clen, in->content_len, (size_t)nc * 4);
+        memcpy(hp + o_vs, in->vscore, (size_t)nc * 8);
+    }
+    if (!in->weights) return fail(LVS_EINVAL, "NULL weights");
+    memcpy(hp + o_w, in->weights, (size_t)nq * 32);
+    cudaStream_t st = g_rank_stream;
+    CU(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    RankParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_queries = nq; p.offsets = (const int32_t*)(dp + o_off); p.kind = dp + o_kind; p.key_id = (const uint32_t*)(dp + o_key);
+    p.file_id = (const uint32_t*)(dp + o_file); p.depth = (const int32_t*)(dp + o_depth); p.entity_match = (const double*)(dp + o_em);
+    p.degree = (const int32_t*)(dp + o_deg); p.flags = dp + o_flags; p.content_len = (const int32_t*)(dp + o_clen);
+    p.vscore = (const double*)(dp + o_vs); p.weights = (const double*)(dp + o_w);
+    p.mode = mode; p.max_per_file = max_per_file; p.max_total = max_total; p.entity_bonus = entity_bonus; p.rel_bonus = rel_bonus;
+    p.out_count = (int32_t*)(dp + r_count); p.out_index = (int32_t*)(dp + r_index); p.out_score = (double*)(dp + r_score);
+    p.out_norm = (double*)(dp + r_norm); p.out_signals = (double*)(dp + r_sig); p.out_sigmask = dp + r_mask; p.out_source = dp + r_src;
+    p.out_leader = (int32_t*)(dp + r_lead);
+    const size_t smem = rank_smem_bytes(std::max(max_c, 1));
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(rank_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaEventRecord(g_rank_ev[0], st));
+    rank_fuse_kernel<<<nq, kRankThreads, smem, st>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g_rank_ev[1], st));
+    CU(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (device_ms) cudaEventElapsedTime(device_ms, g_rank_ev[0], g_rank_ev[1]);
+    memcpy(out_count, hp + r_count, (size_t)nq * 4);
+    memcpy(out_index, hp + r_index, rows * 4);
+    memcpy(out_score, hp + r_score, rows * 8);
+    if (out_norm) memcpy(out_norm, hp + r_norm, rows * 8);
+    if (out_signals) memcpy(out_signals, hp + r_sig, rows * 8 * kRankSignals);
+    if (out_sigmask) memcpy(out_sigmask, hp + r_mask, rows);
+    if (out_source) memcpy(out_source, hp + r_src, rows);
+    if (nc > 0) memcpy(out_leader, hp + r_lead, (size_t)nc * 4);
     return LVS_OK;
 }
 

@@ -118,6 +118,33 @@ int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const u
                           int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                           void* stream);   /* enqueue only: ordered on `stream` */
 
+/* ---- K3: fused hybrid ranking (HybridRanker.rank_results query/ranking/ranker.py:18-226 + ResultScorer scorer.py:9-126
+ *      [mode 0]; ResultReranker.fuse_results / deduplicate / normalize_scores query/reranker.py:29-145 [mode 1]) -------------
+ * Candidates of all queries are concatenated in the reference's insertion order (primary, callers, callees, methods,
+ * parent_classes, child_classes, vector hits); offsets[q]..offsets[q+1] are query q's.  Strings are interned by the caller:
+ * key_id / file_id are dense ids of f"{file_path}:{entity_name}:{start_line}" and of file_path.  All host pointers. */
+typedef struct lvs_rank_batch {
+    int32_t n_queries;
+    const int32_t* offsets;        /* [n_queries + 1] */
+    const uint8_t* kind;           /* 0 primary, 1 caller, 2 callee, 3 method/parent/child, 4 vector hit */
+    const uint32_t* key_id;
+    const uint32_t* file_id;
+    const int32_t* depth;          /* callers/callees: metadata depth (0 is treated as 1, scorer.py:25) */
+    const double* entity_match;    /* 1.0 exact name match, 0.5 substring, 0.0 none (scorer.py:31-35) */
+    const int32_t* degree;         /* total_degree of the entity in the centrality dict, -1 if absent */
+    const uint8_t* flags;          /* bit0 summary, bit1 docstring, bit2 signature, bit3 content present */
+    const int32_t* content_len;    /* vector hits: len(content), -1 if none */
+    const double* vscore;          /* vector hits: similarity score */
+    const double* weights;         /* [n_queries][4]: graph, vector, centrality, context weight (models.py:59-91) */
+} lvs_rank_batch;
+/* Outputs (host, per query max_total rows): leader candidate index within the query, merged score, min-max normalised score,
+ * 7 merged signals (RankingSignal order: graph_match, vector_similarity, centrality, query_entity_match,
+ * relationship_relevance, code_quality, context_richness) + presence mask, source (0 graph, 1 vector, 2 hybrid);
+ * out_leader[total candidates] = leader of every candidate (lets the host fill missing text fields in merge order). */
+int lvs_rank_fuse(const lvs_rank_batch* in, int mode, int max_per_file, int max_total, double entity_bonus, double rel_bonus,
+                  int32_t* out_count, int32_t* out_index, double* out_score, double* out_norm, double* out_signals,
+                  uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the collection's stream) of the kernels of the last lvs_search* call on this handle:
  * [0] query prep  [1] scan / tensor-core kernel(s)  [2] finalize  [3] whole device section; n_launches = kernels launched. */
