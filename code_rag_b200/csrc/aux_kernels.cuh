@@ -134,6 +134,17 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const PrepParams p) {
     if (tid == 0) p.qnorm[qi] = (float)nrm;
 }
 
+// bf16 copy of the unit queries for the tensor-core path: [n_rows_out][k_pad], zero padded in both directions
+__global__ void __launch_bounds__(256) prep_qb16_kernel(const double* q64, int Q, int dim, __nv_bfloat16* out, uint32_t k_pad, uint32_t rows_out) {
+    const uint32_t r = blockIdx.x;
+    if (r >= rows_out) return;
+    for (uint32_t c = threadIdx.x; c < k_pad; c += 256) {
+        double v = 0.0;
+        if ((int)r < Q && (int)c < dim) v = q64[(size_t)r * dim + c];
+        out[(size_t)r * k_pad + c] = __double2bfloat16(v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Filter-only matching (query_vector=None searches, delete-by-filter, count, scroll):
 // appends every live row whose codes satisfy the conjunction to out_rows (unordered), counts all matches.

@@ -40,6 +40,7 @@ struct PwProgram {
 struct FinalizeParams {
     const uint64_t* keys;      // [Q][M]   fast keys (0 = empty)
     const uint64_t* tops;      // [Q][L]   best key of each list
+    const uint64_t* drops;     // [Q][L]   K2 only: bound on what a (full) list dropped, 0 = nothing; nullptr for K1 lists
     uint32_t M;
     uint32_t L;
     uint32_t kp;               // k' candidates to rescore (<= kMaxCand)
@@ -296,32 +297,21 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     if (folded) {
     WarpTopK<KPL> acc;
     acc.init();
-    uint64_t nxt[KPL];
-    uint32_t l = warp;
-    if (l < p.L) {
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) nxt[j] = keys[(size_t)l * KPW + j * 32 + lane];
-    }
-    while (l < p.L) {
-        uint64_t cur[KPL];
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) cur[j] = nxt[j];
-        const uint32_t ln = l + kFinWarps;
-        if (ln < p.L) {
-#pragma unroll
-            for (int j = 0; j < KPL; ++j) nxt[j] = keys[(size_t)ln * KPW + j * 32 + lane];
+    const uint32_t nchunks = p.M / 32u;                  // lists are multiples of 32 keys: walk them as flat 32-key chunks
+    uint32_t ch = warp;
+    uint64_t nxt = ch < nchunks ? keys[(size_t)ch * 32 + lane] : 0ull;
+    while (ch < nchunks) {
+        const uint64_t cur = nxt;
+        const uint32_t cn = ch + kFinWarps;
+        if (cn < nchunks) nxt = keys[(size_t)cn * 32 + lane];
+        uint32_t ball = __ballot_sync(0xFFFFFFFFu, cur > acc.thr);
+        while (ball) {
+            const int src = __ffs(ball) - 1;
+            ball &= ball - 1;
+            const uint64_t kk = shfl_u64(cur, src);
+            if (kk > acc.thr) acc.insert(kk, lane);
         }
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) {
-            uint32_t ball = __ballot_sync(0xFFFFFFFFu, cur[j] > acc.thr);
-            while (ball) {
-                const int src = __ffs(ball) - 1;
-                ball &= ball - 1;
-                const uint64_t kk = shfl_u64(cur[j], src);
-                if (kk > acc.thr) acc.insert(kk, lane);
-            }
-        }
-        l = ln;
+        ch = cn;
     }
 #pragma unroll
     for (int j = 0; j < KPL; ++j) sortbuf[(size_t)warp * KPW + j * 32 + lane] = acc.key[j];
@@ -355,8 +345,24 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         __syncthreads();
     }
     // the fast-score bound for every row that is NOT a candidate
-    const bool lists_dropped_nothing = nsurv < kp;      // fewer keys than k' survive => no list ever overflowed
-    const float t_fast = ncand > 0 ? key_score(ckey[ncand - 1]) : 0.f;
+    // K2 lists are shorter than k': what a full list dropped is bounded by its last key (drops[])
+    uint64_t drop_key = 0ull;
+    if (p.drops != nullptr) {
+        unsigned long long* Dp = reinterpret_cast<unsigned long long*>(scal + 6);
+        if (tid == 0) *Dp = 0ull;
+        __syncthreads();
+        uint64_t t = 0;
+        for (uint32_t i = tid; i < p.L; i += kFinThreads) { const uint64_t v = p.drops[(size_t)qi * p.L + i]; t = v > t ? v : t; }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) { const uint64_t v = shfl_xor_u64(t, o); t = v > t ? v : t; }
+        if (lane == 0 && t) atomicMax(Dp, (unsigned long long)t);
+        __syncthreads();
+        drop_key = *Dp;
+    }
+    const bool lists_dropped_nothing = nsurv < kp && drop_key == 0ull;   // no list ever overflowed
+    float t_fast = ncand > 0 ? key_score(ckey[ncand - 1]) : 0.f;
+    if (nsurv < kp) t_fast = -INFINITY;                 // every kept key is a candidate
+    if (drop_key != 0ull) t_fast = fmaxf(t_fast, key_score(drop_key));
     // ---- 4. exact rescoring: candidate c belongs to CTA c / nrw, warp c % nrw ----
     const uint32_t nrw = (uint32_t)p.n_rescore_warps;
     double* gscore = p.cand_scores + (size_t)qi * kMaxCand;

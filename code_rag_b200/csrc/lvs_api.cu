@@ -11,8 +11,11 @@
 #include <string>
 #include <vector>
 
+#include <cudaTypedefs.h>
+
 #include "aux_kernels.cuh"
 #include "finalize_kernel.cuh"
+#include "gemm_topk_kernel.cuh"
 #include "rank_kernel.cuh"
 #include "scan_kernel.cuh"
 
@@ -112,6 +115,7 @@ struct lvs_collection {
     int last_kind = 0;
 
     Scratch s_qraw, s_q64, s_q32, s_qnorm, s_keys, s_mins, s_flags, s_res, s_stage_dev, s_misc, s_cand;
+    Scratch s_gkeys, s_gtops, s_gdrops, s_qb16, s_tickets, s_dbg;
     Scratch h_pin, h_pin2, h_flags;
 
     // ring of event pairs around the scan launches (read back by lvs_scan_times after a synchronisation)
@@ -138,6 +142,10 @@ struct lvs_collection {
     int opt_stages = 0;   // 0 = as many as fit
     int opt_grid = 0;     // 0 = one CTA per SM
     int opt_force_kpl = 0;
+    int opt_gemm_min_q = 8;   // batches of at least this many queries take the tensor-core path (K2)
+    int opt_path = 0;         // 0 auto, 1 force K1 scan, 2 force K2 (when eligible)
+    int opt_gemm_dbg = 0;
+    int opt_gemm_stages = 0;
 
     std::mutex mu;
 };
@@ -310,7 +318,8 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_arrays(c);
     cudaFree(c->d_max_norm); cudaFree(c->d_pw); cudaFree(c->d_counter);
-    Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc};
+    Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc,
+                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg};
     for (Scratch* s : ds) if (s->p) cudaFree(s->p);
     if (c->h_pin.p) cudaFreeHost(c->h_pin.p);
     if (c->h_pin2.p) cudaFreeHost(c->h_pin2.p);
@@ -725,6 +734,126 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
     return LVS_OK;
 }
 
+// ---- K2: tensor-core path -------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+
+static int get_encode_tiled() {
+    if (g_encode_tiled) return LVS_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(LVS_ECUDA, "cuTensorMapEncodeTiled is not available from the driver (%s)", cudaGetErrorString(e));
+    g_encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    return LVS_OK;
+}
+
+static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
+    if (c->opt_path == 1) return false;
+    if (c->storage != LVS_STORAGE_BF16 || filter) return false;
+    const uint32_t nk = (c->q_stride + kGemmKC - 1) / kGemmKC;
+    if (nk > (uint32_t)kGemmMaxKChunks || c->dim < 64) return false;
+    if (c->n_rows < (int64_t)kGemmN * 64) return false;             // too few tiles to fill the machine / the lists
+    return c->opt_path == 2 || Q >= c->opt_gemm_min_q;
+}
+
+// Enqueue K2 + finalize for queries [0, Q) in batches of up to 256.  No synchronisation.
+static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t search_base, double* d_scores, int64_t* d_rows,
+                        uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches) {
+    int rc;
+    if ((rc = get_encode_tiled()) != LVS_OK) return rc;
+    const int sm = g_lib.sm_count;
+    const uint32_t nk = (c->q_stride + kGemmKC - 1) / kGemmKC;
+    const uint32_t k_pad = nk * kGemmKC;
+    const size_t keys_bytes = (size_t)256 * sm * kGemmList * 8;
+    if ((rc = ensure_dev(c->s_gkeys, keys_bytes)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_gtops, (size_t)256 * sm * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_gdrops, (size_t)256 * sm * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_qb16, (size_t)256 * k_pad * 2)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_cand, (size_t)256 * kMaxCand * 8)) != LVS_OK) return rc;
+    if (c->s_tickets.bytes < 256 * 4) {
+        if ((rc = ensure_dev(c->s_tickets, 256 * 4)) != LVS_OK) return rc;
+        CU(cudaMemsetAsync(c->s_tickets.p, 0, c->s_tickets.bytes, st));
+    }
+    if (c->opt_gemm_dbg) { if ((rc = ensure_dev(c->s_dbg, (size_t)kGemmM * kGemmN * 4)) != LVS_OK) return rc; }
+    // tensor map over the shard: [n_rows][ld] bf16, box = 128 rows x 64 elements, 128-byte swizzle, zero fill out of bounds
+    CUtensorMap tmap;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)c->q_stride, (cuuint64_t)c->n_rows};
+        cuuint64_t gstr[1] = {(cuuint64_t)c->row_bytes};
+        cuuint32_t box[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)kGemmN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_vec, gdim, gstr, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    }
+    uint32_t S = kGemmMaxStages;
+    if (c->opt_gemm_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_gemm_stages);
+    while (S > 2 && gemm_smem_bytes(S) > g_lib.smem_optin) --S;
+    const size_t smem = gemm_smem_bytes(S);
+    static bool attr = false;
+    if (!attr) { CU(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin)); attr = true; }
+    const uint32_t n_tiles = (uint32_t)((c->n_rows + kGemmN - 1) / kGemmN);
+    for (int q0 = 0; q0 < Q; q0 += 256) {
+        const int qb = std::min(256, Q - q0);
+        const uint32_t G = (uint32_t)((qb + kGemmM - 1) / kGemmM);
+        const uint32_t P = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sm / G, n_tiles));
+        prep_qb16_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
+                                                   (__nv_bfloat16*)c->s_qb16.p, k_pad, G * kGemmM);
+        CU(cudaGetLastError());
+        ++*launches;
+        GemmParams gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.qb16 = (const __nv_bfloat16*)c->s_qb16.p; gp.k_pad = k_pad; gp.n_kchunks = nk; gp.n_rows = (uint32_t)c->n_rows;
+        gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S;
+        gp.inv_norm = c->metric == LVS_METRIC_COSINE ? c->d_inv_norm : nullptr; gp.live = c->d_live;
+        gp.out_keys = (uint64_t*)c->s_gkeys.p; gp.out_tops = (uint64_t*)c->s_gtops.p; gp.out_drops = (uint64_t*)c->s_gdrops.p;
+        gp.dbg = c->opt_gemm_dbg ? (float*)c->s_dbg.p : nullptr;
+        cudaEvent_t es = nullptr, ee = nullptr;
+        if (c->opt_timing) {
+            const int slot = c->ring_pos % kEventRing;
+            es = c->ring_ev[2 * slot]; ee = c->ring_ev[2 * slot + 1];
+            c->ring_bytes[slot] = (double)c->n_rows * c->row_bytes;
+            c->ring_pos++;
+            CU(cudaEventRecord(es, st));
+        }
+        gemm_topk_kernel<<<P * G, kGemmThreads, smem, st>>>(tmap, gp);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(LVS_ECUDA, "gemm kernel launch failed: %s (smem=%zu grid=%u)", cudaGetErrorString(e), smem, P * G);
+        ++*launches;
+        if (c->opt_timing) CU(cudaEventRecord(ee, st));
+        if (q0 == 0) { c->first_scan_start = es; c->first_scan_end = ee; }
+
+        FinalizeParams fp;
+        memset(&fp, 0, sizeof(fp));
+        const uint32_t kpw = 32u * kpl;
+        fp.keys = gp.out_keys; fp.tops = gp.out_tops; fp.drops = gp.out_drops;
+        fp.M = P * kGemmList; fp.L = P; fp.kp = kpw; fp.k = (uint32_t)k;
+        fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
+        fp.storage = c->storage; fp.metric = c->metric;
+        fp.q64 = (const double*)c->s_q64.p + (size_t)q0 * c->dim;
+        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)q0;
+        fp.pw = c->d_pw; fp.row_base = c->row_base;
+        fp.eps = 2.2e-3f;    // |bf16(q).row - q.row| <= 2^-9 * sum|q_i row_i| <= 2^-9 for unit vectors, + fp32 accumulation
+        int nrw = kFinWarps;
+        while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
+        fp.n_rescore_warps = nrw;
+        fp.cand_scores = (double*)c->s_cand.p; fp.tickets = (uint32_t*)c->s_tickets.p;
+        fp.out_scores = d_scores + (size_t)q0 * k; fp.out_rows = d_rows + (size_t)q0 * k; fp.out_ties = d_ties + (size_t)q0 * k;
+        fp.out_flags = d_flags + q0; fp.out_counts = d_counts + q0;
+        fp.qnorm = (const float*)c->s_qnorm.p + q0; fp.max_norm = c->d_max_norm;
+        const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
+        const unsigned ncta = (unsigned)std::min<uint32_t>(64u, (kpw + nrw - 1) / nrw);
+        cudaError_t fe = kpl == 1 ? launch_finalize<1>(fp, qb, ncta, fsm, st) : kpl == 2 ? launch_finalize<2>(fp, qb, ncta, fsm, st)
+                       : kpl == 4 ? launch_finalize<4>(fp, qb, ncta, fsm, st) : launch_finalize<8>(fp, qb, ncta, fsm, st);
+        if (fe != cudaSuccess) return fail(LVS_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(fe));
+        ++*launches;
+        if (q0 == 0 && c->opt_timing) CU(cudaEventRecord(c->ev[4], st));
+    }
+    return LVS_OK;
+}
+
 // Core: queries already on the device (raw, `dtype`); outputs are device buffers.  With `async` the work is only
 // enqueued (no escalation, flags stay on the device in d_flags_out); otherwise flagged queries are repeated with a
 // larger candidate set and the host flags are returned.
@@ -776,6 +905,20 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     const uint32_t search_base = base_override >= 0 ? (uint32_t)base_override : c->search_counter + 1;
     int32_t* hf = (int32_t*)c->h_flags.p;
     bool first = true;
+    int kind = 1;
+    if (!only && gemm_eligible(c, Q, filter)) {
+        // K2 for the whole batch; queries whose exactness bound is not met fall through to the K1 levels below
+        kind = 2;
+        rc = enqueue_gemm(c, Q, k, kpl, search_base, d_scores, d_rows, d_ties, d_counts, d_flags, st, &launches);
+        if (rc != LVS_OK) return rc;
+        first = false;
+        pending.clear();
+        if (!async) {
+            CU(cudaMemcpyAsync(hf, d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (int qi = 0; qi < Q; ++qi) if (hf[qi] & 1) pending.push_back(qi);
+        }
+    }
     while (!pending.empty()) {
         rc = enqueue_level(c, pending, k, kpl, filter, fcodes, fwant, nf, search_base, d_scores, d_rows, d_ties, d_counts,
                            d_flags, st, &launches, first);
@@ -790,7 +933,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
         if (!pending.empty()) kpl <<= 1;
     }
     c->last_launches = launches;
-    c->last_kind = 1;
+    c->last_kind = kind;
     c->last_kpl = kpl;
     if (base_override < 0) c->search_counter += (uint32_t)Q;
     if (!async) {
@@ -1116,6 +1259,10 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "grid")) c->opt_grid = value;
     else if (!strcmp(name, "force_kpl")) c->opt_force_kpl = value;
     else if (!strcmp(name, "timing")) c->opt_timing = value ? 1 : 0;
+    else if (!strcmp(name, "gemm_min_q")) c->opt_gemm_min_q = value;
+    else if (!strcmp(name, "path")) c->opt_path = value;
+    else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;
+    else if (!strcmp(name, "gemm_stages")) c->opt_gemm_stages = value;
     else return fail(LVS_EINVAL, "unknown option '%s'", name);
     return LVS_OK;
 }

@@ -214,6 +214,42 @@ def test_odd_dimensions(lib, dim):
         dev.close()
 
 
+@pytest.mark.parametrize("Q,k", [(8, 10), (100, 10), (128, 100), (256, 100), (300, 20)])
+def test_gemm_path_parity(lib, Q, k):
+    """K2 (tcgen05 GEMM + fused top-k) on a bf16 shard: same ids and scores as the oracle's consecutive searches."""
+    n = 24_000
+    x, q = synth.unit_rows(n, 768, seed=3456 + Q, n_queries=Q)
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xb, [None] * n)
+    dev = _dev("gemm", 768, storage="bf16")
+    dev.upsert(xb)
+    dev.delete_rows(np.array([5, 77, 12_345]))
+    ora.deleted[[5, 77, 12_345]] = True
+    res = dev.search(q.astype(np.float64), k)
+    assert dev.last_timing()["kernel"] == "gemm"
+    for i in range(Q):
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16)
+    dev.close()
+
+
+def test_gemm_falls_back_when_bound_fails(lib):
+    """Near-duplicate rows concentrated in one tile defeat the 32-key lists: flagged queries are redone on the K1 path."""
+    n = 16_384
+    x, q = synth.unit_rows(n, 768, seed=11, n_queries=8)
+    rng = np.random.default_rng(3)
+    x[4096:4096 + 120] = q[0] + 0.01 * rng.standard_normal((120, 768)).astype(np.float32)   # 120 close neighbours of query 0
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xb, [None] * n)
+    dev = _dev("gemmfb", 768, storage="bf16")
+    dev.upsert(xb)
+    res = dev.search(q.astype(np.float64), 100)
+    for i in range(8):
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), 100), REL_BF16)
+    dev.close()
+
+
 def test_submit_wait_pipeline(lib):
     """lvs_search_submit / lvs_search_wait: 3 searches in flight are accounted as consecutive reference searches."""
     x, q = synth.unit_rows(9_000, 768, seed=31, n_queries=9)
