@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""K2 probe: 10M x 768 bf16, batches of queries through the tensor-core path; prints kernel / finalize / total times."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "benchmarks"))
+from configs import fill  # noqa: E402
+
+from code_rag_b200.collection import DeviceCollection  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+dev = DeviceCollection("k2", 768, storage="bf16", capacity=n)
+fill(dev, n, 768, "bf16", seed=3456)
+rng = np.random.default_rng(6)
+cfgs = [(256, 100), (256, 10), (128, 10), (64, 100), (64, 10), (16, 10)]
+if len(sys.argv) > 3:
+    cfgs = [(int(sys.argv[2]), int(sys.argv[3]))]
+for Q, k in cfgs:
+    qs = rng.standard_normal((Q, 768))
+    for rep in range(3):
+        res = dev.search(qs, k)
+    t = dev.last_timing()
+    print(json.dumps({"Q": Q, "k": k, **t, "flagged": int(res.flags.sum()),
+                      "gemm_gbs": n * 1536 / (t["scan_ms"] * 1e-3) / 1e9, "gemm_tflops": 2.0 * Q * n * 768 / (t["scan_ms"] * 1e-3) / 1e12}), flush=True)
+dev.close()

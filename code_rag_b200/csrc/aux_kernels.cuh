@@ -134,14 +134,29 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const PrepParams p) {
     if (tid == 0) p.qnorm[qi] = (float)nrm;
 }
 
-// bf16 copy of the unit queries for the tensor-core path: [n_rows_out][k_pad], zero padded in both directions
-__global__ void __launch_bounds__(256) prep_qb16_kernel(const double* q64, int Q, int dim, __nv_bfloat16* out, uint32_t k_pad, uint32_t rows_out) {
+// bf16 copy of the unit queries for the tensor-core path: [rows_out][k_pad], zero padded in both directions, plus the
+// per-query bound on |bf16(q).x - q.x| for unit rows x:  ||q - bf16(q)||_2  (Cauchy-Schwarz) + fp32 accumulation slack.
+__global__ void __launch_bounds__(256) prep_qb16_kernel(const double* q64, int Q, int dim, __nv_bfloat16* out, uint32_t k_pad, uint32_t rows_out,
+                                                        float* eps_out) {
+    __shared__ double red[8];
     const uint32_t r = blockIdx.x;
     if (r >= rows_out) return;
+    double e2 = 0.0;
     for (uint32_t c = threadIdx.x; c < k_pad; c += 256) {
         double v = 0.0;
         if ((int)r < Q && (int)c < dim) v = q64[(size_t)r * dim + c];
-        out[(size_t)r * k_pad + c] = __double2bfloat16(v);
+        const __nv_bfloat16 b = __double2bfloat16(v);
+        out[(size_t)r * k_pad + c] = b;
+        const double d = v - (double)__bfloat162float(b);
+        e2 = fma(d, d, e2);
+    }
+    e2 = warp_sum_f64(e2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e2;
+    __syncthreads();
+    if (threadIdx.x == 0 && (int)r < Q) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        eps_out[r] = (float)(sqrt(t) * 1.0001 + 1.0e-4);
     }
 }
 

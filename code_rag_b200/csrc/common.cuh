@@ -96,6 +96,12 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
     hi = __shfl_sync(0xFFFFFFFFu, hi, src);
     return ((uint64_t)hi << 32) | lo;
 }
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_up_sync(0xFFFFFFFFu, lo, d);
+    hi = __shfl_up_sync(0xFFFFFFFFu, hi, d);
+    return ((uint64_t)hi << 32) | lo;
+}
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) {
     return __longlong_as_double((long long)shfl_xor_u64((uint64_t)__double_as_longlong(v), m));
 }

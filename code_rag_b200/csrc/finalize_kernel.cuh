@@ -57,6 +57,7 @@ struct FinalizeParams {
     uint32_t search_no;        // counter value of query 0 of this launch (query qi is search_no + qi)
     const PwProgram* pw;
     float eps;                 // bound on |fast score - exact score| for unit vectors
+    const float* eps_q;        // [Q] per-query bound (K2: bf16 rounding of the query), nullptr => eps
     const float* qnorm;        // [Q] ||q||      } dot metric: the bound scales with ||q|| * max ||row||
     const float* max_norm;     // [1] max ||row|| }
     int64_t row_base;          // global row of local row 0
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
             int32_t flag = 0;
             if (!lists_dropped_nothing && ncand >= p.k) {
                 // rows outside the candidate set have exact score <= t_fast + eps
-                double eps = (double)p.eps;
+                double eps = p.eps_q != nullptr ? (double)p.eps_q[qi] : (double)p.eps;
                 if (p.metric == LVS_METRIC_DOT) eps *= (double)p.qnorm[qi] * (double)(*p.max_norm);
                 if (!(cscore[c] > (double)t_fast + eps)) flag = 1;
                 if (ncand == kp && kp == p.k) flag = 1;  // no margin at all

@@ -4,22 +4,26 @@
 // Replaces, for Q >= 8 queries at a time, the O(Q*N*D) loop that the reference delegates to Qdrant behind
 // QdrantManager.search (reference src/lattice/embeddings/client.py:132-157) - there one gRPC call per query.
 //
-// Orientation: D[128 queries x 128 corpus rows] += A[128 x K] * B[128 x K]^T, bf16 inputs, fp32 accumulate.
+// Orientation: D[128 queries x 64 corpus rows] += A[128 x K] * B[64 x K]^T, bf16 inputs, fp32 accumulate.
 //   * A (the queries of this CTA, unit-norm, rounded to bf16) is loaded ONCE into tensor memory: 128 lanes (one per
 //     query) x K/2 32-bit columns (two bf16 per column) - 384 of the 512 TMEM columns for K = 768.  The MMA reads A
-//     from TMEM ("TS" form), so shared memory is left entirely to the corpus pipeline.
-//   * B = 128 corpus rows x 64 K-elements per stage (16 KB, K-major, 128-byte swizzle), streamed with
-//     cp.async.bulk.tensor.2d (TMA, SASS UTMALDG) into a 12-stage mbarrier ring: ~192 KB in flight per SM.
-//   * D lives in the remaining 128 TMEM columns.  The epilogue warps read it with tcgen05.ld; thread = query, so each
-//     thread walks the 128 scores of "its" query, multiplies by 1/||row|| (cosine) and keeps a sorted top-32 in
-//     registers (a score is looked at again only if it beats the thread's 32nd best).
+//     from TMEM ("TS" form), so shared memory is left to the corpus pipeline.
+//   * B = 64 corpus rows x 64 K-elements per stage (8 KB, K-major, 128-byte swizzle), streamed with
+//     cp.async.bulk.tensor.2d (TMA, SASS UTMALDG) into an 18-stage mbarrier ring: ~144 KB in flight per SM.
+//   * D is double buffered in the remaining 2 x 64 TMEM columns: the MMA of tile t+1 overlaps the epilogue of tile t.
+//   * Epilogue (4 warps, thread = query = TMEM lane): tcgen05.ld the 64 scores of the tile, release the accumulator,
+//     scale by 1/||row|| (NaN for tombstones and rows past the end, so they never pass), compare with the query's
+//     current 32nd-best score.  Passing (query, row, score) items go to a per-warp shared-memory queue by ballot; the
+//     queue is drained WARP-COOPERATIVELY into sorted 32-key lists in shared memory (one list per query: lane j holds
+//     key j, the insertion position is a ballot/popc, the shift is one shuffle), so the rare inserts cost ~15
+//     full-warp instructions instead of a 32-step single-lane chain.
 // Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane) + TMEM allocation,
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 // More than 128 queries: G = ceil(Q/128) CTAs ("a pair") walk the same tile sequence for different query groups; the
 // second reader of a tile hits the 126 MB L2, so HBM still sees every row once.
 //
-// Exactness: lists hold 32 keys per (CTA, query); the finalize kernel rescoring proves the result against the bound
-// max(k'-th kept fast score, largest dropped score) + eps and the host repeats flagged queries on the K1 path.
+// Exactness: lists hold 32 keys per (CTA, query); the finalize kernel proves the result against the bound
+// max(k'-th kept fast score, largest dropped score) + eps_q and the host repeats flagged queries on the K1 path.
 // Algorithmic bytes per launch = rows x row_bytes; FLOPs = 2 * Q * rows * K.
 #pragma once
 #include <cuda.h>
@@ -30,20 +34,21 @@ namespace lvs {
 
 constexpr int kGemmThreads = 192;
 constexpr int kGemmM = 128;            // queries per CTA (TMEM lanes)
-constexpr int kGemmN = 128;            // corpus rows per tile (accumulator columns)
+constexpr int kGemmN = 64;             // corpus rows per tile (accumulator columns per buffer)
 constexpr int kGemmKC = 64;            // K elements per pipeline stage (= one 128-byte swizzle row)
-constexpr int kGemmStageBytes = kGemmN * kGemmKC * 2;   // 16 KB
-constexpr int kGemmMaxStages = 12;
+constexpr int kGemmStageBytes = kGemmN * kGemmKC * 2;   // 8 KB
+constexpr int kGemmMaxStages = 18;
 constexpr int kGemmList = 32;          // keys kept per (CTA, query)
-constexpr int kGemmMaxKChunks = 12;    // A occupies 32 columns per chunk: 12 * 32 + 128 (D) = 512 TMEM columns
+constexpr int kGemmMaxKChunks = 12;    // A occupies 32 columns per chunk: 12 * 32 + 2 * 64 (D) = 512 TMEM columns
 constexpr uint32_t kGemmDCol = 384;    // first accumulator column
+constexpr int kGemmQueue = 256;        // pending items per epilogue warp
 
 struct GemmParams {
     const __nv_bfloat16* qb16;   // [n_groups * 128][k_pad] unit queries rounded to bf16, zero padded
     uint32_t k_pad;              // n_kchunks * 64
     uint32_t n_kchunks;
     uint32_t n_rows;
-    uint32_t n_tiles;            // ceil(n_rows / 128)
+    uint32_t n_tiles;            // ceil(n_rows / 64)
     uint32_t n_groups;           // G: CTAs per pair
     uint32_t n_pairs;            // P: lists per query
     uint32_t n_stages;
@@ -52,11 +57,13 @@ struct GemmParams {
     uint64_t* out_keys;          // [n_groups * 128][P][32]
     uint64_t* out_tops;          // [n_groups * 128][P]  best key of the list
     uint64_t* out_drops;         // [n_groups * 128][P]  32nd key when the list is full (bound on what was dropped), else 0
-    float* dbg;                  // optional: CTA 0 dumps its first accumulator tile [128 x 128] (already scaled)
+    float* dbg;                  // optional: CTA 0 dumps its first accumulator tile [128 x 64] (already scaled)
 };
 
+// shared memory: [stages][lists 128*32*8][queue keys 4*256*8][queue lanes 4*256][inv 2*64*4][thr 128*4][barriers]
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages) {
-    return 1024 /* alignment slack */ + (size_t)n_stages * kGemmStageBytes + 2 * kGemmN * 4 + (2 * kGemmMaxStages + 4) * 8 + 16;
+    return 1024 /* alignment slack */ + (size_t)n_stages * kGemmStageBytes + (size_t)kGemmM * kGemmList * 8 + 4 * kGemmQueue * 8 +
+           4 * kGemmQueue + 2 * kGemmN * 4 + kGemmM * 4 + (2 * kGemmMaxStages + 8) * 8 + 16;
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -103,13 +110,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     extern __shared__ uint8_t gsm_raw[];
     uint8_t* gsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t S = p.n_stages;
-    uint8_t* stages = gsm;                                                   // S x 16 KB, 1024-byte aligned
-    float* inv_sm = reinterpret_cast<float*>(gsm + (size_t)S * kGemmStageBytes);          // [2][128]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(inv_sm + 2 * kGemmN);
+    uint8_t* stages = gsm;                                                   // S x 8 KB, 1024-byte aligned
+    uint64_t* lists = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kGemmStageBytes);     // [128][32] sorted descending
+    uint64_t* wq_key = lists + kGemmM * kGemmList;                           // [4][kGemmQueue]
+    uint8_t* wq_lane = reinterpret_cast<uint8_t*>(wq_key + 4 * kGemmQueue);  // [4][kGemmQueue]
+    float* inv_sm = reinterpret_cast<float*>(wq_lane + 4 * kGemmQueue);      // [2][64]
+    float* thr_sm = inv_sm + 2 * kGemmN;                                     // [128]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(thr_sm + kGemmM);
     uint64_t* empty_bar = full_bar + kGemmMaxStages;
-    uint64_t* tmem_full = empty_bar + kGemmMaxStages;
-    uint64_t* tmem_empty = tmem_full + 1;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    uint64_t* tmem_full = empty_bar + kGemmMaxStages;                        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                                    // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t group = blockIdx.x % p.n_groups;
@@ -118,14 +129,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
 
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         mbar_fence_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = tid; i < kGemmM * kGemmList; i += kGemmThreads) lists[i] = 0ull;
+    for (int i = tid; i < kGemmM; i += kGemmThreads) thr_sm[i] = -INFINITY;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -166,12 +178,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N = 128, M = 128
+            // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N = 64, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGemmN >> 3) << 17) | ((uint32_t)(kGemmM >> 4) << 24);
-            const uint32_t tmem_d = tmem_base + kGemmDCol;
             uint32_t it = 0;
             for (uint32_t lt = 0; lt < my_tiles; ++lt) {
-                mbar_wait(tmem_empty, (lt & 1u) ^ 1u);          // the epilogue has drained the accumulator
+                const uint32_t buf = lt & 1u;
+                const uint32_t tmem_d = tmem_base + kGemmDCol + buf * kGemmN;
+                mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
                 tc_fence_after();
                 for (uint32_t kc = 0; kc < nk; ++kc, ++it) {
                     const uint32_t s = it % S;
@@ -185,69 +198,95 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                     }
                     tc_commit(&empty_bar[s]);                    // frees the stage when these MMAs have read it
                 }
-                tc_commit(tmem_full);                            // accumulator of this tile is complete
+                tc_commit(&tmem_full[buf]);                      // accumulator of this tile is complete
             }
         }
     } else {
         // ================================ epilogue: thread = query ================================
         const uint32_t lq = warp & 3;
         const uint32_t et = lq * 32 + lane;                      // 0..127: TMEM lane == query within the group
-        float ls[kGemmList];
-        uint32_t lr[kGemmList];
-#pragma unroll
-        for (int j = 0; j < kGemmList; ++j) { ls[j] = -INFINITY; lr[j] = 0xFFFFFFFFu; }
+        uint64_t* my_q_key = wq_key + lq * kGemmQueue;
+        uint8_t* my_q_lane = wq_lane + lq * kGemmQueue;
+        uint64_t* warp_lists = lists + (size_t)lq * 32 * kGemmList;
         float thr = -INFINITY;
-        const uint32_t taddr = tmem_base + ((lq * 32u) << 16) + kGemmDCol;
+        uint32_t qcnt = 0;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+
+        // warp-cooperative drain of this warp's queue into the sorted per-query lists (lane j <-> key j)
+        auto drain = [&]() {
+            __syncwarp();
+            for (uint32_t i = 0; i < qcnt; ++i) {
+                const uint64_t key = my_q_key[i];
+                const uint32_t ql = my_q_lane[i];
+                uint64_t* L = warp_lists + ql * kGemmList;
+                const uint64_t cur = L[lane];
+                const uint32_t pos = __popc(__ballot_sync(0xFFFFFFFFu, cur > key));
+                if (pos < (uint32_t)kGemmList) {
+                    const uint64_t up = shfl_up_u64(cur, 1);
+                    const uint64_t nv = (uint32_t)lane < pos ? cur : ((uint32_t)lane == pos ? key : up);
+                    L[lane] = nv;
+                    if (lane == kGemmList - 1) thr_sm[lq * 32 + ql] = nv != 0ull ? key_score(nv) : -INFINITY;
+                }
+                __syncwarp();
+            }
+            qcnt = 0;
+            __syncwarp();
+            thr = thr_sm[et];
+        };
+
         for (uint32_t lt = 0; lt < my_tiles; ++lt) {
             const uint32_t tile = pair + lt * p.n_pairs;
             const uint32_t row0 = tile * kGemmN;
-            float* inv = inv_sm + (lt & 1u) * kGemmN;
-            {
+            const uint32_t buf = lt & 1u;
+            float* inv = inv_sm + buf * kGemmN;
+            if (et < (uint32_t)kGemmN) {
                 const uint32_t r = row0 + et;
-                inv[et] = (r < p.n_rows) ? (p.inv_norm ? p.inv_norm[r] : 1.0f) : 0.0f;
+                float f = __int_as_float(0x7FC00000);          // NaN: never passes a comparison
+                if (r < p.n_rows && p.live[r] != 0) f = p.inv_norm ? p.inv_norm[r] : 1.0f;
+                inv[et] = f;
             }
             named_bar_sync(2, 128);
-            mbar_wait(tmem_full, lt & 1u);
+            mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (uint32_t cb = 0; cb < kGemmN / 32; ++cb) {
-                uint32_t v[32];
-                tc_ld32(taddr + cb * 32u, v);
-                tc_wait_ld();
-                if (cb == kGemmN / 32 - 1) {
-                    // all of this tile's accumulator is in registers: let the MMA warp start the next tile
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
-                }
+            const uint32_t taddr = tmem_base + ((lq * 32u) << 16) + kGemmDCol + buf * kGemmN;
+            uint32_t v0[32], v1[32];
+            tc_ld32(taddr, v0);
+            tc_ld32(taddr + 32u, v1);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);        // the MMA warp may overwrite this accumulator now
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const uint32_t col = cb * 32u + c;
-                    const float sc = __uint_as_float(v[c]) * inv[col];
+                    const uint32_t col = h * 32 + c;
+                    const float sc = __uint_as_float(h == 0 ? v0[c] : v1[c]) * inv[col];
                     if (p.dbg != nullptr && blockIdx.x == 0 && lt == 0) p.dbg[(size_t)et * kGemmN + col] = sc;
-                    const uint32_t row = row0 + col;
-                    bool pass = (row < p.n_rows) && (sc > thr);
-                    if (__any_sync(0xFFFFFFFFu, pass)) {
-                        if (pass) pass = p.live[row] != 0;
+                    const bool pass = sc > thr;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+                    if (m) {
                         if (pass) {
-                            float cs = sc; uint32_t cr = row;
-#pragma unroll
-                            for (int j = 0; j < kGemmList; ++j) {
-                                if (cs > ls[j]) { const float ts = ls[j]; const uint32_t tr = lr[j]; ls[j] = cs; lr[j] = cr; cs = ts; cr = tr; }
-                            }
-                            thr = ls[kGemmList - 1];
+                            const uint32_t slot = qcnt + __popc(m & lt_mask);
+                            my_q_key[slot] = make_key(sc, row0 + col);
+                            my_q_lane[slot] = (uint8_t)lane;
                         }
+                        qcnt += __popc(m);
+                        if (qcnt > (uint32_t)(kGemmQueue - 32)) drain();
                     }
                 }
             }
+            if (qcnt) drain();
         }
-        // ---- write this (CTA, query) list ----
-        const size_t q = (size_t)group * kGemmM + et;
-        uint64_t* dst = p.out_keys + (q * p.n_pairs + pair) * kGemmList;
-#pragma unroll
-        for (int j = 0; j < kGemmList; ++j) dst[j] = lr[j] != 0xFFFFFFFFu ? make_key(ls[j], lr[j]) : 0ull;
-        p.out_tops[q * p.n_pairs + pair] = lr[0] != 0xFFFFFFFFu ? make_key(ls[0], lr[0]) : 0ull;
-        p.out_drops[q * p.n_pairs + pair] = lr[kGemmList - 1] != 0xFFFFFFFFu ? make_key(ls[kGemmList - 1], lr[kGemmList - 1]) : 0ull;
+        // ---- write this warp's 32 (CTA, query) lists ----
+        __syncwarp();
+        for (uint32_t ql = 0; ql < 32; ++ql) {
+            const size_t q = (size_t)group * kGemmM + lq * 32 + ql;
+            const uint64_t kv = warp_lists[ql * kGemmList + lane];
+            p.out_keys[(q * p.n_pairs + pair) * kGemmList + lane] = kv;
+            if (lane == 0) p.out_tops[q * p.n_pairs + pair] = kv;
+            if (lane == kGemmList - 1) p.out_drops[q * p.n_pairs + pair] = kv;
+        }
     }
 
     tc_fence_before();

@@ -115,7 +115,7 @@ struct lvs_collection {
     int last_kind = 0;
 
     Scratch s_qraw, s_q64, s_q32, s_qnorm, s_keys, s_mins, s_flags, s_res, s_stage_dev, s_misc, s_cand;
-    Scratch s_gkeys, s_gtops, s_gdrops, s_qb16, s_tickets, s_dbg;
+    Scratch s_gkeys, s_gtops, s_gdrops, s_qb16, s_tickets, s_dbg, s_geps;
     Scratch h_pin, h_pin2, h_flags;
 
     // ring of event pairs around the scan launches (read back by lvs_scan_times after a synchronisation)
@@ -319,7 +319,7 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     free_arrays(c);
     cudaFree(c->d_max_norm); cudaFree(c->d_pw); cudaFree(c->d_counter);
     Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc,
-                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg};
+                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg, &c->s_geps};
     for (Scratch* s : ds) if (s->p) cudaFree(s->p);
     if (c->h_pin.p) cudaFreeHost(c->h_pin.p);
     if (c->h_pin2.p) cudaFreeHost(c->h_pin2.p);
@@ -770,6 +770,8 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
     if ((rc = ensure_dev(c->s_gtops, (size_t)256 * sm * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_gdrops, (size_t)256 * sm * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_qb16, (size_t)256 * k_pad * 2)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_geps, (size_t)256 * 4)) != LVS_OK) return rc;
+    kpl = std::min(8, 2 * kpl);      // the bf16-query scores are coarser than K1's: rescore a larger candidate set
     if ((rc = ensure_dev(c->s_cand, (size_t)256 * kMaxCand * 8)) != LVS_OK) return rc;
     if (c->s_tickets.bytes < 256 * 4) {
         if ((rc = ensure_dev(c->s_tickets, 256 * 4)) != LVS_OK) return rc;
@@ -800,7 +802,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         const uint32_t G = (uint32_t)((qb + kGemmM - 1) / kGemmM);
         const uint32_t P = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sm / G, n_tiles));
         prep_qb16_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
-                                                   (__nv_bfloat16*)c->s_qb16.p, k_pad, G * kGemmM);
+                                                   (__nv_bfloat16*)c->s_qb16.p, k_pad, G * kGemmM, (float*)c->s_geps.p);
         CU(cudaGetLastError());
         ++*launches;
         GemmParams gp;
@@ -835,7 +837,8 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         fp.q64 = (const double*)c->s_q64.p + (size_t)q0 * c->dim;
         fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)q0;
         fp.pw = c->d_pw; fp.row_base = c->row_base;
-        fp.eps = 2.2e-3f;    // |bf16(q).row - q.row| <= 2^-9 * sum|q_i row_i| <= 2^-9 for unit vectors, + fp32 accumulation
+        fp.eps = 2.2e-3f;    // fallback; the per-query bound ||q - bf16(q)||_2 + accumulation slack is used
+        fp.eps_q = c->metric == LVS_METRIC_COSINE ? (const float*)c->s_geps.p : nullptr;
         int nrw = kFinWarps;
         while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
         fp.n_rescore_warps = nrw;
@@ -933,7 +936,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
         if (!pending.empty()) kpl <<= 1;
     }
     c->last_launches = launches;
-    c->last_kind = kind;
+    if (!only) c->last_kind = kind;
     c->last_kpl = kpl;
     if (base_override < 0) c->search_counter += (uint32_t)Q;
     if (!async) {
