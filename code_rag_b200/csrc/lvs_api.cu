@@ -146,6 +146,7 @@ struct lvs_collection {
     int opt_path = 0;         // 0 auto, 1 force K1 scan, 2 force K2 (when eligible)
     int opt_gemm_dbg = 0;
     int opt_gemm_stages = 0;
+    int opt_gemm_prefetch = 2;
 
     std::mutex mu;
 };
@@ -765,10 +766,10 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
     const int sm = g_lib.sm_count;
     const uint32_t nk = (c->q_stride + kGemmKC - 1) / kGemmKC;
     const uint32_t k_pad = nk * kGemmKC;
-    const size_t keys_bytes = (size_t)256 * sm * kGemmList * 8;
+    const size_t keys_bytes = (size_t)256 * sm * 2 * kGemmList * 8;
     if ((rc = ensure_dev(c->s_gkeys, keys_bytes)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_gtops, (size_t)256 * sm * 8)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_gdrops, (size_t)256 * sm * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_gtops, (size_t)256 * sm * 2 * 8)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_gdrops, (size_t)256 * sm * 2 * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_qb16, (size_t)256 * k_pad * 2)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_geps, (size_t)256 * 4)) != LVS_OK) return rc;
     kpl = std::min(8, 2 * kpl);      // the bf16-query scores are coarser than K1's: rescore a larger candidate set
@@ -777,7 +778,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         if ((rc = ensure_dev(c->s_tickets, 256 * 4)) != LVS_OK) return rc;
         CU(cudaMemsetAsync(c->s_tickets.p, 0, c->s_tickets.bytes, st));
     }
-    if (c->opt_gemm_dbg) { if ((rc = ensure_dev(c->s_dbg, (size_t)kGemmM * kGemmN * 4)) != LVS_OK) return rc; }
+    if (c->opt_gemm_dbg & 1) { if ((rc = ensure_dev(c->s_dbg, (size_t)kGemmM * kGemmN * 4)) != LVS_OK) return rc; }
     // tensor map over the shard: [n_rows][ld] bf16, box = 128 rows x 64 elements, 128-byte swizzle, zero fill out of bounds
     CUtensorMap tmap;
     {
@@ -810,8 +811,10 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         gp.qb16 = (const __nv_bfloat16*)c->s_qb16.p; gp.k_pad = k_pad; gp.n_kchunks = nk; gp.n_rows = (uint32_t)c->n_rows;
         gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S;
         gp.inv_norm = c->metric == LVS_METRIC_COSINE ? c->d_inv_norm : nullptr; gp.live = c->d_live;
+        gp.base = c->d_vec; gp.row_bytes = c->row_bytes; gp.prefetch_tiles = (uint32_t)std::max(0, c->opt_gemm_prefetch);
         gp.out_keys = (uint64_t*)c->s_gkeys.p; gp.out_tops = (uint64_t*)c->s_gtops.p; gp.out_drops = (uint64_t*)c->s_gdrops.p;
-        gp.dbg = c->opt_gemm_dbg ? (float*)c->s_dbg.p : nullptr;
+        gp.dbg = (c->opt_gemm_dbg & 1) ? (float*)c->s_dbg.p : nullptr;
+        gp.dbg_mode = (uint32_t)(c->opt_gemm_dbg >> 1);
         cudaEvent_t es = nullptr, ee = nullptr;
         if (c->opt_timing) {
             const int slot = c->ring_pos % kEventRing;
@@ -831,7 +834,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         memset(&fp, 0, sizeof(fp));
         const uint32_t kpw = 32u * kpl;
         fp.keys = gp.out_keys; fp.tops = gp.out_tops; fp.drops = gp.out_drops;
-        fp.M = P * kGemmList; fp.L = P; fp.kp = kpw; fp.k = (uint32_t)k;
+        fp.M = 2 * P * kGemmList; fp.L = 2 * P; fp.kp = kpw; fp.k = (uint32_t)k;   // two lists per CTA and query
         fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
         fp.storage = c->storage; fp.metric = c->metric;
         fp.q64 = (const double*)c->s_q64.p + (size_t)q0 * c->dim;
@@ -1266,6 +1269,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;
     else if (!strcmp(name, "gemm_stages")) c->opt_gemm_stages = value;
+    else if (!strcmp(name, "gemm_prefetch")) c->opt_gemm_prefetch = value;
     else return fail(LVS_EINVAL, "unknown option '%s'", name);
     return LVS_OK;
 }
