@@ -42,7 +42,7 @@ struct UpsertParams {
     uint32_t* codes[kMaxFilterCols];
     const uint32_t* codes_src;  // [n][n_cols] row-major, or nullptr => kNullCode
     int n_cols;
-    float* max_norm;            // running max ||row|| (dot metric error bound)
+    float* max_norm;            // [0] running max ||row|| (dot metric error bound), [1] running max | ||row|| - 1 | (bf16 storage)
 };
 
 __global__ void __launch_bounds__(256) upsert_kernel(const UpsertParams p) {
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256) upsert_kernel(const UpsertParams p) {
             if (lane == 0) {
                 const double n2 = sqrt(ss2);
                 p.inv_norm[row] = n2 > 0.0 ? (float)(1.0 / n2) : 0.f;
+                atomicMax(reinterpret_cast<int*>(p.max_norm + 1), __float_as_int((float)fabs(n2 - 1.0) * 1.0000002f));
                 if (p.metric == LVS_METRIC_DOT) atomicMax(reinterpret_cast<int*>(p.max_norm), __float_as_int((float)n2 * 1.0000002f));
             }
         }

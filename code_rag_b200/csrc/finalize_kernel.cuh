@@ -4,8 +4,8 @@
 // engine behind the reference's QdrantManager.search (reference src/lattice/embeddings/client.py:132-157) -
 // scores in float64 on a float32 matrix that it re-normalises IN PLACE on every cosine search
 // (oracle/qdrant_local.py, point 2).  To return bit-identical id lists this kernel
-//   1. selects the k' best fast keys out of the per-CTA lists (8 warps fold the lists into register top-k' lists
-//      with the scan's threshold-and-insert step, the 8 lists are ranked in shared memory),
+//   1. selects the k' best fast keys out of the per-CTA lists (threshold = k'-th largest list maximum; when too many keys
+//      survive it, an exact MSB-first radix select over the keys), then ranks the survivors in shared memory,
 //   2. recomputes each candidate's score the way local mode does: float32 row (for bf16 storage:
 //      float32(row / ||row||_f64), i.e. what local mode would have stored), the per-search float32 in-place
 //      re-normalisation replayed `searches since the row was written` times (numpy's pair-wise float32 row
@@ -58,6 +58,7 @@ struct FinalizeParams {
     const PwProgram* pw;
     float eps;                 // bound on |fast score - exact score| for unit vectors
     const float* eps_q;        // [Q] per-query bound (K2: bf16 rounding of the query), nullptr => eps
+    float eps_add;             // added to eps_q (K2 on unit-norm shards: the norm deviation it ignores)
     const float* qnorm;        // [Q] ||q||      } dot metric: the bound scales with ||q|| * max ||row||
     const float* max_norm;     // [1] max ||row|| }
     int64_t row_base;          // global row of local row 0
@@ -74,7 +75,7 @@ struct FinalizeParams {
 __host__ __device__ inline size_t finalize_smem_bytes(int dim_pad, int n_rescore_warps) {
     size_t b = 0;
     b += (size_t)kSortCap * 8;                    // merged warp lists / sort buffer
-    b += 64 + ((sizeof(PwProgram) + 15) & ~(size_t)15);   // scalars + pair-wise program
+    b += 64 + 1024 + ((sizeof(PwProgram) + 15) & ~(size_t)15);   // scalars + radix histogram + pair-wise program
     b += (size_t)kMaxCand * (8 + 8 + 8 + 4 + 4);  // cand key, score, tie, row, rank
     b = (b + 15) & ~(size_t)15;
     b += (size_t)dim_pad * 8;                     // float64 query
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     extern __shared__ __align__(16) uint8_t fsm[];
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(fsm);
     uint32_t* scal = reinterpret_cast<uint32_t*>(fsm + (size_t)kSortCap * 8);   // [3]=is_last
-    PwProgram* pws = reinterpret_cast<PwProgram*>(scal + 16);
+    uint32_t* hist = scal + 16;                                                  // [256] radix-select histogram
+    PwProgram* pws = reinterpret_cast<PwProgram*>(hist + 256);
     uint8_t* cp = reinterpret_cast<uint8_t*>(pws) + ((sizeof(PwProgram) + 15) & ~(size_t)15);
     uint64_t* ckey = reinterpret_cast<uint64_t*>(cp);  cp += (size_t)kMaxCand * 8;
     double* cscore = reinterpret_cast<double*>(cp);    cp += (size_t)kMaxCand * 8;
@@ -294,29 +296,57 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         }
         __syncthreads();
     }
-    // ---- 1b. general path: per-warp fold of the lists into register top-k' lists ----
+    // ---- 1b. general path: exact radix select of the kp-th largest key (MSB first, 8 bits per pass over the keys in L2);
+    //          stops as soon as the keys at or above the current bucket fit the sort buffer
     if (folded) {
-    WarpTopK<KPL> acc;
-    acc.init();
-    const uint32_t nchunks = p.M / 32u;                  // lists are multiples of 32 keys: walk them as flat 32-key chunks
-    uint32_t ch = warp;
-    uint64_t nxt = ch < nchunks ? keys[(size_t)ch * 32 + lane] : 0ull;
-    while (ch < nchunks) {
-        const uint64_t cur = nxt;
-        const uint32_t cn = ch + kFinWarps;
-        if (cn < nchunks) nxt = keys[(size_t)cn * 32 + lane];
-        uint32_t ball = __ballot_sync(0xFFFFFFFFu, cur > acc.thr);
-        while (ball) {
-            const int src = __ffs(ball) - 1;
-            ball &= ball - 1;
-            const uint64_t kk = shfl_u64(cur, src);
-            if (kk > acc.thr) acc.insert(kk, lane);
+        uint64_t prefix = 0, mask = 0;
+        uint32_t remaining = kp;                         // rank still to be located inside the current prefix bucket
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            hist[tid] = 0;                               // kFinThreads == 256
+            __syncthreads();
+            for (uint32_t i = tid; i < p.M; i += kFinThreads) {
+                const uint64_t v = keys[i];
+                if (v != 0ull && (v & mask) == prefix) atomicAdd(&hist[(uint32_t)(v >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t cum = 0, digit = 0, rem = 0, stop = 1;
+                for (int b = 255; b >= 0; --b) {
+                    if (cum + hist[b] >= remaining) {
+                        digit = (uint32_t)b; rem = remaining - cum;
+                        // keys above the bucket: (kp - remaining) + cum; with the bucket itself they must fit the buffer
+                        stop = ((kp - remaining) + cum + hist[b] <= kFinWarps * KPW) ? 1u : 0u;
+                        break;
+                    }
+                    cum += hist[b];
+                    if (b == 0) { digit = 0; rem = 0; stop = 1; }   // fewer than kp keys in this bucket chain: keep everything
+                }
+                scal[0] = digit; scal[1] = rem; scal[2] = stop;
+            }
+            __syncthreads();
+            const uint32_t digit = scal[0], rem = scal[1], stop = scal[2];
+            __syncthreads();
+            if (rem == 0) { mask = ~0ull; prefix = 1ull; break; }   // every non-empty key qualifies
+            prefix |= (uint64_t)digit << shift;
+            mask |= 0xFFull << shift;
+            remaining = rem;
+            if (stop) break;
         }
-        ch = cn;
-    }
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) sortbuf[(size_t)warp * KPW + j * 32 + lane] = acc.key[j];
-    __syncthreads();
+        // gather the keys >= prefix (lower bits zero): at most 8*KPW of them by construction
+        if (tid == 0) scal[0] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < p.M; i += kFinThreads) {
+            const uint64_t v = keys[i];
+            if (v != 0ull && v >= prefix) {
+                const uint32_t pos = atomicAdd(&scal[0], 1u);
+                if (pos < kFinWarps * KPW) sortbuf[pos] = v;
+            }
+        }
+        __syncthreads();
+        const uint32_t got = min(scal[0], kFinWarps * KPW);
+        for (uint32_t i = got + tid; i < kFinWarps * KPW; i += kFinThreads) sortbuf[i] = 0ull;
+        __syncthreads();
     }
     // ---- 2. rank the 8*KPW merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
     const uint32_t nmerged = kFinWarps * KPW;
@@ -420,7 +450,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
             int32_t flag = 0;
             if (!lists_dropped_nothing && ncand >= p.k) {
                 // rows outside the candidate set have exact score <= t_fast + eps
-                double eps = p.eps_q != nullptr ? (double)p.eps_q[qi] : (double)p.eps;
+                double eps = p.eps_q != nullptr ? (double)p.eps_q[qi] + (double)p.eps_add : (double)p.eps;
                 if (p.metric == LVS_METRIC_DOT) eps *= (double)p.qnorm[qi] * (double)(*p.max_norm);
                 if (!(cscore[c] > (double)t_fast + eps)) flag = 1;
                 if (ncand == kp && kp == p.k) flag = 1;  // no margin at all

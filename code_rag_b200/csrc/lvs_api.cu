@@ -97,6 +97,7 @@ struct lvs_collection {
     int64_t n_rows = 0;
     int64_t row_base = 0;
     uint32_t search_counter = 0;
+    float h_norm_stats[2] = {0.f, 0.f};   // host mirror of d_max_norm: max ||row||, max | ||row|| - 1 |
 
     uint8_t* d_vec = nullptr;
     uint8_t* d_live = nullptr;
@@ -146,7 +147,7 @@ struct lvs_collection {
     int opt_path = 0;         // 0 auto, 1 force K1 scan, 2 force K2 (when eligible)
     int opt_gemm_dbg = 0;
     int opt_gemm_stages = 0;
-    int opt_gemm_prefetch = 2;
+    int opt_gemm_no_unit = 0;
 
     std::mutex mu;
 };
@@ -294,8 +295,8 @@ extern "C" int lvs_collection_create(const char* name, int dim, int storage, int
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 * kEventRing && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ring_ev[i]);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_max_norm, 4);
-    if (e == cudaSuccess) e = cudaMemset(c->d_max_norm, 0, 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_max_norm, 8);
+    if (e == cudaSuccess) e = cudaMemset(c->d_max_norm, 0, 8);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 64);
     if (e == cudaSuccess) e = cudaMemset(c->d_counter, 0, 64);
     PwProgram pg;
@@ -444,6 +445,7 @@ extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_
         CU(cudaStreamSynchronize(st));   // the pinned buffer is reused by the next batch
     }
     c->n_rows = hi;
+    CU(cudaMemcpy(c->h_norm_stats, c->d_max_norm, 8, cudaMemcpyDeviceToHost));
     return LVS_OK;
 }
 
@@ -466,6 +468,7 @@ extern "C" int lvs_upsert_device(lvs_collection* c, const void* d_vecs, int dtyp
     if (rc != LVS_OK) return rc;
     CU(cudaStreamSynchronize(st));
     c->n_rows = hi;
+    CU(cudaMemcpy(c->h_norm_stats, c->d_max_norm, 8, cudaMemcpyDeviceToHost));
     return LVS_OK;
 }
 
@@ -722,7 +725,7 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
         fp.qnorm = qnorm + first; fp.max_norm = c->d_max_norm;
         // keys of query slot s of this group live at keys + s*grid*kpw: the finalize CTA x-index is the slot
         const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
-        const unsigned ncta = (unsigned)std::min<uint32_t>(64u, (kpw + nrw - 1) / nrw);
+        const unsigned ncta = (unsigned)std::min<uint32_t>(8u, (kpw + nrw - 1) / nrw);
         {
             cudaError_t fe = kpl == 1 ? launch_finalize<1>(fp, cnt, ncta, fsm, st) : kpl == 2 ? launch_finalize<2>(fp, cnt, ncta, fsm, st)
                            : kpl == 4 ? launch_finalize<4>(fp, cnt, ncta, fsm, st) : launch_finalize<8>(fp, cnt, ncta, fsm, st);
@@ -779,17 +782,25 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         CU(cudaMemsetAsync(c->s_tickets.p, 0, c->s_tickets.bytes, st));
     }
     if (c->opt_gemm_dbg & 1) { if ((rc = ensure_dev(c->s_dbg, (size_t)kGemmM * kGemmN * 4)) != LVS_OK) return rc; }
-    // tensor map over the shard: [n_rows][ld] bf16, box = 128 rows x 64 elements, 128-byte swizzle, zero fill out of bounds
-    CUtensorMap tmap;
+    // tensor maps: B over the shard [n_rows][ld] bf16 (box = 256 rows x 64 elements) and A over the bf16 queries
+    // [256][k_pad] (box = 128 rows x 64 elements); 128-byte swizzle, zero fill out of bounds
+    CUtensorMap tmap_b, tmap_a;
     {
         cuuint64_t gdim[2] = {(cuuint64_t)c->q_stride, (cuuint64_t)c->n_rows};
         cuuint64_t gstr[1] = {(cuuint64_t)c->row_bytes};
         cuuint32_t box[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)kGemmN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_vec, gdim, gstr, box, estr,
+        CUresult r = g_encode_tiled(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_vec, gdim, gstr, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (corpus) failed with CUresult %d", (int)r);
+        cuuint64_t qdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)256};
+        cuuint64_t qstr[1] = {(cuuint64_t)k_pad * 2};
+        cuuint32_t qbox[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)kGemmM};
+        r = g_encode_tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->s_qb16.p, qdim, qstr, qbox, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", (int)r);
     }
     uint32_t S = kGemmMaxStages;
     if (c->opt_gemm_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_gemm_stages);
@@ -808,11 +819,13 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         ++*launches;
         GemmParams gp;
         memset(&gp, 0, sizeof(gp));
-        gp.qb16 = (const __nv_bfloat16*)c->s_qb16.p; gp.k_pad = k_pad; gp.n_kchunks = nk; gp.n_rows = (uint32_t)c->n_rows;
+        gp.n_kchunks = nk; gp.n_rows = (uint32_t)c->n_rows;
         gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S;
         gp.inv_norm = c->metric == LVS_METRIC_COSINE ? c->d_inv_norm : nullptr; gp.live = c->d_live;
-        gp.base = c->d_vec; gp.row_bytes = c->row_bytes; gp.prefetch_tiles = (uint32_t)std::max(0, c->opt_gemm_prefetch);
+
         gp.out_keys = (uint64_t*)c->s_gkeys.p; gp.out_tops = (uint64_t*)c->s_gtops.p; gp.out_drops = (uint64_t*)c->s_gdrops.p;
+        const bool unit_rows = c->metric == LVS_METRIC_COSINE && c->h_norm_stats[1] <= 0.001953125f && !c->opt_gemm_no_unit;
+        gp.unit_rows = unit_rows ? 1u : 0u;
         gp.dbg = (c->opt_gemm_dbg & 1) ? (float*)c->s_dbg.p : nullptr;
         gp.dbg_mode = (uint32_t)(c->opt_gemm_dbg >> 1);
         cudaEvent_t es = nullptr, ee = nullptr;
@@ -823,7 +836,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
             c->ring_pos++;
             CU(cudaEventRecord(es, st));
         }
-        gemm_topk_kernel<<<P * G, kGemmThreads, smem, st>>>(tmap, gp);
+        gemm_topk_kernel<<<P * G, kGemmThreads, smem, st>>>(tmap_b, tmap_a, gp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(LVS_ECUDA, "gemm kernel launch failed: %s (smem=%zu grid=%u)", cudaGetErrorString(e), smem, P * G);
         ++*launches;
@@ -842,6 +855,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         fp.pw = c->d_pw; fp.row_base = c->row_base;
         fp.eps = 2.2e-3f;    // fallback; the per-query bound ||q - bf16(q)||_2 + accumulation slack is used
         fp.eps_q = c->metric == LVS_METRIC_COSINE ? (const float*)c->s_geps.p : nullptr;
+        fp.eps_add = unit_rows ? c->h_norm_stats[1] * 1.01f : 0.f;
         int nrw = kFinWarps;
         while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
         fp.n_rescore_warps = nrw;
@@ -850,7 +864,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         fp.out_flags = d_flags + q0; fp.out_counts = d_counts + q0;
         fp.qnorm = (const float*)c->s_qnorm.p + q0; fp.max_norm = c->d_max_norm;
         const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
-        const unsigned ncta = (unsigned)std::min<uint32_t>(64u, (kpw + nrw - 1) / nrw);
+        const unsigned ncta = (unsigned)std::min<uint32_t>(8u, (kpw + nrw - 1) / nrw);
         cudaError_t fe = kpl == 1 ? launch_finalize<1>(fp, qb, ncta, fsm, st) : kpl == 2 ? launch_finalize<2>(fp, qb, ncta, fsm, st)
                        : kpl == 4 ? launch_finalize<4>(fp, qb, ncta, fsm, st) : launch_finalize<8>(fp, qb, ncta, fsm, st);
         if (fe != cudaSuccess) return fail(LVS_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(fe));
@@ -1269,7 +1283,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;
     else if (!strcmp(name, "gemm_stages")) c->opt_gemm_stages = value;
-    else if (!strcmp(name, "gemm_prefetch")) c->opt_gemm_prefetch = value;
+    else if (!strcmp(name, "gemm_no_unit")) c->opt_gemm_no_unit = value;
     else return fail(LVS_EINVAL, "unknown option '%s'", name);
     return LVS_OK;
 }
