@@ -336,9 +336,10 @@ def run_ours(args) -> None:
         achieved = algo_bytes / (scan_mean * 1e-3) / 1e9
         traffic = None
         tf = ROOT / "profiles" / "scan_traffic.json"
-        if tf.exists():
-            try:
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        if tf.exists() and Q == 1:
+            try:   # ncu capture of this kernel on the 10M-row shard; other shard sizes scale with the rows scanned
+                tj = json.loads(tf.read_text())
+                traffic = int(tj["dram_bytes_per_launch"] * (algo_bytes / tj["algorithmic_bytes_per_launch"]))
             except Exception:
                 traffic = None
         line = {
@@ -359,7 +360,7 @@ def run_ours(args) -> None:
                     "api": "lvs_search_submit/lvs_search_wait (C ABI, host buffers)" if world == 1 else "ShardedSearcher.submit/wait",
                     "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel" if Q < 8 else "gemm_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": scan_mean,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},

@@ -24,9 +24,9 @@ def lib(native_lib):
     return native_lib
 
 
-def _dev(name, dim, storage="f32", ncols=0, **kw):
+def _dev(name, dim, storage="f32", ncols=0, metric="cosine", **kw):
     from code_rag_b200.collection import DeviceCollection
-    return DeviceCollection(name, dim, storage=storage, n_filter_cols=ncols, **kw)
+    return DeviceCollection(name, dim, storage=storage, metric=metric, n_filter_cols=ncols, **kw)
 
 
 def _assert_same(res, qi, rows_o, scores_o, rel, tight=TIGHT):
@@ -230,6 +230,61 @@ def test_gemm_path_parity(lib, Q, k):
     assert dev.last_timing()["kernel"] == "gemm"
     for i in range(Q):
         _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16)
+    dev.close()
+
+
+@pytest.mark.parametrize("dim", [100, 1000, 1536])
+def test_gemm_path_other_dimensions(lib, dim):
+    """K2 with K not a multiple of the 64-element chunk (TMA zero-fills the tail) and with K > 768."""
+    n, Q, k = 20_000, 24, 10
+    x, q = synth.unit_rows(n, dim, seed=dim + 1, n_queries=Q)
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(dim)
+    ora.upsert_rows_f32(0, xb, [None] * n)
+    dev = _dev("gemmdim", dim, storage="bf16")
+    dev.upsert(xb)
+    res = dev.search(q.astype(np.float64), k)
+    assert dev.last_timing()["kernel"] == "gemm"
+    for i in range(Q):
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16)
+    dev.close()
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_dot_metric(lib, storage):
+    """metric = dot: rows and queries are used as given (no normalisation), float64 scores as np.dot would give."""
+    n, dim = 9_000, 256
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((n, dim)) * rng.uniform(0.5, 2.0, size=(n, 1))).astype(np.float32)
+    if storage == "bf16":
+        x = synth.bf16_round(x)
+    q = rng.standard_normal((5, dim))
+    ora = OracleCollection(dim, distance="dot")
+    ora.upsert_rows_f32(0, x, [None] * n)
+    dev = _dev("dot", dim, storage=storage, metric="dot")
+    dev.upsert(x)
+    for i in range(len(q)):
+        res = dev.search(q[i], 10)
+        rows_o, scores_o = ora.search_topk_rows(q[i], 10)
+        assert np.array_equal(res.rows[0], rows_o)
+        assert np.allclose(res.scores[0], scores_o, rtol=1e-12, atol=1e-12)
+    res = dev.search(q, 10)            # batch (K1 passes for f32, K1 or K2 for bf16)
+    for i in range(len(q)):
+        rows_o, scores_o = ora.search_topk_rows(q[i], 10)
+        assert np.array_equal(res.rows[i], rows_o)
+    dev.close()
+
+
+def test_f32_storage_large_batch_uses_scan_passes(lib):
+    x, q = synth.unit_rows(20_000, 384, seed=21, n_queries=33)
+    ora = OracleCollection(384)
+    ora.upsert_rows_f32(0, x, [None] * len(x))
+    dev = _dev("f32batch", 384)
+    dev.upsert(x.astype(np.float64))
+    res = dev.search(q.astype(np.float64), 10)
+    assert dev.last_timing()["kernel"] == "scan"
+    for i in range(len(q)):
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
     dev.close()
 
 
