@@ -60,6 +60,7 @@ struct GemmParams {
     uint64_t* out_tops;          // [n_groups * 128][2P]  best key of the list
     uint64_t* out_drops;         // [n_groups * 128][2P]  32nd key when the list is full (bound on what was dropped), else 0
     float* dbg;                  // optional: CTA 0 dumps its first accumulator tile [128 x 256] (already scaled)
+    uint32_t keep;               // keys kept per list (<= 32): fewer keys = fewer inserts but a weaker drop bound
     uint32_t unit_rows;          // every stored row has | ||row|| - 1 | <= 2^-9: clean tiles skip the 1/||row|| scaling
     uint32_t dbg_mode;           // profiling aid: bit0 skip the epilogue's scoring, bit1 skip the MMA issue, bit2 skip tcgen05.ld
 };
@@ -111,7 +112,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
 // shared by the two warps that serve a query: raising it to the 32nd key of EITHER list is safe because that key is
 // recorded as the list's drop bound.
 __device__ __noinline__ float gemm_drain_queue(const uint64_t* q_key, const uint8_t* q_lane, uint64_t* warp_lists, uint32_t* thr_q,
-                                               uint32_t qcnt, int lane) {
+                                               uint32_t qcnt, int lane, uint32_t keep) {
     __syncwarp();
     uint64_t key = 0, cur = 0;
     uint32_t ql = 0;
@@ -121,11 +122,12 @@ __device__ __noinline__ float gemm_drain_queue(const uint64_t* q_key, const uint
         uint32_t nql = 0;
         if (i + 1 < qcnt) { nkey = q_key[i + 1]; nql = q_lane[i + 1]; ncur = warp_lists[nql * kGemmList + lane]; }
         const uint32_t pos = __popc(__ballot_sync(0xFFFFFFFFu, cur > key));
-        if (pos < (uint32_t)kGemmList) {
+        if (pos < keep) {
             const uint64_t up = shfl_up_u64(cur, 1);
-            const uint64_t nv = (uint32_t)lane < pos ? cur : ((uint32_t)lane == pos ? key : up);
+            uint64_t nv = (uint32_t)lane < pos ? cur : ((uint32_t)lane == pos ? key : up);
+            if ((uint32_t)lane >= keep) nv = 0ull;
             warp_lists[ql * kGemmList + lane] = nv;
-            if (lane == kGemmList - 1 && nv != 0ull) atomicMax(thr_q + ql, (uint32_t)(nv >> 32));
+            if ((uint32_t)lane == keep - 1 && nv != 0ull) atomicMax(thr_q + ql, (uint32_t)(nv >> 32));
             if (nql == ql) ncur = nv;                    // the prefetched row of the same list is stale
         }
         key = nkey; ql = nql; cur = ncur;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
         constexpr int NB = kGemmN / 2 / 32;                      // 4 blocks of 32 columns per warp and tile
 
         auto drain = [&]() {
-            thr = gemm_drain_queue(my_q_key, my_q_lane, warp_lists, my_thr, qcnt, lane);
+            thr = gemm_drain_queue(my_q_key, my_q_lane, warp_lists, my_thr, qcnt, lane, p.keep);
             qcnt = 0;
         };
         // lane c holds 1/||row|| of column (32 j + c) of this warp's half of the tile for j = 0..3 (NaN for tombstones and
@@ -314,8 +316,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                                 x = take_min ? (o < x ? o : x) : (o > x ? o : x);
                             }
                         }
+                        if ((uint32_t)lane >= p.keep) x = 0ull;
                         warp_lists[ql * kGemmList + lane] = x;           // descending: lane 0 holds the best key
-                        if (lane == kGemmList - 1 && x != 0ull) atomicMax(my_thr + ql, (uint32_t)(x >> 32));
+                        if ((uint32_t)lane == p.keep - 1 && x != 0ull) atomicMax(my_thr + ql, (uint32_t)(x >> 32));
                     }
                     __syncwarp();
                     { const uint32_t t = my_thr[lane]; thr = t ? f32_from_orderable(t) : -INFINITY; }
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
             const uint64_t kv = warp_lists[ql * kGemmList + lane];
             p.out_keys[li * kGemmList + lane] = kv;
             if (lane == 0) p.out_tops[li] = kv;
-            if (lane == kGemmList - 1) p.out_drops[li] = kv;
+            if ((uint32_t)lane == p.keep - 1) p.out_drops[li] = kv;
         }
     }
 
