@@ -1,0 +1,122 @@
+"""Runs the REFERENCE's own callers of the vector store (query/vector_search.py, embeddings/indexer.py) against
+B200VectorStore.  Executed in a fresh interpreter by tests/test_reference_callers_cpu.py (build container only: it
+needs /root/reference).  `qdrant_client` is not installed, so a stub module satisfies the import of
+lattice/embeddings/client.py; the reference classes under test are the unmodified files."""
+import asyncio
+import hashlib
+import sys
+import types
+from pathlib import Path
+from types import SimpleNamespace as NS
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = "/root/reference/src"
+sys.path[:0] = [SRC, str(ROOT), str(ROOT / "tests")]
+
+
+def ns(name, path=None):
+    m = types.ModuleType(name)
+    if path:
+        m.__path__ = [path]
+    sys.modules[name] = m
+    return m
+
+
+# namespace packages: skip the heavy __init__ chains (tree_sitter, neo4j, qdrant_client ...)
+for pkg in ("lattice", "lattice.embeddings", "lattice.query", "lattice.parsing", "lattice.graph"):
+    ns(pkg, SRC + "/" + pkg.replace(".", "/"))
+qc = ns("qdrant_client")
+qc.AsyncQdrantClient = object
+qc.models = ns("qdrant_client.models")
+for _n in ("Filter", "CollectionInfo", "FieldCondition", "MatchValue", "MatchText", "PointStruct", "VectorParams", "Distance",
+           "PayloadSchemaType", "FilterSelector"):
+    setattr(qc.models, _n, type(_n, (), {}))          # only named in annotations / never called on this path
+
+from lattice.core.errors import IndexingError, QueryError, VectorStoreError  # noqa: E402  (reference classes)
+from lattice.embeddings.chunker import CodeChunk  # noqa: E402
+from lattice.embeddings.indexer import VectorIndexer, VectorSearcher as LegacySearcher  # noqa: E402
+from lattice.query.vector_search import VectorSearcher  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from code_rag_b200 import errors as our_errors  # noqa: E402
+from code_rag_b200.client import B200VectorStore  # noqa: E402
+from helpers import FakeDevice  # noqa: E402
+
+assert our_errors.VectorStoreError is VectorStoreError, "the adapter must raise the reference's own exception class"
+DIM = 48
+
+
+def vec(text: str) -> list[float]:
+    seed = int.from_bytes(hashlib.sha256(text.encode()).digest()[:8], "little")
+    return np.random.default_rng(seed).standard_normal(DIM).tolist()
+
+
+class Embedder:
+    async def embed(self, text):
+        return vec(text)
+
+    async def embed_with_progress(self, texts, progress_callback=None):
+        return [vec(t) for t in texts]
+
+
+class Chunker:
+    def chunk_file(self, parsed_file, project_name=None):
+        fp = str(parsed_file.file_info.path)
+        return [CodeChunk(content=f"{fp} chunk {i}", file_path=fp, entity_type="function", entity_name=f"fn{i}", language="python",
+                          start_line=10 * i + 1, end_line=10 * i + 9, graph_node_id=f"m.fn{i}",
+                          content_hash=parsed_file.file_info.content_hash, project_name=project_name) for i in range(parsed_file.n)]
+
+
+async def main(use_gpu: bool):
+    store = B200VectorStore(dimensions=DIM, _device_factory=None if use_gpu else FakeDevice)
+    await store.connect()
+    await store.create_collections()
+    indexer = VectorIndexer(qdrant=store, embedder=Embedder(), chunker=Chunker())
+    files = [NS(file_info=NS(path=Path(f"/repo/pkg/f{j}.py"), content_hash=f"h{j}"), n=4 + j) for j in range(5)]
+    total = await indexer.index_files(files, project_name="demo")
+    assert total == sum(f.n for f in files) == 30
+    assert (await store.get_collection_info("code_chunks")).points_count == 30
+    assert await indexer.index_file(files[2]) == 0                        # unchanged hash -> skipped (indexer.py:57-59)
+    files[2].file_info.content_hash = "h2-new"
+    files[2].n = 3
+    assert await indexer.index_file(files[2], project_name="demo") == 3  # delete by file_path, then upsert
+    assert (await store.get_collection_info("code_chunks")).points_count == 30 - 6 + 3
+    await indexer.index_summary("/repo/pkg/f0.py", "function", "fn0", "summary of fn0", "m.fn0")
+
+    searcher = VectorSearcher(store, Embedder())
+    hits = await searcher.search_code("/repo/pkg/f1.py chunk 2", limit=5, language="python", project_name="demo")
+    assert hits and set(hits[0]) == {"score", "file_path", "entity_type", "entity_name", "language", "content", "start_line", "end_line", "graph_node_id"}
+    assert hits[0]["content"] == "/repo/pkg/f1.py chunk 2" and abs(hits[0]["score"] - 1.0) < 1e-6
+    assert [h["score"] for h in hits] == sorted((h["score"] for h in hits), reverse=True)
+    assert await searcher.search_code("x", limit=5, language="rust") == []
+    sims = await searcher.find_similar_code("/repo/pkg/f1.py chunk 2", limit=3, exclude_file="/repo/pkg/f1.py")
+    assert len(sims) == 3 and all(s["file_path"] != "/repo/pkg/f1.py" for s in sims)
+    summ = await searcher.search_summaries("summary of fn0", limit=2)
+    assert summ and summ[0]["summary"] == "summary of fn0"
+    try:
+        await searcher.search_code("   ")
+        raise AssertionError("empty query must raise QueryError")
+    except QueryError:
+        pass
+
+    legacy = LegacySearcher(store, Embedder())
+    res = await legacy.search_code("/repo/pkg/f3.py chunk 0", limit=5, entity_type="function")
+    assert res[0].content == "/repo/pkg/f3.py chunk 0" and res[0].start_line == 1
+
+    await store.close()
+    try:                                                                   # vector store failures surface as QueryError
+        await searcher.search_code("anything")
+        raise AssertionError("expected QueryError after close()")
+    except QueryError as e:
+        assert isinstance(e.cause, VectorStoreError)
+    try:
+        await indexer.index_file(files[0], force=True)
+        raise AssertionError("expected IndexingError after close()")
+    except IndexingError:
+        pass
+    print("reference callers OK")
+
+
+if __name__ == "__main__":
+    asyncio.run(main(use_gpu="--gpu" in sys.argv))
