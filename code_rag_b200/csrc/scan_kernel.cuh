@@ -162,33 +162,48 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             }
         } else {
             uint32_t it = 0, slot = 0, s = 0;
-            for (uint32_t blk = blockIdx.x; blk < p.n_blocks32; blk += gridDim.x) {
-                const uint32_t row = blk * 32u + lane;
-                bool pass = row < p.n_rows;
-                if (pass) pass = p.live[row] != 0;
-                for (uint32_t f = 0; f < p.n_filter; ++f) {
-                    if (pass) pass = __ldg(p.codes[f] + row) == p.want[f];
+            constexpr uint32_t UB = 4;                            // 32-row blocks whose flag loads are in flight together
+            for (uint32_t blk0 = blockIdx.x * UB; blk0 < p.n_blocks32; blk0 += gridDim.x * UB) {
+                bool pass[UB];
+#pragma unroll
+                for (uint32_t u = 0; u < UB; ++u) {
+                    const uint32_t row = (blk0 + u) * 32u + lane;
+                    pass[u] = row < p.n_rows;
+                    uint8_t lv = 0;
+                    if (pass[u]) lv = p.live[row];
+                    uint32_t cv[kMaxFilterCols];
+#pragma unroll
+                    for (uint32_t f = 0; f < (uint32_t)kMaxFilterCols; ++f)
+                        cv[f] = (f < p.n_filter && pass[u]) ? __ldg(p.codes[f] + row) : 0u;
+                    pass[u] = pass[u] && lv != 0;
+#pragma unroll
+                    for (uint32_t f = 0; f < (uint32_t)kMaxFilterCols; ++f)
+                        if (f < p.n_filter) pass[u] = pass[u] && (cv[f] == p.want[f]);
                 }
-                uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-                while (m) {
-                    const uint32_t b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t r = blk * 32u + b;
-                    if (slot == 0) {
-                        s = it % S;
-                        if (lane == 0) mbar_wait(&empty_bar[s], ((it / S) & 1u) ^ 1u);
-                        __syncwarp();
-                    }
-                    if (lane == 0) {
-                        mbar_expect_tx(&full_bar[s], p.row_bytes);
-                        bulk_g2s(stages + (size_t)s * p.stage_bytes + (size_t)slot * p.row_bytes,
-                                 p.base + (size_t)r * p.row_bytes, p.row_bytes, &full_bar[s]);
-                        meta[s * meta_stride + 4 + slot] = r;
-                    }
-                    ++slot;
-                    if (slot == p.stage_rows) {
-                        if (lane == 0) { meta[s * meta_stride] = slot; mbar_arrive(&full_bar[s]); }
-                        slot = 0; ++it;
+#pragma unroll
+                for (uint32_t u = 0; u < UB; ++u) {
+                    const uint32_t blk = blk0 + u;
+                    uint32_t m = __ballot_sync(0xFFFFFFFFu, pass[u]);
+                    while (m) {
+                        const uint32_t b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t r = blk * 32u + b;
+                        if (slot == 0) {
+                            s = it % S;
+                            if (lane == 0) mbar_wait(&empty_bar[s], ((it / S) & 1u) ^ 1u);
+                            __syncwarp();
+                        }
+                        if (lane == 0) {
+                            mbar_expect_tx(&full_bar[s], p.row_bytes);
+                            bulk_g2s(stages + (size_t)s * p.stage_bytes + (size_t)slot * p.row_bytes,
+                                     p.base + (size_t)r * p.row_bytes, p.row_bytes, &full_bar[s]);
+                            meta[s * meta_stride + 4 + slot] = r;
+                        }
+                        ++slot;
+                        if (slot == p.stage_rows) {
+                            if (lane == 0) { meta[s * meta_stride] = slot; mbar_arrive(&full_bar[s]); }
+                            slot = 0; ++it;
+                        }
                     }
                 }
             }
