@@ -322,7 +322,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
 
     // ============== CTA epilogue: merge the 8 warp lists of each query, write one list per CTA ==============
+    // The 8 * KPW keys of a query are sorted in shared memory by a bitonic network run by all 256 consumer threads
+    // (named barrier between stages); the first KPW keys are the CTA's list.  This replaced a serial fold by one warp
+    // (dozens of dependent warp-level inserts), which cost ~9 us at the tail of every CTA - visible on small shards.
     constexpr int NCT = kScanConsumerWarps * kWarp;
+    constexpr int NM = kScanConsumerWarps * KPW;          // keys to merge per query (a power of two)
 #pragma unroll 1
     for (int qi = 0; qi < QT; ++qi) {
         named_bar_sync(1, NCT);                       // previous round's readers are done with merge_buf
@@ -334,34 +338,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             merge_buf[(size_t)warp * KPW + j * 32 + lane] = kv;
         }
         named_bar_sync(1, NCT);
-        if (warp == (qi % kScanConsumerWarps)) {
-            // this warp folds the other 7 lists into its own
-            WarpTopK<KPL> acc;
-#pragma unroll
-            for (int q2 = 0; q2 < QT; ++q2) if (q2 == qi) acc = top[q2];
-            for (int w = 0; w < kScanConsumerWarps; ++w) {
-                if (w == warp) continue;
-                for (int j = 0; j < KPL; ++j) {
-                    const uint64_t cand = merge_buf[(size_t)w * KPW + j * 32 + lane];
-                    uint32_t ball = __ballot_sync(0xFFFFFFFFu, cand > acc.thr);
-                    while (ball) {
-                        const int src = __ffs(ball) - 1;
-                        ball &= ball - 1;
-                        const uint64_t k = shfl_u64(cand, src);
-                        if (k > acc.thr) acc.insert(k, lane);
+        for (int k = 2; k <= NM; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < NM; i += NCT) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint64_t a = merge_buf[i], b2 = merge_buf[ixj];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (a < b2) : (a > b2)) { merge_buf[i] = b2; merge_buf[ixj] = a; }
                     }
                 }
+                named_bar_sync(1, NCT);
             }
-            uint64_t* dst = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * KPW;
-#pragma unroll
-            for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = acc.key[j];
-            uint64_t best = acc.key[0];
-#pragma unroll
-            for (int j = 1; j < KPL; ++j) best = acc.key[j] > best ? acc.key[j] : best;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) { const uint64_t other = shfl_xor_u64(best, o); best = other > best ? other : best; }
-            if (lane == 0) p.out_tops[(size_t)qi * gridDim.x + blockIdx.x] = best;
         }
+        uint64_t* dst = p.out_keys + ((size_t)qi * gridDim.x + blockIdx.x) * KPW;
+        for (int i = tid; i < KPW; i += NCT) dst[i] = merge_buf[i];
+        if (tid == 0) p.out_tops[(size_t)qi * gridDim.x + blockIdx.x] = merge_buf[0];
     }
 }
 

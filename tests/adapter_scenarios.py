@@ -125,6 +125,14 @@ async def scenario_parity_with_oracle(factory, n=3000, dim=256):
     got_b = await store.search_batch(collection=CODE, query_vectors=qb.tolist(), limit=5)
     for i in range(3):
         _same_hits(got_b[i], ora.search(CODE, qb[i].tolist(), limit=5), what=f"batch {i}")
+    # concurrent awaits, as QueryEngine does with asyncio.gather (query/engine.py:142-146): calls are serialised per collection
+    import asyncio
+    qv = q[0].astype(np.float64).tolist()
+    many = await asyncio.gather(*[store.search(collection=CODE, query_vector=qv, limit=10) for _ in range(6)])
+    exp = [ora.search(CODE, qv, limit=10) for _ in range(6)]
+    for g in many:
+        assert [h["id"] for h in g] == [h["id"] for h in exp[0]]
+        assert max(abs(a["score"] - b["score"]) for a, b in zip(g, exp[0])) < 1e-9
     # summaries collection is independent
     assert await store.search(collection=SUMM, query_vector=q[0].astype(np.float64).tolist(), limit=3) == []
     # clear_collections resets both (client.py:212-221)
