@@ -350,7 +350,7 @@ def run_ours(args) -> None:
                                    f"row-sharded over {world} GPU(s)",
                        "rows": args.rows, "dim": args.dim, "k": k, "queries_per_step": Q, "storage": args.storage,
                        "rows_per_gpu": n_local, "l2": "inputs_exceed_l2", "corpus_gen_s": round(t_gen, 1),
-                       "parallelism": f"row-shard x{world} + all-gather(top-k) + merge",
+                       "parallelism": f"row-shard x{world} + top-k exchange ({searcher.exchange_mode}) + merge",
                        "value_mode": "K searches enqueued back to back on one stream (device-resident queries/results)",
                        "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K, "sync_scan_ms": sync_scan_ms,
                        "e2e_scan_ms": e2e_scan_ms,
@@ -370,6 +370,7 @@ def run_ours(args) -> None:
             cb = cpu_reference_qps(args, steps=8, warmup=2)
             line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
+    searcher.close()
     shard.close()
     if world > 1:
         dist.destroy_process_group()

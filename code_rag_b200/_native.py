@@ -56,6 +56,11 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_scan_times": (C.c_int, [_vp, C.c_int, _f32p, _f64p, _ip]),
     "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _vp]),
+    "lvs_exchange_connect": (C.c_int, [_vp, _vp]),
+    "lvs_exchange_merge_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "lvs_exchange_error": (C.c_int, [_vp]),
+    "lvs_exchange_destroy": (C.c_int, [_vp]),
     "lvs_rank_fuse": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
     "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),
     "lvs_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),

@@ -14,6 +14,7 @@
 #include <cudaTypedefs.h>
 
 #include "aux_kernels.cuh"
+#include "exchange_kernel.cuh"
 #include "finalize_kernel.cuh"
 #include "gemm_topk_kernel.cuh"
 #include "rank_kernel.cuh"
@@ -1148,6 +1149,107 @@ extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_ro
     if (smem > 40 * 1024) CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_topk_kernel<<<Q, 256, smem, st>>>(p);
     CU(cudaGetLastError());
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5': fused exchange + merge over peer memory
+// ------------------------------------------------------------------------------------------------------
+struct lvs_exchange {
+    int world = 1, rank = 0, max_q = 0, max_k = 0;
+    size_t blk_stride = 0;          // int64 elements per rank block
+    size_t slot_elems = 0;          // int64 elements per slot = world * blk_stride
+    uint8_t* base = nullptr;        // [2 slots][world][blk_stride] int64, then flags [2][kMaxRanks] uint64
+    size_t flags_off = 0;
+    uint8_t* peers[kMaxRanks] = {nullptr};
+    bool opened[kMaxRanks] = {false};
+    uint32_t* d_counter = nullptr;  // [0] done counter, [1] error word
+    uint64_t seq = 0;
+    bool connected = false;
+};
+
+extern "C" int lvs_exchange_create(int world, int rank, int max_q, int max_k, lvs_exchange** out, void* ipc_handle_out) {
+    if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
+    if (!out || !ipc_handle_out) return fail(LVS_EINVAL, "NULL argument");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(LVS_EINVAL, "bad world / rank");
+    if (max_q < 1 || max_k < 1) return fail(LVS_EINVAL, "bad max_q / max_k");
+    lvs_exchange* ex = new (std::nothrow) lvs_exchange();
+    if (!ex) return fail(LVS_ENOMEM, "host allocation failed");
+    ex->world = world; ex->rank = rank; ex->max_q = max_q; ex->max_k = max_k;
+    ex->blk_stride = (((size_t)3 * max_q * max_k) + 31) & ~(size_t)31;
+    ex->slot_elems = (size_t)world * ex->blk_stride;
+    ex->flags_off = 2 * ex->slot_elems * 8;
+    const size_t bytes = ex->flags_off + 2 * kMaxRanks * 8;
+    cudaError_t e = cudaMalloc(&ex->base, bytes);
+    if (e == cudaSuccess) e = cudaMemset(ex->base, 0, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ex->d_counter, 8);
+    if (e == cudaSuccess) e = cudaMemset(ex->d_counter, 0, 8);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ex->base);
+    if (e != cudaSuccess) { lvs_exchange_destroy(ex); return fail(LVS_ECUDA, "exchange setup failed: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_out, &h, 64);
+    ex->peers[rank] = ex->base;
+    *out = ex;
+    return LVS_OK;
+}
+
+extern "C" int lvs_exchange_connect(lvs_exchange* ex, const void* all_handles) {
+    if (!ex || !all_handles) return fail(LVS_EINVAL, "NULL argument");
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t*)all_handles + (size_t)r * 64, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(LVS_ECUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        ex->peers[r] = (uint8_t*)ptr;
+        ex->opened[r] = true;
+    }
+    ex->connected = true;
+    return LVS_OK;
+}
+
+extern "C" int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, int Q, int k, int64_t* d_out, uint32_t* d_out_counts,
+                                         void* stream) {
+    if (!ex || !d_local || !d_out || !d_out_counts) return fail(LVS_EINVAL, "NULL argument");
+    if (!ex->connected && ex->world > 1) return fail(LVS_ESTATE, "lvs_exchange_connect() has not been called");
+    if (Q < 1 || k < 1 || (size_t)3 * Q * k > ex->blk_stride) return fail(LVS_ELIMIT, "Q x k = %d x %d exceeds the exchange buffer (%d x %d)", Q, k, ex->max_q, ex->max_k);
+    const size_t smem = (size_t)ex->world * k * 24;
+    if (smem > 200 * 1024) return fail(LVS_ELIMIT, "world * k too large for the merge");
+    ex->seq += 1;
+    const int slot = (int)(ex->seq & 1);
+    ExchangeParams p;
+    memset(&p, 0, sizeof(p));
+    p.local = d_local; p.Q = Q; p.k = k; p.world = ex->world; p.rank = ex->rank;
+    for (int r = 0; r < ex->world; ++r) {
+        p.peer_data[r] = (int64_t*)ex->peers[r] + (size_t)slot * ex->slot_elems;
+        p.peer_flags[r] = (uint64_t*)(ex->peers[r] + ex->flags_off) + (size_t)slot * kMaxRanks;
+    }
+    p.my_data = (const int64_t*)ex->base + (size_t)slot * ex->slot_elems;
+    p.my_flags = (const uint64_t*)(ex->base + ex->flags_off) + (size_t)slot * kMaxRanks;
+    p.seq = ex->seq; p.blk_stride = ex->blk_stride; p.done_counter = ex->d_counter; p.err = ex->d_counter + 1;
+    p.out = d_out; p.out_counts = d_out_counts;
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::max(1, std::min(Q, 32));
+    exchange_merge_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    CU(cudaGetLastError());
+    return LVS_OK;
+}
+
+extern "C" int lvs_exchange_error(lvs_exchange* ex) {
+    if (!ex) return 0;
+    uint32_t h = 0;
+    if (cudaMemcpy(&h, ex->d_counter + 1, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return (int)h;
+}
+
+extern "C" int lvs_exchange_destroy(lvs_exchange* ex) {
+    if (!ex) return LVS_OK;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < kMaxRanks; ++r) if (ex->opened[r] && ex->peers[r]) cudaIpcCloseMemHandle(ex->peers[r]);
+    cudaFree(ex->base); cudaFree(ex->d_counter);
+    delete ex;
     return LVS_OK;
 }
 

@@ -11,6 +11,10 @@ from __future__ import annotations
 
 import numpy as np
 
+import ctypes as C
+import os
+
+from . import _native as N
 from .collection import DeviceCollection, merge_topk_device
 
 
@@ -58,6 +62,41 @@ class ShardedSearcher:
         self.stream = torch.cuda.Stream(device=self.device)
         self.n_slots = 4
         self._next_slot = 0
+        # exchange step: "p2p" = one kernel per rank that stores its block into every peer's gather buffer over NVLink
+        # (CUDA-IPC mapped), flags, waits and merges; "nccl" = all_gather_into_tensor + merge kernel
+        self.exchange_mode = os.environ.get("LATTICE_B200_EXCHANGE", "p2p") if self.world > 1 else "none"
+        self._ex = None
+        self._ex_cap = (0, 0)
+
+    def _exchange(self, Q: int, k: int):
+        """Create (or grow) the peer-memory exchange; collective: every rank calls it with the same arguments."""
+        if self._ex is not None and Q <= self._ex_cap[0] and k <= self._ex_cap[1]:
+            return self._ex
+        lib = N.load()
+        if self._ex is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            lib.lvs_exchange_destroy(self._ex)
+            self._ex = None
+        cap_q, cap_k = max(Q, self._ex_cap[0], 1), max(k, self._ex_cap[1], 16)
+        ex = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        N.check(lib.lvs_exchange_create(self.world, self.rank, cap_q, cap_k, C.byref(ex), handle), "lvs_exchange_create")
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, bytes(handle), group=self.group)
+        blob = b"".join(handles)
+        N.check(lib.lvs_exchange_connect(ex, C.c_char_p(blob)), "lvs_exchange_connect")
+        self.torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)       # every rank has mapped every buffer before the first store
+        self._ex, self._ex_cap = ex, (cap_q, cap_k)
+        return ex
+
+    def close(self) -> None:
+        if self._ex is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            N.load().lvs_exchange_destroy(self._ex)
+            self._ex = None
 
     def _slot(self, Q: int, k: int, slot: int, host: bool) -> dict:
         key = (Q, k, slot, host)
@@ -86,6 +125,13 @@ class ShardedSearcher:
         local = b["local"]
         self.shard.search_device_async(q_ptr, q_dtype, Q, k, want, local[0].data_ptr(), local[1].data_ptr(), local[2].data_ptr(),
                                        b["local_counts"].data_ptr(), b["flags"].data_ptr(), stream)
+        if self.exchange_mode == "p2p":
+            ex = self._exchange(Q, k)
+            N.check(N.load().lvs_exchange_merge_device(ex, C.c_void_p(local.data_ptr()), Q, k, C.c_void_p(out.data_ptr()),
+                                                       C.c_void_p(b["counts"].data_ptr()), C.c_void_p(stream)),
+                    "lvs_exchange_merge_device")
+            self.merge_launches += 1
+            return
         with self.torch.cuda.stream(self.stream):
             allgather_packed(local, b["gathered"], self.group)
         n = Q * k

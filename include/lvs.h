@@ -118,6 +118,21 @@ int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const u
                           int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                           void* stream);   /* enqueue only: ordered on `stream` */
 
+/* ---- K5': exchange + merge in ONE kernel over NVLink peer memory (replaces the NCCL all-gather + lvs_merge_topk_device) ---
+ * One lvs_exchange per process.  create allocates this rank's gather buffer and returns its 64-byte CUDA IPC handle; the
+ * caller all-gathers the handles (any transport) and passes the world x 64 bytes to connect, which maps the peers' buffers.
+ * lvs_exchange_merge_device: d_local = this rank's packed [3][Q][k] int64 block (float64 score bits | global rows | tie keys);
+ * the kernel stores it into every rank's buffer with P2P stores, raises a system-scope flag, waits for all ranks' flags and
+ * merges into d_out ([3][Q][k]) / d_out_counts ([Q]).  Enqueue only (ordered on `stream`).  Every rank must issue the same
+ * sequence of calls. */
+typedef struct lvs_exchange lvs_exchange;
+int lvs_exchange_create(int world, int rank, int max_q, int max_k, lvs_exchange** out, void* ipc_handle_out);
+int lvs_exchange_connect(lvs_exchange* ex, const void* all_handles);
+int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, int Q, int k, int64_t* d_out, uint32_t* d_out_counts,
+                              void* stream);
+int lvs_exchange_error(lvs_exchange* ex);     /* 1 if a peer's flag ever timed out (synchronises) */
+int lvs_exchange_destroy(lvs_exchange* ex);
+
 /* ---- K3: fused hybrid ranking (HybridRanker.rank_results query/ranking/ranker.py:18-226 + ResultScorer scorer.py:9-126
  *      [mode 0]; ResultReranker.fuse_results / deduplicate / normalize_scores query/reranker.py:29-145 [mode 1]) -------------
  * Candidates of all queries are concatenated in the reference's insertion order (primary, callers, callees, methods,
