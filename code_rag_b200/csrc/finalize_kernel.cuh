@@ -134,6 +134,7 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
     float* cur = buf;
     float* prev = buf + p.dim_pad;
     float* nxt = buf + 2 * p.dim_pad;
+    const uint32_t row_epoch = __ldg(p.epoch + row);    // issued together with the row's loads
     // stage the stored row as float32 (128-bit loads, all chunks of a lane in flight together); the padding
     // columns of a row are zero, so they may be staged and summed as well
     double ss = 0.0;
@@ -172,7 +173,7 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
         __syncwarp();
     }
     // replay of the per-search in-place re-normalisation
-    uint32_t count = search_no - p.epoch[row];          // searches run since the row was written, this one included
+    uint32_t count = search_no - row_epoch;             // searches run since the row was written, this one included
     if (count > 64u) count = 64u + ((count - 64u) & 1u);
     bool have_prev = false;
     for (uint32_t j = 1; j <= count; ++j) {
@@ -275,17 +276,26 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         uint64_t T = *Tp;
         if (T == 0ull) T = 1ull;                          // fewer than kp non-empty lists: keep every key
         __syncthreads();
-        constexpr int U = 4;
-        for (uint32_t i0 = tid; i0 < p.M; i0 += kFinThreads * U) {
-            uint64_t v[U];
+        // the lists are sorted descending (bitonic merge in K1, sorted insertion in K2), so the keys >= T of a list are a
+        // prefix of it: one thread per list reads 4 keys (32 bytes) at a time and stops at the first key below T
+        const uint32_t llen = p.M / p.L;
+        for (uint32_t l = tid; l < p.L; l += kFinThreads) {
+            const uint64_t* lk = keys + (size_t)l * llen;
+            for (uint32_t i = 0; i < llen; i += 4) {
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(lk + i);
+                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(lk + i + 2);
+                const uint64_t v[4] = {a.x, a.y, b.x, b.y};
+                bool more = true;
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const uint32_t i = i0 + u * kFinThreads; v[u] = i < p.M ? keys[i] : 0ull; }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (v[u] >= T) {
-                    const uint32_t pos = atomicAdd(&scal[0], 1u);
-                    if (pos < kFinWarps * KPW) sortbuf[pos] = v[u];
+                for (int u = 0; u < 4; ++u) {
+                    if (v[u] >= T) {
+                        const uint32_t pos = atomicAdd(&scal[0], 1u);
+                        if (pos < kFinWarps * KPW) sortbuf[pos] = v[u];
+                    } else {
+                        more = false;
+                    }
                 }
+                if (!more) break;
             }
         }
         __syncthreads();
