@@ -150,6 +150,7 @@ struct lvs_collection {
     int opt_gemm_stages = 0;
     int opt_gemm_no_unit = 0;
     int opt_gemm_keep = 16;
+    int opt_gemm_no_pair = 0;
 
     std::mutex mu;
 };
@@ -784,9 +785,10 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         CU(cudaMemsetAsync(c->s_tickets.p, 0, c->s_tickets.bytes, st));
     }
     if (c->opt_gemm_dbg & 1) { if ((rc = ensure_dev(c->s_dbg, (size_t)kGemmM * kGemmN * 4)) != LVS_OK) return rc; }
-    // tensor maps: B over the shard [n_rows][ld] bf16 (box = 256 rows x 64 elements) and A over the bf16 queries
-    // [256][k_pad] (box = 128 rows x 64 elements); 128-byte swizzle, zero fill out of bounds
-    CUtensorMap tmap_b, tmap_a;
+    // tensor maps: B over the shard [n_rows][ld] bf16 (box = 256 rows x 64 elements; 128 rows for the CTA-pair form, where
+    // each CTA of the pair loads half a tile) and A over the bf16 queries [256][k_pad] (box = 128 rows x 64 elements);
+    // 128-byte swizzle, zero fill out of bounds
+    CUtensorMap tmap_b, tmap_b_half, tmap_a;
     {
         cuuint64_t gdim[2] = {(cuuint64_t)c->q_stride, (cuuint64_t)c->n_rows};
         cuuint64_t gstr[1] = {(cuuint64_t)c->row_bytes};
@@ -796,6 +798,11 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (corpus) failed with CUresult %d", (int)r);
+        cuuint32_t hbox[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)(kGemmN / 2)};
+        r = g_encode_tiled(&tmap_b_half, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_vec, gdim, gstr, hbox, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (corpus, half tile) failed with CUresult %d", (int)r);
         cuuint64_t qdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)256};
         cuuint64_t qstr[1] = {(cuuint64_t)k_pad * 2};
         cuuint32_t qbox[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)kGemmM};
@@ -804,17 +811,23 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", (int)r);
     }
-    uint32_t S = kGemmMaxStages;
-    if (c->opt_gemm_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_gemm_stages);
-    while (S > 2 && gemm_smem_bytes(S) > g_lib.smem_optin) --S;
-    const size_t smem = gemm_smem_bytes(S);
     static bool attr = false;
-    if (!attr) { CU(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin)); attr = true; }
+    if (!attr) {
+        CU(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+        CU(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+        attr = true;
+    }
     const uint32_t n_tiles = (uint32_t)((c->n_rows + kGemmN - 1) / kGemmN);
     for (int q0 = 0; q0 < Q; q0 += 256) {
         const int qb = std::min(256, Q - q0);
         const uint32_t G = (uint32_t)((qb + kGemmM - 1) / kGemmM);
+        // more than 128 queries: clusters of two CTAs share every corpus tile (tcgen05 cta_group::2)
+        const bool pair_form = G == 2 && !c->opt_gemm_no_pair;
         const uint32_t P = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sm / G, n_tiles));
+        uint32_t S = pair_form ? 4 : 3;
+        if (c->opt_gemm_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_gemm_stages);
+        while (S > 2 && gemm_smem_bytes(S, pair_form) > g_lib.smem_optin) --S;
+        const size_t smem = gemm_smem_bytes(S, pair_form);
         prep_qb16_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
                                                    (__nv_bfloat16*)c->s_qb16.p, k_pad, G * kGemmM, (float*)c->s_geps.p);
         CU(cudaGetLastError());
@@ -839,8 +852,20 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
             c->ring_pos++;
             CU(cudaEventRecord(es, st));
         }
-        gemm_topk_kernel<<<P * G, kGemmThreads, smem, st>>>(tmap_b, tmap_a, gp);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e;
+        if (pair_form) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(P * 2); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute la[1];
+            la[0].id = cudaLaunchAttributeClusterDimension;
+            la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+            cfg.attrs = la; cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true>, tmap_b_half, tmap_a, gp);
+        } else {
+            gemm_topk_kernel<false><<<P * G, kGemmThreads, smem, st>>>(tmap_b, tmap_a, gp);
+            e = cudaGetLastError();
+        }
         if (e != cudaSuccess) return fail(LVS_ECUDA, "gemm kernel launch failed: %s (smem=%zu grid=%u)", cudaGetErrorString(e), smem, P * G);
         ++*launches;
         if (c->opt_timing) CU(cudaEventRecord(ee, st));
@@ -1389,6 +1414,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "gemm_stages")) c->opt_gemm_stages = value;
     else if (!strcmp(name, "gemm_no_unit")) c->opt_gemm_no_unit = value;
     else if (!strcmp(name, "gemm_keep")) c->opt_gemm_keep = value;
+    else if (!strcmp(name, "gemm_no_pair")) c->opt_gemm_no_pair = value;
     else return fail(LVS_EINVAL, "unknown option '%s'", name);
     return LVS_OK;
 }
