@@ -18,7 +18,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 dev = DeviceCollection("k2", 768, storage="bf16", capacity=n)
 fill(dev, n, 768, "bf16", seed=3456)
 import os
-for opt in ("gemm_no_unit", "gemm_stages", "gemm_dbg", "gemm_keep"):
+for opt in ("gemm_no_unit", "gemm_stages", "gemm_dbg", "gemm_keep", "gemm_no_pair"):
     if os.environ.get(opt.upper()):
         dev.set_option(opt, int(os.environ[opt.upper()]))
 rng = np.random.default_rng(6)

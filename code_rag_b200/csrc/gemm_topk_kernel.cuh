@@ -23,11 +23,11 @@
 //     tcgen05.ld 32 columns, (scale by 1/||row|| unless the shard is unit-norm and the tile clean; NaN for tombstones
 //     and rows past the end, and NaN never passes), then a NaN-ignoring MAX TREE over the 32 scores and ONE vote:
 //     if no query of the warp has a score above its current threshold (the common case once the lists have warmed
-//     up) the block costs ~40 instructions.  Otherwise each lane counts its passing scores, a warp reduction sizes
-//     the batch, a shared-memory atomic hands out queue slots and the lanes write (key, query) items; the queue is
-//     drained WARP-COOPERATIVELY into sorted per-query lists in shared memory (lane j holds key j; the insertion
-//     position is a ballot + popc, the shift one shuffle).  The first 32 columns a warp ever sees are sorted into
-//     the lists directly (bitonic network) instead of 1024 inserts.
+//     up) the block costs ~40 instructions.  Otherwise every lane builds the bit mask of its passing columns, the
+//     passing lanes park their 32 scores in a shared-memory column (so that they can be indexed) and ALL LANES INSERT
+//     IN PARALLEL, one item per round: a lane owns its query's list (16 unsorted keys in a bank-conflict-free shared
+//     memory column, the minimum tracked in registers), an insert replaces the minimum and rescans.  No queue, no
+//     atomics, no warp-wide serialisation per item; the lists are sorted once, when the kernel ends.
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane) + TMEM allocation,
 // warps 2..9 = epilogue (TMEM lane quarter = warp % 4).
 //
@@ -49,9 +49,8 @@ constexpr int kGemmKC = 64;            // K elements per pipeline stage (= one 1
 constexpr int kGemmABytes = kGemmM * kGemmKC * 2;       // 16 KB
 constexpr int kGemmBBytes = kGemmN * kGemmKC * 2;       // 32 KB (PAIR: each CTA holds half, 16 KB)
 constexpr int kGemmMaxStages = 4;
-constexpr int kGemmList = 32;          // keys kept per (CTA, column half, query)
+constexpr int kGemmList = 16;          // keys kept per (CTA, column half, query)
 constexpr int kGemmMaxKChunks = 64;    // dim <= 4096
-constexpr int kGemmQueue = 128;        // pending items per epilogue warp
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA of a pair
 
 __host__ __device__ constexpr int gemm_stage_bytes(bool pair) { return kGemmABytes + (pair ? kGemmBBytes / 2 : kGemmBBytes); }
@@ -65,20 +64,19 @@ struct GemmParams {
     uint32_t n_stages;
     const float* inv_norm;       // [rows] 1/||row||, or nullptr (dot metric)
     const uint8_t* live;
-    uint64_t* out_keys;          // [n_groups * 128][2P][32]   (two lists per CTA and query: one per column half)
+    uint64_t* out_keys;          // [n_groups * 128][2P][16]   (two lists per CTA and query: one per column half), sorted descending
     uint64_t* out_tops;          // [n_groups * 128][2P]  best key of the list
-    uint64_t* out_drops;         // [n_groups * 128][2P]  last kept key when the list is full (bound on what was dropped), else 0
+    uint64_t* out_drops;         // [n_groups * 128][2P]  key-shaped bound on every score this list dropped (its final threshold), 0 = nothing dropped
     float* dbg;                  // optional: CTA 0 dumps its first accumulator tile [128 x 256] (already scaled)
-    uint32_t keep;               // keys kept per list (<= 32): fewer keys = fewer inserts but a weaker drop bound
+    uint32_t keep;               // keys kept per list (<= 16): fewer keys = fewer inserts but a weaker drop bound
     uint32_t unit_rows;          // every stored row has | ||row|| - 1 | <= 2^-9: clean tiles skip the 1/||row|| scaling
     uint32_t dbg_mode;           // profiling aid: bit0 skip the epilogue's scoring, bit1 skip the MMA issue, bit2 skip tcgen05.ld
 };
 
-// shared memory: [stages][lists 8*32*32*8][queue keys 8*128*8][queue lanes 8*128][thr 128*4][inv 8*128*4][qcnt 8*4][barriers]
+// shared memory: [stages][lists 8 warps * 16 keys * 32 lanes * 8][score columns 8 * 32 * 32 * 4][thr 128*4][inv 8*128*4][barriers]
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, bool pair) {
     return 1024 /* alignment slack */ + (size_t)n_stages * gemm_stage_bytes(pair) + (size_t)kGemmEpiWarps * 32 * kGemmList * 8 +
-           kGemmEpiWarps * kGemmQueue * 8 + kGemmEpiWarps * kGemmQueue + kGemmM * 4 + kGemmEpiWarps * 128 * 4 + kGemmEpiWarps * 4 +
-           (2 * kGemmMaxStages + 8) * 8 + 16;
+           (size_t)kGemmEpiWarps * 32 * 32 * 4 + kGemmM * 4 + kGemmEpiWarps * 128 * 4 + (2 * kGemmMaxStages + 8) * 8 + 16;
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -142,43 +140,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on the barrier at this offset in the leader CTA of the pair (works from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
 
 // K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), version 1 (sm_100), layout SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-// Warp-cooperative drain of one epilogue warp's queue into its sorted per-query lists (lane j holds key j of a list).
-// Kept out of line.  The next item's list row is fetched while the current one is inserted.  thr_q is the CTA-wide
-// per-query threshold (orderable u32 of the score), shared by the two warps that serve a query: raising it to the
-// last kept key of EITHER list is safe because that key is recorded as the list's drop bound.
-__device__ __noinline__ float gemm_drain_queue(const uint64_t* q_key, const uint8_t* q_lane, uint64_t* warp_lists, uint32_t* thr_q,
-                                               uint32_t* q_count, uint32_t qcnt, int lane, uint32_t keep) {
-    __syncwarp();
-    uint64_t key = 0, cur = 0;
-    uint32_t ql = 0;
-    if (qcnt) { key = q_key[0]; ql = q_lane[0]; cur = warp_lists[ql * kGemmList + lane]; }
-    for (uint32_t i = 0; i < qcnt; ++i) {
-        uint64_t nkey = 0, ncur = 0;
-        uint32_t nql = 0;
-        if (i + 1 < qcnt) { nkey = q_key[i + 1]; nql = q_lane[i + 1]; ncur = warp_lists[nql * kGemmList + lane]; }
-        const uint32_t pos = __popc(__ballot_sync(0xFFFFFFFFu, cur > key));
-        if (pos < keep) {
-            const uint64_t up = shfl_up_u64(cur, 1);
-            uint64_t nv = (uint32_t)lane < pos ? cur : ((uint32_t)lane == pos ? key : up);
-            if ((uint32_t)lane >= keep) nv = 0ull;
-            warp_lists[ql * kGemmList + lane] = nv;
-            if ((uint32_t)lane == keep - 1 && nv != 0ull) atomicMax(thr_q + ql, (uint32_t)(nv >> 32));
-            if (nql == ql) ncur = nv;                    // the prefetched row of the same list is stale
-        }
-        key = nkey; ql = nql; cur = ncur;
-    }
-    if (lane == 0) *q_count = 0u;
-    __syncwarp();
-    const uint32_t t = thr_q[lane];
-    return t ? f32_from_orderable(t) : -INFINITY;
 }
 
 template <bool PAIR>
@@ -191,13 +158,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     constexpr int kBRows = PAIR ? kGemmN / 2 : kGemmN;       // corpus rows this CTA loads per tile
     const uint32_t S = p.n_stages;
     uint8_t* stages = gsm;                                                   // S x (A 16 KB | B), 1024-byte aligned
-    uint64_t* lists = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kStageBytes);         // [8 warps][32 queries][32] sorted desc
-    uint64_t* wq_key = lists + kGemmEpiWarps * 32 * kGemmList;               // [8][kGemmQueue]
-    uint8_t* wq_lane = reinterpret_cast<uint8_t*>(wq_key + kGemmEpiWarps * kGemmQueue);   // [8][kGemmQueue]
-    uint32_t* thr_sm = reinterpret_cast<uint32_t*>(wq_lane + kGemmEpiWarps * kGemmQueue); // [128] orderable threshold per query
+    uint64_t* lists = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kStageBytes);         // [8 warps][16 keys][32 lanes], unsorted
+    float* sbuf = reinterpret_cast<float*>(lists + kGemmEpiWarps * 32 * kGemmList);       // [8 warps][32 columns][32 lanes]
+    uint32_t* thr_sm = reinterpret_cast<uint32_t*>(sbuf + kGemmEpiWarps * 32 * 32);       // [128] orderable threshold per query
     float* inv_sm = reinterpret_cast<float*>(thr_sm + kGemmM);               // [8][128] 1/||row|| of a warp's 128 columns
-    uint32_t* qcnt_sm = reinterpret_cast<uint32_t*>(inv_sm + kGemmEpiWarps * 128);        // [8] queue fill
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(qcnt_sm + kGemmEpiWarps);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(inv_sm + kGemmEpiWarps * 128);
     uint64_t* empty_bar = full_bar + kGemmMaxStages;
     uint64_t* tmem_full = empty_bar + kGemmMaxStages;                        // [2]
     uint64_t* tmem_empty = tmem_full + 2;                                    // [2]
@@ -225,7 +190,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     }
     for (int i = tid; i < kGemmEpiWarps * 32 * kGemmList; i += kGemmThreads) lists[i] = 0ull;
     for (int i = tid; i < kGemmM; i += kGemmThreads) thr_sm[i] = 0u;
-    if (tid < kGemmEpiWarps) qcnt_sm[tid] = 0u;
     tc_fence_before();
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer's barriers must exist before anything signals them
     tc_fence_after();
@@ -291,119 +255,112 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
         const uint32_t lq = warp & 3;                            // TMEM lane quarter this warp may read
         const uint32_t half = ew >> 2;                           // which 128 of the tile's 256 columns
         const uint32_t et = lq * 32 + lane;                      // 0..127: TMEM lane == query within the group
-        uint64_t* my_q_key = wq_key + ew * kGemmQueue;
-        uint8_t* my_q_lane = wq_lane + ew * kGemmQueue;
-        uint64_t* warp_lists = lists + (size_t)ew * 32 * kGemmList;
+        uint64_t* my_list = lists + (size_t)ew * 32 * kGemmList + lane;     // key j of this lane's list at my_list[j * 32]
+        float* my_sbuf = sbuf + (size_t)ew * 32 * 32 + lane;                 // score of column c at my_sbuf[c * 32]
         uint32_t* my_thr = thr_sm + lq * 32;                     // shared by the two warps of this lane quarter
         float* my_inv = inv_sm + ew * 128;
-        uint32_t* my_qcnt = qcnt_sm + ew;
-        float thr = -INFINITY;
-        uint32_t qcnt = 0;                                       // warp-uniform mirror of *my_qcnt
-        const uint32_t lt_mask = (1u << lane) - 1u;
+        const uint32_t keep = p.keep;
+        float thr = -INFINITY;                                   // scores at or below thr are dropped
+        uint64_t minkey = 0ull;                                  // smallest key of the list (0 while it has empty slots)
+        uint32_t minpos = 0;
         constexpr int NB = kGemmN / 2 / 32;                      // 4 blocks of 32 columns per warp and tile
 
-        auto drain = [&]() {
-            thr = gemm_drain_queue(my_q_key, my_q_lane, warp_lists, my_thr, my_qcnt, qcnt, lane, p.keep);
-            qcnt = 0;
+        // new minimum of the lane's list; a full list raises the query's threshold (published for the partner warp)
+        auto rescan = [&]() {
+            uint64_t mn = ~0ull;
+            uint32_t mp = 0;
+#pragma unroll 4
+            for (uint32_t j = 0; j < keep; ++j) {
+                const uint64_t kk = my_list[j * 32];
+                if (kk < mn) { mn = kk; mp = j; }
+            }
+            minkey = mn; minpos = mp;
+            if (mn != 0ull) {
+                const float t = key_score(mn);
+                if (t > thr) { thr = t; atomicMax(my_thr + lane, (uint32_t)(mn >> 32)); }
+            }
         };
-        // lane c holds 1/||row|| of column (32 j + c) of this warp's half of the tile for j = 0..3 (NaN for tombstones and
-        // rows past the end: a NaN score never passes a comparison); the NEXT tile's values are fetched during this one
-        auto fetch_inv = [&](uint32_t lt, float (&f)[NB]) -> bool {
-            bool ok = true;
+        // the NEXT tile's 1/||row|| and live bytes are requested during this tile and only looked at when it starts
+        // (lane c: column 32 j + c of this warp's half of the tile, j = 0..3)
+        auto fetch_inv = [&](uint32_t lt, float (&f)[NB], uint32_t (&lv)[NB]) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
-                f[j] = __int_as_float(0x7FC00000);
+                f[j] = 1.0f; lv[j] = 0u;
                 if (lt < my_tiles) {
-                    const uint32_t r = (pair + lt * p.n_pairs) * kGemmN + half * (kGemmN / 2) + j * 32 + lane;
-                    if (r < p.n_rows && p.live[r] != 0) f[j] = p.inv_norm ? p.inv_norm[r] : 1.0f;
-                    else ok = false;
+                    uint32_t r = (pair + lt * p.n_pairs) * kGemmN + half * (kGemmN / 2) + j * 32 + lane;
+                    r = r < p.n_rows ? r : p.n_rows - 1;
+                    lv[j] = p.live[r];
+                    if (p.inv_norm) f[j] = p.inv_norm[r];
                 }
             }
-            return ok;
         };
-        // One block of 32 scores per lane (v = fp32 bit patterns, already scaled).  Fast exit: nothing above any threshold.
-        auto select_block = [&](uint32_t (&v)[32], uint32_t row0) {
-            float g[8];
+        // One block of 32 scores per lane (v = fp32 bit patterns, already scaled; NaN = not a candidate).
+        auto select_block = [&](uint32_t (&v)[32], uint32_t row0, bool first) {
+            uint32_t mask = 0;
+            if (first) {
+                // the first columns a list sees are its first keys
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                g[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
-                             fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
-            const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-            if (!__any_sync(0xFFFFFFFFu, mx > thr)) return;
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) cnt += (__uint_as_float(v[c]) > thr) ? 1u : 0u;
-            uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, cnt);
-            if (qcnt + tot > (uint32_t)kGemmQueue) {
-                drain();                                         // raises thr: count again
-                cnt = 0;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) cnt += (__uint_as_float(v[c]) > thr) ? 1u : 0u;
-                tot = __reduce_add_sync(0xFFFFFFFFu, cnt);
-            }
-            if (tot <= (uint32_t)kGemmQueue) {
-                if (tot == 0u) return;
-                uint32_t slot = 0;
-                if (cnt) slot = atomicAdd(my_qcnt, cnt);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (g[i] > thr) {
-#pragma unroll
-                        for (int c = 4 * i; c < 4 * i + 4; ++c) {
-                            const float sc = __uint_as_float(v[c]);
-                            if (sc > thr) {
-                                my_q_key[slot] = make_key(sc, row0 + c);
-                                my_q_lane[slot] = (uint8_t)lane;
-                                ++slot;
-                            }
-                        }
-                    }
+                for (int c = 0; c < kGemmList; ++c) {
+                    const float sc = __uint_as_float(v[c]);
+                    if ((uint32_t)c < keep) my_list[c * 32] = (sc == sc) ? make_key(sc, row0 + c) : 0ull;
                 }
-                qcnt += tot;
-                __syncwarp();
+                rescan();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mask |= ((uint32_t)c >= keep && __uint_as_float(v[c]) > thr) ? (1u << c) : 0u;
             } else {
-                // early in the run more scores pass than the queue holds: column by column, draining in between
-#pragma unroll 1
-                for (int c4 = 0; c4 < 8; ++c4) {
+                float g[8];
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float sc = 0.f;
+                for (int i = 0; i < 8; ++i)
+                    g[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                                 fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                const float mx = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                if (!__any_sync(0xFFFFFFFFu, mx > thr)) return;                  // fast exit: nothing above any threshold
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) if (i == c4) sc = __uint_as_float(v[4 * i + cc]);   // register select, no local memory
-                        const bool pass = sc > thr;
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-                        if (m) {
-                            if (pass) {
-                                const uint32_t slot = qcnt + __popc(m & lt_mask);
-                                my_q_key[slot] = make_key(sc, row0 + 4 * c4 + cc);
-                                my_q_lane[slot] = (uint8_t)lane;
-                            }
-                            qcnt += __popc(m);
-                            if (qcnt > (uint32_t)(kGemmQueue - 32)) drain();
-                        }
+                for (int c = 0; c < 32; ++c) mask |= (__uint_as_float(v[c]) > thr) ? (1u << c) : 0u;
+            }
+            if (mask) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) my_sbuf[c * 32] = __uint_as_float(v[c]);
+                // every lane inserts its own items; the threshold rises as it goes, so later items are re-checked
+                while (mask) {
+                    const uint32_t c = (uint32_t)__ffs((int)mask) - 1u;
+                    mask &= mask - 1u;
+                    const float sc = my_sbuf[c * 32];
+                    if (sc > thr) {
+                        my_list[minpos * 32] = make_key(sc, row0 + c);
+                        rescan();
                     }
                 }
-                if (lane == 0) *my_qcnt = qcnt;
-                __syncwarp();
             }
+            __syncwarp();
         };
         float inv_next[NB];
-        bool ok_next = fetch_inv(0, inv_next);
+        uint32_t live_next[NB];
+        fetch_inv(0, inv_next, live_next);
 
         for (uint32_t lt = 0; lt < my_tiles; ++lt) {
             const uint32_t tile = pair + lt * p.n_pairs;
             const uint32_t row_base = tile * kGemmN + half * (kGemmN / 2);   // first row of this warp's 128 columns
             const uint32_t buf = lt & 1u;
+            bool ok = true;
+            float inv_cur[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const bool good = row_base + j * 32 + lane < p.n_rows && live_next[j] != 0u;
+                inv_cur[j] = good ? inv_next[j] : __int_as_float(0x7FC00000);      // NaN: tombstone or past the end
+                ok = ok && good;
+            }
             // unit-norm shards: when all 128 rows of this warp's half are live and in range the raw dot IS the score
             // (to within the norm deviation that the host adds to the error bound), so the scaling can be skipped
-            const bool raw = p.unit_rows != 0u && p.dbg == nullptr && __all_sync(0xFFFFFFFFu, ok_next);
+            const bool raw = p.unit_rows != 0u && p.dbg == nullptr && __all_sync(0xFFFFFFFFu, ok);
             if (!raw) {
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < NB; ++j) my_inv[j * 32 + lane] = inv_next[j];
+                for (int j = 0; j < NB; ++j) my_inv[j * 32 + lane] = inv_cur[j];
                 __syncwarp();
             }
-            ok_next = fetch_inv(lt + 1, inv_next);
+            fetch_inv(lt + 1, inv_next, live_next);
+            { const uint32_t t = my_thr[lane]; if (t) thr = fmaxf(thr, f32_from_orderable(t)); }   // the partner warp's progress
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((lq * 32u) << 16) + buf * kGemmN + half * (kGemmN / 2);
@@ -440,49 +397,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
 #pragma unroll
                     for (int c = 0; c < 32; ++c) p.dbg[(size_t)et * kGemmN + half * (kGemmN / 2) + j * 32 + c] = __uint_as_float(v[c]);
                 }
-                if (lt == 0 && j == 0) {
-                    // the first 32 scores of every query ARE its list: transpose through shared memory and sort each list
-                    // with a warp bitonic network instead of 1024 one-by-one inserts
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float sc = __uint_as_float(v[c]);
-                        warp_lists[lane * kGemmList + c] = (sc == sc) ? make_key(sc, row0 + c) : 0ull;
-                    }
-                    __syncwarp();
-                    for (uint32_t ql = 0; ql < 32; ++ql) {
-                        uint64_t x = warp_lists[ql * kGemmList + lane];
-#pragma unroll
-                        for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-                            for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                                const uint64_t o = shfl_xor_u64(x, jj);
-                                const bool asc = (lane & k) != 0, lower = (lane & jj) == 0;
-                                const bool take_min = (lower == asc);
-                                x = take_min ? (o < x ? o : x) : (o > x ? o : x);
-                            }
-                        }
-                        if ((uint32_t)lane >= p.keep) x = 0ull;
-                        warp_lists[ql * kGemmList + lane] = x;           // descending: lane 0 holds the best key
-                        if ((uint32_t)lane == p.keep - 1 && x != 0ull) atomicMax(my_thr + ql, (uint32_t)(x >> 32));
-                    }
-                    __syncwarp();
-                    { const uint32_t t = my_thr[lane]; thr = t ? f32_from_orderable(t) : -INFINITY; }
-                    continue;
-                }
-                select_block(v, row0);
+                select_block(v, row0, lt == 0 && j == 0);
             }
-            if (qcnt) drain();
         }
-        // ---- write this warp's 32 (CTA, column half, query) lists ----
+        // ---- sort (warp bitonic network, descending) and write this warp's 32 (CTA, column half, query) lists ----
         __syncwarp();
         const uint32_t L2 = 2 * p.n_pairs;
+        uint64_t* warp_lists = lists + (size_t)ew * 32 * kGemmList;
         for (uint32_t ql = 0; ql < 32; ++ql) {
+            uint64_t x = (uint32_t)lane < keep ? warp_lists[lane * 32 + ql] : 0ull;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    const uint64_t o = shfl_xor_u64(x, jj);
+                    const bool asc = (lane & k) != 0, lower = (lane & jj) == 0;
+                    const bool take_min = (lower == asc);
+                    x = take_min ? (o < x ? o : x) : (o > x ? o : x);
+                }
+            }
             const size_t q = (size_t)group * kGemmM + lq * 32 + ql;
             const size_t li = q * L2 + pair * 2 + half;
-            const uint64_t kv = warp_lists[ql * kGemmList + lane];
-            p.out_keys[li * kGemmList + lane] = kv;
-            if (lane == 0) p.out_tops[li] = kv;
-            if ((uint32_t)lane == p.keep - 1) p.out_drops[li] = kv;
+            if (lane < kGemmList) p.out_keys[li * kGemmList + lane] = x;             // lane 0 holds the best key
+            if (lane == 0) p.out_tops[li] = x;
+        }
+        {
+            const size_t q = (size_t)group * kGemmM + lq * 32 + lane;
+            const size_t li = q * L2 + pair * 2 + half;
+            p.out_drops[li] = thr > -INFINITY ? (((uint64_t)f32_orderable(thr) << 32) | 0xFFFFFFFFull) : 0ull;
         }
     }
 

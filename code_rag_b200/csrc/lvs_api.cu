@@ -841,7 +841,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         gp.out_keys = (uint64_t*)c->s_gkeys.p; gp.out_tops = (uint64_t*)c->s_gtops.p; gp.out_drops = (uint64_t*)c->s_gdrops.p;
         const bool unit_rows = c->metric == LVS_METRIC_COSINE && c->h_norm_stats[1] <= 0.001953125f && !c->opt_gemm_no_unit;
         gp.unit_rows = unit_rows ? 1u : 0u;
-        gp.keep = (uint32_t)std::min(32, std::max(4, c->opt_gemm_keep));
+        gp.keep = (uint32_t)std::min(kGemmList, std::max(4, c->opt_gemm_keep));
         gp.dbg = (c->opt_gemm_dbg & 1) ? (float*)c->s_dbg.p : nullptr;
         gp.dbg_mode = (uint32_t)(c->opt_gemm_dbg >> 1);
         cudaEvent_t es = nullptr, ee = nullptr;
