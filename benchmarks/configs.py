@@ -168,8 +168,59 @@ def c4(Q=64, k=100, n=10_000_000, G=64):
     dev.close()
 
 
+def c4f(Q=64, k=100, n=10_000_000, G=64):
+    """C4 through the fused C-ABI call (lvs_search_rank): search + on-device candidate build + K3, host buffers in and out.
+    Ranking attributes are synthetic per-row columns; graph candidates arrive as packed arrays (what the host packs from a
+    GraphContext); the ranked lists come back as arrays (index, score, signals)."""
+    import ctypes as C
+
+    from code_rag_b200 import _native as N
+    dim = 768
+    dev = DeviceCollection("c4f", dim, storage="bf16", capacity=n)
+    fill(dev, n, dim, "bf16", seed=3456)
+    n_names = 100_000
+    first = dev.rank_names_append([f"e{i}".encode() for i in range(n_names)])
+    assert first == 0
+    t0 = time.perf_counter()
+    for lo in range(0, n, 1_000_000):
+        r = np.arange(lo, min(n, lo + 1_000_000), dtype=np.int64)
+        dev.rank_attrs_set(r, r.astype(np.uint32), (r // 20).astype(np.uint32), r.astype(np.uint32), (r % n_names).astype(np.uint32),
+                           (10 + r % 300).astype(np.int32), np.full(len(r), 8, dtype=np.uint8))
+    t_attr = time.perf_counter() - t0
+    rng = np.random.default_rng(4567)
+    walls, sms, rms = [], [], []
+    for rep in range(5):
+        qs = rng.standard_normal((Q, dim))
+        ng = Q * G
+        arr = {
+            "offsets": (np.arange(Q + 1) * G).astype(np.int32), "kind": rng.choice([0, 1, 2, 3], size=ng).astype(np.uint8),
+            "key_id": rng.integers(0, n, size=ng).astype(np.uint32), "file_id": rng.integers(0, n // 20, size=ng).astype(np.uint32),
+            "depth": rng.integers(1, 4, size=ng).astype(np.int32), "entity_match": rng.choice([0.0, 0.5, 1.0], size=ng),
+            "degree": rng.poisson(12, size=ng).astype(np.int32), "flags": rng.integers(0, 8, size=ng).astype(np.uint8),
+            "weights": np.tile(np.array([0.5, 0.5, 0.2, 0.1]), (Q, 1)),
+        }
+        rb = N.RankBatch(); rb.n_queries = Q
+        for name, a in arr.items():
+            setattr(rb, name, a.ctypes.data_as(C.c_void_p))
+        ents = [f"e{int(x)}".encode() for x in rng.integers(0, n_names, size=Q)]
+        cx_arr = {"ent_off": np.arange(Q + 1, dtype=np.int32), "ent_str_off": np.concatenate([[0], np.cumsum([len(e) for e in ents])]).astype(np.uint32),
+                  "ent_bytes": np.frombuffer(b"".join(ents), dtype=np.uint8), "cen_off": (np.arange(Q + 1) * 10).astype(np.int32),
+                  "cen_id": rng.integers(0, n, size=Q * 10).astype(np.uint32), "cen_deg": rng.poisson(12, size=Q * 10).astype(np.int32)}
+        cx = N.RankQueryCtx()
+        for name, a in cx_arr.items():
+            setattr(cx, name, a.ctypes.data_as(C.c_void_p))
+        t1 = time.perf_counter()
+        out = dev.search_rank(qs, k, None, rb, cx, ng, 5, 50, 0.3, 0.15)
+        walls.append((time.perf_counter() - t1) * 1e3); sms.append(out["search_ms"]); rms.append(out["rank_ms"])
+    w = statistics.median(walls[1:])
+    emit(f"C4 fused (lvs_search_rank) 10M x 768 bf16, Q={Q}, vector top-{k} + {G} graph candidates", wall_ms=w,
+         search_device_ms=statistics.median(sms[1:]), gather_rank_device_us=statistics.median(rms[1:]) * 1e3, fused_qps=Q * 1e3 / w,
+         results_per_query=int(out["count"][0]), flagged=int((out["flags"] & 1).sum()), attr_upload_s=t_attr)
+    dev.close()
+
+
 if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["c1", "c2"]
     torch.cuda.init()
     for w in which:
-        {"c1": c1, "c2": c2, "c3": c3, "c4": c4}[w]()
+        {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c4f": c4f}[w]()

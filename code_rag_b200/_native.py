@@ -62,6 +62,10 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_exchange_error": (C.c_int, [_vp]),
     "lvs_exchange_destroy": (C.c_int, [_vp]),
     "lvs_rank_fuse": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
+    "lvs_rank_names_append": (C.c_int, [_vp, _vp, _vp, C.c_int, _u32p]),
+    "lvs_rank_attrs_set": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_search_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
     "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),
     "lvs_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lvs_fetch_rows_f32": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
@@ -71,6 +75,11 @@ class RankBatch(C.Structure):
     """``lvs_rank_batch`` of include/lvs.h."""
     _fields_ = [("n_queries", C.c_int32), ("offsets", _vp), ("kind", _vp), ("key_id", _vp), ("file_id", _vp), ("depth", _vp),
                 ("entity_match", _vp), ("degree", _vp), ("flags", _vp), ("content_len", _vp), ("vscore", _vp), ("weights", _vp)]
+
+
+class RankQueryCtx(C.Structure):
+    """``lvs_rank_query_ctx`` of include/lvs.h."""
+    _fields_ = [("ent_off", _vp), ("ent_str_off", _vp), ("ent_bytes", _vp), ("cen_off", _vp), ("cen_id", _vp), ("cen_deg", _vp)]
 
 
 _lib: C.CDLL | None = None

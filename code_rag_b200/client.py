@@ -75,8 +75,17 @@ def _id_sort_key(point_id: Any):
 class _HostCollection:
     """Host half of a collection: ids, payloads and the per-column value dictionaries."""
 
-    def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int, dev_factory=None):
+    def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int, dev_factory=None,
+                 rank_kind: str | None = None):
         self.name = name
+        # fused search -> rank (include/lvs.h lvs_search_rank): per-row ranking attributes are derived from the payload at
+        # upsert, the way VectorSearcher._transform_code_result / _transform_summary_result (query/vector_search.py:221-260)
+        # and HybridRanker._process_vector_results (ranking/ranker.py:150-169) would read them.  None = feature off.
+        self.rank_kind = rank_kind
+        self.rk_keys: dict[str, int] = {}
+        self.rk_files: dict[Any, int] = {}
+        self.rk_cent: dict[Any, int] = {}
+        self.rk_names: dict[str, int] = {}
         self.dim = dim
         self.columns: list[str] = list(index_fields)[: N.MAX_FILTER_COLS]
         self.dicts: list[dict[Any, int]] = [dict() for _ in self.columns]
@@ -184,6 +193,49 @@ class _HostCollection:
             self.payloads.append(None)
         for j, r in enumerate(rows):
             self.payloads[int(r)] = pl[j]
+        if self.rank_kind is not None:
+            self._set_rank_attrs(rows, pl)
+
+    def vector_result(self, row: int, score: float) -> dict[str, Any]:
+        """The dict VectorSearcher hands to the ranker for this row (query/vector_search.py:221-260)."""
+        p = self.payloads[row] or {}
+        if self.rank_kind == "summary":
+            return {"score": score, "file_path": p.get("file_path"), "entity_type": p.get("entity_type"),
+                    "entity_name": p.get("entity_name"), "summary": p.get("summary"), "graph_node_id": p.get("graph_node_id")}
+        return {"score": score, "file_path": p.get("file_path"), "entity_type": p.get("entity_type"),
+                "entity_name": p.get("entity_name"), "language": p.get("language"), "content": p.get("content"),
+                "start_line": p.get("start_line"), "end_line": p.get("end_line"), "graph_node_id": p.get("graph_node_id")}
+
+    def vector_result_from_hit(self, hit: dict[str, Any]) -> dict[str, Any]:
+        return self.vector_result(self.id_to_row[_canonical_id(hit["id"])], hit["score"])
+
+    def _set_rank_attrs(self, rows: np.ndarray, pl: Sequence[dict[str, Any] | None]) -> None:
+        n = len(rows)
+        key = np.empty(n, dtype=np.uint32); fil = np.empty(n, dtype=np.uint32); cent = np.empty(n, dtype=np.uint32)
+        nam = np.empty(n, dtype=np.uint32); clen = np.empty(n, dtype=np.int32); flg = np.empty(n, dtype=np.uint8)
+        new_names: list[bytes] = []
+        first_new = len(self.rk_names)
+        for j in range(n):
+            vr = self.vector_result(int(rows[j]), 0.0)
+            name = vr.get("entity_name")
+            content, summary = vr.get("content"), vr.get("summary")
+            key[j] = self.rk_keys.setdefault(f"{vr.get('file_path')}:{name}:{vr.get('start_line')}", len(self.rk_keys))
+            fil[j] = self.rk_files.setdefault(vr.get("file_path"), len(self.rk_files))
+            cent[j] = self.rk_cent.setdefault(vr.get("graph_node_id") or name, len(self.rk_cent))
+            low = name.lower() if isinstance(name, str) else ""      # the reference raises on a missing name; here: no match
+            nid = self.rk_names.get(low)
+            if nid is None:
+                nid = len(self.rk_names)
+                self.rk_names[low] = nid
+                new_names.append(low.encode("utf-8"))
+            nam[j] = nid
+            clen[j] = len(content) if content else -1
+            flg[j] = (1 if summary else 0) | (8 if content else 0)
+        if new_names:
+            got = self.dev.rank_names_append(new_names)
+            if got != first_new:
+                raise RuntimeError(f"entity-name pool out of step (device {got}, host {first_new})")
+        self.dev.rank_attrs_set(rows, key, fil, cent, nam, clen, flg)
 
     def _hits(self, rows: np.ndarray, scores: np.ndarray) -> list[dict[str, Any]]:
         out = []
@@ -301,7 +353,7 @@ class B200VectorStore:
 
     def __init__(self, host: str | None = None, port: int | None = None, grpc_port: int | None = None, *,
                  dimensions: int | None = None, storage: str | None = None, device: int | None = None,
-                 _device_factory=None):
+                 rank_attrs: bool = False, _device_factory=None):
         self._host, self._port, self._grpc_port = host, port, grpc_port
         if dimensions is None:
             dimensions = int(os.environ.get("EMBEDDING_DIMENSIONS", DEFAULT_DIMENSIONS))
@@ -314,6 +366,7 @@ class B200VectorStore:
         self._storage = storage or os.environ.get("LATTICE_B200_STORAGE", "f32")
         self._device = int(device if device is not None else os.environ.get("LOCAL_RANK", "0"))
         self._device_factory = _device_factory
+        self._rank_attrs = bool(rank_attrs)     # keep per-row ranking attributes on the device (enables search_and_rank)
         self._connected = False
         self._collections: dict[str, _HostCollection] = {}
         self._shim = _ClientShim(self)
@@ -370,7 +423,8 @@ class B200VectorStore:
                 if name not in self._collections:
                     self._collections[name] = await asyncio.to_thread(
                         _HostCollection, name, self._dimensions, self._storage, _INDEX_FIELDS[name], self._device,
-                        self._device_factory)
+                        self._device_factory,
+                        ("summary" if name == CollectionName.SUMMARIES.value else "code") if self._rank_attrs else None)
                     logger.info(f"Created collection: {name}")
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError("Failed to create collections", cause=e)
@@ -440,6 +494,28 @@ class B200VectorStore:
             return await asyncio.to_thread(work)
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to search {collection}", cause=e)
+
+    async def search_and_rank(self, collection: str, items: Sequence[tuple], limit: int = 10,
+                              filters: dict[str, Any] | None = None, ranker=None):
+        """Additive API: vector search + hybrid ranking in one device pass.
+
+        ``items``: one ``(plan, graph_context, query_vector, centrality_scores)`` per query.  Equivalent to
+        ``ranker.rank_results(plan, graph_context, <VectorSearcher-shaped results of search(query_vector, limit, filters)>,
+        centrality_scores)`` for every item (query/engine.py:176-181), but the top-k hits never leave the GPU between the
+        search and the blend.  Needs ``rank_attrs=True``.  Returns ``list[list[RankedResult]]``."""
+        try:
+            coll = self._get(collection)
+            if coll.rank_kind is None:
+                raise ValueError("search_and_rank needs a store created with rank_attrs=True")
+            from .ranking import HybridRanker
+            rk = ranker or HybridRanker()
+
+            def work():
+                with coll.lock:
+                    return rk.rank_batch_fused(coll, items, limit, filters or None)
+            return await asyncio.to_thread(work)
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to search and rank in {collection}", cause=e)
 
     async def delete(self, collection: str, filters: dict[str, Any]) -> None:
         try:

@@ -193,6 +193,52 @@ class DeviceCollection:
                                      _ptr(ties), _ptr(counts), _ptr(flags)), "lvs_search")
         return SearchResult(scores, rows, ties, counts, flags)
 
+    # ---- fused search -> rank (include/lvs.h: lvs_rank_names_append / lvs_rank_attrs_set / lvs_search_rank) ----------
+    def rank_names_append(self, names: list[bytes]) -> int:
+        """Append lower-cased UTF-8 entity names to the device-side pool; returns the id of the first one."""
+        lens = np.asarray([len(b) for b in names], dtype=np.uint32)
+        blob = np.frombuffer(b"".join(names), dtype=np.uint8) if lens.sum() else np.zeros(0, dtype=np.uint8)
+        first = C.c_uint32()
+        N.check(self._lib.lvs_rank_names_append(self._handle(), _ptr(blob) if len(blob) else None, _ptr(lens), len(names),
+                                                C.byref(first)), "lvs_rank_names_append")
+        return int(first.value)
+
+    def rank_attrs_set(self, rows, key_id, file_id, cent_id, name_id, content_len, flags) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        a = [np.ascontiguousarray(x, dtype=t) for x, t in ((key_id, np.uint32), (file_id, np.uint32), (cent_id, np.uint32),
+                                                             (name_id, np.uint32), (content_len, np.int32), (flags, np.uint8))]
+        N.check(self._lib.lvs_rank_attrs_set(self._handle(), _ptr(rows), len(rows), *[_ptr(x) for x in a]), "lvs_rank_attrs_set")
+
+    def search_rank(self, queries: np.ndarray, k: int, want, graph: "N.RankBatch", ctx: "N.RankQueryCtx", n_graph_total: int,
+                    max_per_file: int, max_total: int, entity_bonus: float, rel_bonus: float) -> dict:
+        q = np.ascontiguousarray(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
+        if q.dtype not in (np.float32, np.float64):
+            q = q.astype(np.float64)
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")
+        Q, k = q.shape[0], int(k)
+        out = {
+            "hit_scores": np.zeros((Q, k), dtype=np.float64), "hit_rows": np.full((Q, k), -1, dtype=np.int64),
+            "hit_counts": np.zeros(Q, dtype=np.uint32), "flags": np.zeros(Q, dtype=np.int32),
+            "count": np.zeros(Q, dtype=np.int32), "index": np.zeros((Q, max_total), dtype=np.int32),
+            "score": np.zeros((Q, max_total), dtype=np.float64), "signals": np.zeros((Q, max_total, 7), dtype=np.float64),
+            "mask": np.zeros((Q, max_total), dtype=np.uint8), "source": np.zeros((Q, max_total), dtype=np.uint8),
+            "leader": np.zeros(max(n_graph_total + Q * k, 1), dtype=np.int32),
+        }
+        ms = (C.c_float * 2)()
+        w = self._want(want)
+        N.check(self._lib.lvs_search_rank(self._handle(), _ptr(q), _np_dtype_code(q), Q, k, _ptr(w), C.byref(graph), C.byref(ctx),
+                                          int(max_per_file), int(max_total), float(entity_bonus), float(rel_bonus),
+                                          _ptr(out["hit_scores"]), _ptr(out["hit_rows"]), _ptr(out["hit_counts"]), _ptr(out["flags"]),
+                                          _ptr(out["count"]), _ptr(out["index"]), _ptr(out["score"]), _ptr(out["signals"]),
+                                          _ptr(out["mask"]), _ptr(out["source"]), _ptr(out["leader"]), ms), "lvs_search_rank")
+        out["search_ms"], out["rank_ms"] = float(ms[0]), float(ms[1])
+        return out
+
     def search_submit(self, queries: np.ndarray, k: int, want=None) -> tuple[int, int, int]:
         """Pipelined search: returns a ticket for :meth:`search_wait`; up to 4 searches may be in flight."""
         q = np.ascontiguousarray(queries)

@@ -144,13 +144,23 @@ struct lvs_collection {
     int opt_stages = 0;   // 0 = as many as fit
     int opt_grid = 0;     // 0 = one CTA per SM
     int opt_force_kpl = 0;
-    int opt_gemm_min_q = 8;   // batches of at least this many queries take the tensor-core path (K2)
+    int opt_gemm_min_q = 5;   // batches of at least this many queries take the tensor-core path (K2): one K2 pass (any Q <= 128)
+                              // costs about one K1 pass, and K1 needs two passes from 5 queries on
     int opt_path = 0;         // 0 auto, 1 force K1 scan, 2 force K2 (when eligible)
     int opt_gemm_dbg = 0;
     int opt_gemm_stages = 0;
     int opt_gemm_no_unit = 0;
     int opt_gemm_keep = 16;
     int opt_gemm_no_pair = 0;
+
+    // per-row ranking attributes + lower-cased entity-name pool (fused search -> rank path, lvs_search_rank)
+    int64_t rk_cap = 0;              // rows covered by the attribute columns
+    uint32_t* d_rk_key = nullptr; uint32_t* d_rk_file = nullptr; uint32_t* d_rk_cent = nullptr; uint32_t* d_rk_name = nullptr;
+    int32_t* d_rk_clen = nullptr; uint8_t* d_rk_flags = nullptr;
+    uint32_t* d_name_off = nullptr; uint8_t* d_name_bytes = nullptr;
+    int64_t n_names = 0, names_cap = 0, name_bytes_used = 0, name_bytes_cap = 0;
+    Scratch s_rk_dev, h_rk_pin;
+    cudaEvent_t rk_ev[3] = {nullptr, nullptr, nullptr};
 
     std::mutex mu;
 };
@@ -321,6 +331,11 @@ extern "C" int lvs_collection_create(const char* name, int dim, int storage, int
 extern "C" int lvs_collection_destroy(lvs_collection* c) {
     if (!c) return LVS_OK;
     if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_rk_key); cudaFree(c->d_rk_file); cudaFree(c->d_rk_cent); cudaFree(c->d_rk_name); cudaFree(c->d_rk_clen);
+    cudaFree(c->d_rk_flags); cudaFree(c->d_name_off); cudaFree(c->d_name_bytes);
+    if (c->s_rk_dev.p) cudaFree(c->s_rk_dev.p);
+    if (c->h_rk_pin.p) cudaFreeHost(c->h_rk_pin.p);
+    for (auto& e : c->rk_ev) if (e) cudaEventDestroy(e);
     free_arrays(c);
     cudaFree(c->d_max_norm); cudaFree(c->d_pw); cudaFree(c->d_counter);
     Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc,
@@ -1386,6 +1401,277 @@ extern "C" int lvs_rank_fuse(const lvs_rank_batch* in, int mode, int max_per_fil
     if (out_sigmask) memcpy(out_sigmask, hp + r_mask, rows);
     if (out_source) memcpy(out_source, hp + r_src, rows);
     if (nc > 0) memcpy(out_leader, hp + r_lead, (size_t)nc * 4);
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused search -> rank
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int regrow(T*& ptr, int64_t old_n, int64_t new_n, cudaStream_t st, int fill = -1) {
+    T* np_ = nullptr;
+    cudaError_t e = cudaMalloc(&np_, (size_t)new_n * sizeof(T));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LVS_ENOMEM, "cannot allocate %lld ranking-attribute entries: %s", (long long)new_n, cudaGetErrorString(e)); }
+    if (fill >= 0) CU(cudaMemsetAsync(np_, fill, (size_t)new_n * sizeof(T), st));
+    if (ptr && old_n > 0) CU(cudaMemcpyAsync(np_, ptr, (size_t)old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(ptr);
+    ptr = np_;
+    return LVS_OK;
+}
+
+extern "C" int lvs_rank_names_append(lvs_collection* c, const uint8_t* bytes, const uint32_t* lens, int n, uint32_t* first_id) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n < 0 || (n > 0 && !lens)) return fail(LVS_EINVAL, "bad name batch");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (first_id) *first_id = (uint32_t)c->n_names;
+    if (n == 0) return LVS_OK;
+    uint64_t total = 0;
+    for (int i = 0; i < n; ++i) total += lens[i];
+    if (total > 0 && !bytes) return fail(LVS_EINVAL, "NULL name bytes");
+    if ((uint64_t)c->name_bytes_used + total >= 0xFFFFFFFFull) return fail(LVS_ELIMIT, "entity-name pool exceeds 4 GiB");
+    cudaStream_t st = c->stream;
+    int rc;
+    if (c->n_names + n + 1 > c->names_cap) {
+        const int64_t nc = std::max<int64_t>(c->n_names + n + 1, std::max<int64_t>(1024, c->names_cap * 2));
+        if ((rc = regrow(c->d_name_off, c->names_cap ? c->n_names + 1 : 0, nc, st, 0)) != LVS_OK) return rc;
+        c->names_cap = nc;
+    }
+    if (c->name_bytes_used + (int64_t)total > c->name_bytes_cap) {
+        const int64_t nb = std::max<int64_t>(c->name_bytes_used + (int64_t)total, std::max<int64_t>(65536, c->name_bytes_cap * 2));
+        if ((rc = regrow(c->d_name_bytes, c->name_bytes_used, nb, st)) != LVS_OK) return rc;
+        c->name_bytes_cap = nb;
+    }
+    std::vector<uint32_t> offs((size_t)n + 1);
+    uint32_t o = (uint32_t)c->name_bytes_used;
+    for (int i = 0; i < n; ++i) { offs[i] = o; o += lens[i]; }
+    offs[n] = o;
+    CU(cudaMemcpyAsync(c->d_name_off + c->n_names, offs.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (total) CU(cudaMemcpyAsync(c->d_name_bytes + c->name_bytes_used, bytes, (size_t)total, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    c->n_names += n;
+    c->name_bytes_used += (int64_t)total;
+    return LVS_OK;
+}
+
+extern "C" int lvs_rank_attrs_set(lvs_collection* c, const int64_t* rows, int n, const uint32_t* key_id, const uint32_t* file_id,
+                                  const uint32_t* cent_id, const uint32_t* name_id, const int32_t* content_len, const uint8_t* flags) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n < 0) return fail(LVS_EINVAL, "bad n");
+    if (n == 0) return LVS_OK;
+    if (!rows || !key_id || !file_id || !cent_id || !name_id || !content_len || !flags) return fail(LVS_EINVAL, "NULL attribute array");
+    std::lock_guard<std::mutex> lk(c->mu);
+    int64_t max_row = -1;
+    for (int i = 0; i < n; ++i) {
+        const int64_t r = rows[i] - c->row_base;
+        if (r < 0 || r >= c->n_rows) return fail(LVS_EINVAL, "row %lld is not in the collection", (long long)rows[i]);
+        if ((int64_t)name_id[i] >= c->n_names) return fail(LVS_EINVAL, "name id %u has not been appended", name_id[i]);
+        max_row = std::max(max_row, r);
+    }
+    cudaStream_t st = c->stream;
+    int rc;
+    if (max_row >= c->rk_cap) {
+        const int64_t nc = std::max<int64_t>(std::max<int64_t>(max_row + 1, c->capacity), c->rk_cap * 2);
+        if ((rc = regrow(c->d_rk_key, c->rk_cap, nc, st, 0xFF)) != LVS_OK) return rc;
+        if ((rc = regrow(c->d_rk_file, c->rk_cap, nc, st, 0xFF)) != LVS_OK) return rc;
+        if ((rc = regrow(c->d_rk_cent, c->rk_cap, nc, st, 0xFF)) != LVS_OK) return rc;
+        if ((rc = regrow(c->d_rk_name, c->rk_cap, nc, st, 0xFF)) != LVS_OK) return rc;
+        if ((rc = regrow(c->d_rk_clen, c->rk_cap, nc, st, 0xFF)) != LVS_OK) return rc;
+        if ((rc = regrow(c->d_rk_flags, c->rk_cap, nc, st, 0)) != LVS_OK) return rc;
+        c->rk_cap = nc;
+    }
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t o = 0;
+    const size_t o_rows = o; o = al(o + (size_t)n * 8);
+    const size_t o_key = o; o = al(o + (size_t)n * 4);
+    const size_t o_file = o; o = al(o + (size_t)n * 4);
+    const size_t o_cent = o; o = al(o + (size_t)n * 4);
+    const size_t o_name = o; o = al(o + (size_t)n * 4);
+    const size_t o_clen = o; o = al(o + (size_t)n * 4);
+    const size_t o_flags = o; o = al(o + (size_t)n);
+    if ((rc = ensure_pinned(c->h_rk_pin, o)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_rk_dev, o)) != LVS_OK) return rc;
+    uint8_t* hp = (uint8_t*)c->h_rk_pin.p;
+    uint8_t* dp = (uint8_t*)c->s_rk_dev.p;
+    int64_t* hr = (int64_t*)(hp + o_rows);
+    for (int i = 0; i < n; ++i) hr[i] = rows[i] - c->row_base;
+    memcpy(hp + o_key, key_id, (size_t)n * 4); memcpy(hp + o_file, file_id, (size_t)n * 4); memcpy(hp + o_cent, cent_id, (size_t)n * 4);
+    memcpy(hp + o_name, name_id, (size_t)n * 4); memcpy(hp + o_clen, content_len, (size_t)n * 4); memcpy(hp + o_flags, flags, (size_t)n);
+    CU(cudaMemcpyAsync(dp, hp, o, cudaMemcpyHostToDevice, st));
+    RankAttrScatter sp;
+    sp.rows = (const int64_t*)(dp + o_rows); sp.n = n;
+    sp.key = (const uint32_t*)(dp + o_key); sp.file = (const uint32_t*)(dp + o_file); sp.cent = (const uint32_t*)(dp + o_cent);
+    sp.name = (const uint32_t*)(dp + o_name); sp.clen = (const int32_t*)(dp + o_clen); sp.flags = dp + o_flags;
+    sp.row_key = c->d_rk_key; sp.row_file = c->d_rk_file; sp.row_cent = c->d_rk_cent; sp.row_name = c->d_rk_name;
+    sp.row_clen = c->d_rk_clen; sp.row_flags = c->d_rk_flags;
+    rank_attr_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(sp);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return LVS_OK;
+}
+
+extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                               const lvs_rank_batch* graph, const lvs_rank_query_ctx* ctx, int max_per_file, int max_total,
+                               double entity_bonus, double rel_bonus, double* out_hit_scores, int64_t* out_hit_rows,
+                               uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
+                               double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+    int rc = check_search_args(c, queries, dtype, Q, k);
+    if (rc != LVS_OK) return rc;
+    if (Q == 0) return LVS_OK;
+    if (!graph || !graph->offsets || !graph->weights || graph->n_queries != Q) return fail(LVS_EINVAL, "graph batch must describe the same %d queries", Q);
+    if (!ctx || !ctx->ent_off || !ctx->ent_str_off || !ctx->cen_off) return fail(LVS_EINVAL, "NULL query context");
+    if (max_total < 1) return fail(LVS_EINVAL, "bad max_total");
+    if (!out_hit_scores || !out_hit_rows || !out_hit_counts || !out_flags || !out_count || !out_index || !out_score || !out_leader)
+        return fail(LVS_EINVAL, "NULL output");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->rk_cap < c->n_rows || !c->d_rk_key) return fail(LVS_ESTATE, "ranking attributes are not set for every row (lvs_rank_attrs_set)");
+    const int32_t* goff = graph->offsets;
+    const int64_t ngc = goff[Q];
+    int max_c = 0;
+    for (int q = 0; q < Q; ++q) {
+        const int g = goff[q + 1] - goff[q];
+        if (g < 0) return fail(LVS_EINVAL, "offsets must be non-decreasing");
+        max_c = std::max(max_c, g + k);
+    }
+    if (max_c > kRankMaxCand) return fail(LVS_ELIMIT, "%d candidates in one query exceed %d", max_c, kRankMaxCand);
+    if (ngc > 0 && (!graph->kind || !graph->key_id || !graph->file_id || !graph->depth || !graph->entity_match || !graph->degree ||
+                    !graph->flags)) return fail(LVS_EINVAL, "NULL graph candidate array");
+    const int64_t nc = ngc + (int64_t)Q * k;                 // combined candidates: per query its graph candidates, then k hit slots
+    const int n_ent = ctx->ent_off[Q], n_cen = ctx->cen_off[Q];
+    const size_t ent_bytes = n_ent > 0 ? ctx->ent_str_off[n_ent] : 0;
+    if (n_ent > 0 && ent_bytes > 0 && !ctx->ent_bytes) return fail(LVS_EINVAL, "NULL entity bytes");
+    if (n_cen > 0 && (!ctx->cen_id || !ctx->cen_deg)) return fail(LVS_EINVAL, "NULL centrality table");
+
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t qraw = (size_t)Q * c->dim * dt_size(dtype);
+    size_t o = 0;
+    const size_t o_q = o; o = al(o + qraw);
+    const size_t o_off = o; o = al(o + (size_t)(Q + 1) * 4);
+    const size_t o_ng = o; o = al(o + (size_t)Q * 4);
+    const size_t o_kind = o; o = al(o + (size_t)nc);
+    const size_t o_key = o; o = al(o + (size_t)nc * 4);
+    const size_t o_file = o; o = al(o + (size_t)nc * 4);
+    const size_t o_depth = o; o = al(o + (size_t)nc * 4);
+    const size_t o_em = o; o = al(o + (size_t)nc * 8);
+    const size_t o_deg = o; o = al(o + (size_t)nc * 4);
+    const size_t o_flags = o; o = al(o + (size_t)nc);
+    const size_t o_clen = o; o = al(o + (size_t)nc * 4);
+    const size_t o_vs = o; o = al(o + (size_t)nc * 8);
+    const size_t o_w = o; o = al(o + (size_t)Q * 32);
+    const size_t o_eoff = o; o = al(o + (size_t)(Q + 1) * 4);
+    const size_t o_esoff = o; o = al(o + (size_t)(n_ent + 1) * 4);
+    const size_t o_eb = o; o = al(o + ent_bytes);
+    const size_t o_coff = o; o = al(o + (size_t)(Q + 1) * 4);
+    const size_t o_cid = o; o = al(o + (size_t)std::max(n_cen, 1) * 4);
+    const size_t o_cdeg = o; o = al(o + (size_t)std::max(n_cen, 1) * 4);
+    const size_t in_bytes = o;
+    const size_t nres = (size_t)Q * k, rows = (size_t)Q * max_total;
+    // outputs (device -> host in one copy)
+    const size_t r_hs = o; o = al(o + nres * 8);
+    const size_t r_hr = o; o = al(o + nres * 8);
+    const size_t r_ht = o; o = al(o + nres * 8);
+    const size_t r_hc = o; o = al(o + (size_t)Q * 4);
+    const size_t r_hf = o; o = al(o + (size_t)Q * 4);
+    const size_t r_cnt = o; o = al(o + (size_t)Q * 4);     // candidates present per query (gather output)
+    const size_t r_err = o; o = al(o + 4);
+    const size_t r_count = o; o = al(o + (size_t)Q * 4);
+    const size_t r_index = o; o = al(o + rows * 4);
+    const size_t r_score = o; o = al(o + rows * 8);
+    const size_t r_norm = o; o = al(o + rows * 8);
+    const size_t r_sig = o; o = al(o + rows * 8 * kRankSignals);
+    const size_t r_mask = o; o = al(o + rows);
+    const size_t r_src = o; o = al(o + rows);
+    const size_t r_lead = o; o = al(o + (size_t)nc * 4);
+    const size_t total = o;
+    if ((rc = ensure_pinned(c->h_rk_pin, total)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_rk_dev, total)) != LVS_OK) return rc;
+    uint8_t* hp = (uint8_t*)c->h_rk_pin.p;
+    uint8_t* dp = (uint8_t*)c->s_rk_dev.p;
+    memcpy(hp + o_q, queries, qraw);
+    int32_t* off2 = (int32_t*)(hp + o_off);
+    int32_t* ngq = (int32_t*)(hp + o_ng);
+    for (int q = 0; q <= Q; ++q) off2[q] = goff[q] + q * k;
+    for (int q = 0; q < Q; ++q) {
+        const int g = goff[q + 1] - goff[q];
+        ngq[q] = g;
+        if (g == 0) continue;
+        const size_t src = (size_t)goff[q], dst = (size_t)off2[q];
+        memcpy(hp + o_kind + dst, graph->kind + src, (size_t)g);
+        memcpy(hp + o_key + dst * 4, graph->key_id + src, (size_t)g * 4);
+        memcpy(hp + o_file + dst * 4, graph->file_id + src, (size_t)g * 4);
+        memcpy(hp + o_depth + dst * 4, graph->depth + src, (size_t)g * 4);
+        memcpy(hp + o_em + dst * 8, graph->entity_match + src, (size_t)g * 8);
+        memcpy(hp + o_deg + dst * 4, graph->degree + src, (size_t)g * 4);
+        memcpy(hp + o_flags + dst, graph->flags + src, (size_t)g);
+        for (int i = 0; i < g; ++i) { ((int32_t*)(hp + o_clen))[dst + i] = -1; ((double*)(hp + o_vs))[dst + i] = 0.0; }
+    }
+    memcpy(hp + o_w, graph->weights, (size_t)Q * 32);
+    memcpy(hp + o_eoff, ctx->ent_off, (size_t)(Q + 1) * 4);
+    memcpy(hp + o_esoff, ctx->ent_str_off, (size_t)(n_ent + 1) * 4);
+    if (ent_bytes) memcpy(hp + o_eb, ctx->ent_bytes, ent_bytes);
+    memcpy(hp + o_coff, ctx->cen_off, (size_t)(Q + 1) * 4);
+    if (n_cen > 0) { memcpy(hp + o_cid, ctx->cen_id, (size_t)n_cen * 4); memcpy(hp + o_cdeg, ctx->cen_deg, (size_t)n_cen * 4); }
+
+    cudaStream_t st = c->stream;
+    for (auto& e : c->rk_ev) if (!e) CU(cudaEventCreate(&e));
+    CU(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dp + r_err, 0, 4, st));
+    CU(cudaEventRecord(c->rk_ev[0], st));
+    // 1. the search: top-k rows and float64 scores stay on the device
+    rc = search_core(c, dp + o_q, dtype, Q, k, want, (double*)(dp + r_hs), (int64_t*)(dp + r_hr), (uint64_t*)(dp + r_ht),
+                     (uint32_t*)(dp + r_hc), nullptr, (int32_t*)(dp + r_hf), true, st);
+    if (rc != LVS_OK) return rc;
+    CU(cudaEventRecord(c->rk_ev[1], st));
+    // 2. hits -> vector candidates, 3. K3
+    RankGatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.k = k; gp.offsets = (const int32_t*)(dp + o_off); gp.n_graph = (const int32_t*)(dp + o_ng);
+    gp.hit_scores = (const double*)(dp + r_hs); gp.hit_rows = (const int64_t*)(dp + r_hr); gp.hit_counts = (const uint32_t*)(dp + r_hc);
+    gp.row_base = c->row_base; gp.attr_rows = std::min(c->rk_cap, c->n_rows);
+    gp.row_key = c->d_rk_key; gp.row_file = c->d_rk_file; gp.row_cent = c->d_rk_cent; gp.row_name = c->d_rk_name;
+    gp.row_clen = c->d_rk_clen; gp.row_flags = c->d_rk_flags;
+    gp.name_off = c->d_name_off; gp.name_bytes = c->d_name_bytes; gp.n_names = (uint32_t)c->n_names;
+    gp.ent_off = (const int32_t*)(dp + o_eoff); gp.ent_str_off = (const uint32_t*)(dp + o_esoff); gp.ent_bytes = dp + o_eb;
+    gp.cen_off = (const int32_t*)(dp + o_coff); gp.cen_id = (const uint32_t*)(dp + o_cid); gp.cen_deg = (const int32_t*)(dp + o_cdeg);
+    gp.kind = dp + o_kind; gp.key_id = (uint32_t*)(dp + o_key); gp.file_id = (uint32_t*)(dp + o_file); gp.depth = (int32_t*)(dp + o_depth);
+    gp.entity_match = (double*)(dp + o_em); gp.degree = (int32_t*)(dp + o_deg); gp.flags = dp + o_flags;
+    gp.content_len = (int32_t*)(dp + o_clen); gp.vscore = (double*)(dp + o_vs);
+    gp.counts = (int32_t*)(dp + r_cnt); gp.error = (int32_t*)(dp + r_err);
+    rank_gather_kernel<<<Q, 128, 0, st>>>(gp);
+    CU(cudaGetLastError());
+    RankParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_queries = Q; p.offsets = gp.offsets; p.counts = gp.counts; p.kind = gp.kind; p.key_id = gp.key_id; p.file_id = gp.file_id;
+    p.depth = gp.depth; p.entity_match = gp.entity_match; p.degree = gp.degree; p.flags = gp.flags; p.content_len = gp.content_len;
+    p.vscore = gp.vscore; p.weights = (const double*)(dp + o_w);
+    p.mode = 0; p.max_per_file = max_per_file; p.max_total = max_total; p.entity_bonus = entity_bonus; p.rel_bonus = rel_bonus;
+    p.out_count = (int32_t*)(dp + r_count); p.out_index = (int32_t*)(dp + r_index); p.out_score = (double*)(dp + r_score);
+    p.out_norm = (double*)(dp + r_norm); p.out_signals = (double*)(dp + r_sig); p.out_sigmask = dp + r_mask; p.out_source = dp + r_src;
+    p.out_leader = (int32_t*)(dp + r_lead);
+    const size_t smem = rank_smem_bytes(std::max(max_c, 1));
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(rank_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rank_fuse_kernel<<<Q, kRankThreads, smem, st>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->rk_ev[2], st));
+    CU(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->last_launches += 2;
+    if (device_ms) {
+        cudaEventElapsedTime(&device_ms[0], c->rk_ev[0], c->rk_ev[1]);
+        cudaEventElapsedTime(&device_ms[1], c->rk_ev[1], c->rk_ev[2]);
+    }
+    if (*(int32_t*)(hp + r_err)) return fail(LVS_ESTATE, "a hit row has no ranking attributes");
+    memcpy(out_hit_scores, hp + r_hs, nres * 8);
+    memcpy(out_hit_rows, hp + r_hr, nres * 8);
+    memcpy(out_hit_counts, hp + r_hc, (size_t)Q * 4);
+    memcpy(out_flags, hp + r_hf, (size_t)Q * 4);
+    memcpy(out_count, hp + r_count, (size_t)Q * 4);
+    memcpy(out_index, hp + r_index, rows * 4);
+    memcpy(out_score, hp + r_score, rows * 8);
+    if (out_signals) memcpy(out_signals, hp + r_sig, rows * 8 * kRankSignals);
+    if (out_sigmask) memcpy(out_sigmask, hp + r_mask, rows);
+    if (out_source) memcpy(out_source, hp + r_src, rows);
+    memcpy(out_leader, hp + r_lead, (size_t)nc * 4);
     return LVS_OK;
 }
 

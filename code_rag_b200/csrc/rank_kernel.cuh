@@ -20,6 +20,7 @@ enum : int { SIG_GRAPH = 0, SIG_VECTOR = 1, SIG_CENTRALITY = 2, SIG_ENTITY = 3, 
 struct RankParams {
     int n_queries;
     const int32_t* offsets;      // [n_queries + 1]
+    const int32_t* counts;       // optional [n_queries]: candidates actually present (fused path: graph + hits found), else offsets diff
     const uint8_t* kind;         // 0 primary, 1 caller, 2 callee, 3 other graph, 4 vector
     const uint32_t* key_id;
     const uint32_t* file_id;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kRankThreads) rank_fuse_kernel(const RankParam
     extern __shared__ __align__(16) uint8_t rsm[];
     const int q = blockIdx.x, tid = threadIdx.x;
     const int base = p.offsets[q];
-    const int C = p.offsets[q + 1] - base;
+    const int C = p.counts ? p.counts[q] : p.offsets[q + 1] - base;
     double* sc = reinterpret_cast<double*>(rsm);                       // [C] candidate score, then merged score (leaders)
     double* fin = sc + C;                                              // [C] merged score of leaders
     uint32_t* key = reinterpret_cast<uint32_t*>(fin + C);              // [C]
@@ -217,6 +218,104 @@ __global__ void __launch_bounds__(kRankThreads) rank_fuse_kernel(const RankParam
     const double range = __dsub_rn(s_max, s_min);
     for (int s = tid; s < nout; s += kRankThreads)
         p.out_norm[ob + s] = range == 0.0 ? 1.0 : __ddiv_rn(__dsub_rn(p.out_score[ob + s], s_min), range);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused search -> rank (QueryEngine._execute_vector_search + rank_results glue,
+// reference query/engine.py:315-346,176-181 and ranking/ranker.py:150-169).  The search leaves its top-k rows and
+// float64 scores on the device; this kernel turns them into vector-hit candidates of K3 WITHOUT a host hop:
+// key / file / centrality-key ids, len(content) and the presence flags are per-row columns written at upsert, the
+// entity-name match (scorer.py:91-96: exact -> 1.0, any query entity contained in the name -> 0.5) is evaluated here on
+// the lower-cased UTF-8 names of a device-side string pool, the centrality degree is looked up in the query's short
+// (id, total_degree) table.  Graph candidates were packed by the host into the same arrays, ahead of the hits.
+// ---------------------------------------------------------------------------------------------------------
+struct RankGatherParams {
+    int k;                          // hit slots per query
+    const int32_t* offsets;         // [Q + 1] combined candidate offsets
+    const int32_t* n_graph;         // [Q] graph candidates of the query; its hits start right after them
+    const double* hit_scores;       // [Q][k]
+    const int64_t* hit_rows;        // [Q][k] global rows
+    const uint32_t* hit_counts;     // [Q]
+    int64_t row_base;
+    int64_t attr_rows;              // rows covered by the attribute columns
+    const uint32_t* row_key; const uint32_t* row_file; const uint32_t* row_cent; const uint32_t* row_name;
+    const int32_t* row_clen; const uint8_t* row_flags;
+    const uint32_t* name_off;       // [n_names + 1] byte offsets into name_bytes
+    const uint8_t* name_bytes;
+    uint32_t n_names;
+    const int32_t* ent_off;         // [Q + 1] -> entity indices of the query
+    const uint32_t* ent_str_off;    // [n_entities + 1] byte offsets into ent_bytes
+    const uint8_t* ent_bytes;
+    const int32_t* cen_off;         // [Q + 1]
+    const uint32_t* cen_id; const int32_t* cen_deg;
+    uint8_t* kind; uint32_t* key_id; uint32_t* file_id; int32_t* depth; double* entity_match; int32_t* degree;
+    uint8_t* flags; int32_t* content_len; double* vscore;
+    int32_t* counts;                // [Q] out: n_graph + hits
+    int32_t* error;                 // set to 1 when a hit row has no attributes
+};
+
+__device__ __forceinline__ bool bytes_equal(const uint8_t* a, const uint8_t* b, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) if (a[i] != b[i]) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) rank_gather_kernel(const RankGatherParams p) {
+    const int q = blockIdx.x;
+    const int hits = (int)min(p.hit_counts[q], (uint32_t)p.k);
+    const int ng = p.n_graph[q];
+    if (threadIdx.x == 0) p.counts[q] = ng + hits;
+    const int e0 = p.ent_off[q], e1 = p.ent_off[q + 1];
+    const int c0 = p.cen_off[q], c1 = p.cen_off[q + 1];
+    for (int s = threadIdx.x; s < hits; s += blockDim.x) {
+        const int g = p.offsets[q] + ng + s;
+        const int64_t row = p.hit_rows[(size_t)q * p.k + s] - p.row_base;
+        if (row < 0 || row >= p.attr_rows) { *p.error = 1; p.kind[g] = 4; p.key_id[g] = 0xFFFFFFFFu; p.file_id[g] = 0xFFFFFFFFu;
+            p.depth[g] = 0; p.entity_match[g] = 0.0; p.degree[g] = -1; p.flags[g] = 0; p.content_len[g] = -1; p.vscore[g] = 0.0; continue; }
+        const uint32_t nid = p.row_name[row];
+        double em = 0.0;
+        if (nid < p.n_names) {
+            const uint8_t* name = p.name_bytes + p.name_off[nid];
+            const uint32_t nlen = p.name_off[nid + 1] - p.name_off[nid];
+            bool sub = false;
+            for (int e = e0; e < e1; ++e) {
+                const uint8_t* es = p.ent_bytes + p.ent_str_off[e];
+                const uint32_t el = p.ent_str_off[e + 1] - p.ent_str_off[e];
+                if (el == nlen && bytes_equal(name, es, el)) { em = 1.0; break; }
+                if (!sub && el <= nlen) {
+                    for (uint32_t pos = 0; pos + el <= nlen; ++pos)
+                        if (bytes_equal(name + pos, es, el)) { sub = true; break; }
+                }
+            }
+            if (em == 0.0 && sub) em = 0.5;
+        }
+        const uint32_t cid = p.row_cent[row];
+        int deg = -1;
+        for (int c = c0; c < c1; ++c) if (p.cen_id[c] == cid) { deg = p.cen_deg[c] < 0 ? 0 : p.cen_deg[c]; break; }
+        p.kind[g] = 4;
+        p.key_id[g] = p.row_key[row];
+        p.file_id[g] = p.row_file[row];
+        p.depth[g] = 0;
+        p.entity_match[g] = em;
+        p.degree[g] = deg;
+        p.flags[g] = p.row_flags[row];
+        p.content_len[g] = p.row_clen[row];
+        p.vscore[g] = p.hit_scores[(size_t)q * p.k + s];
+    }
+}
+
+// row attribute scatter (upsert of ranking attributes)
+struct RankAttrScatter {
+    const int64_t* rows; int n;
+    const uint32_t* key; const uint32_t* file; const uint32_t* cent; const uint32_t* name; const int32_t* clen; const uint8_t* flags;
+    uint32_t* row_key; uint32_t* row_file; uint32_t* row_cent; uint32_t* row_name; int32_t* row_clen; uint8_t* row_flags;
+};
+__global__ void rank_attr_scatter_kernel(const RankAttrScatter p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const int64_t r = p.rows[i];
+    p.row_key[r] = p.key[i]; p.row_file[r] = p.file[i]; p.row_cent[r] = p.cent[i]; p.row_name[r] = p.name[i];
+    p.row_clen[r] = p.clen[i]; p.row_flags[r] = p.flags[i];
 }
 
 __host__ __device__ inline size_t rank_smem_bytes(int max_c) { return (size_t)max_c * (8 + 8 + 4 + 4 + 4 + 4 + 4); }

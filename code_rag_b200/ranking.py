@@ -191,6 +191,7 @@ class HybridRanker:
     def __init__(self, config: RankingConfig | None = None):
         self.config = config or RankingConfig()
         self.last_device_ms = 0.0
+        self.last_search_ms = 0.0
 
     def rank_results(self, plan, graph_context, vector_results: list[dict[str, Any]],
                      centrality_scores: dict[str, dict[str, int]] | None = None) -> list[RankedResult]:
@@ -251,6 +252,128 @@ class HybridRanker:
                 r.signal_scores = sig
                 r.final_score = float(out["score"][q, s])
                 r.source = _SOURCES[int(out["source"][q, s])]
+                ranked.append(r)
+            results.append(ranked)
+        return results
+
+    def rank_batch_fused(self, coll, items: Sequence[tuple], limit: int, filters=None) -> list[list[RankedResult]]:
+        """Search + rank in one device pass (``lvs_search_rank``).  ``coll`` is the adapter's host collection
+        (``client._HostCollection`` with ranking attributes); each item is ``(plan, graph_context, query_vector, centrality)``.
+        Same results as ``rank_batch`` fed with the VectorSearcher-shaped hits of ``coll.search`` - the vector-hit candidates
+        (key / file ids, entity match, centrality, quality inputs) are built on the GPU from per-row columns."""
+        cfg = self.config
+        nq = len(items)
+        if nq == 0:
+            return []
+        want = coll.want_codes(filters)
+        b = _Batch()
+        ent_off, ent_str_off, ent_blob = [0], [0], []
+        cen_off, cen_id, cen_deg = [0], [], []
+        tmp_keys: dict[str, int] = {}
+        tmp_files: dict[Any, int] = {}
+        queries = np.empty((nq, coll.dim), dtype=np.float64)
+        groups = (("primary_entities", 0, None), ("callers", 1, "caller"), ("callees", 2, "callee"), ("methods", 3, "method"),
+                  ("parent_classes", 3, "parent_class"), ("child_classes", 3, "child_class"))
+        for qi, (plan, ctx, qvec, centrality) in enumerate(items):
+            centrality = centrality or {}
+            queries[qi] = np.asarray(qvec, dtype=np.float64)
+            qents = {e.name.lower() for e in plan.entities}
+            b.weights.append(cfg.weights_for(plan.primary_intent))
+            for attr, kind, rel in groups:
+                for node in getattr(ctx, attr):
+                    depth = None
+                    if kind in (1, 2):
+                        md = getattr(node, "metadata", None)
+                        depth = md.get("depth", 1) if md else 1
+                    flags = (1 if node.summary else 0) | (2 if node.docstring else 0) | (4 if node.signature else 0)
+                    ks = f"{node.file_path}:{node.name}:{node.start_line}"
+                    kid = coll.rk_keys.get(ks)
+                    if kid is None:        # not a key of any stored row: ids above 2^31 cannot collide with row keys
+                        kid = 0x80000000 + tmp_keys.setdefault(ks, len(tmp_keys))
+                    fid = coll.rk_files.get(node.file_path)
+                    if fid is None:
+                        fid = 0x80000000 + tmp_files.setdefault(node.file_path, len(tmp_files))
+                    b.kind.append(kind); b.key.append(kid); b.file.append(fid); b.depth.append(int(depth) if depth else 0)
+                    b.em.append(_entity_match(node.name, qents)); b.degree.append(_degree(node.qualified_name or node.name, centrality))
+                    b.flags.append(flags)
+                    b.records.append((kind, node, rel, depth))
+            b.offsets.append(len(b.kind))
+            for e in qents:
+                eb = e.encode("utf-8")
+                ent_blob.append(eb)
+                ent_str_off.append(ent_str_off[-1] + len(eb))
+            ent_off.append(len(ent_str_off) - 1)
+            for name, d in centrality.items():
+                cid = coll.rk_cent.get(name)
+                if cid is not None:
+                    cen_id.append(cid)
+                    cen_deg.append(max(int(d.get("total_degree", 0)), 0))
+            cen_off.append(len(cen_id))
+        ng_total = len(b.kind)
+        arr = {
+            "offsets": np.asarray(b.offsets, dtype=np.int32), "kind": np.asarray(b.kind, dtype=np.uint8),
+            "key_id": np.asarray(b.key, dtype=np.uint32), "file_id": np.asarray(b.file, dtype=np.uint32),
+            "depth": np.asarray(b.depth, dtype=np.int32), "entity_match": np.asarray(b.em, dtype=np.float64),
+            "degree": np.asarray(b.degree, dtype=np.int32), "flags": np.asarray(b.flags, dtype=np.uint8),
+            "weights": np.asarray(b.weights, dtype=np.float64).reshape(nq, 4),
+        }
+        rb = N.RankBatch()
+        rb.n_queries = nq
+        for name, a in arr.items():
+            setattr(rb, name, a.ctypes.data_as(C.c_void_p))
+        cx_arr = {
+            "ent_off": np.asarray(ent_off, dtype=np.int32), "ent_str_off": np.asarray(ent_str_off, dtype=np.uint32),
+            "ent_bytes": np.frombuffer(b"".join(ent_blob) or b"\0", dtype=np.uint8),
+            "cen_off": np.asarray(cen_off, dtype=np.int32), "cen_id": np.asarray(cen_id or [0], dtype=np.uint32),
+            "cen_deg": np.asarray(cen_deg or [0], dtype=np.int32),
+        }
+        cx = N.RankQueryCtx()
+        for name, a in cx_arr.items():
+            setattr(cx, name, a.ctypes.data_as(C.c_void_p))
+        k = int(limit)
+        out = coll.dev.search_rank(queries, k, want, rb, cx, ng_total, cfg.max_per_file, cfg.max_total, cfg.entity_match_bonus,
+                                   cfg.relationship_bonus)
+        self.last_device_ms = out["rank_ms"]
+        self.last_search_ms = out["search_ms"]
+        if (out["flags"] & 1).any():
+            # rare: the search could not prove exactness with the default candidate set - take the two-step route
+            hits = coll.search(queries, k, filters)
+            return self.rank_batch([(it[0], it[1], [coll.vector_result_from_hit(h) for h in hits[i]], it[3])
+                                    for i, it in enumerate(items)])
+        results = []
+        for q in range(nq):
+            g0, g1 = b.offsets[q], b.offsets[q + 1]
+            ng = g1 - g0
+            base = g0 + q * k                       # combined candidate index of this query's first candidate
+            nh = int(out["hit_counts"][q])
+
+            def record(ci, q=q, g0=g0, ng=ng):
+                if ci < ng:
+                    return b.records[g0 + ci]
+                s_ = ci - ng
+                return (4, coll.vector_result(int(out["hit_rows"][q, s_]), float(out["hit_scores"][q, s_])), None, None)
+            members: dict[int, list[int]] = {}
+            for ci in range(ng + nh):
+                members.setdefault(int(out["leader"][base + ci]), []).append(ci)
+            ranked = []
+            for s_ in range(int(out["count"][q])):
+                li = int(out["index"][q, s_])
+                rec = record(li)
+                r = self._to_result(rec)
+                for mi in members[li][1:]:
+                    o = self._to_result(record(mi))
+                    for f in ("content", "summary", "signature", "docstring"):
+                        if not getattr(r, f) and getattr(o, f):
+                            setattr(r, f, getattr(o, f))
+                mask = int(out["mask"][q, s_])
+                order = _VECTOR_ORDER if rec[0] == 4 else _GRAPH_ORDER
+                sig = {n: float(out["signals"][q, s_, SIGNAL_NAMES.index(n)]) for n in order}
+                for n_i, n in enumerate(SIGNAL_NAMES):
+                    if mask & (1 << n_i) and n not in sig:
+                        sig[n] = float(out["signals"][q, s_, n_i])
+                r.signal_scores = sig
+                r.final_score = float(out["score"][q, s_])
+                r.source = _SOURCES[int(out["source"][q, s_])]
                 ranked.append(r)
             results.append(ranked)
         return results

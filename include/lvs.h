@@ -160,6 +160,35 @@ int lvs_rank_fuse(const lvs_rank_batch* in, int mode, int max_per_file, int max_
                   int32_t* out_count, int32_t* out_index, double* out_score, double* out_norm, double* out_signals,
                   uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms);
 
+/* ---- fused search -> rank (the glue between QueryEngine._execute_vector_search query/engine.py:315-346
+ *      and HybridRanker._process_vector_results ranking/ranker.py:150-169) ---------------------------------------------
+ * Per-row ranking attributes are written once, at upsert: the interned ids of f"{file_path}:{entity_name}:{start_line}",
+ * of file_path and of (graph_node_id or entity_name); the id of the lower-cased entity name in the collection's name
+ * pool; len(content) (-1: none) and the presence flags (bit0 summary, bit3 content).  lvs_search_rank then runs the
+ * search, builds the vector-hit candidates from those columns on the device (entity-name match scorer.py:91-96 included)
+ * and ranks them together with the caller's graph candidates in ONE call: no host hop between top-k and blend. */
+int lvs_rank_names_append(lvs_collection* c, const uint8_t* bytes, const uint32_t* lens, int n, uint32_t* first_id);
+int lvs_rank_attrs_set(lvs_collection* c, const int64_t* rows, int n, const uint32_t* key_id, const uint32_t* file_id,
+                       const uint32_t* cent_id, const uint32_t* name_id, const int32_t* content_len, const uint8_t* flags);
+typedef struct lvs_rank_query_ctx {
+    const int32_t* ent_off;        /* [Q + 1]: query q's entities are ent_off[q] .. ent_off[q+1] */
+    const uint32_t* ent_str_off;   /* [n_entities + 1] byte offsets of the lower-cased UTF-8 entity names */
+    const uint8_t* ent_bytes;
+    const int32_t* cen_off;        /* [Q + 1]: query q's centrality entries */
+    const uint32_t* cen_id;        /* interned (graph_node_id or entity_name) */
+    const int32_t* cen_deg;        /* total_degree */
+} lvs_rank_query_ctx;
+/* `graph` holds ONLY the graph candidates (kinds 0..3; content_len / vscore ignored) and the weights; each query's vector hits
+ * are appended behind its graph candidates, k slots per query: candidate index i >= n_graph(q) is hit slot i - n_graph(q).
+ * out_leader has graph->offsets[Q] + Q*k entries in that combined order.  out_flags bit0: the search could not prove
+ * exactness for the query with the default candidate set (repeat it through lvs_search + lvs_rank_fuse).
+ * device_ms[2]: search, gather + rank. */
+int lvs_search_rank(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                    const lvs_rank_batch* graph, const lvs_rank_query_ctx* ctx, int max_per_file, int max_total,
+                    double entity_bonus, double rel_bonus, double* out_hit_scores, int64_t* out_hit_rows,
+                    uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
+                    double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the collection's stream) of the kernels of the last lvs_search* call on this handle:
  * [0] query prep  [1] scan / tensor-core kernel(s)  [2] finalize  [3] whole device section; n_launches = kernels launched. */

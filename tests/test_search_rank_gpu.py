@@ -1,0 +1,165 @@
+"""Fused search -> rank (lvs_search_rank) vs the two-step route and the ranking oracle.
+
+The fused call must return exactly what the reference's flow returns (query/engine.py:315-346 then 176-181):
+VectorSearcher-shaped hits of ``search`` fed to ``HybridRanker.rank_results``.  Checked three ways: against our own two-step
+``search`` + ``rank_batch`` (bit-exact K3 pinned on goldens made by the reference's code), against the CPU ranking oracle
+fed with the hits of the CPU search oracle, and on the edge cases (filters, empty graph context, no entities, no hits).
+"""
+import asyncio
+import random
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+
+import lvs_synth as synth
+
+pytestmark = pytest.mark.gpu
+
+DIM = 96
+N_ROWS = 6000
+INTENTS = ["find_callers", "find_similar", "search_functionality", "explain_architecture", "locate_entity", "find_hierarchy"]
+
+
+def _payloads(rng: random.Random, n: int):
+    out = []
+    for i in range(n):
+        name = rng.choice(["Parse", "parse_file", "load", "UserService", "save", "handle_request", "Größe", "λ_fn"]) + (f"_{i % 97}" if i % 3 else "")
+        p = {"file_path": f"src/m{rng.randrange(60)}.py", "entity_type": rng.choice(["function", "method", "class"]),
+             "entity_name": name, "language": "python", "start_line": rng.randrange(1, 400), "end_line": 500,
+             "content": "x" * rng.choice([0, 10, 60, 150, 1999, 2500, 3500]), "project_name": rng.choice(["a", "b"]),
+             "graph_node_id": rng.choice([None, f"pkg.{name}"])}
+        if p["content"] == "":
+            p["content"] = None
+        out.append(p)
+    return out
+
+
+def _case(rng: random.Random, payloads, q: int, qvec):
+    nodes = []
+    for i in range(rng.choice([0, 7, 30])):
+        if rng.random() < 0.4:
+            p = rng.choice(payloads)      # same key as a stored row: merges when that row is a hit
+            nm, fp, sl = p["entity_name"], p["file_path"], p["start_line"]
+        else:
+            nm, fp, sl = f"g{i}", f"src/m{rng.randrange(60)}.py", 1000 + i
+        nodes.append(NS(node_type="Function", name=nm, qualified_name=rng.choice([None, f"pkg.{nm}"]), file_path=fp,
+                        signature=rng.choice([None, "s"]), docstring=rng.choice([None, "d"]), summary=rng.choice([None, "x"]),
+                        start_line=sl, end_line=sl + 1, metadata={"depth": rng.choice([0, 1, 2, 3, 5])}))
+    cut = [0, len(nodes) // 6, len(nodes) // 2, (2 * len(nodes)) // 3, (5 * len(nodes)) // 6, (11 * len(nodes)) // 12, len(nodes)]
+    names = ("primary_entities", "callers", "callees", "methods", "parent_classes", "child_classes")
+    ctx = NS(**{nm: nodes[cut[i]:cut[i + 1]] for i, nm in enumerate(names)})
+    ents = rng.choice([[], ["parse"], ["Parse_5", "save"], ["größe"], [""], ["userservice", "load_12", "zzz"]])
+    plan = NS(primary_intent=NS(value=INTENTS[q % len(INTENTS)]), entities=[NS(name=e) for e in ents])
+    cent = {}
+    for p in rng.sample(payloads, 8):
+        cent[p["graph_node_id"] or p["entity_name"]] = {"total_degree": rng.choice([-3, 0, 5, 12, 49, 50, 80])}
+    cent["not.in.the.index"] = {"total_degree": 7}
+    return plan, ctx, qvec, cent
+
+
+@pytest.fixture(scope="module")
+def store(native_lib):
+    """Two identical stores: local-mode scores depend on how many searches ran since a row was written,
+    so the fused route runs on one and the two-step route on the other, search for search."""
+    from code_rag_b200.client import B200VectorStore
+    rng = random.Random(77)
+    x, q = synth.unit_rows(N_ROWS, DIM, seed=5, n_queries=24)
+    payloads = _payloads(rng, N_ROWS)
+    ids = [str(__import__("uuid").UUID(int=i + 1)) for i in range(N_ROWS)]
+    rewritten = {i: dict(payloads[i], entity_name="Rewritten", start_line=7, content="y" * 120) for i in (3, 500, 4242)}
+
+    async def setup(st):
+        await st.connect()
+        await st.create_collections()
+        for lo in range(0, N_ROWS, 1500):
+            await st.upsert("code_chunks", ids[lo:lo + 1500], x[lo:lo + 1500].astype(np.float64).tolist(), payloads[lo:lo + 1500])
+        # overwrite a few rows (new payloads, same ids) and delete one file's chunks: the attribute columns must follow
+        await st.upsert("code_chunks", [ids[i] for i in rewritten], x[list(rewritten)].astype(np.float64).tolist(), list(rewritten.values()))
+        await st.delete("code_chunks", {"file_path": "src/m7.py"})
+    st_a = B200VectorStore(dimensions=DIM, storage="f32", rank_attrs=True)
+    st_b = B200VectorStore(dimensions=DIM, storage="f32", rank_attrs=True)
+    asyncio.run(setup(st_a))
+    asyncio.run(setup(st_b))
+    for i, p in rewritten.items():
+        payloads[i] = p
+    yield st_a, st_b, payloads, q.astype(np.float64), x
+    asyncio.run(st_a.close())
+    asyncio.run(st_b.close())
+
+
+def _same(a, b):
+    assert [r.get_key() for r in a] == [r.get_key() for r in b]
+    for ra, rb in zip(a, b):
+        assert ra.final_score == rb.final_score and ra.source == rb.source and ra.signal_scores == rb.signal_scores, ra.get_key()
+        for f in ("file_path", "entity_name", "entity_type", "qualified_name", "content", "summary", "signature", "docstring",
+                  "start_line", "end_line", "graph_node_id", "relationship_path", "depth_from_query"):
+            assert getattr(ra, f) == getattr(rb, f), (ra.get_key(), f)
+
+
+@pytest.mark.parametrize("filters", [None, {"project_name": "a"}, {"file_path": "src/m3.py"}, {"project_name": "nobody"}])
+def test_fused_equals_two_step(store, filters):
+    from code_rag_b200.ranking import HybridRanker
+    st, st_b, payloads, q, _ = store
+    rng = random.Random(11)
+    items = [_case(rng, payloads, i, q[i]) for i in range(len(q))]
+    coll = st_b._get("code_chunks")
+    ranker = HybridRanker()
+    fused = asyncio.run(st.search_and_rank("code_chunks", items, limit=20, filters=filters, ranker=ranker))
+    assert ranker.last_search_ms > 0 and ranker.last_device_ms > 0
+    hits = asyncio.run(st_b.search_batch("code_chunks", [it[2] for it in items], limit=20, filters=filters))
+    two_step = ranker.rank_batch([(it[0], it[1], [coll.vector_result_from_hit(h) for h in hits[i]], it[3]) for i, it in enumerate(items)])
+    assert len(fused) == len(two_step) == len(items)
+    n_hybrid = 0
+    for a, b in zip(fused, two_step):
+        _same(a, b)
+        n_hybrid += sum(r.source == "hybrid" for r in a)
+    if filters is None:
+        assert n_hybrid > 0, "the cases are meant to produce graph/vector merges"
+
+
+def test_fused_equals_cpu_oracles(store):
+    """End to end against the CPU restatements: search oracle (qdrant local mode) -> ranking oracle (reference ranker)."""
+    from oracle import ranking as R
+    from oracle.qdrant_local import OracleCollection
+    st, _, payloads, q, x = store
+    coll = st._get("code_chunks")
+    # the oracle replays the store's history: same rows, same overwrites and deletions, same number of earlier searches
+    ora = OracleCollection(DIM)
+    ora.upsert_rows_f32(0, x.astype(np.float32), [None] * len(x))
+    dead = [r for r, p in enumerate(coll.payloads) if p and p.get("file_path") == "src/m7.py"]
+    ora.deleted[dead] = True
+    for _ in range(coll.dev.search_counter):
+        ora.search_topk_rows(q[0], 1)           # a local-mode search re-normalises the matrix in place, whatever the query
+    rng = random.Random(23)
+    items = [_case(rng, payloads, i, q[i]) for i in range(8)]
+    fused = asyncio.run(st.search_and_rank("code_chunks", items, limit=15))
+    for i, (plan, ctx, qv, cent) in enumerate(items):
+        rows, scores = ora.search_topk_rows(qv, 15)
+        vec = [coll.vector_result(int(r), float(s)) for r, s in zip(rows, scores)]
+        node = lambda n: {"node_type": n.node_type, "name": n.name, "qualified_name": n.qualified_name, "file_path": n.file_path,
+                          "signature": n.signature, "docstring": n.docstring, "summary": n.summary, "start_line": n.start_line,
+                          "end_line": n.end_line, "metadata": n.metadata}
+        case = {"intent": plan.primary_intent.value, "entities": [e.name for e in plan.entities], "vector": vec, "centrality": cent,
+                "graph": {k: [node(n) for n in getattr(ctx, k)] for k in
+                          ("primary_entities", "callers", "callees", "methods", "parent_classes", "child_classes")}}
+        exp = R.hybrid_rank(case)
+        got = fused[i]
+        assert [r.get_key() for r in got] == [e["key"] for e in exp]
+        assert [r.source for r in got] == [e["source"] for e in exp]
+        for r, e in zip(got, exp):
+            assert abs(r.final_score - e["final_score"]) <= 1e-9 * max(1.0, abs(e["final_score"]))
+
+
+def test_fused_needs_rank_attrs(native_lib):
+    from code_rag_b200.client import B200VectorStore
+    from code_rag_b200.errors import VectorStoreError
+    st = B200VectorStore(dimensions=8)
+
+    async def run():
+        await st.connect()
+        await st.create_collections()
+        with pytest.raises(VectorStoreError):
+            await st.search_and_rank("code_chunks", [(None, None, [0.0] * 8, None)])
+        await st.close()
+    asyncio.run(run())
