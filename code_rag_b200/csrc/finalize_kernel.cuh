@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     // ---- 1a. fast path (L >= kp lists): the kp-th largest LIST MAXIMUM is a threshold with at least kp keys at or
     //          above it (the kp maxima themselves) and, for well-mixed shards, few more; gather those keys.
     bool folded = true;
+    uint32_t nmerged = 32;                               // keys handed to the ranking step (a power of two, zero padded)
     if (p.L >= kp && p.L <= (uint32_t)kSortCap) {
         const uint64_t* tops = p.tops + (size_t)qi * p.L;
         if (tid == 0) { scal[0] = 0; scal[1] = 0; }
@@ -301,16 +302,19 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         __syncthreads();
         const uint32_t got = scal[0];
         if (got <= kFinWarps * KPW) {
-            for (uint32_t i = got + tid; i < kFinWarps * KPW; i += kFinThreads) sortbuf[i] = 0ull;
+            while (nmerged < got) nmerged <<= 1;          // sort no more than the next power of two above the survivors
+            for (uint32_t i = got + tid; i < nmerged; i += kFinThreads) sortbuf[i] = 0ull;
             folded = false;
         }
         __syncthreads();
     }
     // ---- 1b. general path: exact radix select of the kp-th largest key (MSB first, 8 bits per pass over the keys in L2);
-    //          stops as soon as the keys at or above the current bucket fit the sort buffer
+    //          stops as soon as at most 2 k' keys lie at or above the current bucket
     if (folded) {
         uint64_t prefix = 0, mask = 0;
         uint32_t remaining = kp;                         // rank still to be located inside the current prefix bucket
+        // refine until at most 2 kp keys survive: a small sort beats another pass over the keys only below that
+        const uint32_t stop_at = min(kFinWarps * KPW, max(2u * kp, 64u));
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = 56 - 8 * pass;
             hist[tid] = 0;                               // kFinThreads == 256
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
                     if (cum + hist[b] >= remaining) {
                         digit = (uint32_t)b; rem = remaining - cum;
                         // keys above the bucket: (kp - remaining) + cum; with the bucket itself they must fit the buffer
-                        stop = ((kp - remaining) + cum + hist[b] <= kFinWarps * KPW) ? 1u : 0u;
+                        stop = ((kp - remaining) + cum + hist[b] <= stop_at) ? 1u : 0u;
                         break;
                     }
                     cum += hist[b];
@@ -355,11 +359,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         }
         __syncthreads();
         const uint32_t got = min(scal[0], kFinWarps * KPW);
-        for (uint32_t i = got + tid; i < kFinWarps * KPW; i += kFinThreads) sortbuf[i] = 0ull;
+        nmerged = 32;
+        while (nmerged < got) nmerged <<= 1;
+        for (uint32_t i = got + tid; i < nmerged; i += kFinThreads) sortbuf[i] = 0ull;
         __syncthreads();
     }
-    // ---- 2. rank the 8*KPW merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
-    const uint32_t nmerged = kFinWarps * KPW;
+    // ---- 2. rank the merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
     if (tid == 0) scal[0] = 0;
     __syncthreads();
     {
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     __syncthreads();
     const uint32_t nsurv = scal[0];
     const uint32_t ncand = min(nsurv, kp);
-    if (nmerged <= 512u) {
+    if (nmerged <= 256u) {
         for (uint32_t i = tid; i < nmerged; i += kFinThreads) {
             const uint64_t v = sortbuf[i];
             if (v == 0ull) continue;
