@@ -66,6 +66,8 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_rank_attrs_set": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
+    "lvs_snapshot_save": (C.c_int, [_vp, C.c_char_p]),
+    "lvs_snapshot_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_vp)]),
     "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),
     "lvs_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lvs_fetch_rows_f32": (C.c_int, [_vp, _vp, C.c_int64, _vp]),

@@ -284,6 +284,32 @@ class _HostCollection:
     def close(self) -> None:
         self.dev.close()
 
+    # -- snapshots ---------------------------------------------------------------------------------------------
+    _HOST_STATE = ("name", "dim", "columns", "dicts", "ids", "id_to_row", "payloads", "rank_kind", "rk_keys", "rk_files",
+                   "rk_cent", "rk_names")
+
+    def save(self, directory: str) -> None:
+        """Device arrays -> ``<name>.lvs`` (raw, row order), host half (ids, payloads, dictionaries) -> ``<name>.host.pkl``."""
+        import pickle
+        os.makedirs(directory, exist_ok=True)
+        self.dev.save_snapshot(os.path.join(directory, f"{self.name}.lvs"))
+        with open(os.path.join(directory, f"{self.name}.host.pkl"), "wb") as f:
+            pickle.dump({k: getattr(self, k) for k in self._HOST_STATE}, f, protocol=pickle.HIGHEST_PROTOCOL)
+
+    @classmethod
+    def load(cls, directory: str, name: str, device: int) -> "_HostCollection":
+        import pickle
+        with open(os.path.join(directory, f"{name}.host.pkl"), "rb") as f:
+            state = pickle.load(f)
+        self = cls.__new__(cls)
+        for k in cls._HOST_STATE:
+            setattr(self, k, state[k])
+        self.lock = threading.Lock()
+        self.dev = DeviceCollection.load_snapshot(os.path.join(directory, f"{name}.lvs"), name=name, device=device)
+        if self.dev.rows != len(self.ids):
+            raise ValueError(f"snapshot of {name}: {self.dev.rows} device rows but {len(self.ids)} host rows")
+        return self
+
 
 class _ClientShim:
     """What ``manager.client`` exposes (reference callers reach through it: projects/cleanup.py:41-61,
@@ -428,6 +454,41 @@ class B200VectorStore:
                     logger.info(f"Created collection: {name}")
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError("Failed to create collections", cause=e)
+
+    # ---- snapshots (the Qdrant volume of docker-compose.yml:42-43) ------------------------------
+    async def save(self, directory: str) -> None:
+        """Additive: persist every collection (device arrays + ids / payloads / dictionaries) under ``directory``."""
+        try:
+            _ = self.client
+
+            def work():
+                for coll in self._collections.values():
+                    with coll.lock:
+                        coll.save(directory)
+            await asyncio.to_thread(work)
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to save collections to {directory}", cause=e)
+
+    async def load(self, directory: str) -> None:
+        """Additive: replace the collections by the ones saved under ``directory``; searches continue exactly where the
+        saved store left off (same scores: the local-mode replay state is part of the snapshot)."""
+        try:
+            _ = self.client
+
+            def work():
+                loaded = {}
+                for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
+                    if os.path.exists(os.path.join(directory, f"{name}.lvs")):
+                        loaded[name] = _HostCollection.load(directory, name, self._device)
+                return loaded
+            loaded = await asyncio.to_thread(work)
+            for name, coll in loaded.items():
+                old = self._collections.pop(name, None)
+                if old is not None:
+                    old.close()
+                self._collections[name] = coll
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to load collections from {directory}", cause=e)
 
     async def get_collection_info(self, collection: str):
         try:

@@ -62,6 +62,32 @@ class DeviceCollection:
                 "lvs_collection_create")
         self._h = h
 
+    # ---- snapshots (include/lvs.h: lvs_snapshot_save / lvs_snapshot_load) -----------------------------------
+    def save_snapshot(self, path: str) -> None:
+        N.check(self._lib.lvs_snapshot_save(self._handle(), str(path).encode()), "lvs_snapshot_save")
+
+    @classmethod
+    def load_snapshot(cls, path: str, name: str | None = None, capacity: int = 0, device: int = 0) -> "DeviceCollection":
+        """A shard restored from ``save_snapshot``: same rows, tombstones, codes, search counter and replay state."""
+        import struct
+        with open(path, "rb") as f:
+            head = f.read(24 + 16)
+        if head[:8] != b"LVSSNAP1":
+            raise ValueError(f"{path} is not a lattice-b200 snapshot")
+        dim, storage, metric, n_cols = struct.unpack_from("<4i", head, 8)
+        _, row_base = struct.unpack_from("<2q", head, 24)
+        N.init(device)
+        self = cls.__new__(cls)
+        self._lib = N.load()
+        self.name = name or "restored"
+        self.dim, self.storage = int(dim), ("bf16" if storage == N.STORAGE_BF16 else "f32")
+        self.metric = "dot" if metric == N.METRIC_DOT else "cosine"
+        self.n_filter_cols, self.row_base = int(n_cols), int(row_base)
+        h = C.c_void_p()
+        N.check(self._lib.lvs_snapshot_load(str(path).encode(), self.name.encode(), int(capacity), C.byref(h)), "lvs_snapshot_load")
+        self._h = h
+        return self
+
     # ---- lifecycle ------------------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):

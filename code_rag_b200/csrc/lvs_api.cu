@@ -1676,6 +1676,146 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
 }
 
 // ------------------------------------------------------------------------------------------------------
+// snapshots: a shard survives a restart the way the Qdrant volume does
+// (reference docker-compose.yml:42-43).  One file per shard: header, then the raw device arrays in row order.
+// ------------------------------------------------------------------------------------------------------
+struct SnapshotHeader {
+    char magic[8];                // "LVSSNAP1"
+    int32_t dim, storage, metric, n_cols;
+    int64_t n_rows, row_base;
+    uint32_t search_counter, row_bytes;
+    float norm_stats[2];
+    int64_t rk_rows;              // rows covered by the ranking attribute columns (0 = none)
+    int64_t n_names, name_bytes;
+    int64_t reserved[4];
+};
+
+static int snap_write(FILE* f, const void* dptr, size_t bytes, Scratch& pin, cudaStream_t st) {
+    const size_t chunk = (size_t)32 << 20;
+    int rc;
+    if ((rc = ensure_pinned(pin, std::min(std::max(bytes, (size_t)4096), chunk))) != LVS_OK) return rc;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t n = std::min(chunk, bytes - o);
+        CU(cudaMemcpyAsync(pin.p, (const uint8_t*)dptr + o, n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (fwrite(pin.p, 1, n, f) != n) return fail(LVS_EINVAL, "short write to the snapshot file");
+    }
+    return LVS_OK;
+}
+static int snap_read(FILE* f, void* dptr, size_t bytes, Scratch& pin, cudaStream_t st) {
+    const size_t chunk = (size_t)32 << 20;
+    int rc;
+    if ((rc = ensure_pinned(pin, std::min(std::max(bytes, (size_t)4096), chunk))) != LVS_OK) return rc;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t n = std::min(chunk, bytes - o);
+        if (fread(pin.p, 1, n, f) != n) return fail(LVS_EINVAL, "snapshot file is truncated");
+        CU(cudaMemcpyAsync((uint8_t*)dptr + o, pin.p, n, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return LVS_OK;
+}
+
+extern "C" int lvs_snapshot_save(lvs_collection* c, const char* path) {
+    if (!c || !path) return fail(LVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto& sl : c->slots) if (sl.in_use) return fail(LVS_ESTATE, "searches are in flight: call lvs_search_wait first");
+    cudaStream_t st = c->stream;
+    CU(cudaStreamSynchronize(st));
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(LVS_EINVAL, "cannot open %s for writing", path);
+    SnapshotHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "LVSSNAP1", 8);
+    h.dim = c->dim; h.storage = c->storage; h.metric = c->metric; h.n_cols = c->n_cols;
+    h.n_rows = c->n_rows; h.row_base = c->row_base; h.search_counter = c->search_counter; h.row_bytes = c->row_bytes;
+    h.norm_stats[0] = c->h_norm_stats[0]; h.norm_stats[1] = c->h_norm_stats[1];
+    h.rk_rows = c->d_rk_key ? std::min(c->rk_cap, c->n_rows) : 0;
+    h.n_names = c->n_names; h.name_bytes = c->name_bytes_used;
+    int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? LVS_OK : fail(LVS_EINVAL, "short write to the snapshot file");
+    const size_t n = (size_t)c->n_rows;
+    Scratch& pin = c->h_pin2;
+    if (rc == LVS_OK && n) rc = snap_write(f, c->d_vec, n * c->row_bytes, pin, st);
+    if (rc == LVS_OK && n) rc = snap_write(f, c->d_live, n, pin, st);
+    if (rc == LVS_OK && n) rc = snap_write(f, c->d_epoch, n * 4, pin, st);
+    if (rc == LVS_OK && n) rc = snap_write(f, c->d_tie, n * 8, pin, st);
+    if (rc == LVS_OK && n) rc = snap_write(f, c->d_inv_norm, n * 4, pin, st);
+    for (int i = 0; i < c->n_cols && rc == LVS_OK && n; ++i) rc = snap_write(f, c->d_codes[i], n * 4, pin, st);
+    if (rc == LVS_OK && h.rk_rows) {
+        const size_t r = (size_t)h.rk_rows;
+        rc = snap_write(f, c->d_rk_key, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_write(f, c->d_rk_file, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_write(f, c->d_rk_cent, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_write(f, c->d_rk_name, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_write(f, c->d_rk_clen, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_write(f, c->d_rk_flags, r, pin, st);
+    }
+    if (rc == LVS_OK && h.n_names) {
+        rc = snap_write(f, c->d_name_off, ((size_t)h.n_names + 1) * 4, pin, st);
+        if (rc == LVS_OK && h.name_bytes) rc = snap_write(f, c->d_name_bytes, (size_t)h.name_bytes, pin, st);
+    }
+    if (fclose(f) != 0 && rc == LVS_OK) rc = fail(LVS_EINVAL, "closing %s failed", path);
+    return rc;
+}
+
+extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t capacity_rows, lvs_collection** out) {
+    if (!path || !out) return fail(LVS_EINVAL, "NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(LVS_EINVAL, "cannot open %s", path);
+    SnapshotHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LVSSNAP1", 8) != 0) { fclose(f); return fail(LVS_EINVAL, "%s is not a lattice-b200 snapshot", path); }
+    lvs_collection* c = nullptr;
+    int rc = lvs_collection_create(name, h.dim, h.storage, h.metric, h.n_cols, std::max(capacity_rows, h.n_rows), h.row_base, &c);
+    if (rc != LVS_OK) { fclose(f); return rc; }
+    if (c->row_bytes != h.row_bytes) { fclose(f); lvs_collection_destroy(c); return fail(LVS_EINVAL, "snapshot row layout differs (%u vs %u bytes)", h.row_bytes, c->row_bytes); }
+    cudaStream_t st = c->stream;
+    const size_t n = (size_t)h.n_rows;
+    Scratch& pin = c->h_pin2;
+    if (n) rc = snap_read(f, c->d_vec, n * c->row_bytes, pin, st);
+    if (rc == LVS_OK && n) rc = snap_read(f, c->d_live, n, pin, st);
+    if (rc == LVS_OK && n) rc = snap_read(f, c->d_epoch, n * 4, pin, st);
+    if (rc == LVS_OK && n) rc = snap_read(f, c->d_tie, n * 8, pin, st);
+    if (rc == LVS_OK && n) rc = snap_read(f, c->d_inv_norm, n * 4, pin, st);
+    for (int i = 0; i < c->n_cols && rc == LVS_OK && n; ++i) rc = snap_read(f, c->d_codes[i], n * 4, pin, st);
+    if (rc == LVS_OK) {
+        c->n_rows = h.n_rows; c->search_counter = h.search_counter;
+        c->h_norm_stats[0] = h.norm_stats[0]; c->h_norm_stats[1] = h.norm_stats[1];
+        cudaError_t e = cudaMemcpy(c->d_max_norm, c->h_norm_stats, 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(LVS_ECUDA, "snapshot load: %s", cudaGetErrorString(e));
+    }
+    if (rc == LVS_OK && h.rk_rows) {
+        const int64_t cap = std::max<int64_t>(h.rk_rows, c->capacity);
+        const size_t r = (size_t)h.rk_rows;
+        rc = regrow(c->d_rk_key, 0, cap, st, 0xFF);
+        if (rc == LVS_OK) rc = regrow(c->d_rk_file, 0, cap, st, 0xFF);
+        if (rc == LVS_OK) rc = regrow(c->d_rk_cent, 0, cap, st, 0xFF);
+        if (rc == LVS_OK) rc = regrow(c->d_rk_name, 0, cap, st, 0xFF);
+        if (rc == LVS_OK) rc = regrow(c->d_rk_clen, 0, cap, st, 0xFF);
+        if (rc == LVS_OK) rc = regrow(c->d_rk_flags, 0, cap, st, 0);
+        if (rc == LVS_OK) c->rk_cap = cap;
+        if (rc == LVS_OK) rc = snap_read(f, c->d_rk_key, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_read(f, c->d_rk_file, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_read(f, c->d_rk_cent, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_read(f, c->d_rk_name, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_read(f, c->d_rk_clen, r * 4, pin, st);
+        if (rc == LVS_OK) rc = snap_read(f, c->d_rk_flags, r, pin, st);
+    }
+    if (rc == LVS_OK && h.n_names) {
+        rc = regrow(c->d_name_off, 0, h.n_names + 1, st, 0);
+        if (rc == LVS_OK) { c->names_cap = h.n_names + 1; rc = snap_read(f, c->d_name_off, ((size_t)h.n_names + 1) * 4, pin, st); }
+        if (rc == LVS_OK && h.name_bytes) {
+            rc = regrow(c->d_name_bytes, 0, h.name_bytes, st);
+            if (rc == LVS_OK) { c->name_bytes_cap = h.name_bytes; rc = snap_read(f, c->d_name_bytes, (size_t)h.name_bytes, pin, st); }
+        }
+        if (rc == LVS_OK) { c->n_names = h.n_names; c->name_bytes_used = h.name_bytes; }
+    }
+    fclose(f);
+    if (rc != LVS_OK) { lvs_collection_destroy(c); return rc; }
+    *out = c;
+    return LVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // instrumentation
 // ------------------------------------------------------------------------------------------------------
 extern "C" int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches, int* kernel_kind) {

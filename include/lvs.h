@@ -189,6 +189,13 @@ int lvs_search_rank(lvs_collection* c, const void* queries, int dtype, int Q, in
                     uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
                     double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms);
 
+/* ---- snapshots: the shard's device arrays (vectors, tombstones, codes, tie keys, write epochs,
+ *      norms, search counter, ranking attributes and name pool) to / from one file, so that an index survives a restart the
+ *      way the Qdrant volume does (reference docker-compose.yml:42-43).  A loaded shard answers every search exactly as the
+ *      saved one would have (the replay state is part of the snapshot).  Ids, payloads and dictionaries are the host's. */
+int lvs_snapshot_save(lvs_collection* c, const char* path);
+int lvs_snapshot_load(const char* path, const char* name, int64_t capacity_rows, lvs_collection** out);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the collection's stream) of the kernels of the last lvs_search* call on this handle:
  * [0] query prep  [1] scan / tensor-core kernel(s)  [2] finalize  [3] whole device section; n_launches = kernels launched. */
