@@ -15,9 +15,11 @@ from configs import fill  # noqa: E402
 from code_rag_b200.collection import DeviceCollection  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-dev = DeviceCollection("k2", 768, storage="bf16", capacity=n)
-fill(dev, n, 768, "bf16", seed=3456)
 import os
+STORAGE = os.environ.get("K2_STORAGE", "bf16")           # "f32": the kind::tf32 form over an fp32 shard
+DIM = int(os.environ.get("K2_DIM", "768"))
+dev = DeviceCollection("k2", DIM, storage=STORAGE, capacity=n)
+fill(dev, n, DIM, STORAGE, seed=3456)
 for opt in ("gemm_no_unit", "gemm_stages", "gemm_dbg", "gemm_keep", "gemm_no_pair"):
     if os.environ.get(opt.upper()):
         dev.set_option(opt, int(os.environ[opt.upper()]))
@@ -26,10 +28,10 @@ cfgs = [(256, 100), (256, 10), (128, 10), (64, 100), (64, 10), (16, 10)]
 if len(sys.argv) > 3:
     cfgs = [(int(sys.argv[2]), int(sys.argv[3]))]
 for Q, k in cfgs:
-    qs = rng.standard_normal((Q, 768))
+    qs = rng.standard_normal((Q, DIM))
     for rep in range(3):
         res = dev.search(qs, k)
     t = dev.last_timing()
     print(json.dumps({"Q": Q, "k": k, **t, "flagged": int(res.flags.sum()),
-                      "gemm_gbs": n * 1536 / (t["scan_ms"] * 1e-3) / 1e9, "gemm_tflops": 2.0 * Q * n * 768 / (t["scan_ms"] * 1e-3) / 1e12}), flush=True)
+                      "gemm_gbs": n * DIM * (2 if STORAGE == "bf16" else 4) / (t["scan_ms"] * 1e-3) / 1e9, "gemm_tflops": 2.0 * Q * n * DIM / (t["scan_ms"] * 1e-3) / 1e12, "storage": STORAGE}), flush=True)
 dev.close()

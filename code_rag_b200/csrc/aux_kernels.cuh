@@ -161,6 +161,36 @@ __global__ void __launch_bounds__(256) prep_qb16_kernel(const double* q64, int Q
     }
 }
 
+// fp32 shards (K2 with kind::tf32): the unit queries rounded to tf32 (round to nearest, low 13 mantissa bits cleared) so that the
+// tensor core's own truncation leaves the query side exact; eps_out = ||q - tf32(q)||_2 + slack
+__global__ void __launch_bounds__(256) prep_qtf32_kernel(const double* q64, int Q, int dim, float* out, uint32_t k_pad, uint32_t rows_out,
+                                                         float* eps_out) {
+    __shared__ double red[8];
+    const uint32_t r = blockIdx.x;
+    if (r >= rows_out) return;
+    double e2 = 0.0;
+    for (uint32_t c = threadIdx.x; c < k_pad; c += 256) {
+        double v = 0.0;
+        if ((int)r < Q && (int)c < dim) v = q64[(size_t)r * dim + c];
+        uint32_t t;
+        const float f = (float)v;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(f));
+        t &= 0xFFFFE000u;
+        const float b = __uint_as_float(t);
+        out[(size_t)r * k_pad + c] = b;
+        const double d = v - (double)b;
+        e2 = fma(d, d, e2);
+    }
+    e2 = warp_sum_f64(e2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e2;
+    __syncthreads();
+    if (threadIdx.x == 0 && (int)r < Q) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        eps_out[r] = (float)(sqrt(t) * 1.0001 + 1.0e-4);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Filter-only matching (query_vector=None searches, delete-by-filter, count, scroll):
 // appends every live row whose codes satisfy the conjunction to out_rows (unordered), counts all matches.

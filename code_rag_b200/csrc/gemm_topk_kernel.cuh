@@ -4,7 +4,10 @@
 // Replaces, for Q >= 8 queries at a time, the O(Q*N*D) loop that the reference delegates to Qdrant behind
 // QdrantManager.search (reference src/lattice/embeddings/client.py:132-157) - there one gRPC call per query.
 //
-// Orientation: D[queries x 256 corpus rows] += A[queries x K] * B[256 x K]^T, bf16 inputs, fp32 accumulate.
+// Orientation: D[queries x 256 corpus rows] += A[queries x K] * B[256 x K]^T, fp32 accumulate.  bf16 shards use kind::f16
+// (64 K-elements per 128-byte swizzle row, K = 16 per MMA); fp32 shards are read AS THEY ARE with kind::tf32 (template parameter
+// TF32: 32 K-elements per swizzle row, K = 8 per MMA - the same bytes per stage and per instruction; the tensor core uses the
+// upper 19 bits of every fp32 value, which the finalize kernel's bound accounts for with 2^-10 ||q|| ||x||).
 // Two forms of the same kernel (template parameter PAIR):
 //   * PAIR = false (Q <= 128 per CTA): tcgen05.mma.cta_group::1, M = 128, N = 256, K = 16 - the full-rate shape of a
 //     single-CTA MMA (128 cycles).  A pipeline stage = one 64-wide K chunk of BOTH operands, K-major with 128-byte
@@ -20,8 +23,8 @@
 //   Both arrive by cp.async.bulk.tensor.2d (TMA, SASS UTMALDG).
 //   * D is double buffered: 2 x 256 TMEM columns, so the MMAs of tile t+1 overlap the epilogue of tile t.
 //   * Epilogue (8 warps; thread = query = TMEM lane; the two warps of a lane quarter split the 256 columns):
-//     tcgen05.ld 32 columns, (scale by 1/||row|| unless the shard is unit-norm and the tile clean; NaN for tombstones
-//     and rows past the end, and NaN never passes), then a NaN-ignoring MAX TREE over the 32 scores and ONE vote:
+//     tcgen05.ld 32 columns, (scale by 1/||row|| unless the shard is unit-norm and the tile clean; NaN for tombstones,
+//     rows that fail the payload filter and rows past the end, and NaN never passes), then a NaN-ignoring MAX TREE over the 32 scores and ONE vote:
 //     if no query of the warp has a score above its current threshold (the common case once the lists have warmed
 //     up) the block costs ~40 instructions.  Otherwise every lane builds the bit mask of its passing columns, the
 //     passing lanes park their 32 scores in a shared-memory column (so that they can be indexed) and ALL LANES INSERT
@@ -45,12 +48,12 @@ constexpr int kGemmEpiWarps = 8;       // two per TMEM lane quarter: each takes 
 constexpr int kGemmThreads = (2 + kGemmEpiWarps) * 32;
 constexpr int kGemmM = 128;            // queries per CTA (TMEM lanes)
 constexpr int kGemmN = 256;            // corpus rows per tile (accumulator columns per buffer)
-constexpr int kGemmKC = 64;            // K elements per pipeline stage (= one 128-byte swizzle row)
+constexpr int kGemmKC = 64;            // K elements per pipeline stage (= one 128-byte swizzle row) for bf16; 32 for fp32 / tf32
 constexpr int kGemmABytes = kGemmM * kGemmKC * 2;       // 16 KB
 constexpr int kGemmBBytes = kGemmN * kGemmKC * 2;       // 32 KB (PAIR: each CTA holds half, 16 KB)
 constexpr int kGemmMaxStages = 4;
 constexpr int kGemmList = 16;          // keys kept per (CTA, column half, query)
-constexpr int kGemmMaxKChunks = 64;    // dim <= 4096
+constexpr int kGemmMaxKChunks = 128;   // dim <= 8192 (bf16) / 4096 (fp32)
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA of a pair
 
 __host__ __device__ constexpr int gemm_stage_bytes(bool pair) { return kGemmABytes + (pair ? kGemmBBytes / 2 : kGemmBBytes); }
@@ -64,6 +67,9 @@ struct GemmParams {
     uint32_t n_stages;
     const float* inv_norm;       // [rows] 1/||row||, or nullptr (dot metric)
     const uint8_t* live;
+    const uint32_t* fcodes[kMaxFilterCols];   // payload filter: dictionary-code columns that must equal fwant[] (conjunction)
+    uint32_t fwant[kMaxFilterCols];
+    uint32_t n_filter;
     uint64_t* out_keys;          // [n_groups * 128][2P][16]   (two lists per CTA and query: one per column half), sorted descending
     uint64_t* out_tops;          // [n_groups * 128][2P]  best key of the list
     uint64_t* out_drops;         // [n_groups * 128][2P]  key-shaped bound on every score this list dropped (its final threshold), 0 = nothing dropped
@@ -100,21 +106,21 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
     }
 }
-// D[tmem_d] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, K = 16
-template <bool PAIR>
+// D[tmem_d] (+)= A[smem desc] * B[smem desc]^T: bf16 x bf16 -> fp32 with K = 16, or tf32 x tf32 -> fp32 with K = 8 (32 bytes either way)
+template <bool PAIR, bool TF32>
 __device__ __forceinline__ void tc_mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (PAIR) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (PAIR && TF32) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (PAIR) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (TF32) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
     } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -148,7 +154,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <bool PAIR>
+template <bool PAIR, bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_b,
                                                                     const __grid_constant__ CUtensorMap tmap_a, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t gsm_raw[];
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
     constexpr int kStageBytes = gemm_stage_bytes(PAIR);
     constexpr int kBRows = PAIR ? kGemmN / 2 : kGemmN;       // corpus rows this CTA loads per tile
+    constexpr int kKcElems = TF32 ? kGemmKC / 2 : kGemmKC;  // K elements per stage (128 bytes of a row)
     const uint32_t S = p.n_stages;
     uint8_t* stages = gsm;                                                   // S x (A 16 KB | B), 1024-byte aligned
     uint64_t* lists = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kStageBytes);         // [8 warps][16 keys][32 lanes], unsorted
@@ -210,12 +217,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                     if constexpr (PAIR) {
                         // the leader's barrier counts the bytes of both CTAs
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * kStageBytes);
-                        tma_load_2d_pair(st, &tmap_a, (int)(kc * kGemmKC), (int)(group * kGemmM), &full_bar[s]);
-                        tma_load_2d_pair(st + kGemmABytes, &tmap_b, (int)(kc * kGemmKC), (int)(tile * kGemmN + rank * kBRows), &full_bar[s]);
+                        tma_load_2d_pair(st, &tmap_a, (int)(kc * kKcElems), (int)(group * kGemmM), &full_bar[s]);
+                        tma_load_2d_pair(st + kGemmABytes, &tmap_b, (int)(kc * kKcElems), (int)(tile * kGemmN + rank * kBRows), &full_bar[s]);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                        tma_load_2d(st, &tmap_a, (int)(kc * kGemmKC), (int)(group * kGemmM), &full_bar[s]);
-                        tma_load_2d(st + kGemmABytes, &tmap_b, (int)(kc * kGemmKC), (int)(tile * kGemmN), &full_bar[s]);
+                        tma_load_2d(st, &tmap_a, (int)(kc * kKcElems), (int)(group * kGemmM), &full_bar[s]);
+                        tma_load_2d(st + kGemmABytes, &tmap_b, (int)(kc * kKcElems), (int)(tile * kGemmN), &full_bar[s]);
                     }
                 }
             }
@@ -224,7 +231,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
         // ================================ MMA issuer (PAIR: the leader CTA only) ================================
         if (lane == 0 && rank == 0) {
             // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N = 256, M = 128 (PAIR: 256 over both CTAs)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
+            // (formats: D = F32 (1 at bit 4); A, B = BF16 (1) or TF32 (2) at bits 7 and 10)
+            constexpr uint32_t kFmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
                                    ((uint32_t)((PAIR ? 2 * kGemmM : kGemmM) >> 4) << 24);
             uint32_t it = 0;
             for (uint32_t lt = 0; lt < my_tiles; ++lt) {
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                     if (!(p.dbg_mode & 2u)) {
 #pragma unroll
                         for (uint32_t k = 0; k < kGemmKC / 16; ++k)
-                            tc_mma_ss<PAIR>(tmem_d, make_kmajor_desc(a_addr + k * 32u), make_kmajor_desc(b_addr + k * 32u), idesc,
+                            tc_mma_ss<PAIR, TF32>(tmem_d, make_kmajor_desc(a_addr + k * 32u), make_kmajor_desc(b_addr + k * 32u), idesc,
                                             (kc | k) != 0u ? 1u : 0u);
                     }
                     tc_commit<PAIR>(&empty_bar[s]);                  // frees the stage (in both CTAs) when these MMAs have read it
@@ -289,7 +298,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                 if (lt < my_tiles) {
                     uint32_t r = (pair + lt * p.n_pairs) * kGemmN + half * (kGemmN / 2) + j * 32 + lane;
                     r = r < p.n_rows ? r : p.n_rows - 1;
-                    lv[j] = p.live[r];
+                    uint32_t ok = p.live[r];
+                    // payload filter (reference client.py:171-176): rows that fail it are treated like tombstones
+                    for (uint32_t c = 0; c < p.n_filter; ++c) ok = (p.fcodes[c][r] == p.fwant[c]) ? ok : 0u;
+                    lv[j] = ok;
                     if (p.inv_norm) f[j] = p.inv_norm[r];
                 }
             }

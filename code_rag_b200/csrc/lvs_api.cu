@@ -152,6 +152,7 @@ struct lvs_collection {
     int opt_gemm_no_unit = 0;
     int opt_gemm_keep = 16;
     int opt_gemm_no_pair = 0;
+    int opt_gemm_no_tf32 = 0;
 
     // per-row ranking attributes + lower-cased entity-name pool (fused search -> rank path, lvs_search_rank)
     int64_t rk_cap = 0;              // rows covered by the attribute columns
@@ -771,9 +772,11 @@ static int get_encode_tiled() {
 }
 
 static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
+    (void)filter;                 // K2 evaluates the payload filter next to the tombstone check
     if (c->opt_path == 1) return false;
-    if (c->storage != LVS_STORAGE_BF16 || filter) return false;
-    const uint32_t nk = (c->q_stride + kGemmKC - 1) / kGemmKC;
+    if (c->storage != LVS_STORAGE_BF16 && c->opt_gemm_no_tf32) return false;   // fp32 shards: kind::tf32
+    const uint32_t kce = c->storage == LVS_STORAGE_BF16 ? kGemmKC : kGemmKC / 2;
+    const uint32_t nk = (c->q_stride + kce - 1) / kce;
     if (nk > (uint32_t)kGemmMaxKChunks || c->dim < 64) return false;
     if (c->n_rows < (int64_t)kGemmN * 64) return false;             // too few tiles to fill the machine / the lists
     return c->opt_path == 2 || Q >= c->opt_gemm_min_q;
@@ -781,17 +784,21 @@ static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
 
 // Enqueue K2 + finalize for queries [0, Q) in batches of up to 256.  No synchronisation.
 static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t search_base, double* d_scores, int64_t* d_rows,
-                        uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches) {
+                        uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches,
+                        const uint32_t* const* fcodes = nullptr, const uint32_t* fwant = nullptr, uint32_t nf = 0) {
     int rc;
     if ((rc = get_encode_tiled()) != LVS_OK) return rc;
     const int sm = g_lib.sm_count;
-    const uint32_t nk = (c->q_stride + kGemmKC - 1) / kGemmKC;
-    const uint32_t k_pad = nk * kGemmKC;
+    const bool tf32 = c->storage == LVS_STORAGE_F32;                 // fp32 shards are multiplied as tf32, straight from their rows
+    const uint32_t kce = tf32 ? kGemmKC / 2 : kGemmKC;               // K elements per 128-byte swizzle row
+    const uint32_t esz = tf32 ? 4 : 2;
+    const uint32_t nk = (c->q_stride + kce - 1) / kce;
+    const uint32_t k_pad = nk * kce;
     const size_t keys_bytes = (size_t)256 * sm * 2 * kGemmList * 8;
     if ((rc = ensure_dev(c->s_gkeys, keys_bytes)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_gtops, (size_t)256 * sm * 2 * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_gdrops, (size_t)256 * sm * 2 * 8)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_qb16, (size_t)256 * k_pad * 2)) != LVS_OK) return rc;
+    if ((rc = ensure_dev(c->s_qb16, (size_t)256 * k_pad * esz)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_geps, (size_t)256 * 4)) != LVS_OK) return rc;
     kpl = std::min(8, 2 * kpl);      // the bf16-query scores are coarser than K1's: rescore a larger candidate set
     if ((rc = ensure_dev(c->s_cand, (size_t)256 * kMaxCand * 8)) != LVS_OK) return rc;
@@ -807,29 +814,32 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
     {
         cuuint64_t gdim[2] = {(cuuint64_t)c->q_stride, (cuuint64_t)c->n_rows};
         cuuint64_t gstr[1] = {(cuuint64_t)c->row_bytes};
-        cuuint32_t box[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)kGemmN};
+        cuuint32_t box[2] = {(cuuint32_t)kce, (cuuint32_t)kGemmN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode_tiled(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_vec, gdim, gstr, box, estr,
+        const CUtensorMapDataType tdt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        CUresult r = g_encode_tiled(&tmap_b, tdt, 2, c->d_vec, gdim, gstr, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (corpus) failed with CUresult %d", (int)r);
-        cuuint32_t hbox[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)(kGemmN / 2)};
-        r = g_encode_tiled(&tmap_b_half, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_vec, gdim, gstr, hbox, estr,
+        cuuint32_t hbox[2] = {(cuuint32_t)kce, (cuuint32_t)(kGemmN / 2)};
+        r = g_encode_tiled(&tmap_b_half, tdt, 2, c->d_vec, gdim, gstr, hbox, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (corpus, half tile) failed with CUresult %d", (int)r);
         cuuint64_t qdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)256};
-        cuuint64_t qstr[1] = {(cuuint64_t)k_pad * 2};
-        cuuint32_t qbox[2] = {(cuuint32_t)kGemmKC, (cuuint32_t)kGemmM};
-        r = g_encode_tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->s_qb16.p, qdim, qstr, qbox, estr,
+        cuuint64_t qstr[1] = {(cuuint64_t)k_pad * esz};
+        cuuint32_t qbox[2] = {(cuuint32_t)kce, (cuuint32_t)kGemmM};
+        r = g_encode_tiled(&tmap_a, tdt, 2, c->s_qb16.p, qdim, qstr, qbox, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", (int)r);
     }
     static bool attr = false;
     if (!attr) {
-        CU(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
-        CU(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+        CU(cudaFuncSetAttribute(gemm_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+        CU(cudaFuncSetAttribute(gemm_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+        CU(cudaFuncSetAttribute(gemm_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
+        CU(cudaFuncSetAttribute(gemm_topk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
         attr = true;
     }
     const uint32_t n_tiles = (uint32_t)((c->n_rows + kGemmN - 1) / kGemmN);
@@ -843,8 +853,12 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         if (c->opt_gemm_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_gemm_stages);
         while (S > 2 && gemm_smem_bytes(S, pair_form) > g_lib.smem_optin) --S;
         const size_t smem = gemm_smem_bytes(S, pair_form);
-        prep_qb16_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
-                                                   (__nv_bfloat16*)c->s_qb16.p, k_pad, G * kGemmM, (float*)c->s_geps.p);
+        if (tf32)
+            prep_qtf32_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
+                                                        (float*)c->s_qb16.p, k_pad, G * kGemmM, (float*)c->s_geps.p);
+        else
+            prep_qb16_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
+                                                       (__nv_bfloat16*)c->s_qb16.p, k_pad, G * kGemmM, (float*)c->s_geps.p);
         CU(cudaGetLastError());
         ++*launches;
         GemmParams gp;
@@ -852,6 +866,8 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         gp.n_kchunks = nk; gp.n_rows = (uint32_t)c->n_rows;
         gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S;
         gp.inv_norm = c->metric == LVS_METRIC_COSINE ? c->d_inv_norm : nullptr; gp.live = c->d_live;
+        gp.n_filter = nf;
+        for (uint32_t i = 0; i < nf; ++i) { gp.fcodes[i] = fcodes[i]; gp.fwant[i] = fwant[i]; }
 
         gp.out_keys = (uint64_t*)c->s_gkeys.p; gp.out_tops = (uint64_t*)c->s_gtops.p; gp.out_drops = (uint64_t*)c->s_gdrops.p;
         const bool unit_rows = c->metric == LVS_METRIC_COSINE && c->h_norm_stats[1] <= 0.001953125f && !c->opt_gemm_no_unit;
@@ -876,9 +892,11 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
             la[0].id = cudaLaunchAttributeClusterDimension;
             la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
             cfg.attrs = la; cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true>, tmap_b_half, tmap_a, gp);
+            e = tf32 ? cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, true>, tmap_b_half, tmap_a, gp)
+                     : cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, false>, tmap_b_half, tmap_a, gp);
         } else {
-            gemm_topk_kernel<false><<<P * G, kGemmThreads, smem, st>>>(tmap_b, tmap_a, gp);
+            if (tf32) gemm_topk_kernel<false, true><<<P * G, kGemmThreads, smem, st>>>(tmap_b, tmap_a, gp);
+            else gemm_topk_kernel<false, false><<<P * G, kGemmThreads, smem, st>>>(tmap_b, tmap_a, gp);
             e = cudaGetLastError();
         }
         if (e != cudaSuccess) return fail(LVS_ECUDA, "gemm kernel launch failed: %s (smem=%zu grid=%u)", cudaGetErrorString(e), smem, P * G);
@@ -899,6 +917,8 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         fp.eps = 2.2e-3f;    // fallback; the per-query bound ||q - bf16(q)||_2 + accumulation slack is used
         fp.eps_q = c->metric == LVS_METRIC_COSINE ? (const float*)c->s_geps.p : nullptr;
         fp.eps_add = unit_rows ? c->h_norm_stats[1] * 1.01f : 0.f;
+        // tf32: the tensor core drops the low 13 mantissa bits of every stored value: |q.(x - tf32(x))| <= 2^-10 ||q|| ||x||
+        if (tf32) fp.eps_add += 0.0009775f + 1.0e-6f;
         int nrw = kFinWarps;
         while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
         fp.n_rescore_warps = nrw;
@@ -972,7 +992,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     if (!only && gemm_eligible(c, Q, filter)) {
         // K2 for the whole batch; queries whose exactness bound is not met fall through to the K1 levels below
         kind = 2;
-        rc = enqueue_gemm(c, Q, k, kpl, search_base, d_scores, d_rows, d_ties, d_counts, d_flags, st, &launches);
+        rc = enqueue_gemm(c, Q, k, kpl, search_base, d_scores, d_rows, d_ties, d_counts, d_flags, st, &launches, fcodes, fwant, nf);
         if (rc != LVS_OK) return rc;
         first = false;
         pending.clear();
@@ -1841,6 +1861,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "gemm_no_unit")) c->opt_gemm_no_unit = value;
     else if (!strcmp(name, "gemm_keep")) c->opt_gemm_keep = value;
     else if (!strcmp(name, "gemm_no_pair")) c->opt_gemm_no_pair = value;
+    else if (!strcmp(name, "gemm_no_tf32")) c->opt_gemm_no_tf32 = value;
     else return fail(LVS_EINVAL, "unknown option '%s'", name);
     return LVS_OK;
 }

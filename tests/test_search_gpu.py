@@ -36,6 +36,9 @@ def _assert_same(res, qi, rows_o, scores_o, rel, tight=TIGHT):
     assert np.array_equal(got, rows_o), (
         f"query {qi}: id lists differ\n device {got.tolist()}\n oracle {rows_o.tolist()}\n"
         f" device scores {res.scores[qi, :n].tolist()}\n oracle scores {scores_o.tolist()}")
+    if n == 0:
+        assert res.flags[qi] == 0
+        return
     err = np.abs(res.scores[qi, :n] - scores_o)
     assert np.all(err <= rel * np.maximum(np.abs(scores_o), 1e-30) + 1e-300), f"query {qi}: score error {err.max()}"
     assert err.max() <= tight, f"query {qi}: replay drift {err.max()} (> {tight})"
@@ -233,6 +236,50 @@ def test_gemm_path_parity(lib, Q, k):
     dev.close()
 
 
+@pytest.mark.parametrize("Q,k,dim", [(9, 10, 768), (130, 50, 1536), (64, 100, 100)])
+def test_gemm_path_tf32_on_f32_storage(lib, Q, k, dim):
+    """K2 over an fp32 shard (tcgen05 kind::tf32 reads the stored fp32 rows): same ids as the oracle, scores within 1e-5."""
+    n = 24_000
+    x, q = synth.unit_rows(n, dim, seed=4242 + Q, n_queries=Q)
+    ora = OracleCollection(dim)
+    ora.upsert_rows_f32(0, x, [None] * n)
+    dev = _dev("gemmtf32", dim, storage="f32")
+    dev.upsert(x.astype(np.float64))
+    dev.delete_rows(np.array([1, 300, 23_999]))
+    ora.deleted[[1, 300, 23_999]] = True
+    res = dev.search(q.astype(np.float64), k)
+    assert dev.last_timing()["kernel"] == "gemm"
+    for i in range(Q):
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_F32)
+    dev.close()
+
+
+@pytest.mark.parametrize("Q", [12, 140])
+def test_gemm_path_with_payload_filter(lib, Q):
+    """K2 with a payload filter (the mask rides with the tombstone check): wide, selective and empty filters, top-10."""
+    n, dim, k = 24_000, 768, 10
+    x, q = synth.unit_rows(n, dim, seed=777 + Q, n_queries=Q)
+    xb = synth.bf16_round(x)
+    rng = np.random.default_rng(5)
+    codes = np.stack([rng.choice([1, 2, 3], size=n, p=[0.5, 0.3, 0.2]), rng.integers(1, 401, size=n)], axis=1).astype(np.uint32)
+    ANY = 0xFFFFFFFF
+    for want_list in ([2, ANY], [1, 17], [ANY, 399], [3, 0xFFFFFFFE]):
+        want = np.array(want_list, dtype=np.uint32)
+        mask = np.ones(n, dtype=bool)
+        for c in range(2):
+            if want[c] != ANY:
+                mask &= codes[:, c] == want[c]
+        ora = OracleCollection(dim)
+        ora.upsert_rows_f32(0, xb, [None] * n)
+        dev = _dev("gemmflt", dim, storage="bf16", ncols=2)
+        dev.upsert(xb, codes=codes)
+        res = dev.search(q.astype(np.float64), k, want)
+        assert dev.last_timing()["kernel"] == "gemm"
+        for i in range(Q):
+            _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k, mask), REL_BF16)
+        dev.close()
+
+
 @pytest.mark.parametrize("dim", [100, 1000, 1536])
 def test_gemm_path_other_dimensions(lib, dim):
     """K2 with K not a multiple of the 64-element chunk (TMA zero-fills the tail) and with K > 768."""
@@ -280,6 +327,7 @@ def test_f32_storage_large_batch_uses_scan_passes(lib):
     ora = OracleCollection(384)
     ora.upsert_rows_f32(0, x, [None] * len(x))
     dev = _dev("f32batch", 384)
+    dev.set_option("gemm_no_tf32", 1)          # keep the batch on K1 (ceil(Q/4) scan passes)
     dev.upsert(x.astype(np.float64))
     res = dev.search(q.astype(np.float64), 10)
     assert dev.last_timing()["kernel"] == "scan"
