@@ -144,8 +144,9 @@ struct lvs_collection {
     int opt_stages = 0;   // 0 = as many as fit
     int opt_grid = 0;     // 0 = one CTA per SM
     int opt_force_kpl = 0;
-    int opt_gemm_min_q = 5;   // batches of at least this many queries take the tensor-core path (K2): one K2 pass (any Q <= 128)
-                              // costs about one K1 pass, and K1 needs two passes from 5 queries on
+    int opt_gemm_min_q = 3;   // batches of at least this many queries take the tensor-core path (K2).  One K2 pass (any Q <= 128) costs
+                              // about one single-query K1 pass (2.2 ms on 10M x 768 bf16); K1 with 3-4 bf16 queries per pass is
+                              // FMA-issue-bound (3.2-3.4 ms) and needs two passes from 5 queries on.  fp32 shards: from 5 queries.
     int opt_path = 0;         // 0 auto, 1 force K1 scan, 2 force K2 (when eligible)
     int opt_gemm_dbg = 0;
     int opt_gemm_stages = 0;
@@ -779,7 +780,8 @@ static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
     const uint32_t nk = (c->q_stride + kce - 1) / kce;
     if (nk > (uint32_t)kGemmMaxKChunks || c->dim < 64) return false;
     if (c->n_rows < (int64_t)kGemmN * 64) return false;             // too few tiles to fill the machine / the lists
-    return c->opt_path == 2 || Q >= c->opt_gemm_min_q;
+    const int min_q = c->storage == LVS_STORAGE_BF16 ? c->opt_gemm_min_q : std::max(c->opt_gemm_min_q, 5);
+    return c->opt_path == 2 || Q >= min_q;
 }
 
 // Enqueue K2 + finalize for queries [0, Q) in batches of up to 256.  No synchronisation.

@@ -204,7 +204,7 @@ int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches,
  * launching stream, with the algorithmic bytes of each launch.  The stream must have been synchronised. */
 int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n);
 /* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record events, default),
- * "gemm_min_q" (batch size from which the tensor-core path is used, default 8), "path" (0 auto, 1 scan only, 2 tensor-core
+ * "gemm_min_q" (batch size from which the tensor-core path is used, default 3; fp32 shards at least 5), "path" (0 auto, 1 scan only, 2 tensor-core
  * whenever eligible), "gemm_stages".  Returns LVS_EINVAL for unknown names. */
 int lvs_set_option(lvs_collection* c, const char* name, int value);
 /* Copy rows back (debug / snapshots): out is n x dim float32 of the values a fresh reference collection would hold. */
