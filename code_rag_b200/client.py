@@ -92,6 +92,9 @@ class _HostCollection:
         self.ids: list[Any] = []                 # row -> id
         self.id_to_row: dict[Any, int] = {}
         self.payloads: list[dict[str, Any] | None] = []
+        # rows of deleted points, reused by later upserts: VectorIndexer.index_file (embeddings/indexer.py:61-77) deletes a
+        # file's chunks and inserts new ones under fresh uuid4 ids on every re-index, so without reuse a shard only grows
+        self.free_rows: list[int] = []
         self.lock = threading.Lock()
         # dev_factory exists so that the host-side bookkeeping can be unit-tested without a GPU (tests only)
         factory = dev_factory or DeviceCollection
@@ -175,18 +178,26 @@ class _HostCollection:
         rows = np.empty(len(keep), dtype=np.int64)
         next_row = len(self.ids)
         new_ids = []
+        reused: list[tuple[Any, int]] = []
         for j, i in enumerate(keep):
             pid = canon[i]
             r = self.id_to_row.get(pid)
             if r is None:
-                r = next_row
-                next_row += 1
-                new_ids.append(pid)
+                if self.free_rows:
+                    r = self.free_rows.pop()
+                    reused.append((pid, r))
+                else:
+                    r = next_row
+                    next_row += 1
+                    new_ids.append(pid)
             rows[j] = r
         pl = [dict(payloads[i]) if payloads[i] is not None else None for i in keep]
         codes = self.encode_payloads(pl)
         ties = np.array([_tie_key(canon[i]) for i in keep], dtype=np.uint64)
         self.dev.upsert(vec[keep], rows=rows, codes=codes, ties=ties)
+        for pid, r in reused:
+            self.id_to_row[pid] = r
+            self.ids[r] = pid
         for pid in new_ids:
             self.id_to_row[pid] = len(self.ids)
             self.ids.append(pid)
@@ -267,9 +278,21 @@ class _HostCollection:
             out.append(self._hits(res.rows[qi, :n], res.scores[qi, :n]))
         return out
 
+    def release_rows(self, rows) -> None:
+        """Forget the ids and payloads of deleted rows and queue the rows for reuse."""
+        for r in np.asarray(rows, dtype=np.int64).tolist():
+            pid = self.ids[r]
+            if pid is None:
+                continue
+            self.id_to_row.pop(pid, None)
+            self.ids[r] = None
+            self.payloads[r] = None
+            self.free_rows.append(r)
+
     def delete(self, filters: dict[str, Any]) -> int:
         want = self.want_codes(filters)
-        _, n = self.dev.delete_where(want, cap=0)
+        rows, n = self.dev.delete_where(want)
+        self.release_rows(rows)
         return n
 
     def scroll(self, filters: dict[str, Any] | None, limit: int) -> list[dict[str, Any]]:
@@ -285,7 +308,7 @@ class _HostCollection:
         self.dev.close()
 
     # -- snapshots ---------------------------------------------------------------------------------------------
-    _HOST_STATE = ("name", "dim", "columns", "dicts", "ids", "id_to_row", "payloads", "rank_kind", "rk_keys", "rk_files",
+    _HOST_STATE = ("name", "dim", "columns", "dicts", "ids", "id_to_row", "payloads", "free_rows", "rank_kind", "rk_keys", "rk_files",
                    "rk_cent", "rk_names")
 
     def save(self, directory: str) -> None:
@@ -366,6 +389,7 @@ class _ClientShim:
                 rows = self._rows_matching(coll, flt)
                 if rows:
                     coll.dev.delete_rows(np.asarray(rows, dtype=np.int64))
+                    coll.release_rows(rows)
                 return len(rows)
         await asyncio.to_thread(work)
         return SimpleNamespace(status="completed")

@@ -187,3 +187,57 @@ async def scenario_client_shim(factory):
     flt2 = NS(must=[NS(key="project_name", match=NS(value="p"))])
     assert (await store.client.count(collection_name=CODE, count_filter=flt2)).count == 20
     await store.close()
+
+
+async def scenario_reindex_churn(factory, n_files=40, chunks=6, dim=48, rounds=12):
+    """VectorIndexer.index_file (embeddings/indexer.py:61-86) over and over: delete a file's chunks, insert new ones under fresh
+    uuid4 ids.  The shard must not grow (deleted rows are reused) and must keep answering like the oracle."""
+    import random
+    rng = random.Random(5)
+    store = B200VectorStore(dimensions=dim, _device_factory=factory)
+    ora = OracleManager(dim)
+    await store.connect()
+    await store.create_collections()
+    ora.create_collections()
+    seed = [0]
+
+    async def index_file(f: int):
+        seed[0] += 1
+        x, _ = synth.unixcoder_like(chunks, dim, seed=1000 + seed[0])
+        ids = synth.random_uuids(chunks, seed=2000 + seed[0])
+        pl = [{"file_path": f"src/f{f}.py", "entity_type": "function", "entity_name": f"fn_{f}_{i}_{seed[0]}", "language": "python",
+               "content": "x" * (20 + i), "start_line": i, "end_line": i + 2, "content_hash": f"h{seed[0]}", "project_name": "p"}
+              for i in range(chunks)]
+        await store.delete(collection=CODE, filters={"file_path": f"src/f{f}.py"})
+        ora.delete(CODE, {"file_path": f"src/f{f}.py"})
+        vecs = x.astype(np.float64).tolist()
+        await store.upsert(collection=CODE, ids=ids, vectors=vecs, payloads=pl)
+        ora.upsert(CODE, ids, vecs, pl)
+        return ids
+    last_ids = {}
+    for f in range(n_files):
+        last_ids[f] = await index_file(f)
+    coll = store._get(CODE)
+    rows_after_first_pass = coll.dev.rows
+    assert rows_after_first_pass == n_files * chunks
+    _, q = synth.unixcoder_like(1, dim, seed=77, n_queries=4)
+    for r in range(rounds):
+        for f in rng.sample(range(n_files), 10):
+            last_ids[f] = await index_file(f)
+        qv = q[r % 4].astype(np.float64).tolist()
+        for flt in (None, {"file_path": f"src/f{rng.randrange(n_files)}.py"}):
+            _same_hits(await store.search(collection=CODE, query_vector=qv, limit=8, filters=flt),
+                       ora.search(CODE, qv, limit=8, filters=flt), what=f"churn round {r} {flt}")
+    assert coll.dev.rows == rows_after_first_pass, "re-indexing must reuse the rows of deleted points"
+    assert (await store.get_collection_info(CODE)).points_count == n_files * chunks == ora.points_count(CODE)
+    # a deleted id can come back (new row), and the filter-only lookup still orders by id
+    victim = last_ids[3][0]
+    await store.delete(collection=CODE, filters={"file_path": "src/f3.py"}); ora.delete(CODE, {"file_path": "src/f3.py"})
+    x, _ = synth.unixcoder_like(1, dim, seed=4040)
+    p = {"file_path": "src/f3.py", "entity_type": "class", "entity_name": "Back", "language": "python", "content": "c", "start_line": 1,
+         "end_line": 2, "content_hash": "hb", "project_name": "p"}
+    await store.upsert(collection=CODE, ids=[victim], vectors=x.astype(np.float64).tolist(), payloads=[p])
+    ora.upsert(CODE, [victim], x.astype(np.float64).tolist(), [p])
+    _same_hits(await store.search(collection=CODE, query_vector=None, limit=50, filters={"project_name": "p"}),
+               ora.search(CODE, None, limit=50, filters={"project_name": "p"}), what="scroll after churn")
+    await store.close()

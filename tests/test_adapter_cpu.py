@@ -19,3 +19,7 @@ def test_error_convention():
 
 def test_client_shim_matchtext():
     asyncio.run(S.scenario_client_shim(FakeDevice))
+
+
+def test_reindex_churn_reuses_rows():
+    asyncio.run(S.scenario_reindex_churn(FakeDevice))
