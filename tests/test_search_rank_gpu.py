@@ -163,3 +163,37 @@ def test_fused_needs_rank_attrs(native_lib):
             await st.search_and_rank("code_chunks", [(None, None, [0.0] * 8, None)])
         await st.close()
     asyncio.run(run())
+
+
+def test_fused_on_summaries_collection(native_lib):
+    """Summary hits carry no start_line and no content (query/vector_search.py:243-260): keys end in ':None', code_quality is 0."""
+    from code_rag_b200.client import B200VectorStore
+    from code_rag_b200.ranking import HybridRanker
+    rng = random.Random(3)
+    n, dim = 800, 64
+    x, q = synth.unit_rows(n, dim, seed=8, n_queries=5)
+    pl = [{"file_path": f"src/m{i % 30}.py", "entity_type": "file", "entity_name": f"m{i % 30}_{i}", "summary": rng.choice([None, "", "does things"]),
+           "graph_node_id": None, "content_hash": "h"} for i in range(n)]
+    ids = [str(__import__("uuid").UUID(int=i + 10)) for i in range(n)]
+
+    async def run():
+        a = B200VectorStore(dimensions=dim, rank_attrs=True)
+        b = B200VectorStore(dimensions=dim, rank_attrs=True)
+        for st in (a, b):
+            await st.connect(); await st.create_collections()
+            await st.upsert("summaries", ids, x.astype(np.float64).tolist(), pl)
+        node = NS(node_type="File", name=pl[5]["entity_name"], qualified_name=None, file_path=pl[5]["file_path"], signature=None, docstring=None,
+                  summary="s", start_line=None, end_line=None, metadata={})
+        ctx = NS(primary_entities=[node], callers=[], callees=[], methods=[], parent_classes=[], child_classes=[])
+        plan = NS(primary_intent=NS(value="explain_architecture"), entities=[NS(name="m5")])
+        items = [(plan, ctx, q[i].astype(np.float64), {pl[5]["entity_name"]: {"total_degree": 30}}) for i in range(5)]
+        ranker = HybridRanker()
+        fused = await a.search_and_rank("summaries", items, limit=25, ranker=ranker)
+        coll = b._get("summaries")
+        hits = await b.search_batch("summaries", [it[2] for it in items], limit=25)
+        two = ranker.rank_batch([(it[0], it[1], [coll.vector_result_from_hit(h) for h in hits[i]], it[3]) for i, it in enumerate(items)])
+        for fa, fb in zip(fused, two):
+            _same(fa, fb)
+            assert all(r.get_key().endswith(":None") for r in fa)
+        await a.close(); await b.close()
+    asyncio.run(run())
