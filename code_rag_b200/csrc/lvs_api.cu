@@ -929,7 +929,10 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         fp.out_flags = d_flags + q0; fp.out_counts = d_counts + q0;
         fp.qnorm = (const float*)c->s_qnorm.p + q0; fp.max_norm = c->d_max_norm;
         const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
-        const unsigned ncta = (unsigned)std::min<uint32_t>(8u, (kpw + nrw - 1) / nrw);
+        // CTAs per query: every CTA of a query repeats the selection, so only as many as it takes to fill the machine once
+        // (two finalize CTAs fit on an SM): 8 for a handful of queries, 1 from ~300 queries on
+        const uint32_t fill = (uint32_t)std::max(1, (2 * sm) / std::max(1, qb));
+        const unsigned ncta = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(8u, fill), (kpw + nrw - 1) / nrw));
         cudaError_t fe = kpl == 1 ? launch_finalize<1>(fp, qb, ncta, fsm, st) : kpl == 2 ? launch_finalize<2>(fp, qb, ncta, fsm, st)
                        : kpl == 4 ? launch_finalize<4>(fp, qb, ncta, fsm, st) : launch_finalize<8>(fp, qb, ncta, fsm, st);
         if (fe != cudaSuccess) return fail(LVS_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(fe));

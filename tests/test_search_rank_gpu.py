@@ -127,7 +127,7 @@ def test_fused_equals_cpu_oracles(store):
     # the oracle replays the store's history: same rows, same overwrites and deletions, same number of earlier searches
     ora = OracleCollection(DIM)
     ora.upsert_rows_f32(0, x.astype(np.float32), [None] * len(x))
-    dead = [r for r, p in enumerate(coll.payloads) if p and p.get("file_path") == "src/m7.py"]
+    dead = [r for r, p in enumerate(payloads) if p.get("file_path") == "src/m7.py"]     # rows: ids were upserted in order
     ora.deleted[dead] = True
     for _ in range(coll.dev.search_counter):
         ora.search_topk_rows(q[0], 1)           # a local-mode search re-normalises the matrix in place, whatever the query
