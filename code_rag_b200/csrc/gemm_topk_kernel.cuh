@@ -76,7 +76,8 @@ struct GemmParams {
     float* dbg;                  // optional: CTA 0 dumps its first accumulator tile [128 x 256] (already scaled)
     uint32_t keep;               // keys kept per list (<= 16): fewer keys = fewer inserts but a weaker drop bound
     uint32_t unit_rows;          // every stored row has | ||row|| - 1 | <= 2^-9: clean tiles skip the 1/||row|| scaling
-    uint32_t dbg_mode;           // profiling aid: bit0 skip the epilogue's scoring, bit1 skip the MMA issue, bit2 skip tcgen05.ld
+    uint32_t dbg_mode;           // profiling aid: bit0 skip the epilogue's scoring, bit1 skip the MMA issue, bit2 skip tcgen05.ld,
+                                 // bit3 (pair form) stop re-loading the query chunks after the first pipeline fill
 };
 
 // shared memory: [stages][lists 8 warps * 16 keys * 32 lanes * 8][score columns 8 * 32 * 32 * 4][thr 128*4][inv 8*128*4][barriers]
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                     uint8_t* st = stages + (size_t)s * kStageBytes;
                     if constexpr (PAIR) {
                         // the leader's barrier counts the bytes of both CTAs
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * kStageBytes);
+                        const bool skip_a = (p.dbg_mode & 8u) != 0u && it >= S;      // profiling aid: stale query chunks, timing only
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], skip_a ? 2u * (kStageBytes - kGemmABytes) : 2u * kStageBytes);
+                        if (!skip_a)
                         tma_load_2d_pair(st, &tmap_a, (int)(kc * kKcElems), (int)(group * kGemmM), &full_bar[s]);
                         tma_load_2d_pair(st + kGemmABytes, &tmap_b, (int)(kc * kKcElems), (int)(tile * kGemmN + rank * kBRows), &full_bar[s]);
                     } else {
