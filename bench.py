@@ -11,6 +11,9 @@ exactly K steps, barrier + synchronize; device time by CUDA events on the launch
 `value` has the queries resident in HBM; `e2e` goes through the host-buffer API (pinned H2D of the query,
 D2H of ids+scores inside the timed region).  Each step scans >= 1.9 GB per GPU, far more than the 126 MB L2,
 so no explicit L2 flush is needed between steps (config.l2: "inputs_exceed_l2").
+`roofline` is the HBM one for the scan (and for the tensor-core kernel up to 128 queries per step) and the tensor one
+(TFLOP/s against the measured cuBLAS bf16 peak) above that.  At N=1 with the default single-query step the line also carries
+`batched`: BASELINE.json's configs[2] (256 queries x top-100 on the tcgen05 path) measured after the headline legs.
 """
 from __future__ import annotations
 
@@ -47,6 +50,7 @@ def parse_args():
     ap.add_argument("--storage", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the C3 (256 queries x top-100) measurement beside the headline")
     ap.add_argument("--stage-kb", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     return ap.parse_args()
@@ -239,6 +243,7 @@ def run_ours(args) -> None:
 
     Q, K, W, k = args.queries, args.steps, args.warmup, args.k
     W = max(W, 3)
+    tensor_path = Q >= (3 if args.storage == "bf16" else 5)       # K2 (tcgen05) takes batches from this size on (lvs_api.cu)
     qs = make_queries((K + W) * Q, args.dim, seed=11).reshape(K + W, Q, args.dim)
     dq_all = torch.from_numpy(qs).to(dev)          # resident queries for the `value` leg
     row_bytes = args.dim * (2 if args.storage == "bf16" else 4)
@@ -268,7 +273,7 @@ def run_ours(args) -> None:
     for i in range(W, W + K):
         out = searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
         flag_bufs[id(out[4])] = out[4]
-        launches += 3          # prep + scan + finalize per search
+        launches += 3 if not tensor_path else 4          # prep + scan + finalize, or prep + query prep + GEMM + finalize
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -342,6 +347,35 @@ def run_ours(args) -> None:
                 traffic = int(tj["dram_bytes_per_launch"] * (algo_bytes / tj["algorithmic_bytes_per_launch"]))
             except Exception:
                 traffic = None
+        roof = {"bound": "hbm", "kernel": "gemm_topk_kernel" if tensor_path else "scan_topk_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_ms": scan_mean,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+        if Q > 128:     # above the ridge (2 Q flop per corpus byte): the tensor pipe bounds the kernel
+            tpeak = float(peaks.get("bf16_tflops", 1649.5)) * (1.0 if args.storage == "bf16" else 0.5)
+            tfl = 2.0 * min(Q, 256) * n_local * args.dim / (scan_mean * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+                    "traffic": None, "algorithmic_flops_per_launch": 2.0 * min(Q, 256) * n_local * args.dim, "kernel_ms": scan_mean,
+                    "hbm_gbs_over_algorithmic_bytes": achieved,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops burst" if peaks else "fallback 1649.5 TFLOP/s") +
+                                   ("" if args.storage == "bf16" else " x 0.5 (tf32)")}
+        batched = None
+        if world == 1 and Q == 1 and args.storage == "bf16" and not args.no_batched:
+            # configs[2] (C3) beside the headline: 256 queries, top-100, tcgen05 path, host buffers through lvs_search
+            qb = make_queries(3 * 256, args.dim, seed=12).reshape(3, 256, args.dim)
+            walls, gms = [], []
+            for r_ in range(3):
+                t0 = time.perf_counter()
+                rb_ = shard.search(qb[r_], 100)
+                walls.append((time.perf_counter() - t0) * 1e3)
+                gms.append(shard.last_timing()["scan_ms"])
+            w_, g_ = min(walls[1:]), min(gms[1:])
+            tfl = 2.0 * 256 * n_local * args.dim / (g_ * 1e-3) / 1e12
+            batched = {"workload": f"C3: 256 queries x top-100, {args.rows}x{args.dim} bf16, one lvs_search call (host buffers)",
+                       "ms_per_batch": w_, "qps": 256e3 / w_, "gemm_topk_kernel_ms": g_, "tflops": tfl,
+                       "frac_of_bf16_burst_peak": tfl / float(peaks.get("bf16_tflops", 1649.5)),
+                       "frac_of_bf16_sustained_peak": tfl / float(peaks.get("bf16_tflops_sustained", 1361.6)),
+                       "flagged": int(rb_.flags.sum())}
         line = {
             "metric": METRIC, "value": K * Q / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -360,12 +394,11 @@ def run_ours(args) -> None:
                     "api": "lvs_search_submit/lvs_search_wait (C ABI, host buffers)" if world == 1 else "ShardedSearcher.submit/wait",
                     "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel" if Q < 8 else "gemm_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel_ms": scan_mean,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "roofline": roof,
             "clocks": clocks,
         }
+        if batched is not None:
+            line["batched"] = batched
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_qps(args, steps=8, warmup=2)
             line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
