@@ -68,6 +68,8 @@ SIGNATURES: dict[str, tuple] = {
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
     "lvs_snapshot_save": (C.c_int, [_vp, C.c_char_p]),
     "lvs_snapshot_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_vp)]),
+    "lvs_search_rank2": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                   C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
     "lvs_last_search_timing": (C.c_int, [_vp, _f32p, _ip, _ip]),
     "lvs_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "lvs_fetch_rows_f32": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
@@ -77,6 +79,11 @@ class RankBatch(C.Structure):
     """``lvs_rank_batch`` of include/lvs.h."""
     _fields_ = [("n_queries", C.c_int32), ("offsets", _vp), ("kind", _vp), ("key_id", _vp), ("file_id", _vp), ("depth", _vp),
                 ("entity_match", _vp), ("degree", _vp), ("flags", _vp), ("content_len", _vp), ("vscore", _vp), ("weights", _vp)]
+
+
+class RankHits(C.Structure):
+    """``lvs_rank_hits`` of include/lvs.h (host output arrays of one collection's hits)."""
+    _fields_ = [("scores", _vp), ("rows", _vp), ("counts", _vp), ("flags", _vp)]
 
 
 class RankQueryCtx(C.Structure):

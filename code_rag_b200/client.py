@@ -76,15 +76,15 @@ class _HostCollection:
     """Host half of a collection: ids, payloads and the per-column value dictionaries."""
 
     def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int, dev_factory=None,
-                 rank_kind: str | None = None):
+                 rank_kind: str | None = None, rank_dicts: tuple[dict, dict, dict] | None = None):
         self.name = name
         # fused search -> rank (include/lvs.h lvs_search_rank): per-row ranking attributes are derived from the payload at
         # upsert, the way VectorSearcher._transform_code_result / _transform_summary_result (query/vector_search.py:221-260)
         # and HybridRanker._process_vector_results (ranking/ranker.py:150-169) would read them.  None = feature off.
         self.rank_kind = rank_kind
-        self.rk_keys: dict[str, int] = {}
-        self.rk_files: dict[Any, int] = {}
-        self.rk_cent: dict[Any, int] = {}
+        # interned keys / file paths / centrality keys: ONE id space per store, so that the hits of `code_chunks` and of
+        # `summaries` can be ranked together (per-file cap, merges with graph candidates); names are per collection
+        self.rk_keys, self.rk_files, self.rk_cent = rank_dicts if rank_dicts is not None else ({}, {}, {})
         self.rk_names: dict[str, int] = {}
         self.dim = dim
         self.columns: list[str] = list(index_fields)[: N.MAX_FILTER_COLS]
@@ -417,6 +417,7 @@ class B200VectorStore:
         self._device = int(device if device is not None else os.environ.get("LOCAL_RANK", "0"))
         self._device_factory = _device_factory
         self._rank_attrs = bool(rank_attrs)     # keep per-row ranking attributes on the device (enables search_and_rank)
+        self._rank_dicts: tuple[dict, dict, dict] = ({}, {}, {})
         self._connected = False
         self._collections: dict[str, _HostCollection] = {}
         self._shim = _ClientShim(self)
@@ -474,7 +475,8 @@ class B200VectorStore:
                     self._collections[name] = await asyncio.to_thread(
                         _HostCollection, name, self._dimensions, self._storage, _INDEX_FIELDS[name], self._device,
                         self._device_factory,
-                        ("summary" if name == CollectionName.SUMMARIES.value else "code") if self._rank_attrs else None)
+                        ("summary" if name == CollectionName.SUMMARIES.value else "code") if self._rank_attrs else None,
+                        self._rank_dicts)
                     logger.info(f"Created collection: {name}")
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError("Failed to create collections", cause=e)
@@ -511,6 +513,11 @@ class B200VectorStore:
                 if old is not None:
                     old.close()
                 self._collections[name] = coll
+            if loaded:       # one id space per store again (the pickles of one save() hold equal copies)
+                first = next(iter(loaded.values()))
+                self._rank_dicts = (first.rk_keys, first.rk_files, first.rk_cent)
+                for coll in self._collections.values():
+                    coll.rk_keys, coll.rk_files, coll.rk_cent = self._rank_dicts
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to load collections from {directory}", cause=e)
 
@@ -529,6 +536,7 @@ class B200VectorStore:
             raise VectorStoreError(f"Failed to get collection info for {collection}", cause=e)
 
     async def clear_collections(self) -> None:
+        self._rank_dicts = ({}, {}, {})
         for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
             coll = self._collections.pop(name, None)
             if coll is not None:
@@ -581,23 +589,32 @@ class B200VectorStore:
             raise VectorStoreError(f"Failed to search {collection}", cause=e)
 
     async def search_and_rank(self, collection: str, items: Sequence[tuple], limit: int = 10,
-                              filters: dict[str, Any] | None = None, ranker=None):
+                              filters: dict[str, Any] | None = None, ranker=None, summaries: bool = False,
+                              summaries_filters: dict[str, Any] | None = None):
         """Additive API: vector search + hybrid ranking in one device pass.
 
         ``items``: one ``(plan, graph_context, query_vector, centrality_scores)`` per query.  Equivalent to
         ``ranker.rank_results(plan, graph_context, <VectorSearcher-shaped results of search(query_vector, limit, filters)>,
         centrality_scores)`` for every item (query/engine.py:176-181), but the top-k hits never leave the GPU between the
-        search and the blend.  Needs ``rank_attrs=True``.  Returns ``list[list[RankedResult]]``."""
+        search and the blend.  With ``summaries=True`` the queries whose intent is one of the five that
+        ``QueryEngine._execute_vector_search`` (query/engine.py:331-344) extends also get the ``limit // 2`` best ``summaries``
+        hits appended behind their code hits (``summaries_filters``: the engine passes the project only).  Needs
+        ``rank_attrs=True``.  Returns ``list[list[RankedResult]]``."""
         try:
             coll = self._get(collection)
             if coll.rank_kind is None:
                 raise ValueError("search_and_rank needs a store created with rank_attrs=True")
+            coll2 = self._get(CollectionName.SUMMARIES.value) if summaries and collection != CollectionName.SUMMARIES.value else None
             from .ranking import HybridRanker
             rk = ranker or HybridRanker()
 
             def work():
-                with coll.lock:
-                    return rk.rank_batch_fused(coll, items, limit, filters or None)
+                if coll2 is None:
+                    with coll.lock:
+                        return rk.rank_batch_fused(coll, items, limit, filters or None)
+                with coll.lock, coll2.lock:
+                    return rk.rank_batch_fused(coll, items, limit, filters or None,
+                                               summaries=(coll2, limit // 2, summaries_filters or None))
             return await asyncio.to_thread(work)
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to search and rank in {collection}", cause=e)

@@ -236,7 +236,9 @@ class DeviceCollection:
         N.check(self._lib.lvs_rank_attrs_set(self._handle(), _ptr(rows), len(rows), *[_ptr(x) for x in a]), "lvs_rank_attrs_set")
 
     def search_rank(self, queries: np.ndarray, k: int, want, graph: "N.RankBatch", ctx: "N.RankQueryCtx", n_graph_total: int,
-                    max_per_file: int, max_total: int, entity_bonus: float, rel_bonus: float) -> dict:
+                    max_per_file: int, max_total: int, entity_bonus: float, rel_bonus: float,
+                    second: "DeviceCollection | None" = None, k2: int = 0, want2=None, sel2=None) -> dict:
+        """lvs_search_rank2: search (this collection, and `second` for the queries sel2) + candidate build + K3 in one call."""
         q = np.ascontiguousarray(queries)
         if q.ndim == 1:
             q = q[None, :]
@@ -247,22 +249,34 @@ class DeviceCollection:
         if np.isnan(q).any():
             raise ValueError("Query vector must not contain NaN")
         Q, k = q.shape[0], int(k)
+        sel = np.ascontiguousarray(sel2 if sel2 is not None else [], dtype=np.int32)
+        Q2 = len(sel) if second is not None and k2 > 0 else 0
+        k2 = int(k2) if Q2 else 0
         out = {
             "hit_scores": np.zeros((Q, k), dtype=np.float64), "hit_rows": np.full((Q, k), -1, dtype=np.int64),
             "hit_counts": np.zeros(Q, dtype=np.uint32), "flags": np.zeros(Q, dtype=np.int32),
+            "hit_scores2": np.zeros((max(Q2, 1), max(k2, 1)), dtype=np.float64), "hit_rows2": np.full((max(Q2, 1), max(k2, 1)), -1, dtype=np.int64),
+            "hit_counts2": np.zeros(max(Q2, 1), dtype=np.uint32), "flags2": np.zeros(max(Q2, 1), dtype=np.int32),
             "count": np.zeros(Q, dtype=np.int32), "index": np.zeros((Q, max_total), dtype=np.int32),
             "score": np.zeros((Q, max_total), dtype=np.float64), "signals": np.zeros((Q, max_total, 7), dtype=np.float64),
             "mask": np.zeros((Q, max_total), dtype=np.uint8), "source": np.zeros((Q, max_total), dtype=np.uint8),
-            "leader": np.zeros(max(n_graph_total + Q * k, 1), dtype=np.int32),
+            "leader": np.zeros(max(n_graph_total + Q * (k + k2), 1), dtype=np.int32),
         }
+        h1, h2 = N.RankHits(), N.RankHits()
+        for h, sfx in ((h1, ""), (h2, "2")):
+            h.scores, h.rows = out["hit_scores" + sfx].ctypes.data_as(C.c_void_p), out["hit_rows" + sfx].ctypes.data_as(C.c_void_p)
+            h.counts, h.flags = out["hit_counts" + sfx].ctypes.data_as(C.c_void_p), out["flags" + sfx].ctypes.data_as(C.c_void_p)
         ms = (C.c_float * 2)()
         w = self._want(want)
-        N.check(self._lib.lvs_search_rank(self._handle(), _ptr(q), _np_dtype_code(q), Q, k, _ptr(w), C.byref(graph), C.byref(ctx),
-                                          int(max_per_file), int(max_total), float(entity_bonus), float(rel_bonus),
-                                          _ptr(out["hit_scores"]), _ptr(out["hit_rows"]), _ptr(out["hit_counts"]), _ptr(out["flags"]),
-                                          _ptr(out["count"]), _ptr(out["index"]), _ptr(out["score"]), _ptr(out["signals"]),
-                                          _ptr(out["mask"]), _ptr(out["source"]), _ptr(out["leader"]), ms), "lvs_search_rank")
+        w2 = second._want(want2) if Q2 else None
+        N.check(self._lib.lvs_search_rank2(self._handle(), second._handle() if Q2 else None, _ptr(q), _np_dtype_code(q), Q, k, k2,
+                                           _ptr(w), _ptr(w2), _ptr(sel) if Q2 else None, Q2, C.byref(graph), C.byref(ctx),
+                                           int(max_per_file), int(max_total), float(entity_bonus), float(rel_bonus),
+                                           C.byref(h1), C.byref(h2) if Q2 else None,
+                                           _ptr(out["count"]), _ptr(out["index"]), _ptr(out["score"]), _ptr(out["signals"]),
+                                           _ptr(out["mask"]), _ptr(out["source"]), _ptr(out["leader"]), ms), "lvs_search_rank2")
         out["search_ms"], out["rank_ms"] = float(ms[0]), float(ms[1])
+        out["k2"], out["Q2"] = k2, Q2
         return out
 
     def search_submit(self, queries: np.ndarray, k: int, want=None) -> tuple[int, int, int]:

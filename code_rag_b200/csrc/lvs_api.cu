@@ -1535,42 +1535,59 @@ extern "C" int lvs_rank_attrs_set(lvs_collection* c, const int64_t* rows, int n,
     return LVS_OK;
 }
 
-extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
-                               const lvs_rank_batch* graph, const lvs_rank_query_ctx* ctx, int max_per_file, int max_total,
-                               double entity_bonus, double rel_bonus, double* out_hit_scores, int64_t* out_hit_rows,
-                               uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
-                               double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+extern "C" int lvs_search_rank2(lvs_collection* c, lvs_collection* c2, const void* queries, int dtype, int Q, int k, int k2,
+                                const uint32_t* want, const uint32_t* want2, const int32_t* sel2, int Q2,
+                                const lvs_rank_batch* graph, const lvs_rank_query_ctx* ctx, int max_per_file, int max_total,
+                                double entity_bonus, double rel_bonus, const lvs_rank_hits* hits1, const lvs_rank_hits* hits2,
+                                int32_t* out_count, int32_t* out_index, double* out_score, double* out_signals, uint8_t* out_sigmask,
+                                uint8_t* out_source, int32_t* out_leader, float* device_ms) {
     int rc = check_search_args(c, queries, dtype, Q, k);
     if (rc != LVS_OK) return rc;
     if (Q == 0) return LVS_OK;
     if (!graph || !graph->offsets || !graph->weights || graph->n_queries != Q) return fail(LVS_EINVAL, "graph batch must describe the same %d queries", Q);
     if (!ctx || !ctx->ent_off || !ctx->ent_str_off || !ctx->cen_off) return fail(LVS_EINVAL, "NULL query context");
     if (max_total < 1) return fail(LVS_EINVAL, "bad max_total");
-    if (!out_hit_scores || !out_hit_rows || !out_hit_counts || !out_flags || !out_count || !out_index || !out_score || !out_leader)
+    if (!hits1 || !hits1->scores || !hits1->rows || !hits1->counts || !hits1->flags || !out_count || !out_index || !out_score || !out_leader)
         return fail(LVS_EINVAL, "NULL output");
-    std::lock_guard<std::mutex> lk(c->mu);
+    const bool two = c2 != nullptr && Q2 > 0;
+    if (c2 == c) return fail(LVS_EINVAL, "the second collection must be a different one");
+    if (two) {
+        if (k2 < 1 || k2 > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k2, LVS_MAX_K);
+        if (Q2 > Q || !sel2) return fail(LVS_EINVAL, "bad query subset for the second collection");
+        if (c2->dim != c->dim) return fail(LVS_EINVAL, "the two collections have different dimensions (%d, %d)", c->dim, c2->dim);
+        if (!hits2 || !hits2->scores || !hits2->rows || !hits2->counts || !hits2->flags) return fail(LVS_EINVAL, "NULL output (second collection)");
+        for (int j = 0; j < Q2; ++j) if (sel2[j] < 0 || sel2[j] >= Q || (j > 0 && sel2[j] <= sel2[j - 1])) return fail(LVS_EINVAL, "sel2 must be increasing query indices");
+    } else { k2 = 0; Q2 = 0; }
+    std::unique_lock<std::mutex> lk(c->mu, std::defer_lock), lk2;
+    if (two) { lk2 = std::unique_lock<std::mutex>(c2->mu, std::defer_lock); std::lock(lk, lk2); } else lk.lock();
     if (c->rk_cap < c->n_rows || !c->d_rk_key) return fail(LVS_ESTATE, "ranking attributes are not set for every row (lvs_rank_attrs_set)");
+    if (two && c2->n_rows > 0 && (c2->rk_cap < c2->n_rows || !c2->d_rk_key))
+        return fail(LVS_ESTATE, "ranking attributes are not set for every row of the second collection");
+    const int kk = k + k2;                                   // hit slots per query
     const int32_t* goff = graph->offsets;
     const int64_t ngc = goff[Q];
     int max_c = 0;
     for (int q = 0; q < Q; ++q) {
         const int g = goff[q + 1] - goff[q];
         if (g < 0) return fail(LVS_EINVAL, "offsets must be non-decreasing");
-        max_c = std::max(max_c, g + k);
+        max_c = std::max(max_c, g + kk);
     }
     if (max_c > kRankMaxCand) return fail(LVS_ELIMIT, "%d candidates in one query exceed %d", max_c, kRankMaxCand);
     if (ngc > 0 && (!graph->kind || !graph->key_id || !graph->file_id || !graph->depth || !graph->entity_match || !graph->degree ||
                     !graph->flags)) return fail(LVS_EINVAL, "NULL graph candidate array");
-    const int64_t nc = ngc + (int64_t)Q * k;                 // combined candidates: per query its graph candidates, then k hit slots
+    const int64_t nc = ngc + (int64_t)Q * kk;                // combined candidates: per query its graph candidates, then the hit slots
     const int n_ent = ctx->ent_off[Q], n_cen = ctx->cen_off[Q];
     const size_t ent_bytes = n_ent > 0 ? ctx->ent_str_off[n_ent] : 0;
     if (n_ent > 0 && ent_bytes > 0 && !ctx->ent_bytes) return fail(LVS_EINVAL, "NULL entity bytes");
     if (n_cen > 0 && (!ctx->cen_id || !ctx->cen_deg)) return fail(LVS_EINVAL, "NULL centrality table");
 
     auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const size_t qraw = (size_t)Q * c->dim * dt_size(dtype);
+    const size_t esz = dt_size(dtype);
+    const size_t qrow = (size_t)c->dim * esz;
     size_t o = 0;
-    const size_t o_q = o; o = al(o + qraw);
+    const size_t o_q = o; o = al(o + (size_t)Q * qrow);
+    const size_t o_q2 = o; o = al(o + (size_t)Q2 * qrow);
+    const size_t o_sel = o; o = al(o + (size_t)std::max(Q2, 1) * 4);
     const size_t o_off = o; o = al(o + (size_t)(Q + 1) * 4);
     const size_t o_ng = o; o = al(o + (size_t)Q * 4);
     const size_t o_kind = o; o = al(o + (size_t)nc);
@@ -1590,13 +1607,18 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
     const size_t o_cid = o; o = al(o + (size_t)std::max(n_cen, 1) * 4);
     const size_t o_cdeg = o; o = al(o + (size_t)std::max(n_cen, 1) * 4);
     const size_t in_bytes = o;
-    const size_t nres = (size_t)Q * k, rows = (size_t)Q * max_total;
+    const size_t nres = (size_t)Q * k, nres2 = (size_t)Q2 * std::max(k2, 1), rows = (size_t)Q * max_total;
     // outputs (device -> host in one copy)
     const size_t r_hs = o; o = al(o + nres * 8);
     const size_t r_hr = o; o = al(o + nres * 8);
     const size_t r_ht = o; o = al(o + nres * 8);
     const size_t r_hc = o; o = al(o + (size_t)Q * 4);
     const size_t r_hf = o; o = al(o + (size_t)Q * 4);
+    const size_t r_hs2 = o; o = al(o + nres2 * 8);
+    const size_t r_hr2 = o; o = al(o + nres2 * 8);
+    const size_t r_ht2 = o; o = al(o + nres2 * 8);
+    const size_t r_hc2 = o; o = al(o + (size_t)std::max(Q2, 1) * 4);
+    const size_t r_hf2 = o; o = al(o + (size_t)std::max(Q2, 1) * 4);
     const size_t r_cnt = o; o = al(o + (size_t)Q * 4);     // candidates present per query (gather output)
     const size_t r_err = o; o = al(o + 4);
     const size_t r_count = o; o = al(o + (size_t)Q * 4);
@@ -1612,10 +1634,14 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
     if ((rc = ensure_dev(c->s_rk_dev, total)) != LVS_OK) return rc;
     uint8_t* hp = (uint8_t*)c->h_rk_pin.p;
     uint8_t* dp = (uint8_t*)c->s_rk_dev.p;
-    memcpy(hp + o_q, queries, qraw);
+    memcpy(hp + o_q, queries, (size_t)Q * qrow);
+    for (int j = 0; j < Q2; ++j) {
+        memcpy(hp + o_q2 + (size_t)j * qrow, (const uint8_t*)queries + (size_t)sel2[j] * qrow, qrow);
+        ((int32_t*)(hp + o_sel))[j] = sel2[j];
+    }
     int32_t* off2 = (int32_t*)(hp + o_off);
     int32_t* ngq = (int32_t*)(hp + o_ng);
-    for (int q = 0; q <= Q; ++q) off2[q] = goff[q] + q * k;
+    for (int q = 0; q <= Q; ++q) off2[q] = goff[q] + q * kk;
     for (int q = 0; q < Q; ++q) {
         const int g = goff[q + 1] - goff[q];
         ngq[q] = g;
@@ -1642,10 +1668,22 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
     CU(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(dp + r_err, 0, 4, st));
     CU(cudaEventRecord(c->rk_ev[0], st));
-    // 1. the search: top-k rows and float64 scores stay on the device
+    // 1. the search(es): top-k rows and float64 scores stay on the device
     rc = search_core(c, dp + o_q, dtype, Q, k, want, (double*)(dp + r_hs), (int64_t*)(dp + r_hr), (uint64_t*)(dp + r_ht),
                      (uint32_t*)(dp + r_hc), nullptr, (int32_t*)(dp + r_hf), true, st);
     if (rc != LVS_OK) return rc;
+    if (two) {
+        if (c2->n_rows > 0) {
+            rc = search_core(c2, dp + o_q2, dtype, Q2, k2, want2, (double*)(dp + r_hs2), (int64_t*)(dp + r_hr2), (uint64_t*)(dp + r_ht2),
+                             (uint32_t*)(dp + r_hc2), nullptr, (int32_t*)(dp + r_hf2), true, st);
+            if (rc != LVS_OK) return rc;
+        } else {
+            CU(cudaMemsetAsync(dp + r_hc2, 0, (size_t)Q2 * 4, st));
+            CU(cudaMemsetAsync(dp + r_hf2, 0, (size_t)Q2 * 4, st));
+            CU(cudaMemsetAsync(dp + r_hr2, 0xFF, nres2 * 8, st));
+            CU(cudaMemsetAsync(dp + r_hs2, 0, nres2 * 8, st));
+        }
+    }
     CU(cudaEventRecord(c->rk_ev[1], st));
     // 2. hits -> vector candidates, 3. K3
     RankGatherParams gp;
@@ -1662,8 +1700,21 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
     gp.entity_match = (double*)(dp + o_em); gp.degree = (int32_t*)(dp + o_deg); gp.flags = dp + o_flags;
     gp.content_len = (int32_t*)(dp + o_clen); gp.vscore = (double*)(dp + o_vs);
     gp.counts = (int32_t*)(dp + r_cnt); gp.error = (int32_t*)(dp + r_err);
+    gp.sel = nullptr;
     rank_gather_kernel<<<Q, 128, 0, st>>>(gp);
     CU(cudaGetLastError());
+    if (two) {
+        RankGatherParams g2 = gp;
+        g2.k = k2; g2.hit_scores = (const double*)(dp + r_hs2); g2.hit_rows = (const int64_t*)(dp + r_hr2);
+        g2.hit_counts = (const uint32_t*)(dp + r_hc2);
+        g2.row_base = c2->row_base; g2.attr_rows = std::min(c2->rk_cap, c2->n_rows);
+        g2.row_key = c2->d_rk_key; g2.row_file = c2->d_rk_file; g2.row_cent = c2->d_rk_cent; g2.row_name = c2->d_rk_name;
+        g2.row_clen = c2->d_rk_clen; g2.row_flags = c2->d_rk_flags;
+        g2.name_off = c2->d_name_off; g2.name_bytes = c2->d_name_bytes; g2.n_names = (uint32_t)c2->n_names;
+        g2.sel = (const int32_t*)(dp + o_sel);
+        rank_gather_kernel<<<Q2, 128, 0, st>>>(g2);
+        CU(cudaGetLastError());
+    }
     RankParams p;
     memset(&p, 0, sizeof(p));
     p.n_queries = Q; p.offsets = gp.offsets; p.counts = gp.counts; p.kind = gp.kind; p.key_id = gp.key_id; p.file_id = gp.file_id;
@@ -1680,16 +1731,22 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
     CU(cudaEventRecord(c->rk_ev[2], st));
     CU(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    c->last_launches += 2;
+    c->last_launches += two ? 3 : 2;
     if (device_ms) {
         cudaEventElapsedTime(&device_ms[0], c->rk_ev[0], c->rk_ev[1]);
         cudaEventElapsedTime(&device_ms[1], c->rk_ev[1], c->rk_ev[2]);
     }
     if (*(int32_t*)(hp + r_err)) return fail(LVS_ESTATE, "a hit row has no ranking attributes");
-    memcpy(out_hit_scores, hp + r_hs, nres * 8);
-    memcpy(out_hit_rows, hp + r_hr, nres * 8);
-    memcpy(out_hit_counts, hp + r_hc, (size_t)Q * 4);
-    memcpy(out_flags, hp + r_hf, (size_t)Q * 4);
+    memcpy(hits1->scores, hp + r_hs, nres * 8);
+    memcpy(hits1->rows, hp + r_hr, nres * 8);
+    memcpy(hits1->counts, hp + r_hc, (size_t)Q * 4);
+    memcpy(hits1->flags, hp + r_hf, (size_t)Q * 4);
+    if (two) {
+        memcpy(hits2->scores, hp + r_hs2, (size_t)Q2 * k2 * 8);
+        memcpy(hits2->rows, hp + r_hr2, (size_t)Q2 * k2 * 8);
+        memcpy(hits2->counts, hp + r_hc2, (size_t)Q2 * 4);
+        memcpy(hits2->flags, hp + r_hf2, (size_t)Q2 * 4);
+    }
     memcpy(out_count, hp + r_count, (size_t)Q * 4);
     memcpy(out_index, hp + r_index, rows * 4);
     memcpy(out_score, hp + r_score, rows * 8);
@@ -1698,6 +1755,18 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
     if (out_source) memcpy(out_source, hp + r_src, rows);
     memcpy(out_leader, hp + r_lead, (size_t)nc * 4);
     return LVS_OK;
+}
+
+extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                               const lvs_rank_batch* graph, const lvs_rank_query_ctx* ctx, int max_per_file, int max_total,
+                               double entity_bonus, double rel_bonus, double* out_hit_scores, int64_t* out_hit_rows,
+                               uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
+                               double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+    lvs_rank_hits h1;
+    h1.scores = out_hit_scores; h1.rows = out_hit_rows; h1.counts = out_hit_counts; h1.flags = out_flags;
+    return lvs_search_rank2(c, nullptr, queries, dtype, Q, k, 0, want, nullptr, nullptr, 0, graph, ctx, max_per_file, max_total,
+                            entity_bonus, rel_bonus, &h1, nullptr, out_count, out_index, out_score, out_signals, out_sigmask, out_source,
+                            out_leader, device_ms);
 }
 
 // ------------------------------------------------------------------------------------------------------

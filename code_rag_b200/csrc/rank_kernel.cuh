@@ -251,8 +251,11 @@ struct RankGatherParams {
     const uint32_t* cen_id; const int32_t* cen_deg;
     uint8_t* kind; uint32_t* key_id; uint32_t* file_id; int32_t* depth; double* entity_match; int32_t* degree;
     uint8_t* flags; int32_t* content_len; double* vscore;
-    int32_t* counts;                // [Q] out: n_graph + hits
+    int32_t* counts;                // [Q] out: n_graph + hits (second segment: += its hits)
     int32_t* error;                 // set to 1 when a hit row has no attributes
+    // second segment (hits of another collection, e.g. summaries behind the code hits, query/engine.py:331-344): the searched
+    // queries are a subset, sel[j] = batch query of searched query j; its candidates go right behind what counts[] already holds
+    const int32_t* sel;             // nullptr = first segment (searched query j is batch query j)
 };
 
 __device__ __forceinline__ bool bytes_equal(const uint8_t* a, const uint8_t* b, uint32_t n) {
@@ -261,15 +264,17 @@ __device__ __forceinline__ bool bytes_equal(const uint8_t* a, const uint8_t* b, 
 }
 
 __global__ void __launch_bounds__(128) rank_gather_kernel(const RankGatherParams p) {
-    const int q = blockIdx.x;
-    const int hits = (int)min(p.hit_counts[q], (uint32_t)p.k);
-    const int ng = p.n_graph[q];
-    if (threadIdx.x == 0) p.counts[q] = ng + hits;
+    const int j = blockIdx.x;                               // searched query
+    const int q = p.sel ? p.sel[j] : j;                     // batch query
+    const int hits = (int)min(p.hit_counts[j], (uint32_t)p.k);
+    const int before = p.sel ? p.counts[q] : p.n_graph[q];  // candidates already in place
+    __syncthreads();                                        // everyone has read counts[q] before it is updated
+    if (threadIdx.x == 0) p.counts[q] = before + hits;
     const int e0 = p.ent_off[q], e1 = p.ent_off[q + 1];
     const int c0 = p.cen_off[q], c1 = p.cen_off[q + 1];
     for (int s = threadIdx.x; s < hits; s += blockDim.x) {
-        const int g = p.offsets[q] + ng + s;
-        const int64_t row = p.hit_rows[(size_t)q * p.k + s] - p.row_base;
+        const int g = p.offsets[q] + before + s;
+        const int64_t row = p.hit_rows[(size_t)j * p.k + s] - p.row_base;
         if (row < 0 || row >= p.attr_rows) { *p.error = 1; p.kind[g] = 4; p.key_id[g] = 0xFFFFFFFFu; p.file_id[g] = 0xFFFFFFFFu;
             p.depth[g] = 0; p.entity_match[g] = 0.0; p.degree[g] = -1; p.flags[g] = 0; p.content_len[g] = -1; p.vscore[g] = 0.0; continue; }
         const uint32_t nid = p.row_name[row];
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(128) rank_gather_kernel(const RankGatherParams
         p.degree[g] = deg;
         p.flags[g] = p.row_flags[row];
         p.content_len[g] = p.row_clen[row];
-        p.vscore[g] = p.hit_scores[(size_t)q * p.k + s];
+        p.vscore[g] = p.hit_scores[(size_t)j * p.k + s];
     }
 }
 

@@ -44,6 +44,11 @@ _INTENT_ADJUSTMENTS = {          # models.py:75-91, keyed by QueryIntent.value
 }
 
 
+# intents for which QueryEngine._execute_vector_search also searches the summaries collection (query/engine.py:331-337)
+SUMMARY_INTENTS = frozenset({"explain_implementation", "explain_relationship", "explain_data_flow", "explain_architecture",
+                             "search_functionality"})
+
+
 def _intent_value(intent: Any) -> str:
     return str(getattr(intent, "value", intent))
 
@@ -256,16 +261,25 @@ class HybridRanker:
             results.append(ranked)
         return results
 
-    def rank_batch_fused(self, coll, items: Sequence[tuple], limit: int, filters=None) -> list[list[RankedResult]]:
+    def rank_batch_fused(self, coll, items: Sequence[tuple], limit: int, filters=None, summaries=None) -> list[list[RankedResult]]:
         """Search + rank in one device pass (``lvs_search_rank``).  ``coll`` is the adapter's host collection
         (``client._HostCollection`` with ranking attributes); each item is ``(plan, graph_context, query_vector, centrality)``.
         Same results as ``rank_batch`` fed with the VectorSearcher-shaped hits of ``coll.search`` - the vector-hit candidates
-        (key / file ids, entity match, centrality, quality inputs) are built on the GPU from per-row columns."""
+        (key / file ids, entity match, centrality, quality inputs) are built on the GPU from per-row columns.
+        ``summaries = (summaries collection, limit, filters)``: queries with one of ``SUMMARY_INTENTS`` also get that many
+        summary hits behind their code hits, as ``QueryEngine._execute_vector_search`` does (query/engine.py:331-344)."""
         cfg = self.config
         nq = len(items)
         if nq == 0:
             return []
         want = coll.want_codes(filters)
+        coll2, k2, want2, sel2 = None, 0, None, []
+        if summaries is not None and summaries[1] > 0:
+            coll2, k2 = summaries[0], int(summaries[1])
+            want2 = coll2.want_codes(summaries[2])
+            sel2 = [qi for qi, it in enumerate(items) if _intent_value(it[0].primary_intent) in SUMMARY_INTENTS]
+            if not sel2:
+                coll2, k2 = None, 0
         b = _Batch()
         ent_off, ent_str_off, ent_blob = [0], [0], []
         cen_off, cen_id, cen_deg = [0], [], []
@@ -332,26 +346,37 @@ class HybridRanker:
             setattr(cx, name, a.ctypes.data_as(C.c_void_p))
         k = int(limit)
         out = coll.dev.search_rank(queries, k, want, rb, cx, ng_total, cfg.max_per_file, cfg.max_total, cfg.entity_match_bonus,
-                                   cfg.relationship_bonus)
+                                   cfg.relationship_bonus, second=coll2.dev if coll2 is not None else None, k2=k2, want2=want2, sel2=sel2)
         self.last_device_ms = out["rank_ms"]
         self.last_search_ms = out["search_ms"]
-        if (out["flags"] & 1).any():
-            # rare: the search could not prove exactness with the default candidate set - take the two-step route
+        k2 = out["k2"]
+        pos2 = {qi: j for j, qi in enumerate(sel2)} if k2 else {}
+        if (out["flags"] & 1).any() or (k2 and (out["flags2"][:len(sel2)] & 1).any()):
+            # rare: a search could not prove exactness with the default candidate set - take the two-step route
             hits = coll.search(queries, k, filters)
-            return self.rank_batch([(it[0], it[1], [coll.vector_result_from_hit(h) for h in hits[i]], it[3])
-                                    for i, it in enumerate(items)])
+            vrs = [[coll.vector_result_from_hit(h) for h in hits[i]] for i in range(nq)]
+            if k2:
+                hits2 = coll2.search(queries[sel2], k2, summaries[2])
+                for j, qi in enumerate(sel2):
+                    vrs[qi].extend(coll2.vector_result_from_hit(h) for h in hits2[j])
+            return self.rank_batch([(it[0], it[1], vrs[i], it[3]) for i, it in enumerate(items)])
         results = []
         for q in range(nq):
             g0, g1 = b.offsets[q], b.offsets[q + 1]
             ng = g1 - g0
-            base = g0 + q * k                       # combined candidate index of this query's first candidate
-            nh = int(out["hit_counts"][q])
+            base = g0 + q * (k + k2)                # combined candidate index of this query's first candidate
+            nh1 = int(out["hit_counts"][q])
+            j2 = pos2.get(q)
+            nh = nh1 + (int(out["hit_counts2"][j2]) if j2 is not None else 0)
 
-            def record(ci, q=q, g0=g0, ng=ng):
+            def record(ci, q=q, g0=g0, ng=ng, nh1=nh1, j2=j2):
                 if ci < ng:
                     return b.records[g0 + ci]
                 s_ = ci - ng
-                return (4, coll.vector_result(int(out["hit_rows"][q, s_]), float(out["hit_scores"][q, s_])), None, None)
+                if s_ < nh1:
+                    return (4, coll.vector_result(int(out["hit_rows"][q, s_]), float(out["hit_scores"][q, s_])), None, None)
+                s_ -= nh1
+                return (4, coll2.vector_result(int(out["hit_rows2"][j2, s_]), float(out["hit_scores2"][j2, s_])), None, None)
             members: dict[int, list[int]] = {}
             for ci in range(ng + nh):
                 members.setdefault(int(out["leader"][base + ci]), []).append(ci)

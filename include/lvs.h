@@ -189,6 +189,19 @@ int lvs_search_rank(lvs_collection* c, const void* queries, int dtype, int Q, in
                     uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
                     double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms);
 
+/* Two collections in one call: QueryEngine._execute_vector_search (query/engine.py:331-344) appends, for five intents, the hits
+ * of a `summaries` search (limit // 2) behind the code hits.  c2 is searched with the queries sel2[0..Q2) (increasing indices into the
+ * batch, k2 hits each); a query's candidates are [its graph candidates][its hits in c][its hits in c2], compact; out_leader has
+ * graph->offsets[Q] + Q*(k + k2) entries.  The interned key / file / centrality ids must be shared by the two collections.
+ * c2 == NULL or Q2 == 0: exactly lvs_search_rank. */
+typedef struct lvs_rank_hits { double* scores; int64_t* rows; uint32_t* counts; int32_t* flags; } lvs_rank_hits;   /* host outputs */
+int lvs_search_rank2(lvs_collection* c, lvs_collection* c2, const void* queries, int dtype, int Q, int k, int k2,
+                     const uint32_t* want, const uint32_t* want2, const int32_t* sel2, int Q2,
+                     const lvs_rank_batch* graph, const lvs_rank_query_ctx* ctx, int max_per_file, int max_total,
+                     double entity_bonus, double rel_bonus, const lvs_rank_hits* hits1, const lvs_rank_hits* hits2,
+                     int32_t* out_count, int32_t* out_index, double* out_score, double* out_signals, uint8_t* out_sigmask,
+                     uint8_t* out_source, int32_t* out_leader, float* device_ms);
+
 /* ---- snapshots: the shard's device arrays (vectors, tombstones, codes, tie keys, write epochs,
  *      norms, search counter, ranking attributes and name pool) to / from one file, so that an index survives a restart the
  *      way the Qdrant volume does (reference docker-compose.yml:42-43).  A loaded shard answers every search exactly as the

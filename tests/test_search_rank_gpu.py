@@ -197,3 +197,51 @@ def test_fused_on_summaries_collection(native_lib):
             assert all(r.get_key().endswith(":None") for r in fa)
         await a.close(); await b.close()
     asyncio.run(run())
+
+
+def test_fused_with_summaries_extension(native_lib):
+    """QueryEngine._execute_vector_search (query/engine.py:315-346): five intents also search `summaries` (limit // 2) and append
+    those hits behind the code hits.  One fused call over both collections == the two-step route, search for search."""
+    from code_rag_b200.client import B200VectorStore
+    from code_rag_b200.ranking import SUMMARY_INTENTS, HybridRanker
+    rng = random.Random(41)
+    n, ns, dim = 3000, 600, 64
+    x, q = synth.unit_rows(n + ns, dim, seed=12, n_queries=12)
+    pl = _payloads(rng, n)
+    spl = [{"file_path": pl[rng.randrange(n)]["file_path"], "entity_type": "file", "entity_name": rng.choice(["parse", "Loader", "m"]) + str(i),
+            "summary": rng.choice([None, "does things"]), "project_name": rng.choice(["a", "b"]), "graph_node_id": None} for i in range(ns)]
+    ids = [str(__import__("uuid").UUID(int=i + 1)) for i in range(n + ns)]
+    intents = ["explain_architecture", "find_callers", "search_functionality", "find_similar", "explain_data_flow", "locate_entity"]
+
+    async def run():
+        a = B200VectorStore(dimensions=dim, rank_attrs=True)
+        b = B200VectorStore(dimensions=dim, rank_attrs=True)
+        for st in (a, b):
+            await st.connect(); await st.create_collections()
+            await st.upsert("summaries", ids[n:n + 200], x[n:n + 200].astype(np.float64).tolist(), spl[:200])   # interleaved on purpose:
+            await st.upsert("code_chunks", ids[:n], x[:n].astype(np.float64).tolist(), pl)                     # one id space for both
+            await st.upsert("summaries", ids[n + 200:], x[n + 200:].astype(np.float64).tolist(), spl[200:])
+        items = []
+        for i in range(12):
+            plan, ctx, qv, cent = _case(rng, pl, i, q[i].astype(np.float64))
+            plan.primary_intent = NS(value=intents[i % len(intents)])
+            items.append((plan, ctx, qv, cent))
+        assert any(it[0].primary_intent.value in SUMMARY_INTENTS for it in items)
+        ranker = HybridRanker()
+        for flt, sflt in ((None, None), ({"project_name": "a"}, {"project_name": "a"})):
+            fused = await a.search_and_rank("code_chunks", items, limit=12, filters=flt, ranker=ranker, summaries=True, summaries_filters=sflt)
+            code, summ = b._get("code_chunks"), b._get("summaries")
+            hits = await b.search_batch("code_chunks", [it[2] for it in items], limit=12, filters=flt)
+            vrs = [[code.vector_result_from_hit(h) for h in hits[i]] for i in range(12)]
+            sel = [i for i, it in enumerate(items) if it[0].primary_intent.value in SUMMARY_INTENTS]
+            hits2 = await b.search_batch("summaries", [items[i][2] for i in sel], limit=6, filters=sflt)
+            for j, i in enumerate(sel):
+                vrs[i].extend(summ.vector_result_from_hit(h) for h in hits2[j])
+            two = ranker.rank_batch([(it[0], it[1], vrs[i], it[3]) for i, it in enumerate(items)])
+            n_summary = 0
+            for fa, fb in zip(fused, two):
+                _same(fa, fb)
+                n_summary += sum(r.get_key().endswith(":None") for r in fa)
+            assert n_summary > 0, "summary hits should reach the ranked lists"
+        await a.close(); await b.close()
+    asyncio.run(run())
