@@ -1858,6 +1858,21 @@ extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t cap
     if (!f) return fail(LVS_EINVAL, "cannot open %s", path);
     SnapshotHeader h;
     if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LVSSNAP1", 8) != 0) { fclose(f); return fail(LVS_EINVAL, "%s is not a lattice-b200 snapshot", path); }
+    // the header must describe a file of exactly this size before anything is allocated from it
+    if (h.n_rows < 0 || h.n_rows >= (int64_t)0xFFFFFFF0ll || h.row_base < 0 || h.dim < 1 || h.dim > 8192 || h.n_cols < 0 ||
+        h.n_cols > kMaxFilterCols || h.rk_rows < 0 || h.rk_rows > h.n_rows || h.n_names < 0 || h.name_bytes < 0 ||
+        h.n_names > (int64_t)0xFFFFFFFFll || h.name_bytes > (int64_t)0xFFFFFFFFll || h.row_bytes == 0 || h.row_bytes > 8192u * 4u) {
+        fclose(f);
+        return fail(LVS_EINVAL, "%s: corrupt snapshot header", path);
+    }
+    {
+        const int64_t expect = (int64_t)sizeof(h) + h.n_rows * ((int64_t)h.row_bytes + 1 + 4 + 8 + 4 + 4 * (int64_t)h.n_cols) + h.rk_rows * 21 +
+                               (h.n_names ? (h.n_names + 1) * 4 + h.name_bytes : 0);
+        if (fseek(f, 0, SEEK_END) != 0 || (int64_t)ftell(f) != expect || fseek(f, (long)sizeof(h), SEEK_SET) != 0) {
+            fclose(f);
+            return fail(LVS_EINVAL, "%s: snapshot size does not match its header (expected %lld bytes)", path, (long long)expect);
+        }
+    }
     lvs_collection* c = nullptr;
     int rc = lvs_collection_create(name, h.dim, h.storage, h.metric, h.n_cols, std::max(capacity_rows, h.n_rows), h.row_base, &c);
     if (rc != LVS_OK) { fclose(f); return rc; }

@@ -60,3 +60,23 @@ def test_product_code_never_imports_the_oracle():
     for path in (ROOT / "code_rag_b200").rglob("*.py"):
         src = path.read_text()
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f"{path} mentions the oracle"
+
+
+def test_snapshot_load_rejects_foreign_and_corrupt_files(native_lib, tmp_path):
+    """Header checks run before any allocation (and before any CUDA call, so this runs without a GPU)."""
+    import struct
+    from code_rag_b200 import _native
+    h = ctypes.c_void_p()
+    bad = tmp_path / "bad.lvs"
+    bad.write_bytes(b"not a snapshot" * 20)
+    assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL and h.value is None
+    assert b"not a lattice-b200 snapshot" in native_lib.lvs_last_error()
+    # right magic, absurd row count / truncated body
+    hdr = b"LVSSNAP1" + struct.pack("<4i2q2I2f3q4q", 768, 1, 0, 2, 1 << 40, 0, 0, 1536, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0)
+    bad.write_bytes(hdr)
+    assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
+    hdr = b"LVSSNAP1" + struct.pack("<4i2q2I2f3q4q", 768, 1, 0, 2, 1000, 0, 0, 1536, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0)
+    bad.write_bytes(hdr + b"\0" * 100)
+    assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
+    assert b"size does not match" in native_lib.lvs_last_error()
+    assert native_lib.lvs_snapshot_load(str(tmp_path / "missing.lvs").encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
