@@ -217,8 +217,10 @@ int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches,
  * launching stream, with the algorithmic bytes of each launch.  The stream must have been synchronised. */
 int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n);
 /* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record events, default),
- * "gemm_min_q" (batch size from which the tensor-core path is used, default 3; fp32 shards at least 5), "path" (0 auto, 1 scan only, 2 tensor-core
- * whenever eligible), "gemm_stages".  Returns LVS_EINVAL for unknown names. */
+ * "gemm_min_q" (batch size from which the tensor-core path is used, default 3; fp32 shards at least 5), "path" (0 auto, 1 scan only,
+ * 2 tensor-core whenever eligible), "gemm_stages", "gemm_keep" (keys per K2 list, 4..16), "gemm_no_pair" (1 = never use the
+ * cta_group::2 form), "gemm_no_tf32" (1 = fp32 shards stay on the scan), "gemm_no_unit" (1 = always scale by 1/||row||),
+ * "gemm_dbg" (profiling switches, see GemmParams::dbg_mode).  Returns LVS_EINVAL for unknown names. */
 int lvs_set_option(lvs_collection* c, const char* name, int value);
 /* Copy rows back (debug / snapshots): out is n x dim float32 of the values a fresh reference collection would hold. */
 int lvs_fetch_rows_f32(lvs_collection* c, const int64_t* rows, int64_t n, float* out);
