@@ -66,6 +66,8 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_rank_attrs_set": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),
+    "lvs_move_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    "lvs_truncate": (C.c_int, [_vp, C.c_int64]),
     "lvs_snapshot_save": (C.c_int, [_vp, C.c_char_p]),
     "lvs_snapshot_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_vp)]),
     "lvs_search_rank2": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int,

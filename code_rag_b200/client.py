@@ -289,10 +289,34 @@ class _HostCollection:
             self.payloads[r] = None
             self.free_rows.append(r)
 
+    COMPACT_MIN_FREE = 4096          # compaction runs when at least this many rows AND a quarter of the shard are free
+
+    def maybe_compact(self, force: bool = False) -> int:
+        """Move the live rows of the tail into the holes and truncate (after a mass delete - projects/cleanup.py:38-73 drops a
+        whole project - tombstones would otherwise keep costing scan bandwidth).  Returns the number of rows dropped."""
+        nfree, n = len(self.free_rows), len(self.ids)
+        if nfree == 0 or not (force or (nfree >= self.COMPACT_MIN_FREE and 4 * nfree >= n)):
+            return 0
+        m = n - nfree                                        # rows after compaction
+        holes = sorted(r for r in self.free_rows if r < m)
+        tail_live = [r for r in range(m, n) if self.ids[r] is not None]
+        assert len(holes) == len(tail_live)
+        if tail_live:
+            self.dev.move_rows(np.asarray(tail_live, dtype=np.int64) + self.dev.row_base, np.asarray(holes, dtype=np.int64) + self.dev.row_base)
+            for src, dst in zip(tail_live, holes):
+                pid = self.ids[src]
+                self.ids[dst], self.payloads[dst] = pid, self.payloads[src]
+                self.id_to_row[pid] = dst
+        self.dev.truncate(m)
+        del self.ids[m:], self.payloads[m:]
+        self.free_rows = []
+        return nfree
+
     def delete(self, filters: dict[str, Any]) -> int:
         want = self.want_codes(filters)
         rows, n = self.dev.delete_where(want)
         self.release_rows(rows)
+        self.maybe_compact()
         return n
 
     def scroll(self, filters: dict[str, Any] | None, limit: int) -> list[dict[str, Any]]:
@@ -390,6 +414,7 @@ class _ClientShim:
                 if rows:
                     coll.dev.delete_rows(np.asarray(rows, dtype=np.int64))
                     coll.release_rows(rows)
+                    coll.maybe_compact()
                 return len(rows)
         await asyncio.to_thread(work)
         return SimpleNamespace(status="completed")

@@ -174,6 +174,17 @@ class DeviceCollection:
         N.check(self._lib.lvs_delete_rows(self._handle(), _ptr(r), r.shape[0], C.byref(nd)), "lvs_delete_rows")
         return nd.value
 
+    def move_rows(self, src: np.ndarray, dst: np.ndarray) -> None:
+        """Compaction step: row src[i] replaces row dst[i] (all of its device state), src[i] becomes a tombstone."""
+        s_ = np.ascontiguousarray(src, dtype=np.int64)
+        d_ = np.ascontiguousarray(dst, dtype=np.int64)
+        if s_.shape != d_.shape:
+            raise ValueError("src and dst must have the same length")
+        N.check(self._lib.lvs_move_rows(self._handle(), _ptr(s_), _ptr(d_), s_.shape[0]), "lvs_move_rows")
+
+    def truncate(self, n_rows: int) -> None:
+        N.check(self._lib.lvs_truncate(self._handle(), int(n_rows)), "lvs_truncate")
+
     def _want(self, want) -> np.ndarray | None:
         if want is None or self.n_filter_cols == 0:
             return None

@@ -229,6 +229,35 @@ __global__ void set_live_kernel(uint8_t* live, const int64_t* rows, int64_t n, u
     }
 }
 
+// Compaction: row src[i] (vector, tombstone, codes, tie key, write epoch, norm, ranking attributes) replaces row dst[i]; the source
+// row becomes a tombstone.  One warp per pair; the two row sets are disjoint, so the order of the pairs does not matter.
+struct MoveRowsParams {
+    const int64_t* src; const int64_t* dst; int64_t n;
+    uint8_t* vec; uint32_t row_bytes;
+    uint8_t* live; uint32_t* epoch; uint64_t* tie; float* inv_norm;
+    uint32_t* codes[kMaxFilterCols]; int n_cols;
+    uint32_t* rk_key; uint32_t* rk_file; uint32_t* rk_cent; uint32_t* rk_name; int32_t* rk_clen; uint8_t* rk_flags; int64_t rk_rows;
+};
+__global__ void __launch_bounds__(256) move_rows_kernel(const MoveRowsParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = w; i < p.n; i += nw) {
+        const int64_t s = p.src[i], d = p.dst[i];
+        const uint4* sp = reinterpret_cast<const uint4*>(p.vec + (size_t)s * p.row_bytes);
+        uint4* dp = reinterpret_cast<uint4*>(p.vec + (size_t)d * p.row_bytes);
+        for (uint32_t c = lane; c < p.row_bytes / 16; c += 32) dp[c] = sp[c];
+        if (lane < p.n_cols) p.codes[lane][d] = p.codes[lane][s];
+        if (lane == 8) { p.epoch[d] = p.epoch[s]; p.tie[d] = p.tie[s]; p.inv_norm[d] = p.inv_norm[s]; }
+        if (lane == 9 && p.rk_key != nullptr && s < p.rk_rows && d < p.rk_rows) {
+            p.rk_key[d] = p.rk_key[s]; p.rk_file[d] = p.rk_file[s]; p.rk_cent[d] = p.rk_cent[s]; p.rk_name[d] = p.rk_name[s];
+            p.rk_clen[d] = p.rk_clen[s]; p.rk_flags[d] = p.rk_flags[s];
+        }
+        __syncwarp();
+        if (lane == 0) { p.live[d] = p.live[s]; p.live[s] = 0; }
+    }
+}
+
 __global__ void set_codes_kernel(uint32_t* col, const int64_t* rows, int64_t row0, const uint32_t* src, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = rows ? rows[i] : row0 + i;

@@ -548,6 +548,58 @@ extern "C" int lvs_delete_rows(lvs_collection* c, const int64_t* rows, int64_t n
     return LVS_OK;
 }
 
+// Compaction: after a mass delete (projects/cleanup.py:38-73 removes a whole project) the tombstones still cost
+// scan bandwidth; the host moves the live rows of the tail into the holes and truncates.
+extern "C" int lvs_move_rows(lvs_collection* c, const int64_t* src, const int64_t* dst, int64_t n) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n <= 0) return LVS_OK;
+    if (!src || !dst) return fail(LVS_EINVAL, "NULL row list");
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::vector<int64_t> both((size_t)2 * n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t s_ = src[i] - c->row_base, d_ = dst[i] - c->row_base;
+        if (s_ < 0 || s_ >= c->n_rows || d_ < 0 || d_ >= c->n_rows || s_ == d_) return fail(LVS_EINVAL, "move %lld -> %lld is outside the shard", (long long)src[i], (long long)dst[i]);
+        both[i] = s_; both[n + i] = d_;
+    }
+    {   // the two sets must be disjoint and free of repeats (a row moved twice would depend on the order)
+        std::vector<int64_t> chk(both);
+        std::sort(chk.begin(), chk.end());
+        if (std::adjacent_find(chk.begin(), chk.end()) != chk.end()) return fail(LVS_EINVAL, "source and destination rows must be distinct");
+    }
+    int rc = ensure_dev(c->s_stage_dev, (size_t)2 * n * 8);
+    if (rc != LVS_OK) return rc;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->s_stage_dev.p, both.data(), (size_t)2 * n * 8, cudaMemcpyHostToDevice, st));
+    MoveRowsParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = (const int64_t*)c->s_stage_dev.p; p.dst = p.src + n; p.n = n;
+    p.vec = c->d_vec; p.row_bytes = c->row_bytes; p.live = c->d_live; p.epoch = c->d_epoch; p.tie = c->d_tie; p.inv_norm = c->d_inv_norm;
+    for (int i = 0; i < c->n_cols; ++i) p.codes[i] = c->d_codes[i];
+    p.n_cols = c->n_cols;
+    p.rk_key = c->d_rk_key; p.rk_file = c->d_rk_file; p.rk_cent = c->d_rk_cent; p.rk_name = c->d_rk_name; p.rk_clen = c->d_rk_clen;
+    p.rk_flags = c->d_rk_flags; p.rk_rows = c->rk_cap;
+    move_rows_kernel<<<(unsigned)std::min<int64_t>(4096, (n + 7) / 8), 256, 0, st>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return LVS_OK;
+}
+
+extern "C" int lvs_truncate(lvs_collection* c, int64_t n_rows) {
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n_rows < 0 || n_rows > c->n_rows) return fail(LVS_EINVAL, "cannot truncate %lld rows to %lld", (long long)c->n_rows, (long long)n_rows);
+    if (n_rows == c->n_rows) return LVS_OK;
+    // every dropped row must be a tombstone
+    cudaStream_t st = c->stream;
+    const int64_t m = c->n_rows - n_rows;
+    std::vector<uint8_t> lv((size_t)m);
+    CU(cudaMemcpyAsync(lv.data(), c->d_live + n_rows, (size_t)m, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < m; ++i) if (lv[i]) return fail(LVS_ESTATE, "row %lld is still live: move it before truncating", (long long)(c->row_base + n_rows + i));
+    c->n_rows = n_rows;
+    return LVS_OK;
+}
+
 static int build_filter(const lvs_collection* c, const uint32_t* want, const uint32_t** codes, uint32_t* wantv, uint32_t* nf) {
     *nf = 0;
     if (!want) return LVS_OK;

@@ -202,6 +202,13 @@ int lvs_search_rank2(lvs_collection* c, lvs_collection* c2, const void* queries,
                      int32_t* out_count, int32_t* out_index, double* out_score, double* out_signals, uint8_t* out_sigmask,
                      uint8_t* out_source, int32_t* out_leader, float* device_ms);
 
+/* ---- compaction: after a mass delete (projects/cleanup.py:38-73 removes a whole project) tombstones still
+ *      cost scan bandwidth.  lvs_move_rows copies row src[i] (vector, tombstone, codes, tie key, write epoch, norm, ranking
+ *      attributes) over row dst[i] and turns src[i] into a tombstone (GLOBAL rows; the two sets are disjoint); lvs_truncate then
+ *      drops the trailing rows, which must all be tombstones.  Search results do not depend on where a row lives. */
+int lvs_move_rows(lvs_collection* c, const int64_t* src, const int64_t* dst, int64_t n);
+int lvs_truncate(lvs_collection* c, int64_t n_rows);
+
 /* ---- snapshots: the shard's device arrays (vectors, tombstones, codes, tie keys, write epochs,
  *      norms, search counter, ranking attributes and name pool) to / from one file, so that an index survives a restart the
  *      way the Qdrant volume does (reference docker-compose.yml:42-43).  A loaded shard answers every search exactly as the

@@ -241,3 +241,47 @@ async def scenario_reindex_churn(factory, n_files=40, chunks=6, dim=48, rounds=1
     _same_hits(await store.search(collection=CODE, query_vector=None, limit=50, filters={"project_name": "p"}),
                ora.search(CODE, None, limit=50, filters={"project_name": "p"}), what="scroll after churn")
     await store.close()
+
+
+async def scenario_mass_delete_compacts(factory, n=2400, dim=48):
+    """projects/cleanup.py:38-73 removes a whole project: the shard is compacted (live rows of the tail move into the holes, the
+    rest is truncated) and keeps answering like the oracle - with filters, after further upserts, and for ids that come back."""
+    from types import SimpleNamespace as NS
+    x, q = synth.unixcoder_like(n, dim, seed=606, n_queries=6)
+    pl = synth.payloads(n, seed=607)
+    for i, p in enumerate(pl):
+        p["project_name"] = ("alpha", "beta", "gamma")[i % 3]
+    ids = synth.random_uuids(n, seed=608)
+    store = B200VectorStore(dimensions=dim, _device_factory=factory)
+    ora = OracleManager(dim)
+    await store.connect(); await store.create_collections(); ora.create_collections()
+    vecs = x.astype(np.float64).tolist()
+    await store.upsert(collection=CODE, ids=ids[:2000], vectors=vecs[:2000], payloads=pl[:2000])
+    ora.upsert(CODE, ids[:2000], vecs[:2000], pl[:2000])
+    coll = store._get(CODE)
+    coll.COMPACT_MIN_FREE = 100                        # small shard: let the quarter rule decide
+    _same_hits(await store.search(collection=CODE, query_vector=q[0].tolist(), limit=8), ora.search(CODE, q[0].tolist(), limit=8), what="before")
+    # the reference's cleanup goes through manager.client.delete with a models.Filter (duck-typed here)
+    flt = NS(must=[NS(key="project_name", match=NS(value="beta"))])
+    await store.client.delete(collection_name=CODE, points_selector=NS(filter=flt))
+    ora.delete(CODE, {"project_name": "beta"})
+    n_left = ora.points_count(CODE)
+    assert coll.dev.rows == n_left == len(coll.ids), "a third of the shard was deleted: it must have been compacted"
+    assert not coll.free_rows and all(i is not None for i in coll.ids)
+    for qi in range(1, 4):
+        for f in (None, {"project_name": "gamma"}, {"project_name": "beta"}, {"language": pl[1]["language"]}):
+            _same_hits(await store.search(collection=CODE, query_vector=q[qi].tolist(), limit=8, filters=f),
+                       ora.search(CODE, q[qi].tolist(), limit=8, filters=f), what=f"after compaction q{qi} {f}")
+    # new points, a deleted id that comes back, an overwrite of a moved point
+    await store.upsert(collection=CODE, ids=ids[2000:], vectors=vecs[2000:], payloads=pl[2000:]); ora.upsert(CODE, ids[2000:], vecs[2000:], pl[2000:])
+    back = next(i for i in range(2000) if pl[i]["project_name"] == "beta")
+    moved = max(range(2000), key=lambda i: coll.id_to_row.get(str(__import__("uuid").UUID(ids[i])), -1) if pl[i]["project_name"] != "beta" else -1)
+    for i in (back, moved):
+        await store.upsert(collection=CODE, ids=[ids[i]], vectors=[vecs[(i + 7) % n]], payloads=[dict(pl[i], language="go")])
+        ora.upsert(CODE, [ids[i]], [vecs[(i + 7) % n]], [dict(pl[i], language="go")])
+    for qi in range(4, 6):
+        for f in (None, {"language": "go"}, {"project_name": "alpha"}):
+            _same_hits(await store.search(collection=CODE, query_vector=q[qi].tolist(), limit=8, filters=f),
+                       ora.search(CODE, q[qi].tolist(), limit=8, filters=f), what=f"after upserts q{qi} {f}")
+    assert (await store.get_collection_info(CODE)).points_count == ora.points_count(CODE)
+    await store.close()

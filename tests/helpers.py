@@ -76,6 +76,25 @@ class FakeDevice:
         self.ora.deleted[rows] = True
         return rows[: (n if cap is None else cap)], n
 
+    def move_rows(self, src, dst):
+        for s_, d_ in zip(np.asarray(src).tolist(), np.asarray(dst).tolist()):
+            self.ora.vectors[d_] = self.ora.vectors[s_]
+            self.ora.deleted[d_] = self.ora.deleted[s_]
+            self.ora.deleted[s_] = True
+            self.codes[d_] = self.codes[s_]
+            self.ties[d_] = self.ties[s_]
+
+    def truncate(self, n):
+        assert self.ora.deleted[n:self.rows].all()
+        for i in range(n, self.rows):
+            self.ora.ids.pop(i, None)
+        del self.ora.payload[n:], self.ora.ids_inv[n:]
+        self.codes, self.ties = self.codes[:n], self.ties[:n]
+
+    @property
+    def row_base(self):
+        return 0
+
     def delete_rows(self, rows):
         rows = np.asarray(rows)
         live = ~self.ora.deleted[rows]

@@ -23,3 +23,7 @@ def test_client_shim_matchtext():
 
 def test_reindex_churn_reuses_rows():
     asyncio.run(S.scenario_reindex_churn(FakeDevice))
+
+
+def test_mass_delete_compacts():
+    asyncio.run(S.scenario_mass_delete_compacts(FakeDevice))

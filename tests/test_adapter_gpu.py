@@ -28,6 +28,10 @@ def test_reindex_churn_reuses_rows(native_lib):
     asyncio.run(S.scenario_reindex_churn(None))
 
 
+def test_mass_delete_compacts(native_lib):
+    asyncio.run(S.scenario_mass_delete_compacts(None))
+
+
 def test_snapshot_restore_continues_exactly(native_lib, tmp_path):
     """a saved store, loaded into a fresh process state, answers every later search (filters, deletes,
     upserts included) exactly as the original does - scores bit for bit, because the local-mode replay state (search counter,

@@ -245,3 +245,39 @@ def test_fused_with_summaries_extension(native_lib):
             assert n_summary > 0, "summary hits should reach the ranked lists"
         await a.close(); await b.close()
     asyncio.run(run())
+
+
+def test_fused_after_compaction(native_lib):
+    """A mass delete compacts the shard (rows move): the per-row ranking attributes and the name ids must move with them."""
+    from code_rag_b200.client import B200VectorStore
+    from code_rag_b200.ranking import HybridRanker
+    rng = random.Random(9)
+    n, dim = 2100, 64
+    x, q = synth.unit_rows(n, dim, seed=44, n_queries=8)
+    pl = _payloads(rng, n)
+    for i, p in enumerate(pl):
+        p["project_name"] = ("a", "b", "c")[i % 3]
+    ids = [str(__import__("uuid").UUID(int=i + 1)) for i in range(n)]
+
+    async def run():
+        stores = [B200VectorStore(dimensions=dim, rank_attrs=True) for _ in range(2)]
+        for st in stores:
+            await st.connect(); await st.create_collections()
+            st._get("code_chunks").COMPACT_MIN_FREE = 100
+            await st.upsert("code_chunks", ids, x.astype(np.float64).tolist(), pl)
+            await st.delete("code_chunks", {"project_name": "b"})
+            coll = st._get("code_chunks")
+            assert coll.dev.rows == len(coll.ids) == n - n // 3 and not coll.free_rows
+        a, b = stores
+        items = [_case(rng, [p for p in pl if p["project_name"] != "b"], i, q[i].astype(np.float64)) for i in range(8)]
+        ranker = HybridRanker()
+        fused = await a.search_and_rank("code_chunks", items, limit=15, ranker=ranker)
+        coll = b._get("code_chunks")
+        hits = await b.search_batch("code_chunks", [it[2] for it in items], limit=15)
+        assert all(h["payload"]["project_name"] != "b" for hs in hits for h in hs)
+        two = ranker.rank_batch([(it[0], it[1], [coll.vector_result_from_hit(h) for h in hits[i]], it[3]) for i, it in enumerate(items)])
+        for fa, fb in zip(fused, two):
+            _same(fa, fb)
+        for st in stores:
+            await st.close()
+    asyncio.run(run())
