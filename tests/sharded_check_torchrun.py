@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU correctness check of the sharded path (run under torchrun, one rank per GPU):
-    torchrun --nproc-per-node N benchmarks/sharded_check.py
+    torchrun --nproc-per-node N tests/sharded_check_torchrun.py
 Every rank holds a contiguous row shard; results of ShardedSearcher (device async, sync and host submit/wait paths, Q = 1 and
 batched) must equal the CPU oracle over the whole corpus, for both exchange modes."""
 import os
@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
+sys.path[:0] = [str(ROOT), str(ROOT / "tests")]   # a checker (it uses the oracle), hence under tests/; not collected by pytest
 
 import lvs_synth as synth  # noqa: E402
 from code_rag_b200.collection import DeviceCollection  # noqa: E402
