@@ -150,3 +150,40 @@ def test_random_operation_sequences_match_the_oracle(native_lib, seed, storage):
         assert coll.dev.rows == len(coll.ids) <= n_ids
         await store.close()
     asyncio.run(run())
+
+
+def test_committed_search_golden_through_the_device(native_lib):
+    """tests/golden/search_oracle_golden.json (frozen outputs of the search oracle: ids, float64 scores, drift between repeated
+    searches, filters, scroll order, overwrite, delete) replayed through B200VectorStore on the GPU."""
+    import json
+    from pathlib import Path
+
+    from code_rag_b200.client import B200VectorStore
+    G = json.loads((Path(__file__).parent / "golden" / "search_oracle_golden.json").read_text())
+    fh = float.fromhex
+
+    async def run():
+        x = [[fh(v) for v in row] for row in G["x"]]
+        q = [[fh(v) for v in row] for row in G["q"]]
+        ids, pl = G["ids"], G["payloads"]
+        st = B200VectorStore(dimensions=G["dim"])
+        await st.connect(); await st.create_collections()
+        await st.upsert("code_chunks", ids[:250], x[:250], pl[:250])
+        for s in G["steps"]:
+            if s["op"] == "search":
+                hits = await st.search("code_chunks", None if s["query"] is None else q[s["query"]], limit=s["limit"], filters=s["filters"])
+                assert [h["id"] for h in hits] == s["ids"], s
+                exp = [fh(v) for v in s["scores"]]
+                assert all(abs(h["score"] - e) <= 1e-5 * abs(e) for h, e in zip(hits, exp))            # the bar for fp32 storage
+                assert all(abs(h["score"] - e) <= 1e-12 for h, e in zip(hits, exp)), [h["score"] - e for h, e in zip(hits, exp)]
+            elif s["op"] == "delete":
+                await st.delete("code_chunks", s["filters"])
+            elif s["op"] == "upsert":
+                await st.upsert("code_chunks", ids[s["lo"]:s["hi"]], x[s["lo"]:s["hi"]], pl[s["lo"]:s["hi"]])
+            elif s["op"] == "overwrite":
+                await st.upsert("code_chunks", [ids[i] for i in s["ids"]], [x[i] for i in s["vectors"]],
+                                [dict(pl[i], language=s["language"]) for i in s["ids"]])
+            elif s["op"] == "count":
+                assert (await st.get_collection_info("code_chunks")).points_count == s["value"]
+        await st.close()
+    asyncio.run(run())
