@@ -187,3 +187,55 @@ def test_committed_search_golden_through_the_device(native_lib):
                 assert (await st.get_collection_info("code_chunks")).points_count == s["value"]
         await st.close()
     asyncio.run(run())
+
+
+def test_no_device_memory_growth_under_churn(native_lib):
+    """Soak: many rounds of upsert / delete (with row reuse and compaction) / batched search / fused search+rank / snapshot-free
+    operations must not leak device memory (scratch is reused, re-grown arrays free their predecessors)."""
+    import ctypes as C
+    import random
+    import uuid
+    from types import SimpleNamespace as NS
+
+    import numpy as np
+
+    from code_rag_b200 import _native as N
+    from code_rag_b200.client import B200VectorStore
+
+    def free_bytes():
+        f = C.c_int64()
+        N.check(N.load().lvs_device_info(None, None, None, None, C.byref(f)), "lvs_device_info")
+        return f.value
+
+    async def run():
+        dim = 64
+        st = B200VectorStore(dimensions=dim, storage="bf16", rank_attrs=True)
+        await st.connect(); await st.create_collections()
+        st._get("code_chunks").COMPACT_MIN_FREE = 64
+        rng = random.Random(1)
+        nprng = np.random.default_rng(1)
+        empty = NS(primary_entities=[], callers=[], callees=[], methods=[], parent_classes=[], child_classes=[])
+        plan = NS(primary_intent=NS(value="find_similar"), entities=[NS(name="fn")])
+
+        async def one_round(r):
+            ids = [str(uuid.UUID(int=rng.getrandbits(100))) for _ in range(200)]
+            vecs = nprng.standard_normal((200, dim)).astype(np.float32).astype(np.float64).tolist()
+            pl = [{"file_path": f"f{(r * 7 + i) % 40}.py", "entity_name": f"fn{i}", "entity_type": "function", "language": "python",
+                   "content": "x" * (i + 1), "start_line": i, "end_line": i + 1, "project_name": f"p{r % 3}", "graph_node_id": None} for i in range(200)]
+            await st.upsert("code_chunks", ids, vecs, pl)
+            await st.delete("code_chunks", {"file_path": f"f{rng.randrange(40)}.py"})
+            if r % 5 == 4:
+                await st.delete("code_chunks", {"project_name": f"p{rng.randrange(3)}"})
+            q = nprng.standard_normal((6, dim))
+            await st.search_batch("code_chunks", q.tolist(), limit=10)
+            await st.search("code_chunks", q[0].tolist(), limit=5, filters={"project_name": "p1"})
+            await st.search_and_rank("code_chunks", [(plan, empty, q[i], {}) for i in range(3)], limit=8)
+        for r in range(40):                 # warm-up: scratch buffers and columns reach their working size
+            await one_round(r)
+        before = free_bytes()
+        for r in range(40, 240):
+            await one_round(r)
+        after = free_bytes()
+        await st.close()
+        assert before - after < (96 << 20), f"device memory fell by {(before - after) / 2**20:.1f} MiB over 200 rounds"
+    asyncio.run(run())
