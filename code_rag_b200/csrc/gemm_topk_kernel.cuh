@@ -77,7 +77,8 @@ struct GemmParams {
     uint32_t keep;               // keys kept per list (<= 16): fewer keys = fewer inserts but a weaker drop bound
     uint32_t unit_rows;          // every stored row has | ||row|| - 1 | <= 2^-9: clean tiles skip the 1/||row|| scaling
     uint32_t dbg_mode;           // profiling aid: bit0 skip the epilogue's scoring, bit1 skip the MMA issue, bit2 skip tcgen05.ld,
-                                 // bit3 (pair form) stop re-loading the query chunks after the first pipeline fill
+                                 // bit3 (pair form) stop re-loading the query chunks after the first pipeline fill, bit4 no loads at all
+                                 // after the first fill (MMA + epilogue hand-off alone)
 };
 
 // shared memory: [stages][lists 8 warps * 16 keys * 32 lanes * 8][score columns 8 * 32 * 32 * 4][thr 128*4][inv 8*128*4][barriers]
@@ -215,6 +216,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
                     const uint32_t s = it % S;
                     mbar_wait(&empty_bar[s], ((it / S) & 1u) ^ 1u);
                     uint8_t* st = stages + (size_t)s * kStageBytes;
+                    if ((p.dbg_mode & 16u) != 0u && it >= S) {                       // profiling aid: no loads at all after the first fill
+                        if (rank == 0) mbar_arrive(&full_bar[s]);                   // (stale operands, timing only)
+                        continue;
+                    }
                     if constexpr (PAIR) {
                         // the leader's barrier counts the bytes of both CTAs
                         const bool skip_a = (p.dbg_mode & 8u) != 0u && it >= S;      // profiling aid: stale query chunks, timing only
