@@ -281,3 +281,31 @@ def test_fused_after_compaction(native_lib):
         for st in stores:
             await st.close()
     asyncio.run(run())
+
+
+def test_fused_with_an_empty_summaries_collection(native_lib):
+    """summaries=True while nothing has been indexed into `summaries` yet: same result as without the extension."""
+    from code_rag_b200.client import B200VectorStore
+    rng = random.Random(5)
+    n, dim = 900, 64
+    x, q = synth.unit_rows(n, dim, seed=3, n_queries=4)
+    pl = _payloads(rng, n)
+    ids = [str(__import__("uuid").UUID(int=i + 1)) for i in range(n)]
+
+    async def run():
+        a = B200VectorStore(dimensions=dim, rank_attrs=True)
+        b = B200VectorStore(dimensions=dim, rank_attrs=True)
+        for st in (a, b):
+            await st.connect(); await st.create_collections()
+            await st.upsert("code_chunks", ids, x.astype(np.float64).tolist(), pl)
+        items = []
+        for i in range(4):
+            plan, ctx, qv, cent = _case(rng, pl, i, q[i].astype(np.float64))
+            plan.primary_intent = NS(value="explain_architecture")
+            items.append((plan, ctx, qv, cent))
+        fa = await a.search_and_rank("code_chunks", items, limit=9, summaries=True)
+        fb = await b.search_and_rank("code_chunks", items, limit=9, summaries=False)
+        for ra, rb in zip(fa, fb):
+            _same(ra, rb)
+        await a.close(); await b.close()
+    asyncio.run(run())
