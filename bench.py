@@ -362,6 +362,14 @@ def run_ours(args) -> None:
                 traffic = int(tj["dram_bytes_per_launch"] * (algo_bytes / tj["algorithmic_bytes_per_launch"]))
             except Exception:
                 traffic = None
+        gf = ROOT / "profiles" / "gemm_traffic.json"
+        if tensor_path and gf.exists():
+            try:   # ncu capture of the tensor-core kernel on a 15.36 GB shard; other shard sizes scale with the rows read
+                gj = json.loads(gf.read_text())
+                key = ("pair_q256_bf16" if Q > 128 else "single_q128_bf16") if args.storage == "bf16" else "single_q128_tf32"
+                traffic = int(gj["dram_bytes_per_launch"][key] * (algo_bytes / gj["algorithmic_bytes_per_launch"]))
+            except Exception:
+                traffic = None
         roof = {"bound": "hbm", "kernel": "gemm_topk_kernel" if tensor_path else "scan_topk_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": scan_mean,
@@ -370,7 +378,7 @@ def run_ours(args) -> None:
             tpeak = float(peaks.get("bf16_tflops", 1649.5)) * (1.0 if args.storage == "bf16" else 0.5)
             tfl = 2.0 * min(Q, 256) * n_local * args.dim / (scan_mean * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
-                    "traffic": None, "algorithmic_flops_per_launch": 2.0 * min(Q, 256) * n_local * args.dim, "kernel_ms": scan_mean,
+                    "traffic": traffic, "algorithmic_flops_per_launch": 2.0 * min(Q, 256) * n_local * args.dim, "kernel_ms": scan_mean,
                     "hbm_gbs_over_algorithmic_bytes": achieved,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops burst" if peaks else "fallback 1649.5 TFLOP/s") +
                                    ("" if args.storage == "bf16" else " x 0.5 (tf32)")}
