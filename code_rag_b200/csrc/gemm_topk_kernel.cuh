@@ -1,7 +1,7 @@
 // K2 - tensor-core path for batched queries (regime 2 of BASELINE.json north_star): tcgen05.mma with the accumulators
 // in TMEM, operands fed by TMA, top-k selection fused into the epilogue.
 //
-// Replaces, for Q >= 8 queries at a time, the O(Q*N*D) loop that the reference delegates to Qdrant behind
+// Replaces, for batches of queries (from 3 on bf16 shards, from 5 on fp32 ones), the O(Q*N*D) loop that the reference delegates to Qdrant behind
 // QdrantManager.search (reference src/lattice/embeddings/client.py:132-157) - there one gRPC call per query.
 //
 // Orientation: D[queries x 256 corpus rows] += A[queries x K] * B[256 x K]^T, fp32 accumulate.  bf16 shards use kind::f16
@@ -13,7 +13,7 @@
 //     single-CTA MMA (128 cycles).  A pipeline stage = one 64-wide K chunk of BOTH operands, K-major with 128-byte
 //     swizzle: the corpus tile B[256 rows x 64] (32 KB, from HBM) and the matching chunk of the CTA's 128 unit-norm
 //     bf16 queries A[128 x 64] (16 KB, L2-resident).  3 stages.  For 128 < Q <= 256 two CTAs would walk the same
-//     tiles, and every CTA pulls 576 KB per tile through L2 -> SM (above the ~42 B/clk/SM the L2 can deliver), so:
+//     tiles and every CTA would pull 576 KB per tile through L2 -> SM, so:
 //   * PAIR = true (128 < Q <= 256): a CLUSTER OF TWO CTAs (one TPC) issues tcgen05.mma.cta_group::2 with M = 256
 //     (128 queries in each CTA's TMEM), N = 256.  Each CTA loads only ITS half of the corpus tile (128 rows x 64,
 //     16 KB) plus its own 128 queries' chunk (16 KB); the tensor cores read the other half from the peer's shared
@@ -24,7 +24,8 @@
 //   * D is double buffered: 2 x 256 TMEM columns, so the MMAs of tile t+1 overlap the epilogue of tile t.
 //   * Epilogue (8 warps; thread = query = TMEM lane; the two warps of a lane quarter split the 256 columns):
 //     tcgen05.ld 32 columns, (scale by 1/||row|| unless the shard is unit-norm and the tile clean; NaN for tombstones,
-//     rows that fail the payload filter and rows past the end, and NaN never passes), then a NaN-ignoring MAX TREE over the 32 scores and ONE vote:
+//     rows that fail the payload filter and rows past the end, and NaN never passes), then a NaN-ignoring MAX TREE over
+//     the 32 scores and ONE vote:
 //     if no query of the warp has a score above its current threshold (the common case once the lists have warmed
 //     up) the block costs ~40 instructions.  Otherwise every lane builds the bit mask of its passing columns, the
 //     passing lanes park their 32 scores in a shared-memory column (so that they can be indexed) and ALL LANES INSERT
@@ -34,8 +35,9 @@
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane) + TMEM allocation,
 // warps 2..9 = epilogue (TMEM lane quarter = warp % 4).
 //
-// Exactness: lists hold up to 32 keys per (CTA, column half, query); the finalize kernel proves the result against the
-// bound max(k'-th kept fast score, largest dropped score) + eps_q and the host repeats flagged queries on the K1 path.
+// Exactness: lists hold up to 16 keys per (CTA, column half, query) and record the threshold below which they dropped
+// scores; the finalize kernel proves the result against the bound max(k'-th kept fast score, largest drop bound) + eps_q and
+// the host repeats flagged queries on the K1 path.
 // Algorithmic bytes per launch = rows x row_bytes; FLOPs = 2 * Q * rows * K.
 #pragma once
 #include <cuda.h>
