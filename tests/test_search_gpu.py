@@ -358,7 +358,7 @@ def test_f32_storage_large_batch_uses_scan_passes(lib):
 
 
 def test_gemm_falls_back_when_bound_fails(lib):
-    """Near-duplicate rows concentrated in one tile defeat the 32-key lists: flagged queries are redone on the K1 path."""
+    """Near-duplicate rows concentrated in one tile defeat the 16-key lists: flagged queries are redone on the K1 path."""
     n = 16_384
     x, q = synth.unit_rows(n, 768, seed=11, n_queries=8)
     rng = np.random.default_rng(3)
