@@ -58,6 +58,15 @@ struct LibState {
 static LibState g_lib;
 static std::mutex g_lib_mu;
 
+// The CUDA device is a per-thread setting and the adapter calls in from worker threads (asyncio.to_thread): every entry point
+// that touches CUDA first makes the calling thread current on the device lvs_init bound this process to.
+static thread_local int t_bound_device = -1;
+static inline void bind_thread() {
+    if (g_lib.ready && t_bound_device != g_lib.device) {
+        if (cudaSetDevice(g_lib.device) == cudaSuccess) t_bound_device = g_lib.device;
+    }
+}
+
 struct Scratch {
     void* p = nullptr;
     size_t bytes = 0;
@@ -218,6 +227,7 @@ extern "C" int lvs_init(int device) {
     g_lib.cc_minor = prop.minor;
     g_lib.smem_optin = prop.sharedMemPerBlockOptin;
     g_lib.ready = true;
+    t_bound_device = device;
     return LVS_OK;
 }
 
@@ -228,6 +238,7 @@ extern "C" int lvs_shutdown(void) {
 }
 
 extern "C" int lvs_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem, int64_t* free_mem) {
+    bind_thread();
     if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called");
     size_t f = 0, t = 0;
     CU(cudaMemGetInfo(&f, &t));
@@ -289,6 +300,7 @@ static int grow_to(lvs_collection* c, int64_t new_cap) {
 
 extern "C" int lvs_collection_create(const char* name, int dim, int storage, int metric, int n_filter_cols,
                                      int64_t capacity_rows, int64_t row_base, lvs_collection** out) {
+    bind_thread();
     if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
     if (!out) return fail(LVS_EINVAL, "out is NULL");
     *out = nullptr;
@@ -331,6 +343,7 @@ extern "C" int lvs_collection_create(const char* name, int dim, int storage, int
 }
 
 extern "C" int lvs_collection_destroy(lvs_collection* c) {
+    bind_thread();
     if (!c) return LVS_OK;
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_rk_key); cudaFree(c->d_rk_file); cudaFree(c->d_rk_cent); cudaFree(c->d_rk_name); cudaFree(c->d_rk_clen);
@@ -359,14 +372,18 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
 }
 
 extern "C" int lvs_collection_reserve(lvs_collection* c, int64_t capacity_rows) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     return grow_to(c, capacity_rows);
 }
 
-extern "C" int64_t lvs_rows(const lvs_collection* c) { return c ? c->n_rows : 0; }
-extern "C" int64_t lvs_capacity(const lvs_collection* c) { return c ? c->capacity : 0; }
-extern "C" uint32_t lvs_search_counter(const lvs_collection* c) { return c ? c->search_counter : 0; }
+extern "C" int64_t lvs_rows(const lvs_collection* c) {
+    bind_thread(); return c ? c->n_rows : 0; }
+extern "C" int64_t lvs_capacity(const lvs_collection* c) {
+    bind_thread(); return c ? c->capacity : 0; }
+extern "C" uint32_t lvs_search_counter(const lvs_collection* c) {
+    bind_thread(); return c ? c->search_counter : 0; }
 
 __global__ void count_live_kernel(const uint8_t* live, uint32_t n, unsigned long long* out) {
     unsigned long long acc = 0;
@@ -376,6 +393,7 @@ __global__ void count_live_kernel(const uint8_t* live, uint32_t n, unsigned long
 }
 
 extern "C" int64_t lvs_count(const lvs_collection* cc) {
+    bind_thread();
     lvs_collection* c = const_cast<lvs_collection*>(cc);
     if (!c) return 0;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -412,6 +430,7 @@ static int launch_upsert(lvs_collection* c, const void* d_src, int dtype, int64_
 
 extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_t n, const int64_t* rows,
                           const uint32_t* codes, const uint64_t* ties) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n < 0 || (n > 0 && !vecs)) return fail(LVS_EINVAL, "bad vecs / n");
     if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64 && dtype != LVS_DT_BF16) return fail(LVS_EINVAL, "unknown dtype %d", dtype);
@@ -471,6 +490,7 @@ extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_
 
 extern "C" int lvs_upsert_device(lvs_collection* c, const void* d_vecs, int dtype, int64_t n, int64_t row0,
                                  const uint32_t* d_codes, const uint64_t* d_ties, void* stream) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n < 0 || (n > 0 && !d_vecs)) return fail(LVS_EINVAL, "bad d_vecs / n");
     if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64 && dtype != LVS_DT_BF16) return fail(LVS_EINVAL, "unknown dtype %d", dtype);
@@ -493,6 +513,7 @@ extern "C" int lvs_upsert_device(lvs_collection* c, const void* d_vecs, int dtyp
 }
 
 extern "C" int lvs_set_codes(lvs_collection* c, int col, const int64_t* rows, int64_t row0, int64_t n, const uint32_t* codes) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (col < 0 || col >= c->n_cols) return fail(LVS_EINVAL, "filter column %d outside 0..%d", col, c->n_cols - 1);
     if (n <= 0) return LVS_OK;
@@ -526,6 +547,7 @@ extern "C" int lvs_set_codes(lvs_collection* c, int col, const int64_t* rows, in
 // delete / match
 // ------------------------------------------------------------------------------------------------------
 extern "C" int lvs_delete_rows(lvs_collection* c, const int64_t* rows, int64_t n, int64_t* n_deleted) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n_deleted) *n_deleted = 0;
     if (n <= 0) return LVS_OK;
@@ -551,6 +573,7 @@ extern "C" int lvs_delete_rows(lvs_collection* c, const int64_t* rows, int64_t n
 // Compaction: after a mass delete (projects/cleanup.py:38-73 removes a whole project) the tombstones still cost
 // scan bandwidth; the host moves the live rows of the tail into the holes and truncates.
 extern "C" int lvs_move_rows(lvs_collection* c, const int64_t* src, const int64_t* dst, int64_t n) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n <= 0) return LVS_OK;
     if (!src || !dst) return fail(LVS_EINVAL, "NULL row list");
@@ -585,6 +608,7 @@ extern "C" int lvs_move_rows(lvs_collection* c, const int64_t* src, const int64_
 }
 
 extern "C" int lvs_truncate(lvs_collection* c, int64_t n_rows) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     if (n_rows < 0 || n_rows > c->n_rows) return fail(LVS_EINVAL, "cannot truncate %lld rows to %lld", (long long)c->n_rows, (long long)n_rows);
@@ -640,9 +664,11 @@ static int match_impl(lvs_collection* c, const uint32_t* want, int64_t* out_rows
 }
 
 extern "C" int lvs_delete_where(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched) {
+    bind_thread();
     return match_impl(c, want, out_rows, cap, n_matched, 1);
 }
 extern "C" int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* out_rows, int64_t cap, int64_t* n_matched) {
+    bind_thread();
     return match_impl(c, want, out_rows, cap, n_matched, 0);
 }
 
@@ -1094,6 +1120,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
 extern "C" int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                                  double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                                  int32_t* out_flags, void* stream) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (Q < 0 || (Q > 0 && (!d_queries || !d_out_scores || !d_out_rows || !d_out_ties || !d_out_counts)))
         return fail(LVS_EINVAL, "NULL device buffer");
@@ -1106,6 +1133,7 @@ extern "C" int lvs_search_device(lvs_collection* c, const void* d_queries, int d
 extern "C" int lvs_search_device_async(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                                        double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                                        int32_t* d_out_flags, void* stream) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (Q < 0 || (Q > 0 && (!d_queries || !d_out_scores || !d_out_rows || !d_out_ties || !d_out_counts || !d_out_flags)))
         return fail(LVS_EINVAL, "NULL device buffer");
@@ -1190,6 +1218,7 @@ static int check_search_args(const lvs_collection* c, const void* queries, int d
 }
 
 extern "C" int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket) {
+    bind_thread();
     if (!ticket) return fail(LVS_EINVAL, "ticket is NULL");
     int rc = check_search_args(c, queries, dtype, Q, k);
     if (rc != LVS_OK) return rc;
@@ -1200,6 +1229,7 @@ extern "C" int lvs_search_submit(lvs_collection* c, const void* queries, int dty
 
 extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
                                uint32_t* out_counts, int32_t* out_flags) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (ticket < 0 || ticket >= kSubmitSlots) return fail(LVS_EINVAL, "bad ticket %d", ticket);
     cudaEvent_t done;
@@ -1215,6 +1245,7 @@ extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores
 
 extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
                           double* out_scores, int64_t* out_rows, uint64_t* out_ties, uint32_t* out_counts, int32_t* out_flags) {
+    bind_thread();
     int rc = check_search_args(c, queries, dtype, Q, k);
     if (rc != LVS_OK) return rc;
     if (Q == 0) return LVS_OK;
@@ -1234,6 +1265,7 @@ extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int
 }
 
 extern "C" int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n) {
+    bind_thread();
     if (!c || !out_ms || !n) return fail(LVS_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     const uint64_t have = std::min<uint64_t>(c->ring_pos, (uint64_t)kEventRing);
@@ -1253,6 +1285,7 @@ extern "C" int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, doubl
 extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const uint64_t* d_ties, int64_t shard_stride,
                                      int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                                      void* stream) {
+    bind_thread();
     if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called");
     if (G < 1 || Q < 0 || k < 1) return fail(LVS_EINVAL, "bad G / Q / k");
     if (Q == 0) return LVS_OK;
@@ -1286,6 +1319,7 @@ struct lvs_exchange {
 };
 
 extern "C" int lvs_exchange_create(int world, int rank, int max_q, int max_k, lvs_exchange** out, void* ipc_handle_out) {
+    bind_thread();
     if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
     if (!out || !ipc_handle_out) return fail(LVS_EINVAL, "NULL argument");
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(LVS_EINVAL, "bad world / rank");
@@ -1312,6 +1346,7 @@ extern "C" int lvs_exchange_create(int world, int rank, int max_q, int max_k, lv
 }
 
 extern "C" int lvs_exchange_connect(lvs_exchange* ex, const void* all_handles) {
+    bind_thread();
     if (!ex || !all_handles) return fail(LVS_EINVAL, "NULL argument");
     for (int r = 0; r < ex->world; ++r) {
         if (r == ex->rank) continue;
@@ -1329,6 +1364,7 @@ extern "C" int lvs_exchange_connect(lvs_exchange* ex, const void* all_handles) {
 
 extern "C" int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, int Q, int k, int64_t* d_out, uint32_t* d_out_counts,
                                          void* stream) {
+    bind_thread();
     if (!ex || !d_local || !d_out || !d_out_counts) return fail(LVS_EINVAL, "NULL argument");
     if (!ex->connected && ex->world > 1) return fail(LVS_ESTATE, "lvs_exchange_connect() has not been called");
     if (Q < 1 || k < 1 || (size_t)3 * Q * k > ex->blk_stride) return fail(LVS_ELIMIT, "Q x k = %d x %d exceeds the exchange buffer (%d x %d)", Q, k, ex->max_q, ex->max_k);
@@ -1355,6 +1391,7 @@ extern "C" int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_loca
 }
 
 extern "C" int lvs_exchange_error(lvs_exchange* ex) {
+    bind_thread();
     if (!ex) return 0;
     uint32_t h = 0;
     if (cudaMemcpy(&h, ex->d_counter + 1, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
@@ -1362,6 +1399,7 @@ extern "C" int lvs_exchange_error(lvs_exchange* ex) {
 }
 
 extern "C" int lvs_exchange_destroy(lvs_exchange* ex) {
+    bind_thread();
     if (!ex) return LVS_OK;
     cudaDeviceSynchronize();
     for (int r = 0; r < kMaxRanks; ++r) if (ex->opened[r] && ex->peers[r]) cudaIpcCloseMemHandle(ex->peers[r]);
@@ -1381,6 +1419,7 @@ static cudaEvent_t g_rank_ev[2] = {nullptr, nullptr};
 extern "C" int lvs_rank_fuse(const lvs_rank_batch* in, int mode, int max_per_file, int max_total, double entity_bonus, double rel_bonus,
                              int32_t* out_count, int32_t* out_index, double* out_score, double* out_norm, double* out_signals,
                              uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+    bind_thread();
     if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
     if (!in || !in->offsets) return fail(LVS_EINVAL, "NULL batch");
     if (mode != 0 && mode != 1) return fail(LVS_EINVAL, "mode must be 0 (HybridRanker) or 1 (ResultReranker)");
@@ -1498,6 +1537,7 @@ static int regrow(T*& ptr, int64_t old_n, int64_t new_n, cudaStream_t st, int fi
 }
 
 extern "C" int lvs_rank_names_append(lvs_collection* c, const uint8_t* bytes, const uint32_t* lens, int n, uint32_t* first_id) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n < 0 || (n > 0 && !lens)) return fail(LVS_EINVAL, "bad name batch");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1533,6 +1573,7 @@ extern "C" int lvs_rank_names_append(lvs_collection* c, const uint8_t* bytes, co
 
 extern "C" int lvs_rank_attrs_set(lvs_collection* c, const int64_t* rows, int n, const uint32_t* key_id, const uint32_t* file_id,
                                   const uint32_t* cent_id, const uint32_t* name_id, const int32_t* content_len, const uint8_t* flags) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n < 0) return fail(LVS_EINVAL, "bad n");
     if (n == 0) return LVS_OK;
@@ -1593,6 +1634,7 @@ extern "C" int lvs_search_rank2(lvs_collection* c, lvs_collection* c2, const voi
                                 double entity_bonus, double rel_bonus, const lvs_rank_hits* hits1, const lvs_rank_hits* hits2,
                                 int32_t* out_count, int32_t* out_index, double* out_score, double* out_signals, uint8_t* out_sigmask,
                                 uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+    bind_thread();
     int rc = check_search_args(c, queries, dtype, Q, k);
     if (rc != LVS_OK) return rc;
     if (Q == 0) return LVS_OK;
@@ -1814,6 +1856,7 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
                                double entity_bonus, double rel_bonus, double* out_hit_scores, int64_t* out_hit_rows,
                                uint32_t* out_hit_counts, int32_t* out_flags, int32_t* out_count, int32_t* out_index, double* out_score,
                                double* out_signals, uint8_t* out_sigmask, uint8_t* out_source, int32_t* out_leader, float* device_ms) {
+    bind_thread();
     lvs_rank_hits h1;
     h1.scores = out_hit_scores; h1.rows = out_hit_rows; h1.counts = out_hit_counts; h1.flags = out_flags;
     return lvs_search_rank2(c, nullptr, queries, dtype, Q, k, 0, want, nullptr, nullptr, 0, graph, ctx, max_per_file, max_total,
@@ -1862,6 +1905,7 @@ static int snap_read(FILE* f, void* dptr, size_t bytes, Scratch& pin, cudaStream
 }
 
 extern "C" int lvs_snapshot_save(lvs_collection* c, const char* path) {
+    bind_thread();
     if (!c || !path) return fail(LVS_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     for (auto& sl : c->slots) if (sl.in_use) return fail(LVS_ESTATE, "searches are in flight: call lvs_search_wait first");
@@ -1904,6 +1948,7 @@ extern "C" int lvs_snapshot_save(lvs_collection* c, const char* path) {
 }
 
 extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t capacity_rows, lvs_collection** out) {
+    bind_thread();
     if (!path || !out) return fail(LVS_EINVAL, "NULL argument");
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -1980,6 +2025,7 @@ extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t cap
 // instrumentation
 // ------------------------------------------------------------------------------------------------------
 extern "C" int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches, int* kernel_kind) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (ms4) memcpy(ms4, c->last_ms, sizeof(float) * 4);
     if (n_launches) *n_launches = c->last_launches;
@@ -1988,6 +2034,7 @@ extern "C" int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* 
 }
 
 extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
+    bind_thread();
     if (!c || !name) return fail(LVS_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     if (!strcmp(name, "stage_kb")) c->opt_stage_kb = value;
@@ -2017,6 +2064,7 @@ __global__ void fetch_rows_kernel(const uint8_t* base, uint32_t row_bytes, int d
 }
 
 extern "C" int lvs_fetch_rows_f32(lvs_collection* c, const int64_t* rows, int64_t n, float* out) {
+    bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (n <= 0) return LVS_OK;
     if (!rows || !out) return fail(LVS_EINVAL, "NULL argument");
