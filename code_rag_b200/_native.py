@@ -139,6 +139,10 @@ def init(device: int = 0) -> None:
     global _initialised_device
     if _initialised_device == device:
         return
+    if _initialised_device is not None:
+        # one process drives one GPU (one process per GPU, torchrun-style): collections created on the first device would
+        # be orphaned by a re-bind
+        raise NativeLibraryError(f"this process is already bound to cuda:{_initialised_device}; cannot re-bind it to cuda:{device}")
     check(load().lvs_init(int(device)), "lvs_init")
     _initialised_device = device
 

@@ -80,3 +80,14 @@ def test_snapshot_load_rejects_foreign_and_corrupt_files(native_lib, tmp_path):
     assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
     assert b"size does not match" in native_lib.lvs_last_error()
     assert native_lib.lvs_snapshot_load(str(tmp_path / "missing.lvs").encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
+
+
+def test_one_process_binds_one_device(native_lib, monkeypatch):
+    """One process per GPU: a second init() with another device must fail loudly instead of orphaning the first device's shards."""
+    import pytest
+    from code_rag_b200 import _native
+    from code_rag_b200.errors import NativeLibraryError
+    monkeypatch.setattr(_native, "_initialised_device", 0)
+    _native.init(0)                                        # idempotent
+    with pytest.raises(NativeLibraryError):
+        _native.init(1)
