@@ -522,7 +522,8 @@ class B200VectorStore:
 
     async def load(self, directory: str) -> None:
         """Additive: replace the collections by the ones saved under ``directory``; searches continue exactly where the
-        saved store left off (same scores: the local-mode replay state is part of the snapshot)."""
+        saved store left off (same scores: the local-mode replay state is part of the snapshot).  The host half is a pickle:
+        load only snapshots this application wrote itself."""
         try:
             _ = self.client
 
