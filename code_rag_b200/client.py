@@ -194,7 +194,11 @@ class _HostCollection:
         pl = [dict(payloads[i]) if payloads[i] is not None else None for i in keep]
         codes = self.encode_payloads(pl)
         ties = np.array([_tie_key(canon[i]) for i in keep], dtype=np.uint64)
-        self.dev.upsert(vec[keep], rows=rows, codes=codes, ties=ties)
+        try:
+            self.dev.upsert(vec[keep], rows=rows, codes=codes, ties=ties)
+        except Exception:
+            self.free_rows.extend(r for _, r in reused)          # nothing was written: the rows stay reusable
+            raise
         for pid, r in reused:
             self.id_to_row[pid] = r
             self.ids[r] = pid
