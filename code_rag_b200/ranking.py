@@ -162,7 +162,8 @@ def _degree(key: Any, centrality: dict) -> int:
 def _run(batch: _Batch, mode: int, max_per_file: int, max_total: int, entity_bonus: float, rel_bonus: float):
     lib = N.load()
     if not N.is_initialised():
-        N.init(0)
+        import os
+        N.init(int(os.environ.get("LOCAL_RANK", "0")))       # the same default the vector store uses (one process per GPU)
     nq = len(batch.weights)
     arr = {
         "offsets": np.asarray(batch.offsets, dtype=np.int32), "kind": np.asarray(batch.kind, dtype=np.uint8),
