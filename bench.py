@@ -26,7 +26,13 @@ import threading
 import time
 from pathlib import Path
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  The reference arm is a CPU measurement on rank 0 alone (the other ranks
+# exit at once), so it gets every host thread back - before numpy loads its BLAS, which reads the variable once.
+if "reference" in sys.argv and os.environ.get("RANK", "0") == "0" and "LATTICE_B200_KEEP_OMP" not in os.environ:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
+import numpy as np  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -64,6 +70,18 @@ def make_queries(n: int, dim: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     q = rng.standard_normal((n, dim))
     return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def blas_threads() -> int:
+    """Threads numpy's BLAS actually runs with in this process (what `cpu_baseline.cores` reports)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(i["num_threads"]) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return max(n)
+    except Exception:  # noqa: BLE001
+        pass
+    return int(os.environ.get("OMP_NUM_THREADS") or os.cpu_count() or 1)
 
 
 def host_chunk(chunk_id: int, rows: int, dim: int, seed: int = 3456) -> np.ndarray:
@@ -112,9 +130,9 @@ def cpu_reference_qps(args, steps: int, warmup: int) -> dict:
     return {
         "best_effort_cpu": {"value": args.queries / (dt_fast * scale), "unit": UNIT,
                             "what": "pre-normalised float32 X @ q (BLAS, all threads) + argpartition, same sample and scaling; not the reference's arithmetic"},
-        "value": args.queries / (dt * scale), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        "value": args.queries / (dt * scale), "unit": UNIT, "cores": blas_threads(), "kind": "port",
         "sample": f"{n} of {args.rows} rows x {args.dim} (bf16-rounded, fp32 in RAM), {steps} searches after {warmup} warm-up; "
-                  f"time scaled x{scale:.0f} (scan+sort is linear in rows); numpy {np.__version__} BLAS threads = all",
+                  f"time scaled x{scale:.0f} (scan+sort is linear in rows); numpy {np.__version__}, {blas_threads()} BLAS threads",
         "ms_per_step_sample": dt * 1e3, "ms_per_step_scaled": ms_full,
     }
 
