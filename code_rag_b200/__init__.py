@@ -5,7 +5,8 @@ Import is light (no CUDA work, no library load); the first object that needs the
 """
 from .errors import NativeLibraryError, VectorStoreError  # noqa: F401
 
-__all__ = ["B200VectorStore", "CollectionName", "DeviceCollection", "NativeLibraryError", "VectorStoreError"]
+__all__ = ["B200VectorStore", "ShardedB200VectorStore", "ShardPlane", "CollectionName", "DeviceCollection", "NativeLibraryError",
+           "VectorStoreError"]
 __version__ = "0.1.0"
 
 
@@ -13,6 +14,9 @@ def __getattr__(name):  # lazy: keep `import code_rag_b200` free of numpy/ctypes
     if name in ("B200VectorStore", "CollectionName", "QdrantManager"):
         from . import client
         return getattr(client, name)
+    if name in ("ShardedB200VectorStore", "ShardPlane"):
+        from . import sharded_store
+        return getattr(sharded_store, name)
     if name in ("DeviceCollection", "SearchResult"):
         from . import collection
         return getattr(collection, name)

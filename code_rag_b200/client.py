@@ -135,14 +135,18 @@ class _HostCollection:
         col = len(self.columns)
         self.columns.append(key)
         self.dicts.append(dict())
-        n = len(self.payloads)
+        self.backfill_column(col)
+        return col
+
+    def backfill_column(self, col: int) -> None:
+        """Codes of a column that was added after rows were written, from the payloads kept on the host."""
+        key, n = self.columns[col], len(self.payloads)
         if n:
             codes = np.zeros(n, dtype=np.uint32)
             for r, p in enumerate(self.payloads):
                 if p and key in p:
                     codes[r] = self._encode_value(col, p[key], create=True)
             self.dev.set_codes(col, codes, row0=0)
-        return col
 
     def want_codes(self, filters: dict[str, Any] | None) -> np.ndarray | None:
         if not filters:
@@ -332,6 +336,23 @@ class _HostCollection:
         _, n = self.dev.match_rows(self.want_codes(filters), cap=0)
         return n
 
+    # -- what ``manager.client`` needs (projects/cleanup.py:38-73): equality conditions on the device, MatchText on the host --
+    def rows_matching(self, eq: dict[str, Any], text: Sequence[tuple[str, str]]) -> list[int]:
+        rows, _ = self.dev.match_rows(self.want_codes(eq))
+        out = []
+        for r in rows.tolist():
+            p = self.payloads[r] or {}
+            # MatchText in local mode is a substring test on the string payload value
+            if all(isinstance(p.get(k), str) and t in p[k] for k, t in text):
+                out.append(r)
+        return out
+
+    def delete_found(self, rows: Sequence[int]) -> None:
+        if len(rows):
+            self.dev.delete_rows(np.asarray(rows, dtype=np.int64))
+            self.release_rows(rows)
+            self.maybe_compact()
+
     def close(self) -> None:
         self.dev.close()
 
@@ -391,14 +412,7 @@ class _ClientShim:
 
     def _rows_matching(self, coll: _HostCollection, flt) -> list[int]:
         eq, text = self._split_filter(flt) if flt is not None else ({}, [])
-        rows, _ = coll.dev.match_rows(coll.want_codes(eq))
-        out = []
-        for r in rows.tolist():
-            p = coll.payloads[r] or {}
-            # MatchText in local mode is a substring test on the string payload value
-            if all(isinstance(p.get(k), str) and t in p[k] for k, t in text):
-                out.append(r)
-        return out
+        return coll.rows_matching(eq, text)
 
     async def count(self, collection_name: str, count_filter=None, exact: bool = True):
         coll = self._store._get(collection_name)
@@ -415,10 +429,7 @@ class _ClientShim:
         def work():
             with coll.lock:
                 rows = self._rows_matching(coll, flt)
-                if rows:
-                    coll.dev.delete_rows(np.asarray(rows, dtype=np.int64))
-                    coll.release_rows(rows)
-                    coll.maybe_compact()
+                coll.delete_found(rows)
                 return len(rows)
         await asyncio.to_thread(work)
         return SimpleNamespace(status="completed")

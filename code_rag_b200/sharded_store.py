@@ -1,0 +1,523 @@
+"""``ShardedB200VectorStore``: the ``QdrantManager`` drop-in over the row shards of ALL GPUs of one box.
+
+SURVEY section 8(e): rows are independent, so a collection is split into one row shard per GPU, new points go to the least-full
+shard, every search scans all shards at once and the per-shard top-k lists are merged after one exchange step
+(``sharded.ShardedSearcher``: NCCL all-gather or the peer-memory kernel, then the K5 merge).  ``B200VectorStore`` (``client.py``)
+is that adapter for ONE GPU; this module puts the same call surface (reference ``embeddings/client.py:18-228``) in front of N.
+
+Process model - one process per GPU (``torchrun``), one of them in charge:
+
+* rank 0 is the **controller**: the lattice application runs there and talks to a ``ShardedB200VectorStore`` exactly as it would
+  to a ``QdrantManager``.  Ids, payload dicts and the value dictionaries of the keyword columns live in its RAM (one
+  ``_HostCollection`` per shard, sharing the dictionaries), as they do in the single-GPU adapter.
+* ranks 1..N-1 are **shard workers**: after ``ShardPlane.start()`` they sit in ``plane.serve()`` and execute what the
+  controller sends.  Nobody else issues commands, so the order of collectives is the controller's order - concurrent awaits on
+  rank 0 (``asyncio.gather`` of graph + vector search, ``query/engine.py:142-146``) are serialised by the plane's lock.
+* control plane: pickled commands over a **gloo** group (scatter to the ranks, gather of the replies); data plane: the search's
+  one exchange step on the NCCL group.  Vectors travel only to the rank that owns their shard.
+
+Global row = ``shard << 32 | local row`` (a shard is created with ``row_base = rank << 32``), so a merged hit names its owner.
+
+A write is queued on the controller and sent with the next command (or at the end of the adapter call), one message per
+rank and call.  Not offered on this store (single-GPU only): the fused search -> rank call and snapshots.
+"""
+from __future__ import annotations
+
+import asyncio
+import logging
+import os
+import threading
+from types import SimpleNamespace
+from typing import Any, Callable, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .client import (B200VectorStore, CollectionName, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key)
+from .errors import VectorStoreError
+
+logger = logging.getLogger(__name__)
+
+SHARD_BITS = 32
+LOCAL_MASK = (1 << SHARD_BITS) - 1
+
+
+def split_row(global_row: int) -> tuple[int, int]:
+    """(shard, local row) of a merged hit."""
+    return int(global_row) >> SHARD_BITS, int(global_row) & LOCAL_MASK
+
+
+def least_full(live: list[int]) -> int:
+    """Shard that takes the next new point: fewest live points, lowest rank on a draw."""
+    return min(range(len(live)), key=live.__getitem__)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the plane: process group plumbing + what every rank (controller included) does with a command
+# ------------------------------------------------------------------------------------------------------------------
+class ShardPlane:
+    """One per process.  ``start()`` is collective; afterwards rank 0 drives and the others ``serve()``."""
+
+    def __init__(self, rank: int, world: int, ctl_group, device: int, device_factory: Callable | None,
+                 searcher_factory: Callable | None):
+        self.rank, self.world, self.ctl, self.device = rank, world, ctl_group, device
+        self._device_factory, self._searcher_factory = device_factory, searcher_factory
+        self.shards: dict[str, Any] = {}          # collection name -> this rank's shard (DeviceCollection)
+        self.searchers: dict[str, Any] = {}
+        self.lock = threading.RLock()             # controller: one command at a time
+        self.pending: list[list[tuple]] = [[] for _ in range(world)]     # controller: queued writes per rank
+        self.closed = False
+
+    @classmethod
+    def start(cls, device_factory: Callable | None = None, searcher_factory: Callable | None = None,
+              ctl_group=None) -> "ShardPlane":
+        """Collective over the default process group (``torchrun`` env; initialised here when the caller has not).  Binds the
+        process to ``cuda:LOCAL_RANK`` and opens the gloo control group.  The two factories exist for the CPU tests."""
+        import torch.distributed as dist
+        device = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+        if device_factory is None:
+            import torch
+            N.init(device)                          # raises without the library or an sm_100 device: no fallback
+            torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if device_factory is None:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+            else:
+                dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if ctl_group is None:
+            ctl_group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+        return cls(rank, world, ctl_group, device, device_factory, searcher_factory)
+
+    # ---- command transport ---------------------------------------------------------------------------------------
+    def _scatter(self, per_rank: list | None):
+        import torch.distributed as dist
+        out = [None]
+        dist.scatter_object_list(out, per_rank if self.rank == 0 else None, src=0, group=self.ctl)
+        return out[0]
+
+    def _gather(self, reply):
+        import torch.distributed as dist
+        got = [None] * self.world if self.rank == 0 else None
+        dist.gather_object(reply, got, dst=0, group=self.ctl)
+        return got
+
+    def call(self, op: str, name: str | None, common=None) -> list:
+        """Controller only.  Sends ``op`` (with the writes queued so far in front of it) to every rank, runs its own share and
+        returns the per-rank results; a failure on any rank is raised here."""
+        if self.rank != 0:
+            raise RuntimeError("only rank 0 drives the shard plane")
+        with self.lock:
+            if self.closed:
+                raise RuntimeError("shard plane is shut down")
+            if op == "search" and any(self.pending):
+                # the search ends in a data-plane collective that every rank must enter: writes still queued go first, in a
+                # command of their own, so that a rank failing one of them is reported instead of missing the exchange
+                self.call("noop", None)
+            writes, self.pending = self.pending, [[] for _ in range(self.world)]
+            mine = self._scatter([(op, name, common, writes[r]) for r in range(self.world)])
+            replies = self._gather(self._execute(*mine))
+        bad = [(r, rep[1]) for r, rep in enumerate(replies) if not rep[0]]
+        if bad:
+            raise RuntimeError("; ".join(f"rank {r}: {msg}" for r, msg in bad))
+        return [rep[1] for rep in replies]
+
+    def queue(self, shard: int, name: str, method: str, *args) -> None:
+        with self.lock:
+            self.pending[shard].append((name, method, args))
+
+    def flush(self) -> None:
+        with self.lock:
+            if any(self.pending):
+                self.call("noop", None)
+
+    def serve(self) -> None:
+        """Ranks 1..N-1: execute the controller's commands until it shuts the plane down."""
+        if self.rank == 0:
+            raise RuntimeError("rank 0 is the controller")
+        while not self.closed:
+            cmd = self._scatter(None)
+            self._gather(self._execute(*cmd))
+
+    def shutdown(self) -> None:
+        """Controller: release the workers (collective with their ``serve()`` loops)."""
+        if self.rank == 0 and not self.closed:
+            self.call("shutdown", None)
+
+    # ---- what a rank does with a command -------------------------------------------------------------------------
+    def _execute(self, op: str, name: str | None, common, writes: list) -> tuple[bool, Any]:
+        """Returns (ok, result or error text).  Data-plane collectives (the search's exchange) are entered by every rank or by
+        none: arguments are validated on the controller before anything is sent."""
+        try:
+            if self._device_factory is None:          # commands may arrive on another thread (asyncio.to_thread on rank 0)
+                import torch
+                torch.cuda.set_device(self.device)
+            for w_name, method, args in writes:
+                self._write(self.shards[w_name], method, args)
+            return True, getattr(self, "_op_" + op)(name, common)
+        except Exception as e:  # noqa: BLE001
+            logger.exception("shard rank %d: %s(%s) failed", self.rank, op, name)
+            return False, f"{type(e).__name__}: {e}"
+
+    @staticmethod
+    def _write(dev, method: str, args: tuple) -> None:
+        base = int(getattr(dev, "row_base", 0))          # the wire carries local rows
+        if method == "upsert":
+            vec, rows, codes, ties = args
+            dev.upsert(vec, rows=rows + base, codes=codes, ties=ties)
+        elif method == "set_codes":
+            col, codes, rows, row0 = args
+            dev.set_codes(col, codes, rows=None if rows is None else rows + base, row0=row0 + base)
+        elif method == "delete_rows":
+            dev.delete_rows(args[0] + base)
+        elif method == "move_rows":
+            dev.move_rows(args[0] + base, args[1] + base)
+        elif method == "truncate":
+            dev.truncate(args[0])
+        else:
+            raise ValueError(f"unknown shard write {method!r}")
+
+    def _op_noop(self, name, common):
+        return None
+
+    def _op_shutdown(self, name, common):
+        for nm in list(self.shards):
+            self._op_destroy(nm, None)
+        self.closed = True
+        return None
+
+    def _op_create(self, name, common):
+        dim, storage, n_cols = common
+        if name in self.shards:
+            self._op_destroy(name, None)
+        if self._device_factory is None:
+            from .collection import DeviceCollection as factory
+        else:
+            factory = self._device_factory
+        shard = factory(name, dim, storage=storage, metric="cosine", n_filter_cols=n_cols, capacity=0,
+                        row_base=self.rank << SHARD_BITS, device=self.device)
+        self.shards[name] = shard
+        if self._searcher_factory is None:
+            from .sharded import ShardedSearcher
+            self.searchers[name] = ShardedSearcher(shard)
+        else:
+            self.searchers[name] = self._searcher_factory(shard, self.rank, self.world)
+        return None
+
+    def _op_destroy(self, name, common):
+        s = self.searchers.pop(name, None)
+        if s is not None and hasattr(s, "close"):
+            s.close()
+        d = self.shards.pop(name, None)
+        if d is not None:
+            d.close()
+        return None
+
+    def _op_search(self, name, common):
+        queries, k, want = common
+        scores, rows, ties, counts, flags = self.searchers[name].search(queries, k, want)
+        # every rank holds the merged answer; only the controller needs it
+        return (scores, rows, counts, flags) if self.rank == 0 else None
+
+    def _local_rows(self, dev, found) -> tuple[np.ndarray, int]:
+        rows, n = found
+        return np.asarray(rows, dtype=np.int64) - int(getattr(dev, "row_base", 0)), int(n)
+
+    def _op_match(self, name, common):
+        want, cap = common
+        dev = self.shards[name]
+        return self._local_rows(dev, dev.match_rows(want, cap))
+
+    def _op_delete_where(self, name, common):
+        dev = self.shards[name]
+        return self._local_rows(dev, dev.delete_where(common))
+
+    def _op_count(self, name, common):
+        return int(self.shards[name].count())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# controller-side host state
+# ------------------------------------------------------------------------------------------------------------------
+class _ShardProxy:
+    """What a shard's ``_HostCollection`` sees as its device on the controller: local rows, writes queued for the owner."""
+
+    row_base = 0
+
+    def __init__(self, plane: ShardPlane, name: str, shard: int):
+        self._plane, self._name, self._shard = plane, name, shard
+
+    def upsert(self, vectors, rows=None, codes=None, ties=None) -> None:
+        self._plane.queue(self._shard, self._name, "upsert", np.ascontiguousarray(vectors), np.asarray(rows, dtype=np.int64),
+                          None if codes is None else np.ascontiguousarray(codes, dtype=np.uint32),
+                          None if ties is None else np.ascontiguousarray(ties, dtype=np.uint64))
+
+    def set_codes(self, col, codes, rows=None, row0=0) -> None:
+        self._plane.queue(self._shard, self._name, "set_codes", int(col), np.ascontiguousarray(codes, dtype=np.uint32),
+                          None if rows is None else np.asarray(rows, dtype=np.int64), int(row0))
+
+    def delete_rows(self, rows) -> None:
+        self._plane.queue(self._shard, self._name, "delete_rows", np.asarray(rows, dtype=np.int64))
+
+    def move_rows(self, src, dst) -> None:
+        self._plane.queue(self._shard, self._name, "move_rows", np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64))
+
+    def truncate(self, n_rows) -> None:
+        self._plane.queue(self._shard, self._name, "truncate", int(n_rows))
+
+    def close(self) -> None:
+        pass
+
+
+class _HostShard(_HostCollection):
+    """Bookkeeping of one shard.  Keyword columns and their dictionaries belong to the collection, not to the shard."""
+
+    def __init__(self, owner: "_ShardedHostCollection", shard: int):
+        super().__init__(owner.name, owner.dim, owner.storage, owner.columns, owner.plane.device,
+                         dev_factory=lambda *a, **kw: _ShardProxy(owner.plane, owner.name, shard))
+        self.columns, self.dicts = owner.columns, owner.dicts          # shared objects
+        self.owner = owner
+
+    def ensure_column(self, key: str) -> int:
+        return self.owner.ensure_column(key)
+
+
+def _whole_op(fn):
+    """An adapter-level operation owns the plane from its first queued write to its last command, so that its writes (and
+    their failures) are not carried by another collection's command."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with self.plane.lock:
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
+class _ShardedHostCollection:
+    """Same operations as ``client._HostCollection`` (what ``B200VectorStore`` calls under ``.lock``), over N shards."""
+
+    rank_kind = None          # fused search -> rank is a single-GPU feature
+
+    def __init__(self, plane: ShardPlane, name: str, dim: int, storage: str, index_fields: Sequence[str]):
+        self.plane, self.name, self.dim, self.storage = plane, name, dim, storage
+        self.columns: list[str] = list(index_fields)[: N.MAX_FILTER_COLS]
+        self.dicts: list[dict[Any, int]] = [dict() for _ in self.columns]
+        self.lock = threading.Lock()
+        plane.call("create", name, (dim, storage, N.MAX_FILTER_COLS))
+        self.shards = [_HostShard(self, s) for s in range(plane.world)]
+
+    # -- columns and filters -------------------------------------------------------------------------------------
+    def ensure_column(self, key: str) -> int:
+        if key in self.columns:
+            return self.columns.index(key)
+        if len(self.columns) >= N.MAX_FILTER_COLS:
+            raise ValueError(f"cannot filter on {key!r}: all {N.MAX_FILTER_COLS} keyword columns are in use ({self.columns})")
+        self.columns.append(key)
+        self.dicts.append(dict())
+        for sh in self.shards:
+            sh.backfill_column(len(self.columns) - 1)
+        return len(self.columns) - 1
+
+    def want_codes(self, filters):
+        return self.shards[0].want_codes(filters)
+
+    # -- operations ----------------------------------------------------------------------------------------------
+    def live_counts(self) -> list[int]:
+        return [len(sh.ids) - len(sh.free_rows) for sh in self.shards]
+
+    def shard_of(self, pid) -> int | None:
+        for s, sh in enumerate(self.shards):
+            if pid in sh.id_to_row:
+                return s
+        return None
+
+    @_whole_op
+    def upsert(self, ids, vectors, payloads) -> None:
+        n = min(len(ids), len(vectors), len(payloads))           # the reference zips the three lists (client.py:123-126)
+        if n == 0:
+            return
+        canon = [_canonical_id(i) for i in ids[:n]]
+        vec = np.asarray(vectors[:n], dtype=np.float64)
+        if vec.ndim != 2 or vec.shape[1] != self.dim:
+            raise ValueError(f"vectors must have dimension {self.dim}, got shape {vec.shape}")
+        if not np.isfinite(vec).all():
+            raise ValueError("vectors must be finite")
+        last = {pid: i for i, pid in enumerate(canon)}           # a repeated id: the last occurrence wins
+        live = self.live_counts()
+        parts: list[list[int]] = [[] for _ in self.shards]
+        for i in sorted(last.values()):
+            s = self.shard_of(canon[i])
+            if s is None:                                        # a new point goes to the least-full shard
+                s = least_full(live)
+                live[s] += 1
+            parts[s].append(i)
+        for s, idx in enumerate(parts):
+            if idx:
+                self.shards[s].upsert([canon[i] for i in idx], vec[idx], [payloads[i] for i in idx])
+        self.plane.flush()
+
+    def _hits(self, rows: np.ndarray, scores: np.ndarray) -> list[dict[str, Any]]:
+        out = []
+        for g, sc in zip(rows.tolist(), scores.tolist()):
+            if g < 0:
+                continue
+            s, r = split_row(g)
+            out.extend(self.shards[s]._hits(np.asarray([r]), np.asarray([sc])))
+        return out
+
+    def _match(self, want, cap=None) -> tuple[list[list[int]], int]:
+        found = self.plane.call("match", self.name, (want, cap))
+        return [rows.tolist() for rows, _ in found], sum(n for _, n in found)
+
+    @_whole_op
+    def search(self, query_vectors, limit: int, filters) -> list[list[dict[str, Any]]]:
+        want = self.want_codes(filters)
+        if limit <= 0:
+            return [[] for _ in range(1 if query_vectors is None else len(query_vectors))]
+        if query_vectors is None:
+            # filter-only lookup (query/context/builder.py:111-119): matching points in ascending id order, score 0.0
+            per_shard, _ = self._match(want)
+            found = [(self.shards[s].ids[r], s, r) for s, rows in enumerate(per_shard) for r in rows]
+            found.sort(key=lambda t: _id_sort_key(t[0]))
+            return [[h for _, s, r in found[:limit] for h in self.shards[s]._hits(np.asarray([r]), np.zeros(1))]]
+        if limit > N.MAX_K:
+            raise ValueError(f"limit {limit} exceeds the largest supported top-k ({N.MAX_K})")
+        q = np.ascontiguousarray(query_vectors, dtype=np.float64)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")
+        scores, rows, counts, flags = self.plane.call("search", self.name, (q, int(limit), want))[0]
+        out = []
+        for qi in range(rows.shape[0]):
+            n = int(counts[qi])
+            if int(flags[qi]) & N.FLAG_UNPROVEN:
+                logger.warning("search on %s: exactness bound not met for query %d (many near-ties)", self.name, qi)
+            out.append(self._hits(rows[qi, :n], scores[qi, :n]))
+        return out
+
+    def scroll(self, filters, limit: int):
+        return self.search(None, limit, filters)[0]
+
+    def _after_delete(self, per_shard: list[list[int]]) -> None:
+        for sh, rows in zip(self.shards, per_shard):
+            if rows:
+                sh.release_rows(rows)
+                sh.maybe_compact()
+        self.plane.flush()
+
+    @_whole_op
+    def delete(self, filters) -> int:
+        want = self.want_codes(filters)
+        found = self.plane.call("delete_where", self.name, want)
+        self._after_delete([rows.tolist() for rows, _ in found])
+        return sum(n for _, n in found)
+
+    @_whole_op
+    def count(self, filters=None) -> int:
+        if not filters:
+            return sum(self.plane.call("count", self.name))
+        return self._match(self.want_codes(filters), cap=0)[1]
+
+    @_whole_op
+    def rows_matching(self, eq, text) -> list[tuple[int, int]]:
+        per_shard, _ = self._match(self.want_codes(eq))
+        out = []
+        for s, rows in enumerate(per_shard):
+            for r in rows:
+                p = self.shards[s].payloads[r] or {}
+                if all(isinstance(p.get(k), str) and t in p[k] for k, t in text):
+                    out.append((s, r))
+        return out
+
+    @_whole_op
+    def delete_found(self, found: Sequence[tuple[int, int]]) -> None:
+        per_shard: list[list[int]] = [[] for _ in self.shards]
+        for s, r in found:
+            per_shard[s].append(r)
+        for sh, rows in zip(self.shards, per_shard):
+            if rows:
+                sh.dev.delete_rows(rows)
+        self._after_delete(per_shard)
+
+    def close(self) -> None:
+        if not self.plane.closed:
+            self.plane.call("destroy", self.name)
+
+    def save(self, directory: str) -> None:
+        raise NotImplementedError("snapshots of a sharded store are not implemented yet (single-GPU stores have them)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the adapter
+# ------------------------------------------------------------------------------------------------------------------
+class ShardedB200VectorStore(B200VectorStore):
+    """``QdrantManager``'s surface (see ``client.B200VectorStore``) over every GPU of the ``torchrun`` job.
+
+    Every rank::
+
+        plane = ShardPlane.start()                       # collective
+        if plane.rank != 0:
+            plane.serve()                                # until rank 0 calls plane.shutdown()
+        else:
+            store = ShardedB200VectorStore(dimensions=768, storage="bf16", plane=plane)
+            await store.connect(); await store.create_collections()
+            ...                                          # QueryEngine(qdrant=store), VectorIndexer(store, ...), ...
+            await store.close(); plane.shutdown()
+    """
+
+    def __init__(self, host: str | None = None, port: int | None = None, grpc_port: int | None = None, *,
+                 dimensions: int | None = None, storage: str | None = None, plane: ShardPlane | None = None):
+        super().__init__(host, port, grpc_port, dimensions=dimensions, storage=storage, device=plane.device if plane else None)
+        self._plane = plane
+
+    @property
+    def plane(self) -> ShardPlane:
+        if self._plane is None:
+            raise VectorStoreError("Client not connected. Call connect() first.")
+        return self._plane
+
+    async def connect(self) -> None:
+        if not self._connected:
+            try:
+                if self._plane is None:
+                    self._plane = await asyncio.to_thread(ShardPlane.start)
+                if self._plane.rank != 0:
+                    raise RuntimeError("ShardedB200VectorStore lives on rank 0; the other ranks run plane.serve()")
+                if self._plane.closed:
+                    raise RuntimeError("shard plane is shut down")
+                self._connected = True
+                logger.info("lattice-b200 sharded vector store: %d shard(s)", self._plane.world)
+            except Exception as e:  # noqa: BLE001
+                raise VectorStoreError("Failed to connect to Qdrant", cause=e)
+
+    async def create_collections(self) -> None:
+        try:
+            _ = self.client
+            for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
+                if name not in self._collections:
+                    self._collections[name] = await asyncio.to_thread(
+                        _ShardedHostCollection, self.plane, name, self._dimensions, self._storage, _INDEX_FIELDS[name])
+                    logger.info(f"Created collection: {name}")
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError("Failed to create collections", cause=e)
+
+    async def get_collection_info(self, collection: str):
+        info = await super().get_collection_info(collection)
+        info.shards = self.plane.world
+        info.shard_points = self._get(collection).live_counts()
+        return info
+
+    async def save(self, directory: str) -> None:
+        raise VectorStoreError("snapshots of a sharded store are not implemented yet")
+
+    async def load(self, directory: str) -> None:
+        raise VectorStoreError("snapshots of a sharded store are not implemented yet")
+
+    async def search_and_rank(self, *args, **kwargs):
+        raise VectorStoreError("search_and_rank needs a single-GPU store created with rank_attrs=True")
+
+
+__all__ = ["ShardPlane", "ShardedB200VectorStore", "split_row", "least_full", "SHARD_BITS"]

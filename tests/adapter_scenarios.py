@@ -21,6 +21,13 @@ CODE = CollectionName.CODE_CHUNKS.value
 SUMM = CollectionName.SUMMARIES.value
 
 
+def _store(factory, **kw):
+    """`factory` is a device class (single-GPU adapter over it) or carries `make_store` (tests/test_sharded_store_cpu.py: the
+    sharded adapter on rank 0 of a gloo job) - the scenarios are the same either way."""
+    make = getattr(factory, "make_store", None)
+    return make(**kw) if make is not None else B200VectorStore(_device_factory=factory, **kw)
+
+
 def _same_hits(got, exp, rel=1e-5, what=""):
     assert [h["id"] for h in got] == [h["id"] for h in exp], f"{what}: ids differ\n got {[h['id'] for h in got]}\n exp {[h['id'] for h in exp]}"
     for g, e in zip(got, exp):
@@ -30,7 +37,7 @@ def _same_hits(got, exp, rel=1e-5, what=""):
 
 async def scenario_test_database(factory):
     """reference tests/test_database.py:62-124 against the new backend."""
-    manager = B200VectorStore(dimensions=1536, _device_factory=factory)
+    manager = _store(factory, dimensions=1536)
     await manager.connect()
     assert await manager.health_check() is True
     await manager.create_collections()
@@ -65,7 +72,7 @@ async def scenario_parity_with_oracle(factory, n=3000, dim=256):
     x, q = synth.unixcoder_like(n, dim, seed=1234, n_queries=6)
     pl = synth.payloads(n, seed=7)
     ids = synth.random_uuids(n, seed=9)
-    store = B200VectorStore(dimensions=dim, _device_factory=factory)
+    store = _store(factory, dimensions=dim)
     ora = OracleManager(dim)
     await store.connect()
     await store.create_collections()
@@ -142,7 +149,7 @@ async def scenario_parity_with_oracle(factory, n=3000, dim=256):
 
 
 async def scenario_errors(factory):
-    store = B200VectorStore(dimensions=8, _device_factory=factory)
+    store = _store(factory, dimensions=8)
     for coro in (store.search(collection=CODE, query_vector=[0.0] * 8), store.upsert(CODE, [], [], []),
                  store.delete(CODE, {"a": 1}), store.create_collections(), store.get_collection_info(CODE)):
         try:
@@ -173,7 +180,7 @@ async def scenario_errors(factory):
 async def scenario_client_shim(factory):
     """projects/cleanup.py:38-73: count + delete with a MatchText (substring) filter through manager.client."""
     from types import SimpleNamespace as NS
-    store = B200VectorStore(dimensions=16, _device_factory=factory)
+    store = _store(factory, dimensions=16)
     await store.connect()
     await store.create_collections()
     x, _ = synth.unit_rows(40, 16, seed=1)
@@ -194,7 +201,7 @@ async def scenario_reindex_churn(factory, n_files=40, chunks=6, dim=48, rounds=1
     uuid4 ids.  The shard must not grow (deleted rows are reused) and must keep answering like the oracle."""
     import random
     rng = random.Random(5)
-    store = B200VectorStore(dimensions=dim, _device_factory=factory)
+    store = _store(factory, dimensions=dim)
     ora = OracleManager(dim)
     await store.connect()
     await store.create_collections()
@@ -252,7 +259,7 @@ async def scenario_mass_delete_compacts(factory, n=2400, dim=48):
     for i, p in enumerate(pl):
         p["project_name"] = ("alpha", "beta", "gamma")[i % 3]
     ids = synth.random_uuids(n, seed=608)
-    store = B200VectorStore(dimensions=dim, _device_factory=factory)
+    store = _store(factory, dimensions=dim)
     ora = OracleManager(dim)
     await store.connect(); await store.create_collections(); ora.create_collections()
     vecs = x.astype(np.float64).tolist()

@@ -130,3 +130,30 @@ def merge_lists_numpy(scores: np.ndarray, rows: np.ndarray, ties: np.ndarray, k:
         order = keep[np.lexsort((r[keep], t[keep], -s[keep]))][:k]
         o_s[q, :len(order)] = s[order]; o_r[q, :len(order)] = r[order]; o_t[q, :len(order)] = t[order]
     return o_s, o_r, o_t
+
+
+class FakeShardSearcher:
+    """CPU stand-in for code_rag_b200.sharded.ShardedSearcher in the sharded adapter's tests: the shard's own top-k (FakeDevice),
+    the path's real exchange step over gloo (``allgather_packed``) and the K5 merge rule in numpy.  TESTS ONLY."""
+
+    def __init__(self, shard, rank, world, group=None):
+        self.shard, self.rank, self.world, self.group = shard, rank, world, group
+
+    def search(self, queries, k, want=None):
+        import torch
+        from code_rag_b200.sharded import allgather_packed
+        res = self.shard.search(queries, k, want)
+        Q = res.rows.shape[0]
+        local = torch.zeros((3, Q, k), dtype=torch.int64)
+        rows = np.where(res.rows >= 0, res.rows + (self.rank << 32), -1)            # global rows, as the real shard returns them
+        local[0] = torch.from_numpy(res.scores.view(np.int64).copy())
+        local[1] = torch.from_numpy(rows)
+        local[2] = torch.from_numpy(res.ties.view(np.int64).copy())
+        gathered = torch.zeros((self.world, 3, Q, k), dtype=torch.int64)
+        allgather_packed(local, gathered, self.group)
+        g = gathered.numpy()
+        s, r, t = merge_lists_numpy(g[:, 0].view(np.float64), g[:, 1], g[:, 2].view(np.uint64), k)
+        return s, r, t, (r >= 0).sum(axis=1).astype(np.uint32), np.zeros(Q, dtype=np.int32)
+
+    def close(self):
+        pass

@@ -1,0 +1,131 @@
+"""The multi-GPU adapter's host logic on CPU: a gloo job (world size 2 and 3) in which rank 0 drives a ``ShardedB200VectorStore``
+through the SAME scenarios as the single-GPU adapter (tests/adapter_scenarios.py: the reference's database test, parity with the
+oracle's QdrantManager over every filter shape, the error convention, the ``.client`` shim) while the other ranks sit in
+``ShardPlane.serve()``.  Each rank's shard is the oracle-backed FakeDevice; the exchange step is the real packed all-gather.
+Placement (least-full shard), overwrite in place, per-shard row reuse and compaction are checked on top."""
+import asyncio
+import os
+import sys
+import traceback
+from pathlib import Path
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+for p_ in (str(ROOT), str(ROOT / "tests")):
+    if p_ not in sys.path:
+        sys.path.insert(0, p_)
+
+from code_rag_b200.sharded_store import least_full, split_row  # noqa: E402
+
+
+def test_row_coding_and_placement():
+    assert split_row((5 << 32) | 77) == (5, 77) and split_row(3) == (0, 3)
+    assert least_full([4, 2, 2]) == 1 and least_full([0]) == 0 and least_full([3, 3, 3]) == 0
+
+
+async def _sharded_specifics(make_store, world):
+    """What only exists with several shards: balance, overwrite stays put, per-shard reuse and compaction, scroll order."""
+    import lvs_synth as synth
+    from adapter_scenarios import CODE, _same_hits
+    from oracle.qdrant_local import OracleManager
+    n, dim = 1800, 48
+    x, q = synth.unixcoder_like(n, dim, seed=31, n_queries=4)
+    pl = synth.payloads(n, seed=32)
+    for i, p in enumerate(pl):
+        p["project_name"] = ("alpha", "beta", "gamma")[i % 3]
+    ids = synth.random_uuids(n, seed=33)
+    vecs = x.astype(np.float64).tolist()
+    store, ora = make_store(dimensions=dim), OracleManager(dim)
+    await store.connect(); await store.create_collections(); ora.create_collections()
+    for s in range(0, 1500, 211):
+        sl = slice(s, min(1500, s + 211))
+        await store.upsert(collection=CODE, ids=ids[sl], vectors=vecs[sl], payloads=pl[sl]); ora.upsert(CODE, ids[sl], vecs[sl], pl[sl])
+    coll = store._get(CODE)
+    info = await store.get_collection_info(CODE)
+    assert info.points_count == 1500 and info.shards == world and sum(info.shard_points) == 1500
+    assert max(info.shard_points) - min(info.shard_points) <= 1, info.shard_points
+    # an overwrite stays in its shard and row
+    where = coll.shard_of(store_id := str(__import__("uuid").UUID(ids[7])))
+    row = coll.shards[where].id_to_row[store_id]
+    await store.upsert(collection=CODE, ids=[ids[7]], vectors=[vecs[99]], payloads=[dict(pl[7], language="go")])
+    ora.upsert(CODE, [ids[7]], [vecs[99]], [dict(pl[7], language="go")])
+    assert coll.shard_of(store_id) == where and coll.shards[where].id_to_row[store_id] == row
+    # delete a third everywhere: every shard compacts on its own
+    for sh in coll.shards:
+        sh.COMPACT_MIN_FREE = 50
+    await store.delete(collection=CODE, filters={"project_name": "beta"}); ora.delete(CODE, {"project_name": "beta"})
+    assert (await store.get_collection_info(CODE)).points_count == ora.points_count(CODE)
+    assert all(not sh.free_rows and all(i is not None for i in sh.ids) for sh in coll.shards), "each shard must have been compacted"
+    # the emptier shards fill up first; a filter on a key that was never indexed (new column over all shards)
+    expect = (await store.get_collection_info(CODE)).shard_points
+    for _ in range(1500, n):
+        expect[least_full(expect)] += 1
+    await store.upsert(collection=CODE, ids=ids[1500:], vectors=vecs[1500:], payloads=pl[1500:]); ora.upsert(CODE, ids[1500:], vecs[1500:], pl[1500:])
+    assert (await store.get_collection_info(CODE)).shard_points == expect
+    for qi in range(4):
+        for f in (None, {"project_name": "gamma"}, {"language": "go"}, {"entity_name": pl[1600]["entity_name"]}, {"project_name": "beta"}):
+            _same_hits(await store.search(collection=CODE, query_vector=q[qi].tolist(), limit=9, filters=f),
+                       ora.search(CODE, q[qi].tolist(), limit=9, filters=f), what=f"sharded q{qi} {f}")
+    got = await store.search_batch(collection=CODE, query_vectors=q.tolist(), limit=6, filters={"project_name": "alpha"})
+    for qi in range(4):
+        _same_hits(got[qi], ora.search(CODE, q[qi].tolist(), limit=6, filters={"project_name": "alpha"}), what=f"sharded batch {qi}")
+    # the filter-only lookup orders by id across shards
+    _same_hits(await store.search(collection=CODE, query_vector=None, limit=40, filters={"project_name": "gamma"}),
+               ora.search(CODE, None, limit=40, filters={"project_name": "gamma"}), what="sharded scroll")
+    # a worker-side failure reaches the caller as VectorStoreError and the plane keeps working
+    from code_rag_b200.errors import VectorStoreError
+    store.plane.queue(world - 1, CODE, "no_such_write")
+    try:
+        await store.search(collection=CODE, query_vector=q[0].tolist(), limit=3)
+        raise AssertionError("expected VectorStoreError")
+    except VectorStoreError as e:
+        assert f"rank {world - 1}" in str(e.cause)
+    _same_hits(await store.search(collection=CODE, query_vector=q[0].tolist(), limit=3), ora.search(CODE, q[0].tolist(), limit=3), what="after failure")
+    await store.close()
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    status = "ok"
+    try:
+        import torch.distributed as dist
+        from helpers import FakeDevice, FakeShardSearcher
+        from code_rag_b200.sharded_store import ShardedB200VectorStore, ShardPlane
+        plane = ShardPlane.start(device_factory=FakeDevice, searcher_factory=FakeShardSearcher)
+        if rank != 0:
+            plane.serve()
+        else:
+            try:
+                import adapter_scenarios as S
+                from types import SimpleNamespace as NS
+                factory = NS(make_store=lambda **kw: ShardedB200VectorStore(plane=plane, **kw))
+                asyncio.run(S.scenario_test_database(factory))
+                asyncio.run(S.scenario_parity_with_oracle(factory, n=900, dim=48))
+                asyncio.run(S.scenario_errors(factory))
+                asyncio.run(S.scenario_client_shim(factory))
+                asyncio.run(_sharded_specifics(factory.make_store, world))
+            except BaseException:  # noqa: BLE001
+                status = traceback.format_exc()
+            finally:
+                plane.shutdown()
+        dist.destroy_process_group()
+    except BaseException:  # noqa: BLE001
+        status = traceback.format_exc()
+    Path(out_dir, f"rank{rank}.txt").write_text(status)
+
+
+def _run(world, tmp_path):
+    port = 31000 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert Path(tmp_path, f"rank{r}.txt").read_text() == "ok", f"rank {r}"
+
+
+def test_sharded_store_world2(tmp_path):
+    _run(2, tmp_path)
+
+
+def test_sharded_store_world3(tmp_path):
+    _run(3, tmp_path)
