@@ -19,7 +19,8 @@ Process model - one process per GPU (``torchrun``), one of them in charge:
 Global row = ``shard << 32 | local row`` (a shard is created with ``row_base = rank << 32``), so a merged hit names its owner.
 
 A write is queued on the controller and sent with the next command (or at the end of the adapter call), one message per
-rank and call.  Not offered on this store (single-GPU only): the fused search -> rank call and snapshots.
+rank and call.  Snapshots: one ``.lvs`` file per rank plus the controller's host half.  Not offered on this store (single-GPU
+only): the fused search -> rank call.
 """
 from __future__ import annotations
 
@@ -198,12 +199,15 @@ class ShardPlane:
         shard = factory(name, dim, storage=storage, metric="cosine", n_filter_cols=n_cols, capacity=0,
                         row_base=self.rank << SHARD_BITS, device=self.device)
         self.shards[name] = shard
+        self._attach_searcher(name, shard)
+        return None
+
+    def _attach_searcher(self, name, shard) -> None:
         if self._searcher_factory is None:
             from .sharded import ShardedSearcher
             self.searchers[name] = ShardedSearcher(shard)
         else:
             self.searchers[name] = self._searcher_factory(shard, self.rank, self.world)
-        return None
 
     def _op_destroy(self, name, common):
         s = self.searchers.pop(name, None)
@@ -235,6 +239,28 @@ class ShardPlane:
 
     def _op_count(self, name, common):
         return int(self.shards[name].count())
+
+    def _shard_file(self, directory: str, name: str) -> str:
+        return os.path.join(directory, f"{name}.shard{self.rank}of{self.world}.lvs")
+
+    def _op_snapshot_save(self, name, common):
+        os.makedirs(common, exist_ok=True)
+        self.shards[name].save_snapshot(self._shard_file(common, name))
+        return int(self.shards[name].rows)
+
+    def _op_snapshot_load(self, name, common):
+        if self._device_factory is None:
+            from .collection import DeviceCollection as factory
+        else:
+            factory = self._device_factory
+        shard = factory.load_snapshot(self._shard_file(common, name), name=name, device=self.device)
+        if int(getattr(shard, "row_base", 0)) not in (0, self.rank << SHARD_BITS):
+            shard.close()
+            raise ValueError(f"{self._shard_file(common, name)} holds rows of another shard")
+        self._op_destroy(name, None)
+        self.shards[name] = shard
+        self._attach_searcher(name, shard)
+        return int(shard.rows)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -307,6 +333,43 @@ class _ShardedHostCollection:
         self.lock = threading.Lock()
         plane.call("create", name, (dim, storage, N.MAX_FILTER_COLS))
         self.shards = [_HostShard(self, s) for s in range(plane.world)]
+
+    # -- snapshots: one raw ``.lvs`` per rank (written and read by its owner) + the controller's host half ---------------
+    _SHARD_STATE = ("ids", "id_to_row", "payloads", "free_rows")
+
+    @_whole_op
+    def save(self, directory: str) -> None:
+        import pickle
+        self.plane.flush()
+        rows = self.plane.call("snapshot_save", self.name, str(directory))
+        if rows != [len(sh.ids) for sh in self.shards]:
+            raise RuntimeError(f"snapshot of {self.name}: device rows {rows} but host rows {[len(sh.ids) for sh in self.shards]}")
+        state = {"name": self.name, "dim": self.dim, "storage": self.storage, "world": self.plane.world, "columns": self.columns,
+                 "dicts": self.dicts, "shards": [{k: getattr(sh, k) for k in self._SHARD_STATE} for sh in self.shards]}
+        with open(os.path.join(directory, f"{self.name}.host{self.plane.world}.pkl"), "wb") as f:
+            pickle.dump(state, f, protocol=pickle.HIGHEST_PROTOCOL)
+
+    @classmethod
+    def load(cls, plane: ShardPlane, directory: str, name: str) -> "_ShardedHostCollection":
+        """The host half is a pickle: load only snapshots this application wrote itself (as with the single-GPU store)."""
+        import pickle
+        with open(os.path.join(directory, f"{name}.host{plane.world}.pkl"), "rb") as f:
+            state = pickle.load(f)
+        if state["world"] != plane.world:
+            raise ValueError(f"snapshot of {name} was written by {state['world']} shard(s), this job has {plane.world}")
+        self = cls.__new__(cls)
+        self.plane, self.name, self.dim, self.storage = plane, name, state["dim"], state["storage"]
+        self.columns, self.dicts = state["columns"], state["dicts"]
+        self.lock = threading.Lock()
+        self.shards = [_HostShard(self, s) for s in range(plane.world)]
+        for sh, st in zip(self.shards, state["shards"]):
+            for k in cls._SHARD_STATE:
+                setattr(sh, k, st[k])
+        with plane.lock:
+            rows = plane.call("snapshot_load", name, str(directory))
+        if rows != [len(sh.ids) for sh in self.shards]:
+            raise ValueError(f"snapshot of {name}: device rows {rows} but host rows {[len(sh.ids) for sh in self.shards]}")
+        return self
 
     # -- columns and filters -------------------------------------------------------------------------------------
     def ensure_column(self, key: str) -> int:
@@ -446,9 +509,6 @@ class _ShardedHostCollection:
         if not self.plane.closed:
             self.plane.call("destroy", self.name)
 
-    def save(self, directory: str) -> None:
-        raise NotImplementedError("snapshots of a sharded store are not implemented yet (single-GPU stores have them)")
-
 
 # ------------------------------------------------------------------------------------------------------------------
 # the adapter
@@ -510,11 +570,21 @@ class ShardedB200VectorStore(B200VectorStore):
         info.shard_points = self._get(collection).live_counts()
         return info
 
-    async def save(self, directory: str) -> None:
-        raise VectorStoreError("snapshots of a sharded store are not implemented yet")
-
     async def load(self, directory: str) -> None:
-        raise VectorStoreError("snapshots of a sharded store are not implemented yet")
+        """Additive, like ``B200VectorStore.load``: every rank reads its own shard file, rank 0 the host half.  The job must have as
+        many ranks as the one that saved."""
+        try:
+            _ = self.client
+
+            def work():
+                loaded = {}
+                for name in (CollectionName.CODE_CHUNKS.value, CollectionName.SUMMARIES.value):
+                    if os.path.exists(os.path.join(directory, f"{name}.host{self.plane.world}.pkl")):
+                        loaded[name] = _ShardedHostCollection.load(self.plane, directory, name)
+                return loaded
+            self._collections.update(await asyncio.to_thread(work))      # the workers replaced their shards in place
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to load collections from {directory}", cause=e)
 
     async def search_and_rank(self, *args, **kwargs):
         raise VectorStoreError("search_and_rank needs a single-GPU store created with rank_attrs=True")

@@ -119,6 +119,21 @@ class FakeDevice:
     def close(self):
         self.closed = True
 
+    def save_snapshot(self, path):
+        import pickle
+        with open(path, "wb") as f:
+            pickle.dump({"name": self.name, "dim": self.dim, "n_filter_cols": self.n_filter_cols, "ora": self.ora, "codes": self.codes,
+                         "ties": self.ties}, f)
+
+    @classmethod
+    def load_snapshot(cls, path, name=None, capacity=0, device=0):
+        import pickle
+        with open(path, "rb") as f:
+            st = pickle.load(f)
+        self = cls(name or st["name"], st["dim"], n_filter_cols=st["n_filter_cols"])
+        self.ora, self.codes, self.ties = st["ora"], st["codes"], st["ties"]
+        return self
+
 
 def merge_lists_numpy(scores: np.ndarray, rows: np.ndarray, ties: np.ndarray, k: int):
     """The K5 merge rule (score desc, tie asc, row asc) over [G, Q, k] lists; rows < 0 are padding."""

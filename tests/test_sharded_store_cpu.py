@@ -74,6 +74,18 @@ async def _sharded_specifics(make_store, world):
     # the filter-only lookup orders by id across shards
     _same_hits(await store.search(collection=CODE, query_vector=None, limit=40, filters={"project_name": "gamma"}),
                ora.search(CODE, None, limit=40, filters={"project_name": "gamma"}), what="sharded scroll")
+    # snapshot: every rank writes / reads its own shard, the restored store answers identically and keeps working
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        await store.save(d)
+        before = await store.search(collection=CODE, query_vector=q[1].tolist(), limit=9, filters={"language": "go"})
+        await store.delete(collection=CODE, filters={"project_name": "gamma"})            # diverge, then restore
+        assert (await store.get_collection_info(CODE)).points_count < ora.points_count(CODE)
+        await store.load(d)
+    coll = store._get(CODE)
+    assert (await store.get_collection_info(CODE)).points_count == ora.points_count(CODE)
+    after = await store.search(collection=CODE, query_vector=q[1].tolist(), limit=9, filters={"language": "go"})
+    assert [h["id"] for h in after] == [h["id"] for h in before] and [h["payload"] for h in after] == [h["payload"] for h in before]
     # a worker-side failure reaches the caller as VectorStoreError and the plane keeps working
     from code_rag_b200.errors import VectorStoreError
     store.plane.queue(world - 1, CODE, "no_such_write")
