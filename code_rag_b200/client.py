@@ -68,6 +68,18 @@ def _tie_key(point_id: Any) -> int:
     return uuid.UUID(point_id).int >> 64
 
 
+def vector_result_from_payload(p: dict[str, Any] | None, score: float, kind: str | None = "code") -> dict[str, Any]:
+    """The dict VectorSearcher hands to the ranker for a hit (query/vector_search.py:221-260): ``kind`` "summary" is
+    ``_transform_summary_result``, anything else ``_transform_code_result``."""
+    p = p or {}
+    if kind == "summary":
+        return {"score": score, "file_path": p.get("file_path"), "entity_type": p.get("entity_type"),
+                "entity_name": p.get("entity_name"), "summary": p.get("summary"), "graph_node_id": p.get("graph_node_id")}
+    return {"score": score, "file_path": p.get("file_path"), "entity_type": p.get("entity_type"),
+            "entity_name": p.get("entity_name"), "language": p.get("language"), "content": p.get("content"),
+            "start_line": p.get("start_line"), "end_line": p.get("end_line"), "graph_node_id": p.get("graph_node_id")}
+
+
 def _id_sort_key(point_id: Any):
     return (0, point_id, "") if isinstance(point_id, int) else (1, 0, point_id)
 
@@ -217,13 +229,7 @@ class _HostCollection:
 
     def vector_result(self, row: int, score: float) -> dict[str, Any]:
         """The dict VectorSearcher hands to the ranker for this row (query/vector_search.py:221-260)."""
-        p = self.payloads[row] or {}
-        if self.rank_kind == "summary":
-            return {"score": score, "file_path": p.get("file_path"), "entity_type": p.get("entity_type"),
-                    "entity_name": p.get("entity_name"), "summary": p.get("summary"), "graph_node_id": p.get("graph_node_id")}
-        return {"score": score, "file_path": p.get("file_path"), "entity_type": p.get("entity_type"),
-                "entity_name": p.get("entity_name"), "language": p.get("language"), "content": p.get("content"),
-                "start_line": p.get("start_line"), "end_line": p.get("end_line"), "graph_node_id": p.get("graph_node_id")}
+        return vector_result_from_payload(self.payloads[row], score, self.rank_kind)
 
     def vector_result_from_hit(self, hit: dict[str, Any]) -> dict[str, Any]:
         return self.vector_result(self.id_to_row[_canonical_id(hit["id"])], hit["score"])

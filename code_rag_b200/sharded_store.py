@@ -19,8 +19,8 @@ Process model - one process per GPU (``torchrun``), one of them in charge:
 Global row = ``shard << 32 | local row`` (a shard is created with ``row_base = rank << 32``), so a merged hit names its owner.
 
 A write is queued on the controller and sent with the next command (or at the end of the adapter call), one message per
-rank and call.  Snapshots: one ``.lvs`` file per rank plus the controller's host half.  Not offered on this store (single-GPU
-only): the fused search -> rank call.
+rank and call.  Snapshots: one ``.lvs`` file per rank plus the controller's host half.  ``search_and_rank`` is there too, as one
+batched search + one K3 launch (the device-resident form of it is single-GPU).
 """
 from __future__ import annotations
 
@@ -28,13 +28,13 @@ import asyncio
 import logging
 import os
 import threading
-from types import SimpleNamespace
 from typing import Any, Callable, Sequence
 
 import numpy as np
 
 from . import _native as N
-from .client import (B200VectorStore, CollectionName, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key)
+from .client import (B200VectorStore, CollectionName, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key,
+                     vector_result_from_payload)
 from .errors import VectorStoreError
 
 logger = logging.getLogger(__name__)
@@ -586,8 +586,40 @@ class ShardedB200VectorStore(B200VectorStore):
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to load collections from {directory}", cause=e)
 
-    async def search_and_rank(self, *args, **kwargs):
-        raise VectorStoreError("search_and_rank needs a single-GPU store created with rank_attrs=True")
+    async def search_and_rank(self, collection: str, items: Sequence[tuple], limit: int = 10,
+                              filters: dict[str, Any] | None = None, ranker=None, summaries: bool = False,
+                              summaries_filters: dict[str, Any] | None = None):
+        """Same call and same results as ``B200VectorStore.search_and_rank``, by the two-step route: ONE batched search over all
+        shards (plus one over ``summaries`` for the queries whose intent ``QueryEngine._execute_vector_search`` extends,
+        query/engine.py:331-344), the hits shaped as ``VectorSearcher`` shapes them (query/vector_search.py:221-260), then ONE
+        K3 launch on rank 0's GPU for the whole batch (``HybridRanker.rank_batch``).  The single-GPU store keeps the hits on
+        the device between the two; over shards the ranking attributes would have to be gathered per shard before the exchange."""
+        try:
+            coll = self._get(collection)
+            summ = CollectionName.SUMMARIES.value
+            coll2 = self._get(summ) if summaries and collection != summ and limit // 2 > 0 else None
+            from .ranking import SUMMARY_INTENTS, HybridRanker, _intent_value
+            rk = ranker or HybridRanker()
+            items = list(items)
+            if not items:
+                return []
+            q = np.asarray([it[2] for it in items], dtype=np.float64)
+            sel2 = [i for i, it in enumerate(items) if _intent_value(it[0].primary_intent) in SUMMARY_INTENTS] if coll2 else []
+            kind = "summary" if collection == summ else "code"
+
+            def work():
+                with coll.lock:
+                    hits = coll.search(q, limit, filters or None)
+                vector_results = [[vector_result_from_payload(h["payload"], h["score"], kind) for h in hs] for hs in hits]
+                if sel2:
+                    with coll2.lock:
+                        hits2 = coll2.search(q[sel2], limit // 2, summaries_filters or None)
+                    for i, hs in zip(sel2, hits2):
+                        vector_results[i].extend(vector_result_from_payload(h["payload"], h["score"], "summary") for h in hs)
+                return rk.rank_batch([(it[0], it[1], vr, it[3]) for it, vr in zip(items, vector_results)])
+            return await asyncio.to_thread(work)
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to search and rank in {collection}", cause=e)
 
 
 __all__ = ["ShardPlane", "ShardedB200VectorStore", "split_row", "least_full", "SHARD_BITS"]

@@ -74,6 +74,30 @@ async def _sharded_specifics(make_store, world):
     # the filter-only lookup orders by id across shards
     _same_hits(await store.search(collection=CODE, query_vector=None, limit=40, filters={"project_name": "gamma"}),
                ora.search(CODE, None, limit=40, filters={"project_name": "gamma"}), what="sharded scroll")
+    # search_and_rank (two-step over shards): the ranker receives, per query, exactly what VectorSearcher would hand it - code hits
+    # of the batched search, then limit // 2 summary hits for the intents QueryEngine extends (query/engine.py:331-344)
+    from types import SimpleNamespace as NS
+    from adapter_scenarios import SUMM
+    from code_rag_b200.client import vector_result_from_payload as shape
+    sx, _ = synth.unixcoder_like(30, dim, seed=35)
+    spl = [{"file_path": f"src/s{i}.py", "entity_type": "file", "entity_name": f"s{i}", "summary": f"summary {i}", "graph_node_id": f"m.s{i}"}
+           for i in range(30)]
+    sids = synth.random_uuids(30, seed=36)
+    await store.upsert(collection=SUMM, ids=sids, vectors=sx.astype(np.float64).tolist(), payloads=spl)
+    ora.upsert(SUMM, sids, sx.astype(np.float64).tolist(), spl)
+    seen = []
+    ranker = NS(rank_batch=lambda items: seen.append(items) or [f"ranked{i}" for i in range(len(items))])
+    intents = ["find_callers", "explain_architecture", "search_functionality", "find_similar"]
+    items = [(NS(primary_intent=NS(value=intents[i]), entities=[]), f"ctx{i}", q[i].tolist(), {"c": i}) for i in range(4)]
+    out = await store.search_and_rank(CODE, items, limit=7, filters={"project_name": "alpha"}, ranker=ranker, summaries=True)
+    assert out == ["ranked0", "ranked1", "ranked2", "ranked3"] and len(seen) == 1
+    for i, (plan, ctx, vr, cen) in enumerate(seen[0]):
+        assert plan is items[i][0] and ctx == f"ctx{i}" and cen == {"c": i}
+        exp = [shape(h["payload"], h["score"], "code") for h in ora.search(CODE, q[i].tolist(), limit=7, filters={"project_name": "alpha"})]
+        if intents[i] in ("explain_architecture", "search_functionality"):
+            exp += [shape(h["payload"], h["score"], "summary") for h in ora.search(SUMM, q[i].tolist(), limit=3)]
+        assert [{k: v for k, v in d.items() if k != "score"} for d in vr] == [{k: v for k, v in d.items() if k != "score"} for d in exp], i
+        assert np.allclose([d["score"] for d in vr], [d["score"] for d in exp], rtol=1e-5)
     # snapshot: every rank writes / reads its own shard, the restored store answers identically and keeps working
     import tempfile
     with tempfile.TemporaryDirectory() as d:
