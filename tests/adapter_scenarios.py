@@ -292,3 +292,67 @@ async def scenario_mass_delete_compacts(factory, n=2400, dim=48):
                        ora.search(CODE, q[qi].tolist(), limit=8, filters=f), what=f"after upserts q{qi} {f}")
     assert (await store.get_collection_info(CODE)).points_count == ora.points_count(CODE)
     await store.close()
+
+
+async def scenario_random_ops(factory, seed, storage="f32", steps=160, rel=1e-9):
+    """Random operation sequence: upserts of new and of existing ids, deletes by file, project clean-ups through .client, searches
+    with every filter shape, filter-only lookups, with frequent compaction; ids, payloads and scores must follow the oracle step
+    by step (the replay state included)."""
+    import random
+    from types import SimpleNamespace as NS
+
+    dim, n_ids = 32, 120
+    files = [f"src/f{i}.py" for i in range(7)]
+    projects = ["p0", "p1", "p2"]
+    rng = random.Random(seed)
+
+    def bf(v):
+        if storage != "bf16":
+            return v
+        u = np.asarray(v, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return ((((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32)).view(np.float32).astype(np.float64)
+
+    store = _store(factory, dimensions=dim, storage=storage)
+    ora = OracleManager(dim)
+    await store.connect(); await store.create_collections(); ora.create_collections()
+    coll = store._get("code_chunks")
+    shards = getattr(coll, "shards", [coll])            # the multi-GPU adapter keeps one bookkeeping object per shard
+    for sh in shards:
+        sh.COMPACT_MIN_FREE = 4
+    ids = [str(uuid.UUID(int=5000 + i)) for i in range(n_ids)]
+    for step in range(steps):
+        r = rng.random()
+        if r < 0.35 or step < 3:
+            slots = rng.sample(range(n_ids), rng.randint(1, 25))
+            salt = rng.randrange(10_000)
+            vecs = bf(np.random.default_rng(salt).standard_normal((len(slots), dim))).tolist()
+            pls = [{"file_path": files[(s + salt) % 7], "project_name": projects[(s * 5 + salt) % 3], "language": ("python", "go")[salt % 2],
+                    "entity_type": "function", "entity_name": f"fn{s}", "content": "x" * (s + 1), "start_line": s, "end_line": s + 1,
+                    "content_hash": f"h{salt % 4}"} for s in slots]
+            await store.upsert("code_chunks", [ids[s] for s in slots], vecs, pls)
+            ora.upsert("code_chunks", [ids[s] for s in slots], vecs, pls)
+        elif r < 0.45:
+            f = rng.choice(files)
+            await store.delete("code_chunks", {"file_path": f}); ora.delete("code_chunks", {"file_path": f})
+        elif r < 0.50:
+            p = rng.choice(projects)
+            flt = NS(must=[NS(key="project_name", match=NS(value=p))])
+            await store.client.delete(collection_name="code_chunks", points_selector=NS(filter=flt))
+            ora.delete("code_chunks", {"project_name": p})
+        elif r < 0.92:
+            q = np.random.default_rng(step * 31 + seed).standard_normal(dim).tolist()
+            flt = rng.choice([None, None, {"file_path": rng.choice(files)}, {"project_name": rng.choice(projects)},
+                              {"file_path": rng.choice(files), "language": "go"}, {"language": "rust"}])
+            k = rng.choice([1, 5, 10, 20])
+            _same_hits(await store.search("code_chunks", q, k, flt), ora.search("code_chunks", q, k, flt), rel=rel, what=f"step {step} {flt}")
+        else:
+            f = rng.choice(files)
+            got, exp = await store.search("code_chunks", None, 40, {"file_path": f}), ora.search("code_chunks", None, 40, {"file_path": f})
+            assert [h["id"] for h in got] == [h["id"] for h in exp], f"step {step}"
+        assert (await store.get_collection_info("code_chunks")).points_count == ora.points_count("code_chunks"), f"step {step}"
+    assert sum(len(sh.ids) for sh in shards) <= n_ids
+    if len(shards) == 1:
+        assert coll.dev.rows == len(coll.ids)
+    await store.close()
+
+

@@ -31,6 +31,7 @@ def main():
                 if storage == "f32":          # bf16 storage rounds the inputs: the 1e-5 bar of the scenario is the fp32 one
                     asyncio.run(S.scenario_parity_with_oracle(factory, n=3000, dim=256))
                     asyncio.run(_sharded_specifics(factory.make_store, plane.world))
+                asyncio.run(S.scenario_random_ops(factory, 4, storage=storage))
                 asyncio.run(S.scenario_errors(factory))
                 asyncio.run(S.scenario_client_shim(factory))
                 print(f"sharded store [{storage}] over {plane.world} GPU(s): OK", flush=True)

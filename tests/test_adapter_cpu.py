@@ -27,3 +27,8 @@ def test_reindex_churn_reuses_rows():
 
 def test_mass_delete_compacts():
     asyncio.run(S.scenario_mass_delete_compacts(FakeDevice))
+
+
+def test_random_operation_sequences_match_the_oracle():
+    for seed in (1, 2):
+        asyncio.run(S.scenario_random_ops(FakeDevice, seed))

@@ -142,6 +142,8 @@ def _worker(rank, world, port, out_dir):
                 asyncio.run(S.scenario_errors(factory))
                 asyncio.run(S.scenario_client_shim(factory))
                 asyncio.run(_sharded_specifics(factory.make_store, world))
+                for seed in (1, 2):
+                    asyncio.run(S.scenario_random_ops(factory, seed))
             except BaseException:  # noqa: BLE001
                 status = traceback.format_exc()
             finally:
