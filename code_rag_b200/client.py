@@ -107,6 +107,11 @@ class _HostCollection:
         # rows of deleted points, reused by later upserts: VectorIndexer.index_file (embeddings/indexer.py:61-77) deletes a
         # file's chunks and inserts new ones under fresh uuid4 ids on every re-index, so without reuse a shard only grows
         self.free_rows: list[int] = []
+        # The device orders equal scores by a 64-bit key derived from the id (_tie_key), then by row.  Ids that share their key
+        # (uuids equal in their leading 64 bits: never uuid4, but e.g. uuid.UUID(int=small)) would come back in row order, so
+        # the keys carried by more than one live point are tracked and such hits are put in id order on the host (search()).
+        self.tie_counts: dict[int, int] = {}
+        self.dup_keys: dict[int, int] = {}
         self.lock = threading.Lock()
         # dev_factory exists so that the host-side bookkeeping can be unit-tested without a GPU (tests only)
         factory = dev_factory or DeviceCollection
@@ -175,6 +180,49 @@ class _HostCollection:
             want[col] = code
         return want
 
+    # -- order among exactly equal scores ----------------------------------------------------------------------
+    def _tie_add(self, key: int) -> None:
+        c = self.tie_counts.get(key, 0) + 1
+        self.tie_counts[key] = c
+        if c > 1:
+            self.dup_keys[key] = c
+
+    def _tie_drop(self, key: int) -> None:
+        c = self.tie_counts.get(key, 0) - 1
+        if c <= 0:
+            self.tie_counts.pop(key, None)
+        else:
+            self.tie_counts[key] = c
+        if c > 1:
+            self.dup_keys[key] = c
+        else:
+            self.dup_keys.pop(key, None)
+
+    def rebuild_tie_counts(self) -> None:
+        self.tie_counts.clear(); self.dup_keys.clear()
+        for pid in self.ids:
+            if pid is not None:
+                self._tie_add(_tie_key(pid))
+
+    def device_limit(self, limit: int) -> int:
+        """How many hits to ask the device for so that the best `limit` in (score desc, id asc) order are among them: the run of
+        equal (score, key) hits that straddles the cut has at most max(dup_keys) members.  Bounded by MAX_TIE_RUN - 1 extra
+        hits (one device call, whatever the ids look like): runs of more than MAX_TIE_RUN bit-identical vectors under ids with
+        one key are cut in row order."""
+        if not self.dup_keys:
+            return limit
+        return min(N.MAX_K, limit + min(max(self.dup_keys.values()), self.MAX_TIE_RUN) - 1)
+
+    MAX_TIE_RUN = 16
+
+    def in_id_order(self, rows: np.ndarray, scores: np.ndarray, limit: int, id_of=None) -> tuple[np.ndarray, np.ndarray]:
+        """(score desc, id asc) - BASELINE.json's rule - for hits that came back ordered by (score desc, key asc, row asc)."""
+        if self.dup_keys and len(rows) > 1:
+            id_of = id_of or (lambda r: self.ids[r])
+            order = sorted(range(len(rows)), key=lambda j: (-float(scores[j]), _id_sort_key(id_of(int(rows[j])))))
+            rows, scores = rows[order], scores[order]
+        return rows[:limit], scores[:limit]
+
     # -- operations (called under self.lock) ---------------------------------------------------------------
     def upsert(self, ids, vectors, payloads) -> None:
         n = len(ids)
@@ -218,10 +266,12 @@ class _HostCollection:
         for pid, r in reused:
             self.id_to_row[pid] = r
             self.ids[r] = pid
+            self._tie_add(_tie_key(pid))
         for pid in new_ids:
             self.id_to_row[pid] = len(self.ids)
             self.ids.append(pid)
             self.payloads.append(None)
+            self._tie_add(_tie_key(pid))
         for j, r in enumerate(rows):
             self.payloads[int(r)] = pl[j]
         if self.rank_kind is not None:
@@ -282,14 +332,14 @@ class _HostCollection:
             return [self._hits(np.asarray(order, dtype=np.int64), np.zeros(len(order)))]
         if limit > N.MAX_K:
             raise ValueError(f"limit {limit} exceeds the largest supported top-k ({N.MAX_K})")
-        res = self.dev.search(query_vectors, limit, want)
+        res = self.dev.search(query_vectors, self.device_limit(limit), want)
         out = []
         for qi in range(res.rows.shape[0]):
             n = int(res.counts[qi])
             if res.flags[qi] & N.FLAG_UNPROVEN:
                 logger.warning("search on %s: exactness bound not met for query %d (many near-ties); "
                                "result is the best of the largest candidate set", self.name, qi)
-            out.append(self._hits(res.rows[qi, :n], res.scores[qi, :n]))
+            out.append(self._hits(*self.in_id_order(res.rows[qi, :n], res.scores[qi, :n], limit)))
         return out
 
     def release_rows(self, rows) -> None:
@@ -299,6 +349,7 @@ class _HostCollection:
             if pid is None:
                 continue
             self.id_to_row.pop(pid, None)
+            self._tie_drop(_tie_key(pid))
             self.ids[r] = None
             self.payloads[r] = None
             self.free_rows.append(r)
@@ -383,6 +434,8 @@ class _HostCollection:
         for k in cls._HOST_STATE:
             setattr(self, k, state[k])
         self.lock = threading.Lock()
+        self.tie_counts, self.dup_keys = {}, {}
+        self.rebuild_tie_counts()
         self.dev = DeviceCollection.load_snapshot(os.path.join(directory, f"{name}.lvs"), name=name, device=device)
         if self.dev.rows != len(self.ids):
             raise ValueError(f"snapshot of {name}: {self.dev.rows} device rows but {len(self.ids)} host rows")

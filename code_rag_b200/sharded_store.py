@@ -33,7 +33,7 @@ from typing import Any, Callable, Sequence
 import numpy as np
 
 from . import _native as N
-from .client import (B200VectorStore, CollectionName, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key,
+from .client import (B200VectorStore, CollectionName, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key, _tie_key,
                      vector_result_from_payload)
 from .errors import VectorStoreError
 
@@ -303,6 +303,7 @@ class _HostShard(_HostCollection):
         super().__init__(owner.name, owner.dim, owner.storage, owner.columns, owner.plane.device,
                          dev_factory=lambda *a, **kw: _ShardProxy(owner.plane, owner.name, shard))
         self.columns, self.dicts = owner.columns, owner.dicts          # shared objects
+        self.tie_counts, self.dup_keys = owner.tie_counts, owner.dup_keys     # ids meet in the merged list whatever their shard
         self.owner = owner
 
     def ensure_column(self, key: str) -> int:
@@ -330,6 +331,8 @@ class _ShardedHostCollection:
         self.plane, self.name, self.dim, self.storage = plane, name, dim, storage
         self.columns: list[str] = list(index_fields)[: N.MAX_FILTER_COLS]
         self.dicts: list[dict[Any, int]] = [dict() for _ in self.columns]
+        self.tie_counts: dict[int, int] = {}
+        self.dup_keys: dict[int, int] = {}
         self.lock = threading.Lock()
         plane.call("create", name, (dim, storage, N.MAX_FILTER_COLS))
         self.shards = [_HostShard(self, s) for s in range(plane.world)]
@@ -360,11 +363,15 @@ class _ShardedHostCollection:
         self = cls.__new__(cls)
         self.plane, self.name, self.dim, self.storage = plane, name, state["dim"], state["storage"]
         self.columns, self.dicts = state["columns"], state["dicts"]
+        self.tie_counts, self.dup_keys = {}, {}
         self.lock = threading.Lock()
         self.shards = [_HostShard(self, s) for s in range(plane.world)]
         for sh, st in zip(self.shards, state["shards"]):
             for k in cls._SHARD_STATE:
                 setattr(sh, k, st[k])
+            for pid in sh.ids:
+                if pid is not None:
+                    sh._tie_add(_tie_key(pid))
         with plane.lock:
             rows = plane.call("snapshot_load", name, str(directory))
         if rows != [len(sh.ids) for sh in self.shards]:
@@ -421,6 +428,10 @@ class _ShardedHostCollection:
                 self.shards[s].upsert([canon[i] for i in idx], vec[idx], [payloads[i] for i in idx])
         self.plane.flush()
 
+    def _id_of(self, global_row: int):
+        s, r = split_row(global_row)
+        return self.shards[s].ids[r]
+
     def _hits(self, rows: np.ndarray, scores: np.ndarray) -> list[dict[str, Any]]:
         out = []
         for g, sc in zip(rows.tolist(), scores.tolist()):
@@ -452,13 +463,14 @@ class _ShardedHostCollection:
             raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
         if np.isnan(q).any():
             raise ValueError("Query vector must not contain NaN")
-        scores, rows, counts, flags = self.plane.call("search", self.name, (q, int(limit), want))[0]
+        k_dev = self.shards[0].device_limit(int(limit))
+        scores, rows, counts, flags = self.plane.call("search", self.name, (q, k_dev, want))[0]
         out = []
         for qi in range(rows.shape[0]):
             n = int(counts[qi])
             if int(flags[qi]) & N.FLAG_UNPROVEN:
                 logger.warning("search on %s: exactness bound not met for query %d (many near-ties)", self.name, qi)
-            out.append(self._hits(rows[qi, :n], scores[qi, :n]))
+            out.append(self._hits(*self.shards[0].in_id_order(rows[qi, :n], scores[qi, :n], limit, self._id_of)))
         return out
 
     def scroll(self, filters, limit: int):

@@ -356,3 +356,43 @@ async def scenario_random_ops(factory, seed, storage="f32", steps=160, rel=1e-9)
     await store.close()
 
 
+
+
+async def scenario_exact_ties_follow_the_id(factory, dim=16):
+    """Identical vectors under ids that share their leading 64 bits (uuid.UUID(int=small)): the device can only order such hits
+    by row, the adapter must return them in id order (BASELINE.json: score desc, id asc) - also when the run of equal hits
+    straddles `limit`, with a filter, after deletes, and next to ordinary uuid4 ids.  Checked against the rule itself (the
+    oracle's BLAS product gives identical rows position-dependent scores); needs a device with position-independent scores
+    (helpers.ExactTieDevice on CPU, the GPU)."""
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((3, dim))
+    store = _store(factory, dimensions=dim)
+    await store.connect(); await store.create_collections()
+    crafted = [str(uuid.UUID(int=1000 + i)) for i in range(12)]
+    order = [7, 2, 11, 0, 5, 9, 1, 3, 10, 4, 8, 6]                       # rows are assigned in this order, ids must win
+    ids = [crafted[i] for i in order] + synth.random_uuids(6, seed=2)
+    which = [0] * 8 + [1] * 4 + [2] * 3 + [0] * 3
+    pl = [{"file_path": f"f{i % 2}.py", "entity_name": f"e{i}"} for i in range(18)]
+    for lo, hi in ((0, 5), (5, 18)):
+        await store.upsert(CODE, ids[lo:hi], [v[w].tolist() for w in which[lo:hi]], pl[lo:hi])
+    live = set(range(18))
+
+    def expected(q, limit, flt):
+        cos = [float(np.dot(v[w], q) / np.linalg.norm(v[w]) / np.linalg.norm(q)) for w in which]
+        pts = [i for i in sorted(live) if flt is None or all(pl[i].get(k) == val for k, val in flt.items())]
+        return [str(uuid.UUID(ids[i])) for i in sorted(pts, key=lambda i: (-round(cos[i], 9), str(uuid.UUID(ids[i]))))[:limit]]
+
+    async def check(what):
+        for q in (v[0], v[1], v[0] + v[1]):
+            for limit in (1, 3, 5, 8, 11, 18):
+                for flt in (None, {"file_path": "f1.py"}):
+                    got = await store.search(CODE, q.tolist(), limit, flt)
+                    assert [h["id"] for h in got] == expected(q, limit, flt), f"{what}: limit={limit} {flt}"
+                    assert all(a["score"] >= b["score"] for a, b in zip(got, got[1:]))
+    await check("ties")
+    await store.delete(CODE, {"entity_name": "e3"}); live.discard(3)
+    await store.delete(CODE, {"entity_name": "e16"}); live.discard(16)
+    await check("ties after deletes")
+    got = await store.search_batch(CODE, [v[0].tolist(), v[1].tolist()], limit=4)
+    assert [[h["id"] for h in g] for g in got] == [expected(v[0], 4, None), expected(v[1], 4, None)]
+    await store.close()

@@ -135,6 +135,31 @@ class FakeDevice:
         return self
 
 
+class ExactTieDevice(FakeDevice):
+    """FakeDevice whose scores do not depend on where a row sits in the matrix: identical rows get bit-identical scores, as on the
+    GPU (one warp re-scores a candidate with a fixed reduction order).  The oracle's BLAS matrix-vector product does not have that
+    property (rows in a tail block are accumulated differently), so exact-tie behaviour is tested against the RULE
+    (score desc, id asc), not against the oracle's noise.  TESTS ONLY."""
+
+    def search(self, queries, k, want=None):
+        q = np.atleast_2d(np.asarray(queries, dtype=np.float64))
+        Q = q.shape[0]
+        res = SearchResult(np.zeros((Q, k)), np.full((Q, k), -1, dtype=np.int64), np.zeros((Q, k), dtype=np.uint64),
+                           np.zeros(Q, dtype=np.uint32), np.zeros(Q, dtype=np.int32))
+        mask = self._mask(want)
+        for i in range(Q):
+            self.ora._scores(q[i])                                  # the in-place re-normalisation of local mode
+            qn = q[i] / np.linalg.norm(q[i])
+            m = self.ora.vectors[:self.rows].astype(np.float64)
+            scores = np.array([np.dot(m[r], qn) for r in range(self.rows)])      # 1-D dot: the same arithmetic for every row
+            cand = np.nonzero(mask)[0]
+            order = cand[np.lexsort((cand, self.ties[cand], -scores[cand]))][:k]
+            res.rows[i, :len(order)] = order
+            res.scores[i, :len(order)] = scores[order]
+            res.counts[i] = len(order)
+        return res
+
+
 def merge_lists_numpy(scores: np.ndarray, rows: np.ndarray, ties: np.ndarray, k: int):
     """The K5 merge rule (score desc, tie asc, row asc) over [G, Q, k] lists; rows < 0 are padding."""
     G, Q, _ = scores.shape

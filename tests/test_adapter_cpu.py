@@ -2,7 +2,7 @@
 import asyncio
 
 import adapter_scenarios as S
-from helpers import FakeDevice
+from helpers import ExactTieDevice, FakeDevice
 
 
 def test_database_scenario():
@@ -32,3 +32,7 @@ def test_mass_delete_compacts():
 def test_random_operation_sequences_match_the_oracle():
     for seed in (1, 2):
         asyncio.run(S.scenario_random_ops(FakeDevice, seed))
+
+
+def test_exact_ties_follow_the_id():
+    asyncio.run(S.scenario_exact_ties_follow_the_id(ExactTieDevice))

@@ -8,7 +8,7 @@ import uuid
 from types import SimpleNamespace as NS
 
 import numpy as np
-from hypothesis import HealthCheck, given, settings
+from hypothesis import HealthCheck, example, given, settings
 from hypothesis import strategies as st
 
 from code_rag_b200.client import B200VectorStore
@@ -35,8 +35,11 @@ def _payload(slot: int, salt: int) -> dict:
             "content_hash": f"h{salt % 4}"}
 
 
-@settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+# derandomize: the gate explores the same 100 sequences on every run (a find made by a random run is kept as an @example)
+@settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.too_slow], derandomize=True)
 @given(st.lists(op, min_size=1, max_size=25))
+# identical vectors under two ids that share their 64-bit tie key: the hits must still come back in id order (client.in_id_order)
+@example([("upsert", [0, 3, 2], 1), ("upsert", [0, 1, 3], 1), ("search", 0, None, 1)])
 def test_store_and_oracle_agree_after_every_operation(ops):
     async def run():
         store = B200VectorStore(dimensions=DIM, _device_factory=FakeDevice)

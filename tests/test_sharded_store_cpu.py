@@ -1,7 +1,7 @@
 """The multi-GPU adapter's host logic on CPU: a gloo job (world size 2 and 3) in which rank 0 drives a ``ShardedB200VectorStore``
 through the SAME scenarios as the single-GPU adapter (tests/adapter_scenarios.py: the reference's database test, parity with the
 oracle's QdrantManager over every filter shape, the error convention, the ``.client`` shim) while the other ranks sit in
-``ShardPlane.serve()``.  Each rank's shard is the oracle-backed FakeDevice; the exchange step is the real packed all-gather.
+``ShardPlane.serve()``.  Each rank's shard is the oracle-backed FakeDevice (its position-independent form, helpers.ExactTieDevice); the exchange step is the real packed all-gather.
 Placement (least-full shard), overwrite in place, per-shard row reuse and compaction are checked on top."""
 import asyncio
 import os
@@ -127,9 +127,9 @@ def _worker(rank, world, port, out_dir):
     status = "ok"
     try:
         import torch.distributed as dist
-        from helpers import FakeDevice, FakeShardSearcher
+        from helpers import ExactTieDevice, FakeShardSearcher
         from code_rag_b200.sharded_store import ShardedB200VectorStore, ShardPlane
-        plane = ShardPlane.start(device_factory=FakeDevice, searcher_factory=FakeShardSearcher)
+        plane = ShardPlane.start(device_factory=ExactTieDevice, searcher_factory=FakeShardSearcher)
         if rank != 0:
             plane.serve()
         else:
@@ -144,6 +144,7 @@ def _worker(rank, world, port, out_dir):
                 asyncio.run(_sharded_specifics(factory.make_store, world))
                 for seed in (1, 2):
                     asyncio.run(S.scenario_random_ops(factory, seed))
+                asyncio.run(S.scenario_exact_ties_follow_the_id(factory))
             except BaseException:  # noqa: BLE001
                 status = traceback.format_exc()
             finally:
@@ -158,7 +159,9 @@ def _run(world, tmp_path):
     port = 31000 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        assert Path(tmp_path, f"rank{r}.txt").read_text() == "ok", f"rank {r}"
+        status = Path(tmp_path, f"rank{r}.txt").read_text()
+        if status != "ok":
+            raise AssertionError(f"rank {r}:\n{status}")
 
 
 def test_sharded_store_world2(tmp_path):
