@@ -1,4 +1,5 @@
-"""Runs the REFERENCE's own callers of the vector store (query/vector_search.py, embeddings/indexer.py) against
+"""Runs the REFERENCE's own callers of the vector store (query/vector_search.py, embeddings/indexer.py, query/context/builder.py,
+projects/cleanup.py, and query/ranking fed with the adapter's hits) against
 B200VectorStore.  Executed in a fresh interpreter by tests/test_reference_callers_cpu.py (build container only: it
 needs /root/reference).  `qdrant_client` is not installed, so a stub module satisfies the import of
 lattice/embeddings/client.py; the reference classes under test are the unmodified files."""
@@ -28,9 +29,22 @@ for pkg in ("lattice", "lattice.embeddings", "lattice.query", "lattice.parsing",
 qc = ns("qdrant_client")
 qc.AsyncQdrantClient = object
 qc.models = ns("qdrant_client.models")
+class _Model:
+    """Keyword-constructed record, as the pydantic models of qdrant_client.models are used by projects/cleanup.py:47-73."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
 for _n in ("Filter", "CollectionInfo", "FieldCondition", "MatchValue", "MatchText", "PointStruct", "VectorParams", "Distance",
            "PayloadSchemaType", "FilterSelector"):
-    setattr(qc.models, _n, type(_n, (), {}))          # only named in annotations / never called on this path
+    setattr(qc.models, _n, type(_n, (_Model,), {}))
+ns("lattice.projects", SRC + "/lattice/projects")
+ns("lattice.query.context", SRC + "/lattice/query/context")
+_neo = ns("neo4j")                                     # graph/client.py imports it; nothing on this path talks to a graph
+_neo.AsyncGraphDatabase = _neo.AsyncDriver = _neo.AsyncSession = object
+_ne = ns("neo4j.exceptions")
+_ne.ServiceUnavailable = _ne.Neo4jError = _ne.AuthError = Exception
 
 from lattice.core.errors import IndexingError, QueryError, VectorStoreError  # noqa: E402  (reference classes)
 from lattice.embeddings.chunker import CodeChunk  # noqa: E402
@@ -103,6 +117,37 @@ async def main(use_gpu: bool):
     legacy = LegacySearcher(store, Embedder())
     res = await legacy.search_code("/repo/pkg/f3.py chunk 0", limit=5, entity_type="function")
     assert res[0].content == "/repo/pkg/f3.py chunk 0" and res[0].start_line == 1
+
+    # ContextBuilder._build_entity_context (query/context/builder.py:103-133): the filter-only lookup, query_vector=None
+    from lattice.query.context.builder import ContextBuilder
+    from lattice.query.graph_reasoning import GraphContext, GraphNode
+    empty = GraphContext([], [], [], [], [], [], [], [], [], [], [], [])
+    node = GraphNode(node_type="Function", name="fn1", qualified_name="m.fn1", file_path="/repo/pkg/f3.py", start_line=11, end_line=19)
+    ctx = await ContextBuilder(memgraph=None, qdrant=store)._build_entity_context(node, empty)
+    assert ctx.code_snippet is not None and ctx.code_snippet.content == "/repo/pkg/f3.py chunk 1" and ctx.code_snippet.language == "python"
+    ghost = GraphNode(node_type="Function", name="nope", qualified_name="m.nope", file_path="/repo/pkg/f3.py")
+    assert (await ContextBuilder(memgraph=None, qdrant=store)._build_entity_context(ghost, empty)).code_snippet is None
+
+    # the reference's own HybridRanker over the adapter's hits (query/engine.py:176-181) == this repo's ranking mirror's host half
+    # is covered elsewhere; here: the hit dicts are what ranker.py:150-169 reads
+    from lattice.query.ranking import HybridRanker as RefRanker
+    from lattice.query.query_planner import ExtractedEntity, QueryIntent, QueryPlan
+    plan = QueryPlan(original_query="fn2", primary_intent=QueryIntent.FIND_SIMILAR, sub_queries=[],
+                     entities=[ExtractedEntity(name="fn2", entity_type="function")], relationships=[])
+    ranked = RefRanker().rank_results(plan, empty, hits, {})
+    assert ranked and ranked[0].source == "vector" and {r.file_path for r in ranked} <= {h["file_path"] for h in hits}
+    assert any(r.entity_name == "fn2" and r.signal_scores["query_entity_match"] == 1.0 for r in ranked)
+
+    # ProjectCleanupService (projects/cleanup.py:12-73): MatchText count + delete through manager.client, both collections
+    from lattice.projects.cleanup import ProjectCleanupService
+    cleanup = ProjectCleanupService(store)
+    assert await cleanup.get_chunk_count("/repo/pkg/f4.py") == 8 and await cleanup.get_chunk_count("/repo/pkg/") == 27
+    assert await cleanup.delete_from_qdrant("/repo/pkg/f4.py") == 0          # it returns what is LEFT (cleanup.py:58-63)
+    assert (await store.get_collection_info("code_chunks")).points_count == 27 - 8
+    assert await cleanup.delete_from_qdrant("/repo/pkg/") == 0
+    assert (await store.get_collection_info("code_chunks")).points_count == 0
+    assert (await store.get_collection_info("summaries")).points_count == 0
+    assert await cleanup.get_chunk_count("/repo/pkg/") == 0
 
     await store.close()
     try:                                                                   # vector store failures surface as QueryError
