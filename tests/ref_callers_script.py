@@ -1,5 +1,5 @@
 """Runs the REFERENCE's own callers of the vector store (query/vector_search.py, embeddings/indexer.py, query/context/builder.py,
-projects/cleanup.py, and query/ranking fed with the adapter's hits) against
+projects/cleanup.py, QueryEngine._execute_vector_search, and query/ranking fed with the adapter's hits) against
 B200VectorStore.  Executed in a fresh interpreter by tests/test_reference_callers_cpu.py (build container only: it
 needs /root/reference).  `qdrant_client` is not installed, so a stub module satisfies the import of
 lattice/embeddings/client.py; the reference classes under test are the unmodified files."""
@@ -40,7 +40,6 @@ for _n in ("Filter", "CollectionInfo", "FieldCondition", "MatchValue", "MatchTex
            "PayloadSchemaType", "FilterSelector"):
     setattr(qc.models, _n, type(_n, (_Model,), {}))
 ns("lattice.projects", SRC + "/lattice/projects")
-ns("lattice.query.context", SRC + "/lattice/query/context")
 _neo = ns("neo4j")                                     # graph/client.py imports it; nothing on this path talks to a graph
 _neo.AsyncGraphDatabase = _neo.AsyncDriver = _neo.AsyncSession = object
 _ne = ns("neo4j.exceptions")
@@ -137,6 +136,19 @@ async def main(use_gpu: bool):
     ranked = RefRanker().rank_results(plan, empty, hits, {})
     assert ranked and ranked[0].source == "vector" and {r.file_path for r in ranked} <= {h["file_path"] for h in hits}
     assert any(r.entity_name == "fn2" and r.signal_scores["query_entity_match"] == 1.0 for r in ranked)
+
+    # QueryEngine._execute_vector_search (query/engine.py:315-346): code hits, then limit // 2 summaries hits for the
+    # five intents it extends - the reference's own engine object over the adapter (no initialize(): only the vector leg runs)
+    from lattice.query.engine import QueryEngine
+    engine = QueryEngine(qdrant=store, vector_searcher=searcher)
+    plan_sf = QueryPlan(original_query="summary of fn0", primary_intent=QueryIntent.SEARCH_FUNCTIONALITY, sub_queries=[], entities=[],
+                        relationships=[])
+    both = await engine._execute_vector_search("summary of fn0", plan_sf, limit=6, language="python")
+    assert len(both) == 6 + 1 and all("content" in h for h in both[:6]) and both[6]["summary"] == "summary of fn0"
+    only_code = await engine._execute_vector_search("summary of fn0", plan, limit=6, language="python")
+    assert only_code == both[:6]
+    ranked2 = engine._ranker.rank_results(plan_sf, empty, both, {})
+    assert len(ranked2) == 7 and any(r.summary == "summary of fn0" for r in ranked2)
 
     # ProjectCleanupService (projects/cleanup.py:12-73): MatchText count + delete through manager.client, both collections
     from lattice.projects.cleanup import ProjectCleanupService
