@@ -32,6 +32,12 @@ def test_mass_delete_compacts(native_lib):
     asyncio.run(S.scenario_mass_delete_compacts(None))
 
 
+def test_exact_ties_follow_the_id(native_lib):
+    """Bit-identical vectors under ids that share their 64-bit tie key come back in id order (the device gives them identical
+    scores; the adapter orders them, tests/adapter_scenarios.py)."""
+    asyncio.run(S.scenario_exact_ties_follow_the_id(None))
+
+
 def test_snapshot_restore_continues_exactly(native_lib, tmp_path):
     """a saved store, loaded into a fresh process state, answers every later search (filters, deletes,
     upserts included) exactly as the original does - scores bit for bit, because the local-mode replay state (search counter,
