@@ -19,7 +19,7 @@ Process model - one process per GPU (``torchrun``), one of them in charge:
 Global row = ``shard << 32 | local row`` (a shard is created with ``row_base = rank << 32``), so a merged hit names its owner.
 
 A write is queued on the controller and sent with the next command (or at the end of the adapter call), one message per
-rank and call.  Snapshots: one ``.lvs`` file per rank plus the controller's host half.  ``search_and_rank`` is there too, as one
+rank and call.  After deletes the shards compact themselves and, when a mass delete left them uneven, are rebalanced.  Snapshots: one ``.lvs`` file per rank plus the controller's host half.  ``search_and_rank`` is there too, as one
 batched search + one K3 launch (the device-resident form of it is single-GPU).
 """
 from __future__ import annotations
@@ -239,6 +239,14 @@ class ShardPlane:
 
     def _op_count(self, name, common):
         return int(self.shards[name].count())
+
+    def _op_fetch(self, name, common):
+        """common: {rank: local rows}; the named ranks return their stored vectors (float32, as stored)."""
+        rows = common.get(self.rank)
+        if rows is None:
+            return None
+        dev = self.shards[name]
+        return dev.fetch_rows(np.asarray(rows, dtype=np.int64) + int(getattr(dev, "row_base", 0)))
 
     def _shard_file(self, directory: str, name: str) -> str:
         return os.path.join(directory, f"{name}.shard{self.rank}of{self.world}.lvs")
@@ -482,6 +490,40 @@ class _ShardedHostCollection:
                 sh.release_rows(rows)
                 sh.maybe_compact()
         self.plane.flush()
+        self.rebalance()
+
+    REBALANCE_MIN_GAP = 4096       # like compaction: only when it pays (the step time of a search is its LARGEST shard's scan)
+
+    @_whole_op
+    def rebalance(self, force: bool = False) -> int:
+        """Shard rebalancing.  New points already go to the least-full shard, so growth evens a
+        collection out by itself; after a mass delete that hit the shards unevenly (a project whose files were indexed in one
+        stretch) the fullest shard keeps bounding every search.  When the fullest and the emptiest shard differ by at least
+        REBALANCE_MIN_GAP points AND a quarter of the mean (`force`: by more than one point), half of the gap moves: the tail
+        rows of the fullest shard are read back (`fetch_rows`), written to the emptiest one under the same ids and payloads,
+        deleted at the source, and the source is compacted.  Returns the number of points moved.  A moved point is a fresh
+        write at its new home (bf16 shards: the same bits; fp32 shards: re-normalised, i.e. within one float32 ulp)."""
+        moved = 0
+        for _ in range(4 * len(self.shards)):
+            live = self.live_counts()
+            hi = max(range(len(live)), key=live.__getitem__)
+            lo = least_full(live)
+            gap = live[hi] - live[lo]
+            mean = sum(live) / len(live)
+            if gap <= 1 or not (force or (gap >= self.REBALANCE_MIN_GAP and 4 * gap >= mean)):
+                break
+            src, dst, n = self.shards[hi], self.shards[lo], gap // 2
+            rows = [r for r in range(len(src.ids) - 1, -1, -1) if src.ids[r] is not None][:n]
+            self.plane.flush()
+            vec = self.plane.call("fetch", self.name, {hi: np.asarray(rows, dtype=np.int64)})[hi]
+            ids, pls = [src.ids[r] for r in rows], [src.payloads[r] for r in rows]
+            src.dev.delete_rows(rows)
+            src.release_rows(rows)
+            dst.upsert(ids, np.asarray(vec, dtype=np.float64), pls)
+            src.maybe_compact(force=True)
+            self.plane.flush()
+            moved += len(rows)
+        return moved
 
     @_whole_op
     def delete(self, filters) -> int:
@@ -581,6 +623,22 @@ class ShardedB200VectorStore(B200VectorStore):
         info.shards = self.plane.world
         info.shard_points = self._get(collection).live_counts()
         return info
+
+    async def rebalance(self, collection: str | None = None, force: bool = True) -> int:
+        """Additive: even out the shards of one collection (or of both) now; deletes do it by themselves once the gap is large
+        (``_ShardedHostCollection.rebalance``).  Returns the number of points moved."""
+        try:
+            colls = [self._get(collection)] if collection else [self._get(n) for n in self._collections]
+
+            def work():
+                total = 0
+                for coll in colls:
+                    with coll.lock:
+                        total += coll.rebalance(force=force)
+                return total
+            return await asyncio.to_thread(work)
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError("Failed to rebalance the shards", cause=e)
 
     async def load(self, directory: str) -> None:
         """Additive, like ``B200VectorStore.load``: every rank reads its own shard file, rank 0 the host half.  The job must have as

@@ -119,6 +119,9 @@ class FakeDevice:
     def close(self):
         self.closed = True
 
+    def fetch_rows(self, rows):
+        return self.ora.vectors[np.asarray(rows)].copy()
+
     def save_snapshot(self, path):
         import pickle
         with open(path, "wb") as f:
