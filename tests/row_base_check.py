@@ -34,6 +34,10 @@ def main():
                 rows_o, scores_o = ora.search_topk_rows(q[i].astype(np.float64), k)
                 assert np.array_equal(res.rows[i] - base, rows_o), (storage, Q, i, res.rows[i], rows_o)
                 assert np.allclose(res.scores[i], scores_o, rtol=1e-9, atol=1e-12)
+        pick = np.array([0, 17, n - 1, 4242])
+        got = dev.fetch_rows(base + pick)                      # what the sharded adapter's rebalancing reads back
+        exp = xs[pick] if storage == "bf16" else (xs[pick].astype(np.float64) / np.linalg.norm(xs[pick].astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+        assert got.shape == exp.shape and np.array_equal(got, exp), (storage, np.abs(got - exp).max())
         want = np.full(8, ANY, dtype=np.uint32); want[0] = 2
         rows, m = dev.match_rows(want)
         assert m == len(rows) == (n + 1) // 3 and np.array_equal(np.sort(rows) - base, np.nonzero(codes[:, 0] == 2)[0]), (m, len(rows))   # unordered
