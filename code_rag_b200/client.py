@@ -404,6 +404,9 @@ class _HostCollection:
                 out.append(r)
         return out
 
+    def point(self, row: int) -> tuple[Any, dict[str, Any] | None]:
+        return self.ids[row], self.payloads[row]
+
     def delete_found(self, rows: Sequence[int]) -> None:
         if len(rows):
             self.dev.delete_rows(np.asarray(rows, dtype=np.int64))
@@ -444,7 +447,7 @@ class _HostCollection:
 
 class _ClientShim:
     """What ``manager.client`` exposes (reference callers reach through it: projects/cleanup.py:41-61,
-    tests/test_database.py:81).  Filters are duck-typed ``models.Filter`` objects (``.must[i].key``,
+    tests/test_database.py:81; ``scroll`` and ``query_points`` are the two calls QdrantManager itself makes, client.py:142,182).  Filters are duck-typed ``models.Filter`` objects (``.must[i].key``,
     ``.match.value`` / ``.match.text``)."""
 
     def __init__(self, store: "B200VectorStore"):
@@ -492,6 +495,37 @@ class _ClientShim:
                 return len(rows)
         await asyncio.to_thread(work)
         return SimpleNamespace(status="completed")
+
+    async def scroll(self, collection_name: str, scroll_filter=None, limit: int = 10, offset=None, with_payload: bool = True,
+                     with_vectors: bool = False, **_ignored):
+        """``AsyncQdrantClient.scroll`` as ``QdrantManager.file_needs_update`` uses it (client.py:182-190): matching points in
+        ascending id order from ``offset`` (a point id) on -> ``(records, next_offset)``.  Vectors are not returned."""
+        coll = self._store._get(collection_name)
+        start = None if offset is None else _id_sort_key(_canonical_id(offset))
+
+        def work():
+            with coll.lock:
+                found = sorted((coll.point(r) for r in self._rows_matching(coll, scroll_filter)), key=lambda t: _id_sort_key(t[0]))
+            if start is not None:
+                found = [t for t in found if _id_sort_key(t[0]) >= start]
+            page, rest = found[:max(0, limit)], found[max(0, limit):]
+            records = [SimpleNamespace(id=pid if isinstance(pid, int) else str(pid), payload=(dict(p) if p is not None else None)
+                                       if with_payload else None, vector=None) for pid, p in page]
+            nxt = rest[0][0] if rest else None
+            return records, (nxt if nxt is None or isinstance(nxt, int) else str(nxt))
+        return await asyncio.to_thread(work)
+
+    async def query_points(self, collection_name: str, query=None, limit: int = 10, query_filter=None, with_payload: bool = True,
+                           **_ignored):
+        """``AsyncQdrantClient.query_points`` as ``QdrantManager.search`` calls it (client.py:142-148) -> ``.points`` of scored
+        points (``id``, ``score``, ``payload``).  ``MatchValue`` conditions only (``MatchText`` is for count / delete / scroll)."""
+        eq, text = self._split_filter(query_filter) if query_filter is not None else ({}, [])
+        if text:
+            raise ValueError("MatchText is not supported in query_points")
+        hits = await self._store.search(collection=collection_name, query_vector=None if query is None else list(query),
+                                        limit=limit, filters=eq or None)
+        return SimpleNamespace(points=[SimpleNamespace(id=h["id"], score=h["score"], payload=h["payload"] if with_payload else None,
+                                                       version=0, vector=None) for h in hits])
 
     async def close(self):
         return None

@@ -550,6 +550,9 @@ class _ShardedHostCollection:
         return out
 
     @_whole_op
+    def point(self, where: tuple[int, int]):
+        return self.shards[where[0]].point(where[1])
+
     def delete_found(self, found: Sequence[tuple[int, int]]) -> None:
         per_shard: list[list[int]] = [[] for _ in self.shards]
         for s, r in found:

@@ -193,6 +193,22 @@ async def scenario_client_shim(factory):
     assert (await store.get_collection_info(CODE)).points_count == 20
     flt2 = NS(must=[NS(key="project_name", match=NS(value="p"))])
     assert (await store.client.count(collection_name=CODE, count_filter=flt2)).count == 20
+    # scroll (what QdrantManager.file_needs_update issues, client.py:182-190): id order, pages chained by next_offset
+    seen, offset = [], None
+    while True:
+        recs, offset = await store.client.scroll(collection_name=CODE, scroll_filter=flt2, limit=7, offset=offset, with_payload=True,
+                                                 with_vectors=False)
+        seen += [(r.id, r.payload["file_path"]) for r in recs]
+        if offset is None:
+            break
+    everything = await store.search(collection=CODE, query_vector=None, limit=100, filters={"project_name": "p"})
+    assert len(seen) == 20 and seen == [(h["id"], h["payload"]["file_path"]) for h in everything]
+    one, nxt = await store.client.scroll(collection_name=CODE, scroll_filter=NS(must=[NS(key="file_path", match=NS(value="/repos/beta/f4.py"))]), limit=1)
+    assert len(one) == 1 and nxt is None and one[0].payload["file_path"] == "/repos/beta/f4.py"
+    # query_points (what QdrantManager.search issues, client.py:142-148)
+    res = await store.client.query_points(collection_name=CODE, query=x[4].astype(np.float64).tolist(), limit=3, query_filter=flt2, with_payload=True)
+    via = await store.search(collection=CODE, query_vector=x[4].astype(np.float64).tolist(), limit=3, filters={"project_name": "p"})
+    assert [(p.id, p.payload) for p in res.points] == [(h["id"], h["payload"]) for h in via] and abs(res.points[0].score - 1.0) < 1e-6
     await store.close()
 
 
