@@ -172,7 +172,32 @@ async def main(use_gpu: bool):
         raise AssertionError("expected IndexingError after close()")
     except IndexingError:
         pass
+    await run_reference_database_tests(use_gpu)
     print("reference callers OK")
+
+
+async def run_reference_database_tests(use_gpu: bool) -> None:
+    """The reference's OWN tests of this seam, unmodified: every test of ``TestQdrantConnection`` in
+    /root/reference/tests/test_database.py (connect + health check, create_collections seen through ``.client``, upsert -> search
+    -> delete), with ``QdrantManager`` in the module under test bound to the adapter.  pytest-asyncio is not installed, so the
+    coroutines are driven here."""
+    import importlib.util
+    import inspect
+
+    class Manager(B200VectorStore):
+        def __init__(self, *a, **kw):
+            super().__init__(*a, _device_factory=None if use_gpu else FakeDevice, **kw)
+
+    spec = importlib.util.spec_from_file_location("ref_test_database", "/root/reference/tests/test_database.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.QdrantManager = Manager                     # the name the tests construct; CollectionName stays the reference's enum
+    suite = mod.TestQdrantConnection()
+    names = [n for n, f in inspect.getmembers(suite, inspect.iscoroutinefunction) if n.startswith("test_")]
+    assert set(names) >= {"test_connect_to_qdrant", "test_create_collections", "test_upsert_and_search_vectors"}, names
+    for n in names:
+        await getattr(suite, n)()
+        print(f"reference tests/test_database.py::TestQdrantConnection::{n} passed on the adapter")
 
 
 if __name__ == "__main__":
