@@ -18,6 +18,7 @@ def main():
     for name, coro in (("exact ties follow the id", lambda: S.scenario_exact_ties_follow_the_id(None)),
                        ("random ops f32", lambda: S.scenario_random_ops(None, 1, storage="f32", steps=100)),
                        ("random ops bf16", lambda: S.scenario_random_ops(None, 3, storage="bf16", steps=100)),
+                       ("edge cases", lambda: S.scenario_edge_cases(None)),
                        ("client shim", lambda: S.scenario_client_shim(None)),
                        ("mass delete compacts", lambda: S.scenario_mass_delete_compacts(None))):
         asyncio.run(coro())

@@ -412,3 +412,54 @@ async def scenario_exact_ties_follow_the_id(factory, dim=16):
     got = await store.search_batch(CODE, [v[0].tolist(), v[1].tolist()], limit=4)
     assert [[h["id"] for h in g] for g in got] == [expected(v[0], 4, None), expected(v[1], 4, None)]
     await store.close()
+
+
+async def scenario_edge_cases(factory, dim=24):
+    """Empty and ragged inputs, limits at and past their bounds, empty collections - against the oracle's QdrantManager where it
+    defines the answer, against the reference's documented behaviour otherwise."""
+    from code_rag_b200 import _native as N
+    x, q = synth.unixcoder_like(40, dim, seed=71, n_queries=2)
+    vecs = x.astype(np.float64).tolist()
+    ids = synth.random_uuids(40, seed=72)
+    pl = [{"file_path": f"f{i % 4}.py", "entity_name": f"e{i}", "language": "python"} for i in range(40)]
+    store, ora = _store(factory, dimensions=dim), OracleManager(dim)
+    await store.connect(); await store.create_collections(); ora.create_collections()
+    qv = q[0].astype(np.float64).tolist()
+    # empty collection: every read answers, nothing raises
+    assert await store.search(collection=CODE, query_vector=qv, limit=5) == []
+    assert await store.search(collection=CODE, query_vector=None, limit=5, filters={"file_path": "f0.py"}) == []
+    assert await store.search_batch(collection=CODE, query_vectors=[qv, qv], limit=3) == [[], []]
+    assert (await store.get_collection_info(CODE)).points_count == 0
+    await store.delete(collection=CODE, filters={"file_path": "f0.py"})
+    assert await store.file_needs_update(CODE, "f0.py", "h") is True
+    # empty and ragged upserts: the reference zips ids, vectors and payloads (client.py:123-126)
+    await store.upsert(collection=CODE, ids=[], vectors=[], payloads=[])
+    await store.upsert(collection=CODE, ids=ids[:10], vectors=vecs[:7], payloads=pl[:9]); ora.upsert(CODE, ids[:7], vecs[:7], pl[:7])
+    assert (await store.get_collection_info(CODE)).points_count == 7
+    await store.upsert(collection=CODE, ids=ids[7:], vectors=vecs[7:], payloads=pl[7:]); ora.upsert(CODE, ids[7:], vecs[7:], pl[7:])
+    # limit: 0 and negative give nothing, more than there is gives everything, the largest supported, one past it
+    assert await store.search(collection=CODE, query_vector=qv, limit=0) == []
+    assert await store.search(collection=CODE, query_vector=qv, limit=-3) == []
+    for limit in (40, 41, 200, N.MAX_K):
+        _same_hits(await store.search(collection=CODE, query_vector=qv, limit=limit), ora.search(CODE, qv, limit=limit), what=f"limit {limit}")
+    _same_hits(await store.search(collection=CODE, query_vector=qv, limit=N.MAX_K, filters={"file_path": "f1.py"}),
+               ora.search(CODE, qv, limit=N.MAX_K, filters={"file_path": "f1.py"}), what="filtered, limit past the matches")
+    try:
+        await store.search(collection=CODE, query_vector=qv, limit=N.MAX_K + 1)
+        raise AssertionError("limit past MAX_K must raise")
+    except VectorStoreError as e:
+        assert "exceeds the largest supported top-k" in str(e.cause)
+    # a batch with one query, an empty batch
+    got = await store.search_batch(collection=CODE, query_vectors=[qv], limit=4)
+    _same_hits(got[0], ora.search(CODE, qv, limit=4), what="batch of one")
+    assert await store.search_batch(collection=CODE, query_vectors=np.zeros((0, dim)).tolist() or np.zeros((0, dim)), limit=4) == []
+    # a zero query vector: local mode divides by EPSILON-guarded norm -> all scores 0.0, order by id
+    zero = await store.search(collection=CODE, query_vector=[0.0] * dim, limit=5)
+    assert len(zero) == 5 and all(h["score"] == 0.0 for h in zero)
+    # delete everything, then the collection behaves as empty again and can be refilled
+    for f in range(4):
+        await store.delete(collection=CODE, filters={"file_path": f"f{f}.py"}); ora.delete(CODE, {"file_path": f"f{f}.py"})
+    assert (await store.get_collection_info(CODE)).points_count == 0 and await store.search(collection=CODE, query_vector=qv, limit=5) == []
+    await store.upsert(collection=CODE, ids=ids[:5], vectors=vecs[:5], payloads=pl[:5]); ora.upsert(CODE, ids[:5], vecs[:5], pl[:5])
+    _same_hits(await store.search(collection=CODE, query_vector=qv, limit=10), ora.search(CODE, qv, limit=10), what="refilled")
+    await store.close()

@@ -152,7 +152,8 @@ class ExactTieDevice(FakeDevice):
         mask = self._mask(want)
         for i in range(Q):
             self.ora._scores(q[i])                                  # the in-place re-normalisation of local mode
-            qn = q[i] / np.linalg.norm(q[i])
+            nq = np.linalg.norm(q[i])
+            qn = q[i] / (nq if nq != 0.0 else np.finfo(np.float64).eps)      # local mode guards a zero norm the same way
             m = self.ora.vectors[:self.rows].astype(np.float64)
             scores = np.array([np.dot(m[r], qn) for r in range(self.rows)])      # 1-D dot: the same arithmetic for every row
             cand = np.nonzero(mask)[0]

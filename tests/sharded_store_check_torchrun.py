@@ -33,6 +33,7 @@ def main():
                     asyncio.run(_sharded_specifics(factory.make_store, plane.world))
                 asyncio.run(S.scenario_random_ops(factory, 4, storage=storage))
                 asyncio.run(S.scenario_errors(factory))
+                asyncio.run(S.scenario_edge_cases(factory))
                 asyncio.run(S.scenario_client_shim(factory))
                 print(f"sharded store [{storage}] over {plane.world} GPU(s): OK", flush=True)
         finally:

@@ -69,3 +69,7 @@ def test_snapshot_host_half_round_trip(tmp_path, monkeypatch):
         assert coll.dev.rows == 30 and (await st.get_collection_info("code_chunks")).points_count == 21
         await st.close()
     asyncio.run(run())
+
+
+def test_edge_cases():
+    asyncio.run(S.scenario_edge_cases(FakeDevice))

@@ -157,6 +157,7 @@ def _worker(rank, world, port, out_dir):
                 for seed in (1, 2):
                     asyncio.run(S.scenario_random_ops(factory, seed))
                 asyncio.run(S.scenario_exact_ties_follow_the_id(factory))
+                asyncio.run(S.scenario_edge_cases(factory))
             except BaseException:  # noqa: BLE001
                 status = traceback.format_exc()
             finally:
