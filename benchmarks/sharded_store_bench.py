@@ -24,6 +24,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 from code_rag_b200.sharded_store import ShardedB200VectorStore, ShardPlane  # noqa: E402
+from code_rag_b200.sharded_store import run as run_sharded  # noqa: E402
 
 
 async def run(plane: ShardPlane, rows: int, dim: int, storage: str) -> None:
@@ -75,16 +76,7 @@ def main():
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
     dim = int(sys.argv[2]) if len(sys.argv) > 2 else 768
     storage = sys.argv[3] if len(sys.argv) > 3 else "bf16"
-    plane = ShardPlane.start()
-    if plane.rank != 0:
-        plane.serve()
-    else:
-        try:
-            asyncio.run(run(plane, rows, dim, storage))
-        finally:
-            plane.shutdown()
-    import torch.distributed as dist
-    dist.destroy_process_group()
+    run_sharded(lambda plane: run(plane, rows, dim, storage))
 
 
 if __name__ == "__main__":

@@ -695,4 +695,25 @@ class ShardedB200VectorStore(B200VectorStore):
             raise VectorStoreError(f"Failed to search and rank in {collection}", cause=e)
 
 
-__all__ = ["ShardPlane", "ShardedB200VectorStore", "split_row", "least_full", "SHARD_BITS"]
+def run(main: Callable, **plane_kwargs) -> Any:
+    """Entry point of a ``torchrun`` job that uses the sharded store: every rank calls ``run(main)``; rank 0 executes
+    ``await main(plane)`` (the application: build a ``ShardedB200VectorStore(plane=plane, ...)`` and use it), the other ranks serve
+    their shard until it returns or raises.  Returns ``main``'s result on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    plane = ShardPlane.start(**plane_kwargs)
+    result = None
+    try:
+        if plane.rank != 0:
+            plane.serve()
+        else:
+            try:
+                result = asyncio.run(main(plane))
+            finally:
+                plane.shutdown()
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    return result
+
+
+__all__ = ["ShardPlane", "ShardedB200VectorStore", "run", "split_row", "least_full", "SHARD_BITS"]

@@ -5,8 +5,6 @@ Rank 0 drives a ``ShardedB200VectorStore`` over the real shards through the scen
 database test, parity with the oracle's QdrantManager over every filter shape, errors, the ``.client`` shim) and the sharded
 specifics of tests/test_sharded_store_cpu.py (placement, overwrite in place, per-shard compaction, scroll order, a worker-side
 failure); the other ranks serve.  The same file runs on CPU (gloo, oracle-backed shards) as tests/test_sharded_store_cpu.py."""
-import asyncio
-import os
 import sys
 from pathlib import Path
 from types import SimpleNamespace as NS
@@ -14,33 +12,25 @@ from types import SimpleNamespace as NS
 ROOT = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
 
-from code_rag_b200.sharded_store import ShardedB200VectorStore, ShardPlane  # noqa: E402
+from code_rag_b200.sharded_store import ShardedB200VectorStore, run  # noqa: E402
 
 
-def main():
-    plane = ShardPlane.start()
-    if plane.rank != 0:
-        plane.serve()
-    else:
-        import adapter_scenarios as S
-        from test_sharded_store_cpu import _sharded_specifics
-        try:
-            for storage in ("f32", "bf16"):
-                factory = NS(make_store=lambda **kw: ShardedB200VectorStore(plane=plane, storage=storage, **kw))
-                asyncio.run(S.scenario_test_database(factory))
-                if storage == "f32":          # bf16 storage rounds the inputs: the 1e-5 bar of the scenario is the fp32 one
-                    asyncio.run(S.scenario_parity_with_oracle(factory, n=3000, dim=256))
-                    asyncio.run(_sharded_specifics(factory.make_store, plane.world))
-                asyncio.run(S.scenario_random_ops(factory, 4, storage=storage))
-                asyncio.run(S.scenario_errors(factory))
-                asyncio.run(S.scenario_edge_cases(factory))
-                asyncio.run(S.scenario_client_shim(factory))
-                print(f"sharded store [{storage}] over {plane.world} GPU(s): OK", flush=True)
-        finally:
-            plane.shutdown()
-    import torch.distributed as dist
-    dist.destroy_process_group()
+async def checks(plane):
+    import adapter_scenarios as S
+    from test_sharded_store_cpu import _sharded_specifics
+    for storage in ("f32", "bf16"):
+        factory = NS(make_store=lambda **kw: ShardedB200VectorStore(plane=plane, **{"storage": storage, **kw}))
+        await S.scenario_test_database(factory)
+        if storage == "f32":          # bf16 storage rounds the inputs: the 1e-5 bar of the scenario is the fp32 one
+            await S.scenario_parity_with_oracle(factory, n=3000, dim=256)
+            await _sharded_specifics(factory.make_store, plane.world)
+            await S.scenario_exact_ties_follow_the_id(factory)
+        await S.scenario_random_ops(factory, 4, storage=storage)
+        await S.scenario_errors(factory)
+        await S.scenario_edge_cases(factory)
+        await S.scenario_client_shim(factory)
+        print(f"sharded store [{storage}] over {plane.world} GPU(s): OK", flush=True)
 
 
 if __name__ == "__main__":
-    main()
+    run(checks)

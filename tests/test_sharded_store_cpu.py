@@ -3,7 +3,6 @@ through the SAME scenarios as the single-GPU adapter (tests/adapter_scenarios.py
 oracle's QdrantManager over every filter shape, the error convention, the ``.client`` shim) while the other ranks sit in
 ``ShardPlane.serve()``.  Each rank's shard is the oracle-backed FakeDevice (its position-independent form, helpers.ExactTieDevice); the exchange step is the real packed all-gather.
 Placement (least-full shard), overwrite in place, per-shard row reuse and compaction are checked on top."""
-import asyncio
 import os
 import sys
 import traceback
@@ -138,31 +137,25 @@ def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     status = "ok"
     try:
-        import torch.distributed as dist
         from helpers import ExactTieDevice, FakeShardSearcher
-        from code_rag_b200.sharded_store import ShardedB200VectorStore, ShardPlane
-        plane = ShardPlane.start(device_factory=ExactTieDevice, searcher_factory=FakeShardSearcher)
-        if rank != 0:
-            plane.serve()
-        else:
-            try:
-                import adapter_scenarios as S
-                from types import SimpleNamespace as NS
-                factory = NS(make_store=lambda **kw: ShardedB200VectorStore(plane=plane, **kw))
-                asyncio.run(S.scenario_test_database(factory))
-                asyncio.run(S.scenario_parity_with_oracle(factory, n=900, dim=48))
-                asyncio.run(S.scenario_errors(factory))
-                asyncio.run(S.scenario_client_shim(factory))
-                asyncio.run(_sharded_specifics(factory.make_store, world))
-                for seed in (1, 2):
-                    asyncio.run(S.scenario_random_ops(factory, seed))
-                asyncio.run(S.scenario_exact_ties_follow_the_id(factory))
-                asyncio.run(S.scenario_edge_cases(factory))
-            except BaseException:  # noqa: BLE001
-                status = traceback.format_exc()
-            finally:
-                plane.shutdown()
-        dist.destroy_process_group()
+        from code_rag_b200.sharded_store import ShardedB200VectorStore, run
+
+        async def main(plane):                               # rank 0 only; the other ranks serve inside run()
+            import adapter_scenarios as S
+            from types import SimpleNamespace as NS
+            factory = NS(make_store=lambda **kw: ShardedB200VectorStore(plane=plane, **kw))
+            await S.scenario_test_database(factory)
+            await S.scenario_parity_with_oracle(factory, n=900, dim=48)
+            await S.scenario_errors(factory)
+            await S.scenario_client_shim(factory)
+            await _sharded_specifics(factory.make_store, world)
+            for seed in (1, 2):
+                await S.scenario_random_ops(factory, seed)
+            await S.scenario_exact_ties_follow_the_id(factory)
+            await S.scenario_edge_cases(factory)
+            return "done"
+        got = run(main, device_factory=ExactTieDevice, searcher_factory=FakeShardSearcher)
+        assert got == ("done" if rank == 0 else None)
     except BaseException:  # noqa: BLE001
         status = traceback.format_exc()
     Path(out_dir, f"rank{rank}.txt").write_text(status)
