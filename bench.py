@@ -28,7 +28,7 @@ from pathlib import Path
 
 # torchrun exports OMP_NUM_THREADS=1 to every rank.  The reference arm is a CPU measurement on rank 0 alone (the other ranks
 # exit at once), so it gets every host thread back - before numpy loads its BLAS, which reads the variable once.
-if "reference" in sys.argv and os.environ.get("RANK", "0") == "0" and "LATTICE_B200_KEEP_OMP" not in os.environ:
+if any(a in ("reference", "--impl=reference") for a in sys.argv) and os.environ.get("RANK", "0") == "0" and "LATTICE_B200_KEEP_OMP" not in os.environ:
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ.pop(_v, None)
 
