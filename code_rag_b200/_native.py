@@ -42,7 +42,8 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_rows": (C.c_int64, [_vp]),
     "lvs_count": (C.c_int64, [_vp]),
     "lvs_capacity": (C.c_int64, [_vp]),
-    "lvs_search_counter": (C.c_uint32, [_vp]),
+    "lvs_search_counter": (C.c_uint64, [_vp]),
+    "lvs_advance_search_counter": (C.c_int, [_vp, C.c_uint64]),
     "lvs_upsert": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, _vp, _vp, _vp]),
     "lvs_upsert_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "lvs_set_codes": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, _vp]),

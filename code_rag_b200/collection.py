@@ -72,7 +72,7 @@ class DeviceCollection:
         import struct
         with open(path, "rb") as f:
             head = f.read(24 + 16)
-        if head[:8] != b"LVSSNAP1":
+        if head[:8] != b"LVSSNAP2":
             raise ValueError(f"{path} is not a lattice-b200 snapshot")
         dim, storage, metric, n_cols = struct.unpack_from("<4i", head, 8)
         _, row_base = struct.unpack_from("<2q", head, 24)
@@ -117,6 +117,10 @@ class DeviceCollection:
     @property
     def search_counter(self) -> int:
         return int(self._lib.lvs_search_counter(self._handle()))
+
+    def advance_search_counter(self, n: int) -> None:
+        """Account `n` reference searches this shard did not execute itself (include/lvs.h)."""
+        N.check(self._lib.lvs_advance_search_counter(self._handle(), int(n)), "lvs_advance_search_counter")
 
     def count(self) -> int:
         n = int(self._lib.lvs_count(self._handle()))

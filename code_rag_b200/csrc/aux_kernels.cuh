@@ -34,8 +34,8 @@ struct UpsertParams {
     int metric;
     float* inv_norm;
     uint8_t* live;
-    uint32_t* epoch;
-    uint32_t epoch_val;
+    uint64_t* epoch;
+    uint64_t epoch_val;
     uint64_t* tiekey;
     const uint64_t* ties_src;   // [n] or nullptr => tie key = global row
     int64_t row_base;
@@ -234,7 +234,7 @@ __global__ void set_live_kernel(uint8_t* live, const int64_t* rows, int64_t n, u
 struct MoveRowsParams {
     const int64_t* src; const int64_t* dst; int64_t n;
     uint8_t* vec; uint32_t row_bytes;
-    uint8_t* live; uint32_t* epoch; uint64_t* tie; float* inv_norm;
+    uint8_t* live; uint64_t* epoch; uint64_t* tie; float* inv_norm;
     uint32_t* codes[kMaxFilterCols]; int n_cols;
     uint32_t* rk_key; uint32_t* rk_file; uint32_t* rk_cent; uint32_t* rk_name; int32_t* rk_clen; uint8_t* rk_flags; int64_t rk_rows;
 };

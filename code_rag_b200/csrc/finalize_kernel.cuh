@@ -53,8 +53,8 @@ struct FinalizeParams {
     int metric;
     const double* q64;         // [Q][dim] unit (cosine) or raw (dot) queries
     const uint64_t* tiekey;    // [rows]
-    const uint32_t* epoch;     // [rows] value of the collection's search counter when the row was written
-    uint32_t search_no;        // counter value of query 0 of this launch (query qi is search_no + qi)
+    const uint64_t* epoch;     // [rows] value of the collection's search counter when the row was written
+    uint64_t search_no;        // counter value of query 0 of this launch (query qi is search_no + qi); 64-bit: never wraps
     const PwProgram* pw;
     float eps;                 // bound on |fast score - exact score| for unit vectors
     const float* eps_q;        // [Q] per-query bound (K2: bf16 rounding of the query), nullptr => eps
@@ -127,14 +127,14 @@ __device__ __forceinline__ float np_norm_f32(const float* v, const PwProgram* pw
 // Exact score of one candidate row (warp-cooperative).  buf = 3 * dim_pad floats of shared memory; q = the float64
 // query staged in shared memory.
 __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwProgram* pw, uint32_t row, const double* q,
-                                              uint32_t search_no, float* buf, float* leaf_out, int lane) {
+                                              uint64_t search_no, float* buf, float* leaf_out, int lane) {
     const int D = p.dim;
     const uint8_t* rp = p.base + (size_t)row * p.row_bytes;
     const uint32_t cpr = p.row_bytes / 16;
     float* cur = buf;
     float* prev = buf + p.dim_pad;
     float* nxt = buf + 2 * p.dim_pad;
-    const uint32_t row_epoch = __ldg(p.epoch + row);    // issued together with the row's loads
+    const uint64_t row_epoch = __ldg(p.epoch + row);    // issued together with the row's loads
     // stage the stored row as float32 (128-bit loads, all chunks of a lane in flight together); the padding
     // columns of a row are zero, so they may be staged and summed as well
     double ss = 0.0;
@@ -173,8 +173,8 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
         __syncwarp();
     }
     // replay of the per-search in-place re-normalisation
-    uint32_t count = search_no - row_epoch;             // searches run since the row was written, this one included
-    if (count > 64u) count = 64u + ((count - 64u) & 1u);
+    const uint64_t age = search_no - row_epoch;         // searches run since the row was written, this one included
+    const uint32_t count = age > 64ull ? 64u + (uint32_t)((age - 64ull) & 1ull) : (uint32_t)age;
     bool have_prev = false;
     for (uint32_t j = 1; j <= count; ++j) {
         const float n = np_norm_f32(cur, pw, leaf_out, lane);

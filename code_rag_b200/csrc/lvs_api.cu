@@ -106,12 +106,12 @@ struct lvs_collection {
     int64_t capacity = 0;
     int64_t n_rows = 0;
     int64_t row_base = 0;
-    uint32_t search_counter = 0;
+    uint64_t search_counter = 0;   // 64-bit: the replay count is counter - epoch[row] and must never wrap
     float h_norm_stats[2] = {0.f, 0.f};   // host mirror of d_max_norm: max ||row||, max | ||row|| - 1 |
 
     uint8_t* d_vec = nullptr;
     uint8_t* d_live = nullptr;
-    uint32_t* d_epoch = nullptr;
+    uint64_t* d_epoch = nullptr;
     uint64_t* d_tie = nullptr;
     float* d_inv_norm = nullptr;
     uint32_t* d_codes[kMaxFilterCols] = {nullptr};
@@ -141,7 +141,8 @@ struct lvs_collection {
     struct Slot {
         bool in_use = false;
         int Q = 0, k = 0, dtype = 0, kpl = 0;
-        uint32_t base = 0;
+        uint64_t base = 0;
+        int kind = 1;          // 1 = K1 scan, 2 = K2 tensor-core path (its flagged queries get the K1 fallback in finish_locked)
         bool has_want = false;
         uint32_t want[kMaxFilterCols];
         Scratch h;
@@ -262,12 +263,12 @@ static void free_arrays(lvs_collection* c) {
 static int grow_to(lvs_collection* c, int64_t new_cap) {
     if (new_cap <= c->capacity) return LVS_OK;
     if (new_cap >= (int64_t)0xFFFFFFF0ll) return fail(LVS_ELIMIT, "capacity %lld rows exceeds the 32-bit local row space", (long long)new_cap);
-    uint8_t* nv = nullptr; uint8_t* nl = nullptr; uint32_t* ne = nullptr; uint64_t* nt = nullptr; float* ni = nullptr;
+    uint8_t* nv = nullptr; uint8_t* nl = nullptr; uint64_t* ne = nullptr; uint64_t* nt = nullptr; float* ni = nullptr;
     uint32_t* nc[kMaxFilterCols] = {nullptr};
     const size_t vb = (size_t)new_cap * c->row_bytes;
     cudaError_t e = cudaMalloc(&nv, vb);
     if (e == cudaSuccess) e = cudaMalloc(&nl, (size_t)new_cap);
-    if (e == cudaSuccess) e = cudaMalloc(&ne, (size_t)new_cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ne, (size_t)new_cap * 8);
     if (e == cudaSuccess) e = cudaMalloc(&nt, (size_t)new_cap * 8);
     if (e == cudaSuccess) e = cudaMalloc(&ni, (size_t)new_cap * 4);
     for (int i = 0; i < c->n_cols && e == cudaSuccess; ++i) e = cudaMalloc(&nc[i], (size_t)new_cap * 4);
@@ -285,7 +286,7 @@ static int grow_to(lvs_collection* c, int64_t new_cap) {
         const size_t n = (size_t)c->n_rows;
         CU(cudaMemcpyAsync(nv, c->d_vec, n * c->row_bytes, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(nl, c->d_live, n, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(ne, c->d_epoch, n * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ne, c->d_epoch, n * 8, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(nt, c->d_tie, n * 8, cudaMemcpyDeviceToDevice, st));
         CU(cudaMemcpyAsync(ni, c->d_inv_norm, n * 4, cudaMemcpyDeviceToDevice, st));
         for (int i = 0; i < c->n_cols; ++i) CU(cudaMemcpyAsync(nc[i], c->d_codes[i], n * 4, cudaMemcpyDeviceToDevice, st));
@@ -382,8 +383,16 @@ extern "C" int64_t lvs_rows(const lvs_collection* c) {
     bind_thread(); return c ? c->n_rows : 0; }
 extern "C" int64_t lvs_capacity(const lvs_collection* c) {
     bind_thread(); return c ? c->capacity : 0; }
-extern "C" uint32_t lvs_search_counter(const lvs_collection* c) {
+extern "C" uint64_t lvs_search_counter(const lvs_collection* c) {
     bind_thread(); return c ? c->search_counter : 0; }
+extern "C" int lvs_advance_search_counter(lvs_collection* c, uint64_t n) {
+    bind_thread();
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto& sl : c->slots) if (sl.in_use) return fail(LVS_ESTATE, "searches are in flight: call lvs_search_wait first");
+    c->search_counter += n;
+    return LVS_OK;
+}
 
 __global__ void count_live_kernel(const uint8_t* live, uint32_t n, unsigned long long* out) {
     unsigned long long acc = 0;
@@ -753,7 +762,7 @@ static int scan_geometry(const lvs_collection* c, int qt, bool filter, ScanGeom*
 // Enqueue one level of the search for the query indices in `pending` (ascending): scan + finalize per group of up to
 // max_qt consecutive queries.  No synchronisation.
 static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int k, int kpl, bool filter, const uint32_t* const* fcodes,
-                         const uint32_t* fwant, uint32_t nf, uint32_t search_base, double* d_scores, int64_t* d_rows,
+                         const uint32_t* fwant, uint32_t nf, uint64_t search_base, double* d_scores, int64_t* d_rows,
                          uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches, bool time_first) {
     const int sm = g_lib.sm_count;
     double* q64 = (double*)c->s_q64.p;
@@ -811,7 +820,7 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
         fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
         fp.storage = c->storage; fp.metric = c->metric;
         fp.q64 = q64 + (size_t)first * c->dim;
-        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)first;
+        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint64_t)first;
         fp.pw = c->d_pw; fp.eps = eps_rel; fp.row_base = c->row_base;
         int nrw = kFinWarps;
         while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
@@ -863,7 +872,7 @@ static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
 }
 
 // Enqueue K2 + finalize for queries [0, Q) in batches of up to 256.  No synchronisation.
-static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t search_base, double* d_scores, int64_t* d_rows,
+static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint64_t search_base, double* d_scores, int64_t* d_rows,
                         uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches,
                         const uint32_t* const* fcodes = nullptr, const uint32_t* fwant = nullptr, uint32_t nf = 0) {
     int rc;
@@ -914,13 +923,18 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(LVS_ECUDA, "cuTensorMapEncodeTiled (queries) failed with CUresult %d", (int)r);
     }
-    static bool attr = false;
-    if (!attr) {
-        CU(cudaFuncSetAttribute(gemm_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
-        CU(cudaFuncSetAttribute(gemm_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
-        CU(cudaFuncSetAttribute(gemm_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
-        CU(cudaFuncSetAttribute(gemm_topk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin));
-        attr = true;
+    {   // collections are searched from several threads (one lock per collection): set the attributes exactly once
+        static std::once_flag once;
+        static cudaError_t once_err = cudaSuccess;
+        std::call_once(once, [] {
+            const int sm_ = (int)g_lib.smem_optin;
+            cudaError_t e_ = cudaFuncSetAttribute(gemm_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_);
+            if (e_ == cudaSuccess) e_ = cudaFuncSetAttribute(gemm_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_);
+            if (e_ == cudaSuccess) e_ = cudaFuncSetAttribute(gemm_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_);
+            if (e_ == cudaSuccess) e_ = cudaFuncSetAttribute(gemm_topk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_);
+            once_err = e_;
+        });
+        if (once_err != cudaSuccess) return fail(LVS_ECUDA, "cudaFuncSetAttribute (tensor-core kernel) failed: %s", cudaGetErrorString(once_err));
     }
     const uint32_t n_tiles = (uint32_t)((c->n_rows + kGemmN - 1) / kGemmN);
     for (int q0 = 0; q0 < Q; q0 += 256) {
@@ -992,7 +1006,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint32_t searc
         fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
         fp.storage = c->storage; fp.metric = c->metric;
         fp.q64 = (const double*)c->s_q64.p + (size_t)q0 * c->dim;
-        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint32_t)q0;
+        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint64_t)q0;
         fp.pw = c->d_pw; fp.row_base = c->row_base;
         fp.eps = 2.2e-3f;    // fallback; the per-query bound ||q - bf16(q)||_2 + accumulation slack is used
         fp.eps_q = c->metric == LVS_METRIC_COSINE ? (const float*)c->s_geps.p : nullptr;
@@ -1068,7 +1082,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     std::vector<int> pending;
     if (only) pending = *only;
     else { pending.resize(Q); for (int i = 0; i < Q; ++i) pending[i] = i; }
-    const uint32_t search_base = base_override >= 0 ? (uint32_t)base_override : c->search_counter + 1;
+    const uint64_t search_base = base_override >= 0 ? (uint64_t)base_override : c->search_counter + 1;
     int32_t* hf = (int32_t*)c->h_flags.p;
     bool first = true;
     int kind = 1;
@@ -1101,7 +1115,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     c->last_launches = launches;
     if (!only) c->last_kind = kind;
     c->last_kpl = kpl;
-    if (base_override < 0) c->search_counter += (uint32_t)Q;
+    if (base_override < 0) c->search_counter += (uint64_t)Q;
     if (!async) {
         if (c->opt_timing) {
             CU(cudaEventRecord(c->ev[5], st));
@@ -1172,6 +1186,7 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
                      (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st);
     if (rc != LVS_OK) return rc;
     sl.kpl = c->last_kpl;
+    sl.kind = c->last_kind;
     CU(cudaEventRecord(sl.done, st));
     sl.in_use = true;
     *ticket = si;
@@ -1186,16 +1201,18 @@ static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int6
     uint8_t* hp = (uint8_t*)sl.h.p + sl.qbytes;
     int32_t* hflags = (int32_t*)(hp + nres * 24 + (size_t)Q * 4);
     std::vector<int> redo;
-    for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && sl.kpl < 8) redo.push_back(i);
+    // a K2 slot (bf16-rounded queries, coarse bound) always gets the exact-scan fallback for its flagged queries, whatever k is;
+    // a K1 slot is repeated with a larger candidate set while one exists
+    for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && (sl.kind == 2 || sl.kpl < 8)) redo.push_back(i);
     if (!redo.empty()) {
-        // rare: repeat the flagged queries with larger candidate sets, as the same reference searches (same numbers)
+        // rare: repeat the flagged queries (K1, larger candidate sets), as the same reference searches (same numbers)
         void* dview = nullptr;
         CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
         uint8_t* rp = (uint8_t*)dview + sl.qbytes;
         std::vector<int32_t> f2(Q, 0);
         int rc = search_core(c, dview, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
                              (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
-                             (int64_t)sl.base, sl.kpl * 2, &redo);
+                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo);
         if (rc != LVS_OK) { sl.in_use = false; return rc; }
         for (int i : redo) hflags[i] = f2[i];
     }
@@ -1869,14 +1886,15 @@ extern "C" int lvs_search_rank(lvs_collection* c, const void* queries, int dtype
 // (reference docker-compose.yml:42-43).  One file per shard: header, then the raw device arrays in row order.
 // ------------------------------------------------------------------------------------------------------
 struct SnapshotHeader {
-    char magic[8];                // "LVSSNAP1"
+    char magic[8];                // "LVSSNAP2" (64-bit write epochs and search counter)
     int32_t dim, storage, metric, n_cols;
     int64_t n_rows, row_base;
-    uint32_t search_counter, row_bytes;
+    uint32_t reserved0, row_bytes;
     float norm_stats[2];
     int64_t rk_rows;              // rows covered by the ranking attribute columns (0 = none)
     int64_t n_names, name_bytes;
-    int64_t reserved[4];
+    uint64_t search_counter;
+    int64_t reserved[3];
 };
 
 static int snap_write(FILE* f, const void* dptr, size_t bytes, Scratch& pin, cudaStream_t st) {
@@ -1915,7 +1933,7 @@ extern "C" int lvs_snapshot_save(lvs_collection* c, const char* path) {
     if (!f) return fail(LVS_EINVAL, "cannot open %s for writing", path);
     SnapshotHeader h;
     memset(&h, 0, sizeof(h));
-    memcpy(h.magic, "LVSSNAP1", 8);
+    memcpy(h.magic, "LVSSNAP2", 8);
     h.dim = c->dim; h.storage = c->storage; h.metric = c->metric; h.n_cols = c->n_cols;
     h.n_rows = c->n_rows; h.row_base = c->row_base; h.search_counter = c->search_counter; h.row_bytes = c->row_bytes;
     h.norm_stats[0] = c->h_norm_stats[0]; h.norm_stats[1] = c->h_norm_stats[1];
@@ -1926,7 +1944,7 @@ extern "C" int lvs_snapshot_save(lvs_collection* c, const char* path) {
     Scratch& pin = c->h_pin2;
     if (rc == LVS_OK && n) rc = snap_write(f, c->d_vec, n * c->row_bytes, pin, st);
     if (rc == LVS_OK && n) rc = snap_write(f, c->d_live, n, pin, st);
-    if (rc == LVS_OK && n) rc = snap_write(f, c->d_epoch, n * 4, pin, st);
+    if (rc == LVS_OK && n) rc = snap_write(f, c->d_epoch, n * 8, pin, st);
     if (rc == LVS_OK && n) rc = snap_write(f, c->d_tie, n * 8, pin, st);
     if (rc == LVS_OK && n) rc = snap_write(f, c->d_inv_norm, n * 4, pin, st);
     for (int i = 0; i < c->n_cols && rc == LVS_OK && n; ++i) rc = snap_write(f, c->d_codes[i], n * 4, pin, st);
@@ -1954,7 +1972,7 @@ extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t cap
     FILE* f = fopen(path, "rb");
     if (!f) return fail(LVS_EINVAL, "cannot open %s", path);
     SnapshotHeader h;
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LVSSNAP1", 8) != 0) { fclose(f); return fail(LVS_EINVAL, "%s is not a lattice-b200 snapshot", path); }
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LVSSNAP2", 8) != 0) { fclose(f); return fail(LVS_EINVAL, "%s is not a lattice-b200 snapshot", path); }
     // the header must describe a file of exactly this size before anything is allocated from it
     if (h.n_rows < 0 || h.n_rows >= (int64_t)0xFFFFFFF0ll || h.row_base < 0 || h.dim < 1 || h.dim > 8192 || h.n_cols < 0 ||
         h.n_cols > kMaxFilterCols || h.rk_rows < 0 || h.rk_rows > h.n_rows || h.n_names < 0 || h.name_bytes < 0 ||
@@ -1963,7 +1981,7 @@ extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t cap
         return fail(LVS_EINVAL, "%s: corrupt snapshot header", path);
     }
     {
-        const int64_t expect = (int64_t)sizeof(h) + h.n_rows * ((int64_t)h.row_bytes + 1 + 4 + 8 + 4 + 4 * (int64_t)h.n_cols) + h.rk_rows * 21 +
+        const int64_t expect = (int64_t)sizeof(h) + h.n_rows * ((int64_t)h.row_bytes + 1 + 8 + 8 + 4 + 4 * (int64_t)h.n_cols) + h.rk_rows * 21 +
                                (h.n_names ? (h.n_names + 1) * 4 + h.name_bytes : 0);
         if (fseek(f, 0, SEEK_END) != 0 || (int64_t)ftell(f) != expect || fseek(f, (long)sizeof(h), SEEK_SET) != 0) {
             fclose(f);
@@ -1979,7 +1997,7 @@ extern "C" int lvs_snapshot_load(const char* path, const char* name, int64_t cap
     Scratch& pin = c->h_pin2;
     if (n) rc = snap_read(f, c->d_vec, n * c->row_bytes, pin, st);
     if (rc == LVS_OK && n) rc = snap_read(f, c->d_live, n, pin, st);
-    if (rc == LVS_OK && n) rc = snap_read(f, c->d_epoch, n * 4, pin, st);
+    if (rc == LVS_OK && n) rc = snap_read(f, c->d_epoch, n * 8, pin, st);
     if (rc == LVS_OK && n) rc = snap_read(f, c->d_tie, n * 8, pin, st);
     if (rc == LVS_OK && n) rc = snap_read(f, c->d_inv_norm, n * 4, pin, st);
     for (int i = 0; i < c->n_cols && rc == LVS_OK && n; ++i) rc = snap_read(f, c->d_codes[i], n * 4, pin, st);
@@ -2039,7 +2057,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     std::lock_guard<std::mutex> lk(c->mu);
     if (!strcmp(name, "stage_kb")) c->opt_stage_kb = value;
     else if (!strcmp(name, "stages")) c->opt_stages = value;
-    else if (!strcmp(name, "grid")) c->opt_grid = value;
+    else if (!strcmp(name, "grid")) c->opt_grid = std::max(0, std::min(value, g_lib.sm_count));   // the scratch lists are sized for one CTA per SM
     else if (!strcmp(name, "force_kpl")) c->opt_force_kpl = value;
     else if (!strcmp(name, "timing")) c->opt_timing = value ? 1 : 0;
     else if (!strcmp(name, "gemm_min_q")) c->opt_gemm_min_q = value;

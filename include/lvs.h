@@ -63,7 +63,11 @@ int lvs_collection_reserve(lvs_collection* c, int64_t capacity_rows);
 int64_t lvs_rows(const lvs_collection* c);                /* high-water mark (rows ever written) */
 int64_t lvs_count(const lvs_collection* c);               /* live rows: CollectionInfo.points_count, client.py:204-210 */
 int64_t lvs_capacity(const lvs_collection* c);
-uint32_t lvs_search_counter(const lvs_collection* c);     /* vector searches served so far (drives the replay) */
+uint64_t lvs_search_counter(const lvs_collection* c);     /* vector searches served so far (drives the replay; 64-bit, never wraps) */
+/* Account n reference searches that this shard did not execute itself (a restored or re-balanced shard catching up with the
+ * collection's history; tests of the counter's 2^32 boundary).  Local mode re-normalises every stored row on every search
+ * (oracle/qdrant_local.py point 2), so the number of searches since a row was written is part of the row's state. */
+int lvs_advance_search_counter(lvs_collection* c, uint64_t n);
 
 /* ---- upsert (QdrantManager.upsert, client.py:115-130; K4 kernel) ----------------------------------------
  * vecs: n x dim row-major host array of `dtype`.  rows: n global row numbers (the shard grows as needed), or NULL to

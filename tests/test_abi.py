@@ -72,10 +72,10 @@ def test_snapshot_load_rejects_foreign_and_corrupt_files(native_lib, tmp_path):
     assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL and h.value is None
     assert b"not a lattice-b200 snapshot" in native_lib.lvs_last_error()
     # right magic, absurd row count / truncated body
-    hdr = b"LVSSNAP1" + struct.pack("<4i2q2I2f3q4q", 768, 1, 0, 2, 1 << 40, 0, 0, 1536, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0)
+    hdr = b"LVSSNAP2" + struct.pack("<4i2q2I2f3q4q", 768, 1, 0, 2, 1 << 40, 0, 0, 1536, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0)
     bad.write_bytes(hdr)
     assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
-    hdr = b"LVSSNAP1" + struct.pack("<4i2q2I2f3q4q", 768, 1, 0, 2, 1000, 0, 0, 1536, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0)
+    hdr = b"LVSSNAP2" + struct.pack("<4i2q2I2f3q4q", 768, 1, 0, 2, 1000, 0, 0, 1536, 1.0, 0.0, 0, 0, 0, 0, 0, 0, 0)
     bad.write_bytes(hdr + b"\0" * 100)
     assert native_lib.lvs_snapshot_load(str(bad).encode(), b"x", 0, ctypes.byref(h)) == _native.EINVAL
     assert b"size does not match" in native_lib.lvs_last_error()
