@@ -287,11 +287,27 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: device-resident queries, searches enqueued back to back ----------------
-    # (each search is still one full pass over the corpus; results stay in HBM, flags are checked after the loop)
+    # ---------------- roofline leg: per-launch kernel time by CUDA events around every scan launch ----------------
+    # (timing on serialises consecutive searches, so this is the kernel ALONE: query prep + scan + exact rescoring, and at
+    #  N > 1 the exchange wait + merge, all one launch; the value leg below runs with it off)
     NSLOT = searcher.n_slots
     stream = searcher.stream
+    KR = min(K, 30)
+    shard.set_option("timing", 1)
     torch.cuda.synchronize()
+    for i in range(W):
+        searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+    barrier()
+    for i in range(W, W + KR):
+        searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+    barrier()
+    ms_ring, bytes_ring = shard.scan_times(KR)
+    scan_ms = [float(v) for v in ms_ring]
+    shard.set_option("timing", 0)
+
+    # ---------------- value: device-resident queries, searches enqueued back to back ----------------
+    # (each search is still one full pass over the corpus; results stay in HBM, flags are checked after the loop; consecutive
+    #  searches overlap by programmatic dependent launch: the next one streams while the last CTAs of this one rescore / exchange)
     for i in range(W):
         searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
     barrier()
@@ -306,15 +322,13 @@ def run_ours(args) -> None:
     for i in range(W, W + K):
         out = searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
         flag_bufs[id(out[4])] = out[4]
-        launches += 3 if not tensor_path else 4          # prep + scan + finalize, or prep + query prep + GEMM + finalize
+        launches += shard.last_timing()["launches"]       # kernels the library launched for this search (1 on the scan path)
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    n_flagged = int(sum(int(f.sum().item()) for f in flag_bufs.values()))
+    n_flagged = int(sum(int((f != 0).sum().item()) for f in flag_bufs.values()))
     launches += searcher.merge_launches if world > 1 else 0
     clocks = sampler.stop() if rank == 0 else None
-    ms_ring, bytes_ring = shard.scan_times(min(K, 256))
-    scan_ms = [float(v) for v in ms_ring]
 
     # ---------------- sync: one search at a time, the host waits for each result (latency-bound) ----------------
     barrier()
@@ -323,7 +337,6 @@ def run_ours(args) -> None:
         searcher.search_device(dq_all[i], k)
     barrier()
     sync_ms = (time.perf_counter() - t0) * 1e3
-    sync_scan_ms = float(np.mean(shard.scan_times(min(K, 256))[0]))
 
     # ---------------- e2e: host buffers through the public API, every step H2D(query) + D2H(result) ----------------
     # N=1: the C ABI's pipelined pair lvs_search_submit / lvs_search_wait (host pointers in, host pointers out);
@@ -351,7 +364,6 @@ def run_ours(args) -> None:
         last = e2e_wait(inflight.pop(0))
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    e2e_scan_ms = float(np.mean(shard.scan_times(min(K, 256))[0]))
     # depth 1 (strict request/response latency)
     barrier()
     t0 = time.perf_counter()
@@ -404,6 +416,7 @@ def run_ours(args) -> None:
         if world == 1 and Q == 1 and args.storage == "bf16" and not args.no_batched:
             # configs[2] (C3) beside the headline: 256 queries, top-100, tcgen05 path, host buffers through lvs_search
             qb = make_queries(3 * 256, args.dim, seed=12).reshape(3, 256, args.dim)
+            shard.set_option("timing", 1)
             walls, gms = [], []
             for r_ in range(3):
                 t0 = time.perf_counter()
@@ -427,8 +440,7 @@ def run_ours(args) -> None:
                        "rows_per_gpu": n_local, "l2": "inputs_exceed_l2", "corpus_gen_s": round(t_gen, 1),
                        "parallelism": f"row-shard x{world} + top-k exchange ({searcher.exchange_mode}) + merge",
                        "value_mode": "K searches enqueued back to back on one stream (device-resident queries/results)",
-                       "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K, "sync_scan_ms": sync_scan_ms,
-                       "e2e_scan_ms": e2e_scan_ms,
+                       "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K,
                        "unproven_queries": int(n_flagged)},
             "e2e": {"value": K * Q / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Q * args.dim * 8,
                     "d2h_bytes_per_step": Q * k * 24 + Q * 8, "ms_per_step": e2e_ms / K, "in_flight": DEPTH,

@@ -19,6 +19,7 @@ NULL_CODE = 0
 NO_MATCH = 0xFFFFFFFE
 MAX_K = 224
 FLAG_UNPROVEN = 1
+FLAG_EXCHANGE = 2
 
 _vp = C.c_void_p
 _i64p = C.POINTER(C.c_int64)
@@ -53,13 +54,15 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_search_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]),
     "lvs_search_wait": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_search_device_at": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_scan_times": (C.c_int, [_vp, C.c_int, _f32p, _f64p, _ip]),
     "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lvs_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _vp]),
     "lvs_exchange_connect": (C.c_int, [_vp, _vp]),
-    "lvs_exchange_merge_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "lvs_exchange_merge_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "lvs_search_sharded_device_async": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lvs_exchange_error": (C.c_int, [_vp]),
     "lvs_exchange_destroy": (C.c_int, [_vp]),
     "lvs_rank_fuse": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32p]),

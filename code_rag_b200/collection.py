@@ -43,7 +43,9 @@ def _ptr(a: np.ndarray | None):
 
 class DeviceCollection:
     def __init__(self, name: str, dim: int, storage: str = "f32", metric: str = "cosine", n_filter_cols: int = 0,
-                 capacity: int = 0, row_base: int = 0, device: int = 0):
+                 capacity: int = 0, row_base: int = 0, device: int = 0, timing: bool = True):
+        """`timing`: record CUDA events around every scan launch (``last_timing`` / ``scan_times``).  It serialises consecutive
+        searches on a stream, so throughput paths (the adapter, the sharded searcher, ``bench.py``'s timed legs) switch it off."""
         if storage not in _STORAGE:
             raise ValueError(f"storage must be one of {sorted(_STORAGE)}")
         if metric not in _METRIC:
@@ -61,6 +63,8 @@ class DeviceCollection:
                                                 self.n_filter_cols, int(capacity), self.row_base, C.byref(h)),
                 "lvs_collection_create")
         self._h = h
+        if timing:
+            self.set_option("timing", 1)
 
     # ---- snapshots (include/lvs.h: lvs_snapshot_save / lvs_snapshot_load) -----------------------------------
     def save_snapshot(self, path: str) -> None:
@@ -333,6 +337,16 @@ class DeviceCollection:
                 "lvs_search_device")
         return flags
 
+    def search_device_at(self, search_no: int, q_ptr: int, q_dtype: str, Q: int, k: int, want, scores_ptr: int, rows_ptr: int,
+                         ties_ptr: int, counts_ptr: int, flags: np.ndarray, stream: int = 0) -> None:
+        """Repeat of flagged queries on the exact scan, numbered as the reference searches they repeat (``lvs_search_device_at``)."""
+        w = self._want(want)
+        code = {"f32": N.DT_F32, "f64": N.DT_F64}[q_dtype]
+        N.check(self._lib.lvs_search_device_at(self._handle(), int(search_no), C.c_void_p(q_ptr), code, int(Q), int(k), _ptr(w),
+                                               C.c_void_p(scores_ptr), C.c_void_p(rows_ptr), C.c_void_p(ties_ptr),
+                                               C.c_void_p(counts_ptr), _ptr(flags), C.c_void_p(stream or None)),
+                "lvs_search_device_at")
+
     def search_device_async(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, scores_ptr: int, rows_ptr: int,
                             ties_ptr: int, counts_ptr: int, flags_ptr: int, stream: int = 0) -> None:
         """Enqueue-only search (pipelined callers): nothing is synchronised; flags land in a device buffer."""
@@ -342,6 +356,16 @@ class DeviceCollection:
                                                   C.c_void_p(scores_ptr), C.c_void_p(rows_ptr), C.c_void_p(ties_ptr),
                                                   C.c_void_p(counts_ptr), C.c_void_p(flags_ptr), C.c_void_p(stream or None)),
                 "lvs_search_device_async")
+
+    def search_sharded_device_async(self, ex, q_ptr: int, q_dtype: str, Q: int, k: int, want, out_ptr: int, counts_ptr: int,
+                                    flags_ptr: int, stream: int = 0) -> None:
+        """This rank's part of a sharded search, enqueue only: local search + exchange over peer memory + merge
+        (``lvs_search_sharded_device_async``); `ex` is the rank's ``lvs_exchange`` handle."""
+        w = self._want(want)
+        code = {"f32": N.DT_F32, "f64": N.DT_F64}[q_dtype]
+        N.check(self._lib.lvs_search_sharded_device_async(self._handle(), ex, C.c_void_p(q_ptr), code, int(Q), int(k), _ptr(w),
+                                                          C.c_void_p(out_ptr), C.c_void_p(counts_ptr), C.c_void_p(flags_ptr),
+                                                          C.c_void_p(stream or None)), "lvs_search_sharded_device_async")
 
     def scan_times(self, max_n: int = 256) -> tuple[np.ndarray, np.ndarray]:
         """(ms, algorithmic bytes) of the last scan-kernel launches (CUDA events on the launching stream)."""

@@ -2,16 +2,12 @@
 // K5 (merge of per-shard top-k lists after the all-gather).
 #pragma once
 #include "common.cuh"
+#include "exchange_kernel.cuh"
 #include "finalize_kernel.cuh"
 
 namespace lvs {
 
 
-__device__ __forceinline__ double load_as_f64(const void* src, int dtype, size_t i) {
-    if (dtype == LVS_DT_F64) return reinterpret_cast<const double*>(src)[i];
-    if (dtype == LVS_DT_F32) return (double)reinterpret_cast<const float*>(src)[i];
-    return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // K4 upsert.  Replaces the point marshalling + server-side insert behind QdrantManager.upsert
@@ -312,6 +308,38 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const MergeParams p) {
         p.out_scores[(size_t)qi * p.k + j] = 0.0; p.out_rows[(size_t)qi * p.k + j] = -1; p.out_ties[(size_t)qi * p.k + j] = 0ull;
     }
     if (tid == 0) p.out_counts[qi] = nout;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5' as its own launch (behind the tensor-core path; the scan path runs the same steps inside its own kernel)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exchange_merge_kernel(const ExchangeParams p) {
+    extern __shared__ __align__(16) uint8_t xsm[];
+    __shared__ uint32_t s_last, s_nvalid, s_timeout;
+    const int tid = threadIdx.x;
+    const size_t n = (size_t)3 * p.Q * p.k;
+    if (tid == 0) s_timeout = 0;
+    // ---- 1. publish: this rank's block (+ flags) -> every rank's gather buffer (its own included) ----
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n + (size_t)p.Q; i += (size_t)gridDim.x * blockDim.x) {
+        const int64_t v = i < n ? p.local[i] : (p.local_flags != nullptr ? (int64_t)p.local_flags[i - n] : 0);
+        for (int r = 0; r < p.world; ++r) p.peer_data[r][(size_t)p.rank * p.blk_stride + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        s_last = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) {
+            *p.done_counter = 0;
+            exchange_signal(p);
+        }
+    }
+    // ---- 2. wait for every rank's flag of this sequence number ----
+    if (tid < p.world && !exchange_wait_one(p, tid)) s_timeout = 1;
+    __syncthreads();
+    // ---- 3. merge, one query at a time ----
+    const bool timed_out = s_timeout != 0;
+    for (int qi = blockIdx.x; qi < p.Q; qi += gridDim.x)
+        exchange_merge_query(p, qi, xsm, &s_nvalid, tid, (int)blockDim.x, timed_out, [] { __syncthreads(); });
 }
 
 }  // namespace lvs

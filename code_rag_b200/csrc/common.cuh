@@ -148,6 +148,13 @@ struct WarpTopK {
     }
 };
 
+// element i of a host-typed array (LVS_DT_*) as float64
+__device__ __forceinline__ double load_as_f64(const void* src, int dtype, size_t i) {
+    if (dtype == LVS_DT_F64) return reinterpret_cast<const double*>(src)[i];
+    if (dtype == LVS_DT_F32) return (double)reinterpret_cast<const float*>(src)[i];
+    return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+}
+
 // bf16 pair (packed in a 32-bit word, little endian: element 0 in the low half) -> two floats
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

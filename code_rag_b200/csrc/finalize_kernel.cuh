@@ -59,7 +59,7 @@ struct FinalizeParams {
     float eps;                 // bound on |fast score - exact score| for unit vectors
     const float* eps_q;        // [Q] per-query bound (K2: bf16 rounding of the query), nullptr => eps
     float eps_add;             // added to eps_q (K2 on unit-norm shards: the norm deviation it ignores)
-    const float* qnorm;        // [Q] ||q||      } dot metric: the bound scales with ||q|| * max ||row||
+    const float* qnorm;        // [Q] ||q||      } dot metric: the bound scales with ||q|| * max ||row||   (nullptr: the fused scan kernel passes its own)
     const float* max_norm;     // [1] max ||row|| }
     int64_t row_base;          // global row of local row 0
     int n_rescore_warps;       // warps per CTA that own chain buffers
@@ -81,6 +81,12 @@ __host__ __device__ inline size_t finalize_smem_bytes(int dim_pad, int n_rescore
     b += (size_t)dim_pad * 8;                     // float64 query
     b += (size_t)n_rescore_warps * ((size_t)3 * dim_pad * 4 + kPwMaxLeaves * 4);
     return b;
+}
+
+// byte offset of the float64 query inside the finalize carve-up (the fused scan kernel stages the query there itself)
+__host__ __device__ inline size_t finalize_query_offset() {
+    size_t b = (size_t)kSortCap * 8 + 64 + 1024 + ((sizeof(PwProgram) + 15) & ~(size_t)15) + (size_t)kMaxCand * (8 + 8 + 8 + 4 + 4);
+    return (b + 15) & ~(size_t)15;
 }
 
 // ||v||_2 in float32 exactly as numpy computes np.linalg.norm(M, axis=-1) for a float32 row:
@@ -204,7 +210,7 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
     return warp_sum_f64(acc);
 }
 
-__device__ __forceinline__ void bitonic_sort_desc(uint64_t* buf, int n, int tid) {
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* buf, int n, int tid) {   // 256 threads, named barrier 1
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < n; i += kFinThreads) {
@@ -215,19 +221,33 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* buf, int n, int tid)
                     if (desc ? (a < b) : (a > b)) { buf[i] = b; buf[ixj] = a; }
                 }
             }
-            __syncthreads();
+            named_bar_sync(1, kFinThreads);
         }
     }
 }
 
-// grid = (queries of the group, C).  Every CTA of a query repeats the (cheap, deterministic) selection, rescoring is
-// split over the C CTAs (one candidate per warp), and the last CTA to finish (atomic ticket) orders and emits.
-// Selection: each of the 8 warps folds its share of the L per-CTA lists into a register top-(32*KPL) with the same
-// threshold-and-insert step the scan uses; the 8 warp lists (<= 2048 keys) are then ranked in shared memory.
-template <int KPL>
-__global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinalizeParams p) {
+// The body runs in two places: as the standalone finalize_kernel<KPL> behind the tensor-core path (grid = (queries, C)), and inside
+// the LAST CTAs of the fused scan kernel (scan_kernel.cuh), which then needs no second launch.  (qi, cy, C) = query, this CTA's
+// index among the C CTAs that work on the query, C.  Every CTA of a query repeats the (cheap, deterministic) selection, rescoring
+// is split over the C CTAs (one candidate per warp), and the last CTA to finish (atomic ticket) orders the candidates.
+// 256 threads take part (named barrier 1): in the scan kernel these are the 8 consumer warps, the producer warp has left.
+// Returns true in the CTA that holds the final result, left in shared memory (FinResult) for the caller to store or exchange.
+__device__ __forceinline__ void fin_sync() { named_bar_sync(1, kFinThreads); }
+
+struct FinResult {
+    const double* score;   // [nout]   (shared memory)
+    const uint32_t* row;   // [nout]   local rows
+    const uint64_t* tie;   // [nout]
+    const uint32_t* rank;  // rank[c] of candidate c; candidates with rank < k are the result, in rank order
+    uint32_t ncand;
+    uint32_t nout;
+    int32_t flag;
+};
+
+template <int KPL, bool Q_STAGED>
+__device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uint32_t qi, const uint32_t cy, const uint32_t C,
+                                              uint8_t* fsm, const float qnorm_in, FinResult& res) {
     constexpr uint32_t KPW = 32u * KPL;
-    extern __shared__ __align__(16) uint8_t fsm[];
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(fsm);
     uint32_t* scal = reinterpret_cast<uint32_t*>(fsm + (size_t)kSortCap * 8);   // [3]=is_last
     uint32_t* hist = scal + 16;                                                  // [256] radix-select histogram
@@ -246,14 +266,14 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     const size_t per_warp = (size_t)3 * p.dim_pad + kPwMaxLeaves;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t qi = blockIdx.x;
-    const uint32_t C = gridDim.y;
     const uint64_t* keys = p.keys + (size_t)qi * p.M;
     const uint32_t kp = p.kp;                            // == KPW
 
     // stage the float64 query and the pair-wise program while the lists stream in
-    const double* qg = p.q64 + (size_t)qi * p.dim;
-    for (int i = tid; i < p.dim; i += kFinThreads) qs[i] = qg[i];
+    if (!Q_STAGED) {                                     // fused scan kernel: the caller has already put the unit query into qs
+        const double* qg = p.q64 + (size_t)qi * p.dim;
+        for (int i = tid; i < p.dim; i += kFinThreads) qs[i] = qg[i];
+    }
     for (int i = tid; i < (int)(sizeof(PwProgram) / 4); i += kFinThreads)
         reinterpret_cast<uint32_t*>(pws)[i] = reinterpret_cast<const uint32_t*>(p.pw)[i];
 
@@ -264,8 +284,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     if (p.L >= kp && p.L <= (uint32_t)kSortCap) {
         const uint64_t* tops = p.tops + (size_t)qi * p.L;
         if (tid == 0) { scal[0] = 0; scal[1] = 0; }
-        for (uint32_t i = tid; i < p.L; i += kFinThreads) sortbuf[i] = tops[i];
-        __syncthreads();
+        for (uint32_t i = tid; i < p.L; i += kFinThreads) sortbuf[i] = __ldcg(tops + i);
+        fin_sync();
         unsigned long long* Tp = reinterpret_cast<unsigned long long*>(scal + 4);
         for (uint32_t i = tid; i < p.L; i += kFinThreads) {
             const uint64_t v = sortbuf[i];
@@ -273,18 +293,18 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
             for (uint32_t o = 0; o < p.L; ++o) { const uint64_t w = sortbuf[o]; rank += (w > v || (w == v && o < i)) ? 1u : 0u; }
             if (rank == kp - 1) *Tp = v;
         }
-        __syncthreads();
+        fin_sync();
         uint64_t T = *Tp;
         if (T == 0ull) T = 1ull;                          // fewer than kp non-empty lists: keep every key
-        __syncthreads();
+        fin_sync();
         // the lists are sorted descending (bitonic merge in K1, sorted insertion in K2), so the keys >= T of a list are a
         // prefix of it: one thread per list reads 4 keys (32 bytes) at a time and stops at the first key below T
         const uint32_t llen = p.M / p.L;
         for (uint32_t l = tid; l < p.L; l += kFinThreads) {
             const uint64_t* lk = keys + (size_t)l * llen;
             for (uint32_t i = 0; i < llen; i += 4) {
-                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(lk + i);
-                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(lk + i + 2);
+                const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(lk + i));
+                const ulonglong2 b = __ldcg(reinterpret_cast<const ulonglong2*>(lk + i + 2));
                 const uint64_t v[4] = {a.x, a.y, b.x, b.y};
                 bool more = true;
 #pragma unroll
@@ -299,14 +319,14 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
                 if (!more) break;
             }
         }
-        __syncthreads();
+        fin_sync();
         const uint32_t got = scal[0];
         if (got <= kFinWarps * KPW) {
             while (nmerged < got) nmerged <<= 1;          // sort no more than the next power of two above the survivors
             for (uint32_t i = got + tid; i < nmerged; i += kFinThreads) sortbuf[i] = 0ull;
             folded = false;
         }
-        __syncthreads();
+        fin_sync();
     }
     // ---- 1b. general path: exact radix select of the kp-th largest key (MSB first, 8 bits per pass over the keys in L2);
     //          stops as soon as at most 2 k' keys lie at or above the current bucket
@@ -318,12 +338,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = 56 - 8 * pass;
             hist[tid] = 0;                               // kFinThreads == 256
-            __syncthreads();
+            fin_sync();
             for (uint32_t i = tid; i < p.M; i += kFinThreads) {
-                const uint64_t v = keys[i];
+                const uint64_t v = __ldcg(keys + i);
                 if (v != 0ull && (v & mask) == prefix) atomicAdd(&hist[(uint32_t)(v >> shift) & 255u], 1u);
             }
-            __syncthreads();
+            fin_sync();
             if (tid == 0) {
                 uint32_t cum = 0, digit = 0, rem = 0, stop = 1;
                 for (int b = 255; b >= 0; --b) {
@@ -338,9 +358,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
                 }
                 scal[0] = digit; scal[1] = rem; scal[2] = stop;
             }
-            __syncthreads();
+            fin_sync();
             const uint32_t digit = scal[0], rem = scal[1], stop = scal[2];
-            __syncthreads();
+            fin_sync();
             if (rem == 0) { mask = ~0ull; prefix = 1ull; break; }   // every non-empty key qualifies
             prefix |= (uint64_t)digit << shift;
             mask |= 0xFFull << shift;
@@ -349,31 +369,31 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         }
         // gather the keys >= prefix (lower bits zero): at most 8*KPW of them by construction
         if (tid == 0) scal[0] = 0;
-        __syncthreads();
+        fin_sync();
         for (uint32_t i = tid; i < p.M; i += kFinThreads) {
-            const uint64_t v = keys[i];
+            const uint64_t v = __ldcg(keys + i);
             if (v != 0ull && v >= prefix) {
                 const uint32_t pos = atomicAdd(&scal[0], 1u);
                 if (pos < kFinWarps * KPW) sortbuf[pos] = v;
             }
         }
-        __syncthreads();
+        fin_sync();
         const uint32_t got = min(scal[0], kFinWarps * KPW);
         nmerged = 32;
         while (nmerged < got) nmerged <<= 1;
         for (uint32_t i = got + tid; i < nmerged; i += kFinThreads) sortbuf[i] = 0ull;
-        __syncthreads();
+        fin_sync();
     }
     // ---- 2. rank the merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
     if (tid == 0) scal[0] = 0;
-    __syncthreads();
+    fin_sync();
     {
         uint32_t nz = 0;
         for (uint32_t i = tid; i < nmerged; i += kFinThreads) nz += sortbuf[i] != 0ull ? 1u : 0u;
         for (int o = 16; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
         if (lane == 0 && nz) atomicAdd(&scal[0], nz);
     }
-    __syncthreads();
+    fin_sync();
     const uint32_t nsurv = scal[0];
     const uint32_t ncand = min(nsurv, kp);
     if (nmerged <= 256u) {
@@ -384,11 +404,11 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
             for (uint32_t o = 0; o < nmerged; ++o) rank += sortbuf[o] > v ? 1u : 0u;
             if (rank < kp) ckey[rank] = v;
         }
-        __syncthreads();
+        fin_sync();
     } else {
         bitonic_sort_desc(sortbuf, (int)nmerged, tid);
         for (uint32_t c = tid; c < ncand; c += kFinThreads) ckey[c] = sortbuf[c];
-        __syncthreads();
+        fin_sync();
     }
     // the fast-score bound for every row that is NOT a candidate
     // K2 lists are shorter than k': what a full list dropped is bounded by its last key (drops[])
@@ -396,13 +416,13 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     if (p.drops != nullptr) {
         unsigned long long* Dp = reinterpret_cast<unsigned long long*>(scal + 6);
         if (tid == 0) *Dp = 0ull;
-        __syncthreads();
+        fin_sync();
         uint64_t t = 0;
-        for (uint32_t i = tid; i < p.L; i += kFinThreads) { const uint64_t v = p.drops[(size_t)qi * p.L + i]; t = v > t ? v : t; }
+        for (uint32_t i = tid; i < p.L; i += kFinThreads) { const uint64_t v = __ldcg(p.drops + (size_t)qi * p.L + i); t = v > t ? v : t; }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) { const uint64_t v = shfl_xor_u64(t, o); t = v > t ? v : t; }
         if (lane == 0 && t) atomicMax(Dp, (unsigned long long)t);
-        __syncthreads();
+        fin_sync();
         drop_key = *Dp;
     }
     const bool lists_dropped_nothing = nsurv < kp && drop_key == 0ull;   // no list ever overflowed
@@ -415,12 +435,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
     if ((uint32_t)warp < nrw) {
         float* buf = chain + (size_t)warp * per_warp;
         float* leaf_out = buf + (size_t)3 * p.dim_pad;
-        for (uint32_t c = blockIdx.y * nrw + warp; c < ncand; c += C * nrw) {
+        for (uint32_t c = cy * nrw + warp; c < ncand; c += C * nrw) {
             const double s = exact_score(p, pws, key_row(ckey[c]), qs, p.search_no + qi, buf, leaf_out, lane);
             if (lane == 0) gscore[c] = s;
         }
     }
-    __syncthreads();
+    fin_sync();
     if (tid == 0) {
         uint32_t last = 1;
         if (C > 1) {
@@ -429,8 +449,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         }
         scal[3] = last;
     }
-    __syncthreads();
-    if (scal[3] == 0) return;
+    fin_sync();
+    if (scal[3] == 0) return false;
     __threadfence();
     for (uint32_t c = tid; c < ncand; c += kFinThreads) {
         const uint32_t r = key_row(ckey[c]);
@@ -439,7 +459,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         cscore[c] = __ldcg(gscore + c);
     }
     if (tid == 0 && C > 1) p.tickets[qi] = 0;            // ready for the next launch
-    __syncthreads();
+    fin_sync();
     // ---- 5. final order: (score desc, tie asc, row asc) by rank counting ----
     for (uint32_t c = tid; c < ncand; c += kFinThreads) {
         const double s = cscore[c]; const uint64_t t = ctie[c]; const uint32_t r = crow[c];
@@ -451,37 +471,54 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
         }
         crank[c] = rank;
     }
-    __syncthreads();
+    fin_sync();
+    // ---- 6. the exactness proof for the weakest returned result ----
     const uint32_t nout = min(ncand, p.k);
+    if (tid == 0) scal[8] = 0u;
+    fin_sync();
     for (uint32_t c = tid; c < ncand; c += kFinThreads) {
         const uint32_t rk = crank[c];
-        if (rk < p.k) {
-            p.out_scores[(size_t)qi * p.k + rk] = cscore[c];
-            p.out_rows[(size_t)qi * p.k + rk] = p.row_base + (int64_t)crow[c];
-            p.out_ties[(size_t)qi * p.k + rk] = ctie[c];
-        }
         if (rk == p.k - 1 || (rk == ncand - 1 && ncand < p.k)) {
             // this candidate is the weakest returned result
-            int32_t flag = 0;
             if (!lists_dropped_nothing && ncand >= p.k) {
                 // rows outside the candidate set have exact score <= t_fast + eps
                 double eps = p.eps_q != nullptr ? (double)p.eps_q[qi] + (double)p.eps_add : (double)p.eps;
-                if (p.metric == LVS_METRIC_DOT) eps *= (double)p.qnorm[qi] * (double)(*p.max_norm);
-                if (!(cscore[c] > (double)t_fast + eps)) flag = 1;
-                if (ncand == kp && kp == p.k) flag = 1;  // no margin at all
+                if (p.metric == LVS_METRIC_DOT) eps *= (double)(p.qnorm != nullptr ? p.qnorm[qi] : qnorm_in) * (double)(*p.max_norm);
+                if (!(cscore[c] > (double)t_fast + eps)) scal[8] = 1u;
+                if (ncand == kp && kp == p.k) scal[8] = 1u;  // no margin at all
             }
-            p.out_flags[qi] = flag;
         }
     }
-    for (uint32_t c = nout + tid; c < p.k; c += kFinThreads) {
+    fin_sync();
+    res.score = cscore; res.row = crow; res.tie = ctie; res.rank = crank; res.ncand = ncand; res.nout = nout;
+    res.flag = ncand == 0 ? 0 : (int32_t)scal[8];
+    return true;
+}
+
+// Stores a finished query's result (local form: this shard IS the collection, or the exchange runs as its own kernel).
+__device__ __forceinline__ void finalize_store_local(const FinalizeParams& p, const uint32_t qi, const FinResult& r, const int tid) {
+    for (uint32_t c = tid; c < r.ncand; c += kFinThreads) {
+        const uint32_t rk = r.rank[c];
+        if (rk < p.k) {
+            p.out_scores[(size_t)qi * p.k + rk] = r.score[c];
+            p.out_rows[(size_t)qi * p.k + rk] = p.row_base + (int64_t)r.row[c];
+            p.out_ties[(size_t)qi * p.k + rk] = r.tie[c];
+        }
+    }
+    for (uint32_t c = r.nout + tid; c < p.k; c += kFinThreads) {
         p.out_scores[(size_t)qi * p.k + c] = 0.0;
         p.out_rows[(size_t)qi * p.k + c] = -1;
         p.out_ties[(size_t)qi * p.k + c] = 0ull;
     }
-    if (tid == 0) {
-        p.out_counts[qi] = nout;
-        if (ncand == 0) p.out_flags[qi] = 0;
-    }
+    if (tid == 0) { p.out_counts[qi] = r.nout; p.out_flags[qi] = r.flag; }
+}
+
+// grid = (queries, C): the standalone form behind the tensor-core path (K2 lists)
+template <int KPL>
+__global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinalizeParams p) {
+    extern __shared__ __align__(16) uint8_t fsm_dyn[];
+    FinResult r;
+    if (finalize_body<KPL, false>(p, blockIdx.x, blockIdx.y, gridDim.y, fsm_dyn, 0.f, r)) finalize_store_local(p, blockIdx.x, r, threadIdx.x);
 }
 
 }  // namespace lvs

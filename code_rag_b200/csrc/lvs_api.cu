@@ -18,7 +18,7 @@
 #include "finalize_kernel.cuh"
 #include "gemm_topk_kernel.cuh"
 #include "rank_kernel.cuh"
-#include "scan_kernel.cuh"
+#include "scan_launch.cuh"
 
 using namespace lvs;
 
@@ -126,7 +126,12 @@ struct lvs_collection {
     int last_kind = 0;
 
     Scratch s_qraw, s_q64, s_q32, s_qnorm, s_keys, s_mins, s_flags, s_res, s_stage_dev, s_misc, s_cand;
-    Scratch s_gkeys, s_gtops, s_gdrops, s_qb16, s_tickets, s_dbg, s_geps;
+    Scratch s_gkeys, s_gtops, s_gdrops, s_qb16, s_tickets, s_dbg, s_geps, s_xlocal;
+    cudaStream_t last_stream = nullptr; bool last_stream_valid = false; cudaEvent_t order_ev = nullptr;
+    uint32_t launch_seq = 0;          // fused scan launches so far (ScanParams::seq)
+    uint32_t tile_base[2] = {0, 0};   // what the two tile counters (launch parity) stand at
+    Scratch s_qstage;                 // host queries staged by CTA 0, one slot per launch parity
+    int opt_dyn_tiles = 1;
     Scratch h_pin, h_pin2, h_flags;
 
     // ring of event pairs around the scan launches (read back by lvs_scan_times after a synchronisation)
@@ -134,7 +139,9 @@ struct lvs_collection {
     double ring_bytes[kEventRing] = {0};
     uint64_t ring_pos = 0;
     cudaEvent_t first_scan_start = nullptr, first_scan_end = nullptr;
-    int opt_timing = 1;
+    int opt_timing = 0;          // 1 = CUDA events around every scan launch (lvs_scan_times / lvs_last_search_timing); this also
+                                 // serialises consecutive searches, i.e. switches the programmatic-launch overlap off
+    int opt_pdl = 1;
     int last_kpl = 0;
 
     // pipelined host API (lvs_search_submit / lvs_search_wait)
@@ -323,6 +330,7 @@ extern "C" int lvs_collection_create(const char* name, int dim, int storage, int
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 * kEventRing && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ring_ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_max_norm, 8);
     if (e == cudaSuccess) e = cudaMemset(c->d_max_norm, 0, 8);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 64);
@@ -355,7 +363,8 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     free_arrays(c);
     cudaFree(c->d_max_norm); cudaFree(c->d_pw); cudaFree(c->d_counter);
     Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc,
-                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg, &c->s_geps};
+                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg, &c->s_geps, &c->s_xlocal, &c->s_qstage};
+    if (c->order_ev) cudaEventDestroy(c->order_ev);
     for (Scratch* s : ds) if (s->p) cudaFree(s->p);
     if (c->h_pin.p) cudaFreeHost(c->h_pin.p);
     if (c->h_pin2.p) cudaFreeHost(c->h_pin2.p);
@@ -684,50 +693,22 @@ extern "C" int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* 
 // ------------------------------------------------------------------------------------------------------
 // search
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int QT, int KPL, bool NORM, bool FILTER>
-static cudaError_t launch_scan_inst(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    auto kfn = scan_topk_kernel<T, QT, KPL, NORM, FILTER>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    kfn<<<grid, kScanThreads, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-template <typename T, bool NORM, bool FILTER>
-static cudaError_t launch_scan_tnf(int qt, int kpl, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
-#define LVS_CASE(Q_, K_) if (qt == Q_ && kpl == K_) return launch_scan_inst<T, Q_, K_, NORM, FILTER>(p, grid, smem, st);
-    LVS_CASE(1, 1) LVS_CASE(1, 2) LVS_CASE(1, 4) LVS_CASE(1, 8)
-    LVS_CASE(2, 1) LVS_CASE(2, 2) LVS_CASE(2, 4)
-    LVS_CASE(4, 1) LVS_CASE(4, 2)
-#undef LVS_CASE
-    return cudaErrorInvalidValue;
-}
-
-static cudaError_t launch_scan(const lvs_collection* c, int qt, int kpl, bool filter, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
-    if (c->storage == LVS_STORAGE_F32) {
-        return filter ? launch_scan_tnf<float, false, true>(qt, kpl, p, grid, smem, st)
-                      : launch_scan_tnf<float, false, false>(qt, kpl, p, grid, smem, st);
-    }
-    if (c->metric == LVS_METRIC_COSINE) {
-        return filter ? launch_scan_tnf<__nv_bfloat16, true, true>(qt, kpl, p, grid, smem, st)
-                      : launch_scan_tnf<__nv_bfloat16, true, false>(qt, kpl, p, grid, smem, st);
-    }
-    return filter ? launch_scan_tnf<__nv_bfloat16, false, true>(qt, kpl, p, grid, smem, st)
-                  : launch_scan_tnf<__nv_bfloat16, false, false>(qt, kpl, p, grid, smem, st);
+// The 36 instantiations of the fused scan kernel are compiled in three translation units of their own (scan_f32.cu,
+// scan_bf16_cos.cu, scan_bf16_dot.cu: build.py compiles every .cu in parallel), through scan_launch.cuh.
+static cudaError_t launch_scan(const lvs_collection* c, int qt, int kpl, bool filter, const ScanParams& p, const FinalizeParams& fp,
+                               const ExchangeParams& xp, int grid, size_t smem, cudaStream_t st) {
+    const size_t optin = g_lib.smem_optin;
+    if (c->storage == LVS_STORAGE_F32) return lvs_launch_scan_f32(qt, kpl, filter, p, fp, xp, grid, smem, st, optin);
+    if (c->metric == LVS_METRIC_COSINE) return lvs_launch_scan_bf16_cos(qt, kpl, filter, p, fp, xp, grid, smem, st, optin);
+    return lvs_launch_scan_bf16_dot(qt, kpl, filter, p, fp, xp, grid, smem, st, optin);
 }
 
 template <int KPL>
 static cudaError_t launch_finalize(const FinalizeParams& fp, int nq, unsigned ncta, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(finalize_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::once_flag once;
+    static cudaError_t once_err = cudaSuccess;
+    std::call_once(once, [] { once_err = cudaFuncSetAttribute(finalize_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_lib.smem_optin); });
+    if (once_err != cudaSuccess) return once_err;
     finalize_kernel<KPL><<<dim3((unsigned)nq, ncta), kFinThreads, smem, st>>>(fp);
     return cudaGetLastError();
 }
@@ -739,18 +720,18 @@ struct ScanGeom {
     size_t smem;
 };
 
-static int scan_geometry(const lvs_collection* c, int qt, bool filter, ScanGeom* g) {
-    const size_t budget = g_lib.smem_optin;   // 227 KB on B200
+static int scan_geometry(const lvs_collection* c, int qt, bool filter, size_t fin_bytes, ScanGeom* g) {
+    const size_t budget = g_lib.smem_optin - kScanStaticSmem;   // 227 KB on B200, minus the kernel's static shared memory
     uint32_t target = (uint32_t)std::max(4, c->opt_stage_kb) * 1024u;
     uint32_t R = std::max<uint32_t>(kScanRW, (target / c->row_bytes) / kScanRW * kScanRW);
     for (;;) {
         const uint32_t sb = R * c->row_bytes;
         uint32_t S = kScanMaxStages;
         if (c->opt_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_stages);
-        while (S >= 2 && scan_smem_bytes(S, sb, qt, c->q_stride, R, filter) > budget) --S;
+        while (S >= 2 && scan_smem_bytes(S, sb, qt, c->q_stride, R, filter, fin_bytes) > budget) --S;
         if (S >= 2) {
             g->stage_rows = R; g->n_stages = S; g->stage_bytes = sb;
-            g->smem = scan_smem_bytes(S, sb, qt, c->q_stride, R, filter);
+            g->smem = scan_smem_bytes(S, sb, qt, c->q_stride, R, filter, fin_bytes);
             return LVS_OK;
         }
         if (R <= (uint32_t)kScanRW) break;
@@ -759,20 +740,68 @@ static int scan_geometry(const lvs_collection* c, int qt, bool filter, ScanGeom*
     return fail(LVS_ELIMIT, "dim %d does not fit the scan's shared-memory ring", c->dim);
 }
 
-// Enqueue one level of the search for the query indices in `pending` (ascending): scan + finalize per group of up to
-// max_qt consecutive queries.  No synchronisation.
-static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int k, int kpl, bool filter, const uint32_t* const* fcodes,
-                         const uint32_t* fwant, uint32_t nf, uint64_t search_base, double* d_scores, int64_t* d_rows,
-                         uint64_t* d_ties, uint32_t* d_counts, int32_t* d_flags, cudaStream_t st, int* launches, bool time_first) {
+struct lvs_exchange {
+    int world = 1, rank = 0, max_q = 0, max_k = 0;
+    size_t blk_stride = 0;          // int64 elements per rank block
+    size_t slot_elems = 0;          // int64 elements per slot = world * blk_stride
+    uint8_t* base = nullptr;        // [2 slots][world][blk_stride] int64, then flags [2][kMaxRanks] uint64
+    size_t flags_off = 0;
+    uint8_t* peers[kMaxRanks] = {nullptr};
+    bool opened[kMaxRanks] = {false};
+    uint32_t* d_counter = nullptr;  // [0] done counter, [1] error word
+    uint64_t seq = 0;
+    bool connected = false;
+};
+
+// Parameters of the next exchange of (Q queries x k results) on `ex`: advances the sequence number (every rank must issue the
+// same sequence of exchanges) and selects the slot by its parity.
+static int exchange_params(lvs_exchange* ex, int Q, int k, ExchangeParams* out) {
+    if (!ex->connected && ex->world > 1) return fail(LVS_ESTATE, "lvs_exchange_connect() has not been called");
+    if (Q < 1 || k < 1 || (size_t)3 * Q * k + (size_t)Q > ex->blk_stride)
+        return fail(LVS_ELIMIT, "Q x k = %d x %d exceeds the exchange buffer (%d x %d)", Q, k, ex->max_q, ex->max_k);
+    if ((size_t)ex->world * k * 24 > 200 * 1024) return fail(LVS_ELIMIT, "world * k too large for the merge");
+    ex->seq += 1;
+    const int slot = (int)(ex->seq & 1);
+    ExchangeParams& p = *out;
+    p.Q = Q; p.k = k; p.world = ex->world; p.rank = ex->rank;
+    for (int r = 0; r < ex->world; ++r) {
+        p.peer_data[r] = (int64_t*)ex->peers[r] + (size_t)slot * ex->slot_elems;
+        p.peer_flags[r] = (uint64_t*)(ex->peers[r] + ex->flags_off) + (size_t)slot * kMaxRanks;
+    }
+    p.my_data = (const int64_t*)ex->base + (size_t)slot * ex->slot_elems;
+    p.my_flags = (const uint64_t*)(ex->base + ex->flags_off) + (size_t)slot * kMaxRanks;
+    p.seq = ex->seq; p.blk_stride = ex->blk_stride; p.done_counter = ex->d_counter; p.err = ex->d_counter + 1;
+    return LVS_OK;
+}
+
+static int launch_exchange(const ExchangeParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)p.world * p.k * 24;
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::max(1, std::min(p.Q, 32));
+    exchange_merge_kernel<<<grid, 256, smem, st>>>(p);
+    CU(cudaGetLastError());
+    return LVS_OK;
+}
+
+// Where a level's results go.  Local form: the four Q x k / Q arrays.  Sharded form (ex != nullptr): every group of queries ends in
+// an exchange with the other ranks and the MERGED lists land in xout ([3][Q][k] int64: score bits | global rows | tie keys).
+struct LevelOut {
+    double* scores; int64_t* rows; uint64_t* ties; uint32_t* counts; int32_t* flags;
+    lvs_exchange* ex; int64_t* xout; int Q_total;
+};
+
+// Enqueue one level of the search for the query indices in `pending` (ascending): ONE fused kernel (query prep + scan + exact
+// rescoring [+ exchange and merge]) per group of up to max_qt consecutive queries.  No synchronisation.
+static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_host, int dtype, const std::vector<int>& pending, int k, int kpl, bool filter,
+                         const uint32_t* const* fcodes, const uint32_t* fwant, uint32_t nf, uint64_t search_base, const LevelOut& out,
+                         cudaStream_t st, int* launches, bool time_first) {
     const int sm = g_lib.sm_count;
-    double* q64 = (double*)c->s_q64.p;
-    float* q32 = (float*)c->s_q32.p;
-    float* qnorm = (float*)c->s_qnorm.p;
     uint64_t* keys = (uint64_t*)c->s_keys.p;
     uint64_t* mins = (uint64_t*)c->s_mins.p;
     const int chain = (int)((c->chunks_per_row + 31) / 32) * (c->storage == LVS_STORAGE_F32 ? 4 : 8);
     const float eps_rel = (float)(chain + 12) * 1.1920929e-7f;
     const int max_qt = max_qt_for_kpl(kpl);
+    const size_t qrow = (size_t)c->dim * dt_size(dtype);
     int rc;
     size_t i = 0;
     bool first_group = time_first;
@@ -783,15 +812,49 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
         int cnt = 1;
         while (cnt < max_qt && i + cnt < pending.size() && pending[i + cnt] == first + cnt) ++cnt;
         const int qt_use = cnt == 1 ? 1 : cnt == 2 ? 2 : 4;
+        const uint32_t kpw = 32u * kpl;
+
+        FinalizeParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.kp = kpw; fp.k = (uint32_t)k;
+        fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
+        fp.storage = c->storage; fp.metric = c->metric;
+        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint64_t)first;
+        fp.pw = c->d_pw; fp.eps = eps_rel; fp.row_base = c->row_base;
+        int nrw = kFinWarps;
+        const size_t xbytes = out.ex ? (size_t)kMaxRanks * k * 24 : 0;       // merge scratch behind the finalize carve-up
+        const size_t fin_budget = g_lib.smem_optin - kScanStaticSmem - xbytes;
+        while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > fin_budget) --nrw;
+        if (finalize_smem_bytes(fp.dim_pad, nrw) > fin_budget) return fail(LVS_ELIMIT, "dim %d does not fit the rescoring buffers", c->dim);
+        fp.n_rescore_warps = nrw;
+        fp.cand_scores = (double*)c->s_cand.p; fp.tickets = c->d_counter + 12;   // 4 tickets (one per query slot)
+        if (!out.ex) {
+            fp.out_scores = out.scores + (size_t)first * k; fp.out_rows = out.rows + (size_t)first * k; fp.out_ties = out.ties + (size_t)first * k;
+            fp.out_flags = out.flags + first; fp.out_counts = out.counts + first;
+        }
+        fp.qnorm = nullptr; fp.max_norm = c->d_max_norm;
+        const size_t fin_bytes = finalize_smem_bytes(fp.dim_pad, nrw) + xbytes;
+
         ScanGeom g;
-        if ((rc = scan_geometry(c, qt_use, filter, &g)) != LVS_OK) return rc;
+        if ((rc = scan_geometry(c, qt_use, filter, fin_bytes, &g)) != LVS_OK) return rc;
         ScanParams sp;
         memset(&sp, 0, sizeof(sp));
         sp.base = c->d_vec; sp.row_bytes = c->row_bytes; sp.chunks_per_row = c->chunks_per_row;
         sp.n_rows = (uint32_t)c->n_rows; sp.stage_rows = g.stage_rows; sp.n_stages = g.n_stages; sp.stage_bytes = g.stage_bytes;
         sp.n_tiles = (uint32_t)((c->n_rows + g.stage_rows - 1) / g.stage_rows);
         sp.n_blocks32 = (uint32_t)((c->n_rows + 31) / 32);
-        sp.queries = q32 + (size_t)first * c->q_stride; sp.q_stride = c->q_stride;
+        sp.q_raw = (const uint8_t*)d_queries + (size_t)first * qrow; sp.q_dtype = dtype; sp.dim = c->dim; sp.metric = c->metric;
+        sp.n_queries = (uint32_t)cnt; sp.q_stride = c->q_stride;
+        const uint32_t seq = c->launch_seq + 1;
+        sp.seq = seq; sp.done_seq = c->d_counter + 10;
+        if (q_in_host) {
+            // mapped pinned host memory: CTA 0 stages the group's queries in HBM for the other CTAs (scan_kernel.cuh)
+            const size_t slot_bytes = (size_t)4 * c->dim * 8;
+            if ((rc = ensure_dev(c->s_qstage, 2 * slot_bytes)) != LVS_OK) return rc;
+            sp.q_host = sp.q_raw;
+            sp.q_stage = (uint8_t*)c->s_qstage.p + (size_t)(seq & 1u) * slot_bytes;
+            sp.q_raw = sp.q_stage; sp.q_flag = c->d_counter + 11; sp.q_bytes = (uint32_t)((size_t)cnt * qrow);
+        }
         sp.live = c->d_live;
         for (uint32_t f = 0; f < nf; ++f) { sp.codes[f] = fcodes[f]; sp.want[f] = fwant[f]; }
         sp.n_filter = nf;
@@ -799,6 +862,21 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
         int grid = c->opt_grid > 0 ? c->opt_grid : sm;
         const uint32_t units = filter ? sp.n_blocks32 : sp.n_tiles;
         grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, units));
+        // keys of query slot s of this group live at keys + s*grid*kpw
+        fp.keys = keys; fp.tops = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid;
+        // CTAs per query for the rescoring: as many as it takes to give every candidate its own warp, at most 8 CTAs in all
+        const uint32_t cq = std::max<uint32_t>(1u, std::min<uint32_t>(8u / (uint32_t)cnt, (kpw + nrw - 1) / nrw));
+        sp.ticket = c->d_counter + 4; sp.n_helpers = (uint32_t)cnt * cq;
+        const bool dyn = !filter && grid == sm && c->opt_dyn_tiles;       // dynamic tile scheduling needs one CTA per SM (see the kernel)
+        if (dyn) { sp.tile_counter = c->d_counter + 6 + (seq & 1u); sp.tile_base = c->tile_base[seq & 1u]; }
+        sp.pdl = c->opt_pdl && !c->opt_timing ? 1u : 0u;
+        ExchangeParams xp;
+        memset(&xp, 0, sizeof(xp));
+        if (out.ex) {
+            if ((rc = exchange_params(out.ex, cnt, k, &xp)) != LVS_OK) return rc;
+            xp.out = out.xout; xp.out_counts = out.counts; xp.out_flags = out.flags; xp.Q_out = out.Q_total; xp.q_out0 = first;
+            sp.exchange = 1u;
+        }
         cudaEvent_t es = nullptr, ee = nullptr;
         if (c->opt_timing) {
             const int slot = c->ring_pos % kEventRing;
@@ -807,39 +885,17 @@ static int enqueue_level(lvs_collection* c, const std::vector<int>& pending, int
             c->ring_pos++;
             CU(cudaEventRecord(es, st));
         }
-        cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, grid, g.smem, st);
+        cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, fp, xp, grid, g.smem, st);
         if (e != cudaSuccess) return fail(LVS_ECUDA, "scan kernel launch failed: %s (qt=%d kpl=%d smem=%zu)", cudaGetErrorString(e), qt_use, kpl, g.smem);
         ++*launches;
+        c->launch_seq = seq;
+        if (dyn) c->tile_base[seq & 1u] += sp.n_tiles + (uint32_t)grid;     // every producer draws exactly one tile past the end
         if (c->opt_timing) CU(cudaEventRecord(ee, st));
-        if (first_group) { c->first_scan_start = es; c->first_scan_end = ee; }
-
-        FinalizeParams fp;
-        memset(&fp, 0, sizeof(fp));
-        const uint32_t kpw = 32u * kpl;
-        fp.keys = keys; fp.tops = mins; fp.M = (uint32_t)grid * kpw; fp.L = (uint32_t)grid; fp.kp = kpw; fp.k = (uint32_t)k;
-        fp.base = c->d_vec; fp.row_bytes = c->row_bytes; fp.dim = c->dim; fp.dim_pad = (int)c->q_stride;
-        fp.storage = c->storage; fp.metric = c->metric;
-        fp.q64 = q64 + (size_t)first * c->dim;
-        fp.tiekey = c->d_tie; fp.epoch = c->d_epoch; fp.search_no = search_base + (uint64_t)first;
-        fp.pw = c->d_pw; fp.eps = eps_rel; fp.row_base = c->row_base;
-        int nrw = kFinWarps;
-        while (nrw > 1 && finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) --nrw;
-        if (finalize_smem_bytes(fp.dim_pad, nrw) > g_lib.smem_optin) return fail(LVS_ELIMIT, "dim %d does not fit the rescoring buffers", c->dim);
-        fp.n_rescore_warps = nrw;
-        fp.cand_scores = (double*)c->s_cand.p; fp.tickets = c->d_counter + 12;   // 4 tickets (one per query slot)
-        fp.out_scores = d_scores + (size_t)first * k; fp.out_rows = d_rows + (size_t)first * k; fp.out_ties = d_ties + (size_t)first * k;
-        fp.out_flags = d_flags + first; fp.out_counts = d_counts + first;
-        fp.qnorm = qnorm + first; fp.max_norm = c->d_max_norm;
-        // keys of query slot s of this group live at keys + s*grid*kpw: the finalize CTA x-index is the slot
-        const size_t fsm = finalize_smem_bytes(fp.dim_pad, nrw);
-        const unsigned ncta = (unsigned)std::min<uint32_t>(8u, (kpw + nrw - 1) / nrw);
-        {
-            cudaError_t fe = kpl == 1 ? launch_finalize<1>(fp, cnt, ncta, fsm, st) : kpl == 2 ? launch_finalize<2>(fp, cnt, ncta, fsm, st)
-                           : kpl == 4 ? launch_finalize<4>(fp, cnt, ncta, fsm, st) : launch_finalize<8>(fp, cnt, ncta, fsm, st);
-            if (fe != cudaSuccess) return fail(LVS_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(fe));
+        if (first_group) {
+            c->first_scan_start = es; c->first_scan_end = ee;
+            if (c->opt_timing) CU(cudaEventRecord(c->ev[4], st));
+            first_group = false;
         }
-        ++*launches;
-        if (first_group) { if (c->opt_timing) CU(cudaEventRecord(c->ev[4], st)); first_group = false; }
         i += cnt;
     }
     return LVS_OK;
@@ -1036,37 +1092,42 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint64_t searc
 
 // Core: queries already on the device (raw, `dtype`); outputs are device buffers.  With `async` the work is only
 // enqueued (no escalation, flags stay on the device in d_flags_out); otherwise flagged queries are repeated with a
-// larger candidate set and the host flags are returned.
+// larger candidate set and the host flags are returned.  Sharded form (ex != nullptr, async only): every rank calls it with
+// the same arguments; the merged result of all ranks lands in xout ([3][Q][k] int64), d_counts and the flags.
 static int search_core(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                        double* d_scores, int64_t* d_rows, uint64_t* d_ties, uint32_t* d_counts, int32_t* h_flags,
                        int32_t* d_flags_out, bool async, cudaStream_t st, int64_t base_override = -1, int kpl_min = 0,
-                       const std::vector<int>* only = nullptr) {
+                       const std::vector<int>* only = nullptr, lvs_exchange* ex = nullptr, int64_t* xout = nullptr,
+                       bool q_in_host = false) {
     if (Q <= 0) return LVS_OK;
     if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
     if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
+    if (ex && !async) return fail(LVS_EINVAL, "the sharded search is enqueue-only");
+    if (!q_in_host) {
+        // callers may hand in mapped pinned HOST memory as a "device" pointer (unified addressing): such queries are staged by
+        // one CTA instead of being pulled over PCIe by every CTA
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, d_queries) == cudaSuccess) q_in_host = pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
     const int sm = g_lib.sm_count;
     int rc;
-    if ((rc = ensure_dev(c->s_q64, (size_t)Q * c->dim * 8)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_q32, (size_t)(Q + 4) * c->q_stride * 4)) != LVS_OK) return rc;
-    if ((rc = ensure_dev(c->s_qnorm, (size_t)Q * 4)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_keys, (size_t)4 * sm * 256 * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_mins, (size_t)4 * sm * 8)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_flags, (size_t)Q * 4)) != LVS_OK) return rc;
     if ((rc = ensure_dev(c->s_cand, (size_t)4 * kMaxCand * 8)) != LVS_OK) return rc;
     if ((rc = ensure_pinned(c->h_flags, (size_t)Q * 4)) != LVS_OK) return rc;
     int32_t* d_flags = d_flags_out ? d_flags_out : (int32_t*)c->s_flags.p;
+    // the per-collection scratch (lists, tickets, candidate scores) is shared by every search on this handle: a search on
+    // another stream than the previous one is ordered behind it
+    if (c->last_stream_valid && c->last_stream != st) {
+        CU(cudaEventRecord(c->order_ev, c->last_stream));
+        CU(cudaStreamWaitEvent(st, c->order_ev, 0));
+    }
+    c->last_stream = st; c->last_stream_valid = true;
 
     int launches = 0;
     if (c->opt_timing) CU(cudaEventRecord(c->ev[0], st));
-    {
-        PrepParams pp;
-        pp.src = d_queries; pp.src_dtype = dtype; pp.dim = c->dim; pp.metric = c->metric;
-        pp.q64 = (double*)c->s_q64.p; pp.q32 = (float*)c->s_q32.p; pp.q_stride = c->q_stride; pp.qnorm = (float*)c->s_qnorm.p;
-        pp.n_zero_rows = 4;
-        prep_queries_kernel<<<Q + 1, 256, 0, st>>>(pp);   // CTA Q zeroes the 4 padding query rows
-        CU(cudaGetLastError());
-        ++launches;
-    }
     const uint32_t* fcodes[kMaxFilterCols];
     uint32_t fwant[kMaxFilterCols];
     uint32_t nf = 0;
@@ -1089,8 +1150,37 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     if (!only && gemm_eligible(c, Q, filter)) {
         // K2 for the whole batch; queries whose exactness bound is not met fall through to the K1 levels below
         kind = 2;
-        rc = enqueue_gemm(c, Q, k, kpl, search_base, d_scores, d_rows, d_ties, d_counts, d_flags, st, &launches, fcodes, fwant, nf);
+        if ((rc = ensure_dev(c->s_q64, (size_t)Q * c->dim * 8)) != LVS_OK) return rc;
+        if ((rc = ensure_dev(c->s_q32, (size_t)(Q + 4) * c->q_stride * 4)) != LVS_OK) return rc;
+        if ((rc = ensure_dev(c->s_qnorm, (size_t)Q * 4)) != LVS_OK) return rc;
+        {
+            PrepParams pp;
+            pp.src = d_queries; pp.src_dtype = dtype; pp.dim = c->dim; pp.metric = c->metric;
+            pp.q64 = (double*)c->s_q64.p; pp.q32 = (float*)c->s_q32.p; pp.q_stride = c->q_stride; pp.qnorm = (float*)c->s_qnorm.p;
+            pp.n_zero_rows = 4;
+            prep_queries_kernel<<<Q + 1, 256, 0, st>>>(pp);   // CTA Q zeroes the 4 padding query rows
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        double* ls = d_scores; int64_t* lr = d_rows; uint64_t* lt = d_ties; uint32_t* lc = d_counts; int32_t* lf = d_flags;
+        if (ex) {
+            // sharded: the local lists go to scratch, the exchange kernel publishes and merges them
+            const size_t n = (size_t)Q * k;
+            if ((rc = ensure_dev(c->s_xlocal, n * 24 + (size_t)Q * 8)) != LVS_OK) return rc;
+            int64_t* xl = (int64_t*)c->s_xlocal.p;
+            ls = (double*)xl; lr = xl + n; lt = (uint64_t*)(xl + 2 * n); lc = (uint32_t*)(xl + 3 * n); lf = (int32_t*)(lc + Q);
+        }
+        rc = enqueue_gemm(c, Q, k, kpl, search_base, ls, lr, lt, lc, lf, st, &launches, fcodes, fwant, nf);
         if (rc != LVS_OK) return rc;
+        if (ex) {
+            ExchangeParams xp;
+            memset(&xp, 0, sizeof(xp));
+            if ((rc = exchange_params(ex, Q, k, &xp)) != LVS_OK) return rc;
+            xp.local = (const int64_t*)c->s_xlocal.p; xp.local_flags = lf;
+            xp.out = xout; xp.out_counts = d_counts; xp.out_flags = d_flags; xp.Q_out = Q; xp.q_out0 = 0;
+            if ((rc = launch_exchange(xp, st)) != LVS_OK) return rc;
+            ++launches;
+        }
         first = false;
         pending.clear();
         if (!async) {
@@ -1099,9 +1189,11 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
             for (int qi = 0; qi < Q; ++qi) if (hf[qi] & 1) pending.push_back(qi);
         }
     }
+    LevelOut lo;
+    lo.scores = d_scores; lo.rows = d_rows; lo.ties = d_ties; lo.counts = d_counts; lo.flags = d_flags;
+    lo.ex = ex; lo.xout = xout; lo.Q_total = Q;
     while (!pending.empty()) {
-        rc = enqueue_level(c, pending, k, kpl, filter, fcodes, fwant, nf, search_base, d_scores, d_rows, d_ties, d_counts,
-                           d_flags, st, &launches, first);
+        rc = enqueue_level(c, d_queries, q_in_host, dtype, pending, k, kpl, filter, fcodes, fwant, nf, search_base, lo, st, &launches, first);
         if (rc != LVS_OK) return rc;
         first = false;
         if (async) break;
@@ -1144,6 +1236,24 @@ extern "C" int lvs_search_device(lvs_collection* c, const void* d_queries, int d
     return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, out_flags, nullptr, false, st);
 }
 
+extern "C" int lvs_search_device_at(lvs_collection* c, uint64_t search_no, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                                    double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                                    int32_t* out_flags, void* stream) {
+    bind_thread();
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (Q < 0 || (Q > 0 && (!d_queries || !d_out_scores || !d_out_rows || !d_out_ties || !d_out_counts)))
+        return fail(LVS_EINVAL, "NULL device buffer");
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (search_no < 1 || search_no + (uint64_t)Q - 1 > c->search_counter) return fail(LVS_EINVAL, "search numbers outside 1..%llu", (unsigned long long)c->search_counter);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    // a repeat: the exact scan (K1) with a candidate set one size up, numbered as the searches it repeats
+    std::vector<int> all(Q);
+    for (int i = 0; i < Q; ++i) all[i] = i;
+    return search_core(c, d_queries, dtype, Q, k, want, d_out_scores, d_out_rows, d_out_ties, d_out_counts, out_flags, nullptr, false, st,
+                       (int64_t)search_no, 0, &all);
+}
+
 extern "C" int lvs_search_device_async(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                                        double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                                        int32_t* d_out_flags, void* stream) {
@@ -1183,7 +1293,8 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
     sl.has_want = want != nullptr;
     if (want) memcpy(sl.want, want, sizeof(uint32_t) * kMaxFilterCols);
     rc = search_core(c, dview, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
-                     (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st);
+                     (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st, -1, 0, nullptr, nullptr,
+                     nullptr, true);
     if (rc != LVS_OK) return rc;
     sl.kpl = c->last_kpl;
     sl.kind = c->last_kind;
@@ -1212,7 +1323,7 @@ static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int6
         std::vector<int32_t> f2(Q, 0);
         int rc = search_core(c, dview, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
                              (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
-                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo);
+                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo, nullptr, nullptr, true);
         if (rc != LVS_OK) { sl.in_use = false; return rc; }
         for (int i : redo) hflags[i] = f2[i];
     }
@@ -1322,19 +1433,6 @@ extern "C" int lvs_merge_topk_device(const double* d_scores, const int64_t* d_ro
 // ------------------------------------------------------------------------------------------------------
 // K5': fused exchange + merge over peer memory
 // ------------------------------------------------------------------------------------------------------
-struct lvs_exchange {
-    int world = 1, rank = 0, max_q = 0, max_k = 0;
-    size_t blk_stride = 0;          // int64 elements per rank block
-    size_t slot_elems = 0;          // int64 elements per slot = world * blk_stride
-    uint8_t* base = nullptr;        // [2 slots][world][blk_stride] int64, then flags [2][kMaxRanks] uint64
-    size_t flags_off = 0;
-    uint8_t* peers[kMaxRanks] = {nullptr};
-    bool opened[kMaxRanks] = {false};
-    uint32_t* d_counter = nullptr;  // [0] done counter, [1] error word
-    uint64_t seq = 0;
-    bool connected = false;
-};
-
 extern "C" int lvs_exchange_create(int world, int rank, int max_q, int max_k, lvs_exchange** out, void* ipc_handle_out) {
     bind_thread();
     if (!g_lib.ready) return fail(LVS_ESTATE, "lvs_init() has not been called (no CUDA device bound)");
@@ -1344,7 +1442,7 @@ extern "C" int lvs_exchange_create(int world, int rank, int max_q, int max_k, lv
     lvs_exchange* ex = new (std::nothrow) lvs_exchange();
     if (!ex) return fail(LVS_ENOMEM, "host allocation failed");
     ex->world = world; ex->rank = rank; ex->max_q = max_q; ex->max_k = max_k;
-    ex->blk_stride = (((size_t)3 * max_q * max_k) + 31) & ~(size_t)31;
+    ex->blk_stride = (((size_t)3 * max_q * max_k + (size_t)max_q) + 31) & ~(size_t)31;   // [3][Q][k] lists + [Q] flags
     ex->slot_elems = (size_t)world * ex->blk_stride;
     ex->flags_off = 2 * ex->slot_elems * 8;
     const size_t bytes = ex->flags_off + 2 * kMaxRanks * 8;
@@ -1379,32 +1477,30 @@ extern "C" int lvs_exchange_connect(lvs_exchange* ex, const void* all_handles) {
     return LVS_OK;
 }
 
-extern "C" int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, int Q, int k, int64_t* d_out, uint32_t* d_out_counts,
-                                         void* stream) {
+extern "C" int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, const int32_t* d_local_flags, int Q, int k,
+                                         int64_t* d_out, uint32_t* d_out_counts, int32_t* d_out_flags, void* stream) {
     bind_thread();
     if (!ex || !d_local || !d_out || !d_out_counts) return fail(LVS_EINVAL, "NULL argument");
-    if (!ex->connected && ex->world > 1) return fail(LVS_ESTATE, "lvs_exchange_connect() has not been called");
-    if (Q < 1 || k < 1 || (size_t)3 * Q * k > ex->blk_stride) return fail(LVS_ELIMIT, "Q x k = %d x %d exceeds the exchange buffer (%d x %d)", Q, k, ex->max_q, ex->max_k);
-    const size_t smem = (size_t)ex->world * k * 24;
-    if (smem > 200 * 1024) return fail(LVS_ELIMIT, "world * k too large for the merge");
-    ex->seq += 1;
-    const int slot = (int)(ex->seq & 1);
     ExchangeParams p;
     memset(&p, 0, sizeof(p));
-    p.local = d_local; p.Q = Q; p.k = k; p.world = ex->world; p.rank = ex->rank;
-    for (int r = 0; r < ex->world; ++r) {
-        p.peer_data[r] = (int64_t*)ex->peers[r] + (size_t)slot * ex->slot_elems;
-        p.peer_flags[r] = (uint64_t*)(ex->peers[r] + ex->flags_off) + (size_t)slot * kMaxRanks;
-    }
-    p.my_data = (const int64_t*)ex->base + (size_t)slot * ex->slot_elems;
-    p.my_flags = (const uint64_t*)(ex->base + ex->flags_off) + (size_t)slot * kMaxRanks;
-    p.seq = ex->seq; p.blk_stride = ex->blk_stride; p.done_counter = ex->d_counter; p.err = ex->d_counter + 1;
-    p.out = d_out; p.out_counts = d_out_counts;
-    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::max(1, std::min(Q, 32));
-    exchange_merge_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-    CU(cudaGetLastError());
-    return LVS_OK;
+    int rc = exchange_params(ex, Q, k, &p);
+    if (rc != LVS_OK) return rc;
+    p.local = d_local; p.local_flags = d_local_flags;
+    p.out = d_out; p.out_counts = d_out_counts; p.out_flags = d_out_flags; p.Q_out = Q; p.q_out0 = 0;
+    return launch_exchange(p, (cudaStream_t)stream);
+}
+
+extern "C" int lvs_search_sharded_device_async(lvs_collection* c, lvs_exchange* ex, const void* d_queries, int dtype, int Q, int k,
+                                               const uint32_t* want, int64_t* d_out, uint32_t* d_out_counts, int32_t* d_out_flags,
+                                               void* stream) {
+    bind_thread();
+    if (!c || !ex) return fail(LVS_EINVAL, "collection / exchange is NULL");
+    if (Q < 0 || (Q > 0 && (!d_queries || !d_out || !d_out_counts || !d_out_flags))) return fail(LVS_EINVAL, "NULL device buffer");
+    if (Q > 65535) return fail(LVS_ELIMIT, "batch of %d queries exceeds 65535", Q);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return search_core(c, d_queries, dtype, Q, k, want, nullptr, nullptr, nullptr, d_out_counts, nullptr, d_out_flags, true, st, -1, 0,
+                       nullptr, ex, d_out);
 }
 
 extern "C" int lvs_exchange_error(lvs_exchange* ex) {
@@ -2060,6 +2156,8 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "grid")) c->opt_grid = std::max(0, std::min(value, g_lib.sm_count));   // the scratch lists are sized for one CTA per SM
     else if (!strcmp(name, "force_kpl")) c->opt_force_kpl = value;
     else if (!strcmp(name, "timing")) c->opt_timing = value ? 1 : 0;
+    else if (!strcmp(name, "pdl")) c->opt_pdl = value ? 1 : 0;
+    else if (!strcmp(name, "dyn_tiles")) c->opt_dyn_tiles = value ? 1 : 0;
     else if (!strcmp(name, "gemm_min_q")) c->opt_gemm_min_q = value;
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;

@@ -16,6 +16,7 @@ import os
 
 from . import _native as N
 from .collection import DeviceCollection, merge_topk_device
+from .errors import NativeLibraryError
 
 
 def shard_bounds(n_total: int, world: int, align: int = 1) -> list[tuple[int, int]]:
@@ -60,6 +61,7 @@ class ShardedSearcher:
         self._bufs: dict[tuple, dict] = {}
         self.merge_launches = 0
         self.stream = torch.cuda.Stream(device=self.device)
+        shard.set_option("timing", 0)      # consecutive searches overlap (programmatic dependent launch); bench.py's roofline leg turns it on
         self.n_slots = 4
         self._next_slot = 0
         # exchange step: "p2p" = one kernel per rank that stores its block into every peer's gather buffer over NVLink
@@ -110,41 +112,108 @@ class ShardedSearcher:
             if self.world > 1:
                 b["local"] = t.zeros((3, Q, k), dtype=t.int64, device=self.device)
                 b["local_counts"] = t.zeros(Q, dtype=t.int32, device=self.device)
+                b["local_flags"] = t.zeros(Q, dtype=t.int32, device=self.device)
                 b["gathered"] = t.zeros((self.world, 3, Q, k), dtype=t.int64, device=self.device)
             self._bufs[key] = b
         return b
 
     def _enqueue(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, b: dict) -> None:
-        """prep + scan + finalize on the shard, then (world > 1) all-gather + merge, all on self.stream."""
+        """This rank's search + the exchange + the merge, all on self.stream.  "p2p" (default): ONE call into the library - for
+        up to 4 queries on the scan path that is one kernel per rank (scan + exact rescoring + peer-memory exchange + merge),
+        batches add the exchange kernel behind the tensor-core path's finalize.  "nccl": local search, all_gather_into_tensor,
+        merge kernel (the form BASELINE.json's north_star names).  Either way every rank ends up with the same merged lists
+        and the same merged flags (OR over the shards)."""
         stream = self.stream.cuda_stream
         out = b["out"]
+        b["base"] = self.shard.search_counter + 1          # reference search number of query 0 (a repeat re-uses it)
+        b["want"], b["q"] = want, (q_ptr, q_dtype, Q, k)
         if self.world == 1:
             self.shard.search_device_async(q_ptr, q_dtype, Q, k, want, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                            b["counts"].data_ptr(), b["flags"].data_ptr(), stream)
             return
-        local = b["local"]
-        self.shard.search_device_async(q_ptr, q_dtype, Q, k, want, local[0].data_ptr(), local[1].data_ptr(), local[2].data_ptr(),
-                                       b["local_counts"].data_ptr(), b["flags"].data_ptr(), stream)
         if self.exchange_mode == "p2p":
             ex = self._exchange(Q, k)
-            N.check(N.load().lvs_exchange_merge_device(ex, C.c_void_p(local.data_ptr()), Q, k, C.c_void_p(out.data_ptr()),
-                                                       C.c_void_p(b["counts"].data_ptr()), C.c_void_p(stream)),
-                    "lvs_exchange_merge_device")
-            self.merge_launches += 1
+            self.shard.search_sharded_device_async(ex, q_ptr, q_dtype, Q, k, want, out.data_ptr(), b["counts"].data_ptr(),
+                                                   b["flags"].data_ptr(), stream)
             return
+        local = b["local"]
+        self.shard.search_device_async(q_ptr, q_dtype, Q, k, want, local[0].data_ptr(), local[1].data_ptr(), local[2].data_ptr(),
+                                       b["local_counts"].data_ptr(), b["local_flags"].data_ptr(), stream)
         with self.torch.cuda.stream(self.stream):
             allgather_packed(local, b["gathered"], self.group)
+            self.dist.all_reduce(b["local_flags"], op=self.dist.ReduceOp.MAX, group=self.group)
+            b["flags"].copy_(b["local_flags"], non_blocking=True)
         n = Q * k
         base = b["gathered"].data_ptr()
         merge_topk_device(base, base + 8 * n, base + 16 * n, self.world, Q, k, out[0].data_ptr(), out[1].data_ptr(),
                           out[2].data_ptr(), b["counts"].data_ptr(), stream, shard_stride=3 * n)
         self.merge_launches += 1
 
+    def _settle(self, b: dict, flags: np.ndarray, queries_of=None) -> np.ndarray:
+        """After a search has completed: raise if the exchange failed, and REPEAT the queries that some shard could not prove
+        exact (merged flags are identical on every rank, so every rank takes the same decision): each rank redoes them through
+        the synchronous path of the library - larger candidate sets, the exact scan instead of the tensor-core path, as the same
+        reference searches - and the lists are exchanged and merged again.  Returns the final flags."""
+        t = self.torch
+        if (flags & N.FLAG_EXCHANGE).any():
+            raise NativeLibraryError("sharded search: a peer's result lists did not arrive (exchange timeout); a rank is down or stalled")
+        idx = np.nonzero(flags & N.FLAG_UNPROVEN)[0]
+        if idx.size == 0:
+            return flags
+        q_ptr, q_dtype, Q, k = b["q"]
+        esz = 8 if q_dtype == "f64" else 4
+        lib = N.load()
+        rb = self._repeat_bufs(k)
+        out = b["out"]
+        for qi in idx.tolist():
+            # the query may live in pinned host memory or on the device: both are addressable from the GPU
+            self.shard.search_device_at(int(b["base"]) + qi, q_ptr + qi * self.shard.dim * esz, q_dtype, 1, k, b["want"],
+                                        rb["local"][0].data_ptr(), rb["local"][1].data_ptr(), rb["local"][2].data_ptr(),
+                                        rb["counts"].data_ptr(), rb["hflags"], self.stream.cuda_stream)
+            if self.world > 1:
+                rb["dflags"].copy_(t.from_numpy(rb["hflags"]), non_blocking=False)
+                if self.exchange_mode == "p2p":
+                    N.check(lib.lvs_exchange_merge_device(self._exchange(1, k), C.c_void_p(rb["local"].data_ptr()), C.c_void_p(rb["dflags"].data_ptr()),
+                                                          1, k, C.c_void_p(rb["out"].data_ptr()), C.c_void_p(rb["counts"].data_ptr()),
+                                                          C.c_void_p(rb["dflags2"].data_ptr()), C.c_void_p(self.stream.cuda_stream)),
+                            "lvs_exchange_merge_device")
+                else:
+                    with t.cuda.stream(self.stream):
+                        allgather_packed(rb["local"], rb["gathered"], self.group)
+                        self.dist.all_reduce(rb["dflags"], op=self.dist.ReduceOp.MAX, group=self.group)
+                        rb["dflags2"].copy_(rb["dflags"])
+                    base = rb["gathered"].data_ptr()
+                    merge_topk_device(base, base + 8 * k, base + 16 * k, self.world, 1, k, rb["out"][0].data_ptr(), rb["out"][1].data_ptr(),
+                                      rb["out"][2].data_ptr(), rb["counts"].data_ptr(), self.stream.cuda_stream, shard_stride=3 * k)
+                self.stream.synchronize()
+                res, f = rb["out"], int(rb["dflags2"].item())
+            else:
+                self.stream.synchronize()
+                res, f = rb["local"], int(rb["hflags"][0])
+            with t.cuda.stream(self.stream):
+                out[:, qi, :].copy_(res[:, 0, :])
+                b["counts"][qi:qi + 1].copy_(rb["counts"])
+            self.stream.synchronize()
+            flags[qi] = f
+        return flags
+
+    def _repeat_bufs(self, k: int) -> dict:
+        rb = self._bufs.get(("repeat", k))
+        if rb is None:
+            t = self.torch
+            dev = lambda *shape, dtype: t.zeros(shape, dtype=dtype, device=self.device)
+            rb = {"local": dev(3, 1, k, dtype=t.int64), "out": dev(3, 1, k, dtype=t.int64), "counts": dev(1, dtype=t.int32),
+                  "dflags": dev(1, dtype=t.int32), "dflags2": dev(1, dtype=t.int32), "hflags": np.zeros(1, dtype=np.int32),
+                  "gathered": dev(self.world, 3, 1, k, dtype=t.int64)}
+            self._bufs[("repeat", k)] = rb
+        return rb
+
     # ---- device entry points ---------------------------------------------------------------------------
     def search_device_async(self, dq, k: int, want=None, slot: int = 0):
         """dq: CUDA tensor [Q, dim] float32/float64 (same on every rank), already valid on ``self.stream``.  Enqueue only;
         returns CUDA tensors (scores f64 [Q,k], rows i64, ties i64, counts i32 [Q], flags i32 [Q]) that are valid once
-        ``self.stream`` has been synchronised.  `slot` rotates result buffers between consecutive searches."""
+        ``self.stream`` has been synchronised.  `slot` rotates result buffers between consecutive searches.  Flagged queries
+        (``flags != 0``: some shard could not prove its list exact) are NOT repeated here; :meth:`search_device` does that."""
         t = self.torch
         Q = int(dq.shape[0])
         b = self._slot(Q, k, slot, host=False)
@@ -153,10 +222,12 @@ class ShardedSearcher:
         return out[0].view(t.float64), out[1], out[2], b["counts"], b["flags"]
 
     def search_device(self, dq, k: int, want=None):
-        """Synchronous device entry; returns the tensors plus the host flags."""
+        """Synchronous device entry; flagged queries are repeated (collectively); returns the tensors plus the host flags."""
         s, r, ti, c, f = self.search_device_async(dq, k, want, slot=0)
         self.stream.synchronize()
-        return s, r, ti, c, f.cpu().numpy()
+        b = self._slot(int(dq.shape[0]), k, 0, host=False)
+        flags = self._settle(b, f.cpu().numpy().copy(), queries_of=dq)
+        return s, r, ti, c, flags
 
     # ---- host entry points -----------------------------------------------------------------------------
     def submit(self, queries: np.ndarray, k: int, want=None):
@@ -178,10 +249,14 @@ class ShardedSearcher:
         return b
 
     def wait(self, handle):
+        """Blocks until the search has finished; flagged queries are repeated (every rank takes the same decision, so this stays
+        a collective); raises when the exchange reported a missing peer."""
         handle["event"].synchronize()
+        flags = handle["flags"].numpy().copy()
+        if flags.any():
+            flags = self._settle(handle, flags, queries_of=handle["hq"])
         o = handle["out"].numpy()
-        return (o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy(), handle["counts"].numpy().copy(),
-                handle["flags"].numpy().copy())
+        return (o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy(), handle["counts"].numpy().copy(), flags)
 
     def search(self, queries: np.ndarray, k: int, want=None):
         """Synchronous host entry (one search at a time)."""

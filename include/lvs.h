@@ -43,6 +43,7 @@ extern "C" {
 #define LVS_NO_MATCH 0xFFFFFFFEu   /* filter value never seen in this column: matches nothing */
 #define LVS_MAX_K 224              /* largest `limit` one search call serves */
 #define LVS_FLAG_UNPROVEN 1        /* out_flags bit: exactness bound not met even at the largest candidate set */
+#define LVS_FLAG_EXCHANGE 2        /* out_flags bit (sharded searches): a peer's lists did not arrive in time; the result is not trustworthy */
 
 typedef struct lvs_collection lvs_collection;
 
@@ -107,8 +108,19 @@ int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* 
 int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                       double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                       int32_t* out_flags, void* stream);
+/* Repeat of queries that an enqueue-only search left flagged: same meaning as lvs_search_device, but always on the exact scan
+ * (never the tensor-core path) and accounted as the reference searches number search_no .. search_no + Q - 1 that it repeats
+ * (1-based, <= lvs_search_counter), so that the scores are the ones the first attempt would have returned. */
+int lvs_search_device_at(lvs_collection* c, uint64_t search_no, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
+                         double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
+                         int32_t* out_flags, void* stream);
 /* Enqueue-only form for pipelined callers: nothing is synchronised, flags are written to the DEVICE buffer d_out_flags
- * and a flagged query is NOT repeated with a larger candidate set (the caller may re-issue it synchronously). */
+ * and a flagged query is NOT repeated with a larger candidate set (the caller may re-issue it synchronously).
+ * Consecutive searches enqueued back to back on one stream overlap (programmatic dependent launch: the next search streams
+ * the shard while this one's last CTAs rescore and exchange; option "pdl", on by default, off while "timing" is on).  The
+ * kernel reads the RAW query buffer before it waits for the previous kernel of the stream: d_queries must be produced by a
+ * copy, by work on another stream ordered with an event, or by a kernel that does not signal programmatic launch completion
+ * early - every ordinary producer qualifies; otherwise set "pdl" to 0. */
 int lvs_search_device_async(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
                             double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                             int32_t* d_out_flags, void* stream);
@@ -122,18 +134,26 @@ int lvs_merge_topk_device(const double* d_scores, const int64_t* d_rows, const u
                           int G, int Q, int k, double* d_out_scores, int64_t* d_out_rows, uint64_t* d_out_ties, uint32_t* d_out_counts,
                           void* stream);   /* enqueue only: ordered on `stream` */
 
-/* ---- K5': exchange + merge in ONE kernel over NVLink peer memory (replaces the NCCL all-gather + lvs_merge_topk_device) ---
+/* ---- K5': exchange + merge over NVLink peer memory (replaces the NCCL all-gather + lvs_merge_topk_device) ----------------------
  * One lvs_exchange per process.  create allocates this rank's gather buffer and returns its 64-byte CUDA IPC handle; the
  * caller all-gathers the handles (any transport) and passes the world x 64 bytes to connect, which maps the peers' buffers.
- * lvs_exchange_merge_device: d_local = this rank's packed [3][Q][k] int64 block (float64 score bits | global rows | tie keys);
- * the kernel stores it into every rank's buffer with P2P stores, raises a system-scope flag, waits for all ranks' flags and
- * merges into d_out ([3][Q][k]) / d_out_counts ([Q]).  Enqueue only (ordered on `stream`).  Every rank must issue the same
- * sequence of calls. */
+ * Every rank must issue the same sequence of exchanges (lvs_exchange_merge_device and lvs_search_sharded_device_async calls).
+ * lvs_exchange_merge_device: d_local = this rank's packed [3][Q][k] int64 block (float64 score bits | global rows | tie keys),
+ * d_local_flags = its [Q] flags (or NULL); the kernel stores them into every rank's buffer with P2P stores, raises a system-scope
+ * flag, waits for all ranks' flags and merges into d_out ([3][Q][k]) / d_out_counts ([Q]) / d_out_flags ([Q]: OR of every rank's
+ * flags, | LVS_FLAG_EXCHANGE after a timeout; may be NULL).  Enqueue only (ordered on `stream`). */
 typedef struct lvs_exchange lvs_exchange;
 int lvs_exchange_create(int world, int rank, int max_q, int max_k, lvs_exchange** out, void* ipc_handle_out);
 int lvs_exchange_connect(lvs_exchange* ex, const void* all_handles);
-int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, int Q, int k, int64_t* d_out, uint32_t* d_out_counts,
-                              void* stream);
+int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, const int32_t* d_local_flags, int Q, int k,
+                              int64_t* d_out, uint32_t* d_out_counts, int32_t* d_out_flags, void* stream);
+/* The sharded search as one call per rank: this shard's search + the exchange + the merge, enqueued on `stream`.
+ * Every rank calls it with the same queries, k and filter; every rank gets the same merged d_out ([3][Q][k] int64 as above),
+ * counts and flags (OR over the shards, so a query that one shard could not prove exact is flagged everywhere and the caller can
+ * repeat it collectively).  Up to 4 queries on the scan path are ONE kernel per rank (scan + exact rescoring + exchange + merge);
+ * batches on the tensor-core path add the exchange kernel behind the finalize kernel.  Enqueue only, no repeat of flagged queries. */
+int lvs_search_sharded_device_async(lvs_collection* c, lvs_exchange* ex, const void* d_queries, int dtype, int Q, int k,
+                                    const uint32_t* want, int64_t* d_out, uint32_t* d_out_counts, int32_t* d_out_flags, void* stream);
 int lvs_exchange_error(lvs_exchange* ex);     /* 1 if a peer's flag ever timed out (synchronises) */
 int lvs_exchange_destroy(lvs_exchange* ex);
 
@@ -227,7 +247,9 @@ int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches,
 /* Device time of the last (up to max_n, <= 256) scan-kernel launches, oldest first, from CUDA events recorded on the
  * launching stream, with the algorithmic bytes of each launch.  The stream must have been synchronised. */
 int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n);
-/* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record events, default),
+/* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record CUDA events around every scan launch for
+ * lvs_last_search_timing / lvs_scan_times; default 0; it serialises consecutive searches), "pdl" (1 = programmatic dependent launch
+ * of the scan kernel, default),
  * "gemm_min_q" (batch size from which the tensor-core path is used, default 3; fp32 shards at least 5), "path" (0 auto, 1 scan only,
  * 2 tensor-core whenever eligible), "gemm_stages", "gemm_keep" (keys per K2 list, 4..16), "gemm_no_pair" (1 = never use the
  * cta_group::2 form), "gemm_no_tf32" (1 = fp32 shards stay on the scan), "gemm_no_unit" (1 = always scale by 1/||row||),

@@ -357,8 +357,11 @@ def test_f32_storage_large_batch_uses_scan_passes(lib):
     dev.close()
 
 
-def test_gemm_falls_back_when_bound_fails(lib):
-    """Near-duplicate rows concentrated in one tile defeat the 16-key lists: flagged queries are redone on the K1 path."""
+@pytest.mark.parametrize("k", [100, 110])
+def test_gemm_falls_back_when_bound_fails(lib, k):
+    """Near-duplicate rows concentrated in one tile defeat the 16-key lists: flagged queries are redone on the K1 path - also from
+    k = 104 on, where the candidate set is already the largest one (the pipelined lvs_search / lvs_search_wait route used to return
+    those queries UNPROVEN instead of giving them the exact scan)."""
     n = 16_384
     x, q = synth.unit_rows(n, 768, seed=11, n_queries=8)
     rng = np.random.default_rng(3)
@@ -368,9 +371,9 @@ def test_gemm_falls_back_when_bound_fails(lib):
     ora.upsert_rows_f32(0, xb, [None] * n)
     dev = _dev("gemmfb", 768, storage="bf16")
     dev.upsert(xb)
-    res = dev.search(q.astype(np.float64), 100)
+    res = dev.search(q.astype(np.float64), k)
     for i in range(8):
-        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), 100), REL_BF16)
+        _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16)
     dev.close()
 
 
@@ -462,3 +465,97 @@ def test_sharded_merge_equals_single(lib):
     for sh in shards:
         sh.close()
     single.close()
+
+
+def _exchange_world1(lib, max_q, max_k):
+    import ctypes as C
+    from code_rag_b200 import _native as N
+    ex, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    N.check(lib.lvs_exchange_create(1, 0, max_q, max_k, C.byref(ex), handle), "lvs_exchange_create")
+    return ex
+
+
+@pytest.mark.parametrize("storage,Q,k,n", [("bf16", 1, 10, 9_000), ("f32", 3, 10, 9_000), ("f32", 4, 50, 9_000), ("bf16", 2, 120, 9_000),
+                                           ("bf16", 7, 10, 9_000), ("bf16", 8, 10, 20_480), ("bf16", 130, 100, 20_480)])
+def test_sharded_entry_on_one_rank(lib, storage, Q, k, n):
+    """lvs_search_sharded_device_async with a world of one rank: the publish / flag / wait / merge code of the fused scan kernel
+    (and of the exchange kernel behind the tensor-core path) runs against the rank's own gather buffer, so the single-GPU tier
+    covers it; results must equal the oracle's (and the local entry's)."""
+    import torch
+    x, q = synth.unit_rows(n, 768, seed=77, n_queries=Q)
+    xs = synth.bf16_round(x) if storage == "bf16" else x
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xs, [None] * n)
+    dev = _dev("shard1", 768, storage=storage, row_base=5 << 32, timing=False)
+    dev.upsert(xs.astype(np.float64))
+    ex = _exchange_world1(lib, max(Q, 4), max(k, 16))
+    dq = torch.from_numpy(q.astype(np.float64)).cuda()
+    out = torch.zeros((3, Q, k), dtype=torch.int64, device="cuda")
+    counts = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    flags = torch.full((Q,), 7, dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(2):        # twice: both slots of the double-buffered exchange, and the replay count moves on
+        dev.search_sharded_device_async(ex, dq.data_ptr(), "f64", Q, k, None, out.data_ptr(), counts.data_ptr(), flags.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        o = out.cpu().numpy()
+        from code_rag_b200.collection import SearchResult
+        res = SearchResult(o[0].view(np.float64), o[1] - (5 << 32), o[2].view(np.uint64), counts.cpu().numpy().astype(np.uint32), flags.cpu().numpy())
+        for i in range(Q):
+            _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16 if storage == "bf16" else REL_F32)
+    assert lib.lvs_exchange_error(ex) == 0
+    lib.lvs_exchange_destroy(ex)
+    dev.close()
+
+
+def test_back_to_back_searches_overlap_correctly(lib):
+    """60 single-query searches enqueued back to back on one stream with the programmatic-launch overlap on (timing off): the next
+    search's CTAs start while the previous one's last CTAs are still rescoring; every result must still be the oracle's, with the
+    replay count of ITS position in the sequence."""
+    import torch
+    n = 60_000
+    x, q = synth.unit_rows(n, 768, seed=78, n_queries=60)
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xb, [None] * n)
+    dev = _dev("b2b", 768, storage="bf16", timing=False)
+    dev.upsert(xb)
+    dq = torch.from_numpy(q.astype(np.float64)).cuda()
+    S = torch.zeros((60, 1, 10), dtype=torch.float64, device="cuda")
+    R = torch.zeros((60, 1, 10), dtype=torch.int64, device="cuda")
+    T = torch.zeros((60, 1, 10), dtype=torch.int64, device="cuda")
+    Cn = torch.zeros((60, 1), dtype=torch.int32, device="cuda")
+    F = torch.zeros((60, 1), dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for i in range(60):
+        dev.search_device_async(dq[i:i + 1].data_ptr(), "f64", 1, 10, None, S[i].data_ptr(), R[i].data_ptr(), T[i].data_ptr(),
+                                Cn[i].data_ptr(), F[i].data_ptr(), st.cuda_stream)
+    st.synchronize()
+    from code_rag_b200.collection import SearchResult
+    for i in range(60):
+        res = SearchResult(S[i].cpu().numpy(), R[i].cpu().numpy(), T[i].cpu().numpy().view(np.uint64), Cn[i].cpu().numpy().astype(np.uint32), F[i].cpu().numpy())
+        _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_BF16)
+    dev.close()
+
+
+def test_search_counter_crosses_2_pow_32(lib):
+    """The replay count is (search number - write epoch): both are 64-bit, so a collection that has served 2^32 searches keeps
+    answering exactly.  Rows written long ago have reached the fixed point (or 2-cycle) of local mode's in-place re-normalisation -
+    only the parity of their age matters - so the oracle can stand in for 2^32 searches with 66 or 67 of them."""
+    x, q = synth.unixcoder_like(3_000, 128, seed=91, n_queries=8)
+    dev = _dev("wrap", 128)
+    dev.upsert(x[:2000].astype(np.float64))
+    ora = OracleCollection(128)
+    ora.upsert_rows_f32(0, x[:2000], [None] * 2000)
+    jump = (1 << 32) - 3
+    dev.advance_search_counter(jump)
+    for _ in range(66 + (jump & 1)):                    # same parity as `jump`, past the point where every chain has settled
+        ora._scores(q[0].astype(np.float64))
+    dev.upsert(x[2000:].astype(np.float64))             # written just before the 2^32 boundary
+    ora.upsert_rows_f32(2000, x[2000:], [None] * 1000)
+    for i in range(8):                                  # searches number 2^32 - 2 ... 2^32 + 5
+        res = dev.search(q[i].astype(np.float64), 10)
+        _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
+    assert dev.search_counter == jump + 8
+    dev.close()
