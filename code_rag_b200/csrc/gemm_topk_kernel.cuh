@@ -62,6 +62,8 @@ __host__ __device__ constexpr int gemm_stage_bytes(bool pair) { return kGemmAByt
 
 struct GemmParams {
     uint32_t n_kchunks;
+    uint32_t n_queries;          // queries of this launch (<= n_groups * 128); the TMEM lanes behind them score a zero query and are
+                                 // masked out of the selection (they would never raise a threshold and drag every block through the insert path)
     uint32_t n_rows;
     uint32_t n_tiles;            // ceil(n_rows / 256)
     uint32_t n_groups;           // G: CTAs that walk the same tiles (PAIR: 2 = the cluster)
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
         uint32_t* my_thr = thr_sm + lq * 32;                     // shared by the two warps of this lane quarter
         float* my_inv = inv_sm + ew * 128;
         const uint32_t keep = p.keep;
-        float thr = -INFINITY;                                   // scores at or below thr are dropped
+        const bool active = group * kGemmM + et < p.n_queries;   // a padding lane never selects anything
+        float thr = active ? -INFINITY : INFINITY;                // scores at or below thr are dropped
         uint64_t minkey = 0ull;                                  // smallest key of the list (0 while it has empty slots)
         uint32_t minpos = 0;
         constexpr int NB = kGemmN / 2 / 32;                      // 4 blocks of 32 columns per warp and tile
@@ -321,12 +324,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
             uint32_t mask = 0;
             if (first) {
                 // the first columns a list sees are its first keys
+                if (active) {
 #pragma unroll
-                for (int c = 0; c < kGemmList; ++c) {
-                    const float sc = __uint_as_float(v[c]);
-                    if ((uint32_t)c < keep) my_list[c * 32] = (sc == sc) ? make_key(sc, row0 + c) : 0ull;
+                    for (int c = 0; c < kGemmList; ++c) {
+                        const float sc = __uint_as_float(v[c]);
+                        if ((uint32_t)c < keep) my_list[c * 32] = (sc == sc) ? make_key(sc, row0 + c) : 0ull;
+                    }
+                    rescan();
                 }
-                rescan();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) mask |= ((uint32_t)c >= keep && __uint_as_float(v[c]) > thr) ? (1u << c) : 0u;
             } else {
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
         {
             const size_t q = (size_t)group * kGemmM + lq * 32 + lane;
             const size_t li = q * L2 + pair * 2 + half;
-            p.out_drops[li] = thr > -INFINITY ? (((uint64_t)f32_orderable(thr) << 32) | 0xFFFFFFFFull) : 0ull;
+            p.out_drops[li] = (active && thr > -INFINITY) ? (((uint64_t)f32_orderable(thr) << 32) | 0xFFFFFFFFull) : 0ull;
         }
     }
 

@@ -153,6 +153,8 @@ struct lvs_collection {
         bool has_want = false;
         uint32_t want[kMaxFilterCols];
         Scratch h;
+        Scratch d;             // device twin of h for batches (staged == true)
+        bool staged = false;
         size_t qbytes = 0;
         cudaEvent_t done = nullptr;
     } slots[kSubmitSlots];
@@ -373,6 +375,7 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     if (c->s_cand.p) cudaFree(c->s_cand.p);
     for (auto& sl : c->slots) {
         if (sl.h.p) cudaFreeHost(sl.h.p);
+        if (sl.d.p) cudaFree(sl.d.p);
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (c->h_flags.p) cudaFreeHost(c->h_flags.p);
@@ -923,7 +926,10 @@ static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
     const uint32_t nk = (c->q_stride + kce - 1) / kce;
     if (nk > (uint32_t)kGemmMaxKChunks || c->dim < 64) return false;
     if (c->n_rows < (int64_t)kGemmN * 64) return false;             // too few tiles to fill the machine / the lists
-    const int min_q = c->storage == LVS_STORAGE_BF16 ? c->opt_gemm_min_q : std::max(c->opt_gemm_min_q, 5);
+    int min_q = c->storage == LVS_STORAGE_BF16 ? c->opt_gemm_min_q : std::max(c->opt_gemm_min_q, 5);
+    // two queries on a large bf16 shard: one tensor-core pass (the price of one single-query scan) beats the two-query scan, which is
+    // FMA-issue-bound; on small shards the scan path's single launch wins
+    if (c->storage == LVS_STORAGE_BF16 && min_q == 3 && c->n_rows >= (int64_t)2000000) min_q = 2;
     return c->opt_path == 2 || Q >= min_q;
 }
 
@@ -1013,7 +1019,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint64_t searc
         ++*launches;
         GemmParams gp;
         memset(&gp, 0, sizeof(gp));
-        gp.n_kchunks = nk; gp.n_rows = (uint32_t)c->n_rows;
+        gp.n_kchunks = nk; gp.n_queries = (uint32_t)qb; gp.n_rows = (uint32_t)c->n_rows;
         gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S;
         gp.inv_norm = c->metric == LVS_METRIC_COSINE ? c->d_inv_norm : nullptr; gp.live = c->d_live;
         gp.n_filter = nf;
@@ -1286,15 +1292,27 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
     void* dview = nullptr;
     CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
     cudaStream_t st = c->stream;
-    memcpy(sl.h.p, queries, (size_t)Q * c->dim * dt_size(dtype));
+    const size_t qraw = (size_t)Q * c->dim * dt_size(dtype);
+    memcpy(sl.h.p, queries, qraw);
     const size_t nres = (size_t)Q * k;
-    uint8_t* rp = (uint8_t*)dview + qbytes;
     sl.Q = Q; sl.k = k; sl.dtype = dtype; sl.base = c->search_counter + 1; sl.qbytes = qbytes;
     sl.has_want = want != nullptr;
     if (want) memcpy(sl.want, want, sizeof(uint32_t) * kMaxFilterCols);
-    rc = search_core(c, dview, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
+    // A handful of queries: zero-copy (the kernels read the query block from and store the result block to mapped pinned memory:
+    // no copy-engine hop on a latency-bound step).  A batch: one H2D copy of the queries and one D2H copy of the results around
+    // device-resident work - hundreds of CTAs storing 24 Q k bytes over PCIe from inside the finalize kernel serialise.
+    sl.staged = qraw + rbytes >= (size_t)64 * 1024;
+    uint8_t* qp = (uint8_t*)dview;
+    if (sl.staged) {
+        if ((rc = ensure_dev(sl.d, qbytes + rbytes)) != LVS_OK) return rc;
+        CU(cudaMemcpyAsync(sl.d.p, sl.h.p, qraw, cudaMemcpyHostToDevice, st));
+        qp = (uint8_t*)sl.d.p;
+    }
+    uint8_t* rp = qp + qbytes;
+    rc = search_core(c, qp, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
                      (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st, -1, 0, nullptr, nullptr,
-                     nullptr, true);
+                     nullptr, !sl.staged);
+    if (rc == LVS_OK && sl.staged) CU(cudaMemcpyAsync((uint8_t*)sl.h.p + qbytes, rp, rbytes, cudaMemcpyDeviceToHost, st));
     if (rc != LVS_OK) return rc;
     sl.kpl = c->last_kpl;
     sl.kind = c->last_kind;
@@ -1319,11 +1337,17 @@ static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int6
         // rare: repeat the flagged queries (K1, larger candidate sets), as the same reference searches (same numbers)
         void* dview = nullptr;
         CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
-        uint8_t* rp = (uint8_t*)dview + sl.qbytes;
+        uint8_t* qp = sl.staged ? (uint8_t*)sl.d.p : (uint8_t*)dview;
+        uint8_t* rp = qp + sl.qbytes;
         std::vector<int32_t> f2(Q, 0);
-        int rc = search_core(c, dview, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
+        int rc = search_core(c, qp, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
                              (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
-                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo, nullptr, nullptr, true);
+                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo, nullptr, nullptr, !sl.staged);
+        if (rc == LVS_OK && sl.staged) {
+            cudaError_t e = cudaMemcpyAsync(hp, rp, res_bytes(Q, k), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = fail(LVS_ECUDA, "copy of the repeated results failed: %s", cudaGetErrorString(e));
+        }
         if (rc != LVS_OK) { sl.in_use = false; return rc; }
         for (int i : redo) hflags[i] = f2[i];
     }
