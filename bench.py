@@ -38,6 +38,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "qps_exact_top10_cosine_10Mx768_bf16"
+CPU_KEYS = ("value", "unit", "cores", "kind", "sample", "extrapolated", "best_effort_cpu")
 UNIT = "queries/s"
 CHUNK_ROWS = 250_000
 
@@ -56,6 +57,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the C3 (256 queries x top-100) measurement beside the headline")
+    ap.add_argument("--no-adapter", action="store_true", help="skip the e2e_adapter leg (await store.search(...) through the QdrantManager drop-in)")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the 100M-row configuration (configs[4])")
     ap.add_argument("--stage-kb", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     return ap.parse_args()
@@ -85,7 +88,7 @@ def blas_threads() -> int:
 
 
 def host_chunk(chunk_id: int, rows: int, dim: int, seed: int = 3456) -> np.ndarray:
-    """CPU twin of the corpus generator for the bounded CPU sample (same distribution, numpy RNG)."""
+    """CPU twin of the corpus generator for the CPU arm (same distribution, numpy RNG; one call per chunk of rows)."""
     rng = np.random.default_rng([seed, chunk_id])
     x = rng.standard_normal((rows, dim)).astype(np.float32)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
@@ -96,45 +99,66 @@ def host_chunk(chunk_id: int, rows: int, dim: int, seed: int = 3456) -> np.ndarr
 # reference arm: the reference's CPU path (qdrant-client local mode, restated in oracle/qdrant_local.py)
 # --------------------------------------------------------------------------------------------------------
 def cpu_reference_qps(args, steps: int, warmup: int) -> dict:
-    """Times the oracle on a bounded row sample and scales linearly to the full corpus (the work is a dense
-    O(N*D) scan + sort, linear in N).  Uses every host thread numpy's BLAS will take."""
+    """The reference's CPU path on this box's host cores.  Engine: the real qdrant-client in local mode when it is importable
+    (oracle/real_qdrant.py probes site-packages, baseline/_ref and oracle/_ref), else the numpy restatement of it
+    (oracle/qdrant_local.py, kind "port").  By default a bounded row sample is timed and scaled linearly to the full corpus (the
+    work is a dense O(N*D) pass + a sort; "extrapolated": true); --cpu-sample-rows 0 times the FULL corpus (fp32 in RAM: 30.7 GB
+    for 10M x 768, a minute or two per search) so that one real point validates the scaling."""
+    from oracle import real_qdrant
     from oracle.qdrant_local import OracleCollection
-    n = min(args.cpu_sample_rows, args.rows)
-    x = host_chunk(0, n, args.dim)
-    ora = OracleCollection(args.dim)
-    ora.upsert_rows_f32(0, x, [None] * n)
+    full = args.cpu_sample_rows <= 0
+    n = args.rows if full else min(args.cpu_sample_rows, args.rows)
+    if full:
+        steps, warmup = min(steps, 2), 1
     qs = make_queries(steps + warmup, args.dim, seed=11)
+    real = real_qdrant.find() is not None and n <= 2_000_000       # PointStruct upserts of python lists: bounded samples only
+    if real:
+        eng = real_qdrant.RealManager(args.dim)
+        eng.create_collections()
+        for c0 in range(0, n, 20_000):
+            x = host_chunk(c0 // 20_000, min(20_000, n - c0), args.dim)
+            eng.upsert("code_chunks", list(range(c0, c0 + len(x))), x.astype(np.float64).tolist(), [None] * len(x))
+        search = lambda q: eng.search("code_chunks", q.tolist(), limit=args.k)
+        kind = f"qdrant-client {real_qdrant.version()} (local mode)"
+    else:
+        ora = OracleCollection(args.dim, capacity=n)               # sized up front: no doubling copy of a 30 GB matrix
+        for c0 in range(0, n, CHUNK_ROWS):
+            x = host_chunk(c0 // CHUNK_ROWS, min(CHUNK_ROWS, n - c0), args.dim)
+            ora.upsert_rows_f32(c0, x, [None] * len(x))
+        search = lambda q: ora.search_topk_rows(q, args.k)
+        kind = "port"
     for i in range(warmup):
-        ora.search_topk_rows(qs[i], args.k)
+        search(qs[i])
     t0 = time.perf_counter()
     for i in range(warmup, warmup + steps):
         for _ in range(args.queries):
-            ora.search_topk_rows(qs[i], args.k)
+            search(qs[i])
     dt = (time.perf_counter() - t0) / max(1, steps)
     scale = args.rows / n
-    ms_full = dt * 1e3 * scale
-    # a CPU path that is NOT the reference's arithmetic, only the fastest plain-numpy way to the same ids: rows normalised once,
-    # float32 matrix-vector product (BLAS, all threads), argpartition + sort of the k winners.  Reported so that the GPU/CPU ratio
-    # is not inflated by local mode's per-search re-normalisation, float64 product and full argsort.
-    xn = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-30)
-    q32 = qs.astype(np.float32)
-    for i in range(warmup):
-        sc = xn @ q32[i]
-    t0 = time.perf_counter()
-    for i in range(warmup, warmup + steps):
-        for _ in range(args.queries):
+    out = {"value": args.queries / (dt * scale), "unit": UNIT, "cores": blas_threads(), "kind": kind, "extrapolated": not full,
+           "sample": (f"all {n} rows" if full else f"{n} of {args.rows} rows") + f" x {args.dim} (bf16-rounded, fp32 in RAM), {steps} searches after "
+                     f"{warmup} warm-up" + ("" if full else f"; time scaled x{scale:.0f} (scan + sort is linear in rows)") +
+                     f"; numpy {np.__version__}, {blas_threads()} BLAS threads",
+           "ms_per_step_sample": dt * 1e3, "ms_per_step_scaled": dt * 1e3 * scale}
+    if not real and not full:
+        # a CPU path that is NOT the reference's arithmetic, only the fastest plain-numpy way to the same ids: rows normalised once,
+        # float32 matrix-vector product (BLAS, all threads), argpartition + sort of the k winners.  Reported so that the GPU/CPU ratio
+        # is not inflated by local mode's per-search re-normalisation, float64 product and full argsort.
+        x = ora.vectors[:n]
+        xn = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-30)
+        q32 = qs.astype(np.float32)
+        for i in range(warmup):
             sc = xn @ q32[i]
-            top = np.argpartition(-sc, args.k)[:args.k]
-            top = top[np.argsort(-sc[top], kind="stable")]
-    dt_fast = (time.perf_counter() - t0) / max(1, steps)
-    return {
-        "best_effort_cpu": {"value": args.queries / (dt_fast * scale), "unit": UNIT,
-                            "what": "pre-normalised float32 X @ q (BLAS, all threads) + argpartition, same sample and scaling; not the reference's arithmetic"},
-        "value": args.queries / (dt * scale), "unit": UNIT, "cores": blas_threads(), "kind": "port",
-        "sample": f"{n} of {args.rows} rows x {args.dim} (bf16-rounded, fp32 in RAM), {steps} searches after {warmup} warm-up; "
-                  f"time scaled x{scale:.0f} (scan+sort is linear in rows); numpy {np.__version__}, {blas_threads()} BLAS threads",
-        "ms_per_step_sample": dt * 1e3, "ms_per_step_scaled": ms_full,
-    }
+        t0 = time.perf_counter()
+        for i in range(warmup, warmup + steps):
+            for _ in range(args.queries):
+                sc = xn @ q32[i]
+                top = np.argpartition(-sc, args.k)[:args.k]
+                top = top[np.argsort(-sc[top], kind="stable")]
+        dt_fast = (time.perf_counter() - t0) / max(1, steps)
+        out["best_effort_cpu"] = {"value": args.queries / (dt_fast * scale), "unit": UNIT,
+                                  "what": "pre-normalised float32 X @ q (BLAS, all threads) + argpartition, same sample and scaling; not the reference's arithmetic"}
+    return out
 
 
 def run_reference(args) -> None:
@@ -150,8 +174,10 @@ def run_reference(args) -> None:
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"exact top-{args.k} cosine, {args.rows}x{args.dim} bf16 corpus, {args.queries} query/step",
                    "rows": args.rows, "dim": args.dim, "k": args.k, "queries_per_step": args.queries,
-                   "engine": "qdrant-client local-mode restatement (oracle/qdrant_local.py); qdrant-client itself is not installable here"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "best_effort_cpu")},
+                   "engine": cb["kind"] if cb["kind"] != "port" else
+                             "qdrant-client local-mode restatement (oracle/qdrant_local.py); qdrant-client itself is not installable here"},
+        "cpu_baseline": {k: cb[k] for k in CPU_KEYS if k in cb},
+        "extrapolated": cb["extrapolated"],
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -223,6 +249,53 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------
+class _LazyIds:
+    """Synthetic host metadata for the adapter leg: the point in row r has id r (qdrant ids are unsigned ints or uuids) and the
+    payload {"row": r}.  A real 10M-point store would hold 10M Python strings and dicts; the leg measures the adapter's call path
+    (list -> ndarray, asyncio.to_thread, the C ABI, payload dict copies), not Python's memory allocator."""
+
+    def __init__(self, n): self.n = n
+    def __len__(self): return self.n
+    def __getitem__(self, r): return int(r)
+    def get(self, pid, default=None): return int(pid) if isinstance(pid, int) and 0 <= pid < self.n else default
+    def __contains__(self, pid): return self.get(pid) is not None
+
+
+class _LazyPayloads(_LazyIds):
+    def __getitem__(self, r): return {"row": int(r), "file_path": f"f{int(r) % 50000}.py", "entity_name": f"e{int(r)}"}
+
+
+def build_shard(args, torch, dev, rank, world, rows_total, name):
+    """This rank's row shard of the synthetic corpus: unit-norm gaussian rows rounded to bf16, generated on the GPU chunk by
+    chunk (seeded per global chunk, so the corpus does not depend on the number of shards)."""
+    from code_rag_b200.collection import DeviceCollection
+    from code_rag_b200.sharded import shard_bounds
+    lo, hi = shard_bounds(rows_total, world, align=CHUNK_ROWS if rows_total % (CHUNK_ROWS * world) == 0 else 1)[rank]
+    # global row = shard << 32 | local row when the collection is sharded (what the multi-GPU adapter expects)
+    shard = DeviceCollection(name, args.dim, storage=args.storage, metric="cosine", n_filter_cols=0, capacity=hi - lo,
+                             row_base=(rank << 32) if world > 1 else 0, device=dev.index, timing=False)
+    if args.stage_kb:
+        shard.set_option("stage_kb", args.stage_kb)
+    if args.stages:
+        shard.set_option("stages", args.stages)
+    t0 = time.perf_counter()
+    row = lo
+    while row < hi:
+        n = min(CHUNK_ROWS - (row % CHUNK_ROWS), hi - row)
+        g = torch.Generator(device=dev)
+        g.manual_seed(3456 * 1_000_003 + row // CHUNK_ROWS)
+        full = torch.randn((CHUNK_ROWS, args.dim), generator=g, device=dev, dtype=torch.float32)
+        x = full[row % CHUNK_ROWS: row % CHUNK_ROWS + n]
+        x = x / x.norm(dim=1, keepdim=True)
+        xb = x.to(torch.bfloat16).contiguous() if args.storage == "bf16" else x.contiguous()
+        torch.cuda.synchronize()
+        shard.upsert_device(xb.data_ptr(), "bf16" if args.storage == "bf16" else "f32", n, shard.row_base + (row - lo))
+        row += n
+        del full, x, xb
+    torch.cuda.synchronize()
+    return shard, hi - lo, time.perf_counter() - t0
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -242,224 +315,288 @@ def run_ours(args) -> None:
         lvs_build.build()
     if world > 1:
         dist.barrier()
-    from code_rag_b200.collection import DeviceCollection
-    from code_rag_b200.sharded import ShardedSearcher, shard_bounds
+    from code_rag_b200.sharded import ShardedSearcher
 
     dev = torch.device("cuda", local_rank)
-    lo, hi = shard_bounds(args.rows, world, align=CHUNK_ROWS if args.rows % (CHUNK_ROWS * world) == 0 else 1)[rank]
-    n_local = hi - lo
-    shard = DeviceCollection(f"bench_r{rank}", args.dim, storage=args.storage, metric="cosine", n_filter_cols=0,
-                             capacity=n_local, row_base=lo, device=local_rank)
-    if args.stage_kb:
-        shard.set_option("stage_kb", args.stage_kb)
-    if args.stages:
-        shard.set_option("stages", args.stages)
-    # synthetic corpus: unit-norm gaussian rows rounded to bf16, generated on the GPU chunk by chunk (seeded per
-    # global chunk so the corpus does not depend on the number of shards)
-    t_gen = time.perf_counter()
-    row = lo
-    while row < hi:
-        n = min(CHUNK_ROWS - (row % CHUNK_ROWS), hi - row)
-        g = torch.Generator(device=dev)
-        g.manual_seed(3456 * 1_000_003 + row // CHUNK_ROWS)
-        full = torch.randn((CHUNK_ROWS, args.dim), generator=g, device=dev, dtype=torch.float32)
-        x = full[row % CHUNK_ROWS: row % CHUNK_ROWS + n]
-        x = x / x.norm(dim=1, keepdim=True)
-        xb = x.to(torch.bfloat16).contiguous() if args.storage == "bf16" else x.contiguous()
-        torch.cuda.synchronize()
-        shard.upsert_device(xb.data_ptr(), "bf16" if args.storage == "bf16" else "f32", n, row)
-        row += n
-        del full, x, xb
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t_gen
-    searcher = ShardedSearcher(shard)
-
-    Q, K, W, k = args.queries, args.steps, args.warmup, args.k
-    W = max(W, 3)
-    tensor_path = Q >= (3 if args.storage == "bf16" else 5)       # K2 (tcgen05) takes batches from this size on (lvs_api.cu)
-    qs = make_queries((K + W) * Q, args.dim, seed=11).reshape(K + W, Q, args.dim)
-    dq_all = torch.from_numpy(qs).to(dev)          # resident queries for the `value` leg
+    peaks = {}
+    pk_file = ROOT / "MEASURED_PEAKS.json"
+    if pk_file.exists():
+        peaks = json.loads(pk_file.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops", 1590.0)) * (1.0 if args.storage == "bf16" else 0.5)
+    tc_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
     row_bytes = args.dim * (2 if args.storage == "bf16" else 4)
-    algo_bytes = n_local * row_bytes
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- roofline leg: per-launch kernel time by CUDA events around every scan launch ----------------
-    # (timing on serialises consecutive searches, so this is the kernel ALONE: query prep + scan + exact rescoring, and at
-    #  N > 1 the exchange wait + merge, all one launch; the value leg below runs with it off)
-    NSLOT = searcher.n_slots
-    stream = searcher.stream
-    KR = min(K, 30)
-    shard.set_option("timing", 1)
-    torch.cuda.synchronize()
-    for i in range(W):
-        searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
-    barrier()
-    for i in range(W, W + KR):
-        searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
-    barrier()
-    ms_ring, bytes_ring = shard.scan_times(KR)
-    scan_ms = [float(v) for v in ms_ring]
-    shard.set_option("timing", 0)
+    def allmax(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
 
-    # ---------------- value: device-resident queries, searches enqueued back to back ----------------
-    # (each search is still one full pass over the corpus; results stay in HBM, flags are checked after the loop; consecutive
-    #  searches overlap by programmatic dependent launch: the next one streams while the last CTAs of this one rescore / exchange)
-    for i in range(W):
-        searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    flag_bufs = {}
-    e0.record(stream)
-    for i in range(W, W + K):
-        out = searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
-        flag_bufs[id(out[4])] = out[4]
-        launches += shard.last_timing()["launches"]       # kernels the library launched for this search (1 on the scan path)
-    e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    n_flagged = int(sum(int((f != 0).sum().item()) for f in flag_bufs.values()))
-    launches += searcher.merge_launches if world > 1 else 0
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---------------- sync: one search at a time, the host waits for each result (latency-bound) ----------------
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(W, W + K):
-        searcher.search_device(dq_all[i], k)
-    barrier()
-    sync_ms = (time.perf_counter() - t0) * 1e3
-
-    # ---------------- e2e: host buffers through the public API, every step H2D(query) + D2H(result) ----------------
-    # N=1: the C ABI's pipelined pair lvs_search_submit / lvs_search_wait (host pointers in, host pointers out);
-    # N>1: ShardedSearcher.submit / wait (adds the all-gather + merge).  Two searches are kept in flight, so the copies
-    # and the host work of step i+1 overlap the scan of step i.
-    DEPTH = 2
-
-    def e2e_submit(qh):
-        return searcher.submit(qh, k) if world > 1 else shard.search_submit(qh, k)
-
-    def e2e_wait(h):
-        return searcher.wait(h) if world > 1 else shard.search_wait(h)
-
-    for i in range(W):
-        e2e_wait(e2e_submit(qs[i]))
-    barrier()
-    t0 = time.perf_counter()
-    inflight = []
-    last = None
-    for i in range(W, W + K):
-        inflight.append(e2e_submit(qs[i]))
-        if len(inflight) >= DEPTH:
-            last = e2e_wait(inflight.pop(0))
-    while inflight:
-        last = e2e_wait(inflight.pop(0))
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    # depth 1 (strict request/response latency)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(W, W + K):
-        last = e2e_wait(e2e_submit(qs[i]))
-    barrier()
-    e2e1_ms = (time.perf_counter() - t0) * 1e3
-
-    t_dev = torch.tensor([dev_ms, e2e_ms, statistics.mean(scan_ms), sync_ms, float(n_flagged)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, scan_mean, sync_ms, n_flagged = (float(v) for v in t_dev.cpu())
-
-    if rank == 0:
-        peaks = {}
-        pk_file = ROOT / "MEASURED_PEAKS.json"
-        if pk_file.exists():
-            peaks = json.loads(pk_file.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = algo_bytes / (scan_mean * 1e-3) / 1e9
-        traffic = None
-        tf = ROOT / "profiles" / "scan_traffic.json"
-        if tf.exists() and Q == 1:
-            try:   # ncu capture of this kernel on the 10M-row shard; other shard sizes scale with the rows scanned
-                tj = json.loads(tf.read_text())
-                traffic = int(tj["dram_bytes_per_launch"] * (algo_bytes / tj["algorithmic_bytes_per_launch"]))
-            except Exception:
-                traffic = None
-        gf = ROOT / "profiles" / "gemm_traffic.json"
-        if tensor_path and gf.exists():
-            try:   # ncu capture of the tensor-core kernel on a 15.36 GB shard; other shard sizes scale with the rows read
-                gj = json.loads(gf.read_text())
-                key = ("pair_q256_bf16" if Q > 128 else "single_q128_bf16") if args.storage == "bf16" else "single_q128_tf32"
-                traffic = int(gj["dram_bytes_per_launch"][key] * (algo_bytes / gj["algorithmic_bytes_per_launch"]))
-            except Exception:
-                traffic = None
-        roof = {"bound": "hbm", "kernel": "gemm_topk_kernel" if tensor_path else "scan_topk_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
-                "kernel_ms": scan_mean,
+    def legs(shard, searcher, n_local, Q, k, K, W, seed, with_sync=True):
+        """The measurements of one workload (Q queries per step, top-k) on the resident shard.  Returns a dict of max-over-ranks
+        numbers; `sampler` clocks are taken during the value leg."""
+        tensor_path = Q >= ((2 if n_local >= 2_000_000 else 3) if args.storage == "bf16" else 5)   # lvs_api.cu gemm_eligible
+        qs = make_queries((K + W) * Q, args.dim, seed=seed).reshape(K + W, Q, args.dim)
+        dq_all = torch.from_numpy(qs).to(dev)          # resident queries for the `value` leg
+        NSLOT, stream = searcher.n_slots, searcher.stream
+        # ---- roofline leg: per-launch kernel time by CUDA events around every scan / tensor-core launch (timing on serialises
+        #      consecutive searches: this is the kernel ALONE - on the scan path one launch that prepares the query, scans, rescores
+        #      and, at N > 1, exchanges and merges)
+        KR = min(K, 30)
+        shard.set_option("timing", 1)
+        torch.cuda.synchronize()
+        for i in range(W):
+            searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+        barrier()
+        for i in range(W, W + KR):
+            searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+        barrier()
+        kernel_ms = float(np.mean(shard.scan_times(KR)[0]))
+        shard.set_option("timing", 0)
+        # ---- value: device-resident queries, K searches enqueued back to back (each one is a full pass over the corpus; results
+        #      stay in HBM; consecutive searches overlap by programmatic dependent launch)
+        for i in range(W):
+            searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        flag_bufs = {}
+        e0.record(stream)
+        for i in range(W, W + K):
+            out = searcher.search_device_async(dq_all[i], k, slot=i % NSLOT)
+            flag_bufs[id(out[4])] = out[4]
+            launches += shard.last_timing()["launches"]       # kernels the library launched for this search
+        e1.record(stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        n_flagged = int(sum(int((f != 0).sum().item()) for f in flag_bufs.values()))
+        launches += searcher.merge_launches if world > 1 else 0
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- sync: one search at a time, the host waits for each result (latency-bound)
+        sync_ms = 0.0
+        if with_sync:
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(W, W + K):
+                searcher.search_device(dq_all[i], k)
+            barrier()
+            sync_ms = (time.perf_counter() - t0) * 1e3
+        # ---- e2e: host buffers through the public API, every step H2D(query) + D2H(result).  N=1: the C ABI's pipelined pair
+        #      lvs_search_submit / lvs_search_wait (host pointers in, host pointers out); N>1: ShardedSearcher.submit / wait (the same
+        #      plus the exchange).  Two searches in flight, so the host work of step i+1 overlaps the scan of step i.
+        DEPTH = 2
+        submit = (lambda qh: searcher.submit(qh, k)) if world > 1 else (lambda qh: shard.search_submit(qh, k))
+        wait = searcher.wait if world > 1 else shard.search_wait
+        for i in range(W):
+            wait(submit(qs[i]))
+        barrier()
+        t0 = time.perf_counter()
+        inflight = []
+        for i in range(W, W + K):
+            inflight.append(submit(qs[i]))
+            if len(inflight) >= DEPTH:
+                wait(inflight.pop(0))
+        while inflight:
+            wait(inflight.pop(0))
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(W, W + K):                       # depth 1 (strict request / response)
+            wait(submit(qs[i]))
+        barrier()
+        e2e1_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms, e2e_ms, e2e1_ms, kernel_ms, sync_ms, n_flagged = allmax(dev_ms, e2e_ms, e2e1_ms, kernel_ms, sync_ms, float(n_flagged))
+        algo_bytes = n_local * row_bytes
+        gbs = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "gemm_topk_kernel" if tensor_path else "scan_topk_kernel (query prep + scan + exact rescoring" +
+                                                                                 (" + exchange + merge)" if world > 1 else ")"),
+                "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+        tfile = ROOT / "profiles" / ("gemm_traffic.json" if tensor_path else "scan_traffic.json")
+        if tfile.exists():
+            try:   # ncu --set full capture of this kernel on a 15.36 GB shard; other shard sizes scale with the rows read
+                tj = json.loads(tfile.read_text())
+                per = tj["dram_bytes_per_launch"]
+                if tensor_path:
+                    per = per[("pair_q256_bf16" if Q > 128 else "single_q128_bf16") if args.storage == "bf16" else "single_q128_tf32"]
+                roof["traffic"] = int(per * (algo_bytes / tj["algorithmic_bytes_per_launch"]))
+                roof["traffic_source"] = f"ncu capture in profiles/{tfile.name}, scaled by rows"
+            except Exception:  # noqa: BLE001
+                pass
         if Q > 128:     # above the ridge (2 Q flop per corpus byte): the tensor pipe bounds the kernel
-            tpeak = float(peaks.get("bf16_tflops", 1649.5)) * (1.0 if args.storage == "bf16" else 0.5)
-            tfl = 2.0 * min(Q, 256) * n_local * args.dim / (scan_mean * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_topk_kernel", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
-                    "traffic": traffic, "algorithmic_flops_per_launch": 2.0 * min(Q, 256) * n_local * args.dim, "kernel_ms": scan_mean,
-                    "hbm_gbs_over_algorithmic_bytes": achieved,
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops burst" if peaks else "fallback 1649.5 TFLOP/s") +
-                                   ("" if args.storage == "bf16" else " x 0.5 (tf32)")}
-        batched = None
-        if world == 1 and Q == 1 and args.storage == "bf16" and not args.no_batched:
-            # configs[2] (C3) beside the headline: 256 queries, top-100, tcgen05 path, host buffers through lvs_search
-            qb = make_queries(3 * 256, args.dim, seed=12).reshape(3, 256, args.dim)
-            shard.set_option("timing", 1)
-            walls, gms = [], []
-            for r_ in range(3):
-                t0 = time.perf_counter()
-                rb_ = shard.search(qb[r_], 100)
-                walls.append((time.perf_counter() - t0) * 1e3)
-                gms.append(shard.last_timing()["scan_ms"])
-            w_, g_ = min(walls[1:]), min(gms[1:])
-            tfl = 2.0 * 256 * n_local * args.dim / (g_ * 1e-3) / 1e12
-            batched = {"workload": f"C3: 256 queries x top-100, {args.rows}x{args.dim} bf16, one lvs_search call (host buffers)",
-                       "ms_per_batch": w_, "qps": 256e3 / w_, "gemm_topk_kernel_ms": g_, "tflops": tfl,
-                       "frac_of_bf16_burst_peak": tfl / float(peaks.get("bf16_tflops", 1649.5)),
-                       "frac_of_bf16_sustained_peak": tfl / float(peaks.get("bf16_tflops_sustained", 1361.6)),
-                       "flagged": int(rb_.flags.sum())}
+            flops = 2.0 * min(Q, 256) * n_local * args.dim
+            tfl = flops / (kernel_ms * 1e-3) / 1e12
+            roof.update({"bound": "tensor", "achieved": tfl, "peak": tc_peak, "unit": "TFLOP/s", "frac": tfl / tc_peak,
+                         "frac_of_sustained_peak": tfl / tc_sustained, "algorithmic_flops_per_launch": flops,
+                         "hbm_gbs_over_algorithmic_bytes": gbs,
+                         "peak_source": ("MEASURED_PEAKS.json bf16_tflops burst" if peaks else "fallback 1590 TFLOP/s") +
+                                        ("" if args.storage == "bf16" else " x 0.5 (tf32)")})
+        return {"value": K * Q / (dev_ms * 1e-3), "ms_per_step": dev_ms / K, "kernel_ms": kernel_ms, "roofline": roof,
+                "sync_qps": K * Q / (sync_ms * 1e-3) if sync_ms else None, "sync_ms_per_step": sync_ms / K if sync_ms else None,
+                "e2e": {"value": K * Q / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Q * args.dim * 8,
+                        "d2h_bytes_per_step": Q * k * 24 + Q * 8, "ms_per_step": e2e_ms / K, "in_flight": DEPTH,
+                        "api": "lvs_search_submit/lvs_search_wait (C ABI, host buffers)" if world == 1 else "ShardedSearcher.submit/wait (host buffers)",
+                        "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K},
+                "unproven_queries": int(n_flagged), "gpu_launches": launches, "clocks": clocks, "steps": K, "warmup": W,
+                "queries_per_step": Q, "k": k}
+
+    # ========================= the metric workload: 10M x 768 bf16, Q queries per step, top-k =========================
+    shard, n_local, t_gen = build_shard(args, torch, dev, rank, world, args.rows, f"bench_r{rank}")
+    searcher = ShardedSearcher(shard)
+    Q, K, W, k = args.queries, args.steps, max(args.warmup, 3), args.k
+    main_leg = legs(shard, searcher, n_local, Q, k, K, W, seed=11)
+
+    # configs[2] (C3) beside the headline at every N: 256 queries x top-100 on the tensor-core path, same corpus
+    batched = None
+    if Q == 1 and args.storage == "bf16" and not args.no_batched:
+        b = legs(shard, searcher, n_local, 256, 100, 6, 3, seed=12, with_sync=False)
+        batched = {"workload": f"C3: 256 queries x top-100 per step, {args.rows}x{args.dim} bf16 over {world} GPU(s)",
+                   "qps": b["value"], "ms_per_batch": b["ms_per_step"], "gemm_topk_kernel_ms": b["kernel_ms"], "roofline": b["roofline"],
+                   "e2e": b["e2e"], "flagged": b["unproven_queries"], "gpu_launches": b["gpu_launches"], "steps": b["steps"]}
+
+    # ---------------- e2e_adapter: the call lattice makes - await store.search(collection=, query_vector=list, limit=10) ----------------
+    # (reference query/vector_search.py:60-116 -> QdrantManager.search).  The store is put in front of the SAME resident shard(s);
+    # ids and payloads are synthetic and lazy (see _LazyIds).  N=1: B200VectorStore; N>1: ShardedB200VectorStore on rank 0, the other
+    # ranks serve their shard (commands through the shared-memory mailbox).
+    adapter = None
+    if Q == 1 and not args.no_adapter:
+        adapter = adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, k)
+        shard = searcher = None           # at N > 1 the plane's shutdown has closed them
+    else:
+        searcher.close()
+        shard.close()
+        shard = searcher = None
+
+    # ---------------- configs[4] (C5): 100M x 768 bf16 row-sharded over the N GPUs (N >= 2: 153.6 GB do not fit one) ----------------
+    c5 = None
+    if world > 1 and Q == 1 and args.storage == "bf16" and not args.no_c5 and args.rows == 10_000_000:
+        torch.cuda.empty_cache()
+        sh5, n5, t5 = build_shard(args, torch, dev, rank, world, 100_000_000, f"c5_r{rank}")
+        se5 = ShardedSearcher(sh5)
+        q1 = legs(sh5, se5, n5, 1, 10, 12, 3, seed=13, with_sync=False)
+        q256 = legs(sh5, se5, n5, 256, 10, 3, 3, seed=14, with_sync=False)
+        c5 = {"workload": f"C5: 100000000x{args.dim} bf16 row-sharded over {world} GPUs, top-10", "rows_per_gpu": n5, "corpus_gen_s": round(t5, 1),
+              "q1": {kk: q1[kk] for kk in ("value", "ms_per_step", "kernel_ms", "roofline", "e2e", "unproven_queries", "steps")},
+              "q256": {kk: q256[kk] for kk in ("value", "ms_per_step", "kernel_ms", "roofline", "e2e", "unproven_queries", "steps")}}
+        se5.close()
+        sh5.close()
+
+    if rank == 0:
+        m = main_leg
         line = {
-            "metric": METRIC, "value": K * Q / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.storage == "f32" else "bf16->f32 scan, f64 rescoring", "data": "synthetic",
             "config": {"workload": f"exact top-{k} cosine, {args.rows}x{args.dim} {args.storage} corpus, {Q} query/step, "
                                    f"row-sharded over {world} GPU(s)",
                        "rows": args.rows, "dim": args.dim, "k": k, "queries_per_step": Q, "storage": args.storage,
                        "rows_per_gpu": n_local, "l2": "inputs_exceed_l2", "corpus_gen_s": round(t_gen, 1),
-                       "parallelism": f"row-shard x{world} + top-k exchange ({searcher.exchange_mode}) + merge",
-                       "value_mode": "K searches enqueued back to back on one stream (device-resident queries/results)",
-                       "sync_qps": K * Q / (sync_ms * 1e-3), "sync_ms_per_step": sync_ms / K,
-                       "unproven_queries": int(n_flagged)},
-            "e2e": {"value": K * Q / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Q * args.dim * 8,
-                    "d2h_bytes_per_step": Q * k * 24 + Q * 8, "ms_per_step": e2e_ms / K, "in_flight": DEPTH,
-                    "api": "lvs_search_submit/lvs_search_wait (C ABI, host buffers)" if world == 1 else "ShardedSearcher.submit/wait",
-                    "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K},
-            "gpu_launches": launches,
-            "roofline": roof,
-            "clocks": clocks,
+                       "parallelism": f"row-shard x{world}; per search ONE kernel per GPU: scan + exact rescoring" +
+                                      (" + peer-memory exchange + merge" if world > 1 else ""),
+                       "value_mode": "K searches enqueued back to back on one stream (device-resident queries/results), "
+                                     "consecutive searches overlapped by programmatic dependent launch",
+                       "sync_qps": m["sync_qps"], "sync_ms_per_step": m["sync_ms_per_step"],
+                       "unproven_queries": m["unproven_queries"]},
+            "e2e": m["e2e"],
+            "gpu_launches": m["gpu_launches"],
+            "roofline": m["roofline"],
+            "clocks": m["clocks"],
         }
         if batched is not None:
             line["batched"] = batched
+        if adapter is not None:
+            line["e2e_adapter"] = adapter
+        if c5 is not None:
+            line["c5"] = c5
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_qps(args, steps=8, warmup=2)
-            line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample", "best_effort_cpu")}
+            line["cpu_baseline"] = {kk: cb[kk] for kk in CPU_KEYS if kk in cb}
         print(json.dumps(line), flush=True)
-    searcher.close()
-    shard.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, k):
+    """QPS of `await store.search(collection="code_chunks", query_vector=<list of floats>, limit=k)` on the resident corpus."""
+    import asyncio
+
+    from code_rag_b200.client import B200VectorStore, CollectionName, _HostCollection
+    CODE = CollectionName.CODE_CHUNKS.value
+    qs = make_queries(K + W, args.dim, seed=15)
+    qlists = [q.tolist() for q in qs]                    # what an embedding provider hands to lattice: list[float]
+
+    async def timed(store):
+        for i in range(W):
+            await store.search(collection=CODE, query_vector=qlists[i], limit=k)
+        t0 = time.perf_counter()
+        for i in range(W, W + K):
+            hits = await store.search(collection=CODE, query_vector=qlists[i], limit=k)
+        dt = time.perf_counter() - t0
+        assert len(hits) == k and all("payload" in h and "score" in h and "id" in h for h in hits)
+        # concurrent awaits, as QueryEngine does with asyncio.gather (query/engine.py:142-146): calls serialise per collection
+        t0 = time.perf_counter()
+        await asyncio.gather(*[store.search(collection=CODE, query_vector=qlists[i], limit=k) for i in range(W, W + K)])
+        dtc = time.perf_counter() - t0
+        return dt, dtc
+
+    def host_half(dev_factory, n_rows):
+        hc = _HostCollection(CODE, args.dim, args.storage, ["file_path", "entity_type", "language", "content_hash", "project_name"], 0,
+                             dev_factory=dev_factory)
+        hc.ids = _LazyIds(n_rows); hc.id_to_row = _LazyIds(n_rows); hc.payloads = _LazyPayloads(n_rows)
+        return hc
+
+    if world == 1:
+        store = B200VectorStore(dimensions=args.dim, storage=args.storage)
+        asyncio.run(store.connect())
+        store._collections[CODE] = host_half(lambda *a, **kw: shard, n_local)
+        dt, dtc = asyncio.run(timed(store))
+        searcher.close()
+        asyncio.run(store.close())                       # closes the shard
+        api = "B200VectorStore.search (asyncio, list[float] in, list[dict] out)"
+    else:
+        from code_rag_b200 import sharded_store as SS
+        plane = SS.ShardPlane.start()                    # collective; re-uses the NCCL group, opens the gloo control group + mailbox
+        plane.shards[CODE], plane.searchers[CODE] = shard, searcher
+        dt = dtc = 0.0
+        if rank != 0:
+            plane.serve()                                # until rank 0 shuts the plane down
+        else:
+            store = SS.ShardedB200VectorStore(dimensions=args.dim, storage=args.storage, plane=plane)
+            asyncio.run(store.connect())
+            coll = SS._ShardedHostCollection.__new__(SS._ShardedHostCollection)
+            coll.plane, coll.name, coll.dim, coll.storage = plane, CODE, args.dim, args.storage
+            coll.columns, coll.dicts = ["file_path", "entity_type", "language", "content_hash", "project_name"], [dict() for _ in range(5)]
+            coll.tie_counts, coll.dup_keys = {}, {}
+            import threading
+            coll.lock = threading.Lock()
+            coll.shards = []
+            for s_ in range(world):
+                hs = SS._HostShard(coll, s_)
+                hs.ids = _LazyIds(n_local); hs.id_to_row = _LazyIds(n_local); hs.payloads = _LazyPayloads(n_local)
+                coll.shards.append(hs)
+            store._collections[CODE] = coll
+            dt, dtc = asyncio.run(timed(store))
+            store._collections.clear()
+            plane.shutdown()                             # the workers leave serve(); every rank closes its shard
+        api = "ShardedB200VectorStore.search on rank 0 (asyncio; search commands through the shared-memory mailbox)"
+    if rank != 0:
+        return None
+    return {"value": K / dt, "unit": UNIT, "ms_per_call": dt / K * 1e3, "api": api, "calls": K,
+            "gathered_qps": K / dtc, "metadata": "synthetic lazy ids / payloads over the resident shard(s)",
+            "h2d_bytes_per_step": args.dim * 8, "d2h_bytes_per_step": k * 24 + 8}
 
 
 def main():

@@ -53,6 +53,137 @@ def least_full(live: list[int]) -> int:
     return min(range(len(live)), key=live.__getitem__)
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# the search fast path of the control plane: a shared-memory mailbox
+# ------------------------------------------------------------------------------------------------------------------
+class _Mailbox:
+    """Fixed-layout command block in POSIX shared memory (all ranks are processes of ONE box).
+
+    A gloo scatter + gather of pickled objects costs hundreds of microseconds per command - more than a whole single-query step
+    on 8 GPUs.  Searches therefore do not travel through gloo: the controller writes (collection, Q, k, filter codes, query
+    vectors) into this block and bumps a sequence word; the workers poll that word (a short spin, then micro-sleeps) and run the
+    search; each worker answers in its own status slot.  Everything else (creates, writes, deletes, snapshots) is announced here
+    with op GLOO and then takes the general scatter / gather path, so there is still exactly one command stream and the
+    controller's order is every rank's order.  x86 total store order makes "payload first, sequence word last" sufficient.
+    """
+
+    OP_GLOO, OP_SEARCH = 1, 2
+    HDR = 256                      # seq u64 | op u32 | Q u32 | k u32 | dim u32 | has_want u32 | want[8] u32 | name_len u32 | name[64]
+    STATUS = 256                   # per rank: seq u64 | ok u32 | msg_len u32 | msg[240]
+    QUERY_BYTES = 4 << 20
+
+    def __init__(self, rank: int, world: int, ctl_group):
+        import torch.distributed as dist
+        from multiprocessing import resource_tracker, shared_memory
+        self.rank, self.world = rank, world
+        size = self.HDR + world * self.STATUS + self.QUERY_BYTES
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=size)
+            self.shm.buf[:self.HDR + world * self.STATUS] = bytes(self.HDR + world * self.STATUS)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=ctl_group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:        # the creator owns the segment: keep this process's resource tracker from unlinking it at exit
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
+        buf = self.shm.buf
+        self.seq = np.ndarray(1, dtype=np.uint64, buffer=buf, offset=0)
+        self.u32 = np.ndarray(14, dtype=np.uint32, buffer=buf, offset=8)          # op Q k dim has_want want[8] name_len
+        self.name = np.ndarray(64, dtype=np.uint8, buffer=buf, offset=64)
+        self.status_seq = [np.ndarray(1, dtype=np.uint64, buffer=buf, offset=self.HDR + r * self.STATUS) for r in range(world)]
+        self.status_u32 = [np.ndarray(2, dtype=np.uint32, buffer=buf, offset=self.HDR + r * self.STATUS + 8) for r in range(world)]
+        self.status_msg = [np.ndarray(240, dtype=np.uint8, buffer=buf, offset=self.HDR + r * self.STATUS + 16) for r in range(world)]
+        self.qoff = self.HDR + world * self.STATUS
+        self.last = 0
+
+    def fits(self, Q: int, dim: int, name: str) -> bool:
+        return Q * dim * 8 <= self.QUERY_BYTES and len(name.encode()) <= 64
+
+    # ---- controller ----------------------------------------------------------------------------------------------
+    def post(self, op: int, name: str = "", queries: np.ndarray | None = None, k: int = 0, want=None) -> int:
+        u = self.u32
+        u[0] = op
+        if op == self.OP_SEARCH:
+            Q, dim = queries.shape
+            u[1], u[2], u[3] = Q, k, dim
+            u[4] = 0 if want is None else 1
+            if want is not None:
+                u[5:13] = np.asarray(want, dtype=np.uint32)
+            nb = name.encode()
+            u[13] = len(nb)
+            self.name[:len(nb)] = np.frombuffer(nb, dtype=np.uint8)
+            np.ndarray((Q, dim), dtype=np.float64, buffer=self.shm.buf, offset=self.qoff)[...] = queries
+        self.last += 1
+        self.seq[0] = self.last                       # published last
+        return self.last
+
+    def collect(self, seq: int, timeout_s: float = 60.0) -> list[tuple[bool, str]]:
+        """Replies of ranks 1..N-1 to command `seq`."""
+        import time
+        out = []
+        t0 = time.perf_counter()
+        for r in range(1, self.world):
+            spins = 0
+            while int(self.status_seq[r][0]) != seq:
+                spins += 1
+                if spins > 2000:
+                    if time.perf_counter() - t0 > timeout_s:
+                        out.append((False, f"no reply within {timeout_s:.0f} s"))
+                        break
+                    time.sleep(20e-6)
+            else:
+                ok, n = int(self.status_u32[r][0]) != 0, int(self.status_u32[r][1])
+                out.append((ok, bytes(self.status_msg[r][:n]).decode(errors="replace")))
+        return out
+
+    # ---- workers -------------------------------------------------------------------------------------------------
+    def wait_command(self, is_closed) -> tuple[int, int]:
+        """Blocks until the controller posts the next command; returns (seq, op).  Spins while commands keep coming (a search
+        step on 8 GPUs is ~0.3 ms), backs off to micro-sleeps when the plane is idle."""
+        import time
+        spins = 0
+        while True:
+            seq = int(self.seq[0])
+            if seq != self.last:
+                self.last = seq
+                return seq, int(self.u32[0])
+            spins += 1
+            if spins > 20000:
+                if is_closed():
+                    return -1, 0
+                time.sleep(50e-6 if spins < 200000 else 500e-6)
+
+    def read_search(self):
+        u = self.u32
+        Q, k, dim = int(u[1]), int(u[2]), int(u[3])
+        want = np.array(u[5:13], dtype=np.uint32) if int(u[4]) else None
+        name = bytes(self.name[:int(u[13])]).decode()
+        q = np.ndarray((Q, dim), dtype=np.float64, buffer=self.shm.buf, offset=self.qoff).copy()
+        return name, q, k, want
+
+    def reply(self, seq: int, ok: bool, msg: str = "") -> None:
+        mb = msg.encode()[:240]
+        self.status_u32[self.rank][0] = 1 if ok else 0
+        self.status_u32[self.rank][1] = len(mb)
+        if mb:
+            self.status_msg[self.rank][:len(mb)] = np.frombuffer(mb, dtype=np.uint8)
+        self.status_seq[self.rank][0] = seq           # published last
+
+    def close(self) -> None:
+        for a in ("seq", "u32", "name", "status_seq", "status_u32", "status_msg"):
+            setattr(self, a, None)
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # the plane: process group plumbing + what every rank (controller included) does with a command
 # ------------------------------------------------------------------------------------------------------------------
@@ -68,6 +199,9 @@ class ShardPlane:
         self.lock = threading.RLock()             # controller: one command at a time
         self.pending: list[list[tuple]] = [[] for _ in range(world)]     # controller: queued writes per rank
         self.closed = False
+        self.mailbox: _Mailbox | None = None
+        if world > 1 and os.environ.get("LATTICE_B200_MAILBOX", "1") != "0":
+            self.mailbox = _Mailbox(rank, world, ctl_group)              # collective
 
     @classmethod
     def start(cls, device_factory: Callable | None = None, searcher_factory: Callable | None = None,
@@ -116,9 +250,17 @@ class ShardPlane:
                 # the search ends in a data-plane collective that every rank must enter: writes still queued go first, in a
                 # command of their own, so that a rank failing one of them is reported instead of missing the exchange
                 self.call("noop", None)
-            writes, self.pending = self.pending, [[] for _ in range(self.world)]
-            mine = self._scatter([(op, name, common, writes[r]) for r in range(self.world)])
-            replies = self._gather(self._execute(*mine))
+            mb = self.mailbox
+            if op == "search" and mb is not None and mb.fits(common[0].shape[0], common[0].shape[1], name):
+                # fast path: the command travels through shared memory, the replies through the workers' status slots
+                seq = mb.post(mb.OP_SEARCH, name, common[0], int(common[1]), common[2])
+                replies = [self._execute(op, name, common, [])] + mb.collect(seq)
+            else:
+                if mb is not None:
+                    mb.post(mb.OP_GLOO)                  # the workers leave the mailbox poll and enter the scatter
+                writes, self.pending = self.pending, [[] for _ in range(self.world)]
+                mine = self._scatter([(op, name, common, writes[r]) for r in range(self.world)])
+                replies = self._gather(self._execute(*mine))
         bad = [(r, rep[1]) for r, rep in enumerate(replies) if not rep[0]]
         if bad:
             raise RuntimeError("; ".join(f"rank {r}: {msg}" for r, msg in bad))
@@ -137,14 +279,29 @@ class ShardPlane:
         """Ranks 1..N-1: execute the controller's commands until it shuts the plane down."""
         if self.rank == 0:
             raise RuntimeError("rank 0 is the controller")
+        mb = self.mailbox
         while not self.closed:
+            if mb is not None:
+                seq, op = mb.wait_command(lambda: self.closed)
+                if seq < 0:
+                    break
+                if op == mb.OP_SEARCH:
+                    name, q, k, want = mb.read_search()
+                    ok, res = self._execute("search", name, (q, k, want), [])
+                    mb.reply(seq, ok, "" if ok else str(res))
+                    continue
             cmd = self._scatter(None)
             self._gather(self._execute(*cmd))
+        if mb is not None:
+            mb.close()
 
     def shutdown(self) -> None:
         """Controller: release the workers (collective with their ``serve()`` loops)."""
         if self.rank == 0 and not self.closed:
             self.call("shutdown", None)
+            if self.mailbox is not None:
+                self.mailbox.close()
+                self.mailbox = None
 
     # ---- what a rank does with a command -------------------------------------------------------------------------
     def _execute(self, op: str, name: str | None, common, writes: list) -> tuple[bool, Any]:

@@ -559,3 +559,33 @@ def test_search_counter_crosses_2_pow_32(lib):
         _assert_same(res, 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
     assert dev.search_counter == jump + 8
     dev.close()
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_fetch_rows_returns_what_the_shard_holds(lib, storage):
+    """lvs_fetch_rows_f32 (what shard rebalancing reads back): fp32 shards hold float32(x / ||x||_64), bf16 shards
+    the bf16 rounding of x; rows are GLOBAL numbers of a shard whose row_base is beyond 2^32 (the multi-GPU adapter's layout); a row
+    written back from its fetched values answers searches exactly like the original."""
+    n, dim, base = 3_000, 200, 3 << 32
+    x, q = synth.unixcoder_like(n, dim, seed=55, n_queries=4)
+    dev = _dev("fetch", dim, storage=storage, row_base=base)
+    dev.upsert(x.astype(np.float64))
+    pick = np.array([0, 1, 17, 1500, n - 1], dtype=np.int64)
+    got = dev.fetch_rows(base + pick)
+    if storage == "f32":
+        x64 = x[pick].astype(np.float64)
+        exp = (x64 / np.linalg.norm(x64, axis=1, keepdims=True)).astype(np.float32)
+    else:
+        exp = synth.bf16_round(x[pick])
+    assert got.dtype == np.float32 and np.array_equal(got, exp)
+    with pytest.raises(Exception):
+        dev.fetch_rows(np.array([base + n], dtype=np.int64))          # past the end
+    with pytest.raises(Exception):
+        dev.fetch_rows(np.array([5], dtype=np.int64))                 # below the shard's row_base
+    # move: fetched values re-written into a second shard give the same hits (bf16: the same bits; fp32: re-normalised, <= 1 ulp)
+    other = _dev("fetch2", dim, storage=storage, row_base=base)
+    other.upsert(dev.fetch_rows(base + np.arange(n, dtype=np.int64)).astype(np.float64))
+    for i in range(len(q)):
+        a, b = dev.search(q[i].astype(np.float64), 10), other.search(q[i].astype(np.float64), 10)
+        assert np.array_equal(a.rows, b.rows) and np.abs(a.scores - b.scores).max() < 1e-6
+    dev.close(); other.close()
