@@ -52,6 +52,7 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_delete_where": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]),
+    "lvs_search_submit_sharded": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]),
     "lvs_search_wait": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device_at": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

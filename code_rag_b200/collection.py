@@ -314,6 +314,21 @@ class DeviceCollection:
                                             C.byref(t)), "lvs_search_submit")
         return (t.value, q.shape[0], int(k))
 
+    def search_submit_sharded(self, ex, queries: np.ndarray, k: int, want=None) -> tuple[int, int, int]:
+        """Pipelined SHARDED search (``lvs_search_submit_sharded``): every rank submits the same queries; ``search_wait`` returns the
+        merged lists and merged flags.  `ex` is the rank's ``lvs_exchange`` handle."""
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")
+        t = C.c_int()
+        N.check(self._lib.lvs_search_submit_sharded(self._handle(), ex, _ptr(q), N.DT_F64, q.shape[0], int(k), _ptr(self._want(want)),
+                                                    C.byref(t)), "lvs_search_submit_sharded")
+        return (t.value, q.shape[0], int(k))
+
     def search_wait(self, ticket: tuple[int, int, int]) -> SearchResult:
         t, Q, k = ticket
         scores = np.zeros((Q, k), dtype=np.float64)

@@ -2,6 +2,7 @@
 #include "../../include/lvs.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -129,6 +130,8 @@ struct lvs_collection {
     Scratch s_gkeys, s_gtops, s_gdrops, s_qb16, s_tickets, s_dbg, s_geps, s_xlocal;
     cudaStream_t last_stream = nullptr; bool last_stream_valid = false; cudaEvent_t order_ev = nullptr;
     uint32_t launch_seq = 0;          // fused scan launches so far (ScanParams::seq)
+    bool last_ready_armed = false;    // the last search_core call armed the host-polled completion word
+    uint32_t ready_seq = 0;
     uint32_t tile_base[2] = {0, 0};   // what the two tile counters (launch parity) stand at
     Scratch s_qstage;                 // host queries staged by CTA 0, one slot per launch parity
     int opt_dyn_tiles = 1;
@@ -155,6 +158,9 @@ struct lvs_collection {
         Scratch h;
         Scratch d;             // device twin of h for batches (staged == true)
         bool staged = false;
+        bool poll = false;     // completion is published by the kernel in the slot's `ready` word (no event)
+        uint32_t ready_val = 0;
+        bool sharded = false;
         size_t qbytes = 0;
         cudaEvent_t done = nullptr;
     } slots[kSubmitSlots];
@@ -791,6 +797,7 @@ static int launch_exchange(const ExchangeParams& p, cudaStream_t st) {
 struct LevelOut {
     double* scores; int64_t* rows; uint64_t* ties; uint32_t* counts; int32_t* flags;
     lvs_exchange* ex; int64_t* xout; int Q_total;
+    uint32_t* host_ready; uint32_t host_ready_val;   // armed only when the level is ONE launch (see search_core)
 };
 
 // Enqueue one level of the search for the query indices in `pending` (ascending): ONE fused kernel (query prep + scan + exact
@@ -870,6 +877,7 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_hos
         // CTAs per query for the rescoring: as many as it takes to give every candidate its own warp, at most 8 CTAs in all
         const uint32_t cq = std::max<uint32_t>(1u, std::min<uint32_t>(8u / (uint32_t)cnt, (kpw + nrw - 1) / nrw));
         sp.ticket = c->d_counter + 4; sp.n_helpers = (uint32_t)cnt * cq;
+        sp.host_ready = out.host_ready; sp.host_ready_val = out.host_ready_val;
         const bool dyn = !filter && grid == sm && c->opt_dyn_tiles;       // dynamic tile scheduling needs one CTA per SM (see the kernel)
         if (dyn) { sp.tile_counter = c->d_counter + 6 + (seq & 1u); sp.tile_base = c->tile_base[seq & 1u]; }
         sp.pdl = c->opt_pdl && !c->opt_timing ? 1u : 0u;
@@ -1104,7 +1112,8 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
                        double* d_scores, int64_t* d_rows, uint64_t* d_ties, uint32_t* d_counts, int32_t* h_flags,
                        int32_t* d_flags_out, bool async, cudaStream_t st, int64_t base_override = -1, int kpl_min = 0,
                        const std::vector<int>* only = nullptr, lvs_exchange* ex = nullptr, int64_t* xout = nullptr,
-                       bool q_in_host = false) {
+                       bool q_in_host = false, uint32_t* host_ready = nullptr, uint32_t host_ready_val = 0) {
+    c->last_ready_armed = false;
     if (Q <= 0) return LVS_OK;
     if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
     if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
@@ -1198,6 +1207,13 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
     LevelOut lo;
     lo.scores = d_scores; lo.rows = d_rows; lo.ties = d_ties; lo.counts = d_counts; lo.flags = d_flags;
     lo.ex = ex; lo.xout = xout; lo.Q_total = Q;
+    lo.host_ready = nullptr; lo.host_ready_val = 0;
+    // a search that is exactly ONE fused launch can publish its completion in host memory itself (no event between consecutive
+    // kernels of the stream, so they keep overlapping; the host polls a word instead of synchronising)
+    if (host_ready && async && kind == 1 && !c->opt_timing && (int)pending.size() == Q && Q <= max_qt_for_kpl(kpl)) {
+        lo.host_ready = host_ready; lo.host_ready_val = host_ready_val;
+        c->last_ready_armed = true;
+    }
     while (!pending.empty()) {
         rc = enqueue_level(c, d_queries, q_in_host, dtype, pending, k, kpl, filter, fcodes, fwant, nf, search_base, lo, st, &launches, first);
         if (rc != LVS_OK) return rc;
@@ -1278,8 +1294,10 @@ extern "C" int lvs_search_device_async(lvs_collection* c, const void* d_queries,
 // host memory, so a step is kernels only (no copy-engine hops between them).
 // Slot layout: [queries, padded to 256 B][scores | rows | ties (Q*k*8 each) | counts (Q*4) | flags (Q*4)]
 static size_t res_bytes(int Q, int k) { return (size_t)Q * k * 24 + (size_t)Q * 8; }
+static size_t ready_off(int Q, int k) { return (res_bytes(Q, k) + 15) & ~(size_t)15; }   // the slot's completion word sits behind the results
 
-static int submit_locked(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket) {
+static int submit_locked(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket,
+                         lvs_exchange* ex = nullptr) {
     int si = -1;
     for (int i = 0; i < kSubmitSlots; ++i) if (!c->slots[i].in_use) { si = i; break; }
     if (si < 0) return fail(LVS_ELIMIT, "%d searches already in flight: call lvs_search_wait first", kSubmitSlots);
@@ -1287,7 +1305,7 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
     const size_t qbytes = ((size_t)Q * c->dim * dt_size(dtype) + 255) & ~(size_t)255;
     const size_t rbytes = res_bytes(Q, k);
     int rc;
-    if ((rc = ensure_pinned(sl.h, qbytes + rbytes)) != LVS_OK) return rc;
+    if ((rc = ensure_pinned(sl.h, qbytes + ready_off(Q, k) + 16)) != LVS_OK) return rc;
     if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     void* dview = nullptr;
     CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
@@ -1302,6 +1320,10 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
     // no copy-engine hop on a latency-bound step).  A batch: one H2D copy of the queries and one D2H copy of the results around
     // device-resident work - hundreds of CTAs storing 24 Q k bytes over PCIe from inside the finalize kernel serialise.
     sl.staged = qraw + rbytes >= (size_t)64 * 1024;
+    sl.sharded = ex != nullptr;
+    sl.ready_val = ++c->ready_seq ? c->ready_seq : ++c->ready_seq;      // never 0
+    volatile uint32_t* h_ready = (volatile uint32_t*)((uint8_t*)sl.h.p + qbytes + ready_off(Q, k));
+    *h_ready = 0;
     uint8_t* qp = (uint8_t*)dview;
     if (sl.staged) {
         if ((rc = ensure_dev(sl.d, qbytes + rbytes)) != LVS_OK) return rc;
@@ -1309,17 +1331,42 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
         qp = (uint8_t*)sl.d.p;
     }
     uint8_t* rp = qp + qbytes;
+    // sharded: the merged lists of all ranks land in the same place, in the same layout ([3][Q][k] = scores | rows | ties)
     rc = search_core(c, qp, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
-                     (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st, -1, 0, nullptr, nullptr,
-                     nullptr, !sl.staged);
+                     (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st, -1, 0, nullptr, ex,
+                     ex ? (int64_t*)rp : nullptr, !sl.staged,
+                     sl.staged ? nullptr : (uint32_t*)((uint8_t*)dview + qbytes + ready_off(Q, k)), sl.ready_val);
     if (rc == LVS_OK && sl.staged) CU(cudaMemcpyAsync((uint8_t*)sl.h.p + qbytes, rp, rbytes, cudaMemcpyDeviceToHost, st));
+    sl.poll = rc == LVS_OK && c->last_ready_armed;
     if (rc != LVS_OK) return rc;
     sl.kpl = c->last_kpl;
     sl.kind = c->last_kind;
-    CU(cudaEventRecord(sl.done, st));
+    if (!sl.poll) CU(cudaEventRecord(sl.done, st));
     sl.in_use = true;
     *ticket = si;
     return LVS_OK;
+}
+
+// Blocks until the search in `sl` has finished: polls the completion word its kernel publishes in the slot's pinned memory, or
+// synchronises the slot's event (batches, multi-launch searches, timing mode).
+static int wait_slot(lvs_collection* c, lvs_collection::Slot& sl) {
+    if (!sl.poll) { CU(cudaEventSynchronize(sl.done)); return LVS_OK; }
+    volatile uint32_t* w = (volatile uint32_t*)((uint8_t*)sl.h.p + sl.qbytes + ready_off(sl.Q, sl.k));
+    for (uint64_t spins = 1;; ++spins) {
+        if (*w == sl.ready_val) { std::atomic_thread_fence(std::memory_order_acquire); return LVS_OK; }
+        if ((spins & 0x3FFF) == 0) {
+            // not there yet: make sure the stream is still alive (a faulted kernel never publishes)
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (*w == sl.ready_val) return LVS_OK;
+                return fail(LVS_ECUDA, "the search finished without publishing its completion word");
+            }
+            if (e != cudaErrorNotReady) return fail(LVS_ECUDA, "search failed: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
 }
 
 static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
@@ -1332,7 +1379,8 @@ static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int6
     std::vector<int> redo;
     // a K2 slot (bf16-rounded queries, coarse bound) always gets the exact-scan fallback for its flagged queries, whatever k is;
     // a K1 slot is repeated with a larger candidate set while one exists
-    for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && (sl.kind == 2 || sl.kpl < 8)) redo.push_back(i);
+    if (!sl.sharded)     // a sharded slot's flags are the merged ones: the caller repeats those queries on every rank (lvs_search_device_at)
+        for (int i = 0; i < Q; ++i) if ((hflags[i] & 1) && (sl.kind == 2 || sl.kpl < 8)) redo.push_back(i);
     if (!redo.empty()) {
         // rare: repeat the flagged queries (K1, larger candidate sets), as the same reference searches (same numbers)
         void* dview = nullptr;
@@ -1379,18 +1427,28 @@ extern "C" int lvs_search_submit(lvs_collection* c, const void* queries, int dty
     return submit_locked(c, queries, dtype, Q, k, want, ticket);
 }
 
+extern "C" int lvs_search_submit_sharded(lvs_collection* c, lvs_exchange* ex, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                                         int* ticket) {
+    bind_thread();
+    if (!ticket || !ex) return fail(LVS_EINVAL, "ticket / exchange is NULL");
+    int rc = check_search_args(c, queries, dtype, Q, k);
+    if (rc != LVS_OK) return rc;
+    if (Q < 1) return fail(LVS_EINVAL, "Q must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    return submit_locked(c, queries, dtype, Q, k, want, ticket, ex);
+}
+
 extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
                                uint32_t* out_counts, int32_t* out_flags) {
     bind_thread();
     if (!c) return fail(LVS_EINVAL, "collection is NULL");
     if (ticket < 0 || ticket >= kSubmitSlots) return fail(LVS_EINVAL, "bad ticket %d", ticket);
-    cudaEvent_t done;
     {
         std::lock_guard<std::mutex> lk(c->mu);
         if (!c->slots[ticket].in_use) return fail(LVS_EINVAL, "ticket %d is not in flight", ticket);
-        done = c->slots[ticket].done;
     }
-    CU(cudaEventSynchronize(done));   // outside the lock: other threads may submit meanwhile
+    int rcw = wait_slot(c, c->slots[ticket]);   // outside the lock: other threads may submit meanwhile (slots are stable storage)
+    if (rcw != LVS_OK) { std::lock_guard<std::mutex> lk(c->mu); c->slots[ticket].in_use = false; return rcw; }
     std::lock_guard<std::mutex> lk(c->mu);
     return finish_locked(c, ticket, out_scores, out_rows, out_ties, out_counts, out_flags);
 }
@@ -1404,7 +1462,7 @@ extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int
     std::lock_guard<std::mutex> lk(c->mu);
     int ticket = -1;
     if ((rc = submit_locked(c, queries, dtype, Q, k, want, &ticket)) != LVS_OK) return rc;
-    CU(cudaEventSynchronize(c->slots[ticket].done));
+    if ((rc = wait_slot(c, c->slots[ticket])) != LVS_OK) { c->slots[ticket].in_use = false; return rc; }
     rc = finish_locked(c, ticket, out_scores, out_rows, out_ties, out_counts, out_flags);
     if (rc == LVS_OK && c->opt_timing && c->first_scan_start) {
         c->last_ms[0] = 0.f;

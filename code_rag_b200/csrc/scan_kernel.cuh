@@ -76,6 +76,8 @@ struct ScanParams {
     void* q_stage;              //   them here (device) for everybody, then publishes *q_flag = seq; q_raw == q_stage
     uint32_t* q_flag;
     uint32_t q_bytes;           // n_queries * dim * sizeof(query element)
+    uint32_t* host_ready;       // optional word in mapped pinned host memory: set to host_ready_val (system-scope release) when every
+    uint32_t host_ready_val;    //   result of this launch has been stored - the host polls it instead of synchronising an event
     uint32_t* ticket;           // [2] arrival counters of this launch's CTAs, zero between launches
     uint32_t n_helpers;         // H = n_queries * C: the last H CTAs to finish run the finalize body (C CTAs per query)
     uint32_t pdl;               // 1: launched with programmatic stream serialisation (griddepcontrol.* are executed)
@@ -582,12 +584,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
         for (uint32_t qi = 0; qi < nq; ++qi)
             if (owned & (1u << qi)) exchange_merge_query(xp, (int)qi, xsm, &s_bcast[0], tid, NCT, timed_out, [] { named_bar_sync(1, NCT); });
     }
-    // the helper that leaves last re-arms the tickets for the next launch
+    // the helper that leaves last re-arms the tickets for the next launch, publishes the launch's completion on the device and,
+    // for host-polled searches, in host memory (every result store above is fenced at system scope before its CTA checks out)
+    if (p.host_ready != nullptr) __threadfence_system();
     named_bar_sync(1, NCT);
     if (tid == 0 && atomicAdd(p.ticket + 1, 1u) == H - 1) {
         p.ticket[0] = 0; p.ticket[1] = 0;
         __threadfence();
         st_release_gpu_u32(p.done_seq, p.seq);
+        if (p.host_ready != nullptr) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.host_ready), "r"(p.host_ready_val) : "memory");
+        }
     }
 }
 

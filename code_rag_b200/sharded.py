@@ -149,62 +149,55 @@ class ShardedSearcher:
                           out[2].data_ptr(), b["counts"].data_ptr(), stream, shard_stride=3 * n)
         self.merge_launches += 1
 
-    def _settle(self, b: dict, flags: np.ndarray, queries_of=None) -> np.ndarray:
-        """After a search has completed: raise if the exchange failed, and REPEAT the queries that some shard could not prove
-        exact (merged flags are identical on every rank, so every rank takes the same decision): each rank redoes them through
-        the synchronous path of the library - larger candidate sets, the exact scan instead of the tensor-core path, as the same
-        reference searches - and the lists are exchanged and merged again.  Returns the final flags."""
+    def _repeat_query(self, qvec: np.ndarray, search_no: int, k: int, want):
+        """Collective (every rank sees the same merged flags, so every rank gets here for the same queries): redo ONE query through
+        the synchronous path of the library - larger candidate sets, the exact scan instead of the tensor-core path, numbered as the
+        reference search it repeats - then exchange and merge the lists again.  Returns ([3, k] int64 merged block, count, flag)."""
         t = self.torch
+        lib = N.load()
+        rb = self._repeat_bufs(k, qvec.shape[-1])
+        rb["hq"].numpy()[0] = qvec
+        st = self.stream.cuda_stream
+        self.shard.search_device_at(int(search_no), rb["hq"].data_ptr(), "f64", 1, k, want, rb["local"][0].data_ptr(), rb["local"][1].data_ptr(),
+                                    rb["local"][2].data_ptr(), rb["counts"].data_ptr(), rb["hflags"], st)
+        if self.world == 1:
+            self.stream.synchronize()
+            return rb["local"][:, 0, :].cpu().numpy(), int(rb["counts"].item()), int(rb["hflags"][0])
+        rb["dflags"].copy_(t.from_numpy(rb["hflags"]), non_blocking=False)
+        if self.exchange_mode == "p2p":
+            N.check(lib.lvs_exchange_merge_device(self._exchange(1, k), C.c_void_p(rb["local"].data_ptr()), C.c_void_p(rb["dflags"].data_ptr()),
+                                                  1, k, C.c_void_p(rb["out"].data_ptr()), C.c_void_p(rb["counts"].data_ptr()),
+                                                  C.c_void_p(rb["dflags2"].data_ptr()), C.c_void_p(st)), "lvs_exchange_merge_device")
+        else:
+            with t.cuda.stream(self.stream):
+                allgather_packed(rb["local"], rb["gathered"], self.group)
+                self.dist.all_reduce(rb["dflags"], op=self.dist.ReduceOp.MAX, group=self.group)
+                rb["dflags2"].copy_(rb["dflags"])
+            base = rb["gathered"].data_ptr()
+            merge_topk_device(base, base + 8 * k, base + 16 * k, self.world, 1, k, rb["out"][0].data_ptr(), rb["out"][1].data_ptr(),
+                              rb["out"][2].data_ptr(), rb["counts"].data_ptr(), st, shard_stride=3 * k)
+        self.stream.synchronize()
+        return rb["out"][:, 0, :].cpu().numpy(), int(rb["counts"].item()), int(rb["dflags2"].item())
+
+    def _settle(self, queries: np.ndarray, base: int, k: int, want, flags: np.ndarray, store) -> np.ndarray:
+        """After a search has completed: raise if the exchange failed, and REPEAT the queries that some shard could not prove
+        exact.  `store(qi, block, count)` puts a repeated query's merged lists where the caller keeps its results."""
         if (flags & N.FLAG_EXCHANGE).any():
             raise NativeLibraryError("sharded search: a peer's result lists did not arrive (exchange timeout); a rank is down or stalled")
-        idx = np.nonzero(flags & N.FLAG_UNPROVEN)[0]
-        if idx.size == 0:
-            return flags
-        q_ptr, q_dtype, Q, k = b["q"]
-        esz = 8 if q_dtype == "f64" else 4
-        lib = N.load()
-        rb = self._repeat_bufs(k)
-        out = b["out"]
-        for qi in idx.tolist():
-            # the query may live in pinned host memory or on the device: both are addressable from the GPU
-            self.shard.search_device_at(int(b["base"]) + qi, q_ptr + qi * self.shard.dim * esz, q_dtype, 1, k, b["want"],
-                                        rb["local"][0].data_ptr(), rb["local"][1].data_ptr(), rb["local"][2].data_ptr(),
-                                        rb["counts"].data_ptr(), rb["hflags"], self.stream.cuda_stream)
-            if self.world > 1:
-                rb["dflags"].copy_(t.from_numpy(rb["hflags"]), non_blocking=False)
-                if self.exchange_mode == "p2p":
-                    N.check(lib.lvs_exchange_merge_device(self._exchange(1, k), C.c_void_p(rb["local"].data_ptr()), C.c_void_p(rb["dflags"].data_ptr()),
-                                                          1, k, C.c_void_p(rb["out"].data_ptr()), C.c_void_p(rb["counts"].data_ptr()),
-                                                          C.c_void_p(rb["dflags2"].data_ptr()), C.c_void_p(self.stream.cuda_stream)),
-                            "lvs_exchange_merge_device")
-                else:
-                    with t.cuda.stream(self.stream):
-                        allgather_packed(rb["local"], rb["gathered"], self.group)
-                        self.dist.all_reduce(rb["dflags"], op=self.dist.ReduceOp.MAX, group=self.group)
-                        rb["dflags2"].copy_(rb["dflags"])
-                    base = rb["gathered"].data_ptr()
-                    merge_topk_device(base, base + 8 * k, base + 16 * k, self.world, 1, k, rb["out"][0].data_ptr(), rb["out"][1].data_ptr(),
-                                      rb["out"][2].data_ptr(), rb["counts"].data_ptr(), self.stream.cuda_stream, shard_stride=3 * k)
-                self.stream.synchronize()
-                res, f = rb["out"], int(rb["dflags2"].item())
-            else:
-                self.stream.synchronize()
-                res, f = rb["local"], int(rb["hflags"][0])
-            with t.cuda.stream(self.stream):
-                out[:, qi, :].copy_(res[:, 0, :])
-                b["counts"][qi:qi + 1].copy_(rb["counts"])
-            self.stream.synchronize()
+        for qi in np.nonzero(flags & N.FLAG_UNPROVEN)[0].tolist():
+            block, count, f = self._repeat_query(queries[qi], base + qi, k, want)
+            store(qi, block, count)
             flags[qi] = f
         return flags
 
-    def _repeat_bufs(self, k: int) -> dict:
+    def _repeat_bufs(self, k: int, dim: int) -> dict:
         rb = self._bufs.get(("repeat", k))
         if rb is None:
             t = self.torch
-            dev = lambda *shape, dtype: t.zeros(shape, dtype=dtype, device=self.device)
+            dev = lambda *shape, dtype: t.zeros(shape, dtype=dtype, device=self.device)  # noqa: E731
             rb = {"local": dev(3, 1, k, dtype=t.int64), "out": dev(3, 1, k, dtype=t.int64), "counts": dev(1, dtype=t.int32),
                   "dflags": dev(1, dtype=t.int32), "dflags2": dev(1, dtype=t.int32), "hflags": np.zeros(1, dtype=np.int32),
-                  "gathered": dev(self.world, 3, 1, k, dtype=t.int64)}
+                  "gathered": dev(self.world, 3, 1, k, dtype=t.int64), "hq": t.zeros((1, dim), dtype=t.float64).pin_memory()}
             self._bufs[("repeat", k)] = rb
         return rb
 
@@ -223,20 +216,35 @@ class ShardedSearcher:
 
     def search_device(self, dq, k: int, want=None):
         """Synchronous device entry; flagged queries are repeated (collectively); returns the tensors plus the host flags."""
+        t = self.torch
         s, r, ti, c, f = self.search_device_async(dq, k, want, slot=0)
         self.stream.synchronize()
         b = self._slot(int(dq.shape[0]), k, 0, host=False)
-        flags = self._settle(b, f.cpu().numpy().copy(), queries_of=dq)
+        flags = f.cpu().numpy().copy()
+        if flags.any():
+            def store(qi, block, count):
+                b["out"][:, qi, :].copy_(t.from_numpy(block))
+                b["counts"][qi] = count
+            flags = self._settle(dq.double().cpu().numpy(), int(b["base"]), k, want, flags, store)
+            t.cuda.synchronize()
         return s, r, ti, c, flags
 
     # ---- host entry points -----------------------------------------------------------------------------
     def submit(self, queries: np.ndarray, k: int, want=None):
-        """Pipelined host entry; returns a handle for :meth:`wait`.  Up to ``n_slots`` searches may be in flight."""
+        """Pipelined host entry; returns a handle for :meth:`wait`.  Up to ``n_slots`` searches may be in flight.  One GPU or the
+        peer-memory exchange: the library's own pipelined pair (``lvs_search_submit[_sharded]`` / ``lvs_search_wait``: pinned slots,
+        the query staged by one CTA, the result and a completion word stored by the kernel, no event between consecutive
+        searches).  "nccl" exchange: pinned torch buffers + all_gather_into_tensor + merge kernel."""
         t = self.torch
         q = np.ascontiguousarray(queries, dtype=np.float64)
         if q.ndim == 1:
             q = q[None, :]
         Q, dim = q.shape
+        if self.world == 1 or self.exchange_mode == "p2p":
+            base = self.shard.search_counter + 1
+            ticket = self.shard.search_submit(q, k, want) if self.world == 1 else \
+                self.shard.search_submit_sharded(self._exchange(Q, k), q, k, want)
+            return {"ticket": ticket, "queries": q, "base": base, "want": want, "k": k}
         slot = self._next_slot
         self._next_slot = (slot + 1) % self.n_slots
         b = self._slot(Q, k, slot, host=True)
@@ -246,17 +254,25 @@ class ShardedSearcher:
         # pinned memory is mapped into the device address space (UVA): the kernels read/write it directly
         self._enqueue(b["hq"].data_ptr(), "f64", Q, k, want, b)
         b["event"].record(self.stream)
+        b["queries"], b["k"] = q, k
         return b
 
     def wait(self, handle):
         """Blocks until the search has finished; flagged queries are repeated (every rank takes the same decision, so this stays
         a collective); raises when the exchange reported a missing peer."""
-        handle["event"].synchronize()
-        flags = handle["flags"].numpy().copy()
-        if flags.any():
-            flags = self._settle(handle, flags, queries_of=handle["hq"])
-        o = handle["out"].numpy()
-        return (o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy(), handle["counts"].numpy().copy(), flags)
+        if "ticket" in handle:
+            res = self.shard.search_wait(handle["ticket"])
+            scores, rows, ties, counts, flags = res.scores, res.rows, res.ties, res.counts, res.flags
+        else:
+            handle["event"].synchronize()
+            o = handle["out"].numpy()
+            scores, rows, ties = o[0].view(np.float64).copy(), o[1].copy(), o[2].view(np.uint64).copy()
+            counts, flags = handle["counts"].numpy().copy(), handle["flags"].numpy().copy()
+        if flags.any() and (self.world > 1 or "ticket" not in handle):      # one GPU through the library: already repeated there
+            def store(qi, block, count):
+                scores[qi], rows[qi], ties[qi], counts[qi] = block[0].view(np.float64), block[1], block[2].view(np.uint64), count
+            flags = self._settle(handle["queries"], int(handle["base"]), handle["k"], handle["want"], flags, store)
+        return scores, rows, ties, counts, flags
 
     def search(self, queries: np.ndarray, k: int, want=None):
         """Synchronous host entry (one search at a time)."""

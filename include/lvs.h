@@ -103,6 +103,9 @@ int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, 
 int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket);
 int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
                     uint32_t* out_counts, int32_t* out_flags);
+/* A search of up to 4 queries on the scan path is ONE kernel that stores its result block and then a completion word into the
+ * slot's mapped pinned memory; lvs_search_wait polls that word (no event between consecutive kernels, so searches submitted back
+ * to back keep overlapping on the GPU).  Batches and timing mode complete through a CUDA event as before. */
 /* Device-pointer form used by the sharded path: queries and the four Q x k / Q outputs are DEVICE buffers, the work is
  * enqueued on `stream` (cudaStream_t, NULL = collection stream) and completed before return; flags are host. */
 int lvs_search_device(lvs_collection* c, const void* d_queries, int dtype, int Q, int k, const uint32_t* want,
@@ -154,6 +157,11 @@ int lvs_exchange_merge_device(lvs_exchange* ex, const int64_t* d_local, const in
  * batches on the tensor-core path add the exchange kernel behind the finalize kernel.  Enqueue only, no repeat of flagged queries. */
 int lvs_search_sharded_device_async(lvs_collection* c, lvs_exchange* ex, const void* d_queries, int dtype, int Q, int k,
                                     const uint32_t* want, int64_t* d_out, uint32_t* d_out_counts, int32_t* d_out_flags, void* stream);
+/* Host-buffer form of the sharded search, pipelined like lvs_search_submit: every rank submits the same queries; lvs_search_wait on
+ * the ticket returns the MERGED lists and the merged flags (OR over the shards).  Flagged queries are not repeated here: every rank
+ * sees the same flags and repeats them collectively (lvs_search_device_at + lvs_exchange_merge_device). */
+int lvs_search_submit_sharded(lvs_collection* c, lvs_exchange* ex, const void* queries, int dtype, int Q, int k, const uint32_t* want,
+                              int* ticket);
 int lvs_exchange_error(lvs_exchange* ex);     /* 1 if a peer's flag ever timed out (synchronises) */
 int lvs_exchange_destroy(lvs_exchange* ex);
 
