@@ -22,6 +22,13 @@ FLAG_UNPROVEN = 1
 FLAG_EXCHANGE = 2
 
 _vp = C.c_void_p
+
+
+class EncoderConfig(C.Structure):
+    """``lvs_encoder_config`` (include/lvs.h)."""
+    _fields_ = [("vocab", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32),
+                ("intermediate", C.c_int32), ("max_pos", C.c_int32), ("pad_id", C.c_int32), ("ln_eps", C.c_float)]
+
 _i64p = C.POINTER(C.c_int64)
 _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
@@ -60,6 +67,12 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_scan_times": (C.c_int, [_vp, C.c_int, _f32p, _f64p, _ip]),
     "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_encoder_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "lvs_encoder_load": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int64]),
+    "lvs_encoder_embed": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    "lvs_encoder_embed_upsert": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "lvs_encoder_last_ms": (C.c_int, [_vp, _f32p]),
+    "lvs_encoder_destroy": (C.c_int, [_vp]),
     "lvs_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _vp]),
     "lvs_exchange_connect": (C.c_int, [_vp, _vp]),
     "lvs_exchange_merge_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),

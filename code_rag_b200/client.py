@@ -230,12 +230,33 @@ class _HostCollection:
             n = min(n, len(vectors), len(payloads))  # the reference zips the three lists (client.py:123-126)
         if n == 0:
             return
-        canon = [_canonical_id(i) for i in ids[:n]]
         vec = np.asarray(vectors[:n], dtype=np.float64)
         if vec.ndim != 2 or vec.shape[1] != self.dim:
             raise ValueError(f"vectors must have dimension {self.dim}, got shape {vec.shape}")
         if not np.isfinite(vec).all():
             raise ValueError("vectors must be finite")
+        self._upsert_with(ids[:n], payloads[:n], lambda keep, rows, codes, ties: self.dev.upsert(vec[keep], rows=rows, codes=codes, ties=ties))
+
+    def upsert_tokens(self, ids, token_ids: np.ndarray, payloads, encoder) -> None:
+        """Embed and upsert in one device call: `token_ids` [n, L] go through `encoder` (embedding.B200CodeEncoder)
+        and the pooled vectors pass from its last kernel to the upsert kernel without leaving HBM - the step that in the reference is
+        embed_batch -> list[list[float]] -> QdrantManager.upsert (embeddings/indexer.py:77-86)."""
+        tok = np.ascontiguousarray(token_ids, dtype=np.int32)
+        n = min(len(ids), tok.shape[0], len(payloads))
+        if n == 0:
+            return
+        if tok.ndim != 2:
+            raise ValueError("token_ids must be [n, L]")
+        if encoder.hidden != self.dim:
+            raise ValueError(f"the encoder produces {encoder.hidden}-dimensional vectors, the collection holds {self.dim}")
+        self._upsert_with(ids[:n], payloads[:n],
+                          lambda keep, rows, codes, ties: encoder.embed_upsert(self.dev, tok[:n][keep], rows=rows, codes=codes, ties=ties))
+
+    def _upsert_with(self, ids, payloads, write) -> None:
+        """Host bookkeeping of an upsert (row assignment, overwrite by id, row reuse, dictionary codes, tie keys) around
+        `write(keep, rows, codes, ties)`, which puts the vectors of the points `keep` into `rows` on the device."""
+        n = len(ids)
+        canon = [_canonical_id(i) for i in ids[:n]]
         # a repeated id inside one batch: the last occurrence wins, as with sequential point upserts
         last = {pid: i for i, pid in enumerate(canon)}
         keep = sorted(last.values())
@@ -259,7 +280,7 @@ class _HostCollection:
         codes = self.encode_payloads(pl)
         ties = np.array([_tie_key(canon[i]) for i in keep], dtype=np.uint64)
         try:
-            self.dev.upsert(vec[keep], rows=rows, codes=codes, ties=ties)
+            write(keep, rows, codes, ties)
         except Exception:
             self.free_rows.extend(r for _, r in reused)          # nothing was written: the rows stay reusable
             raise
@@ -688,6 +709,21 @@ class B200VectorStore:
                     coll.upsert(ids, vectors, payloads)
             await asyncio.to_thread(work)
             logger.debug(f"Upserted {len(ids)} vectors to {collection}")
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError(f"Failed to upsert vectors to {collection}", cause=e)
+
+    async def upsert_tokens(self, collection: str, ids: list[str], token_ids, payloads: list[dict[str, Any]], encoder) -> None:
+        """Additive API: index chunks from their TOKEN IDS.  `encoder` (``embedding.B200CodeEncoder``) embeds
+        them on this store's GPU and the vectors go straight into the shard - what ``VectorIndexer.index_file`` does with
+        ``embedder.embed_batch`` + ``upsert`` (reference embeddings/indexer.py:77-86) without the list[float] round trip."""
+        try:
+            coll = self._get(collection)
+
+            def work():
+                with coll.lock:
+                    coll.upsert_tokens(ids, token_ids, payloads, encoder)
+            await asyncio.to_thread(work)
+            logger.debug(f"Embedded and upserted {len(ids)} vectors to {collection}")
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to upsert vectors to {collection}", cause=e)
 

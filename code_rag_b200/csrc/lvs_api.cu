@@ -19,6 +19,7 @@
 #include "finalize_kernel.cuh"
 #include "gemm_topk_kernel.cuh"
 #include "rank_kernel.cuh"
+#include "host_util.h"
 #include "scan_launch.cuh"
 
 using namespace lvs;
@@ -455,13 +456,10 @@ static int launch_upsert(lvs_collection* c, const void* d_src, int dtype, int64_
     return LVS_OK;
 }
 
-extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_t n, const int64_t* rows,
-                          const uint32_t* codes, const uint64_t* ties) {
-    bind_thread();
-    if (!c) return fail(LVS_EINVAL, "collection is NULL");
-    if (n < 0 || (n > 0 && !vecs)) return fail(LVS_EINVAL, "bad vecs / n");
-    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64 && dtype != LVS_DT_BF16) return fail(LVS_EINVAL, "unknown dtype %d", dtype);
-    if (n == 0) return LVS_OK;
+// Shared body of lvs_upsert (host vectors) and lvs_upsert_device_vectors (vectors already in HBM: the encoder's output): row numbers,
+// tie keys and filter codes are staged through pinned memory either way.
+static int upsert_impl(lvs_collection* c, const void* vecs, const void* d_vecs, int dtype, int64_t n, const int64_t* rows,
+                       const uint32_t* codes, const uint64_t* ties) {
     std::lock_guard<std::mutex> lk(c->mu);
     int64_t hi = c->n_rows;
     int64_t row0 = c->n_rows;
@@ -479,8 +477,9 @@ extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_
     }
     // stage through pinned memory in batches of <= 32 MiB of vector data
     const size_t vrow = (size_t)c->dim * dt_size(dtype);
+    const size_t vstage = d_vecs ? 0 : vrow;                       // device vectors are read in place
     const int64_t batch = std::max<int64_t>(1, (int64_t)((32u << 20) / vrow));
-    const size_t per_row = vrow + 8 + 8 + (size_t)c->n_cols * 4;
+    const size_t per_row = vstage + 8 + 8 + (size_t)c->n_cols * 4;
     const int64_t b0 = std::min(batch, n);
     int rc = ensure_pinned(c->h_pin, (size_t)b0 * per_row + 64);
     if (rc != LVS_OK) return rc;
@@ -492,11 +491,11 @@ extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_
         uint8_t* hp = (uint8_t*)c->h_pin.p;
         uint8_t* dp = (uint8_t*)c->s_stage_dev.p;
         size_t o_vec = 0;
-        size_t o_rows = ((size_t)m * vrow + 15) & ~(size_t)15;
+        size_t o_rows = ((size_t)m * vstage + 15) & ~(size_t)15;
         size_t o_ties = o_rows + (size_t)m * 8;
         size_t o_codes = o_ties + (size_t)m * 8;
         size_t total = o_codes + (size_t)m * c->n_cols * 4;
-        memcpy(hp + o_vec, (const uint8_t*)vecs + (size_t)s * vrow, (size_t)m * vrow);
+        if (!d_vecs) memcpy(hp + o_vec, (const uint8_t*)vecs + (size_t)s * vrow, (size_t)m * vrow);
         if (rows) {
             int64_t* lr = (int64_t*)(hp + o_rows);
             for (int64_t j = 0; j < m; ++j) lr[j] = rows[s + j] - c->row_base;   // global -> local
@@ -504,7 +503,8 @@ extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_
         if (ties) memcpy(hp + o_ties, ties + s, (size_t)m * 8);
         if (codes && c->n_cols) memcpy(hp + o_codes, codes + (size_t)s * c->n_cols, (size_t)m * c->n_cols * 4);
         CU(cudaMemcpyAsync(dp, hp, total, cudaMemcpyHostToDevice, st));
-        rc = launch_upsert(c, dp + o_vec, dtype, m, rows ? (const int64_t*)(dp + o_rows) : nullptr, row0 + s,
+        const void* src = d_vecs ? (const void*)((const uint8_t*)d_vecs + (size_t)s * vrow) : (const void*)(dp + o_vec);
+        rc = launch_upsert(c, src, dtype, m, rows ? (const int64_t*)(dp + o_rows) : nullptr, row0 + s,
                            (codes && c->n_cols) ? (const uint32_t*)(dp + o_codes) : nullptr,
                            ties ? (const uint64_t*)(dp + o_ties) : nullptr, st);
         if (rc != LVS_OK) return rc;
@@ -513,6 +513,26 @@ extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_
     c->n_rows = hi;
     CU(cudaMemcpy(c->h_norm_stats, c->d_max_norm, 8, cudaMemcpyDeviceToHost));
     return LVS_OK;
+}
+
+extern "C" int lvs_upsert(lvs_collection* c, const void* vecs, int dtype, int64_t n, const int64_t* rows,
+                          const uint32_t* codes, const uint64_t* ties) {
+    bind_thread();
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n < 0 || (n > 0 && !vecs)) return fail(LVS_EINVAL, "bad vecs / n");
+    if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64 && dtype != LVS_DT_BF16) return fail(LVS_EINVAL, "unknown dtype %d", dtype);
+    if (n == 0) return LVS_OK;
+    return upsert_impl(c, vecs, nullptr, dtype, n, rows, codes, ties);
+}
+
+int lvs_upsert_device_vectors(lvs_collection* c, const void* d_vecs, int dtype, int64_t n, const int64_t* rows, const uint32_t* codes,
+                              const uint64_t* ties) {
+    bind_thread();
+    if (!c) return fail(LVS_EINVAL, "collection is NULL");
+    if (n < 0 || (n > 0 && !d_vecs)) return fail(LVS_EINVAL, "bad d_vecs / n");
+    if (n == 0) return LVS_OK;
+    // the vectors were produced on another stream: the caller has synchronised it (encoder_api.cu does)
+    return upsert_impl(c, nullptr, d_vecs, dtype, n, rows, codes, ties);
 }
 
 extern "C" int lvs_upsert_device(lvs_collection* c, const void* d_vecs, int dtype, int64_t n, int64_t row0,
@@ -925,6 +945,21 @@ static int get_encode_tiled() {
     g_encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     return LVS_OK;
 }
+
+int lvs_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+bool lvs_lib_ready() { return g_lib.ready; }
+int lvs_lib_sm_count() { return g_lib.sm_count; }
+size_t lvs_lib_smem_optin() { return g_lib.smem_optin; }
+void lvs_lib_bind_thread() { bind_thread(); }
+PFN_cuTensorMapEncodeTiled_v12000 lvs_lib_encode_tiled() { return get_encode_tiled() == LVS_OK ? g_encode_tiled : nullptr; }
 
 static bool gemm_eligible(const lvs_collection* c, int Q, bool filter) {
     (void)filter;                 // K2 evaluates the payload filter next to the tombstone check

@@ -248,6 +248,31 @@ int lvs_truncate(lvs_collection* c, int64_t n_rows);
 int lvs_snapshot_save(lvs_collection* c, const char* path);
 int lvs_snapshot_load(const char* path, const char* name, int64_t capacity_rows, lvs_collection** out);
 
+/* ---- embedding on the GPUs that search -----------------------------------------------------------
+ * The step in front of upsert: the reference embeds a chunk with UniXcoder - transformers' RobertaModel over the token ids with
+ * bidirectional attention among the non-pad tokens, masked mean pooling (src/lattice/providers/unixcoder_provider.py:137-155) -
+ * converts the vectors to python lists (:194-215) and passes them to QdrantManager.upsert (embeddings/indexer.py:77-86).  The
+ * encoder below runs that forward pass on the device (tcgen05 GEMMs with fused bias / GELU / residual epilogues, attention on
+ * mma.sync, LayerNorm and pooling kernels; bf16 activations, fp32 accumulation) and lvs_encoder_embed_upsert feeds the pooled
+ * vectors straight into the shard's upsert kernel.  Tokenisation stays with the caller (the tokenizer is a host-side dictionary).
+ * Parameters are loaded by their Hugging Face state-dict names ("embeddings.word_embeddings.weight",
+ * "encoder.layer.3.attention.self.query.weight", ...; a leading "roberta." / "model." is ignored) as fp32 host arrays. */
+typedef struct lvs_encoder lvs_encoder;
+typedef struct lvs_encoder_config {
+    int32_t vocab, hidden, n_layers, n_heads, intermediate, max_pos, pad_id;   /* RobertaConfig; hidden = 64 * n_heads */
+    float ln_eps;
+} lvs_encoder_config;
+int lvs_encoder_create(const lvs_encoder_config* cfg, lvs_encoder** out);
+int lvs_encoder_load(lvs_encoder* e, const char* name, const float* data, int64_t n);
+/* ids: B x L token ids (host, pad_id-padded).  out: B x hidden float32 sentence embeddings (host). */
+int lvs_encoder_embed(lvs_encoder* e, const int32_t* ids, int B, int L, float* out);
+/* Embed and upsert in one call: the B vectors go from the pooling kernel to the upsert kernel without leaving HBM.  rows / codes /
+ * ties as in lvs_upsert. */
+int lvs_encoder_embed_upsert(lvs_encoder* e, lvs_collection* c, const int32_t* ids, int B, int L, const int64_t* rows,
+                             const uint32_t* codes, const uint64_t* ties);
+int lvs_encoder_last_ms(const lvs_encoder* e, float* ms);   /* device time of the last forward pass (CUDA events) */
+int lvs_encoder_destroy(lvs_encoder* e);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the collection's stream) of the kernels of the last lvs_search* call on this handle:
  * [0] query prep  [1] scan / tensor-core kernel(s)  [2] finalize  [3] whole device section; n_launches = kernels launched. */

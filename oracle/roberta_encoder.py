@@ -34,7 +34,10 @@ def _ln(x: np.ndarray, w: np.ndarray, b: np.ndarray, eps: float) -> np.ndarray:
     return (x - mu) / np.sqrt(var + eps) * w + b
 
 
-_erf = np.vectorize(math.erf, otypes=[np.float64])
+try:
+    from scipy.special import erf as _erf          # vectorised; math.erf element by element is the fallback
+except Exception:  # noqa: BLE001
+    _erf = np.vectorize(math.erf, otypes=[np.float64])
 
 
 def _gelu(x: np.ndarray) -> np.ndarray:
