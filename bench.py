@@ -397,8 +397,12 @@ def run_ours(args) -> None:
         DEPTH = 2
         submit = (lambda qh: searcher.submit(qh, k)) if world > 1 else (lambda qh: shard.search_submit(qh, k))
         wait = searcher.wait if world > 1 else shard.search_wait
-        for i in range(max(W, NSLOT)):                  # every result slot (pinned buffers, exchange capacity) exists before the clock starts
+        for i in range(W):
             wait(submit(qs[i % (K + W)]))
+        # every result slot (pinned + device staging buffers are allocated at a slot's first use) exists before the clock starts:
+        # the library hands out the first free slot, so all of them have to be in flight at once
+        for h in [submit(qs[i % (K + W)]) for i in range(NSLOT)]:
+            wait(h)
         barrier()
         t0 = time.perf_counter()
         inflight = []

@@ -87,19 +87,26 @@ __device__ __forceinline__ void exchange_merge_query(const ExchangeParams& p, in
         if (r[i] >= 0) atomicAdd(s_nvalid, 1u);
     }
     bar();
+    // every rank's list arrives sorted best-first (padding last), so the global rank of an entry is the sum over the lists of how
+    // many of their entries beat it: a binary search per list (world * log2 k steps) instead of a scan of all world * k entries
     for (int i = tid; i < m; i += nthreads) {
         if (r[i] < 0) continue;
+        const double si = s[i]; const uint64_t ti = t[i]; const int64_t ri = r[i];
         uint32_t rank = 0;
-        for (int o = 0; o < m; ++o) {
-            if (r[o] < 0) continue;
-            const bool better = (s[o] > s[i]) || (s[o] == s[i] && (t[o] < t[i] || (t[o] == t[i] && r[o] < r[i])));
-            rank += better ? 1u : 0u;
+        for (int g = 0; g < p.world; ++g) {
+            int lo = 0, hi = p.k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1, o = g * p.k + mid;
+                const bool better = r[o] >= 0 && ((s[o] > si) || (s[o] == si && (t[o] < ti || (t[o] == ti && r[o] < ri))));
+                if (better) lo = mid + 1; else hi = mid;
+            }
+            rank += (uint32_t)lo;
         }
         if (rank < (uint32_t)p.k) {
             const size_t o = (size_t)qo * p.k + rank;
-            p.out[o] = __double_as_longlong(s[i]);
-            p.out[oqk + o] = r[i];
-            p.out[2 * oqk + o] = (int64_t)t[i];
+            p.out[o] = __double_as_longlong(si);
+            p.out[oqk + o] = ri;
+            p.out[2 * oqk + o] = (int64_t)ti;
         }
     }
     const uint32_t nout = min(*s_nvalid, (uint32_t)p.k);

@@ -806,7 +806,7 @@ static int exchange_params(lvs_exchange* ex, int Q, int k, ExchangeParams* out) 
 static int launch_exchange(const ExchangeParams& p, cudaStream_t st) {
     const size_t smem = (size_t)p.world * p.k * 24;
     if (smem > 40 * 1024) CU(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::max(1, std::min(p.Q, 32));
+    const int grid = std::max(1, std::min(p.Q, 2 * g_lib.sm_count));      // a CTA merges one query at a time
     exchange_merge_kernel<<<grid, 256, smem, st>>>(p);
     CU(cudaGetLastError());
     return LVS_OK;

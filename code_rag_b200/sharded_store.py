@@ -199,6 +199,7 @@ class ShardPlane:
         self.lock = threading.RLock()             # controller: one command at a time
         self.pending: list[list[tuple]] = [[] for _ in range(world)]     # controller: queued writes per rank
         self.closed = False
+        self._deferred: int | None = None
         self.mailbox: _Mailbox | None = None
         if world > 1 and os.environ.get("LATTICE_B200_MAILBOX", "1") != "0":
             self.mailbox = _Mailbox(rank, world, ctl_group)              # collective
@@ -251,10 +252,21 @@ class ShardPlane:
                 # command of their own, so that a rank failing one of them is reported instead of missing the exchange
                 self.call("noop", None)
             mb = self.mailbox
+            if self._deferred is not None:
+                # the workers' replies to the previous fast-path search (see below) are due before the mailbox is written again
+                seq, self._deferred = self._deferred, None
+                bad = [(r + 1, msg) for r, (ok, msg) in enumerate(mb.collect(seq)) if not ok]
+                if bad:
+                    raise RuntimeError("previous search: " + "; ".join(f"rank {r}: {msg}" for r, msg in bad))
             if op == "search" and mb is not None and mb.fits(common[0].shape[0], common[0].shape[1], name):
-                # fast path: the command travels through shared memory, the replies through the workers' status slots
+                # fast path: the command travels through shared memory, the replies through the workers' status slots.  The controller
+                # holds the MERGED result as soon as its own shard's kernel has finished (the exchange made every rank wait for every
+                # other one), so it returns without waiting for the workers' host-side epilogue; their replies are collected before
+                # the next command (a worker that failed before its exchange shows up right away as an exchange timeout)
                 seq = mb.post(mb.OP_SEARCH, name, common[0], int(common[1]), common[2])
-                replies = [self._execute(op, name, common, [])] + mb.collect(seq)
+                mine = self._execute(op, name, common, [])
+                self._deferred = seq
+                replies = [mine]
             else:
                 if mb is not None:
                     mb.post(mb.OP_GLOO)                  # the workers leave the mailbox poll and enter the scatter
