@@ -246,10 +246,11 @@ static int forward(lvs_encoder* e, int B, int L) {
     EmbedParams ep;
     ep.ids = e->d_ids; ep.B = B; ep.L = L; ep.H = H; ep.pad_id = c.pad_id; ep.max_pos = c.max_pos; ep.vocab = c.vocab;
     ep.word = e->word; ep.pos = e->pos; ep.type0 = e->type0; ep.ln_w = e->eln_w; ep.ln_b = e->eln_b; ep.eps = c.ln_eps; ep.out = e->x; ep.error = e->d_err;
-    embed_ln_kernel<<<B, 256, (size_t)L * 4, st>>>(ep);
+    embed_ln_kernel<<<dim3((unsigned)B, (unsigned)((L + 63) / 64)), 256, (size_t)L * 4, st>>>(ep);
     LVS_CU(cudaGetLastError());
     const int Lp = (L + 63) / 64 * 64;
     const size_t asmem = attention_smem_bytes(Lp);
+    if (Lp > 512) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens exceed the attention kernel's 512 (the reference's default max_length)", L);
     if (asmem > lvs_lib_smem_optin()) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens do not fit the attention kernel's shared memory", L);
     {
         static std::once_flag once;
@@ -273,7 +274,7 @@ static int forward(lvs_encoder* e, int B, int L) {
         add_ln_kernel<<<ln_grid, 256, 0, st>>>(e->y, (int)M, H, Lr.ln2_w, Lr.ln2_b, c.ln_eps, e->x);
         LVS_CU(cudaGetLastError());
     }
-    pool_kernel<<<B, 256, 0, st>>>(e->x, e->d_ids, L, H, c.pad_id, e->pooled);
+    pool_kernel<<<dim3((unsigned)B, (unsigned)((H + 255) / 256)), 256, 0, st>>>(e->x, e->d_ids, L, H, c.pad_id, e->pooled);
     LVS_CU(cudaGetLastError());
     return LVS_OK;
 }

@@ -11,7 +11,8 @@
 namespace lvs {
 
 // ---------------------------------------------------------------------------------------------------------
-// embeddings + LayerNorm.  One CTA per sequence (256 threads): positions by a block scan over the mask, then a warp per token.
+// embeddings + LayerNorm.  grid = (sequences, blocks of 64 tokens), 256 threads: positions by a block scan over the sequence's mask
+// (repeated by every CTA of the sequence: a few hundred integers), then a warp per token of the CTA's block.
 // ---------------------------------------------------------------------------------------------------------
 struct EmbedParams {
     const int32_t* ids;        // [B][L]
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const EmbedParams p) {
         __syncthreads();
     }
     const int nper = (p.H + 31) / 32;
-    for (int t = warp; t < p.L; t += 8) {
+    for (int t = blockIdx.y * 64 + warp; t < min(p.L, (int)(blockIdx.y + 1) * 64); t += 8) {
         const int id = ids[t], pos = esm[t];
         if (id < 0 || id >= p.vocab || pos < 0 || pos >= p.max_pos) { if (lane == 0) *p.error = 1; continue; }
         const float* w = p.word + (size_t)id * p.H;
@@ -108,45 +109,52 @@ __global__ void __launch_bounds__(256) add_ln_kernel(const float* in, int M, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// masked mean pooling: out[b] = sum_{t: ids[b][t] != pad} x[b][t] / count.  One CTA per sequence.
+// masked mean pooling: out[b] = sum_{t: ids[b][t] != pad} x[b][t] / count.  grid = (sequences, column blocks of 256): a thread owns
+// one column and walks the tokens eight at a time (the mask in shared memory, eight independent loads in flight).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* x, const int32_t* ids, int L, int H, int pad_id, float* out) {
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x;
+    __shared__ uint8_t s_m[1024];
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     int cnt = 0;
-    for (int t = threadIdx.x; t < L; t += 256) cnt += ids[(size_t)b * L + t] != pad_id ? 1 : 0;
+    for (int t = threadIdx.x; t < L; t += 256) { const int m = ids[(size_t)b * L + t] != pad_id ? 1 : 0; if (t < 1024) s_m[t] = (uint8_t)m; cnt += m; }
     cnt = (int)warp_sum_f32((float)cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
     __syncthreads();
+    if (c >= H) return;
     const float inv = 1.0f / (float)max(s_cnt, 1);
-    for (int c = threadIdx.x; c < H; c += 256) {
-        float acc = 0.f;
-        for (int t = 0; t < L; ++t)
-            if (ids[(size_t)b * L + t] != pad_id) acc += __bfloat162float(x[((size_t)b * L + t) * H + c]);
-        out[(size_t)b * H + c] = acc * inv;
+    const __nv_bfloat16* xp = x + (size_t)b * L * H + c;
+    float acc = 0.f;
+    int t = 0;
+    for (; t + 8 <= L; t += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __bfloat162float(xp[(size_t)(t + u) * H]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += s_m[t + u] ? v[u] : 0.f;
     }
+    for (; t < L; ++t) acc += s_m[t] ? __bfloat162float(xp[(size_t)t * H]) : 0.f;
+    out[(size_t)b * H + c] = acc * inv;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // attention.  qkv [B*L][3H] bf16 (q | k | v, head h at columns h*64 of each third); ctx [B*L][H] bf16.
-// One CTA = (sequence, head, block of 128 queries): 8 warps x 16 queries.  K (row-major, padded rows) and V^T (padded rows) of the
-// whole sequence sit in shared memory; each warp walks the keys in blocks of 64 with an online softmax:
-//   S = Q K^T        8 n-tiles x 4 k-steps of mma.sync.m16n8k16 (A = Q fragment held in registers, B = K rows)
+// One CTA = (sequence, head, block of 128 queries): 8 warps x 16 queries.  K and V of the whole sequence are brought into shared
+// memory (row-major, rows padded to 72 bf16) by cp.async in groups of 64 keys, so the first key blocks are being multiplied while the
+// later ones are still in flight; each warp walks the keys in blocks of 64 with an online softmax:
+//   S = Q K^T        8 n-tiles x 4 k-steps of mma.sync.m16n8k16 (A = Q fragment held in registers, B = K rows by ldmatrix.x4)
 //   P = exp(S - m)   in registers; the accumulator layout of two adjacent n-tiles IS the A-fragment layout of one k-step
-//   O += P V         4 k-steps x 8 n-tiles (B = V^T rows)
+//   O += P V         4 k-steps x 8 n-tiles (B = V by ldmatrix.x4.trans: no transposed copy of V is ever made)
 // Pad keys get -inf before the softmax (the reference masks them: mask.unsqueeze(1) * mask.unsqueeze(2)); pad query rows are
 // computed like the others and dropped by the pooling.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAttnD = 64;
 constexpr int kAttnQB = 128;
-constexpr int kAttnKPad = 72;          // K row stride in bf16 (36 words: conflict-free fragment loads)
+constexpr int kAttnKPad = 72;          // K / V row stride in bf16 (36 words: conflict-free fragment and ldmatrix loads)
 
-__host__ __device__ inline int attn_vt_stride(int Lp) { return Lp + 8; }
-__host__ __device__ inline size_t attention_smem_bytes(int Lp) {
-    return (size_t)Lp * kAttnKPad * 2 + (size_t)kAttnD * attn_vt_stride(Lp) * 2 + (size_t)Lp * 4;
-}
+__host__ __device__ inline size_t attention_smem_bytes(int Lp) { return (size_t)2 * Lp * kAttnKPad * 2 + (size_t)Lp * 4; }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -156,14 +164,38 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's committed groups are still in flight (pending is 0..7)
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
 
 __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv, const int32_t* ids, int L, int Lp, int H, int n_heads, int pad_id,
                                                         __nv_bfloat16* ctx) {
     extern __shared__ __align__(16) uint8_t asm_[];
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(asm_);                       // [Lp][72]
-    const int vts = attn_vt_stride(Lp);
-    __nv_bfloat16* Vt = Ks + (size_t)Lp * kAttnKPad;                                  // [64][Lp + 8]
-    float* kmask = reinterpret_cast<float*>(Vt + (size_t)kAttnD * vts);               // [Lp] 0 or -inf
+    __nv_bfloat16* Vs = Ks + (size_t)Lp * kAttnKPad;                                  // [Lp][72]
+    float* kmask = reinterpret_cast<float*>(Vs + (size_t)Lp * kAttnKPad);             // [Lp] 0 or -inf
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const size_t row0 = (size_t)b * L;
@@ -171,53 +203,65 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
     const __nv_bfloat16* Qg = qkv + row0 * ld + (size_t)h * kAttnD;
     const __nv_bfloat16* Kg = Qg + H;
     const __nv_bfloat16* Vg = Qg + 2 * H;
-    // ---- K, V^T, mask -> shared (keys beyond L are zero rows with mask -inf) ----
-    for (int i = tid; i < Lp * 8; i += 256) {                  // 8 x 16-byte chunks per key row
-        const int key = i >> 3, ch = i & 7;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (key < L) {
-            kv = *reinterpret_cast<const uint4*>(Kg + (size_t)key * ld + ch * 8);
-            vv = *reinterpret_cast<const uint4*>(Vg + (size_t)key * ld + ch * 8);
+    const int n_blocks = Lp / 64;                              // <= 8 (host: Lp <= 512)
+    // ---- K, V -> shared, one cp.async group per block of 64 keys (keys beyond L: zero rows, mask -inf) ----
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        for (int i = tid; i < 64 * 8; i += 256) {              // 8 x 16-byte chunks per key row
+            const int key = blk * 64 + (i >> 3), ch = i & 7;
+            __nv_bfloat16* kd = Ks + (size_t)key * kAttnKPad + ch * 8;
+            __nv_bfloat16* vd = Vs + (size_t)key * kAttnKPad + ch * 8;
+            if (key < L) {
+                cp_async_16(kd, Kg + (size_t)key * ld + ch * 8);
+                cp_async_16(vd, Vg + (size_t)key * ld + ch * 8);
+            } else {
+                *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
+            }
         }
-        *reinterpret_cast<uint4*>(Ks + (size_t)key * kAttnKPad + ch * 8) = kv;
-        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Vt[(size_t)(ch * 8 + e) * vts + key] = ve[e];
+        cp_async_commit();
     }
     for (int i = tid; i < Lp; i += 256) kmask[i] = (i < L && ids[row0 + i] != pad_id) ? 0.f : -INFINITY;
-    __syncthreads();
 
     const int q0 = qb * kAttnQB + warp * 16;                   // this warp's 16 query rows
-    if (q0 >= L) return;
+    const bool active = q0 < L;
     const int g = lane >> 2, tq = lane & 3;                    // fragment coordinates: row g (and g + 8), column pair tq
-    // ---- Q fragments: 4 k-steps (d = 16 each) x 4 registers ----
+    // ---- Q fragments: 4 k-steps (d = 16 each) x 4 registers, straight from global ----
     uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         const int r0 = q0 + g, r1 = q0 + g + 8;
         const int c = ks * 16 + tq * 2;
-        qa[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r0 * ld + c) : 0u;
-        qa[ks][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r1 * ld + c) : 0u;
-        qa[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r0 * ld + c + 8) : 0u;
-        qa[ks][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r1 * ld + c + 8) : 0u;
+        qa[ks][0] = (active && r0 < L) ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r0 * ld + c) : 0u;
+        qa[ks][1] = (active && r1 < L) ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r1 * ld + c) : 0u;
+        qa[ks][2] = (active && r0 < L) ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r0 * ld + c + 8) : 0u;
+        qa[ks][3] = (active && r1 < L) ? *reinterpret_cast<const uint32_t*>(Qg + (size_t)r1 * ld + c + 8) : 0u;
     }
     const float scale = 0.125f;                                // 1 / sqrt(64)
     float o[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max / sum of rows g and g + 8
+    // ldmatrix lane roles: lane supplies the address of row (lane & 7) of matrix (lane >> 3)
+    const int lm_row = lane & 7, lm_mat = lane >> 3;
 
-    for (int kb = 0; kb < Lp; kb += 64) {
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        const int kb = blk * 64;
+        cp_async_wait_pending(n_blocks - 1 - blk);             // this thread's copies of blocks 0..blk have landed ...
+        __syncthreads();                                       // ... and everybody else's
+        if (!active) continue;
         float s[8][4];
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-            const __nv_bfloat16* kr = Ks + (size_t)(kb + n * 8 + g) * kAttnKPad + tq * 2;      // B fragment: key = n*8 + g, d pair tq
+        for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+        // S = Q K^T.  B fragment of (n-tile, k-step): K[key = kb + 8n + g][d = 16 ks + 2 tq (+8)].  One ldmatrix.x4 = the two
+        // registers of k-steps ks and ks + 1 for one n-tile: matrices (d 16ks..+7 | +8..15 | 16(ks+1)..+7 | +8..15) of keys 8n..8n+7
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-                mma_bf16_16816(s[n], qa[ks], b0, b1);
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                uint32_t kf[4];
+                ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + lm_row) * kAttnKPad + kp * 32 + lm_mat * 8);
+                mma_bf16_16816(s[n], qa[kp * 2], kf[0], kf[1]);
+                mma_bf16_16816(s[n], qa[kp * 2 + 1], kf[2], kf[3]);
             }
         }
         // scale + mask; accumulator (n, i): row g (i < 2) or g + 8, key kb + n*8 + tq*2 + (i & 1)
@@ -249,18 +293,21 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
         l0 = l0 * r0 + ps0; l1 = l1 * r1 + ps1; m0 = nm0; m1 = nm1;
 #pragma unroll
         for (int n = 0; n < 8; ++n) { o[n][0] *= r0; o[n][1] *= r0; o[n][2] *= r1; o[n][3] *= r1; }
-        // O += P V: n-tile = 8 head dims, k-step = 16 keys; B fragment: d = n*8 + g, key pair kb + 16 j + tq*2 (+8)
+        // O += P V.  B fragment of (k-step j, n-tile): V[key = kb + 16 j + 2 tq (+8)][d = 8 n + g] = the TRANSPOSE of the 8 x 8 tiles of
+        // the row-major V block.  One ldmatrix.x4.trans = both registers for n-tiles n and n + 1: matrices
+        // (keys +0..7, d 8n | keys +8..15, d 8n | keys +0..7, d 8n+8 | keys +8..15, d 8n+8)
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const __nv_bfloat16* vr = Vt + (size_t)(n * 8 + g) * vts + kb + tq * 2;
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr + j * 16);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + j * 16 + 8);
-                mma_bf16_16816(o[n], pa[j], b0, b1);
+            for (int np = 0; np < 4; ++np) {
+                uint32_t vf[4];
+                ldmatrix_x4_trans(vf, Vs + (size_t)(kb + j * 16 + (lm_mat & 1) * 8 + lm_row) * kAttnKPad + np * 16 + (lm_mat >> 1) * 8);
+                mma_bf16_16816(o[np * 2], pa[j], vf[0], vf[1]);
+                mma_bf16_16816(o[np * 2 + 1], pa[j], vf[2], vf[3]);
             }
         }
     }
+    if (!active) return;
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     const int r0 = q0 + g, r1 = q0 + g + 8;
     __nv_bfloat16* C0 = ctx + (row0 + r0) * H + (size_t)h * kAttnD + tq * 2;
