@@ -8,6 +8,7 @@
 // kernel: they never leave HBM.
 #include "../../include/lvs.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -52,6 +53,7 @@ struct lvs_encoder {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0.f;
+    int opt_pair = 1;          // 0: dense layers never use the CTA-pair form (env LATTICE_B200_ENCODER_PAIR=0; for A/B timing)
     std::mutex mu;
 };
 
@@ -73,6 +75,7 @@ extern "C" int lvs_encoder_create(const lvs_encoder_config* cfg, lvs_encoder** o
     lvs_encoder* e = new (std::nothrow) lvs_encoder();
     if (!e) return lvs_fail(LVS_ENOMEM, "host allocation failed");
     e->cfg = *cfg;
+    if (const char* ev = getenv("LATTICE_B200_ENCODER_PAIR")) e->opt_pair = atoi(ev) != 0;
     const int H = cfg->hidden, I = cfg->intermediate;
     int rc = LVS_OK;
     auto A = [&](void** p, size_t bytes) { if (rc == LVS_OK) rc = dev_alloc(p, bytes); };
@@ -221,19 +224,40 @@ template <int EPI>
 static int launch_linear(lvs_encoder* e, const __nv_bfloat16* X, const Dense& d, int64_t M, const __nv_bfloat16* resid, void* out) {
     static std::once_flag once;
     static cudaError_t once_err = cudaSuccess;
-    std::call_once(once, [] { once_err = cudaFuncSetAttribute(linear_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes()); });
+    std::call_once(once, [] {
+        once_err = cudaFuncSetAttribute(linear_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes(false));
+        if (once_err == cudaSuccess)
+            once_err = cudaFuncSetAttribute(linear_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes(true));
+    });
     if (once_err != cudaSuccess) return lvs_fail(LVS_ECUDA, "encoder: cudaFuncSetAttribute failed: %s", cudaGetErrorString(once_err));
+    // enough row blocks to keep every SM busy with 256-row tiles: pairs of CTAs share each weight tile (see linear_kernel.cuh)
+    const int sm = lvs_lib_sm_count();
+    const uint32_t tiles_n = (uint32_t)((d.out + kLinN - 1) / kLinN);
+    const bool pair = e->opt_pair && (uint64_t)((M + 2 * kLinM - 1) / (2 * kLinM)) * tiles_n >= (uint64_t)(sm / 2);
     CUtensorMap tx, tw;
     int rc;
     if ((rc = tmap_2d(&tx, X, (uint64_t)M, (uint64_t)d.in, kLinM)) != LVS_OK) return rc;
-    if ((rc = tmap_2d(&tw, d.w, (uint64_t)d.out, (uint64_t)d.in, kLinN)) != LVS_OK) return rc;
+    if ((rc = tmap_2d(&tw, d.w, (uint64_t)d.out, (uint64_t)d.in, pair ? kLinN / 2 : kLinN)) != LVS_OK) return rc;
     LinearParams p;
     p.M = (uint32_t)M; p.N = (uint32_t)d.out; p.K = (uint32_t)d.in;
-    p.tiles_m = (uint32_t)((M + kLinM - 1) / kLinM); p.tiles_n = (uint32_t)((d.out + kLinN - 1) / kLinN);
+    const int64_t bm = pair ? 2 * kLinM : kLinM;
+    p.tiles_m = (uint32_t)((M + bm - 1) / bm); p.tiles_n = tiles_n;
     p.bias = d.b; p.resid = resid; p.out = out;
-    const uint32_t grid = std::min<uint32_t>(p.tiles_m * p.tiles_n, (uint32_t)lvs_lib_sm_count());
-    linear_kernel<EPI><<<grid, kLinThreads, linear_smem_bytes(), e->stream>>>(tx, tw, p);
-    LVS_CU(cudaGetLastError());
+    if (pair) {
+        const uint32_t walkers = std::min<uint32_t>(p.tiles_m * p.tiles_n, (uint32_t)(sm / 2));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(walkers * 2); cfg.blockDim = dim3(kLinThreads); cfg.dynamicSmemBytes = linear_smem_bytes(true); cfg.stream = e->stream;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeClusterDimension;
+        la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+        cfg.attrs = la; cfg.numAttrs = 1;
+        LVS_CU(cudaLaunchKernelEx(&cfg, linear_kernel<EPI, true>, tx, tw, p));
+    } else {
+        const uint32_t grid = std::min<uint32_t>(p.tiles_m * p.tiles_n, (uint32_t)sm);
+        linear_kernel<EPI, false><<<grid, kLinThreads, linear_smem_bytes(false), e->stream>>>(tx, tw, p);
+        LVS_CU(cudaGetLastError());
+    }
     return LVS_OK;
 }
 
@@ -250,7 +274,6 @@ static int forward(lvs_encoder* e, int B, int L) {
     LVS_CU(cudaGetLastError());
     const int Lp = (L + 63) / 64 * 64;
     const size_t asmem = attention_smem_bytes(Lp);
-    if (Lp > 512) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens exceed the attention kernel's 512 (the reference's default max_length)", L);
     if (asmem > lvs_lib_smem_optin()) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens do not fit the attention kernel's shared memory", L);
     {
         static std::once_flag once;

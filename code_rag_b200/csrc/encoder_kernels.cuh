@@ -89,22 +89,41 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const EmbedParams p) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) add_ln_kernel(const float* in, int M, int H, const float* ln_w, const float* ln_b, float eps,
                                                      __nv_bfloat16* out) {
+    // H is a multiple of 64 (checked at create): a lane owns float4 chunks lane, lane + 32, ... of the row (16-byte loads, 8-byte stores)
     const int lane = threadIdx.x & 31;
-    const int nper = (H + 31) / 32;
+    const int nvec = H / 4;
+    constexpr int kMaxVec = 8;                 // hidden <= 1024
     for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += gridDim.x * 8) {
-        const float* x_ = in + (size_t)r * H;
-        float x[kLnMaxPerLane];
+        const float4* x_ = reinterpret_cast<const float4*>(in + (size_t)r * H);
+        float4 x[kMaxVec];
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < kLnMaxPerLane; ++j) { const int c = j * 32 + lane; x[j] = (j < nper && c < H) ? x_[c] : 0.f; s += x[j]; }
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int c = j * 32 + lane;
+            x[j] = c < nvec ? x_[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+        }
         const float mu = warp_sum_f32(s) / (float)H;
         float var = 0.f;
 #pragma unroll
-        for (int j = 0; j < kLnMaxPerLane; ++j) { const int c = j * 32 + lane; if (j < nper && c < H) { const float d = x[j] - mu; var += d * d; } }
+        for (int j = 0; j < kMaxVec; ++j) {
+            if (j * 32 + lane < nvec) {
+                const float a = x[j].x - mu, b = x[j].y - mu, c = x[j].z - mu, d = x[j].w - mu;
+                var += (a * a + b * b) + (c * c + d * d);
+            }
+        }
         const float rstd = rsqrtf(warp_sum_f32(var) / (float)H + eps);
-        __nv_bfloat16* o = out + (size_t)r * H;
+        uint2* o = reinterpret_cast<uint2*>(out + (size_t)r * H);
 #pragma unroll
-        for (int j = 0; j < kLnMaxPerLane; ++j) { const int c = j * 32 + lane; if (j < nper && c < H) o[c] = __float2bfloat16((x[j] - mu) * rstd * ln_w[c] + ln_b[c]); }
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int c = j * 32 + lane;
+            if (c < nvec) {
+                const float4 w = reinterpret_cast<const float4*>(ln_w)[c], bb = reinterpret_cast<const float4*>(ln_b)[c];
+                __nv_bfloat162 lo = __floats2bfloat162_rn((x[j].x - mu) * rstd * w.x + bb.x, (x[j].y - mu) * rstd * w.y + bb.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn((x[j].z - mu) * rstd * w.z + bb.z, (x[j].w - mu) * rstd * w.w + bb.w);
+                o[c] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
+        }
     }
 }
 
@@ -141,9 +160,9 @@ __global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* x, const
 
 // ---------------------------------------------------------------------------------------------------------
 // attention.  qkv [B*L][3H] bf16 (q | k | v, head h at columns h*64 of each third); ctx [B*L][H] bf16.
-// One CTA = (sequence, head, block of 128 queries): 8 warps x 16 queries.  K and V of the whole sequence are brought into shared
-// memory (row-major, rows padded to 72 bf16) by cp.async in groups of 64 keys, so the first key blocks are being multiplied while the
-// later ones are still in flight; each warp walks the keys in blocks of 64 with an online softmax:
+// One CTA = (sequence, head, block of 128 queries): 8 warps x 16 queries.  K and V stream through a three-stage ring of 64-key blocks
+// (row-major, rows padded to 72 bf16) filled by cp.async two blocks ahead of the products - 57 KB of shared memory, so two CTAs share an
+// SM and one's softmax overlaps the other's MMAs; each warp walks the key blocks with an online softmax:
 //   S = Q K^T        8 n-tiles x 4 k-steps of mma.sync.m16n8k16 (A = Q fragment held in registers, B = K rows by ldmatrix.x4)
 //   P = exp(S - m)   in registers; the accumulator layout of two adjacent n-tiles IS the A-fragment layout of one k-step
 //   O += P V         4 k-steps x 8 n-tiles (B = V by ldmatrix.x4.trans: no transposed copy of V is ever made)
@@ -154,7 +173,9 @@ constexpr int kAttnD = 64;
 constexpr int kAttnQB = 128;
 constexpr int kAttnKPad = 72;          // K / V row stride in bf16 (36 words: conflict-free fragment and ldmatrix loads)
 
-__host__ __device__ inline size_t attention_smem_bytes(int Lp) { return (size_t)2 * Lp * kAttnKPad * 2 + (size_t)Lp * 4; }
+constexpr int kAttnStages = 3;
+constexpr int kAttnStageElems = 2 * 64 * kAttnKPad;      // K block then V block, bf16 elements
+__host__ __device__ inline size_t attention_smem_bytes(int Lp) { return (size_t)kAttnStages * kAttnStageElems * 2 + (size_t)Lp * 4; }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -193,9 +214,8 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {
 __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv, const int32_t* ids, int L, int Lp, int H, int n_heads, int pad_id,
                                                         __nv_bfloat16* ctx) {
     extern __shared__ __align__(16) uint8_t asm_[];
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(asm_);                       // [Lp][72]
-    __nv_bfloat16* Vs = Ks + (size_t)Lp * kAttnKPad;                                  // [Lp][72]
-    float* kmask = reinterpret_cast<float*>(Vs + (size_t)Lp * kAttnKPad);             // [Lp] 0 or -inf
+    __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(asm_);                     // [3 stages][K 64 x 72 | V 64 x 72]
+    float* kmask = reinterpret_cast<float*>(ring + (size_t)kAttnStages * kAttnStageElems);   // [Lp] 0 or -inf
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const size_t row0 = (size_t)b * L;
@@ -203,23 +223,29 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
     const __nv_bfloat16* Qg = qkv + row0 * ld + (size_t)h * kAttnD;
     const __nv_bfloat16* Kg = Qg + H;
     const __nv_bfloat16* Vg = Qg + 2 * H;
-    const int n_blocks = Lp / 64;                              // <= 8 (host: Lp <= 512)
-    // ---- K, V -> shared, one cp.async group per block of 64 keys (keys beyond L: zero rows, mask -inf) ----
-    for (int blk = 0; blk < n_blocks; ++blk) {
-        for (int i = tid; i < 64 * 8; i += 256) {              // 8 x 16-byte chunks per key row
-            const int key = blk * 64 + (i >> 3), ch = i & 7;
-            __nv_bfloat16* kd = Ks + (size_t)key * kAttnKPad + ch * 8;
-            __nv_bfloat16* vd = Vs + (size_t)key * kAttnKPad + ch * 8;
-            if (key < L) {
-                cp_async_16(kd, Kg + (size_t)key * ld + ch * 8);
-                cp_async_16(vd, Vg + (size_t)key * ld + ch * 8);
-            } else {
-                *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
+    const int n_blocks = Lp / 64;
+    // one cp.async group per block of 64 keys (keys beyond L: zero rows, mask -inf); a group is committed even when it is empty so
+    // that "all but the newest group have landed" always means "block blk is there"
+    auto issue_block = [&](int blk) {
+        if (blk < n_blocks) {
+            __nv_bfloat16* st = ring + (size_t)(blk % kAttnStages) * kAttnStageElems;
+            for (int i = tid; i < 64 * 8; i += 256) {          // 8 x 16-byte chunks per key row
+                const int kr = i >> 3, ch = i & 7, key = blk * 64 + kr;
+                __nv_bfloat16* kd = st + (size_t)kr * kAttnKPad + ch * 8;
+                __nv_bfloat16* vd = kd + 64 * kAttnKPad;
+                if (key < L) {
+                    cp_async_16(kd, Kg + (size_t)key * ld + ch * 8);
+                    cp_async_16(vd, Vg + (size_t)key * ld + ch * 8);
+                } else {
+                    *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
+                }
             }
         }
         cp_async_commit();
-    }
+    };
+    issue_block(0);
+    issue_block(1);
     for (int i = tid; i < Lp; i += 256) kmask[i] = (i < L && ids[row0 + i] != pad_id) ? 0.f : -INFINITY;
 
     const int q0 = qb * kAttnQB + warp * 16;                   // this warp's 16 query rows
@@ -246,9 +272,12 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
 
     for (int blk = 0; blk < n_blocks; ++blk) {
         const int kb = blk * 64;
-        cp_async_wait_pending(n_blocks - 1 - blk);             // this thread's copies of blocks 0..blk have landed ...
-        __syncthreads();                                       // ... and everybody else's
+        cp_async_wait_pending(1);                              // this thread's copies of block blk have landed (blk + 1 may be in flight) ...
+        __syncthreads();                                       // ... and everybody else's; and every warp is done with block blk - 1
+        issue_block(blk + 2);                                  // into the stage block blk - 1 has just vacated
         if (!active) continue;
+        const __nv_bfloat16* Ks = ring + (size_t)(blk % kAttnStages) * kAttnStageElems;   // this block's 64 keys
+        const __nv_bfloat16* Vs = Ks + 64 * kAttnKPad;
         float s[8][4];
 #pragma unroll
         for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
@@ -259,7 +288,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
 #pragma unroll
             for (int kp = 0; kp < 2; ++kp) {
                 uint32_t kf[4];
-                ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + lm_row) * kAttnKPad + kp * 32 + lm_mat * 8);
+                ldmatrix_x4(kf, Ks + (size_t)(n * 8 + lm_row) * kAttnKPad + kp * 32 + lm_mat * 8);
                 mma_bf16_16816(s[n], qa[kp * 2], kf[0], kf[1]);
                 mma_bf16_16816(s[n], qa[kp * 2 + 1], kf[2], kf[3]);
             }
@@ -301,7 +330,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
 #pragma unroll
             for (int np = 0; np < 4; ++np) {
                 uint32_t vf[4];
-                ldmatrix_x4_trans(vf, Vs + (size_t)(kb + j * 16 + (lm_mat & 1) * 8 + lm_row) * kAttnKPad + np * 16 + (lm_mat >> 1) * 8);
+                ldmatrix_x4_trans(vf, Vs + (size_t)(j * 16 + (lm_mat & 1) * 8 + lm_row) * kAttnKPad + np * 16 + (lm_mat >> 1) * 8);
                 mma_bf16_16816(o[np * 2], pa[j], vf[0], vf[1]);
                 mma_bf16_16816(o[np * 2 + 1], pa[j], vf[2], vf[3]);
             }

@@ -112,3 +112,30 @@ def test_embed_upsert_equals_embed_then_upsert(lib):
         await a.close(); await b.close()
     asyncio.run(run())
     enc.close()
+
+
+def test_pair_form_of_the_dense_layers_equals_the_single_cta_form(lib, monkeypatch):
+    """Large batches run the dense layers as clusters of two CTAs (tcgen05 cta_group::2, 256-row tiles, each CTA loads half of the
+    weight tile); small ones as single CTAs.  Same K order, same accumulators: the sentence embeddings must agree bit for bit - on a
+    batch whose token count is not a multiple of the 256-row tile - and the large batch must still match the float32 oracle."""
+    from code_rag_b200.embedding import B200CodeEncoder
+    vocab, hidden, layers, heads, inter, max_pos = 2000, 768, 4, 12, 3072, 1026
+    sd = R.random_state_dict(vocab, hidden, layers, inter, max_pos, seed=9)
+    rng = np.random.default_rng(12)
+    B, L = 47, 384                                     # 18,048 tokens = 70.5 tiles of 256 rows
+    ids = rng.integers(3, vocab, size=(B, L)).astype(np.int32)
+    for b in range(1, B):
+        ids[b, int(rng.integers(L // 3, L + 1)):] = 1
+    monkeypatch.setenv("LATTICE_B200_ENCODER_PAIR", "0")
+    single = B200CodeEncoder(sd, n_layers=layers, n_heads=heads, pad_id=1)
+    monkeypatch.setenv("LATTICE_B200_ENCODER_PAIR", "1")
+    pair = B200CodeEncoder(sd, n_layers=layers, n_heads=heads, pad_id=1)
+    try:
+        a, t_single = single.embed_ids(ids), single.last_ms
+        b_, t_pair = pair.embed_ids(ids), pair.last_ms
+        print(f"4 layers, {B} x {L}: single-CTA form {t_single:.3f} ms, CTA-pair form {t_pair:.3f} ms")
+        assert np.array_equal(a, b_)
+        _, exp = R.encode(sd, ids[:6], n_layers=layers, n_heads=heads, pad_id=1)
+        _close(b_[:6], exp, "pair form vs float32 oracle (first 6 sequences)")
+    finally:
+        single.close(); pair.close()
