@@ -21,8 +21,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from code_rag_b200.embedding import B200CodeEncoder  # noqa: E402
-from oracle.roberta_encoder import random_state_dict  # noqa: E402   (weights only: the oracle's forward pass is not used here)
+from code_rag_b200.embedding import B200CodeEncoder, random_state_dict  # noqa: E402
 
 VOCAB, H, LAYERS, HEADS, INTER, MAXPOS = 51416, 768, 12, 12, 3072, 1026
 

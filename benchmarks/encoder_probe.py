@@ -7,8 +7,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from code_rag_b200.embedding import B200CodeEncoder  # noqa: E402
-from oracle.roberta_encoder import random_state_dict  # noqa: E402   (weights only)
+from code_rag_b200.embedding import B200CodeEncoder, random_state_dict  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 512

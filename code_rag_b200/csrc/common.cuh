@@ -155,6 +155,10 @@ __device__ __forceinline__ double load_as_f64(const void* src, int dtype, size_t
     return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
 }
 
+// single-instruction approximations (MUFU): 2^x and 1/x
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // bf16 pair (packed in a 32-bit word, little endian: element 0 in the low half) -> two floats
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

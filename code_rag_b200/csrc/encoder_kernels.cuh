@@ -306,13 +306,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv
         bm1 = fmaxf(bm1, __shfl_xor_sync(0xFFFFFFFFu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xFFFFFFFFu, bm1, 2));
         const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
         // a block of pad keys only leaves the maximum at -inf: keep exp() away from (-inf) - (-inf)
-        const float r0 = nm0 == -INFINITY ? 1.f : exp2f(m0 - nm0), r1 = nm1 == -INFINITY ? 1.f : exp2f(m1 - nm1);
+        const float r0 = nm0 == -INFINITY ? 1.f : ex2_approx(m0 - nm0), r1 = nm1 == -INFINITY ? 1.f : ex2_approx(m1 - nm1);
         const float e0 = nm0 == -INFINITY ? 0.f : nm0, e1 = nm1 == -INFINITY ? 0.f : nm1;
         float ps0 = 0.f, ps1 = 0.f;
         uint32_t pa[4][4];                                     // P as A fragments: k-step j covers keys kb + 16 j .. + 15
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const float p0 = exp2f(s[n][0] - e0), p1 = exp2f(s[n][1] - e0), p2 = exp2f(s[n][2] - e1), p3 = exp2f(s[n][3] - e1);
+            const float p0 = ex2_approx(s[n][0] - e0), p1 = ex2_approx(s[n][1] - e0), p2 = ex2_approx(s[n][2] - e1), p3 = ex2_approx(s[n][3] - e1);
             ps0 += p0 + p1; ps1 += p2 + p3;
             pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0, p1);   // rows g:     a0a1 (keys +0..7) / a4a5 (keys +8..15)
             pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);   // rows g + 8: a2a3 / a6a7

@@ -56,9 +56,9 @@ __host__ __device__ constexpr size_t linear_smem_bytes(bool pair = false) {
 // ex2 and a degree-5 polynomial instead of erff's two branches - the intermediate layer's epilogue is instruction-bound
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
     const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    const float e = fmaf(-poly, __expf(-z * z), 1.0f);          // erf(|x| / sqrt 2)
+    const float e = fmaf(-poly, ex2_approx(-1.4426950408889634f * z * z), 1.0f);   // erf(|x| / sqrt 2)
     return 0.5f * x * (1.0f + copysignf(e, x));
 }
 

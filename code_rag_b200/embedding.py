@@ -147,6 +147,29 @@ class B200CodeEncoder:
             pass
 
 
+def random_state_dict(vocab: int, hidden: int, n_layers: int, inter: int, max_pos: int, seed: int, pad_id: int = 1) -> dict[str, np.ndarray]:
+    """Random RobertaModel-shaped weights (Hugging Face parameter names) for benchmarks and smoke runs - there is no checkpoint in an
+    offline image.  Dense weights ~ N(0, 1/in) so that activations stay O(1) through every layer; LayerNorm weights near 1."""
+    import math
+    rng = np.random.default_rng(seed)
+    n = lambda *s: (0.02 * rng.standard_normal(s)).astype(np.float32)  # noqa: E731
+    sd = {"embeddings.word_embeddings.weight": n(vocab, hidden), "embeddings.position_embeddings.weight": n(max_pos, hidden),
+          "embeddings.token_type_embeddings.weight": n(1, hidden),
+          "embeddings.LayerNorm.weight": (1 + 0.1 * rng.standard_normal(hidden)).astype(np.float32), "embeddings.LayerNorm.bias": n(hidden)}
+    sd["embeddings.word_embeddings.weight"][pad_id] = 0
+    shapes = {"attention.self.query": (hidden, hidden), "attention.self.key": (hidden, hidden), "attention.self.value": (hidden, hidden),
+              "attention.output.dense": (hidden, hidden), "intermediate.dense": (inter, hidden), "output.dense": (hidden, inter)}
+    for layer in range(n_layers):
+        p = f"encoder.layer.{layer}."
+        for name, (o, i) in shapes.items():
+            sd[p + name + ".weight"] = (rng.standard_normal((o, i)) / math.sqrt(i)).astype(np.float32)
+            sd[p + name + ".bias"] = n(o)
+        for name in ("attention.output.LayerNorm", "output.LayerNorm"):
+            sd[p + name + ".weight"] = (1 + 0.1 * rng.standard_normal(hidden)).astype(np.float32)
+            sd[p + name + ".bias"] = n(hidden)
+    return sd
+
+
 def _to_numpy(v):
     if isinstance(v, np.ndarray):
         return v
