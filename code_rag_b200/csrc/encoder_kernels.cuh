@@ -211,7 +211,7 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {
     }
 }
 
-__global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* qkv, const int32_t* ids, int L, int Lp, int H, int n_heads, int pad_id,
+__global__ void __launch_bounds__(256, 2) attention_kernel(const __nv_bfloat16* qkv, const int32_t* ids, int L, int Lp, int H, int n_heads, int pad_id,
                                                         __nv_bfloat16* ctx) {
     extern __shared__ __align__(16) uint8_t asm_[];
     __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(asm_);                     // [3 stages][K 64 x 72 | V 64 x 72]
