@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* x, const
 //   P = exp(S - m)   in registers; the accumulator layout of two adjacent n-tiles IS the A-fragment layout of one k-step
 //   O += P V         4 k-steps x 8 n-tiles (B = V by ldmatrix.x4.trans: no transposed copy of V is ever made)
 // Pad keys get -inf before the softmax (the reference masks them: mask.unsqueeze(1) * mask.unsqueeze(2)); pad query rows are
-// computed like the others and dropped by the pooling.
+// dropped by the pooling.  Chunks are ragged: key blocks behind a sequence's last real token are skipped (their probabilities are
+// exactly zero) and query blocks that hold only padding write zeros instead of attending.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAttnD = 64;
 constexpr int kAttnQB = 128;
@@ -223,7 +224,29 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const __nv_bfloat16* 
     const __nv_bfloat16* Qg = qkv + row0 * ld + (size_t)h * kAttnD;
     const __nv_bfloat16* Kg = Qg + H;
     const __nv_bfloat16* Vg = Qg + 2 * H;
-    const int n_blocks = Lp / 64;
+    // the sequence's extent: index of its last non-pad token + 1 (pads may sit anywhere, but everything behind `len` is padding)
+    __shared__ int s_len;
+    if (tid == 0) s_len = 0;
+    __syncthreads();
+    {
+        int last = 0;
+        for (int i = tid; i < L; i += 256) if (ids[row0 + i] != pad_id) last = i + 1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, o));
+        if (lane == 0 && last) atomicMax(&s_len, last);
+    }
+    __syncthreads();
+    const int len = s_len;
+    if (qb * kAttnQB >= len) {
+        // nothing but padding in this query block: finite, deterministic rows for the layers that follow (0 x NaN would poison the
+        // next layer's P V product through these rows' V values)
+        for (int i = tid; i < kAttnQB * 8; i += 256) {
+            const int r = qb * kAttnQB + (i >> 3);
+            if (r < L) *reinterpret_cast<uint4*>(ctx + (row0 + r) * H + (size_t)h * kAttnD + (i & 7) * 8) = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+    const int n_blocks = (len + 63) / 64;                      // key blocks that hold at least one real token
     // one cp.async group per block of 64 keys (keys beyond L: zero rows, mask -inf); a group is committed even when it is empty so
     // that "all but the newest group have landed" always means "block blk is there"
     auto issue_block = [&](int blk) {
