@@ -115,8 +115,10 @@ class _HostCollection:
         self.lock = threading.Lock()
         # dev_factory exists so that the host-side bookkeeping can be unit-tested without a GPU (tests only)
         factory = dev_factory or DeviceCollection
+        # timing off: no CUDA events around the kernels, so a search completes through the word its kernel stores into the pinned
+        # slot (lower latency) and consecutive searches of concurrent awaits overlap on the GPU
         self.dev = factory(name, dim, storage=storage, metric="cosine", n_filter_cols=N.MAX_FILTER_COLS,
-                           capacity=0, device=device)
+                           capacity=0, device=device, timing=False)
 
     # -- dictionary encoding ---------------------------------------------------------------------------
     def _encode_value(self, col: int, value: Any, create: bool) -> int:

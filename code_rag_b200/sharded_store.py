@@ -366,7 +366,7 @@ class ShardPlane:
         else:
             factory = self._device_factory
         shard = factory(name, dim, storage=storage, metric="cosine", n_filter_cols=n_cols, capacity=0,
-                        row_base=self.rank << SHARD_BITS, device=self.device)
+                        row_base=self.rank << SHARD_BITS, device=self.device, timing=False)
         self.shards[name] = shard
         self._attach_searcher(name, shard)
         return None

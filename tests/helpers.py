@@ -13,7 +13,7 @@ ANY = 0xFFFFFFFF
 class FakeDevice:
     """Same methods as code_rag_b200.collection.DeviceCollection; arithmetic by the oracle.  TESTS ONLY."""
 
-    def __init__(self, name, dim, storage="f32", metric="cosine", n_filter_cols=0, capacity=0, row_base=0, device=0):
+    def __init__(self, name, dim, storage="f32", metric="cosine", n_filter_cols=0, capacity=0, row_base=0, device=0, timing=True):
         self.name, self.dim, self.n_filter_cols = name, dim, n_filter_cols
         self.ora = OracleCollection(dim)
         self.codes = np.zeros((0, n_filter_cols), dtype=np.uint32)
