@@ -274,12 +274,17 @@ static int forward(lvs_encoder* e, int B, int L) {
     LVS_CU(cudaGetLastError());
     const int Lp = (L + 63) / 64 * 64;
     const size_t asmem = attention_smem_bytes(Lp);
-    if (asmem > lvs_lib_smem_optin()) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens do not fit the attention kernel's shared memory", L);
+    if (asmem + 1024 > lvs_lib_smem_optin()) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens do not fit the attention kernel's shared memory", L);
     {
         static std::once_flag once;
         static cudaError_t once_err = cudaSuccess;
         const int optin = (int)lvs_lib_smem_optin();
-        std::call_once(once, [optin] { once_err = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin); });
+        std::call_once(once, [optin] {
+            cudaFuncAttributes fa;                 // the kernel has a word of static shared memory: the opt-in limit covers both
+            once_err = cudaFuncGetAttributes(&fa, attention_kernel);
+            if (once_err == cudaSuccess)
+                once_err = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+        });
         if (once_err != cudaSuccess) return lvs_fail(LVS_ECUDA, "encoder: cudaFuncSetAttribute failed: %s", cudaGetErrorString(once_err));
     }
     const unsigned ln_grid = (unsigned)std::min<int64_t>((M + 7) / 8, (int64_t)lvs_lib_sm_count() * 8);
