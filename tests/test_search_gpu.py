@@ -589,3 +589,42 @@ def test_fetch_rows_returns_what_the_shard_holds(lib, storage):
         a, b = dev.search(q[i].astype(np.float64), 10), other.search(q[i].astype(np.float64), 10)
         assert np.array_equal(a.rows, b.rows) and np.abs(a.scores - b.scores).max() < 1e-6
     dev.close(); other.close()
+
+
+def test_pipelined_sharded_submit_on_one_rank_and_repeat_at(lib):
+    """lvs_search_submit_sharded / lvs_search_wait with a world of one rank (host buffers in, merged lists out, completion by the word
+    the kernel stores into the pinned slot), four searches in flight; and lvs_search_device_at: a repeat numbered as the search it
+    repeats returns exactly what the first attempt returned, without advancing the search counter."""
+    import ctypes as C
+
+    import torch
+    x, q = synth.unixcoder_like(12_000, 256, seed=44, n_queries=9)
+    ora = OracleCollection(256)
+    ora.upsert_rows_f32(0, x, [None] * len(x))
+    dev = _dev("subsh", 256, timing=False)
+    dev.upsert(x.astype(np.float64))
+    ex = _exchange_world1(lib, 4, 16)
+    tickets = [dev.search_submit_sharded(ex, q[i].astype(np.float64), 10) for i in range(4)]       # all four slots in flight
+    got = [dev.search_wait(t) for t in tickets]
+    tickets = [dev.search_submit_sharded(ex, q[4:7].astype(np.float64), 10), dev.search_submit_sharded(ex, q[7].astype(np.float64), 5)]
+    got += [dev.search_wait(t) for t in tickets]
+    exp = [ora.search_topk_rows(q[i].astype(np.float64), 10) for i in range(7)] + [ora.search_topk_rows(q[7].astype(np.float64), 5)]
+    for i in range(4):
+        _assert_same(got[i], 0, *exp[i], REL_F32)
+    for j in range(3):
+        _assert_same(got[4], j, *exp[4 + j], REL_F32)
+    _assert_same(got[5], 0, *exp[7], REL_F32)
+    assert lib.lvs_exchange_error(ex) == 0 and dev.search_counter == 8
+    # repeat search number 3 (query 2): same scores bit for bit, counter untouched
+    dq = torch.from_numpy(q[2:3].astype(np.float64)).cuda()
+    s = torch.zeros((1, 10), dtype=torch.float64, device="cuda"); r = torch.zeros((1, 10), dtype=torch.int64, device="cuda")
+    t = torch.zeros((1, 10), dtype=torch.int64, device="cuda"); c = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flags = np.zeros(1, dtype=np.int32)
+    torch.cuda.synchronize()
+    dev.search_device_at(3, dq.data_ptr(), "f64", 1, 10, None, s.data_ptr(), r.data_ptr(), t.data_ptr(), c.data_ptr(), flags)
+    assert np.array_equal(r.cpu().numpy()[0], got[2].rows[0]) and np.array_equal(s.cpu().numpy()[0], got[2].scores[0])
+    assert flags[0] == 0 and dev.search_counter == 8
+    with pytest.raises(Exception):
+        dev.search_device_at(99, dq.data_ptr(), "f64", 1, 10, None, s.data_ptr(), r.data_ptr(), t.data_ptr(), c.data_ptr(), flags)
+    lib.lvs_exchange_destroy(ex)
+    dev.close()
