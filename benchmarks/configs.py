@@ -72,7 +72,16 @@ def c1():
     dev.upsert(x)
     qs = (mu + rng.standard_normal((32, 1, dim)))
     _, wall, scan, total = timed(dev, qs, 10, None, 200)
+    # the same calls without CUDA events around the kernel: the search completes through the word its kernel stores into the pinned slot
+    dev.set_option("timing", 0)
+    walls = []
+    for i in range(230):
+        t0 = time.perf_counter()
+        dev.search(qs[i % len(qs)], 10)
+        if i >= 30:
+            walls.append((time.perf_counter() - t0) * 1e3)
     emit("C1 10k x 768 fp32, Q=1, top-10 (L2-resident: latency config)", wall_ms=wall, scan_ms=scan, device_ms=total,
+         wall_ms_no_events=statistics.median(walls), wall_ms_no_events_p10=sorted(walls)[len(walls) // 10],
          qps=1e3 / wall, bytes_per_pass=n * dim * 4)
     dev.close()
 
