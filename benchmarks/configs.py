@@ -80,7 +80,15 @@ def c1():
         dev.search(qs[i % len(qs)], 10)
         if i >= 30:
             walls.append((time.perf_counter() - t0) * 1e3)
-    emit("C1 10k x 768 fp32, Q=1, top-10 (L2-resident: latency config)", wall_ms=wall, scan_ms=scan, device_ms=total,
+    dev.set_option("dbg_times", 1)
+    ph = []
+    for i in range(20):
+        dev.search(qs[i % len(qs)], 10)
+        ph.append(dev.last_kernel_phases())
+    dev.set_option("dbg_times", 0)
+    phases = dict(zip(("queries_ready", "scanned", "list_written", "lists_visible", "rescored", "ordered", "stored"),
+                      [round(float(v), 2) for v in np.median(np.array(ph), axis=0)]))
+    emit("C1 10k x 768 fp32, Q=1, top-10 (L2-resident: latency config)", wall_ms=wall, scan_ms=scan, device_ms=total, kernel_phases_us=phases,
          wall_ms_no_events=statistics.median(walls), wall_ms_no_events_p10=sorted(walls)[len(walls) // 10],
          qps=1e3 / wall, bytes_per_pass=n * dim * 4)
     dev.close()

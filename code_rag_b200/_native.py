@@ -64,6 +64,7 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_search_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device_at": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_last_kernel_phases": (C.c_int, [_vp, _u64p]),
     "lvs_scan_times": (C.c_int, [_vp, C.c_int, _f32p, _f64p, _ip]),
     "lvs_match_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "lvs_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),

@@ -84,8 +84,15 @@ def _id_sort_key(point_id: Any):
     return (0, point_id, "") if isinstance(point_id, int) else (1, 0, point_id)
 
 
+_INLINE_SEARCH_BYTES = 256 << 20      # shards up to this size (a ~50 us scan) are searched without leaving the event loop's thread
+
+
 class _HostCollection:
     """Host half of a collection: ids, payloads and the per-column value dictionaries."""
+
+    def inline_bytes(self) -> int:
+        """Bytes one search has to stream (decides whether ``B200VectorStore.search`` hops to a worker thread)."""
+        return len(self.ids) * self.dim * (2 if getattr(self.dev, "storage", "f32") == "bf16" else 4)
 
     def __init__(self, name: str, dim: int, storage: str, index_fields: Sequence[str], device: int, dev_factory=None,
                  rank_kind: str | None = None, rank_dicts: tuple[dict, dict, dict] | None = None):
@@ -738,7 +745,17 @@ class B200VectorStore:
             def work():
                 with coll.lock:
                     return coll.search(q, limit, filters or None)[0]
-            results = await asyncio.to_thread(work)
+            # A small collection (lattice's usual operating point: 10^4 - 10^5 chunks) answers in ~0.1 ms: hopping to a worker thread
+            # and back costs about as much as the search itself, so it runs inline when nobody else holds the collection; anything
+            # larger, or a contended collection, goes to a thread and leaves the event loop free (threading).
+            inline = getattr(coll, "inline_bytes", None)
+            if inline is not None and inline() <= _INLINE_SEARCH_BYTES and coll.lock.acquire(blocking=False):
+                try:
+                    results = coll.search(q, limit, filters or None)[0]
+                finally:
+                    coll.lock.release()
+            else:
+                results = await asyncio.to_thread(work)
             logger.debug(f"Found {len(results)} results in {collection}")
             return results
         except Exception as e:  # noqa: BLE001

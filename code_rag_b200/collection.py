@@ -382,6 +382,13 @@ class DeviceCollection:
                                                           C.c_void_p(out_ptr), C.c_void_p(counts_ptr), C.c_void_p(flags_ptr),
                                                           C.c_void_p(stream or None)), "lvs_search_sharded_device_async")
 
+    def last_kernel_phases(self) -> np.ndarray:
+        """Profiling aid (``set_option("dbg_times", 1)`` first): microseconds from the first CTA's start to each phase of the last
+        scan-kernel launch (queries ready, shard scanned, list written, lists visible, rescoring done, result ordered, result stored)."""
+        ns = np.zeros(8, dtype=np.uint64)
+        N.check(self._lib.lvs_last_kernel_phases(self._handle(), ns.ctypes.data_as(C.POINTER(C.c_uint64))), "lvs_last_kernel_phases")
+        return (ns[1:].astype(np.int64) - np.int64(ns[0])) / 1e3
+
     def scan_times(self, max_n: int = 256) -> tuple[np.ndarray, np.ndarray]:
         """(ms, algorithmic bytes) of the last scan-kernel launches (CUDA events on the launching stream)."""
         ms = np.zeros(max_n, dtype=np.float32)

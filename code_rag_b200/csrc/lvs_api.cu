@@ -136,6 +136,8 @@ struct lvs_collection {
     uint32_t tile_base[2] = {0, 0};   // what the two tile counters (launch parity) stand at
     Scratch s_qstage;                 // host queries staged by CTA 0, one slot per launch parity
     int opt_dyn_tiles = 1;
+    int opt_dbg_times = 0;            // 1: the scan kernel stamps its phases (lvs_last_kernel_phases)
+    Scratch s_dbg_times;
     Scratch h_pin, h_pin2, h_flags;
 
     // ring of event pairs around the scan launches (read back by lvs_scan_times after a synchronisation)
@@ -372,7 +374,7 @@ extern "C" int lvs_collection_destroy(lvs_collection* c) {
     free_arrays(c);
     cudaFree(c->d_max_norm); cudaFree(c->d_pw); cudaFree(c->d_counter);
     Scratch* ds[] = {&c->s_qraw, &c->s_q64, &c->s_q32, &c->s_qnorm, &c->s_keys, &c->s_mins, &c->s_flags, &c->s_res, &c->s_stage_dev, &c->s_misc,
-                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg, &c->s_geps, &c->s_xlocal, &c->s_qstage};
+                     &c->s_gkeys, &c->s_gtops, &c->s_gdrops, &c->s_qb16, &c->s_tickets, &c->s_dbg, &c->s_geps, &c->s_xlocal, &c->s_qstage, &c->s_dbg_times};
     if (c->order_ev) cudaEventDestroy(c->order_ev);
     for (Scratch* s : ds) if (s->p) cudaFree(s->p);
     if (c->h_pin.p) cudaFreeHost(c->h_pin.p);
@@ -898,6 +900,12 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_hos
         const uint32_t cq = std::max<uint32_t>(1u, std::min<uint32_t>(8u / (uint32_t)cnt, (kpw + nrw - 1) / nrw));
         sp.ticket = c->d_counter + 4; sp.n_helpers = (uint32_t)cnt * cq;
         sp.host_ready = out.host_ready; sp.host_ready_val = out.host_ready_val;
+        if (c->opt_dbg_times) {
+            if ((rc = ensure_dev(c->s_dbg_times, 64)) != LVS_OK) return rc;
+            CU(cudaMemsetAsync(c->s_dbg_times.p, 0xFF, 8, st));                       // slot 0 takes a minimum
+            CU(cudaMemsetAsync((uint8_t*)c->s_dbg_times.p + 8, 0, 56, st));
+            sp.dbg_times = (unsigned long long*)c->s_dbg_times.p;
+        }
         const bool dyn = !filter && grid == sm && c->opt_dyn_tiles;       // dynamic tile scheduling needs one CTA per SM (see the kernel)
         if (dyn) { sp.tile_counter = c->d_counter + 6 + (seq & 1u); sp.tile_base = c->tile_base[seq & 1u]; }
         sp.pdl = c->opt_pdl && !c->opt_timing ? 1u : 0u;
@@ -2264,6 +2272,16 @@ extern "C" int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* 
     return LVS_OK;
 }
 
+extern "C" int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns8) {
+    bind_thread();
+    if (!c || !ns8) return fail(LVS_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->s_dbg_times.p) return fail(LVS_ESTATE, "option dbg_times was not set before the search");
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(ns8, c->s_dbg_times.p, 64, cudaMemcpyDeviceToHost));
+    return LVS_OK;
+}
+
 extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     bind_thread();
     if (!c || !name) return fail(LVS_EINVAL, "NULL argument");
@@ -2275,6 +2293,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "timing")) c->opt_timing = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) c->opt_pdl = value ? 1 : 0;
     else if (!strcmp(name, "dyn_tiles")) c->opt_dyn_tiles = value ? 1 : 0;
+    else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value ? 1 : 0;
     else if (!strcmp(name, "gemm_min_q")) c->opt_gemm_min_q = value;
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;

@@ -76,6 +76,7 @@ struct ScanParams {
     void* q_stage;              //   them here (device) for everybody, then publishes *q_flag = seq; q_raw == q_stage
     uint32_t* q_flag;
     uint32_t q_bytes;           // n_queries * dim * sizeof(query element)
+    unsigned long long* dbg_times;  // optional [8]: globaltimer stamps of the launch's phases (min of the starts, max of the rest); profiling aid
     uint32_t* host_ready;       // optional word in mapped pinned host memory: set to host_ready_val (system-scope release) when every
     uint32_t host_ready_val;    //   result of this launch has been stored - the host polls it instead of synchronising an event
     uint32_t* ticket;           // [2] arrival counters of this launch's CTAs, zero between launches
@@ -183,6 +184,17 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase stamp of the profiling aid (option "dbg_times"): slot 0 keeps the earliest, the others the latest time any CTA got there
+__device__ __forceinline__ void stamp(unsigned long long* times, int slot) {
+    if (times == nullptr) return;
+    if (slot == 0) atomicMin(times, global_ns()); else atomicMax(times + slot, global_ns());
+}
+
 __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -223,6 +235,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     const int lane = tid & 31;
 
     if (tid == 0) {
+        stamp(p.dbg_times, 0);
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kScanConsumerWarps);
@@ -364,6 +377,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
         }
     }
     named_bar_sync(1, 256);
+    if (tid == 0) stamp(p.dbg_times, 1);                  // queries ready
 
     WarpTopK<KPL> top[QT];
 #pragma unroll
@@ -455,6 +469,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
         ++it;
     }
 
+    if (tid == 0) stamp(p.dbg_times, 2);                  // this CTA's share of the shard is scanned
     // ============== CTA epilogue: merge the 8 warp lists of each query, write one list per CTA ==============
     // From here on the kernel writes memory that the previous search on this stream also used (lists, tickets, candidate
     // scores): wait until that search has completed (it has, long ago, unless this shard is tiny).
@@ -523,7 +538,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     // ============== ticket: the last H CTAs to finish stay and finalize ==============
     __threadfence();
     named_bar_sync(1, NCT);
-    if (tid == 0) s_bcast[0] = atomicAdd(p.ticket, 1u);
+    if (tid == 0) { s_bcast[0] = atomicAdd(p.ticket, 1u); stamp(p.dbg_times, 3); }      // list written, ticket taken
     named_bar_sync(1, NCT);
     const uint32_t G = gridDim.x;
     const uint32_t n_items = p.n_helpers;                 // (query, CTA-of-the-query) work items: n_queries * C
@@ -536,6 +551,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
         named_bar_sync(1, NCT);
     }
     __threadfence();
+    if (tid == 0) stamp(p.dbg_times, 4);                  // helper: every list is there
 
     const uint32_t nq = p.n_queries;
     const uint32_t C = n_items / nq;
@@ -547,7 +563,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
         named_bar_sync(1, NCT);                           // the previous item's shared memory is no longer read
         for (int e = tid; e < p.dim; e += NCT) qs[e] = load_as_f64(p.q_raw, p.q_dtype, (size_t)qi * p.dim + e) / s_div[qi];
         FinResult r;
-        if (!finalize_body<KPL, true>(fp, qi, cy, C, smem, s_qnorm[qi], r)) continue;
+        const bool mine = finalize_body<KPL, true>(fp, qi, cy, C, smem, s_qnorm[qi], r);
+        if (tid == 0) stamp(p.dbg_times, mine ? 6 : 5);   // 5: a helper's share of the rescoring is done; 6: the result is ordered
+        if (!mine) continue;
         owned |= 1u << qi;
         if (!p.exchange) { finalize_store_local(fp, qi, r, tid); continue; }
         // sharded collection: this query's local top-k (+ its flag) -> every rank's gather buffer
@@ -588,6 +606,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     // for host-polled searches, in host memory (every result store above is fenced at system scope before its CTA checks out)
     if (p.host_ready != nullptr) __threadfence_system();
     named_bar_sync(1, NCT);
+    if (tid == 0) stamp(p.dbg_times, 7);                  // results stored (and merged)
     if (tid == 0 && atomicAdd(p.ticket + 1, 1u) == H - 1) {
         p.ticket[0] = 0; p.ticket[1] = 0;
         __threadfence();

@@ -280,6 +280,10 @@ int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches,
 /* Device time of the last (up to max_n, <= 256) scan-kernel launches, oldest first, from CUDA events recorded on the
  * launching stream, with the algorithmic bytes of each launch.  The stream must have been synchronised. */
 int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n);
+/* Profiling aid (option "dbg_times" = 1): globaltimer stamps (ns) of the phases of the last scan-kernel launch on this handle -
+ * [0] first CTA starts, then the LATEST CTA to reach: [1] queries normalised, [2] shard scanned, [3] list written, [4] helpers see every
+ * list, [5] rescoring shares done, [6] result ordered, [7] result stored / merged. */
+int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns8);
 /* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record CUDA events around every scan launch for
  * lvs_last_search_timing / lvs_scan_times; default 0; it serialises consecutive searches), "pdl" (1 = programmatic dependent launch
  * of the scan kernel, default),
