@@ -74,22 +74,44 @@ def c1():
     _, wall, scan, total = timed(dev, qs, 10, None, 200)
     # the same calls without CUDA events around the kernel: the search completes through the word its kernel stores into the pinned slot
     dev.set_option("timing", 0)
-    walls = []
-    for i in range(230):
+    names = ("queries_ready", "scanned", "list_written", "lists_visible", "selected", "rescored", "stored", "sel_loaded", "sel_threshold",
+             "sel_gathered", "scores_collected", "ordered", "host_told", "rows_staged", "replayed")
+    variants = {}
+    for label, inline in (("query_in_kernel_params", 1), ("query_staged_by_cta0", 0)):
+        dev.set_option("inline_query", inline)
+        w = []
+        for i in range(230):
+            t0 = time.perf_counter()
+            dev.search(qs[i % len(qs)], 10)
+            if i >= 30:
+                w.append((time.perf_counter() - t0) * 1e3)
+        dev.set_option("dbg_times", 1)
+        ph = []
+        for i in range(20):
+            dev.search(qs[i % len(qs)], 10)
+            ph.append(dev.last_kernel_phases())
+        dev.set_option("dbg_times", 0)
+        variants[label] = {"wall_ms": statistics.median(w), "wall_ms_p10": sorted(w)[len(w) // 10],
+                           "kernel_phases_us": dict(zip(names, [round(float(v), 2) for v in np.median(np.array(ph), axis=0)]))}
+    dev.set_option("inline_query", 1)
+    walls = [variants["query_in_kernel_params"]["wall_ms"]]
+    # the C-ABI call alone (include/lvs.h: lvs_search), arguments prepared once: what a compiled host pays
+    from code_rag_b200 import _native as N
+    from code_rag_b200.collection import _result_block
+    q0 = np.ascontiguousarray(qs[0], dtype=np.float64)
+    block, (ps, pr, pt, pc, pf) = _result_block(1, 10)
+    lib, h, qa = dev._lib, dev._handle(), q0.ctypes.data
+    cw = []
+    for i in range(330):
         t0 = time.perf_counter()
-        dev.search(qs[i % len(qs)], 10)
+        rc = lib.lvs_search(h, qa, N.DT_F64, 1, 10, None, ps, pr, pt, pc, pf)
         if i >= 30:
-            walls.append((time.perf_counter() - t0) * 1e3)
-    dev.set_option("dbg_times", 1)
-    ph = []
-    for i in range(20):
-        dev.search(qs[i % len(qs)], 10)
-        ph.append(dev.last_kernel_phases())
-    dev.set_option("dbg_times", 0)
-    phases = dict(zip(("queries_ready", "scanned", "list_written", "lists_visible", "rescored", "ordered", "stored"),
-                      [round(float(v), 2) for v in np.median(np.array(ph), axis=0)]))
+            cw.append((time.perf_counter() - t0) * 1e3)
+        assert rc == 0
+    variants["c_abi_call_only"] = {"wall_ms": statistics.median(cw), "wall_ms_p10": sorted(cw)[len(cw) // 10]}
+    phases = variants["query_in_kernel_params"]["kernel_phases_us"]
     emit("C1 10k x 768 fp32, Q=1, top-10 (L2-resident: latency config)", wall_ms=wall, scan_ms=scan, device_ms=total, kernel_phases_us=phases,
-         wall_ms_no_events=statistics.median(walls), wall_ms_no_events_p10=sorted(walls)[len(walls) // 10],
+         wall_ms_no_events=walls[0], wall_ms_no_events_p10=variants["query_in_kernel_params"]["wall_ms_p10"], no_events=variants,
          qps=1e3 / wall, bytes_per_pass=n * dim * 4)
     dev.close()
 

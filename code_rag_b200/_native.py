@@ -9,7 +9,7 @@ from .errors import NativeLibraryError
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "liblattice_b200.so"
 
-OK, EINVAL, ECUDA, ENOMEM, ESTATE, ELIMIT = 0, -1, -2, -3, -4, -5
+OK, EINVAL, ECUDA, ENOMEM, ESTATE, ELIMIT, ENAN = 0, -1, -2, -3, -4, -5, -6
 STORAGE_F32, STORAGE_BF16 = 0, 1
 METRIC_COSINE, METRIC_DOT = 0, 1
 DT_F32, DT_F64, DT_BF16 = 0, 1, 2
@@ -146,6 +146,8 @@ def last_error() -> str:
 
 
 def check(rc: int, what: str) -> None:
+    if rc == ENAN:
+        raise ValueError(last_error())          # "Query vector must not contain NaN", as local mode says it
     if rc != OK:
         raise NativeLibraryError(f"{what} failed (code {rc}): {last_error()}")
 

@@ -8,7 +8,6 @@ arithmetic on this path and no fallback when the library or the GPU is missing.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 
 import numpy as np
 
@@ -20,13 +19,60 @@ _STORAGE = {"f32": N.STORAGE_F32, "fp32": N.STORAGE_F32, "float32": N.STORAGE_F3
 _METRIC = {"cosine": N.METRIC_COSINE, "dot": N.METRIC_DOT}
 
 
-@dataclass
 class SearchResult:
-    scores: np.ndarray   # float64 [Q, k]
-    rows: np.ndarray     # int64   [Q, k]  global rows, -1 padded
-    ties: np.ndarray     # uint64  [Q, k]
-    counts: np.ndarray   # uint32  [Q]
-    flags: np.ndarray    # int32   [Q]     bit0 = exactness not proven
+    """Top-k lists of a batch of queries: ``scores`` float64 [Q, k], ``rows`` int64 [Q, k] (global rows, -1 padded), ``ties`` uint64
+    [Q, k], ``counts`` uint32 [Q], ``flags`` int32 [Q] (bit0 = exactness not proven).  Built either from the five arrays or from
+    the one block the library fills (scores | rows | ties | counts | flags), which is only taken apart when a field is read -
+    a single-query search is tens of microseconds, numpy views are one each."""
+    __slots__ = ("_f", "_block", "_Q", "_k")
+    _NAMES = ("scores", "rows", "ties", "counts", "flags")
+
+    def __init__(self, scores=None, rows=None, ties=None, counts=None, flags=None):
+        self._f = [scores, rows, ties, counts, flags]
+        self._block = None
+        self._Q = self._k = 0
+
+    @classmethod
+    def from_block(cls, block, Q: int, k: int) -> "SearchResult":
+        r = cls.__new__(cls)
+        r._f = None
+        r._block, r._Q, r._k = block, Q, k
+        return r
+
+    def _fields(self):
+        if self._f is None:
+            Q, k = self._Q, self._k
+            n = Q * k
+            a = np.frombuffer(self._block, dtype=np.int64)
+            tail = a[3 * n:].view(np.uint32)
+            self._f = [a[:n].view(np.float64).reshape(Q, k), a[n:2 * n].reshape(Q, k), a[2 * n:3 * n].view(np.uint64).reshape(Q, k),
+                       tail[:Q], tail[Q:2 * Q].view(np.int32)]
+        return self._f
+
+    scores = property(lambda self: self._fields()[0], lambda self, v: self._fields().__setitem__(0, v))
+    rows = property(lambda self: self._fields()[1], lambda self, v: self._fields().__setitem__(1, v))
+    ties = property(lambda self: self._fields()[2], lambda self, v: self._fields().__setitem__(2, v))
+    counts = property(lambda self: self._fields()[3], lambda self, v: self._fields().__setitem__(3, v))
+    flags = property(lambda self: self._fields()[4], lambda self, v: self._fields().__setitem__(4, v))
+
+    def __repr__(self) -> str:
+        return "SearchResult(" + ", ".join(f"{n}={v!r}" for n, v in zip(self._NAMES, self._fields())) + ")"
+
+
+def _result_block(Q: int, k: int):
+    """(ctypes block, the five addresses lvs_search / lvs_search_wait write to)."""
+    n = Q * k
+    block = (C.c_int64 * (3 * n + Q))()
+    base = C.addressof(block)
+    return block, (base, base + 8 * n, base + 16 * n, base + 24 * n, base + 24 * n + 4 * Q)
+
+
+def _addr(a: np.ndarray) -> int:
+    """Address of a contiguous array's data (the cheap way when the array is writable)."""
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError):
+        return a.ctypes.data
 
 
 def _np_dtype_code(a: np.ndarray) -> int:
@@ -216,27 +262,25 @@ class DeviceCollection:
         return out[:min(cap, nm.value)].copy(), int(nm.value)
 
     # ---- search ---------------------------------------------------------------------------------------
-    def search(self, queries: np.ndarray, k: int, want=None) -> SearchResult:
+    def _queries(self, queries) -> np.ndarray:
         q = np.ascontiguousarray(queries)
         if q.ndim == 1:
             q = q[None, :]
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
-        if q.dtype not in (np.float32, np.float64):
+        if q.dtype != np.float64 and q.dtype != np.float32:
             q = q.astype(np.float64)
-        if np.isnan(q).any():
-            raise ValueError("Query vector must not contain NaN")   # local mode asserts the same
+        return q
+
+    def search(self, queries: np.ndarray, k: int, want=None) -> SearchResult:
+        """NaN in a query raises ValueError (the library checks while it copies the queries into its pinned slot)."""
+        q = self._queries(queries)
         Q = q.shape[0]
         k = int(k)
-        scores = np.zeros((Q, k), dtype=np.float64)
-        rows = np.full((Q, k), -1, dtype=np.int64)
-        ties = np.zeros((Q, k), dtype=np.uint64)
-        counts = np.zeros(Q, dtype=np.uint32)
-        flags = np.zeros(Q, dtype=np.int32)
-        w = self._want(want)
-        N.check(self._lib.lvs_search(self._handle(), _ptr(q), _np_dtype_code(q), Q, k, _ptr(w), _ptr(scores), _ptr(rows),
-                                     _ptr(ties), _ptr(counts), _ptr(flags)), "lvs_search")
-        return SearchResult(scores, rows, ties, counts, flags)
+        block, (ps, pr, pt, pc, pf) = _result_block(Q, k)
+        N.check(self._lib.lvs_search(self._handle(), _addr(q), N.DT_F64 if q.dtype == np.float64 else N.DT_F32, Q, k, _ptr(self._want(want)),
+                                     ps, pr, pt, pc, pf), "lvs_search")
+        return SearchResult.from_block(block, Q, k)
 
     # ---- fused search -> rank (include/lvs.h: lvs_rank_names_append / lvs_rank_attrs_set / lvs_search_rank) ----------
     def rank_names_append(self, names: list[bytes]) -> int:
@@ -300,18 +344,10 @@ class DeviceCollection:
 
     def search_submit(self, queries: np.ndarray, k: int, want=None) -> tuple[int, int, int]:
         """Pipelined search: returns a ticket for :meth:`search_wait`; up to 4 searches may be in flight."""
-        q = np.ascontiguousarray(queries)
-        if q.ndim == 1:
-            q = q[None, :]
-        if q.ndim != 2 or q.shape[1] != self.dim:
-            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
-        if q.dtype not in (np.float32, np.float64):
-            q = q.astype(np.float64)
-        if np.isnan(q).any():
-            raise ValueError("Query vector must not contain NaN")
+        q = self._queries(queries)
         t = C.c_int()
-        N.check(self._lib.lvs_search_submit(self._handle(), _ptr(q), _np_dtype_code(q), q.shape[0], int(k), _ptr(self._want(want)),
-                                            C.byref(t)), "lvs_search_submit")
+        N.check(self._lib.lvs_search_submit(self._handle(), _addr(q), N.DT_F64 if q.dtype == np.float64 else N.DT_F32, q.shape[0], int(k),
+                                            _ptr(self._want(want)), C.byref(t)), "lvs_search_submit")
         return (t.value, q.shape[0], int(k))
 
     def search_submit_sharded(self, ex, queries: np.ndarray, k: int, want=None) -> tuple[int, int, int]:
@@ -322,23 +358,16 @@ class DeviceCollection:
             q = q[None, :]
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
-        if np.isnan(q).any():
-            raise ValueError("Query vector must not contain NaN")
         t = C.c_int()
-        N.check(self._lib.lvs_search_submit_sharded(self._handle(), ex, _ptr(q), N.DT_F64, q.shape[0], int(k), _ptr(self._want(want)),
+        N.check(self._lib.lvs_search_submit_sharded(self._handle(), ex, _addr(q), N.DT_F64, q.shape[0], int(k), _ptr(self._want(want)),
                                                     C.byref(t)), "lvs_search_submit_sharded")
         return (t.value, q.shape[0], int(k))
 
     def search_wait(self, ticket: tuple[int, int, int]) -> SearchResult:
         t, Q, k = ticket
-        scores = np.zeros((Q, k), dtype=np.float64)
-        rows = np.full((Q, k), -1, dtype=np.int64)
-        ties = np.zeros((Q, k), dtype=np.uint64)
-        counts = np.zeros(Q, dtype=np.uint32)
-        flags = np.zeros(Q, dtype=np.int32)
-        N.check(self._lib.lvs_search_wait(self._handle(), t, _ptr(scores), _ptr(rows), _ptr(ties), _ptr(counts), _ptr(flags)),
-                "lvs_search_wait")
-        return SearchResult(scores, rows, ties, counts, flags)
+        block, (ps, pr, pt, pc, pf) = _result_block(Q, k)
+        N.check(self._lib.lvs_search_wait(self._handle(), t, ps, pr, pt, pc, pf), "lvs_search_wait")
+        return SearchResult.from_block(block, Q, k)
 
     def search_device(self, q_ptr: int, q_dtype: str, Q: int, k: int, want, scores_ptr: int, rows_ptr: int, ties_ptr: int,
                       counts_ptr: int, stream: int = 0) -> np.ndarray:
@@ -384,8 +413,9 @@ class DeviceCollection:
 
     def last_kernel_phases(self) -> np.ndarray:
         """Profiling aid (``set_option("dbg_times", 1)`` first): microseconds from the first CTA's start to each phase of the last
-        scan-kernel launch (queries ready, shard scanned, list written, lists visible, rescoring done, result ordered, result stored)."""
-        ns = np.zeros(8, dtype=np.uint64)
+        scan-kernel launch, 15 values in the order of ``include/lvs.h`` (queries ready, shard scanned, list written, lists visible,
+        candidates selected, rescoring done, result stored; then the finer stamps inside the selection and the ordering)."""
+        ns = np.zeros(16, dtype=np.uint64)
         N.check(self._lib.lvs_last_kernel_phases(self._handle(), ns.ctypes.data_as(C.POINTER(C.c_uint64))), "lvs_last_kernel_phases")
         return (ns[1:].astype(np.int64) - np.int64(ns[0])) / 1e3
 

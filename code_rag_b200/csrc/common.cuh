@@ -163,4 +163,46 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// 32 keys, one per lane -> sorted descending across the lanes (bitonic network on shuffles)
+__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t o = shfl_xor_u64(x, j);
+            const bool keep_max = (((lane & k) == 0) == ((lane & j) == 0));
+            x = keep_max ? (o > x ? o : x) : (o < x ? o : x);
+        }
+    }
+    return x;
+}
+// a bitonic sequence of 32 keys -> sorted descending
+__device__ __forceinline__ uint64_t warp_bitonic_merge_desc(uint64_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t o = shfl_xor_u64(x, j);
+        x = ((lane & j) == 0) ? (o > x ? o : x) : (o < x ? o : x);
+    }
+    return x;
+}
+
+// number of keys greater than v in a list of 32 keys sorted descending (binary search: six probes)
+__device__ __forceinline__ uint32_t count_greater_desc32(const uint64_t* list, uint64_t v) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t step = 16; step >= 1; step >>= 1) if (list[pos + step - 1] > v) pos += step;
+    return pos + (list[pos] > v ? 1u : 0u);
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase stamp of the profiling aid (option "dbg_times"): slot 0 keeps the earliest, the others the latest time any CTA got there
+__device__ __forceinline__ void stamp(unsigned long long* times, int slot) {
+    if (times == nullptr) return;
+    if (slot == 0) atomicMin(times, global_ns()); else atomicMax(times + slot, global_ns());
+}
+
 }  // namespace lvs

@@ -31,6 +31,8 @@ constexpr int kPwMaxLeaves = 128;      // numpy pair-wise blocks for dim <= 8192
 struct PwProgram {
     int n_leaves;
     int n_steps;
+    int regular;               // every leaf is a non-zero multiple of 8 long, at most 8 leaves: the register form of np_norm_f32 applies
+    int balanced;              // ... and the combine steps form a perfect binary tree over the leaves (a power of two of them)
     uint16_t leaf_off[kPwMaxLeaves];
     uint16_t leaf_len[kPwMaxLeaves];
     uint8_t step_dst[kPwMaxLeaves];
@@ -70,6 +72,7 @@ struct FinalizeParams {
     uint64_t* out_ties;        // [Q][k]
     int32_t* out_flags;        // [Q]      bit0: exactness not proven
     uint32_t* out_counts;      // [Q]      number of valid results
+    unsigned long long* dbg_times;  // optional phase stamps (see stamp() in common.cuh); nullptr in normal operation
 };
 
 __host__ __device__ inline size_t finalize_smem_bytes(int dim_pad, int n_rescore_warps) {
@@ -93,29 +96,56 @@ __host__ __device__ inline size_t finalize_query_offset() {
 // s_i = fl(v_i*v_i); pairwise_sum(s); sqrt.  Warp-cooperative; all lanes return the same value.
 __device__ __forceinline__ float np_norm_f32(const float* v, const PwProgram* pw, float* leaf_out, int lane) {
     const int nl = pw->n_leaves;
-    for (int base = 0; base < nl; base += 4) {
-        const int li = base + (lane >> 3);
-        const int j = lane & 7;
+    if (pw->regular) {
+        // Register form (dim 384 / 768 / 1024 ...): 4 lanes per leaf, each with two ADJACENT accumulators of numpy's eight
+        // (r[2j], r[2j+1]; one 64-bit load per step), all <= 8 leaves at once.  numpy's combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+        // is the in-lane add followed by two xor-shuffles; a perfect tree over the leaves is three more.  Starting the
+        // accumulators at +0 instead of at the first square changes nothing (squares are never -0).
+        const int li = lane >> 2;
         const bool ok = li < nl;
         const int off = ok ? pw->leaf_off[li] : 0;
         const int len = ok ? pw->leaf_len[li] : 0;
-        float r = 0.f;
-        if (len >= 8) {
-            const int lim = len - (len & 7);
-            float x = v[off + j];
-            r = __fmul_rn(x, x);
-            for (int i = 8; i < lim; i += 8) { x = v[off + i + j]; r = __fadd_rn(r, __fmul_rn(x, x)); }
+        const float2* vp = reinterpret_cast<const float2*>(v + off + (lane & 3) * 2);
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < len; i += 8) {
+            const float2 x = vp[i >> 1];
+            r0 = __fadd_rn(r0, __fmul_rn(x.x, x.x));
+            r1 = __fadd_rn(r1, __fmul_rn(x.y, x.y));
         }
+        float r = __fadd_rn(r0, r1);
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
-        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
-        if (len >= 8) {
-            for (int i = len - (len & 7); i < len; ++i) { const float x = v[off + i]; r = __fadd_rn(r, __fmul_rn(x, x)); }
-        } else {
-            r = 0.f;
-            for (int i = 0; i < len; ++i) { const float x = v[off + i]; r = __fadd_rn(r, __fmul_rn(x, x)); }
+        if (pw->balanced) {
+            for (int m = 4; m < 4 * nl; m <<= 1) r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, m));
+            return __fsqrt_rn(__shfl_sync(0xFFFFFFFFu, r, 0));
         }
-        if (ok && j == 0) leaf_out[li] = r;
+        if (ok && (lane & 3) == 0) leaf_out[li] = r;
+    } else {
+        for (int base = 0; base < nl; base += 4) {
+            const int li = base + (lane >> 3);
+            const int j = lane & 7;
+            const bool ok = li < nl;
+            const int off = ok ? pw->leaf_off[li] : 0;
+            const int len = ok ? pw->leaf_len[li] : 0;
+            float r = 0.f;
+            if (len >= 8) {
+                const int lim = len - (len & 7);
+                float x = v[off + j];
+                r = __fmul_rn(x, x);
+                for (int i = 8; i < lim; i += 8) { x = v[off + i + j]; r = __fadd_rn(r, __fmul_rn(x, x)); }
+            }
+            r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
+            r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
+            r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
+            if (len >= 8) {
+                for (int i = len - (len & 7); i < len; ++i) { const float x = v[off + i]; r = __fadd_rn(r, __fmul_rn(x, x)); }
+            } else {
+                r = 0.f;
+                for (int i = 0; i < len; ++i) { const float x = v[off + i]; r = __fadd_rn(r, __fmul_rn(x, x)); }
+            }
+            if (ok && j == 0) leaf_out[li] = r;
+        }
     }
     __syncwarp();
     if (lane == 0) {
@@ -128,6 +158,22 @@ __device__ __forceinline__ float np_norm_f32(const float* v, const PwProgram* pw
     const float tot = leaf_out[0];
     __syncwarp();
     return __fsqrt_rn(tot);
+}
+
+// this lane's share of sum_i v[i] * q[i] in float64: four columns per step (one 128-bit and two 128-bit loads), two accumulators
+__device__ __forceinline__ double lane_dot_f64(const float* v, const double* q, int D, int lane) {
+    double a0 = 0.0, a1 = 0.0;
+    const int D4 = D >> 2;
+#pragma unroll 2
+    for (int i = lane; i < D4; i += 32) {
+        const float4 x = reinterpret_cast<const float4*>(v)[i];
+        const double2 qa = reinterpret_cast<const double2*>(q)[2 * i], qb = reinterpret_cast<const double2*>(q)[2 * i + 1];
+        a0 = fma((double)x.x, qa.x, a0); a1 = fma((double)x.y, qa.y, a1);
+        a0 = fma((double)x.z, qb.x, a0); a1 = fma((double)x.w, qb.y, a1);
+    }
+    const int i = 4 * D4 + lane;
+    if (i < D) a0 = fma((double)v[i], q[i], a0);
+    return a0 + a1;
 }
 
 // Exact score of one candidate row (warp-cooperative).  buf = 3 * dim_pad floats of shared memory; q = the float64
@@ -164,8 +210,7 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
     }
     __syncwarp();
     if (p.metric == LVS_METRIC_DOT) {
-        double acc = 0.0;
-        for (int i = lane; i < D; i += 32) acc = fma((double)cur[i], q[i], acc);
+        const double acc = lane_dot_f64(cur, q, D, lane);
         __syncwarp();
         return warp_sum_f64(acc);
     }
@@ -178,20 +223,28 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
         }
         __syncwarp();
     }
+    if (lane == 0) stamp(p.dbg_times, 14);                // row staged
     // replay of the per-search in-place re-normalisation
     const uint64_t age = search_no - row_epoch;         // searches run since the row was written, this one included
     const uint32_t count = age > 64ull ? 64u + (uint32_t)((age - 64ull) & 1ull) : (uint32_t)age;
     bool have_prev = false;
+    const int n4 = p.dim_pad >> 2;
     for (uint32_t j = 1; j <= count; ++j) {
         const float n = np_norm_f32(cur, pw, leaf_out, lane);
         if (n == 1.0f) break;                            // fixed point
         const float d = (n != 0.0f) ? n : 1.1920929e-7f;
         bool same_cur = true, same_prev = true;
-        for (int i = lane; i < D; i += 32) {
-            const float y = __fdiv_rn(cur[i], d);
-            nxt[i] = y;
-            same_cur &= (y == cur[i]) || (y != y);
-            if (have_prev) same_prev &= (y == prev[i]) || (y != y);
+        // four columns per lane and step; the zero padding columns ride along (0 / d = 0, or NaN when d is: "same" either way)
+        for (int i = lane; i < n4; i += 32) {
+            const float4 x = reinterpret_cast<const float4*>(cur)[i];
+            float4 y;
+            y.x = __fdiv_rn(x.x, d); y.y = __fdiv_rn(x.y, d); y.z = __fdiv_rn(x.z, d); y.w = __fdiv_rn(x.w, d);
+            reinterpret_cast<float4*>(nxt)[i] = y;
+            same_cur &= ((y.x == x.x) || (y.x != y.x)) && ((y.y == x.y) || (y.y != y.y)) && ((y.z == x.z) || (y.z != y.z)) && ((y.w == x.w) || (y.w != y.w));
+            if (have_prev) {
+                const float4 o = reinterpret_cast<const float4*>(prev)[i];
+                same_prev &= ((y.x == o.x) || (y.x != y.x)) && ((y.y == o.y) || (y.y != y.y)) && ((y.z == o.z) || (y.z != y.z)) && ((y.w == o.w) || (y.w != y.w));
+            }
         }
         same_cur = __all_sync(0xFFFFFFFFu, same_cur);
         same_prev = have_prev && __all_sync(0xFFFFFFFFu, same_prev);
@@ -204,8 +257,8 @@ __device__ __forceinline__ double exact_score(const FinalizeParams& p, const PwP
         float* t = prev; prev = cur; cur = nxt; nxt = t;
         have_prev = true;
     }
-    double acc = 0.0;
-    for (int i = lane; i < D; i += 32) acc = fma((double)cur[i], q[i], acc);
+    if (lane == 0) stamp(p.dbg_times, 15);                // re-normalisations replayed
+    const double acc = lane_dot_f64(cur, q, D, lane);
     __syncwarp();
     return warp_sum_f64(acc);
 }
@@ -244,9 +297,11 @@ struct FinResult {
     int32_t flag;
 };
 
-template <int KPL, bool Q_STAGED>
+// stage_q(qs): the caller's way of putting the float64 unit query into shared memory (dim values; called by all 256 threads once,
+// after the first loads of the selection have been issued, so that its divisions hide their latency)
+template <int KPL, class StageQ>
 __device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uint32_t qi, const uint32_t cy, const uint32_t C,
-                                              uint8_t* fsm, const float qnorm_in, FinResult& res) {
+                                              uint8_t* fsm, const float qnorm_in, FinResult& res, StageQ stage_q) {
     constexpr uint32_t KPW = 32u * KPL;
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(fsm);
     uint32_t* scal = reinterpret_cast<uint32_t*>(fsm + (size_t)kSortCap * 8);   // [3]=is_last
@@ -269,42 +324,77 @@ __device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uin
     const uint64_t* keys = p.keys + (size_t)qi * p.M;
     const uint32_t kp = p.kp;                            // == KPW
 
-    // stage the float64 query and the pair-wise program while the lists stream in
-    if (!Q_STAGED) {                                     // fused scan kernel: the caller has already put the unit query into qs
-        const double* qg = p.q64 + (size_t)qi * p.dim;
-        for (int i = tid; i < p.dim; i += kFinThreads) qs[i] = qg[i];
-    }
+    // stage the pair-wise program (and, below, the float64 query) while the lists stream in
     for (int i = tid; i < (int)(sizeof(PwProgram) / 4); i += kFinThreads)
         reinterpret_cast<uint32_t*>(pws)[i] = reinterpret_cast<const uint32_t*>(p.pw)[i];
+    bool q_staged = false;
 
     // ---- 1a. fast path (L >= kp lists): the kp-th largest LIST MAXIMUM is a threshold with at least kp keys at or
     //          above it (the kp maxima themselves) and, for well-mixed shards, few more; gather those keys.
     bool folded = true;
+    uint32_t nsurv = 0;                                  // non-empty keys that survived the threshold
     uint32_t nmerged = 32;                               // keys handed to the ranking step (a power of two, zero padded)
-    if (p.L >= kp && p.L <= (uint32_t)kSortCap) {
+    if (p.L >= kp && p.L < (uint32_t)kSortCap) {
         const uint64_t* tops = p.tops + (size_t)qi * p.L;
-        if (tid == 0) { scal[0] = 0; scal[1] = 0; }
-        for (uint32_t i = tid; i < p.L; i += kFinThreads) sortbuf[i] = __ldcg(tops + i);
-        fin_sync();
         unsigned long long* Tp = reinterpret_cast<unsigned long long*>(scal + 4);
-        for (uint32_t i = tid; i < p.L; i += kFinThreads) {
-            const uint64_t v = sortbuf[i];
-            uint32_t rank = 0;
-            for (uint32_t o = 0; o < p.L; ++o) { const uint64_t w = sortbuf[o]; rank += (w > v || (w == v && o < i)) ? 1u : 0u; }
-            if (rank == kp - 1) *Tp = v;
+        if (tid == 0) { scal[0] = 0; scal[1] = 0; *Tp = 0ull; }
+        // one thread per list: its maximum and its first four keys are requested together (one trip to L2 instead of two);
+        // lists beyond the first 256 take their loads in the gather loop below
+        const uint32_t llen = p.M / p.L;
+        const uint32_t l0 = (uint32_t)tid;
+        ulonglong2 ha = make_ulonglong2(0ull, 0ull), hb = ha;
+        uint64_t top0 = 0ull;
+        if (l0 < p.L) {
+            top0 = __ldcg(tops + l0);
+            ha = __ldcg(reinterpret_cast<const ulonglong2*>(keys + (size_t)l0 * llen));
+            hb = __ldcg(reinterpret_cast<const ulonglong2*>(keys + (size_t)l0 * llen + 2));
+        }
+        stage_q(qs); q_staged = true;                     // the loads above are in flight meanwhile
+        if (p.L <= (uint32_t)kFinThreads) {
+            // up to 256 lists (one scan CTA per SM): every warp sorts its 32 maxima on shuffles; a key's rank is its place in its
+            // own warp's list plus, by binary search, the number of greater keys in the others - ~40 shared-memory reads per
+            // thread instead of L.  Empty maxima (0) tie with each other; no rank may then equal kp - 1 and T stays 0 (keep all).
+            const uint64_t x = warp_sort_desc(top0, lane);
+            sortbuf[tid] = x;
+            fin_sync();
+            if (tid == 0) stamp(p.dbg_times, 8);
+            const uint32_t nw = (p.L + 31u) / 32u;
+            if (x != 0ull) {
+                uint32_t rank = (uint32_t)lane;
+                for (uint32_t w = 0; w < nw; ++w) if (w != (uint32_t)warp) rank += count_greater_desc32(sortbuf + 32u * w, x);
+                if (rank == kp - 1) *Tp = x;
+            }
+        } else {
+            sortbuf[l0] = top0;
+            for (uint32_t i = tid + kFinThreads; i < p.L; i += kFinThreads) sortbuf[i] = __ldcg(tops + i);
+            if (tid == 0) sortbuf[p.L] = 0ull;            // pad to an even count: the rank loop reads two keys per load (an empty key outranks nothing)
+            fin_sync();
+            if (tid == 0) stamp(p.dbg_times, 8);
+            for (uint32_t i = tid; i < p.L; i += kFinThreads) {
+                const uint64_t v = sortbuf[i];
+                uint32_t rank = 0;
+                for (uint32_t o = 0; o < p.L; o += 2) {
+                    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sortbuf + o);
+                    rank += (w.x > v || (w.x == v && o < i)) ? 1u : 0u;
+                    rank += (w.y > v || (w.y == v && o + 1 < i)) ? 1u : 0u;
+                }
+                if (rank == kp - 1) *Tp = v;
+            }
         }
         fin_sync();
+        if (tid == 0) stamp(p.dbg_times, 9);
         uint64_t T = *Tp;
         if (T == 0ull) T = 1ull;                          // fewer than kp non-empty lists: keep every key
-        fin_sync();
         // the lists are sorted descending (bitonic merge in K1, sorted insertion in K2), so the keys >= T of a list are a
-        // prefix of it: one thread per list reads 4 keys (32 bytes) at a time and stops at the first key below T
-        const uint32_t llen = p.M / p.L;
+        // prefix of it: one thread per list takes 4 keys (32 bytes) at a time and stops at the first key below T
         for (uint32_t l = tid; l < p.L; l += kFinThreads) {
             const uint64_t* lk = keys + (size_t)l * llen;
             for (uint32_t i = 0; i < llen; i += 4) {
-                const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(lk + i));
-                const ulonglong2 b = __ldcg(reinterpret_cast<const ulonglong2*>(lk + i + 2));
+                ulonglong2 a = ha, b = hb;
+                if (i > 0 || l != l0) {
+                    a = __ldcg(reinterpret_cast<const ulonglong2*>(lk + i));
+                    b = __ldcg(reinterpret_cast<const ulonglong2*>(lk + i + 2));
+                }
                 const uint64_t v[4] = {a.x, a.y, b.x, b.y};
                 bool more = true;
 #pragma unroll
@@ -320,16 +410,19 @@ __device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uin
             }
         }
         fin_sync();
+        if (tid == 0) stamp(p.dbg_times, 10);
         const uint32_t got = scal[0];
         if (got <= kFinWarps * KPW) {
             while (nmerged < got) nmerged <<= 1;          // sort no more than the next power of two above the survivors
             for (uint32_t i = got + tid; i < nmerged; i += kFinThreads) sortbuf[i] = 0ull;
             folded = false;
+            nsurv = got;
         }
         fin_sync();
     }
     // ---- 1b. general path: exact radix select of the kp-th largest key (MSB first, 8 bits per pass over the keys in L2);
     //          stops as soon as at most 2 k' keys lie at or above the current bucket
+    if (!q_staged) stage_q(qs);
     if (folded) {
         uint64_t prefix = 0, mask = 0;
         uint32_t remaining = kp;                         // rank still to be located inside the current prefix bucket
@@ -382,28 +475,24 @@ __device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uin
         nmerged = 32;
         while (nmerged < got) nmerged <<= 1;
         for (uint32_t i = got + tid; i < nmerged; i += kFinThreads) sortbuf[i] = 0ull;
+        nsurv = got;
         fin_sync();
     }
-    // ---- 2. rank the merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key) ----
-    if (tid == 0) scal[0] = 0;
-    fin_sync();
-    {
-        uint32_t nz = 0;
-        for (uint32_t i = tid; i < nmerged; i += kFinThreads) nz += sortbuf[i] != 0ull ? 1u : 0u;
-        for (int o = 16; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
-        if (lane == 0 && nz) atomicAdd(&scal[0], nz);
-    }
-    fin_sync();
-    const uint32_t nsurv = scal[0];
+    // ---- 2. rank the merged keys, keep the kp best (non-empty keys are distinct: the row is part of the key).  Every gathered
+    //         key is non-empty (>= T >= 1, or tested), so the number of survivors is the number gathered. ----
     const uint32_t ncand = min(nsurv, kp);
     if (nmerged <= 256u) {
-        for (uint32_t i = tid; i < nmerged; i += kFinThreads) {
-            const uint64_t v = sortbuf[i];
-            if (v == 0ull) continue;
-            uint32_t rank = 0;
-            for (uint32_t o = 0; o < nmerged; ++o) rank += sortbuf[o] > v ? 1u : 0u;
-            if (rank < kp) ckey[rank] = v;
+        // 256 / nmerged threads per key (adjacent lanes), each counting the greater keys in its share of the buffer
+        const uint32_t tpe = (uint32_t)kFinThreads / nmerged, share = nmerged / tpe;
+        const uint32_t i = (uint32_t)tid / tpe, part = (uint32_t)tid % tpe;
+        const uint64_t v = sortbuf[i];
+        uint32_t rank = 0;
+        for (uint32_t o = part * share; o < (part + 1) * share; o += 2) {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sortbuf + o);
+            rank += (w.x > v ? 1u : 0u) + (w.y > v ? 1u : 0u);
         }
+        for (uint32_t m = 1; m < tpe; m <<= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, m);
+        if (part == 0 && v != 0ull && rank < kp) ckey[rank] = v;
         fin_sync();
     } else {
         bitonic_sort_desc(sortbuf, (int)nmerged, tid);
@@ -429,6 +518,11 @@ __device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uin
     float t_fast = ncand > 0 ? key_score(ckey[ncand - 1]) : 0.f;
     if (nsurv < kp) t_fast = -INFINITY;                 // every kept key is a candidate
     if (drop_key != 0ull) t_fast = fmaxf(t_fast, key_score(drop_key));
+    // rows and tie keys of the candidates: requested now, needed by the ordering step (their latency hides behind the rescoring)
+    // (ncand <= kMaxCand = 256 = threads: one candidate per thread, kept in registers until the rescoring is done)
+    uint32_t my_row = 0; uint64_t my_tie = 0ull;
+    if ((uint32_t)tid < ncand) { my_row = key_row(ckey[tid]); my_tie = p.tiekey[my_row]; }
+    if (tid == 0) stamp(p.dbg_times, 5);                 // candidates selected
     // ---- 4. exact rescoring: candidate c belongs to CTA c / nrw, warp c % nrw ----
     const uint32_t nrw = (uint32_t)p.n_rescore_warps;
     double* gscore = p.cand_scores + (size_t)qi * kMaxCand;
@@ -440,56 +534,60 @@ __device__ __forceinline__ bool finalize_body(const FinalizeParams& p, const uin
             if (lane == 0) gscore[c] = s;
         }
     }
+    if ((uint32_t)tid < ncand) { crow[tid] = my_row; ctie[tid] = my_tie; }
     fin_sync();
     if (tid == 0) {
+        stamp(p.dbg_times, 6);                           // this CTA's share of the rescoring is done
         uint32_t last = 1;
         if (C > 1) {
             __threadfence();
             last = (atomicAdd(p.tickets + qi, 1u) == C - 1) ? 1u : 0u;
         }
         scal[3] = last;
+        scal[8] = 0u;                                    // the "exactness not proven" mark of step 6
     }
     fin_sync();
     if (scal[3] == 0) return false;
     __threadfence();
-    for (uint32_t c = tid; c < ncand; c += kFinThreads) {
-        const uint32_t r = key_row(ckey[c]);
-        crow[c] = r;
-        ctie[c] = p.tiekey[r];
-        cscore[c] = __ldcg(gscore + c);
-    }
+    for (uint32_t c = tid; c < ncand; c += kFinThreads) cscore[c] = __ldcg(gscore + c);
     if (tid == 0 && C > 1) p.tickets[qi] = 0;            // ready for the next launch
     fin_sync();
-    // ---- 5. final order: (score desc, tie asc, row asc) by rank counting ----
-    for (uint32_t c = tid; c < ncand; c += kFinThreads) {
-        const double s = cscore[c]; const uint64_t t = ctie[c]; const uint32_t r = crow[c];
+    if (tid == 0) stamp(p.dbg_times, 11);
+    // ---- 5. final order: (score desc, tie asc, row asc) by rank counting, and
+    //      6. the exactness proof for the weakest returned result ----
+    const uint32_t nout = min(ncand, p.k);
+    {
+        // 256 / next_pow2(ncand) threads per candidate (adjacent lanes), each comparing with its share of the others
+        uint32_t np2 = 32;
+        while (np2 < ncand) np2 <<= 1;                   // <= kMaxCand = 256
+        const uint32_t tpe = (uint32_t)kFinThreads / np2, share = np2 / tpe;
+        const uint32_t c = (uint32_t)tid / tpe, part = (uint32_t)tid % tpe;
+        const bool real = c < ncand;
+        const double s = real ? cscore[c] : 0.0; const uint64_t t = real ? ctie[c] : 0ull; const uint32_t r = real ? crow[c] : 0u;
         uint32_t rank = 0;
-        for (uint32_t o = 0; o < ncand; ++o) {
+        const uint32_t o_end = min((part + 1) * share, ncand);
+        for (uint32_t o = part * share; o < o_end; ++o) {
             const double so = cscore[o]; const uint64_t to = ctie[o]; const uint32_t ro = crow[o];
             const bool better = (so > s) || (so == s && (to < t || (to == t && ro < r)));
             rank += better ? 1u : 0u;
         }
-        crank[c] = rank;
-    }
-    fin_sync();
-    // ---- 6. the exactness proof for the weakest returned result ----
-    const uint32_t nout = min(ncand, p.k);
-    if (tid == 0) scal[8] = 0u;
-    fin_sync();
-    for (uint32_t c = tid; c < ncand; c += kFinThreads) {
-        const uint32_t rk = crank[c];
-        if (rk == p.k - 1 || (rk == ncand - 1 && ncand < p.k)) {
-            // this candidate is the weakest returned result
-            if (!lists_dropped_nothing && ncand >= p.k) {
-                // rows outside the candidate set have exact score <= t_fast + eps
-                double eps = p.eps_q != nullptr ? (double)p.eps_q[qi] + (double)p.eps_add : (double)p.eps;
-                if (p.metric == LVS_METRIC_DOT) eps *= (double)(p.qnorm != nullptr ? p.qnorm[qi] : qnorm_in) * (double)(*p.max_norm);
-                if (!(cscore[c] > (double)t_fast + eps)) scal[8] = 1u;
-                if (ncand == kp && kp == p.k) scal[8] = 1u;  // no margin at all
+        for (uint32_t m = 1; m < tpe; m <<= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, m);
+        if (real && part == 0) {
+            crank[c] = rank;
+            if (rank == p.k - 1 || (rank == ncand - 1 && ncand < p.k)) {
+                // this candidate is the weakest returned result
+                if (!lists_dropped_nothing && ncand >= p.k) {
+                    // rows outside the candidate set have exact score <= t_fast + eps
+                    double eps = p.eps_q != nullptr ? (double)p.eps_q[qi] + (double)p.eps_add : (double)p.eps;
+                    if (p.metric == LVS_METRIC_DOT) eps *= (double)(p.qnorm != nullptr ? p.qnorm[qi] : qnorm_in) * (double)(*p.max_norm);
+                    if (!(s > (double)t_fast + eps)) scal[8] = 1u;
+                    if (ncand == kp && kp == p.k) scal[8] = 1u;  // no margin at all
+                }
             }
         }
     }
     fin_sync();
+    if (tid == 0) stamp(p.dbg_times, 12);
     res.score = cscore; res.row = crow; res.tie = ctie; res.rank = crank; res.ncand = ncand; res.nout = nout;
     res.flag = ncand == 0 ? 0 : (int32_t)scal[8];
     return true;
@@ -518,7 +616,12 @@ template <int KPL>
 __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinalizeParams p) {
     extern __shared__ __align__(16) uint8_t fsm_dyn[];
     FinResult r;
-    if (finalize_body<KPL, false>(p, blockIdx.x, blockIdx.y, gridDim.y, fsm_dyn, 0.f, r)) finalize_store_local(p, blockIdx.x, r, threadIdx.x);
+    const uint32_t qi = blockIdx.x;
+    const auto stage_q = [&](double* qs) {
+        const double* qg = p.q64 + (size_t)qi * p.dim;
+        for (int i = threadIdx.x; i < p.dim; i += kFinThreads) qs[i] = qg[i];
+    };
+    if (finalize_body<KPL>(p, qi, blockIdx.y, gridDim.y, fsm_dyn, 0.f, r, stage_q)) finalize_store_local(p, qi, r, threadIdx.x);
 }
 
 }  // namespace lvs

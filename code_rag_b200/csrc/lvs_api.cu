@@ -137,6 +137,8 @@ struct lvs_collection {
     Scratch s_qstage;                 // host queries staged by CTA 0, one slot per launch parity
     int opt_dyn_tiles = 1;
     int opt_dbg_times = 0;            // 1: the scan kernel stamps its phases (lvs_last_kernel_phases)
+    int opt_inline_query = 1;         // host queries of up to kInlineQueryBytes ride in the kernel's parameter block
+    InlineQueries iq;                 // ... assembled here (under the collection's lock)
     Scratch s_dbg_times;
     Scratch h_pin, h_pin2, h_flags;
 
@@ -217,6 +219,27 @@ static int pw_build(PwProgram& pg, int off, int n) {
     pg.step_src[pg.n_steps] = (uint8_t)r;
     pg.n_steps++;
     return l;
+}
+
+// steps a perfect binary tree over leaves [lo, lo + cnt) would have produced (post-order), compared with the program's
+static int pw_expect_perfect(const PwProgram& pg, int lo, int cnt, int* step, bool* same) {
+    if (cnt == 1) return lo;
+    const int l = pw_expect_perfect(pg, lo, cnt / 2, step, same);
+    const int r = pw_expect_perfect(pg, lo + cnt / 2, cnt / 2, step, same);
+    if (*step >= pg.n_steps || pg.step_dst[*step] != l || pg.step_src[*step] != r) *same = false;
+    ++*step;
+    return l;
+}
+// the shapes np_norm_f32's register form handles (finalize_kernel.cuh): dim 384 / 768 / 1024 and the like
+static void pw_classify(PwProgram& pg) {
+    pg.regular = pg.n_leaves <= 8 ? 1 : 0;
+    for (int i = 0; i < pg.n_leaves; ++i) if (pg.leaf_len[i] < 8 || pg.leaf_len[i] % 8 != 0 || pg.leaf_off[i] % 8 != 0) pg.regular = 0;
+    pg.balanced = 0;
+    if (pg.regular && (pg.n_leaves & (pg.n_leaves - 1)) == 0) {
+        int step = 0; bool same = true;
+        pw_expect_perfect(pg, 0, pg.n_leaves, &step, &same);
+        pg.balanced = same && step == pg.n_steps ? 1 : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -350,6 +373,7 @@ extern "C" int lvs_collection_create(const char* name, int dim, int storage, int
     memset(&pg, 0, sizeof(pg));
     if (dim < 8) { pg.n_leaves = 1; pg.leaf_off[0] = 0; pg.leaf_len[0] = (uint16_t)dim; }
     else if (pw_build(pg, 0, dim) < 0) { lvs_collection_destroy(c); return fail(LVS_ELIMIT, "dim %d needs too many pairwise blocks", dim); }
+    pw_classify(pg);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_pw, sizeof(PwProgram));
     if (e == cudaSuccess) e = cudaMemcpy(c->d_pw, &pg, sizeof(PwProgram), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -727,11 +751,11 @@ extern "C" int lvs_match_rows(lvs_collection* c, const uint32_t* want, int64_t* 
 // The 36 instantiations of the fused scan kernel are compiled in three translation units of their own (scan_f32.cu,
 // scan_bf16_cos.cu, scan_bf16_dot.cu: build.py compiles every .cu in parallel), through scan_launch.cuh.
 static cudaError_t launch_scan(const lvs_collection* c, int qt, int kpl, bool filter, const ScanParams& p, const FinalizeParams& fp,
-                               const ExchangeParams& xp, int grid, size_t smem, cudaStream_t st) {
+                               const ExchangeParams& xp, const InlineQueries& iq, int grid, size_t smem, cudaStream_t st) {
     const size_t optin = g_lib.smem_optin;
-    if (c->storage == LVS_STORAGE_F32) return lvs_launch_scan_f32(qt, kpl, filter, p, fp, xp, grid, smem, st, optin);
-    if (c->metric == LVS_METRIC_COSINE) return lvs_launch_scan_bf16_cos(qt, kpl, filter, p, fp, xp, grid, smem, st, optin);
-    return lvs_launch_scan_bf16_dot(qt, kpl, filter, p, fp, xp, grid, smem, st, optin);
+    if (c->storage == LVS_STORAGE_F32) return lvs_launch_scan_f32(qt, kpl, filter, p, fp, xp, iq, grid, smem, st, optin);
+    if (c->metric == LVS_METRIC_COSINE) return lvs_launch_scan_bf16_cos(qt, kpl, filter, p, fp, xp, iq, grid, smem, st, optin);
+    return lvs_launch_scan_bf16_dot(qt, kpl, filter, p, fp, xp, iq, grid, smem, st, optin);
 }
 
 template <int KPL>
@@ -824,7 +848,7 @@ struct LevelOut {
 
 // Enqueue one level of the search for the query indices in `pending` (ascending): ONE fused kernel (query prep + scan + exact
 // rescoring [+ exchange and merge]) per group of up to max_qt consecutive queries.  No synchronisation.
-static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_host, int dtype, const std::vector<int>& pending, int k, int kpl, bool filter,
+static int enqueue_level(lvs_collection* c, const void* d_queries, const void* h_queries, int dtype, const std::vector<int>& pending, int k, int kpl, bool filter,
                          const uint32_t* const* fcodes, const uint32_t* fwant, uint32_t nf, uint64_t search_base, const LevelOut& out,
                          cudaStream_t st, int* launches, bool time_first) {
     const int sm = g_lib.sm_count;
@@ -879,7 +903,12 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_hos
         sp.n_queries = (uint32_t)cnt; sp.q_stride = c->q_stride;
         const uint32_t seq = c->launch_seq + 1;
         sp.seq = seq; sp.done_seq = c->d_counter + 10;
-        if (q_in_host) {
+        InlineQueries& iq = c->iq;        // only the first cnt * qrow bytes mean anything; the launch copies the block
+        if (h_queries != nullptr && c->opt_inline_query && (size_t)cnt * qrow <= kInlineQueryBytes) {
+            // a handful of host queries: they travel in the kernel's parameter block (scan_kernel.cuh)
+            sp.q_inline = 1u; sp.q_raw = nullptr;
+            memcpy(iq.bytes, (const uint8_t*)h_queries + (size_t)first * qrow, (size_t)cnt * qrow);
+        } else if (h_queries != nullptr) {
             // mapped pinned host memory: CTA 0 stages the group's queries in HBM for the other CTAs (scan_kernel.cuh)
             const size_t slot_bytes = (size_t)4 * c->dim * 8;
             if ((rc = ensure_dev(c->s_qstage, 2 * slot_bytes)) != LVS_OK) return rc;
@@ -901,10 +930,10 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_hos
         sp.ticket = c->d_counter + 4; sp.n_helpers = (uint32_t)cnt * cq;
         sp.host_ready = out.host_ready; sp.host_ready_val = out.host_ready_val;
         if (c->opt_dbg_times) {
-            if ((rc = ensure_dev(c->s_dbg_times, 64)) != LVS_OK) return rc;
+            if ((rc = ensure_dev(c->s_dbg_times, 128)) != LVS_OK) return rc;
             CU(cudaMemsetAsync(c->s_dbg_times.p, 0xFF, 8, st));                       // slot 0 takes a minimum
-            CU(cudaMemsetAsync((uint8_t*)c->s_dbg_times.p + 8, 0, 56, st));
-            sp.dbg_times = (unsigned long long*)c->s_dbg_times.p;
+            CU(cudaMemsetAsync((uint8_t*)c->s_dbg_times.p + 8, 0, 120, st));
+            sp.dbg_times = (unsigned long long*)c->s_dbg_times.p; fp.dbg_times = sp.dbg_times;
         }
         const bool dyn = !filter && grid == sm && c->opt_dyn_tiles;       // dynamic tile scheduling needs one CTA per SM (see the kernel)
         if (dyn) { sp.tile_counter = c->d_counter + 6 + (seq & 1u); sp.tile_base = c->tile_base[seq & 1u]; }
@@ -924,7 +953,7 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, bool q_in_hos
             c->ring_pos++;
             CU(cudaEventRecord(es, st));
         }
-        cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, fp, xp, grid, g.smem, st);
+        cudaError_t e = launch_scan(c, qt_use, kpl, filter, sp, fp, xp, iq, grid, g.smem, st);
         if (e != cudaSuccess) return fail(LVS_ECUDA, "scan kernel launch failed: %s (qt=%d kpl=%d smem=%zu)", cudaGetErrorString(e), qt_use, kpl, g.smem);
         ++*launches;
         c->launch_seq = seq;
@@ -1155,17 +1184,17 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
                        double* d_scores, int64_t* d_rows, uint64_t* d_ties, uint32_t* d_counts, int32_t* h_flags,
                        int32_t* d_flags_out, bool async, cudaStream_t st, int64_t base_override = -1, int kpl_min = 0,
                        const std::vector<int>* only = nullptr, lvs_exchange* ex = nullptr, int64_t* xout = nullptr,
-                       bool q_in_host = false, uint32_t* host_ready = nullptr, uint32_t host_ready_val = 0) {
+                       const void* h_queries = nullptr, uint32_t* host_ready = nullptr, uint32_t host_ready_val = 0) {
     c->last_ready_armed = false;
     if (Q <= 0) return LVS_OK;
     if (k < 1 || k > LVS_MAX_K) return fail(LVS_ELIMIT, "limit %d outside 1..%d", k, LVS_MAX_K);
     if (dtype != LVS_DT_F32 && dtype != LVS_DT_F64) return fail(LVS_EINVAL, "query dtype must be f32 or f64");
     if (ex && !async) return fail(LVS_EINVAL, "the sharded search is enqueue-only");
-    if (!q_in_host) {
-        // callers may hand in mapped pinned HOST memory as a "device" pointer (unified addressing): such queries are staged by
-        // one CTA instead of being pulled over PCIe by every CTA
+    if (h_queries == nullptr) {
+        // callers may hand in mapped pinned HOST memory as a "device" pointer (unified addressing): such queries travel in the
+        // kernel's parameter block or are staged by one CTA instead of being pulled over PCIe by every CTA
         cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, d_queries) == cudaSuccess) q_in_host = pa.type == cudaMemoryTypeHost;
+        if (cudaPointerGetAttributes(&pa, d_queries) == cudaSuccess) { if (pa.type == cudaMemoryTypeHost) h_queries = pa.hostPointer; }
         else cudaGetLastError();
     }
     const int sm = g_lib.sm_count;
@@ -1258,7 +1287,7 @@ static int search_core(lvs_collection* c, const void* d_queries, int dtype, int 
         c->last_ready_armed = true;
     }
     while (!pending.empty()) {
-        rc = enqueue_level(c, d_queries, q_in_host, dtype, pending, k, kpl, filter, fcodes, fwant, nf, search_base, lo, st, &launches, first);
+        rc = enqueue_level(c, d_queries, h_queries, dtype, pending, k, kpl, filter, fcodes, fwant, nf, search_base, lo, st, &launches, first);
         if (rc != LVS_OK) return rc;
         first = false;
         if (async) break;
@@ -1354,7 +1383,14 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
     CU(cudaHostGetDevicePointer(&dview, sl.h.p, 0));
     cudaStream_t st = c->stream;
     const size_t qraw = (size_t)Q * c->dim * dt_size(dtype);
-    memcpy(sl.h.p, queries, qraw);
+    // copy into the slot and look for NaN on the way (the reference's local mode refuses such a query)
+    {
+        const size_t n = (size_t)Q * c->dim;
+        int bad = 0;
+        if (dtype == LVS_DT_F64) { const double* s = (const double*)queries; double* d = (double*)sl.h.p; for (size_t i = 0; i < n; ++i) { const double x = s[i]; d[i] = x; bad |= x != x; } }
+        else { const float* s = (const float*)queries; float* d = (float*)sl.h.p; for (size_t i = 0; i < n; ++i) { const float x = s[i]; d[i] = x; bad |= x != x; } }
+        if (bad) return fail(LVS_ENAN, "Query vector must not contain NaN");
+    }
     const size_t nres = (size_t)Q * k;
     sl.Q = Q; sl.k = k; sl.dtype = dtype; sl.base = c->search_counter + 1; sl.qbytes = qbytes;
     sl.has_want = want != nullptr;
@@ -1377,7 +1413,7 @@ static int submit_locked(lvs_collection* c, const void* queries, int dtype, int 
     // sharded: the merged lists of all ranks land in the same place, in the same layout ([3][Q][k] = scores | rows | ties)
     rc = search_core(c, qp, dtype, Q, k, want, (double*)rp, (int64_t*)(rp + nres * 8), (uint64_t*)(rp + nres * 16),
                      (uint32_t*)(rp + nres * 24), nullptr, (int32_t*)(rp + nres * 24 + (size_t)Q * 4), true, st, -1, 0, nullptr, ex,
-                     ex ? (int64_t*)rp : nullptr, !sl.staged,
+                     ex ? (int64_t*)rp : nullptr, sl.staged ? nullptr : sl.h.p,
                      sl.staged ? nullptr : (uint32_t*)((uint8_t*)dview + qbytes + ready_off(Q, k)), sl.ready_val);
     if (rc == LVS_OK && sl.staged) CU(cudaMemcpyAsync((uint8_t*)sl.h.p + qbytes, rp, rbytes, cudaMemcpyDeviceToHost, st));
     sl.poll = rc == LVS_OK && c->last_ready_armed;
@@ -1433,7 +1469,7 @@ static int finish_locked(lvs_collection* c, int ticket, double* out_scores, int6
         std::vector<int32_t> f2(Q, 0);
         int rc = search_core(c, qp, sl.dtype, Q, k, sl.has_want ? sl.want : nullptr, (double*)rp, (int64_t*)(rp + nres * 8),
                              (uint64_t*)(rp + nres * 16), (uint32_t*)(rp + nres * 24), f2.data(), nullptr, false, c->stream,
-                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo, nullptr, nullptr, !sl.staged);
+                             (int64_t)sl.base, sl.kind == 2 ? sl.kpl : sl.kpl * 2, &redo, nullptr, nullptr, sl.staged ? nullptr : sl.h.p);
         if (rc == LVS_OK && sl.staged) {
             cudaError_t e = cudaMemcpyAsync(hp, rp, res_bytes(Q, k), cudaMemcpyDeviceToHost, c->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -2272,13 +2308,13 @@ extern "C" int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* 
     return LVS_OK;
 }
 
-extern "C" int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns8) {
+extern "C" int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns16) {
     bind_thread();
-    if (!c || !ns8) return fail(LVS_EINVAL, "NULL argument");
+    if (!c || !ns16) return fail(LVS_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->s_dbg_times.p) return fail(LVS_ESTATE, "option dbg_times was not set before the search");
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaMemcpy(ns8, c->s_dbg_times.p, 64, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ns16, c->s_dbg_times.p, 128, cudaMemcpyDeviceToHost));
     return LVS_OK;
 }
 
@@ -2294,6 +2330,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "pdl")) c->opt_pdl = value ? 1 : 0;
     else if (!strcmp(name, "dyn_tiles")) c->opt_dyn_tiles = value ? 1 : 0;
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value ? 1 : 0;
+    else if (!strcmp(name, "inline_query")) c->opt_inline_query = value ? 1 : 0;
     else if (!strcmp(name, "gemm_min_q")) c->opt_gemm_min_q = value;
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;

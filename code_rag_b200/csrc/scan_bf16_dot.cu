@@ -2,6 +2,6 @@
 #include "scan_launch.cuh"
 
 LVS_SCAN_ENTRY(lvs_launch_scan_bf16_dot) {
-    return filter ? lvs::launch_scan_tnf<__nv_bfloat16, false, true>(qt, kpl, p, fp, xp, grid, smem, st, smem_optin)
-                  : lvs::launch_scan_tnf<__nv_bfloat16, false, false>(qt, kpl, p, fp, xp, grid, smem, st, smem_optin);
+    return filter ? lvs::launch_scan_tnf<__nv_bfloat16, false, true>(qt, kpl, p, fp, xp, iq, grid, smem, st, smem_optin)
+                  : lvs::launch_scan_tnf<__nv_bfloat16, false, false>(qt, kpl, p, fp, xp, iq, grid, smem, st, smem_optin);
 }

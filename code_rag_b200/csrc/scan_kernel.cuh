@@ -45,6 +45,11 @@ constexpr int kScanRW = 4;            // rows a consumer warp processes together
 constexpr int kScanMaxStages = 12;
 constexpr size_t kScanStaticSmem = 1024;   // static shared memory of the kernel (a few words, padded to the ring's alignment)
 
+// A handful of host queries ride in the kernel's parameter block (one copy at launch, readable by every CTA from its first
+// instruction): no PCIe read, no staging hop, no flag.  8 KB = one 1024-dimensional float64 query.
+constexpr uint32_t kInlineQueryBytes = 8192;
+struct InlineQueries { uint8_t bytes[kInlineQueryBytes]; };
+
 struct ScanParams {
     const uint8_t* base;        // shard, row-major, row stride = row_bytes
     uint32_t row_bytes;         // multiple of 16
@@ -76,6 +81,7 @@ struct ScanParams {
     void* q_stage;              //   them here (device) for everybody, then publishes *q_flag = seq; q_raw == q_stage
     uint32_t* q_flag;
     uint32_t q_bytes;           // n_queries * dim * sizeof(query element)
+    uint32_t q_inline;          // 1: the raw queries are in the InlineQueries parameter (q_raw / q_host are unused)
     unsigned long long* dbg_times;  // optional [8]: globaltimer stamps of the launch's phases (min of the starts, max of the rest); profiling aid
     uint32_t* host_ready;       // optional word in mapped pinned host memory: set to host_ready_val (system-scope release) when every
     uint32_t host_ready_val;    //   result of this launch has been stored - the host polls it instead of synchronising an event
@@ -155,44 +161,10 @@ __device__ __forceinline__ double block_query_norm(const void* src, int dtype, s
     return sqrt(t);
 }
 
-// 32 keys, one per lane -> sorted descending across the lanes (bitonic network on shuffles)
-__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t x, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint64_t o = shfl_xor_u64(x, j);
-            const bool keep_max = (((lane & k) == 0) == ((lane & j) == 0));
-            x = keep_max ? (o > x ? o : x) : (o < x ? o : x);
-        }
-    }
-    return x;
-}
-// a bitonic sequence of 32 keys -> sorted descending
-__device__ __forceinline__ uint64_t warp_bitonic_merge_desc(uint64_t x, int lane) {
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-        const uint64_t o = shfl_xor_u64(x, j);
-        x = ((lane & j) == 0) ? (o > x ? o : x) : (o < x ? o : x);
-    }
-    return x;
-}
-
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// phase stamp of the profiling aid (option "dbg_times"): slot 0 keeps the earliest, the others the latest time any CTA got there
-__device__ __forceinline__ void stamp(unsigned long long* times, int slot) {
-    if (times == nullptr) return;
-    if (slot == 0) atomicMin(times, global_ns()); else atomicMax(times + slot, global_ns());
 }
 
 __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
@@ -205,7 +177,8 @@ __device__ __forceinline__ void wait_seq_reached(const uint32_t* word, uint32_t 
 
 template <typename T, int QT, int KPL, bool NORM, bool FILTER>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid_constant__ ScanParams p, const __grid_constant__ FinalizeParams fp,
-                                                                    const __grid_constant__ ExchangeParams xp) {
+                                                                    const __grid_constant__ ExchangeParams xp,
+                                                                    const __grid_constant__ InlineQueries iq) {
     constexpr int E = ChunkTraits<T>::kElems;
     constexpr int RW = kScanRW;
     constexpr int NVAL = RW * (QT + (NORM ? 1 : 0));
@@ -344,15 +317,37 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     // raw queries -> unit fp32 queries in shared memory, while the producer is already streaming.  For 8-element chunks the two
     // float4 halves of a chunk go to separate planes ([h][chunk] float4) so that a warp's LDS.128 over consecutive chunks is
     // bank-conflict free.
+    const void* const q_raw = p.q_inline ? static_cast<const void*>(iq.bytes) : p.q_raw;
     if (p.q_host != nullptr) {
         // queries in mapped pinned host memory (the host-buffer API): ONE CTA pulls them over PCIe and stages them in HBM,
         // the others wait for its flag and read the staged copy - 6 KB over the bus instead of 148 x 6 KB
         if (blockIdx.x == 0) {
             if (tid == 0) wait_seq_reached(p.done_seq, p.seq - 2u);     // the launch that last read this staging slot is done
             named_bar_sync(1, 256);
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_host);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(p.q_stage);
-            for (uint32_t i = tid; i < p.q_bytes / 4; i += 256) dst[i] = src[i];
+            // every load of a thread is in flight before its first store: one PCIe round trip for the block, not one per word
+            if ((reinterpret_cast<uintptr_t>(p.q_host) & 15u) == 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.q_host);      // reads up to 15 bytes past the block: slots are padded
+                uint4* dst = reinterpret_cast<uint4*>(p.q_stage);
+                const uint32_t n16 = (p.q_bytes + 15u) / 16u;
+                for (uint32_t i0 = tid; i0 < n16; i0 += 256 * 4) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (i0 + u * 256 < n16) v[u] = src[i0 + u * 256];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (i0 + u * 256 < n16) dst[i0 + u * 256] = v[u];
+                }
+            } else {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_host);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(p.q_stage);
+                const uint32_t n4 = p.q_bytes / 4u;
+                for (uint32_t i0 = tid; i0 < n4; i0 += 256 * 8) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (i0 + u * 256 < n4) v[u] = src[i0 + u * 256];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (i0 + u * 256 < n4) dst[i0 + u * 256] = v[u];
+                }
+            }
             __threadfence();
             named_bar_sync(1, 256);
             if (tid == 0) st_release_gpu_u32(p.q_flag, p.seq);
@@ -365,13 +360,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     for (uint32_t qi = 0; qi < (uint32_t)QT; ++qi) {
         double div = 1.0;
         if (qi < p.n_queries) {
-            const double nrm = block_query_norm(p.q_raw, p.q_dtype, (size_t)qi * p.dim, p.dim, s_red, tid);
+            const double nrm = block_query_norm(q_raw, p.q_dtype, (size_t)qi * p.dim, p.dim, s_red, tid);
             div = (p.metric == LVS_METRIC_COSINE) ? (nrm != 0.0 ? nrm : 1.1920929e-7) : 1.0;
             if (tid == 0) { s_div[qi] = div; s_qnorm[qi] = (float)nrm; }
         }
         for (uint32_t e = tid; e < p.q_stride; e += 256) {
             float v = 0.f;
-            if (qi < p.n_queries && (int)e < p.dim) v = (float)(load_as_f64(p.q_raw, p.q_dtype, (size_t)qi * p.dim + e) / div);
+            if (qi < p.n_queries && (int)e < p.dim) v = (float)(load_as_f64(q_raw, p.q_dtype, (size_t)qi * p.dim + e) / div);
             const uint32_t c = e / E, w = e % E;
             qsm[(size_t)qi * p.q_stride + (size_t)(w / 4) * (p.chunks_per_row * 4) + c * 4 + (w % 4)] = v;
         }
@@ -555,19 +550,32 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
 
     const uint32_t nq = p.n_queries;
     const uint32_t C = n_items / nq;
-    double* qs = reinterpret_cast<double*>(smem + finalize_query_offset());
     uint32_t owned = 0;                                   // queries whose final local result this CTA produced
+    const bool early_ready = p.host_ready != nullptr && nq == 1 && !p.exchange;
 #pragma unroll 1
     for (uint32_t w = h; w < n_items; w += H) {
         const uint32_t qi = w % nq, cy = w / nq;
         named_bar_sync(1, NCT);                           // the previous item's shared memory is no longer read
-        for (int e = tid; e < p.dim; e += NCT) qs[e] = load_as_f64(p.q_raw, p.q_dtype, (size_t)qi * p.dim + e) / s_div[qi];
+        const auto stage_q = [&](double* qdst) {
+            for (int e = tid; e < p.dim; e += NCT) qdst[e] = load_as_f64(q_raw, p.q_dtype, (size_t)qi * p.dim + e) / s_div[qi];
+        };
         FinResult r;
-        const bool mine = finalize_body<KPL, true>(fp, qi, cy, C, smem, s_qnorm[qi], r);
-        if (tid == 0) stamp(p.dbg_times, mine ? 6 : 5);   // 5: a helper's share of the rescoring is done; 6: the result is ordered
+        const bool mine = finalize_body<KPL>(fp, qi, cy, C, smem, s_qnorm[qi], r, stage_q);
         if (!mine) continue;
         owned |= 1u << qi;
-        if (!p.exchange) { finalize_store_local(fp, qi, r, tid); continue; }
+        if (!p.exchange) {
+            finalize_store_local(fp, qi, r, tid);
+            if (early_ready) {
+                // the only result of this launch is stored: tell the polling host now, the housekeeping below is device business.
+                // One system-scope release by one thread: the barrier orders every thread's stores before it, the fence is cumulative
+                named_bar_sync(1, NCT);
+                if (tid == 0) {
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.host_ready), "r"(p.host_ready_val) : "memory");
+                    stamp(p.dbg_times, 13);
+                }
+            }
+            continue;
+        }
         // sharded collection: this query's local top-k (+ its flag) -> every rank's gather buffer
         const size_t qk = (size_t)nq * fp.k;
         for (uint32_t c = tid; c < r.ncand + fp.k; c += NCT) {
@@ -604,16 +612,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     }
     // the helper that leaves last re-arms the tickets for the next launch, publishes the launch's completion on the device and,
     // for host-polled searches, in host memory (every result store above is fenced at system scope before its CTA checks out)
-    if (p.host_ready != nullptr) __threadfence_system();
-    named_bar_sync(1, NCT);
-    if (tid == 0) stamp(p.dbg_times, 7);                  // results stored (and merged)
-    if (tid == 0 && atomicAdd(p.ticket + 1, 1u) == H - 1) {
-        p.ticket[0] = 0; p.ticket[1] = 0;
-        __threadfence();
-        st_release_gpu_u32(p.done_seq, p.seq);
-        if (p.host_ready != nullptr) {
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.host_ready), "r"(p.host_ready_val) : "memory");
+    named_bar_sync(1, NCT);                               // every thread's result stores are ordered before thread 0's fence below
+    if (tid == 0) {
+        if (owned) stamp(p.dbg_times, 7);                 // results stored (and merged)
+        if (p.host_ready != nullptr && !early_ready) __threadfence_system();   // cumulative over this CTA's stores to host memory
+        if (atomicAdd(p.ticket + 1, 1u) == H - 1) {
+            p.ticket[0] = 0; p.ticket[1] = 0;
+            __threadfence();
+            st_release_gpu_u32(p.done_seq, p.seq);
+            if (p.host_ready != nullptr && !early_ready)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.host_ready), "r"(p.host_ready_val) : "memory");
         }
     }
 }

@@ -9,8 +9,8 @@
 namespace lvs {
 
 template <typename T, int QT, int KPL, bool NORM, bool FILTER>
-static cudaError_t launch_scan_inst(const ScanParams& p, const FinalizeParams& fp, const ExchangeParams& xp, int grid, size_t smem, cudaStream_t st,
-                                    size_t smem_optin) {
+static cudaError_t launch_scan_inst(const ScanParams& p, const FinalizeParams& fp, const ExchangeParams& xp, const InlineQueries& iq, int grid,
+                                    size_t smem, cudaStream_t st, size_t smem_optin) {
     static std::once_flag once;
     static cudaError_t once_err = cudaSuccess;
     auto kfn = scan_topk_kernel<T, QT, KPL, NORM, FILTER>;
@@ -29,13 +29,13 @@ static cudaError_t launch_scan_inst(const ScanParams& p, const FinalizeParams& f
     la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see the kernel's header
     la[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = la; cfg.numAttrs = p.pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kfn, p, fp, xp);
+    return cudaLaunchKernelEx(&cfg, kfn, p, fp, xp, iq);
 }
 
 template <typename T, bool NORM, bool FILTER>
-static cudaError_t launch_scan_tnf(int qt, int kpl, const ScanParams& p, const FinalizeParams& fp, const ExchangeParams& xp, int grid, size_t smem,
-                                   cudaStream_t st, size_t smem_optin) {
-#define LVS_CASE(Q_, K_) if (qt == Q_ && kpl == K_) return launch_scan_inst<T, Q_, K_, NORM, FILTER>(p, fp, xp, grid, smem, st, smem_optin);
+static cudaError_t launch_scan_tnf(int qt, int kpl, const ScanParams& p, const FinalizeParams& fp, const ExchangeParams& xp, const InlineQueries& iq,
+                                   int grid, size_t smem, cudaStream_t st, size_t smem_optin) {
+#define LVS_CASE(Q_, K_) if (qt == Q_ && kpl == K_) return launch_scan_inst<T, Q_, K_, NORM, FILTER>(p, fp, xp, iq, grid, smem, st, smem_optin);
     LVS_CASE(1, 1) LVS_CASE(1, 2) LVS_CASE(1, 4) LVS_CASE(1, 8)
     LVS_CASE(2, 1) LVS_CASE(2, 2) LVS_CASE(2, 4)
     LVS_CASE(4, 1) LVS_CASE(4, 2)
@@ -47,7 +47,7 @@ static cudaError_t launch_scan_tnf(int qt, int kpl, const ScanParams& p, const F
 
 #define LVS_SCAN_ENTRY(name) \
     cudaError_t name(int qt, int kpl, bool filter, const lvs::ScanParams& p, const lvs::FinalizeParams& fp, const lvs::ExchangeParams& xp, \
-                     int grid, size_t smem, cudaStream_t st, size_t smem_optin)
+                     const lvs::InlineQueries& iq, int grid, size_t smem, cudaStream_t st, size_t smem_optin)
 LVS_SCAN_ENTRY(lvs_launch_scan_f32);        // fp32 shards (cosine rows are stored unit-norm; dot uses the same kernel)
 LVS_SCAN_ENTRY(lvs_launch_scan_bf16_cos);   // bf16 shards, cosine: the row norm is fused into the scan
 LVS_SCAN_ENTRY(lvs_launch_scan_bf16_dot);   // bf16 shards, dot product

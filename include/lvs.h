@@ -29,6 +29,7 @@ extern "C" {
 #define LVS_ENOMEM (-3)     /* device or host allocation failed */
 #define LVS_ESTATE (-4)     /* library not initialised / no CUDA device */
 #define LVS_ELIMIT (-5)     /* k, dim or batch beyond what the kernels support */
+#define LVS_ENAN (-6)       /* a host query contains NaN (qdrant local mode refuses it too) */
 
 #define LVS_STORAGE_F32 0
 #define LVS_STORAGE_BF16 1
@@ -280,10 +281,13 @@ int lvs_last_search_timing(const lvs_collection* c, float* ms4, int* n_launches,
 /* Device time of the last (up to max_n, <= 256) scan-kernel launches, oldest first, from CUDA events recorded on the
  * launching stream, with the algorithmic bytes of each launch.  The stream must have been synchronised. */
 int lvs_scan_times(lvs_collection* c, int max_n, float* out_ms, double* out_bytes, int* n);
-/* Profiling aid (option "dbg_times" = 1): globaltimer stamps (ns) of the phases of the last scan-kernel launch on this handle -
+/* Profiling aid (option "dbg_times" = 1): 16 globaltimer stamps (ns) of the phases of the last scan-kernel launch on this handle -
  * [0] first CTA starts, then the LATEST CTA to reach: [1] queries normalised, [2] shard scanned, [3] list written, [4] helpers see every
- * list, [5] rescoring shares done, [6] result ordered, [7] result stored / merged. */
-int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns8);
+ * list, [5] candidates selected, [6] rescoring shares done, [7] result stored / merged; inside the selection: [8] list maxima and
+ * list heads loaded, [9] threshold found, [10] keys gathered; after the rescoring: [11] the ordering CTA has every exact score,
+ * [12] result ordered and proven, [13] completion word stored for the polling host;
+ * inside the rescoring: [14] candidate rows staged, [15] re-normalisations replayed. */
+int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns16);
 /* Tunables: "stage_kb", "stages", "grid", "force_kpl" (0 = auto), "timing" (1 = record CUDA events around every scan launch for
  * lvs_last_search_timing / lvs_scan_times; default 0; it serialises consecutive searches), "pdl" (1 = programmatic dependent launch
  * of the scan kernel, default),
