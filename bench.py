@@ -405,19 +405,25 @@ def run_ours(args) -> None:
             wait(h)
         barrier()
         t0 = time.perf_counter()
-        inflight = []
+        inflight, done_at = [], []
         for i in range(W, W + K):
             inflight.append(submit(qs[i]))
             if len(inflight) >= DEPTH:
                 wait(inflight.pop(0))
+                done_at.append(time.perf_counter())
         while inflight:
             wait(inflight.pop(0))
+            done_at.append(time.perf_counter())
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        gaps = np.diff(np.array(done_at)) * 1e3         # time between consecutive completions: the median ignores a host hiccup
         barrier()
         t0 = time.perf_counter()
+        each = []
         for i in range(W, W + K):                       # depth 1 (strict request / response)
+            t1 = time.perf_counter()
             wait(submit(qs[i]))
+            each.append((time.perf_counter() - t1) * 1e3)
         barrier()
         e2e1_ms = (time.perf_counter() - t0) * 1e3
         dev_ms, e2e_ms, e2e1_ms, kernel_ms, sync_ms, n_flagged = allmax(dev_ms, e2e_ms, e2e1_ms, kernel_ms, sync_ms, float(n_flagged))
@@ -452,7 +458,10 @@ def run_ours(args) -> None:
                 "e2e": {"value": K * Q / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Q * args.dim * 8,
                         "d2h_bytes_per_step": Q * k * 24 + Q * 8, "ms_per_step": e2e_ms / K, "in_flight": DEPTH,
                         "api": "lvs_search_submit/lvs_search_wait (C ABI, host buffers)" if world == 1 else "ShardedSearcher.submit/wait (host buffers)",
-                        "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K},
+                        "depth1_qps": K * Q / (e2e1_ms * 1e-3), "depth1_ms_per_step": e2e1_ms / K,
+                        "this_rank": {"p50_ms_between_completions": float(np.median(gaps)) if len(gaps) else None,
+                                      "max_ms_between_completions": float(gaps.max()) if len(gaps) else None,
+                                      "depth1_p50_ms": float(np.median(each)), "depth1_max_ms": float(max(each))}},
                 "unproven_queries": int(n_flagged), "gpu_launches": launches, "clocks": clocks, "steps": K, "warmup": W,
                 "queries_per_step": Q, "k": k}
 
@@ -537,6 +546,7 @@ def adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, 
     """QPS of `await store.search(collection="code_chunks", query_vector=<list of floats>, limit=k)` on the resident corpus."""
     import asyncio
 
+    from code_rag_b200 import client as C_
     from code_rag_b200.client import B200VectorStore, CollectionName, _HostCollection
     CODE = CollectionName.CODE_CHUNKS.value
     qs = make_queries(K + W, args.dim, seed=15)
@@ -567,6 +577,9 @@ def adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, 
         asyncio.run(store.connect())
         store._collections[CODE] = host_half(lambda *a, **kw: shard, n_local)
         dt, dtc = asyncio.run(timed(store))
+        C_._POLLED_SEARCH = False                        # the same calls through a worker thread (asyncio.to_thread), for comparison
+        dt_thread, dtc_thread = asyncio.run(timed(store))
+        C_._POLLED_SEARCH = True
         searcher.close()
         asyncio.run(store.close())                       # closes the shard
         api = "B200VectorStore.search (asyncio, list[float] in, list[dict] out)"
@@ -574,7 +587,7 @@ def adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, 
         from code_rag_b200 import sharded_store as SS
         plane = SS.ShardPlane.start()                    # collective; re-uses the NCCL group, opens the gloo control group + mailbox
         plane.shards[CODE], plane.searchers[CODE] = shard, searcher
-        dt = dtc = 0.0
+        dt = dtc = dt_thread = dtc_thread = 0.0
         if rank != 0:
             plane.serve()                                # until rank 0 shuts the plane down
         else:
@@ -584,8 +597,8 @@ def adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, 
             coll.plane, coll.name, coll.dim, coll.storage = plane, CODE, args.dim, args.storage
             coll.columns, coll.dicts = ["file_path", "entity_type", "language", "content_hash", "project_name"], [dict() for _ in range(5)]
             coll.tie_counts, coll.dup_keys = {}, {}
-            import threading
-            coll.lock = threading.Lock()
+            from code_rag_b200.client import _CollectionLock
+            coll.lock = _CollectionLock()
             coll.shards = []
             for s_ in range(world):
                 hs = SS._HostShard(coll, s_)
@@ -593,13 +606,17 @@ def adapter_leg(args, torch, dist, shard, searcher, n_local, rank, world, K, W, 
                 coll.shards.append(hs)
             store._collections[CODE] = coll
             dt, dtc = asyncio.run(timed(store))
+            C_._POLLED_SEARCH = False
+            dt_thread, dtc_thread = asyncio.run(timed(store))
+            C_._POLLED_SEARCH = True
             store._collections.clear()
             plane.shutdown()                             # the workers leave serve(); every rank closes its shard
         api = "ShardedB200VectorStore.search on rank 0 (asyncio; search commands through the shared-memory mailbox)"
     if rank != 0:
         return None
     return {"value": K / dt, "unit": UNIT, "ms_per_call": dt / K * 1e3, "api": api, "calls": K,
-            "gathered_qps": K / dtc, "metadata": "synthetic lazy ids / payloads over the resident shard(s)",
+            "gathered_qps": K / dtc, "through_a_worker_thread": {"ms_per_call": dt_thread / K * 1e3, "gathered_qps": K / dtc_thread},
+            "metadata": "synthetic lazy ids / payloads over the resident shard(s)",
             "h2d_bytes_per_step": args.dim * 8, "d2h_bytes_per_step": k * 24 + 8}
 
 

@@ -61,6 +61,7 @@ SIGNATURES: dict[str, tuple] = {
     "lvs_search_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]),
     "lvs_search_submit_sharded": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _ip]),
     "lvs_search_wait": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lvs_search_poll": (C.c_int, [_vp, C.c_int, _ip]),
     "lvs_search_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device_at": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lvs_search_device_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

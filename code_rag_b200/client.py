@@ -24,9 +24,94 @@ from typing import Any, Sequence
 
 import numpy as np
 
+import struct
+
 from . import _native as N
 from .collection import DeviceCollection
 from .errors import VectorStoreError
+
+_PACKERS: dict[int, struct.Struct] = {}
+
+
+def _as_query(query_vector) -> np.ndarray:
+    """list[float] (what an embedding provider hands to lattice) -> float64 [1, dim].  ``struct.pack`` converts a 768-element list
+    in a quarter of the time ``np.asarray`` takes; anything it refuses (nested sequences, strings) goes the numpy way and fails there
+    the way it always did."""
+    if type(query_vector) is list:
+        n = len(query_vector)
+        pk = _PACKERS.get(n)
+        if pk is None:
+            pk = _PACKERS[n] = struct.Struct(f"{n}d")
+        try:
+            return np.frombuffer(pk.pack(*query_vector), dtype=np.float64)[None, :]
+        except (struct.error, TypeError):
+            pass
+    return np.asarray(query_vector, dtype=np.float64)[None, :]
+
+
+class _CollectionLock:
+    """The lock of a collection's host half.  ``with lock:`` is exclusive - writes, blocking searches - and waits until the
+    pipelined searches in flight have been collected.  Such a search (``B200VectorStore.search`` on the event loop) holds the mutex
+    only while it submits (``try_enter`` ... ``entered``) and while it collects (``try_reenter`` ... ``reader_done``); several may be
+    in flight, they execute in submission order on the collection's stream, and no write can slip between a search's submission
+    and the moment its rows are turned into payloads.  A waiting writer keeps new readers out."""
+
+    def __init__(self):
+        self._m = threading.Lock()
+        self._c = threading.Condition(self._m)
+        self.readers = 0
+        self._writers = 0
+
+    def acquire(self, blocking: bool = True) -> bool:
+        if not self._m.acquire(blocking):
+            return False
+        if self.readers:
+            if not blocking:
+                self._m.release()
+                return False
+            self._writers += 1
+            try:
+                while self.readers:
+                    self._c.wait()
+            finally:
+                self._writers -= 1
+        return True
+
+    def release(self) -> None:
+        self._m.release()
+
+    def __enter__(self):
+        self.acquire()
+        return self
+
+    def __exit__(self, *exc):
+        self._m.release()
+
+    def try_enter(self, max_readers: int) -> bool:
+        """Non-blocking: the mutex for a reader about to submit; refused while a writer waits or `max_readers` are in flight."""
+        if not self._m.acquire(False):
+            return False
+        if self._writers or self.readers >= max_readers:
+            self._m.release()
+            return False
+        return True
+
+    def entered(self) -> None:
+        """The reader has submitted: it counts as in flight and gives the mutex back."""
+        self.readers += 1
+        self._m.release()
+
+    def try_reenter(self) -> bool:
+        return self._m.acquire(False)
+
+    def reenter(self) -> None:
+        self._m.acquire()
+
+    def reader_done(self) -> None:
+        """The reader (holding the mutex) has collected its result."""
+        self.readers -= 1
+        self._c.notify_all()
+        self._m.release()
 
 logger = logging.getLogger(__name__)
 
@@ -85,6 +170,9 @@ def _id_sort_key(point_id: Any):
 
 
 _INLINE_SEARCH_BYTES = 256 << 20      # shards up to this size (a ~50 us scan) are searched without leaving the event loop's thread
+_POLLED_SEARCH = os.environ.get("LATTICE_B200_POLLED_SEARCH", "1") != "0"   # 0: every large search takes a worker thread (A/B switch)
+_ENTER_SPINS = 2000          # event-loop turns a search waits for a free submit slot / for a writer before it takes a thread
+_POLL_SPINS = 20000          # event-loop turns a search polls its completion word before a thread waits for it
 
 
 class _HostCollection:
@@ -119,7 +207,7 @@ class _HostCollection:
         # the keys carried by more than one live point are tracked and such hits are put in id order on the host (search()).
         self.tie_counts: dict[int, int] = {}
         self.dup_keys: dict[int, int] = {}
-        self.lock = threading.Lock()
+        self.lock = _CollectionLock()
         # dev_factory exists so that the host-side bookkeeping can be unit-tested without a GPU (tests only)
         factory = dev_factory or DeviceCollection
         # timing off: no CUDA events around the kernels, so a search completes through the word its kernel stores into the pinned
@@ -362,7 +450,9 @@ class _HostCollection:
             return [self._hits(np.asarray(order, dtype=np.int64), np.zeros(len(order)))]
         if limit > N.MAX_K:
             raise ValueError(f"limit {limit} exceeds the largest supported top-k ({N.MAX_K})")
-        res = self.dev.search(query_vectors, self.device_limit(limit), want)
+        return self._shape(self.dev.search(query_vectors, self.device_limit(limit), want), limit)
+
+    def _shape(self, res, limit: int) -> list[list[dict[str, Any]]]:
         out = []
         for qi in range(res.rows.shape[0]):
             n = int(res.counts[qi])
@@ -371,6 +461,39 @@ class _HostCollection:
                                "result is the best of the largest candidate set", self.name, qi)
             out.append(self._hits(*self.in_id_order(res.rows[qi, :n], res.scores[qi, :n], limit)))
         return out
+
+    # The same search in three steps, for callers that must not block (``B200VectorStore.search`` on the event loop): begin
+    # submits (``lvs_search_submit``) and returns, ready polls the completion word the kernel stores, end collects and shapes.
+    # begin and end run under the collection's mutex, the wait in between does not (``_CollectionLock``).
+    MAX_IN_FLIGHT = 4                # the library's submit slots per collection
+
+    def search_begin(self, query_vectors: np.ndarray | None, limit: int, filters: dict[str, Any] | None) -> dict:
+        if query_vectors is None or limit <= 0 or len(query_vectors) == 0 or not hasattr(self.dev, "search_poll"):
+            return {"result": self.search(query_vectors, limit, filters)}
+        if limit > N.MAX_K:
+            raise ValueError(f"limit {limit} exceeds the largest supported top-k ({N.MAX_K})")
+        return {"ticket": self.dev.search_submit(query_vectors, self.device_limit(limit), self.want_codes(filters)), "limit": limit}
+
+    def search_ready(self, h: dict) -> bool:
+        return "ticket" not in h or self.dev.search_poll(h["ticket"])
+
+    def search_block(self, h: dict) -> None:
+        """Blocking wait (from a worker thread, when polling has gone on for too long); needs no host-side lock."""
+        if "ticket" in h:
+            h["res"] = self.dev.search_wait(h.pop("ticket"))
+
+    def search_end(self, h: dict) -> list[list[dict[str, Any]]]:
+        if "result" in h:
+            return h["result"]
+        self.search_block(h)
+        return self._shape(h["res"], h["limit"])
+
+    def search_discard(self, h: dict) -> None:
+        """The caller gave up (cancelled): the ticket must not stay in flight."""
+        try:
+            self.search_block(h)
+        except Exception:  # noqa: BLE001
+            pass
 
     def release_rows(self, rows) -> None:
         """Forget the ids and payloads of deleted rows and queue the rows for reuse."""
@@ -466,7 +589,7 @@ class _HostCollection:
         self = cls.__new__(cls)
         for k in cls._HOST_STATE:
             setattr(self, k, state[k])
-        self.lock = threading.Lock()
+        self.lock = _CollectionLock()
         self.tie_counts, self.dup_keys = {}, {}
         self.rebuild_tie_counts()
         self.dev = DeviceCollection.load_snapshot(os.path.join(directory, f"{name}.lvs"), name=name, device=device)
@@ -740,26 +863,71 @@ class B200VectorStore:
                      filters: dict[str, Any] | None = None) -> list[dict[str, Any]]:
         try:
             coll = self._get(collection)
-            q = None if query_vector is None else np.asarray(query_vector, dtype=np.float64)[None, :]
+            q = None if query_vector is None else _as_query(query_vector)
+            flt = filters or None
 
             def work():
                 with coll.lock:
-                    return coll.search(q, limit, filters or None)[0]
-            # A small collection (lattice's usual operating point: 10^4 - 10^5 chunks) answers in ~0.1 ms: hopping to a worker thread
-            # and back costs about as much as the search itself, so it runs inline when nobody else holds the collection; anything
-            # larger, or a contended collection, goes to a thread and leaves the event loop free (threading).
+                    return coll.search(q, limit, flt)[0]
+            # A small collection (lattice's usual operating point: 10^4 - 10^5 chunks) answers in tens of microseconds: it is searched
+            # inline when nobody else holds the collection.  Anything larger is SUBMITTED from the event loop (a non-blocking library
+            # call) and polled between yields - a hop to a worker thread and back costs 0.1-0.2 ms, as much as a whole step on eight
+            # GPUs - so concurrent awaits (asyncio.gather in query/engine.py:142-146) pipeline on the device instead of queueing
+            # behind a lock.  Filter-only lookups and contended collections take a thread (threading).
             inline = getattr(coll, "inline_bytes", None)
             if inline is not None and inline() <= _INLINE_SEARCH_BYTES and coll.lock.acquire(blocking=False):
                 try:
-                    results = coll.search(q, limit, filters or None)[0]
+                    results = coll.search(q, limit, flt)[0]
                 finally:
                     coll.lock.release()
+            elif _POLLED_SEARCH and q is not None and hasattr(coll, "search_begin") and hasattr(coll.lock, "try_enter"):
+                results = await self._search_polled(coll, q, limit, flt, work)
             else:
                 results = await asyncio.to_thread(work)
             logger.debug(f"Found {len(results)} results in {collection}")
             return results
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to search {collection}", cause=e)
+
+    @staticmethod
+    async def _search_polled(coll, q, limit, flt, work):
+        lock = coll.lock
+        spins = 0
+        while not lock.try_enter(coll.MAX_IN_FLIGHT):
+            spins += 1
+            if spins > _ENTER_SPINS:                     # a long write is under way: queue behind it in a thread
+                return await asyncio.to_thread(work)
+            await asyncio.sleep(0)
+        try:
+            h = coll.search_begin(q, limit, flt)
+        except BaseException:
+            lock.release()
+            raise
+        if h is None:                                    # not this way (sharded store: another command is under way)
+            lock.release()
+            return await asyncio.to_thread(work)
+        lock.entered()
+        try:
+            spins = 0
+            while not coll.search_ready(h):
+                spins += 1
+                if spins > _POLL_SPINS:                  # a long search: let a thread wait for it
+                    await asyncio.to_thread(coll.search_block, h)
+                    break
+                await asyncio.sleep(0)
+            while not lock.try_reenter():
+                await asyncio.sleep(0)
+        except BaseException:                            # cancelled (or the poll failed): the ticket must not stay in flight
+            lock.reenter()
+            try:
+                coll.search_discard(h)
+            finally:
+                lock.reader_done()
+            raise
+        try:
+            return coll.search_end(h)[0]
+        finally:
+            lock.reader_done()
 
     async def search_batch(self, collection: str, query_vectors: Sequence[Sequence[float]], limit: int = 10,
                            filters: dict[str, Any] | None = None) -> list[list[dict[str, Any]]]:

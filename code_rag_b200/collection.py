@@ -363,6 +363,12 @@ class DeviceCollection:
                                                     C.byref(t)), "lvs_search_submit_sharded")
         return (t.value, q.shape[0], int(k))
 
+    def search_poll(self, ticket: tuple[int, int, int]) -> bool:
+        """True once :meth:`search_wait` will not block on the device (``lvs_search_poll``)."""
+        d = C.c_int()
+        N.check(self._lib.lvs_search_poll(self._handle(), ticket[0], C.byref(d)), "lvs_search_poll")
+        return bool(d.value)
+
     def search_wait(self, ticket: tuple[int, int, int]) -> SearchResult:
         t, Q, k = ticket
         block, (ps, pr, pt, pc, pf) = _result_block(Q, k)

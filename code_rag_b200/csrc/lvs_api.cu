@@ -137,7 +137,8 @@ struct lvs_collection {
     Scratch s_qstage;                 // host queries staged by CTA 0, one slot per launch parity
     int opt_dyn_tiles = 1;
     int opt_dbg_times = 0;            // 1: the scan kernel stamps its phases (lvs_last_kernel_phases)
-    int opt_inline_query = 1;         // host queries of up to kInlineQueryBytes ride in the kernel's parameter block
+    int opt_inline_query = 1;         // a host query of up to kInlineQueryBytes rides in the kernel's parameter block ...
+    int opt_inline_max_mb = 1024;     // ... when the shard is at most this large
     InlineQueries iq;                 // ... assembled here (under the collection's lock)
     Scratch s_dbg_times;
     Scratch h_pin, h_pin2, h_flags;
@@ -904,8 +905,11 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, const void* h
         const uint32_t seq = c->launch_seq + 1;
         sp.seq = seq; sp.done_seq = c->d_counter + 10;
         InlineQueries& iq = c->iq;        // only the first cnt * qrow bytes mean anything; the launch copies the block
-        if (h_queries != nullptr && c->opt_inline_query && (size_t)cnt * qrow <= kInlineQueryBytes) {
-            // a handful of host queries: they travel in the kernel's parameter block (scan_kernel.cuh)
+        // One unfiltered host query on a shard that is scanned in well under a millisecond - where the microseconds count and there is
+        // no previous search worth overlapping with - travels in the kernel's parameter block (scan_kernel.cuh).  Long scans keep
+        // their parameters small: a launch with more than 4 KB of them does not start early behind its predecessor.
+        const bool short_scan = (double)c->n_rows * c->row_bytes <= (double)c->opt_inline_max_mb * 1048576.0;
+        if (h_queries != nullptr && c->opt_inline_query && cnt == 1 && !filter && short_scan && qrow <= kInlineQueryBytes) {
             sp.q_inline = 1u; sp.q_raw = nullptr;
             memcpy(iq.bytes, (const uint8_t*)h_queries + (size_t)first * qrow, (size_t)cnt * qrow);
         } else if (h_queries != nullptr) {
@@ -1530,6 +1534,26 @@ extern "C" int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores
     if (rcw != LVS_OK) { std::lock_guard<std::mutex> lk(c->mu); c->slots[ticket].in_use = false; return rcw; }
     std::lock_guard<std::mutex> lk(c->mu);
     return finish_locked(c, ticket, out_scores, out_rows, out_ties, out_counts, out_flags);
+}
+
+extern "C" int lvs_search_poll(lvs_collection* c, int ticket, int* done) {
+    bind_thread();
+    if (!c || !done) return fail(LVS_EINVAL, "NULL argument");
+    if (ticket < 0 || ticket >= kSubmitSlots) return fail(LVS_EINVAL, "bad ticket %d", ticket);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->slots[ticket].in_use) return fail(LVS_EINVAL, "ticket %d is not in flight", ticket);
+    }
+    auto& sl = c->slots[ticket];              // stable storage while the ticket is in flight
+    if (sl.poll) {
+        volatile uint32_t* w = (volatile uint32_t*)((uint8_t*)sl.h.p + sl.qbytes + ready_off(sl.Q, sl.k));
+        *done = *w == sl.ready_val ? 1 : 0;
+        return LVS_OK;
+    }
+    cudaError_t e = cudaEventQuery(sl.done);
+    if (e == cudaSuccess) { *done = 1; return LVS_OK; }
+    if (e == cudaErrorNotReady) { cudaGetLastError(); *done = 0; return LVS_OK; }
+    return fail(LVS_ECUDA, "search failed: %s", cudaGetErrorString(e));
 }
 
 extern "C" int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want,
@@ -2331,6 +2355,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "dyn_tiles")) c->opt_dyn_tiles = value ? 1 : 0;
     else if (!strcmp(name, "dbg_times")) c->opt_dbg_times = value ? 1 : 0;
     else if (!strcmp(name, "inline_query")) c->opt_inline_query = value ? 1 : 0;
+    else if (!strcmp(name, "inline_max_mb")) c->opt_inline_max_mb = value < 0 ? 0 : value;
     else if (!strcmp(name, "gemm_min_q")) c->opt_gemm_min_q = value;
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;

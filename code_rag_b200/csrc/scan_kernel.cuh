@@ -49,6 +49,11 @@ constexpr size_t kScanStaticSmem = 1024;   // static shared memory of the kernel
 // instruction): no PCIe read, no staging hop, no flag.  8 KB = one 1024-dimensional float64 query.
 constexpr uint32_t kInlineQueryBytes = 8192;
 struct InlineQueries { uint8_t bytes[kInlineQueryBytes]; };
+// The block is a parameter of the INLINE instantiations only (one query slot, no filter): kernels whose parameters stay below
+// 4 KB launch the classic way, and those are the ones long scans use - see DESIGN.md for what the large block costs them.
+struct NoInlineQueries { uint8_t bytes[16]; };
+template <bool INLINE> struct InlineBlock { using type = NoInlineQueries; };
+template <> struct InlineBlock<true> { using type = InlineQueries; };
 
 struct ScanParams {
     const uint8_t* base;        // shard, row-major, row stride = row_bytes
@@ -81,7 +86,7 @@ struct ScanParams {
     void* q_stage;              //   them here (device) for everybody, then publishes *q_flag = seq; q_raw == q_stage
     uint32_t* q_flag;
     uint32_t q_bytes;           // n_queries * dim * sizeof(query element)
-    uint32_t q_inline;          // 1: the raw queries are in the InlineQueries parameter (q_raw / q_host are unused)
+    uint32_t q_inline;          // 1: the raw queries are in the InlineQueries parameter of an INLINE instantiation (q_raw / q_host unused)
     unsigned long long* dbg_times;  // optional [8]: globaltimer stamps of the launch's phases (min of the starts, max of the rest); profiling aid
     uint32_t* host_ready;       // optional word in mapped pinned host memory: set to host_ready_val (system-scope release) when every
     uint32_t host_ready_val;    //   result of this launch has been stored - the host polls it instead of synchronising an event
@@ -175,10 +180,10 @@ __device__ __forceinline__ void wait_seq_reached(const uint32_t* word, uint32_t 
     while ((int32_t)(ld_acquire_gpu_u32(word) - target) < 0) __nanosleep(64);
 }
 
-template <typename T, int QT, int KPL, bool NORM, bool FILTER>
+template <typename T, int QT, int KPL, bool NORM, bool FILTER, bool INLINE>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid_constant__ ScanParams p, const __grid_constant__ FinalizeParams fp,
                                                                     const __grid_constant__ ExchangeParams xp,
-                                                                    const __grid_constant__ InlineQueries iq) {
+                                                                    const __grid_constant__ typename InlineBlock<INLINE>::type iq) {
     constexpr int E = ChunkTraits<T>::kElems;
     constexpr int RW = kScanRW;
     constexpr int NVAL = RW * (QT + (NORM ? 1 : 0));
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
     // raw queries -> unit fp32 queries in shared memory, while the producer is already streaming.  For 8-element chunks the two
     // float4 halves of a chunk go to separate planes ([h][chunk] float4) so that a warp's LDS.128 over consecutive chunks is
     // bank-conflict free.
-    const void* const q_raw = p.q_inline ? static_cast<const void*>(iq.bytes) : p.q_raw;
+    const void* const q_raw = INLINE ? static_cast<const void*>(iq.bytes) : p.q_raw;
     if (p.q_host != nullptr) {
         // queries in mapped pinned host memory (the host-buffer API): ONE CTA pulls them over PCIe and stages them in HBM,
         // the others wait for its flag and read the staged copy - 6 KB over the bus instead of 148 x 6 KB

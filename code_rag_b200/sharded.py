@@ -240,6 +240,8 @@ class ShardedSearcher:
         if q.ndim == 1:
             q = q[None, :]
         Q, dim = q.shape
+        if Q == 0:                                     # nothing to search (every rank sees the same empty batch: no collective)
+            return {"empty": int(k)}
         if self.world == 1 or self.exchange_mode == "p2p":
             base = self.shard.search_counter + 1
             ticket = self.shard.search_submit(q, k, want) if self.world == 1 else \
@@ -257,9 +259,21 @@ class ShardedSearcher:
         b["queries"], b["k"] = q, k
         return b
 
+    def poll(self, handle) -> bool:
+        """True once :meth:`wait` will not block on the device."""
+        if "empty" in handle:
+            return True
+        if "ticket" in handle:
+            return self.shard.search_poll(handle["ticket"])
+        return bool(handle["event"].query())
+
     def wait(self, handle):
         """Blocks until the search has finished; flagged queries are repeated (every rank takes the same decision, so this stays
         a collective); raises when the exchange reported a missing peer."""
+        if "empty" in handle:
+            k = handle["empty"]
+            return (np.zeros((0, k)), np.zeros((0, k), dtype=np.int64), np.zeros((0, k), dtype=np.uint64), np.zeros(0, dtype=np.uint32),
+                    np.zeros(0, dtype=np.int32))
         if "ticket" in handle:
             res = self.shard.search_wait(handle["ticket"])
             scores, rows, ties, counts, flags = res.scores, res.rows, res.ties, res.counts, res.flags

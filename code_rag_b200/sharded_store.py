@@ -33,8 +33,8 @@ from typing import Any, Callable, Sequence
 import numpy as np
 
 from . import _native as N
-from .client import (B200VectorStore, CollectionName, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key, _tie_key,
-                     vector_result_from_payload)
+from .client import (B200VectorStore, CollectionName, _CollectionLock, _HostCollection, _INDEX_FIELDS, _canonical_id, _id_sort_key,
+                     _tie_key, vector_result_from_payload)
 from .errors import VectorStoreError
 
 logger = logging.getLogger(__name__)
@@ -200,6 +200,8 @@ class ShardPlane:
         self.pending: list[list[tuple]] = [[] for _ in range(world)]     # controller: queued writes per rank
         self.closed = False
         self._deferred: int | None = None
+        self._polled: dict | None = None          # controller: the search begun with search_begin and not yet ended
+        self.polled_searches = 0                  # ... how many took that route (tests, diagnostics)
         self.mailbox: _Mailbox | None = None
         if world > 1 and os.environ.get("LATTICE_B200_MAILBOX", "1") != "0":
             self.mailbox = _Mailbox(rank, world, ctl_group)              # collective
@@ -256,7 +258,9 @@ class ShardPlane:
                 # the workers' replies to the previous fast-path search (see below) are due before the mailbox is written again
                 seq, self._deferred = self._deferred, None
                 bad = [(r + 1, msg) for r, (ok, msg) in enumerate(mb.collect(seq)) if not ok]
-                if bad:
+                if bad and op == "shutdown":             # the workers must still be released
+                    logger.warning("previous search failed on %s", "; ".join(f"rank {r}: {msg}" for r, msg in bad))
+                elif bad:
                     raise RuntimeError("previous search: " + "; ".join(f"rank {r}: {msg}" for r, msg in bad))
             if op == "search" and mb is not None and mb.fits(common[0].shape[0], common[0].shape[1], name):
                 # fast path: the command travels through shared memory, the replies through the workers' status slots.  The controller
@@ -277,6 +281,52 @@ class ShardPlane:
         if bad:
             raise RuntimeError("; ".join(f"rank {r}: {msg}" for r, msg in bad))
         return [rep[1] for rep in replies]
+
+    # ---- the same fast-path search in three steps, for the event loop (client.B200VectorStore._search_polled) ------------------
+    def search_begin(self, name: str, queries: np.ndarray, k: int, want) -> dict | None:
+        """Controller, non-blocking: posts the search to the workers and submits it on this rank's shard.  Returns a handle for
+        ``search_ready`` / ``search_end``, or None when this search has to take ``call`` (another command under way, writes queued,
+        no mailbox, a searcher without the pipelined pair).  The plane stays locked until ``search_end``: one search at a time
+        across the shards (a flagged query is repeated collectively - every rank must be at the same point of the command stream)."""
+        if self.rank != 0:
+            raise RuntimeError("only rank 0 drives the shard plane")
+        if self._polled is not None or not self.lock.acquire(blocking=False):
+            return None
+        try:
+            mb, searcher = self.mailbox, self.searchers.get(name)
+            if (self.closed or mb is None or any(self.pending) or searcher is None or not hasattr(searcher, "poll")
+                    or not mb.fits(queries.shape[0], queries.shape[1], name)):
+                self.lock.release()
+                return None
+            if self._deferred is not None:
+                seq, self._deferred = self._deferred, None
+                bad = [(r + 1, msg) for r, (ok, msg) in enumerate(mb.collect(seq)) if not ok]
+                if bad:
+                    raise RuntimeError("previous search: " + "; ".join(f"rank {r}: {msg}" for r, msg in bad))
+            if self._device_factory is None:
+                import torch
+                torch.cuda.set_device(self.device)
+            seq = mb.post(mb.OP_SEARCH, name, queries, int(k), want)
+            self._deferred = seq                         # the workers' replies are due before the next command, whatever happens below
+            self._polled = {"seq": seq, "searcher": searcher, "handle": searcher.submit(queries, int(k), want)}
+            self.polled_searches += 1
+            return self._polled
+        except BaseException:
+            self._polled = None
+            self.lock.release()
+            raise
+
+    def search_ready(self, h: dict) -> bool:
+        return h["searcher"].poll(h["handle"])
+
+    def search_end(self, h: dict):
+        """(scores, rows, counts, flags) of the merged result; blocks if the search has not finished.  Unlocks the plane."""
+        try:
+            scores, rows, _ties, counts, flags = h["searcher"].wait(h["handle"])
+            return scores, rows, counts, flags
+        finally:
+            self._polled = None
+            self.lock.release()
 
     def queue(self, shard: int, name: str, method: str, *args) -> None:
         with self.lock:
@@ -510,7 +560,7 @@ class _ShardedHostCollection:
         self.dicts: list[dict[Any, int]] = [dict() for _ in self.columns]
         self.tie_counts: dict[int, int] = {}
         self.dup_keys: dict[int, int] = {}
-        self.lock = threading.Lock()
+        self.lock = _CollectionLock()
         plane.call("create", name, (dim, storage, N.MAX_FILTER_COLS))
         self.shards = [_HostShard(self, s) for s in range(plane.world)]
 
@@ -541,7 +591,7 @@ class _ShardedHostCollection:
         self.plane, self.name, self.dim, self.storage = plane, name, state["dim"], state["storage"]
         self.columns, self.dicts = state["columns"], state["dicts"]
         self.tie_counts, self.dup_keys = {}, {}
-        self.lock = threading.Lock()
+        self.lock = _CollectionLock()
         self.shards = [_HostShard(self, s) for s in range(plane.world)]
         for sh, st in zip(self.shards, state["shards"]):
             for k in cls._SHARD_STATE:
@@ -640,8 +690,13 @@ class _ShardedHostCollection:
             raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
         if np.isnan(q).any():
             raise ValueError("Query vector must not contain NaN")
+        if q.shape[0] == 0:
+            return []
         k_dev = self.shards[0].device_limit(int(limit))
         scores, rows, counts, flags = self.plane.call("search", self.name, (q, k_dev, want))[0]
+        return self._shape(scores, rows, counts, flags, limit)
+
+    def _shape(self, scores, rows, counts, flags, limit: int) -> list[list[dict[str, Any]]]:
         out = []
         for qi in range(rows.shape[0]):
             n = int(counts[qi])
@@ -649,6 +704,44 @@ class _ShardedHostCollection:
                 logger.warning("search on %s: exactness bound not met for query %d (many near-ties)", self.name, qi)
             out.append(self._hits(*self.shards[0].in_id_order(rows[qi, :n], scores[qi, :n], limit, self._id_of)))
         return out
+
+    # three-step form (see client._HostCollection.search_begin): begin may return None = "take a thread and call search()"
+    MAX_IN_FLIGHT = 1
+
+    def search_begin(self, query_vectors, limit: int, filters) -> dict | None:
+        if query_vectors is None or limit <= 0:
+            return None
+        if limit > N.MAX_K:
+            raise ValueError(f"limit {limit} exceeds the largest supported top-k ({N.MAX_K})")
+        q = np.ascontiguousarray(query_vectors, dtype=np.float64)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}], got {q.shape}")
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")
+        if q.shape[0] == 0:
+            return None
+        h = self.plane.search_begin(self.name, q, self.shards[0].device_limit(int(limit)), self.want_codes(filters))
+        if h is not None:
+            h["limit"] = limit
+        return h
+
+    def search_ready(self, h: dict) -> bool:
+        return self.plane.search_ready(h)
+
+    def search_block(self, h: dict) -> None:
+        if "res" not in h:
+            h["res"] = self.plane.search_end(h)
+
+    def search_end(self, h: dict):
+        self.search_block(h)
+        scores, rows, counts, flags = h["res"]
+        return self._shape(scores, rows, counts, flags, h["limit"])
+
+    def search_discard(self, h: dict) -> None:
+        try:
+            self.search_block(h)
+        except Exception:  # noqa: BLE001
+            pass
 
     def scroll(self, filters, limit: int):
         return self.search(None, limit, filters)[0]

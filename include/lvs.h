@@ -104,6 +104,9 @@ int lvs_search(lvs_collection* c, const void* queries, int dtype, int Q, int k, 
 int lvs_search_submit(lvs_collection* c, const void* queries, int dtype, int Q, int k, const uint32_t* want, int* ticket);
 int lvs_search_wait(lvs_collection* c, int ticket, double* out_scores, int64_t* out_rows, uint64_t* out_ties,
                     uint32_t* out_counts, int32_t* out_flags);
+/* Non-blocking: *done = 1 once the device work of `ticket` has finished (lvs_search_wait will then return without waiting, unless it
+ * has flagged queries to repeat).  For event loops (the asyncio adapter polls between yields instead of parking a thread). */
+int lvs_search_poll(lvs_collection* c, int ticket, int* done);
 /* A search of up to 4 queries on the scan path is ONE kernel that stores its result block and then a completion word into the
  * slot's mapped pinned memory; lvs_search_wait polls that word (no event between consecutive kernels, so searches submitted back
  * to back keep overlapping on the GPU).  Batches and timing mode complete through a CUDA event as before. */

@@ -116,6 +116,26 @@ class FakeDevice:
             res.counts[i] = len(order)
         return res
 
+    # pipelined pair + poll (DeviceCollection.search_submit / search_poll / search_wait): the search runs at submit, the first
+    # poll says "not yet" so that callers' polling loops are exercised
+    def search_submit(self, queries, k, want=None):
+        if len(getattr(self, "_tickets", {})) >= 4:
+            raise RuntimeError("4 searches already in flight")
+        if not hasattr(self, "_tickets"):
+            self._tickets, self._next_ticket = {}, 0
+        t = self._next_ticket
+        self._next_ticket += 1
+        self._tickets[t] = [self.search(queries, k, want), 0]
+        return (t, 0, k)
+
+    def search_poll(self, ticket):
+        ent = self._tickets[ticket[0]]
+        ent[1] += 1
+        return ent[1] > 1
+
+    def search_wait(self, ticket):
+        return self._tickets.pop(ticket[0])[0]
+
     def close(self):
         self.closed = True
 
@@ -198,6 +218,18 @@ class FakeShardSearcher:
         g = gathered.numpy()
         s, r, t = merge_lists_numpy(g[:, 0].view(np.float64), g[:, 1], g[:, 2].view(np.uint64), k)
         return s, r, t, (r >= 0).sum(axis=1).astype(np.uint32), np.zeros(Q, dtype=np.int32)
+
+    # the pipelined pair the controller's event-loop path uses (ShardedSearcher.submit / poll / wait): the search (and its
+    # collective) runs at submit; the first poll says "not yet"
+    def submit(self, queries, k, want=None):
+        return {"res": self.search(queries, k, want), "polls": 0}
+
+    def poll(self, handle):
+        handle["polls"] += 1
+        return handle["polls"] > 1
+
+    def wait(self, handle):
+        return handle["res"]
 
     def close(self):
         pass

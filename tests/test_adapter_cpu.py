@@ -73,3 +73,80 @@ def test_snapshot_host_half_round_trip(tmp_path, monkeypatch):
 
 def test_edge_cases():
     asyncio.run(S.scenario_edge_cases(FakeDevice))
+
+
+def test_scenarios_through_the_polled_search_path(monkeypatch):
+    """Large collections are searched by submit + poll on the event loop (no worker thread); force that path on the small ones."""
+    from code_rag_b200 import client
+    monkeypatch.setattr(client, "_INLINE_SEARCH_BYTES", -1)
+    asyncio.run(S.scenario_parity_with_oracle(FakeDevice, n=600, dim=32))
+    asyncio.run(S.scenario_reindex_churn(FakeDevice))
+    asyncio.run(S.scenario_errors(FakeDevice))
+    for seed in (3,):
+        asyncio.run(S.scenario_random_ops(FakeDevice, seed))
+
+
+def test_gathered_searches_pipeline_and_writers_wait(monkeypatch):
+    """asyncio.gather of searches on one collection (query/engine.py:142-146): every search sees the collection as it was when it
+    was submitted, up to four are in flight, and a write issued meanwhile goes in between two searches, never inside one."""
+    import threading
+
+    import numpy as np
+
+    import lvs_synth as synth
+    from code_rag_b200 import client
+    monkeypatch.setattr(client, "_INLINE_SEARCH_BYTES", -1)
+
+    peak = [0]
+
+    class Counting(FakeDevice):
+        def search_submit(self, queries, k, want=None):
+            t = super().search_submit(queries, k, want)
+            peak[0] = max(peak[0], len(self._tickets))
+            return t
+
+    async def run():
+        st = client.B200VectorStore(dimensions=16, _device_factory=Counting)
+        await st.connect(); await st.create_collections()
+        x, _ = synth.unit_rows(200, 16, seed=5)
+        ids = synth.random_uuids(200, 9)
+        pl = [{"file_path": f"f{i % 7}.py", "entity_name": f"e{i}"} for i in range(200)]
+        await st.upsert("code_chunks", ids, x.astype(np.float64).tolist(), pl)
+        qs = [x[i].tolist() for i in range(24)]
+        one_by_one = [await st.search("code_chunks", q, 5) for q in qs]
+        together = await asyncio.gather(*[st.search("code_chunks", q, 5) for q in qs])
+        ids_of = lambda hits: [h["id"] for h in hits]  # noqa: E731  (scores drift with local mode's in-place re-normalisation)
+        assert [ids_of(h) for h in together] == [ids_of(h) for h in one_by_one]
+        assert 2 <= peak[0] <= 4
+        # a delete in the middle of a gather: each search answers from before or from after it, as a whole
+        before = {i: ids_of(r) for i, r in enumerate(one_by_one)}
+        res = await asyncio.gather(*[st.search("code_chunks", q, 5) for q in qs[:12]], st.delete("code_chunks", {"file_path": "f3.py"}),
+                                   *[st.search("code_chunks", q, 5) for q in qs[12:]])
+        after = [ids_of(await st.search("code_chunks", q, 5)) for q in qs]
+        hits = res[:12] + res[13:]
+        assert any(before[i] != after[i] for i in range(24))
+        for i, h in enumerate(hits):
+            assert ids_of(h) == before[i] or ids_of(h) == after[i]
+            assert all(p["payload"]["entity_name"] == f"e{ids.index(p['id'])}" for p in h)
+        assert st._collections["code_chunks"].lock.readers == 0
+        await st.close()
+    asyncio.run(run())
+
+    # the lock itself: an exclusive acquire waits for the readers in flight and keeps new ones out meanwhile
+    lk = client._CollectionLock()
+    assert lk.try_enter(4)
+    lk.entered()
+    got = []
+    th = threading.Thread(target=lambda: (lk.acquire(), got.append(1), lk.release()))
+    th.start()
+    th.join(0.2)
+    assert th.is_alive() and not got
+    for _ in range(100):                          # the writer is waiting by now (or will be): readers are refused once it is
+        if not lk.try_enter(4):
+            break
+        lk.release()
+        th.join(0.01)
+    assert lk.try_reenter()
+    lk.reader_done()
+    th.join(5)
+    assert got == [1] and lk.readers == 0

@@ -393,6 +393,22 @@ def test_submit_wait_pipeline(lib):
         got.append(dev.search_wait(inflight.pop(0)))
     for i in range(len(q)):
         _assert_same(got[i], 0, *ora.search_topk_rows(q[i].astype(np.float64), 10), REL_F32)
+    # lvs_search_poll: turns true by itself (kernel-stored completion word for a single query, the slot's event for a staged
+    # batch), after which the wait returns the same answer a blocking search gives
+    import time
+    from code_rag_b200.errors import NativeLibraryError
+    for Qn in (1, 40):
+        t = dev.search_submit(np.tile(q, (5, 1))[:Qn].astype(np.float64), 10)
+        t0 = time.perf_counter()
+        while not dev.search_poll(t):
+            assert time.perf_counter() - t0 < 5.0, "the search never completed"
+        res = dev.search_wait(t)
+        assert res.rows.shape == (Qn, 10) and (res.counts == 10).all()
+        for i in range(Qn):
+            rows_o, _ = ora.search_topk_rows(q[i % len(q)].astype(np.float64), 10)
+            assert np.array_equal(res.rows[i], rows_o)
+    with pytest.raises(NativeLibraryError):
+        dev.search_poll((3, 1, 10))            # not in flight
     dev.close()
 
 

@@ -82,6 +82,11 @@ async def _sharded_specifics(make_store, world):
     got = await store.search_batch(collection=CODE, query_vectors=q.tolist(), limit=6, filters={"project_name": "alpha"})
     for qi in range(4):
         _same_hits(got[qi], ora.search(CODE, q[qi].tolist(), limit=6, filters={"project_name": "alpha"}), what=f"sharded batch {qi}")
+    # concurrent awaits (query/engine.py:142-146): one search at a time crosses the shards, the others queue - all answer correctly
+    import asyncio
+    many = await asyncio.gather(*[store.search(collection=CODE, query_vector=q[i % 4].tolist(), limit=5) for i in range(8)])
+    for i, h in enumerate(many):
+        _same_hits(h, ora.search(CODE, q[i % 4].tolist(), limit=5), rel=1e-6, what=f"gathered {i}")
     # the filter-only lookup orders by id across shards
     _same_hits(await store.search(collection=CODE, query_vector=None, limit=40, filters={"project_name": "gamma"}),
                ora.search(CODE, None, limit=40, filters={"project_name": "gamma"}), what="sharded scroll")
@@ -153,6 +158,7 @@ def _worker(rank, world, port, out_dir):
                 await S.scenario_random_ops(factory, seed)
             await S.scenario_exact_ties_follow_the_id(factory)
             await S.scenario_edge_cases(factory)
+            assert plane.polled_searches > 0 and plane._polled is None, "searches must take the event-loop path (submit + poll)"
             return "done"
         got = run(main, device_factory=ExactTieDevice, searcher_factory=FakeShardSearcher)
         assert got == ("done" if rank == 0 else None)
