@@ -208,7 +208,8 @@ async def scenario_client_shim(factory):
     # query_points (what QdrantManager.search issues, client.py:142-148)
     res = await store.client.query_points(collection_name=CODE, query=x[4].astype(np.float64).tolist(), limit=3, query_filter=flt2, with_payload=True)
     via = await store.search(collection=CODE, query_vector=x[4].astype(np.float64).tolist(), limit=3, filters={"project_name": "p"})
-    assert [(p.id, p.payload) for p in res.points] == [(h["id"], h["payload"]) for h in via] and abs(res.points[0].score - 1.0) < 1e-6
+    tol = 1e-4 if str(getattr(store, "_storage", "f32")).startswith("bf") else 1e-6      # a bf16 shard stores the rounded vector
+    assert [(p.id, p.payload) for p in res.points] == [(h["id"], h["payload"]) for h in via] and abs(res.points[0].score - 1.0) < tol
     await store.close()
 
 
