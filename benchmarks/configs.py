@@ -110,6 +110,36 @@ def c1():
         assert rc == 0
     variants["c_abi_call_only"] = {"wall_ms": statistics.median(cw), "wall_ms_p10": sorted(cw)[len(cw) // 10]}
     phases = variants["query_in_kernel_params"]["kernel_phases_us"]
+    # the same collection behind the QdrantManager drop-in: `await store.search(collection=, query_vector=list, limit=10)` with ids and
+    # payload dicts, filtered and not (what lattice's VectorSearcher issues, query/vector_search.py:97-128)
+    import asyncio
+    import uuid
+
+    from code_rag_b200.client import B200VectorStore
+
+    async def adapter():
+        st = B200VectorStore(dimensions=dim, storage="f32")
+        await st.connect(); await st.create_collections()
+        ids = [str(uuid.UUID(int=i + 1)) for i in range(n)]
+        pl = [{"file_path": f"src/f{i % 400}.py", "entity_type": "function", "entity_name": f"fn{i}", "language": "python",
+               "content_hash": "h", "project_name": f"p{i % 4}", "content": "def f(): pass"} for i in range(n)]
+        xv = x.astype(np.float64)
+        for s0 in range(0, n, 2000):
+            await st.upsert(collection="code_chunks", ids=ids[s0:s0 + 2000], vectors=xv[s0:s0 + 2000].tolist(), payloads=pl[s0:s0 + 2000])
+        ql = [q[0].tolist() for q in qs]
+        res = {}
+        for label, flt in (("no_filter", None), ("project_filter", {"project_name": "p1"})):
+            w = []
+            for i in range(260):
+                t0 = time.perf_counter()
+                hits = await st.search(collection="code_chunks", query_vector=ql[i % len(ql)], limit=10, filters=flt)
+                if i >= 60:
+                    w.append((time.perf_counter() - t0) * 1e3)
+            assert len(hits) == 10
+            res[label] = {"ms_per_await": statistics.median(w), "p10": sorted(w)[len(w) // 10]}
+        await st.close()
+        return res
+    variants["adapter_await_search"] = asyncio.run(adapter())
     emit("C1 10k x 768 fp32, Q=1, top-10 (L2-resident: latency config)", wall_ms=wall, scan_ms=scan, device_ms=total, kernel_phases_us=phases,
          wall_ms_no_events=walls[0], wall_ms_no_events_p10=variants["query_in_kernel_params"]["wall_ms_p10"], no_events=variants,
          qps=1e3 / wall, bytes_per_pass=n * dim * 4)

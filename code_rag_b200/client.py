@@ -33,6 +33,20 @@ from .errors import VectorStoreError
 _PACKERS: dict[int, struct.Struct] = {}
 
 
+def _pack_query(query_vector) -> bytes | None:
+    """list[float] -> the bytes of its float64 values, or None when ``struct`` refuses the list (the numpy way reports the error)."""
+    if type(query_vector) is not list:
+        return None
+    n = len(query_vector)
+    pk = _PACKERS.get(n)
+    if pk is None:
+        pk = _PACKERS[n] = struct.Struct(f"{n}d")
+    try:
+        return pk.pack(*query_vector)
+    except (struct.error, TypeError):
+        return None
+
+
 def _as_query(query_vector) -> np.ndarray:
     """list[float] (what an embedding provider hands to lattice) -> float64 [1, dim].  ``struct.pack`` converts a 768-element list
     in a quarter of the time ``np.asarray`` takes; anything it refuses (nested sequences, strings) goes the numpy way and fails there
@@ -430,14 +444,32 @@ class _HostCollection:
                 raise RuntimeError(f"entity-name pool out of step (device {got}, host {first_new})")
         self.dev.rank_attrs_set(rows, key, fil, cent, nam, clen, flg)
 
-    def _hits(self, rows: np.ndarray, scores: np.ndarray) -> list[dict[str, Any]]:
+    def _hits(self, rows, scores) -> list[dict[str, Any]]:
+        """rows / scores: arrays or plain lists."""
+        if not isinstance(rows, list):
+            rows, scores = rows.tolist(), scores.tolist()
+        ids, payloads = self.ids, self.payloads
         out = []
-        for r, s in zip(rows.tolist(), scores.tolist()):
+        for r, s in zip(rows, scores):
             if r < 0:
                 continue
-            p = self.payloads[r]
-            out.append({"id": str(self.ids[r]), "score": float(s), "payload": dict(p) if p is not None else None})
+            p = payloads[r]
+            out.append({"id": str(ids[r]), "score": float(s), "payload": dict(p) if p is not None else None})
         return out
+
+    def search_one(self, query_vector, limit: int, filters: dict[str, Any] | None) -> list[dict[str, Any]]:
+        """``search`` for one query given as the caller's list, without numpy in between (the inline path of a small collection)."""
+        packed = _pack_query(query_vector) if 0 < limit <= N.MAX_K and hasattr(self.dev, "search_packed") else None
+        if packed is None or len(packed) != 8 * self.dim:
+            return self.search(_as_query(query_vector), limit, filters)[0]
+        n, flags, rows, scores = self.dev.search_packed(packed, self.device_limit(limit), self.want_codes(filters)).single()
+        if flags & N.FLAG_UNPROVEN:
+            logger.warning("search on %s: exactness bound not met (many near-ties); result is the best of the largest candidate set", self.name)
+        rows, scores = rows[:n], scores[:n]
+        if self.dup_keys and n > 1:                      # (score desc, id asc): see in_id_order
+            order = sorted(range(n), key=lambda j: (-scores[j], _id_sort_key(self.ids[rows[j]])))
+            rows, scores = [rows[j] for j in order], [scores[j] for j in order]
+        return self._hits(rows[:limit], scores[:limit])
 
     def search(self, query_vectors: np.ndarray | None, limit: int, filters: dict[str, Any] | None) -> list[list[dict[str, Any]]]:
         want = self.want_codes(filters)
@@ -863,24 +895,25 @@ class B200VectorStore:
                      filters: dict[str, Any] | None = None) -> list[dict[str, Any]]:
         try:
             coll = self._get(collection)
-            q = None if query_vector is None else _as_query(query_vector)
             flt = filters or None
+            inline = getattr(coll, "inline_bytes", None)
+            if query_vector is not None and inline is not None and inline() <= _INLINE_SEARCH_BYTES and coll.lock.acquire(blocking=False):
+                try:                                     # see below
+                    return coll.search_one(query_vector, limit, flt)
+                finally:
+                    coll.lock.release()
+            q = None if query_vector is None else _as_query(query_vector)
 
             def work():
                 with coll.lock:
                     return coll.search(q, limit, flt)[0]
             # A small collection (lattice's usual operating point: 10^4 - 10^5 chunks) answers in tens of microseconds: it is searched
-            # inline when nobody else holds the collection.  Anything larger is SUBMITTED from the event loop (a non-blocking library
-            # call) and polled between yields - a hop to a worker thread and back costs 0.1-0.2 ms, as much as a whole step on eight
-            # GPUs - so concurrent awaits (asyncio.gather in query/engine.py:142-146) pipeline on the device instead of queueing
-            # behind a lock.  Filter-only lookups and contended collections take a thread (threading).
-            inline = getattr(coll, "inline_bytes", None)
-            if inline is not None and inline() <= _INLINE_SEARCH_BYTES and coll.lock.acquire(blocking=False):
-                try:
-                    results = coll.search(q, limit, flt)[0]
-                finally:
-                    coll.lock.release()
-            elif _POLLED_SEARCH and q is not None and hasattr(coll, "search_begin") and hasattr(coll.lock, "try_enter"):
+            # inline (above) when nobody else holds the collection - list in, dicts out, no numpy in between.  Anything larger is
+            # SUBMITTED from the event loop (a non-blocking library call) and polled between yields - a hop to a worker thread and
+            # back costs 0.1-0.2 ms, as much as a whole step on eight GPUs - so concurrent awaits (asyncio.gather in
+            # query/engine.py:142-146) pipeline on the device instead of queueing behind a lock.  Filter-only lookups and contended
+            # collections take a thread (threading).
+            if _POLLED_SEARCH and q is not None and hasattr(coll, "search_begin") and hasattr(coll.lock, "try_enter"):
                 results = await self._search_polled(coll, q, limit, flt, work)
             else:
                 results = await asyncio.to_thread(work)

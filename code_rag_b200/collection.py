@@ -8,6 +8,7 @@ arithmetic on this path and no fallback when the library or the GPU is missing.
 from __future__ import annotations
 
 import ctypes as C
+import struct
 
 import numpy as np
 
@@ -49,6 +50,19 @@ class SearchResult:
                        tail[:Q], tail[Q:2 * Q].view(np.int32)]
         return self._f
 
+    def single(self) -> tuple[int, int, list, list]:
+        """(count, flags, rows, scores) of a ONE-query result as plain Python values - no numpy views: behind a small collection
+        the whole search is tens of microseconds and five array views are a third of that."""
+        if self._f is None and self._Q == 1:
+            k = self._k
+            st = _UNPACK1.get(k)
+            if st is None:
+                st = _UNPACK1[k] = struct.Struct(f"<{k}d{k}q{k}QIi")       # scores | rows | ties | count | flags
+            v = st.unpack_from(self._block)
+            return v[3 * k], v[3 * k + 1], list(v[k:2 * k]), list(v[:k])
+        f = self._fields()
+        return int(f[3][0]), int(f[4][0]), f[1][0].tolist(), f[0][0].tolist()
+
     scores = property(lambda self: self._fields()[0], lambda self, v: self._fields().__setitem__(0, v))
     rows = property(lambda self: self._fields()[1], lambda self, v: self._fields().__setitem__(1, v))
     ties = property(lambda self: self._fields()[2], lambda self, v: self._fields().__setitem__(2, v))
@@ -57,6 +71,9 @@ class SearchResult:
 
     def __repr__(self) -> str:
         return "SearchResult(" + ", ".join(f"{n}={v!r}" for n, v in zip(self._NAMES, self._fields())) + ")"
+
+
+_UNPACK1: dict[int, struct.Struct] = {}
 
 
 def _result_block(Q: int, k: int):
@@ -362,6 +379,16 @@ class DeviceCollection:
         N.check(self._lib.lvs_search_submit_sharded(self._handle(), ex, _addr(q), N.DT_F64, q.shape[0], int(k), _ptr(self._want(want)),
                                                     C.byref(t)), "lvs_search_submit_sharded")
         return (t.value, q.shape[0], int(k))
+
+    def search_packed(self, packed: bytes, k: int, want=None) -> SearchResult:
+        """``search`` for ONE float64 query that is already a bytes object of ``dim`` doubles (``struct.pack``): nothing is converted
+        or checked twice on the way to ``lvs_search`` (which refuses NaN itself)."""
+        if len(packed) != 8 * self.dim:
+            raise ValueError(f"query must have {self.dim} components")
+        k = int(k)
+        block, (ps, pr, pt, pc, pf) = _result_block(1, k)
+        N.check(self._lib.lvs_search(self._handle(), packed, N.DT_F64, 1, k, _ptr(self._want(want)), ps, pr, pt, pc, pf), "lvs_search")
+        return SearchResult.from_block(block, 1, k)
 
     def search_poll(self, ticket: tuple[int, int, int]) -> bool:
         """True once :meth:`search_wait` will not block on the device (``lvs_search_poll``)."""

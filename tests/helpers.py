@@ -116,6 +116,15 @@ class FakeDevice:
             res.counts[i] = len(order)
         return res
 
+    def search_packed(self, packed, k, want=None):
+        """DeviceCollection.search_packed: one float64 query as bytes."""
+        q = np.frombuffer(packed, dtype=np.float64)
+        if q.shape[0] != self.dim:
+            raise ValueError(f"query must have {self.dim} components")
+        if np.isnan(q).any():
+            raise ValueError("Query vector must not contain NaN")
+        return self.search(q[None, :], k, want)
+
     # pipelined pair + poll (DeviceCollection.search_submit / search_poll / search_wait): the search runs at submit, the first
     # poll says "not yet" so that callers' polling loops are exercised
     def search_submit(self, queries, k, want=None):
