@@ -191,15 +191,17 @@ class ShardPlane:
     """One per process.  ``start()`` is collective; afterwards rank 0 drives and the others ``serve()``."""
 
     def __init__(self, rank: int, world: int, ctl_group, device: int, device_factory: Callable | None,
-                 searcher_factory: Callable | None):
+                 searcher_factory: Callable | None, encoder_factory: Callable | None = None):
         self.rank, self.world, self.ctl, self.device = rank, world, ctl_group, device
-        self._device_factory, self._searcher_factory = device_factory, searcher_factory
+        self._device_factory, self._searcher_factory, self._encoder_factory = device_factory, searcher_factory, encoder_factory
+        self.encoder = None                       # this rank's code encoder (op "encoder"): chunks are embedded where they will live
         self.shards: dict[str, Any] = {}          # collection name -> this rank's shard (DeviceCollection)
         self.searchers: dict[str, Any] = {}
         self.lock = threading.RLock()             # controller: one command at a time
         self.pending: list[list[tuple]] = [[] for _ in range(world)]     # controller: queued writes per rank
         self.closed = False
         self._deferred: int | None = None
+        self.encoder_hidden: int | None = None    # controller: width of the encoders the ranks hold (attach_encoder)
         self._polled: dict | None = None          # controller: the search begun with search_begin and not yet ended
         self.polled_searches = 0                  # ... how many took that route (tests, diagnostics)
         self.mailbox: _Mailbox | None = None
@@ -208,7 +210,7 @@ class ShardPlane:
 
     @classmethod
     def start(cls, device_factory: Callable | None = None, searcher_factory: Callable | None = None,
-              ctl_group=None) -> "ShardPlane":
+              ctl_group=None, encoder_factory: Callable | None = None) -> "ShardPlane":
         """Collective over the default process group (``torchrun`` env; initialised here when the caller has not).  Binds the
         process to ``cuda:LOCAL_RANK`` and opens the gloo control group.  The two factories exist for the CPU tests."""
         import torch.distributed as dist
@@ -226,7 +228,7 @@ class ShardPlane:
         rank, world = dist.get_rank(), dist.get_world_size()
         if ctl_group is None:
             ctl_group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
-        return cls(rank, world, ctl_group, device, device_factory, searcher_factory)
+        return cls(rank, world, ctl_group, device, device_factory, searcher_factory, encoder_factory)
 
     # ---- command transport ---------------------------------------------------------------------------------------
     def _scatter(self, per_rank: list | None):
@@ -380,10 +382,15 @@ class ShardPlane:
             logger.exception("shard rank %d: %s(%s) failed", self.rank, op, name)
             return False, f"{type(e).__name__}: {e}"
 
-    @staticmethod
-    def _write(dev, method: str, args: tuple) -> None:
+    def _write(self, dev, method: str, args: tuple) -> None:
         base = int(getattr(dev, "row_base", 0))          # the wire carries local rows
-        if method == "upsert":
+        if method == "upsert_tokens":
+            # SURVEY section 8f row 4 over N GPUs: the token ids came over the control plane, the vectors never exist outside this GPU
+            tok, rows, codes, ties = args
+            if self.encoder is None:
+                raise RuntimeError("no encoder attached to the shard plane (ShardedB200VectorStore.attach_encoder)")
+            self.encoder.embed_upsert(dev, tok, rows=rows + base, codes=codes, ties=ties)
+        elif method == "upsert":
             vec, rows, codes, ties = args
             dev.upsert(vec, rows=rows + base, codes=codes, ties=ties)
         elif method == "set_codes":
@@ -401,7 +408,32 @@ class ShardPlane:
     def _op_noop(self, name, common):
         return None
 
+    def _op_encoder(self, name, spec):
+        """Every rank builds the same code encoder on its own GPU.  spec: {"pretrained": path-or-name} (transformers'
+        ``RobertaModel`` checkpoint, as unixcoder_provider.py:65-83 loads it), or {"random": {vocab, hidden, layers, intermediate,
+        max_pos, seed}} (benchmarks, tests), plus n_heads / pad_id where they are not the checkpoint's.  None detaches."""
+        if self.encoder is not None:
+            close = getattr(self.encoder, "close", None)
+            if close:
+                close()
+            self.encoder = None
+        if spec is None:
+            return None
+        if self._encoder_factory is not None:
+            self.encoder = self._encoder_factory(spec)
+        else:
+            from .embedding import B200CodeEncoder, random_state_dict
+            if "pretrained" in spec:
+                self.encoder = B200CodeEncoder.from_pretrained(spec["pretrained"], device=self.device)
+            else:
+                r = spec["random"]
+                sd = random_state_dict(r["vocab"], r["hidden"], r["layers"], r["intermediate"], r["max_pos"], seed=r.get("seed", 0))
+                self.encoder = B200CodeEncoder(sd, n_layers=r["layers"], n_heads=spec.get("n_heads", r["hidden"] // 64), pad_id=spec.get("pad_id", 1),
+                                               device=self.device)
+        return int(self.encoder.hidden)
+
     def _op_shutdown(self, name, common):
+        self._op_encoder(None, None)
         for nm in list(self.shards):
             self._op_destroy(nm, None)
         self.closed = True
@@ -506,6 +538,11 @@ class _ShardProxy:
                           None if codes is None else np.ascontiguousarray(codes, dtype=np.uint32),
                           None if ties is None else np.ascontiguousarray(ties, dtype=np.uint64))
 
+    def upsert_tokens(self, token_ids, rows=None, codes=None, ties=None) -> None:
+        self._plane.queue(self._shard, self._name, "upsert_tokens", np.ascontiguousarray(token_ids, dtype=np.int32),
+                          np.asarray(rows, dtype=np.int64), None if codes is None else np.ascontiguousarray(codes, dtype=np.uint32),
+                          None if ties is None else np.ascontiguousarray(ties, dtype=np.uint64))
+
     def set_codes(self, col, codes, rows=None, row0=0) -> None:
         self._plane.queue(self._shard, self._name, "set_codes", int(col), np.ascontiguousarray(codes, dtype=np.uint32),
                           None if rows is None else np.asarray(rows, dtype=np.int64), int(row0))
@@ -521,6 +558,17 @@ class _ShardProxy:
 
     def close(self) -> None:
         pass
+
+
+class _PlaneEncoder:
+    """What ``_HostCollection.upsert_tokens`` takes for an encoder on the controller: the embedding itself happens on the rank that
+    owns the shard (``ShardPlane._write``: "upsert_tokens"), so this only forwards the token ids to the shard's proxy."""
+
+    def __init__(self, hidden: int):
+        self.hidden = int(hidden)
+
+    def embed_upsert(self, dev, token_ids, rows=None, codes=None, ties=None) -> None:
+        dev.upsert_tokens(token_ids, rows=rows, codes=codes, ties=ties)
 
 
 class _HostShard(_HostCollection):
@@ -653,6 +701,38 @@ class _ShardedHostCollection:
         for s, idx in enumerate(parts):
             if idx:
                 self.shards[s].upsert([canon[i] for i in idx], vec[idx], [payloads[i] for i in idx])
+        self.plane.flush()
+
+    @_whole_op
+    def upsert_tokens(self, ids, token_ids, payloads, encoder=None) -> None:
+        """``upsert`` from token ids: every point's tokens travel to the rank that owns (or will own) it, which embeds them with its
+        own encoder and writes the vectors into its shard in place (``attach_encoder`` first).  `encoder` is ignored: a vector
+        computed on one GPU would have to cross the control plane to reach another."""
+        hidden = getattr(self.plane, "encoder_hidden", None)
+        if hidden is None:
+            raise ValueError("no encoder attached: call ShardedB200VectorStore.attach_encoder(...) first")
+        if hidden != self.dim:
+            raise ValueError(f"the encoder produces {hidden}-dimensional vectors, the collection holds {self.dim}")
+        tok = np.ascontiguousarray(token_ids, dtype=np.int32)
+        if tok.ndim != 2:
+            raise ValueError("token_ids must be [n, L]")
+        n = min(len(ids), tok.shape[0], len(payloads))
+        if n == 0:
+            return
+        canon = [_canonical_id(i) for i in ids[:n]]
+        last = {pid: i for i, pid in enumerate(canon)}           # a repeated id: the last occurrence wins
+        live = self.live_counts()
+        parts: list[list[int]] = [[] for _ in self.shards]
+        for i in sorted(last.values()):
+            s = self.shard_of(canon[i])
+            if s is None:
+                s = least_full(live)
+                live[s] += 1
+            parts[s].append(i)
+        enc = _PlaneEncoder(hidden)
+        for s, idx in enumerate(parts):
+            if idx:
+                self.shards[s].upsert_tokens([canon[i] for i in idx], tok[idx], [payloads[i] for i in idx], enc)
         self.plane.flush()
 
     def _id_of(self, global_row: int):
@@ -920,6 +1000,27 @@ class ShardedB200VectorStore(B200VectorStore):
             self._collections.update(await asyncio.to_thread(work))      # the workers replaced their shards in place
         except Exception as e:  # noqa: BLE001
             raise VectorStoreError(f"Failed to load collections from {directory}", cause=e)
+
+    async def attach_encoder(self, spec: dict | None) -> int | None:
+        """Additive API (SURVEY section 8f row 4 over N GPUs): every rank builds the code encoder `spec` describes on its own GPU
+        (``ShardPlane._op_encoder``: {"pretrained": path} or {"random": {...}}); afterwards ``upsert_tokens`` embeds every chunk on
+        the GPU whose shard will hold it - N encoders work in parallel and no vector crosses the control plane.  Returns the
+        embedding width; None detaches."""
+        try:
+            widths = await asyncio.to_thread(self.plane.call, "encoder", None, spec)
+            if spec is None:
+                self.plane.encoder_hidden = None
+                return None
+            if len(set(widths)) != 1:
+                raise RuntimeError(f"the ranks built encoders of different widths: {widths}")
+            self.plane.encoder_hidden = int(widths[0])
+            return self.plane.encoder_hidden
+        except Exception as e:  # noqa: BLE001
+            raise VectorStoreError("Failed to attach the encoder", cause=e)
+
+    async def upsert_tokens(self, collection: str, ids: list[str], token_ids, payloads: list[dict[str, Any]], encoder=None) -> None:
+        """``B200VectorStore.upsert_tokens`` over the shards: see ``attach_encoder``."""
+        return await super().upsert_tokens(collection, ids, token_ids, payloads, encoder)
 
     async def search_and_rank(self, collection: str, items: Sequence[tuple], limit: int = 10,
                               filters: dict[str, Any] | None = None, ranker=None, summaries: bool = False,

@@ -242,3 +242,25 @@ class FakeShardSearcher:
 
     def close(self):
         pass
+
+
+def fake_embed(token_ids, hidden: int, pad_id: int = 1) -> np.ndarray:
+    """A deterministic stand-in for the code encoder on CPU: the mean of fixed random token vectors over the non-pad tokens."""
+    tok = np.asarray(token_ids)
+    table = np.random.default_rng(77).standard_normal((1000, hidden))
+    m = (tok != pad_id)[..., None]
+    return (table[tok % 1000] * m).sum(1) / np.maximum(m.sum(1), 1)
+
+
+class FakeEncoder:
+    """``embedding.B200CodeEncoder`` as far as the sharded adapter uses it (``hidden``, ``embed_upsert``, ``close``).  TESTS ONLY."""
+
+    def __init__(self, spec):
+        self.hidden = int(spec["random"]["hidden"])
+        self.closed = False
+
+    def embed_upsert(self, dev, token_ids, rows=None, codes=None, ties=None):
+        dev.upsert(fake_embed(token_ids, self.hidden), rows=rows, codes=codes, ties=ties)
+
+    def close(self):
+        self.closed = True

@@ -30,6 +30,16 @@ async def checks(plane):
         if storage == "f32":          # compares with the oracle on unrounded inputs at the fp32 bar
             await S.scenario_edge_cases(factory)
         await S.scenario_client_shim(factory)
+        if storage == "f32":
+            # embedding on the GPUs that will search (SURVEY section 8f row 4 over N GPUs): every rank builds the same small encoder,
+            # chunks are embedded on the rank that owns them; expected vectors from the numpy oracle of the encoder
+            from oracle import roberta_encoder as R
+            from test_sharded_store_cpu import _sharded_upsert_tokens
+            r = {"vocab": 600, "hidden": 128, "layers": 2, "intermediate": 256, "max_pos": 64, "seed": 3}
+            sd = R.random_state_dict(r["vocab"], r["hidden"], r["layers"], r["intermediate"], r["max_pos"], seed=r["seed"])
+            await _sharded_upsert_tokens(factory.make_store, plane.world, {"random": r, "n_heads": 2, "pad_id": 1},
+                                         lambda t: R.encode(sd, t, n_layers=2, n_heads=2, pad_id=1)[1])
+            print(f"upsert_tokens over {plane.world} GPU(s) (one encoder per rank): OK", flush=True)
         print(f"sharded store [{storage}] over {plane.world} GPU(s): OK", flush=True)
 
 

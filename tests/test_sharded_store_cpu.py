@@ -138,11 +138,51 @@ async def _sharded_specifics(make_store, world):
     await store.close()
 
 
+async def _sharded_upsert_tokens(make_store, world, spec, embed):
+    """``upsert_tokens`` over the shards (SURVEY section 8f row 4 at N GPUs): token ids go to the rank that owns the point, which
+    embeds them itself.  `embed(token_ids)` = the vectors the ranks' encoders are expected to produce (the oracle's)."""
+    import lvs_synth as synth
+    from adapter_scenarios import CODE
+    from code_rag_b200.errors import VectorStoreError
+    hidden = spec["random"]["hidden"]
+    store = make_store(dimensions=hidden)
+    await store.connect(); await store.create_collections()
+    rng = np.random.default_rng(41)
+    n, L = 48, 24
+    tok = rng.integers(3, spec["random"]["vocab"], size=(n, L)).astype(np.int32)
+    for i in range(1, n):
+        tok[i, int(rng.integers(L // 3, L + 1)):] = 1                      # ragged: pad id 1
+    ids = synth.random_uuids(n, seed=42)
+    pl = [{"file_path": f"src/t{i % 5}.py", "entity_name": f"tok{i}", "project_name": ("alpha", "beta")[i % 2]} for i in range(n)]
+    try:
+        await store.upsert_tokens(CODE, ids[:4], tok[:4], pl[:4])
+        raise AssertionError("upsert_tokens without an attached encoder must fail")
+    except VectorStoreError:
+        pass
+    assert await store.attach_encoder(spec) == hidden
+    await store.upsert_tokens(CODE, ids[:30], tok[:30], pl[:30])
+    await store.upsert_tokens(CODE, ids[25:], tok[25:], pl[25:])                # five overwrites among them
+    info = await store.get_collection_info(CODE)
+    assert info.points_count == n and max(info.shard_points) - min(info.shard_points) <= 1, info.shard_points
+    want = embed(tok)
+    for i in (0, 7, 26, 29, 47):
+        hits = await store.search(collection=CODE, query_vector=want[i].astype(np.float64).tolist(), limit=3)
+        assert hits[0]["id"] == ids[i] and hits[0]["payload"]["entity_name"] == f"tok{i}" and abs(hits[0]["score"] - 1.0) < 2e-3, (i, hits[0])
+    hits = await store.search(collection=CODE, query_vector=want[3].astype(np.float64).tolist(), limit=5, filters={"project_name": "beta"})
+    assert hits and hits[0]["id"] == ids[3] and all(h["payload"]["project_name"] == "beta" for h in hits)
+    # vectors and tokens may be mixed in one collection: the same point re-written from its vector stays where it is
+    await store.upsert(collection=CODE, ids=[ids[7]], vectors=[want[9].astype(np.float64).tolist()], payloads=[dict(pl[7], entity_name="swapped")])
+    hits = await store.search(collection=CODE, query_vector=want[9].astype(np.float64).tolist(), limit=2)
+    assert {h["payload"]["entity_name"] for h in hits} == {"swapped", "tok9"}
+    await store.attach_encoder(None)
+    await store.close()
+
+
 def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     status = "ok"
     try:
-        from helpers import ExactTieDevice, FakeShardSearcher
+        from helpers import ExactTieDevice, FakeEncoder, FakeShardSearcher, fake_embed
         from code_rag_b200.sharded_store import ShardedB200VectorStore, run
 
         async def main(plane):                               # rank 0 only; the other ranks serve inside run()
@@ -158,9 +198,11 @@ def _worker(rank, world, port, out_dir):
                 await S.scenario_random_ops(factory, seed)
             await S.scenario_exact_ties_follow_the_id(factory)
             await S.scenario_edge_cases(factory)
+            spec = {"random": {"vocab": 500, "hidden": 32, "layers": 1, "intermediate": 64, "max_pos": 64, "seed": 3}}
+            await _sharded_upsert_tokens(factory.make_store, world, spec, lambda t: fake_embed(t, 32))
             assert plane.polled_searches > 0 and plane._polled is None, "searches must take the event-loop path (submit + poll)"
             return "done"
-        got = run(main, device_factory=ExactTieDevice, searcher_factory=FakeShardSearcher)
+        got = run(main, device_factory=ExactTieDevice, searcher_factory=FakeShardSearcher, encoder_factory=FakeEncoder)
         assert got == ("done" if rank == 0 else None)
     except BaseException:  # noqa: BLE001
         status = traceback.format_exc()
