@@ -225,9 +225,9 @@ static int launch_linear(lvs_encoder* e, const __nv_bfloat16* X, const Dense& d,
     static std::once_flag once;
     static cudaError_t once_err = cudaSuccess;
     std::call_once(once, [] {
-        once_err = cudaFuncSetAttribute(linear_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes(false));
+        once_err = cudaFuncSetAttribute(linear_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes(false, EPI));
         if (once_err == cudaSuccess)
-            once_err = cudaFuncSetAttribute(linear_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes(true));
+            once_err = cudaFuncSetAttribute(linear_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linear_smem_bytes(true, EPI));
     });
     if (once_err != cudaSuccess) return lvs_fail(LVS_ECUDA, "encoder: cudaFuncSetAttribute failed: %s", cudaGetErrorString(once_err));
     // enough row blocks to keep every SM busy with 256-row tiles: pairs of CTAs share each weight tile (see linear_kernel.cuh)
@@ -247,7 +247,7 @@ static int launch_linear(lvs_encoder* e, const __nv_bfloat16* X, const Dense& d,
         const uint32_t walkers = std::min<uint32_t>(p.tiles_m * p.tiles_n, (uint32_t)(sm / 2));
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(walkers * 2); cfg.blockDim = dim3(kLinThreads); cfg.dynamicSmemBytes = linear_smem_bytes(true); cfg.stream = e->stream;
+        cfg.gridDim = dim3(walkers * 2); cfg.blockDim = dim3(lin_threads(EPI)); cfg.dynamicSmemBytes = linear_smem_bytes(true, EPI); cfg.stream = e->stream;
         cudaLaunchAttribute la[1];
         la[0].id = cudaLaunchAttributeClusterDimension;
         la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
@@ -255,7 +255,7 @@ static int launch_linear(lvs_encoder* e, const __nv_bfloat16* X, const Dense& d,
         LVS_CU(cudaLaunchKernelEx(&cfg, linear_kernel<EPI, true>, tx, tw, p));
     } else {
         const uint32_t grid = std::min<uint32_t>(p.tiles_m * p.tiles_n, (uint32_t)sm);
-        linear_kernel<EPI, false><<<grid, kLinThreads, linear_smem_bytes(false), e->stream>>>(tx, tw, p);
+        linear_kernel<EPI, false><<<grid, lin_threads(EPI), linear_smem_bytes(false, EPI), e->stream>>>(tx, tw, p);
         LVS_CU(cudaGetLastError());
     }
     return LVS_OK;
@@ -274,6 +274,7 @@ static int forward(lvs_encoder* e, int B, int L) {
     LVS_CU(cudaGetLastError());
     const int Lp = (L + 63) / 64 * 64;
     const size_t asmem = attention_smem_bytes(Lp);
+    if (Lp / 64 > kAttnMaxBlocks) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens exceed the attention kernel's %d key blocks", L, kAttnMaxBlocks);
     if (asmem + 1024 > lvs_lib_smem_optin()) return lvs_fail(LVS_ELIMIT, "encoder: sequences of %d tokens do not fit the attention kernel's shared memory", L);
     {
         static std::once_flag once;

@@ -175,16 +175,13 @@ constexpr int kAttnQB = 128;
 constexpr int kAttnKPad = 72;          // K / V row stride in bf16 (36 words: conflict-free fragment and ldmatrix loads)
 
 constexpr int kAttnStages = 3;
+constexpr int kAttnMaxBlocks = 64;        // 64-key blocks per sequence: L <= 4096
 constexpr int kAttnStageElems = 2 * 64 * kAttnKPad;      // K block then V block, bf16 elements
 __host__ __device__ inline size_t attention_smem_bytes(int Lp) { return (size_t)kAttnStages * kAttnStageElems * 2 + (size_t)Lp * 4; }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -269,7 +266,15 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const __nv_bfloat16* 
     };
     issue_block(0);
     issue_block(1);
-    for (int i = tid; i < Lp; i += 256) kmask[i] = (i < L && ids[row0 + i] != pad_id) ? 0.f : -INFINITY;
+    // 0 / -inf per key, and per 64-key block whether it holds a pad at all (most blocks do not: they skip the mask)
+    __shared__ int s_blk_pad[kAttnMaxBlocks];
+    for (int i = tid; i < kAttnMaxBlocks; i += 256) s_blk_pad[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < Lp; i += 256) {
+        const bool real = i < L && ids[row0 + i] != pad_id;
+        kmask[i] = real ? 0.f : -INFINITY;
+        if (!real) s_blk_pad[i >> 6] = 1;
+    }
 
     const int q0 = qb * kAttnQB + warp * 16;                   // this warp's 16 query rows
     const bool active = q0 < L;
@@ -289,7 +294,9 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const __nv_bfloat16* 
     float o[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max / sum of rows g and g + 8
+    float m0 = -INFINITY, m1 = -INFINITY;                      // running maxima of rows g and g + 8 (scaled, log2 domain)
+    float lsum[4] = {0.f, 0.f, 0.f, 0.f};                      // [0] / [2] of the lanes with tq == 0: running sums of rows g / g + 8
+    const uint32_t ones_b = g == 0 ? 0x3F803F80u : 0u;         // B fragment of the ones column: B[k][n] = (n == 0)
     // ldmatrix lane roles: lane supplies the address of row (lane & 7) of matrix (lane >> 3)
     const int lm_row = lane & 7, lm_mat = lane >> 3;
 
@@ -316,35 +323,42 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const __nv_bfloat16* 
                 mma_bf16_16816(s[n], qa[kp * 2 + 1], kf[2], kf[3]);
             }
         }
-        // scale + mask; accumulator (n, i): row g (i < 2) or g + 8, key kb + n*8 + tq*2 + (i & 1)
+        // mask (only in blocks that hold a pad key) and row maxima, on the RAW scores: the scale is positive, so it commutes with max.
+        // Accumulator (n, i): row g (i < 2) or g + 8, key kb + n*8 + tq*2 + (i & 1)
+        if (s_blk_pad[blk]) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const float k0 = kmask[kb + n * 8 + tq * 2], k1 = kmask[kb + n * 8 + tq * 2 + 1];
+                s[n][0] += k0; s[n][1] += k1; s[n][2] += k0; s[n][3] += k1;
+            }
+        }
         float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const float k0 = kmask[kb + n * 8 + tq * 2], k1 = kmask[kb + n * 8 + tq * 2 + 1];
-            s[n][0] = s[n][0] * scale + k0; s[n][1] = s[n][1] * scale + k1;
-            s[n][2] = s[n][2] * scale + k0; s[n][3] = s[n][3] * scale + k1;
-            bm0 = fmaxf(bm0, fmaxf(s[n][0], s[n][1])); bm1 = fmaxf(bm1, fmaxf(s[n][2], s[n][3]));
-        }
+        for (int n = 0; n < 8; ++n) { bm0 = fmaxf(bm0, fmaxf(s[n][0], s[n][1])); bm1 = fmaxf(bm1, fmaxf(s[n][2], s[n][3])); }
         bm0 = fmaxf(bm0, __shfl_xor_sync(0xFFFFFFFFu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xFFFFFFFFu, bm0, 2));
         bm1 = fmaxf(bm1, __shfl_xor_sync(0xFFFFFFFFu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xFFFFFFFFu, bm1, 2));
-        const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+        const float nm0 = fmaxf(m0, bm0 * scale), nm1 = fmaxf(m1, bm1 * scale);      // running maxima live in the scaled (log2) domain
         // a block of pad keys only leaves the maximum at -inf: keep exp() away from (-inf) - (-inf)
         const float r0 = nm0 == -INFINITY ? 1.f : ex2_approx(m0 - nm0), r1 = nm1 == -INFINITY ? 1.f : ex2_approx(m1 - nm1);
-        const float e0 = nm0 == -INFINITY ? 0.f : nm0, e1 = nm1 == -INFINITY ? 0.f : nm1;
-        float ps0 = 0.f, ps1 = 0.f;
+        const float e0 = nm0 == -INFINITY ? 0.f : -nm0, e1 = nm1 == -INFINITY ? 0.f : -nm1;
         uint32_t pa[4][4];                                     // P as A fragments: k-step j covers keys kb + 16 j .. + 15
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const float p0 = ex2_approx(s[n][0] - e0), p1 = ex2_approx(s[n][1] - e0), p2 = ex2_approx(s[n][2] - e1), p3 = ex2_approx(s[n][3] - e1);
-            ps0 += p0 + p1; ps1 += p2 + p3;
+            // p = 2^(s * scale - max): one FMA and one MUFU per score (a masked score is -inf: p = 0)
+            const float p0 = ex2_approx(fmaf(s[n][0], scale, e0)), p1 = ex2_approx(fmaf(s[n][1], scale, e0));
+            const float p2 = ex2_approx(fmaf(s[n][2], scale, e1)), p3 = ex2_approx(fmaf(s[n][3], scale, e1));
             pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0, p1);   // rows g:     a0a1 (keys +0..7) / a4a5 (keys +8..15)
             pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);   // rows g + 8: a2a3 / a6a7
         }
-        ps0 += __shfl_xor_sync(0xFFFFFFFFu, ps0, 1); ps0 += __shfl_xor_sync(0xFFFFFFFFu, ps0, 2);
-        ps1 += __shfl_xor_sync(0xFFFFFFFFu, ps1, 1); ps1 += __shfl_xor_sync(0xFFFFFFFFu, ps1, 2);
-        l0 = l0 * r0 + ps0; l1 = l1 * r1 + ps1; m0 = nm0; m1 = nm1;
+        m0 = nm0; m1 = nm1;
 #pragma unroll
         for (int n = 0; n < 8; ++n) { o[n][0] *= r0; o[n][1] *= r0; o[n][2] *= r1; o[n][3] *= r1; }
+        lsum[0] *= r0; lsum[2] *= r1;
+        // the row sums ride on the tensor cores: P times a column of ones (a B fragment that is 1.0 in output column 0, held in
+        // registers) accumulates sum_k P[row][k] of the bf16 P the numerator uses, in column 0 of a ninth n-tile - four HMMAs instead
+        // of 32 FADDs and the shuffles
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_bf16_16816(lsum, pa[j], ones_b, ones_b);
         // O += P V.  B fragment of (k-step j, n-tile): V[key = kb + 16 j + 2 tq (+8)][d = 8 n + g] = the TRANSPOSE of the 8 x 8 tiles of
         // the row-major V block.  One ldmatrix.x4.trans = both registers for n-tiles n and n + 1: matrices
         // (keys +0..7, d 8n | keys +8..15, d 8n | keys +0..7, d 8n+8 | keys +8..15, d 8n+8)
@@ -360,6 +374,7 @@ __global__ void __launch_bounds__(256, 2) attention_kernel(const __nv_bfloat16* 
         }
     }
     if (!active) return;
+    const float l0 = __shfl_sync(0xFFFFFFFFu, lsum[0], lane & ~3), l1 = __shfl_sync(0xFFFFFFFFu, lsum[2], lane & ~3);
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     const int r0 = q0 + g, r1 = q0 + g + 8;
     __nv_bfloat16* C0 = ctx + (row0 + r0) * H + (size_t)h * kAttnD + tq * 2;
