@@ -275,7 +275,7 @@ class ShardedSearcher:
             return (np.zeros((0, k)), np.zeros((0, k), dtype=np.int64), np.zeros((0, k), dtype=np.uint64), np.zeros(0, dtype=np.uint32),
                     np.zeros(0, dtype=np.int32))
         if "ticket" in handle:
-            res = self.shard.search_wait(handle["ticket"])
+            res = handle["done"] if "done" in handle else self.shard.search_wait(handle["ticket"])
             scores, rows, ties, counts, flags = res.scores, res.rows, res.ties, res.counts, res.flags
         else:
             handle["event"].synchronize()

@@ -324,7 +324,15 @@ class ShardPlane:
     def search_end(self, h: dict):
         """(scores, rows, counts, flags) of the merged result; blocks if the search has not finished.  Unlocks the plane."""
         try:
-            scores, rows, _ties, counts, flags = h["searcher"].wait(h["handle"])
+            hd = h["handle"]
+            if isinstance(hd, dict) and "ticket" in hd and hd["ticket"][1] == 1 and hasattr(h["searcher"], "shard"):
+                # one query, nothing flagged (the usual case): plain Python values, no numpy views (see SearchResult.single)
+                res = h["searcher"].shard.search_wait(hd["ticket"])
+                n, flag, rows, scores = res.single()
+                if flag == 0:
+                    return [scores], [rows], [n], [0]
+                hd = dict(hd, done=res)                  # flagged: the general path repeats / raises
+            scores, rows, _ties, counts, flags = h["searcher"].wait(hd)
             return scores, rows, counts, flags
         finally:
             self._polled = None
@@ -739,13 +747,18 @@ class _ShardedHostCollection:
         s, r = split_row(global_row)
         return self.shards[s].ids[r]
 
-    def _hits(self, rows: np.ndarray, scores: np.ndarray) -> list[dict[str, Any]]:
+    def _hits(self, rows, scores) -> list[dict[str, Any]]:
+        if not isinstance(rows, list):
+            rows, scores = rows.tolist(), scores.tolist()
+        shards = self.shards
         out = []
-        for g, sc in zip(rows.tolist(), scores.tolist()):
+        for g, sc in zip(rows, scores):
             if g < 0:
                 continue
-            s, r = split_row(g)
-            out.extend(self.shards[s]._hits(np.asarray([r]), np.asarray([sc])))
+            sh = shards[g >> SHARD_BITS]
+            r = g & LOCAL_MASK
+            p = sh.payloads[r]
+            out.append({"id": str(sh.ids[r]), "score": float(sc), "payload": dict(p) if p is not None else None})
         return out
 
     def _match(self, want, cap=None) -> tuple[list[list[int]], int]:
@@ -778,6 +791,15 @@ class _ShardedHostCollection:
 
     def _shape(self, scores, rows, counts, flags, limit: int) -> list[list[dict[str, Any]]]:
         out = []
+        if isinstance(rows, list):                       # the one-query fast path of ShardPlane.search_end: lists of lists
+            for qi in range(len(rows)):
+                n = counts[qi]
+                r, sc = rows[qi][:n], scores[qi][:n]
+                if self.dup_keys and n > 1:              # (score desc, id asc): see client._HostCollection.in_id_order
+                    order = sorted(range(n), key=lambda j: (-sc[j], _id_sort_key(self._id_of(r[j]))))
+                    r, sc = [r[j] for j in order], [sc[j] for j in order]
+                out.append(self._hits(r[:limit], sc[:limit]))
+            return out
         for qi in range(rows.shape[0]):
             n = int(counts[qi])
             if int(flags[qi]) & N.FLAG_UNPROVEN:
