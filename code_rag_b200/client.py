@@ -51,15 +51,9 @@ def _as_query(query_vector) -> np.ndarray:
     """list[float] (what an embedding provider hands to lattice) -> float64 [1, dim].  ``struct.pack`` converts a 768-element list
     in a quarter of the time ``np.asarray`` takes; anything it refuses (nested sequences, strings) goes the numpy way and fails there
     the way it always did."""
-    if type(query_vector) is list:
-        n = len(query_vector)
-        pk = _PACKERS.get(n)
-        if pk is None:
-            pk = _PACKERS[n] = struct.Struct(f"{n}d")
-        try:
-            return np.frombuffer(pk.pack(*query_vector), dtype=np.float64)[None, :]
-        except (struct.error, TypeError):
-            pass
+    packed = _pack_query(query_vector)
+    if packed is not None:
+        return np.frombuffer(packed, dtype=np.float64)[None, :]
     return np.asarray(query_vector, dtype=np.float64)[None, :]
 
 
