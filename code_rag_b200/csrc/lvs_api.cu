@@ -905,9 +905,10 @@ static int enqueue_level(lvs_collection* c, const void* d_queries, const void* h
         const uint32_t seq = c->launch_seq + 1;
         sp.seq = seq; sp.done_seq = c->d_counter + 10;
         InlineQueries& iq = c->iq;        // only the first cnt * qrow bytes mean anything; the launch copies the block
-        // One unfiltered host query on a shard that is scanned in well under a millisecond - where the microseconds count and there is
-        // no previous search worth overlapping with - travels in the kernel's parameter block (scan_kernel.cuh).  Long scans keep
-        // their parameters small: a launch with more than 4 KB of them does not start early behind its predecessor.
+        // One unfiltered host query on a shard that is scanned in well under a millisecond - where the microseconds count - travels
+        // in the kernel's parameter block (scan_kernel.cuh).  Longer scans let CTA 0 stage the query instead: 3 us more in front of
+        // a millisecond, and their launches keep the classic sub-4 KB parameter block (pipelined host searches on a 5M-row shard
+        // measured the same either way: profiles/r02_inline_overlap_probe.jsonl).
         const bool short_scan = (double)c->n_rows * c->row_bytes <= (double)c->opt_inline_max_mb * 1048576.0;
         if (h_queries != nullptr && c->opt_inline_query && cnt == 1 && !filter && short_scan && qrow <= kInlineQueryBytes) {
             sp.q_inline = 1u; sp.q_raw = nullptr;

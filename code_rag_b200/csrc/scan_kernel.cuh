@@ -49,8 +49,8 @@ constexpr size_t kScanStaticSmem = 1024;   // static shared memory of the kernel
 // instruction): no PCIe read, no staging hop, no flag.  8 KB = one 1024-dimensional float64 query.
 constexpr uint32_t kInlineQueryBytes = 8192;
 struct InlineQueries { uint8_t bytes[kInlineQueryBytes]; };
-// The block is a parameter of the INLINE instantiations only (one query slot, no filter): kernels whose parameters stay below
-// 4 KB launch the classic way, and those are the ones long scans use - see DESIGN.md for what the large block costs them.
+// The block is a parameter of the INLINE instantiations only (one query slot, no filter); every other instantiation keeps the
+// classic sub-4 KB parameter block.
 struct NoInlineQueries { uint8_t bytes[16]; };
 template <bool INLINE> struct InlineBlock { using type = NoInlineQueries; };
 template <> struct InlineBlock<true> { using type = InlineQueries; };
