@@ -91,3 +91,36 @@ def test_one_process_binds_one_device(native_lib, monkeypatch):
     _native.init(0)                                        # idempotent
     with pytest.raises(NativeLibraryError):
         _native.init(1)
+
+
+def test_search_result_block_decodes_both_ways():
+    """The one block lvs_search fills (scores | rows | ties | counts | flags) read through numpy views and, for one query, through
+    SearchResult.single() (one struct.unpack, what the adapter's small-collection path uses)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from code_rag_b200.collection import SearchResult, _result_block
+    for Q, k in ((1, 10), (3, 4), (1, 1)):
+        block, ptrs = _result_block(Q, k)
+        n = Q * k
+        assert ptrs[0] == C.addressof(block) and [p - ptrs[0] for p in ptrs] == [0, 8 * n, 16 * n, 24 * n, 24 * n + 4 * Q]
+        a = np.frombuffer(block, dtype=np.int64)
+        rng = np.random.default_rng(Q * 10 + k)
+        scores = rng.standard_normal(n)
+        rows = rng.integers(-1, 1 << 40, n)
+        ties = rng.integers(0, 1 << 63, n, dtype=np.uint64)
+        a[:n] = scores.view(np.int64); a[n:2 * n] = rows; a[2 * n:3 * n] = ties.view(np.int64)
+        tail = a[3 * n:].view(np.uint32)
+        tail[:Q] = np.arange(1, Q + 1); tail[Q:2 * Q] = np.arange(Q) % 2
+        res = SearchResult.from_block(block, Q, k)
+        if Q == 1:
+            cnt, flag, r1, s1 = res.single()
+            assert (cnt, flag) == (1, 0) and r1 == rows.tolist() and s1 == scores.tolist()
+        assert np.array_equal(res.scores, scores.reshape(Q, k)) and np.array_equal(res.rows, rows.reshape(Q, k))
+        assert np.array_equal(res.ties, ties.reshape(Q, k)) and res.counts.tolist() == list(range(1, Q + 1))
+        assert res.flags.tolist() == [q % 2 for q in range(Q)] and res.flags.dtype == np.int32 and res.counts.dtype == np.uint32
+    # the five-array form still works and single() agrees with it
+    res = SearchResult(np.array([[0.5, 0.25]]), np.array([[7, -1]]), np.zeros((1, 2), dtype=np.uint64), np.array([1], dtype=np.uint32),
+                       np.array([1], dtype=np.int32))
+    assert res.single() == (1, 1, [7, -1], [0.5, 0.25])
