@@ -150,3 +150,59 @@ def test_gathered_searches_pipeline_and_writers_wait(monkeypatch):
     lk.reader_done()
     th.join(5)
     assert got == [1] and lk.readers == 0
+
+
+def test_polled_searches_under_concurrent_writes(monkeypatch):
+    """Searches on the event loop (submit + poll), upserts and deletes in worker threads, all on one collection for a while: no
+    exception, no reader left behind, and every hit pairs an id with ITS payload (a write never lands between a search's
+    submission and the moment its rows become payloads)."""
+    import random
+    import time
+
+    import numpy as np
+
+    import lvs_synth as synth
+    from code_rag_b200 import client
+    monkeypatch.setattr(client, "_INLINE_SEARCH_BYTES", -1)
+
+    async def run():
+        st = client.B200VectorStore(dimensions=16, _device_factory=FakeDevice)
+        await st.connect(); await st.create_collections()
+        n = 300
+        x, _ = synth.unit_rows(n, 16, seed=8)
+        ids = synth.random_uuids(n, 10)
+        tag = {pid: i for i, pid in enumerate(ids)}
+        pl = lambda i, gen: {"file_path": f"f{i % 9}.py", "entity_name": f"e{i}", "gen": gen}  # noqa: E731
+        await st.upsert("code_chunks", ids[:200], x[:200].astype(np.float64).tolist(), [pl(i, 0) for i in range(200)])
+        stop = time.perf_counter() + 1.5
+        rnd = random.Random(3)
+        counts = {"search": 0, "write": 0}
+
+        async def searcher(seed):
+            r = random.Random(seed)
+            while time.perf_counter() < stop:
+                hits = await st.search("code_chunks", x[r.randrange(n)].tolist(), 6, {"file_path": f"f{r.randrange(9)}.py"} if r.random() < 0.3 else None)
+                for h in hits:
+                    assert h["payload"]["entity_name"] == f"e{tag[h['id']]}", h
+                counts["search"] += 1
+
+        async def writer():
+            gen = 1
+            while time.perf_counter() < stop:
+                lo = rnd.randrange(0, n - 20)
+                sel = list(range(lo, lo + 20))
+                if rnd.random() < 0.5:
+                    await st.upsert("code_chunks", [ids[i] for i in sel], x[sel].astype(np.float64).tolist(), [pl(i, gen) for i in sel])
+                else:
+                    await st.delete("code_chunks", {"file_path": f"f{rnd.randrange(9)}.py"})
+                gen += 1
+                counts["write"] += 1
+                await asyncio.sleep(0)
+
+        await asyncio.gather(*[searcher(s) for s in range(6)], writer(), writer())
+        lock = st._collections["code_chunks"].lock
+        assert lock.readers == 0 and lock.acquire(blocking=False)
+        lock.release()
+        assert counts["search"] > 50 and counts["write"] > 5, counts
+        await st.close()
+    asyncio.run(run())
