@@ -188,12 +188,15 @@ def run_reference(args) -> None:
 # clocks
 # --------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML every ~10 ms while the timed region runs."""
+    """Samples SM clock, throttle reasons and board power through NVML every few ms while the timed region runs."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.index = index
+        self.period_s = period_s
         self.samples: list[tuple[float, int]] = []
+        self.power_w: list[float] = []
         self.max_mhz = None
+        self.power_limit_w = None
         self._stop = threading.Event()
         self._thread = None
         self._err = None
@@ -215,6 +218,10 @@ class ClockSampler:
         except Exception as e:  # noqa: BLE001
             self._err = repr(e)
             return
+        try:
+            self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1e3
+        except Exception:  # noqa: BLE001
+            pass
 
         def loop():
             while not self._stop.is_set():
@@ -228,7 +235,11 @@ class ClockSampler:
                 except Exception as e:  # noqa: BLE001
                     self._err = repr(e)
                     return
-                time.sleep(0.01)
+                try:
+                    self.power_w.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(self.period_s)
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
 
@@ -242,8 +253,12 @@ class ClockSampler:
         seen = 0
         for _, r in self.samples:
             seen |= r
-        return {"sm_mhz": statistics.median(m for m, _ in self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(n for b_, n in bits.items() if seen & b_), "samples": len(self.samples)}
+        out = {"sm_mhz": statistics.median(m for m, _ in self.samples), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(n for b_, n in bits.items() if seen & b_), "samples": len(self.samples)}
+        if self.power_w:      # what the power cap is about: board power next to the enforced limit (the K2 leg runs into it)
+            out["power_w"] = statistics.median(self.power_w)
+            out["power_limit_w"] = self.power_limit_w
+        return out
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -477,7 +492,8 @@ def run_ours(args) -> None:
         b = legs(shard, searcher, n_local, 256, 100, 6, 3, seed=12, with_sync=False)
         batched = {"workload": f"C3: 256 queries x top-100 per step, {args.rows}x{args.dim} bf16 over {world} GPU(s)",
                    "qps": b["value"], "ms_per_batch": b["ms_per_step"], "gemm_topk_kernel_ms": b["kernel_ms"], "roofline": b["roofline"],
-                   "e2e": b["e2e"], "flagged": b["unproven_queries"], "gpu_launches": b["gpu_launches"], "steps": b["steps"]}
+                   "e2e": b["e2e"], "flagged": b["unproven_queries"], "gpu_launches": b["gpu_launches"], "steps": b["steps"],
+                   "clocks": b["clocks"]}
 
     # ---------------- e2e_adapter: the call lattice makes - await store.search(collection=, query_vector=list, limit=10) ----------------
     # (reference query/vector_search.py:60-116 -> QdrantManager.search).  The store is put in front of the SAME resident shard(s);
@@ -501,8 +517,8 @@ def run_ours(args) -> None:
         q1 = legs(sh5, se5, n5, 1, 10, 12, 3, seed=13, with_sync=False)
         q256 = legs(sh5, se5, n5, 256, 10, 3, 3, seed=14, with_sync=False)
         c5 = {"workload": f"C5: 100000000x{args.dim} bf16 row-sharded over {world} GPUs, top-10", "rows_per_gpu": n5, "corpus_gen_s": round(t5, 1),
-              "q1": {kk: q1[kk] for kk in ("value", "ms_per_step", "kernel_ms", "roofline", "e2e", "unproven_queries", "steps")},
-              "q256": {kk: q256[kk] for kk in ("value", "ms_per_step", "kernel_ms", "roofline", "e2e", "unproven_queries", "steps")}}
+              "q1": {kk: q1[kk] for kk in ("value", "ms_per_step", "kernel_ms", "roofline", "e2e", "unproven_queries", "steps", "clocks")},
+              "q256": {kk: q256[kk] for kk in ("value", "ms_per_step", "kernel_ms", "roofline", "e2e", "unproven_queries", "steps", "clocks")}}
         se5.close()
         sh5.close()
 
