@@ -54,6 +54,9 @@ constexpr int kGemmKC = 64;            // K elements per pipeline stage (= one 1
 constexpr int kGemmABytes = kGemmM * kGemmKC * 2;       // 16 KB
 constexpr int kGemmBBytes = kGemmN * kGemmKC * 2;       // 32 KB (PAIR: each CTA holds half, 16 KB)
 constexpr int kGemmMaxStages = 4;
+constexpr int kGemmMaxStagesB = 8;     // split rings (pair form): corpus half-tiles in flight
+constexpr int kGemmDefaultStagesA = 4; // defaults of the pair form: 0 corpus buffers = one combined ring of kGemmDefaultStagesA stages
+constexpr int kGemmDefaultStagesB = 5;
 constexpr int kGemmList = 16;          // keys kept per (CTA, column half, query)
 constexpr int kGemmMaxKChunks = 128;   // dim <= 8192 (bf16) / 4096 (fp32)
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA of a pair
@@ -69,6 +72,9 @@ struct GemmParams {
     uint32_t n_groups;           // G: CTAs that walk the same tiles (PAIR: 2 = the cluster)
     uint32_t n_pairs;            // P: tile walkers
     uint32_t n_stages;
+    uint32_t n_stages_b;         // pair form only, 0 = one ring of (query chunk | corpus half-tile) stages.  > 0: SPLIT RINGS - n_stages query-chunk
+                                 // buffers (L2-resident, short latency) and n_stages_b corpus half-tile buffers (HBM, long latency) of 16 KB
+                                 // each, requested independently, so that more of the shared memory holds bytes that are in flight from HBM
     const float* inv_norm;       // [rows] 1/||row||, or nullptr (dot metric)
     const uint8_t* live;
     const uint32_t* fcodes[kMaxFilterCols];   // payload filter: dictionary-code columns that must equal fwant[] (conjunction)
@@ -86,9 +92,11 @@ struct GemmParams {
 };
 
 // shared memory: [stages][lists 8 warps * 16 keys * 32 lanes * 8][score columns 8 * 32 * 32 * 4][thr 128*4][inv 8*128*4][barriers]
-__host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, bool pair) {
-    return 1024 /* alignment slack */ + (size_t)n_stages * gemm_stage_bytes(pair) + (size_t)kGemmEpiWarps * 32 * kGemmList * 8 +
-           (size_t)kGemmEpiWarps * 32 * 32 * 4 + kGemmM * 4 + kGemmEpiWarps * 128 * 4 + (2 * kGemmMaxStages + 8) * 8 + 16;
+__host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, bool pair, uint32_t n_stages_b = 0) {
+    const size_t ring = n_stages_b ? (size_t)n_stages * kGemmABytes + (size_t)n_stages_b * (kGemmBBytes / 2)
+                                   : (size_t)n_stages * gemm_stage_bytes(pair);
+    return 1024 /* alignment slack */ + ring + (size_t)kGemmEpiWarps * 32 * kGemmList * 8 +
+           (size_t)kGemmEpiWarps * 32 * 32 * 4 + kGemmM * 4 + kGemmEpiWarps * 128 * 4 + 256 /* barriers */;
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -170,8 +178,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     constexpr int kBRows = PAIR ? kGemmN / 2 : kGemmN;       // corpus rows this CTA loads per tile
     constexpr int kKcElems = TF32 ? kGemmKC / 2 : kGemmKC;  // K elements per stage (128 bytes of a row)
     const uint32_t S = p.n_stages;
+    const uint32_t SB = PAIR ? p.n_stages_b : 0u;                            // split rings: S query-chunk buffers, then SB corpus buffers
     uint8_t* stages = gsm;                                                   // S x (A 16 KB | B), 1024-byte aligned
-    uint64_t* lists = reinterpret_cast<uint64_t*>(gsm + (size_t)S * kStageBytes);         // [8 warps][16 keys][32 lanes], unsorted
+    uint8_t* b_bufs = gsm + (size_t)S * kGemmABytes;                         // split rings only
+    const size_t ring_bytes = SB ? (size_t)S * kGemmABytes + (size_t)SB * (kGemmBBytes / 2) : (size_t)S * kStageBytes;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(gsm + ring_bytes);         // [8 warps][16 keys][32 lanes], unsorted
     float* sbuf = reinterpret_cast<float*>(lists + kGemmEpiWarps * 32 * kGemmList);       // [8 warps][32 columns][32 lanes]
     uint32_t* thr_sm = reinterpret_cast<uint32_t*>(sbuf + kGemmEpiWarps * 32 * 32);       // [128] orderable threshold per query
     float* inv_sm = reinterpret_cast<float*>(thr_sm + kGemmM);               // [8][128] 1/||row|| of a warp's 128 columns
@@ -180,6 +191,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
     uint64_t* tmem_full = empty_bar + kGemmMaxStages;                        // [2]
     uint64_t* tmem_empty = tmem_full + 2;                                    // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* full_b = tmem_empty + 3;                                       // split rings: [kGemmMaxStagesB]
+    uint64_t* empty_b = full_b + kGemmMaxStagesB;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -189,6 +202,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
 
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (uint32_t s = 0; s < SB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (PAIR ? 2 : 1) * kGemmEpiWarps); }
         mbar_fence_init();
     }
@@ -212,7 +226,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        if (lane == 0 && SB != 0u) {
+            if constexpr (PAIR) {
+                // split rings: one thread polls both rings and requests whatever has a free buffer, the corpus first - its ring is
+                // the deep one, so its requests run ahead of the query chunks' by the difference in depth
+                const uint32_t total = my_tiles * nk;
+                uint32_t ia = 0, sa = 0, pa = 1, kca = 0;                    // next query chunk: index, buffer, parity to wait for, K chunk
+                uint32_t ib = 0, sb = 0, pb = 1, kcb = 0, ltb = 0;           // next corpus half-tile
+                while (ia < total || ib < total) {
+                    if (ib < total && mbar_test(&empty_b[sb], pb)) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_b[sb], (uint32_t)kGemmBBytes);      // both CTAs' halves
+                        tma_load_2d_pair(b_bufs + (size_t)sb * (kGemmBBytes / 2), &tmap_b, (int)(kcb * kKcElems),
+                                         (int)((pair + ltb * p.n_pairs) * kGemmN + rank * kBRows), &full_b[sb]);
+                        ++ib;
+                        if (++sb == SB) { sb = 0; pb ^= 1u; }
+                        if (++kcb == nk) { kcb = 0; ++ltb; }
+                    }
+                    if (ia < total && mbar_test(&empty_bar[sa], pa)) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[sa], 2u * kGemmABytes);         // both CTAs' query chunks
+                        tma_load_2d_pair(stages + (size_t)sa * kGemmABytes, &tmap_a, (int)(kca * kKcElems), (int)(group * kGemmM), &full_bar[sa]);
+                        ++ia;
+                        if (++sa == S) { sa = 0; pa ^= 1u; }
+                        if (++kca == nk) kca = 0;
+                    }
+                }
+            }
+        } else if (lane == 0) {
             uint32_t it = 0;
             for (uint32_t lt = 0; lt < my_tiles; ++lt) {
                 const uint32_t tile = pair + lt * p.n_pairs;
@@ -248,24 +287,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_topk_kernel(const __grid
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(kGemmN >> 3) << 17) |
                                    ((uint32_t)((PAIR ? 2 * kGemmM : kGemmM) >> 4) << 24);
             uint32_t it = 0;
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;                  // split rings: buffer and parity of the next chunk of each ring
             for (uint32_t lt = 0; lt < my_tiles; ++lt) {
                 const uint32_t buf = lt & 1u;
                 const uint32_t tmem_d = tmem_base + buf * kGemmN;
                 mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);   // the epilogue(s) have drained this accumulator
                 tc_fence_after();
                 for (uint32_t kc = 0; kc < nk; ++kc, ++it) {
-                    const uint32_t s = it % S;
-                    mbar_wait(&full_bar[s], (it / S) & 1u);
+                    uint32_t a_addr, b_addr;
+                    if (SB != 0u) {
+                        mbar_wait(&full_b[sb], pb);
+                        mbar_wait(&full_bar[sa], pa);
+                        a_addr = smem_u32(stages + (size_t)sa * kGemmABytes);
+                        b_addr = smem_u32(b_bufs + (size_t)sb * (kGemmBBytes / 2));
+                    } else {
+                        const uint32_t s = it % S;
+                        mbar_wait(&full_bar[s], (it / S) & 1u);
+                        a_addr = smem_u32(stages + (size_t)s * kStageBytes);
+                        b_addr = a_addr + kGemmABytes;
+                    }
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(stages + (size_t)s * kStageBytes);
-                    const uint32_t b_addr = a_addr + kGemmABytes;
                     if (!(p.dbg_mode & 2u)) {
 #pragma unroll
                         for (uint32_t k = 0; k < kGemmKC / 16; ++k)
                             tc_mma_ss<PAIR, TF32>(tmem_d, make_kmajor_desc(a_addr + k * 32u), make_kmajor_desc(b_addr + k * 32u), idesc,
                                             (kc | k) != 0u ? 1u : 0u);
                     }
-                    tc_commit<PAIR>(&empty_bar[s]);                  // frees the stage (in both CTAs) when these MMAs have read it
+                    if (SB != 0u) {                                  // each ring's buffer is freed (in both CTAs) when these MMAs have read it
+                        tc_commit<PAIR>(&empty_bar[sa]);
+                        tc_commit<PAIR>(&empty_b[sb]);
+                        if (++sa == S) { sa = 0; pa ^= 1u; }
+                        if (++sb == SB) { sb = 0; pb ^= 1u; }
+                    } else {
+                        tc_commit<PAIR>(&empty_bar[it % S]);         // frees the stage (in both CTAs) when these MMAs have read it
+                    }
                 }
                 tc_commit<PAIR>(&tmem_full[buf]);                    // accumulator of this tile is complete (in both CTAs)
             }

@@ -181,6 +181,7 @@ struct lvs_collection {
     int opt_path = 0;         // 0 auto, 1 force K1 scan, 2 force K2 (when eligible)
     int opt_gemm_dbg = 0;
     int opt_gemm_stages = 0;
+    int opt_gemm_stages_b = -1;   // pair form: corpus buffers of the split rings (-1 = default, 0 = one combined ring)
     int opt_gemm_no_unit = 0;
     int opt_gemm_keep = 16;
     int opt_gemm_no_pair = 0;
@@ -1092,8 +1093,18 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint64_t searc
         const uint32_t P = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)sm / G, n_tiles));
         uint32_t S = pair_form ? 4 : 3;
         if (c->opt_gemm_stages > 0) S = std::min<uint32_t>(S, (uint32_t)c->opt_gemm_stages);
-        while (S > 2 && gemm_smem_bytes(S, pair_form) > g_lib.smem_optin) --S;
-        const size_t smem = gemm_smem_bytes(S, pair_form);
+        // pair form, split rings: S query-chunk buffers + SB corpus half-tile buffers (16 KB each) instead of S stages of both
+        uint32_t SB = 0;
+        if (pair_form) {
+            static const int env_b = [] { const char* e = getenv("LATTICE_B200_GEMM_STAGES_B"); return e ? atoi(e) : -1; }();   // A/B switch
+            const int want_b = c->opt_gemm_stages_b >= 0 ? c->opt_gemm_stages_b : env_b >= 0 ? env_b : kGemmDefaultStagesB;
+            SB = (uint32_t)std::min(want_b, kGemmMaxStagesB);
+            if (SB != 0 && c->opt_gemm_stages <= 0) S = kGemmDefaultStagesA;
+            while (SB > 2 && gemm_smem_bytes(S, true, SB) > g_lib.smem_optin) --SB;
+            if (SB != 0 && (SB < 2 || gemm_smem_bytes(S, true, SB) > g_lib.smem_optin)) SB = 0;
+        }
+        while (S > 2 && gemm_smem_bytes(S, pair_form, SB) > g_lib.smem_optin) --S;
+        const size_t smem = gemm_smem_bytes(S, pair_form, SB);
         if (tf32)
             prep_qtf32_kernel<<<G * kGemmM, 256, 0, st>>>((const double*)c->s_q64.p + (size_t)q0 * c->dim, qb, c->dim,
                                                         (float*)c->s_qb16.p, k_pad, G * kGemmM, (float*)c->s_geps.p);
@@ -1105,7 +1116,7 @@ static int enqueue_gemm(lvs_collection* c, int Q, int k, int kpl, uint64_t searc
         GemmParams gp;
         memset(&gp, 0, sizeof(gp));
         gp.n_kchunks = nk; gp.n_queries = (uint32_t)qb; gp.n_rows = (uint32_t)c->n_rows;
-        gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S;
+        gp.n_tiles = n_tiles; gp.n_groups = G; gp.n_pairs = P; gp.n_stages = S; gp.n_stages_b = SB;
         gp.inv_norm = c->metric == LVS_METRIC_COSINE ? c->d_inv_norm : nullptr; gp.live = c->d_live;
         gp.n_filter = nf;
         for (uint32_t i = 0; i < nf; ++i) { gp.fcodes[i] = fcodes[i]; gp.fwant[i] = fwant[i]; }
@@ -2361,6 +2372,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;
     else if (!strcmp(name, "gemm_stages")) c->opt_gemm_stages = value;
+    else if (!strcmp(name, "gemm_stages_b")) c->opt_gemm_stages_b = value;
     else if (!strcmp(name, "gemm_no_unit")) c->opt_gemm_no_unit = value;
     else if (!strcmp(name, "gemm_keep")) c->opt_gemm_keep = value;
     else if (!strcmp(name, "gemm_no_pair")) c->opt_gemm_no_pair = value;
