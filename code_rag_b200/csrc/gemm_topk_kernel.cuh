@@ -17,9 +17,16 @@
 //   * PAIR = true (128 < Q <= 256): a CLUSTER OF TWO CTAs (one TPC) issues tcgen05.mma.cta_group::2 with M = 256
 //     (128 queries in each CTA's TMEM), N = 256.  Each CTA loads only ITS half of the corpus tile (128 rows x 64,
 //     16 KB) plus its own 128 queries' chunk (16 KB); the tensor cores read the other half from the peer's shared
-//     memory.  L2 -> SM traffic per tile and CTA drops from 576 KB to 384 KB; 4 stages of 32 KB.  The leader CTA
+//     memory.  L2 -> SM traffic per tile and CTA drops from 576 KB to 384 KB.  The leader CTA
 //     (cluster rank 0) issues all MMAs; both CTAs' TMA loads signal the leader's mbarrier; tcgen05.commit is
 //     multicast to both CTAs' barriers; the peer's epilogue warps arrive remotely on the leader's tmem_empty barrier.
+//     SPLIT RINGS (default of the pair form): the two operands have very different latencies - the query chunks come out of L2,
+//     the corpus out of HBM - so they do not share pipeline stages.  4 query-chunk buffers and 5 corpus half-tile buffers
+//     (16 KB each, own full / empty barriers) are requested independently by the one producer thread, which polls both
+//     rings (mbarrier.test_wait) and serves the corpus ring first: 80 KB of HBM bytes in flight per SM instead of 64 KB in
+//     the same shared memory, and a late query chunk no longer holds a corpus request back.  The MMA thread waits for one
+//     buffer of each ring and commits to both.  6-10 % shorter kernel on every same-box comparison (profiles/r02_k2_split_rings_notes.md);
+//     n_stages_b = 0 gives the former single ring of 4 x 32 KB stages.
 //   Both arrive by cp.async.bulk.tensor.2d (TMA, SASS UTMALDG).
 //   * D is double buffered: 2 x 256 TMEM columns, so the MMAs of tile t+1 overlap the epilogue of tile t.
 //   * Epilogue (8 warps; thread = query = TMEM lane; the two warps of a lane quarter split the 256 columns):

@@ -295,7 +295,8 @@ int lvs_last_kernel_phases(lvs_collection* c, uint64_t* ns16);
  * lvs_last_search_timing / lvs_scan_times; default 0; it serialises consecutive searches), "pdl" (1 = programmatic dependent launch
  * of the scan kernel, default),
  * "gemm_min_q" (batch size from which the tensor-core path is used, default 3; fp32 shards at least 5), "path" (0 auto, 1 scan only,
- * 2 tensor-core whenever eligible), "gemm_stages", "gemm_keep" (keys per K2 list, 4..16), "gemm_no_pair" (1 = never use the
+ * 2 tensor-core whenever eligible), "gemm_stages", "gemm_stages_b" (CTA-pair form: corpus buffers of the split operand rings, default 5;
+ * 0 = one ring of combined stages), "gemm_keep" (keys per K2 list, 4..16), "gemm_no_pair" (1 = never use the
  * cta_group::2 form), "gemm_no_tf32" (1 = fp32 shards stay on the scan), "gemm_no_unit" (1 = always scale by 1/||row||),
  * "gemm_dbg" (profiling switches, see GemmParams::dbg_mode).  Returns LVS_EINVAL for unknown names. */
 int lvs_set_option(lvs_collection* c, const char* name, int value);
