@@ -2372,7 +2372,7 @@ extern "C" int lvs_set_option(lvs_collection* c, const char* name, int value) {
     else if (!strcmp(name, "path")) c->opt_path = value;
     else if (!strcmp(name, "gemm_dbg")) c->opt_gemm_dbg = value;
     else if (!strcmp(name, "gemm_stages")) c->opt_gemm_stages = value;
-    else if (!strcmp(name, "gemm_stages_b")) c->opt_gemm_stages_b = value;
+    else if (!strcmp(name, "gemm_stages_b")) c->opt_gemm_stages_b = std::max(-1, std::min(value, kGemmMaxStagesB));
     else if (!strcmp(name, "gemm_no_unit")) c->opt_gemm_no_unit = value;
     else if (!strcmp(name, "gemm_keep")) c->opt_gemm_keep = value;
     else if (!strcmp(name, "gemm_no_pair")) c->opt_gemm_no_pair = value;
