@@ -257,6 +257,26 @@ def test_gemm_path_parity(lib, Q, k):
     dev.close()
 
 
+def test_gemm_pair_form_ring_geometries(lib):
+    """K2's CTA-pair form with every operand-ring layout: split rings (query-chunk buffers : corpus buffers = 4:5, the default;
+    3:6; 2:7) and the single ring of combined stages (gemm_stages_b = 0) return the oracle's consecutive searches alike."""
+    n, Q, k = 20_000, 160, 20
+    x, q = synth.unit_rows(n, 768, seed=977, n_queries=Q)
+    xb = synth.bf16_round(x)
+    ora = OracleCollection(768)
+    ora.upsert_rows_f32(0, xb, [None] * n)
+    dev = _dev("rings", 768, storage="bf16")
+    dev.upsert(xb)
+    for stages, stages_b in ((0, -1), (4, 0), (3, 6), (2, 7), (4, 5)):
+        dev.set_option("gemm_stages", stages)
+        dev.set_option("gemm_stages_b", stages_b)
+        res = dev.search(q.astype(np.float64), k)
+        assert dev.last_timing()["kernel"] == "gemm"
+        for i in range(Q):
+            _assert_same(res, i, *ora.search_topk_rows(q[i].astype(np.float64), k), REL_BF16)
+    dev.close()
+
+
 @pytest.mark.parametrize("Q,k,dim", [(9, 10, 768), (130, 50, 1536), (64, 100, 100)])
 def test_gemm_path_tf32_on_f32_storage(lib, Q, k, dim):
     """K2 over an fp32 shard (tcgen05 kind::tf32 reads the stored fp32 rows): same ids as the oracle, scores within 1e-5."""
