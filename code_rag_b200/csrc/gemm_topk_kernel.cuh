@@ -95,7 +95,8 @@ struct GemmParams {
     uint32_t unit_rows;          // every stored row has | ||row|| - 1 | <= 2^-9: clean tiles skip the 1/||row|| scaling
     uint32_t dbg_mode;           // profiling aid: bit0 skip the epilogue's scoring, bit1 skip the MMA issue, bit2 skip tcgen05.ld,
                                  // bit3 (pair form) stop re-loading the query chunks after the first pipeline fill, bit4 no loads at all
-                                 // after the first fill (MMA + epilogue hand-off alone)
+                                 // after the first fill (MMA + epilogue hand-off alone); bits 3 and 4 act on the combined ring only
+                                 // (n_stages_b = 0)
 };
 
 // shared memory: [stages][lists 8 warps * 16 keys * 32 lanes * 8][score columns 8 * 32 * 32 * 4][thr 128*4][inv 8*128*4][barriers]
